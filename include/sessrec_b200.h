@@ -1,0 +1,222 @@
+/* sessrec_b200 — C ABI of the B200-native session-recommendation training path.
+ *
+ * Drop-in boundary for the per-batch hot path of SpaceLearner/SessionRec-pytorch
+ * (`src/models/{srgnn,niser,msgifsr}.py` forward / `nll_loss` / autograd backward).  The reference has no
+ * FFI of its own: its boundary is the `nn.Module.forward(batched_graph) -> (B, V) log-probs` contract
+ * consumed by `src/utils/train.py:94-101`.  Each entry point below replaces the library kernels the
+ * reference reaches for one stage of that forward/backward (file:line given per function).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; the caller owns all memory;
+ *   - floating tensors are fp32 row-major, indices are int32 (the Python boundary converts from int64);
+ *   - `stream` is a `cudaStream_t` (passed as void*); calls only enqueue work, they never synchronise;
+ *   - return value: SRK_OK or a negative error code, message via srk_last_error() (thread-local);
+ *   - d (embedding dim) must be a multiple of 4 and <= 1024; GAT heads are fixed to 8 like the reference.
+ */
+#ifndef SESSREC_B200_H
+#define SESSREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRK_OK 0
+#define SRK_ERR_INVALID (-1)
+#define SRK_ERR_CUDA (-2)
+#define SRK_ERR_UNSUPPORTED (-3)
+
+#define SRK_HEADS 8
+#define SRK_MAX_GAT_INST 8
+
+/* row-normalisation modes */
+#define SRK_NORM_NONE 0
+#define SRK_NORM_NISER 1   /* x / (||x|| + 1e-12) then x / ||x||   (niser.py:134-135,141-142) */
+#define SRK_NORM_L2 2      /* F.normalize: x / max(||x||, 1e-12)    (msgifsr.py:252-253)        */
+#define SRK_NORM_EPS 3     /* x / (||x|| + 1e-12)                   (niser.py:147-151)          */
+
+/* dropout sites (shared with oracle/models.py) */
+#define SRK_SITE_EMBED 0x100
+#define SRK_SITE_READOUT 0x200
+#define SRK_SITE_GGNN 0x300
+#define SRK_SITE_GAT_SRC 0x1000
+#define SRK_SITE_GAT_DST 0x1001
+#define SRK_SITE_GAT_ATTN 0x1002
+
+typedef struct srk_dropout {
+  float p;        /* 0 disables */
+  uint32_t site;  /* SRK_SITE_* (+ offset) */
+  uint64_t seed;
+} srk_dropout;
+
+const char* srk_last_error(void);
+int srk_version(void);
+
+/* ---- dense building block -------------------------------------------------------------------------
+ * C[rc(m), n] (op)= alpha * sum_k A[ra(m)*sa_m + k*sa_k] * B[rb(k)*sb_k + n*sb_n] (+ bias[n]).
+ * Replaces the cuBLAS sgemm behind every nn.Linear / `@` on the path (srgnn.py:42-45,80-81,143;
+ * gatconv.py:273-274; msgifsr.py:139-140,271).  split_k <= 0 picks a split automatically. */
+int srk_gemm(int M, int N, int K, const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,
+             long long sb_n, float* C, long long ldc, const int* a_idx, const int* b_idx, const int* c_idx,
+             const float* bias, float alpha, int accumulate, int split_k, void* stream);
+
+/* ---- item-embedding gather / scatter-add (K1 / K8) -------------------------------------------------
+ * Forward: X[i] = norm_mode(dropout(E[iid[i]])), i < P.  Replaces `self.embedding(iid)` + feat_drop +
+ * normalisation (srgnn.py:133; niser.py:133-135,141-142; msgifsr.py:247-253).  rnorm[i] receives the L2
+ * norm of the dropped row (needed by backward).  x_first (optional, NISER only) receives the
+ * once-normalised rows that feed the GGNN layers (niser.py:136). */
+int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d, int norm_mode, const srk_dropout* drop,
+                         float* X, float* rnorm, float* x_first, void* stream);
+/* Backward: dE[u] += sum over the occurrences i of item u of d(dropped row i), deterministic: `perm`
+ * lists positions sorted by item id, uoff[U+1] delimits each distinct item, uid[U] is its id.  Replaces
+ * `embedding_dense_backward` (autograd of srgnn.py:133). dX_first may be NULL. */
+int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid, int U,
+                          int d, int norm_mode, const srk_dropout* drop, const float* rnorm, const float* dX,
+                          const float* dX_first, float* dE, void* stream);
+
+/* ---- catalog pre-pass (K6a) -------------------------------------------------------------------------
+ * mode SRK_NORM_L2 (MSGIFSR): renormalise IN PLACE every row of E whose norm exceeds max_norm (> 0) by
+ * max_norm / (norm + 1e-7) (`nn.Embedding(max_norm=1)`, msgifsr.py:162,276), then Ehat = F.normalize(E)
+ * (msgifsr.py:278-279).  mode SRK_NORM_EPS (NISER): Ehat = E / (||E|| + 1e-12) (niser.py:149-151).
+ * enorm[V] receives the (post-renorm) row norms. */
+int srk_catalog_prep_fwd(float* E, int V, int d, int norm_mode, float max_norm, float* Ehat, float* enorm,
+                         void* stream);
+int srk_catalog_prep_bwd(const float* E, const float* Ehat, const float* enorm, const float* dEhat, int V, int d,
+                         int norm_mode, float* dE, void* stream);
+/* In-place max_norm renorm of the rows touched by a gather (msgifsr.py:247); duplicates are safe. */
+int srk_renorm_rows(float* E, const int* uid, int U, int d, float max_norm, void* stream);
+
+/* ---- row normalisation -------------------------------------------------------------------------------
+ * Y = norm_mode(X) row-wise over [R, d] (ldx/ldy row strides); rnorm[R] keeps ||x||. */
+int srk_rownorm_fwd(const float* X, long long ldx, int R, int d, int norm_mode, float* Y, long long ldy, float* rnorm,
+                    void* stream);
+int srk_rownorm_bwd(const float* X, long long ldx, const float* Y, long long ldy, const float* rnorm, const float* dY,
+                    long long lddy, int R, int d, int norm_mode, float* dX, long long lddx, int accumulate,
+                    void* stream);
+
+/* ---- elementwise helpers -------------------------------------------------------------------------------
+ * Y = dropout(X) over n elements (flat index = element index); accumulate: Y += dropout_mask * X. */
+int srk_dropout_apply(const float* X, float* Y, long long n, const srk_dropout* drop, int accumulate, void* stream);
+int srk_fill(float* X, long long n, float value, void* stream);
+int srk_gather_rows(const float* X, const int* idx, int R, int d, float* Y, long long ldy, void* stream);
+int srk_scatter_add_rows(const float* X, long long ldx, const int* idx, int R, int d, float* Y, void* stream);
+int srk_colsum(const float* X, long long ldx, int R, int d, float* out, int accumulate, void* stream);
+
+/* ---- attention readout (K5) ------------------------------------------------------------------------------
+ * Rows F[R, d] are grouped in B contiguous segments seg[B+1]; u = F Wu^T (+bu) [R, d] and v [B, d] are
+ * computed by the caller with srk_gemm.  e_i = <we, sigmoid(u_i + v_b)>, alpha = segment softmax,
+ * g_b = sum alpha_i F_i.  Writes sr_in[b] = [F[last_b] | g_b] (row stride 2d), e[R] and the per-segment
+ * softmax statistics ms[B, 2] = (max, sum); with_last == 0 leaves the first half of sr_in to the caller.  Replaces srgnn.py:82-86 / msgifsr.py:141-146 (+ the concat
+ * at srgnn.py:141-142, msgifsr.py:269-270). last[B] = row index of each segment's "last" node. */
+int srk_readout_fwd(const float* F, const float* u, const float* v, const float* we, const int* seg,
+                    const int* last, int B, int d, int with_last, float* e, float* ms, float* sr_in, void* stream);
+/* Backward: given d sr_in [B, 2d], overwrites u with du and v with dv IN PLACE, writes dF[R, d] = alpha_i *
+ * dg_b, adds into dwe[d]. The caller finishes with GEMMs (dF += du Wu, dWu += du^T F, ...). */
+int srk_readout_bwd(const float* F, float* u, float* v, const float* we, const int* seg, const int* last,
+                    const float* e, const float* ms, const float* sr_in, const float* dsr_in, int B, int d, int with_last,
+                    float* dF, float* dwe, void* stream);
+
+/* ---- scoring head + cross-entropy (K6 / K7 elementwise parts) ----------------------------------------------
+ * Z[B, V] (row stride ldz >= V) holds scale * sr Ehat^T (srk_gemm or the tcgen05 kernel).  Row kernel: lse[b] = logsumexp(Z[b]),
+ * nll[b] = lse[b] - Z[b, label[b]] (skipped when labels == NULL); write_logp != 0 rewrites Z in place to log-probabilities
+ * (srgnn.py:146-147, niser.py:152-156, msgifsr.py:308-309,321; nll_loss at train.py:99). */
+int srk_ce_rows_fwd(float* Z, long long ldz, const int* labels, int B, int V, int write_logp, float* lse, float* nll,
+                    void* stream);
+/* loss = mean(nll) (deterministic single-block reduction). */
+int srk_mean(const float* x, int n, float* out, void* stream);
+/* Fused-loss backward: Z <- dZ = gscale[0] * scale * (exp(Z - lse) - onehot) / B in place (Z = logits). */
+int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale, float scale,
+                    int B, int V, int z_is_logp, void* stream);
+/* Compat backward from an arbitrary upstream gradient G[B, V] of the log-probs LP:
+ * dZ = scale * (G - exp(LP) * rowsum(G)), written into DZ (may alias G). */
+int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V, float* DZ,
+                 long long lddz, void* stream);
+
+/* ---- GGNN layer (K2 / K3) ---------------------------------------------------------------------------------
+ * Weighted-mean aggregation over in-edges and out-edges: NN[v] = [ sum_in w x[u] / sum_in w | sum_out w x[t] /
+ * sum_out w ] (row stride 2d; 0 where a node has no such edge).  CSR by destination (in_*) and by source
+ * (out_*), per-edge weights indexed by edge id.  Replaces the DGL UDF degree-bucketing update_all on the graph
+ * and its reverse (srgnn.py:21-29,37-41). */
+int srk_ggnn_aggregate_fwd(const float* X, int N, int d, const int* in_ptr, const int* in_src, const int* in_eid,
+                           const int* out_ptr, const int* out_dst, const int* out_eid, const float* w, float* NN,
+                           float* wsum, void* stream);
+/* dX[u] (+)= sum_out (w/W_in[v]) dNN1[v] + sum_in (w/W_out[t]) dNN2[t]. */
+int srk_ggnn_aggregate_bwd(const float* dNN, int N, int d, const int* in_ptr, const int* in_src, const int* in_eid,
+                           const int* out_ptr, const int* out_dst, const int* out_eid, const float* w,
+                           const float* wsum, float* dX, int accumulate, void* stream);
+/* GRUCell pointwise part (torch gate order r, z, n): gi[N, 3d], gh[N, 3d] (biases included), h[N, d] ->
+ * hnew[N, d]; saves nothing (backward recomputes the gates from gi/gh). srgnn.py:45. */
+int srk_gru_pointwise_fwd(const float* gi, const float* gh, const float* h, int N, int d, float* hnew, void* stream);
+/* dgi, dgh overwrite gi, gh IN PLACE; dh (+)= direct path z * dhnew. */
+int srk_gru_pointwise_bwd(float* gi, float* gh, const float* h, const float* dhnew, int N, int d, float* dh,
+                          int accumulate, void* stream);
+
+/* ---- GAT / MSHGNN layer (K4) ----------------------------------------------------------------------------------
+ * One "instance" = one relation of the heterograph in one direction (conv1 on the graph, conv2 on its reverse)
+ * feeding destination nodes of one node type. Zel[N_src, 8d+8] = x'_src [W ; wl]^T (columns 8d..8d+7 are the
+ * per-head source scores el), er[N_dst, 8] = x'_dst wr^T. */
+typedef struct srk_gat_inst {
+  const int* in_ptr;    /* [N_dst+1] CSR by destination (for this direction) */
+  const int* in_src;    /* [M] source node of each CSR slot */
+  const int* in_eid;    /* [M] edge id of each CSR slot (indexes att / dedge) */
+  const int* out_ptr;   /* [N_src+1] CSR by source */
+  const int* out_dst;   /* [M] */
+  const int* out_eid;   /* [M] */
+  const float* Zel;     /* [N_src, 8d+8] */
+  const float* er;      /* [N_dst, 8] */
+  const float* bias;    /* [8d] */
+  const float* xdst;    /* [N_dst, d] residual input (dropped destination copy) */
+  float* att;           /* [M, 8] attention after softmax, before attn_drop */
+  float* dedge;         /* [M, 8] backward: d(pre-LeakyReLU score) */
+  float* der;           /* [N_dst, 8] backward */
+  float* dZel;          /* [N_src, 8d+8] backward */
+  int n_src, n_dst, n_edges;
+  uint32_t attn_site;   /* dropout site of attn_drop for this instance */
+} srk_gat_inst;
+
+/* wl[h, :] = sum_j attn_l[h, j] W[h*d + j, :], wr likewise: Waug[8d+8, d] = [W ; wl], wr[8, d]. (gatconv.py:285-286
+ * reassociated so that el/er come out of the same GEMM as the projection.) */
+int srk_gat_prep(const float* W, const float* attn_l, const float* attn_r, int d, float* Waug, float* wr, void* stream);
+/* dW += dWaug[:8d] + attn_l (x) dwl + attn_r (x) dwr ; dattn_l[h, j] += <W[h*d+j], dwl[h]> ; same for r. */
+int srk_gat_prep_bwd(const float* W, const float* attn_l, const float* attn_r, const float* dWaug, const float* dwr,
+                     int d, float* dW, float* dattn_l, float* dattn_r, void* stream);
+/* Per destination node of one type: sum over instances of (edge-softmax attention aggregation + residual +
+ * bias), max over the 8 heads, + mean of the session's input rows (segmean[B, d], node2seg[N]); optionally
+ * L2-normalise.  Hpre = un-normalised result (NULL allowed when normalize != 0 is the only consumer), amax[N, d]
+ * = winning head.  Replaces gatconv.py:294-311 + msgifsr.py:74-90 (+ 260-263 when normalize). n_inst == 0:
+ * H = segmean broadcast (msgifsr.py:78-83 fallback). */
+int srk_gat_aggregate_fwd(const srk_gat_inst* inst_host, int n_inst, int N, int d, const float* segmean,
+                          const int* node2seg, const srk_dropout* attn_drop, int normalize, float* H, float* rnorm,
+                          uint8_t* amax, void* stream);
+/* Backward part 1 (per destination node): dH -> (normalise bwd) -> dHpre[N, d]; per instance writes dedge, der. */
+int srk_gat_aggregate_bwd_dst(const srk_gat_inst* inst_host, int n_inst, int N, int d, const srk_dropout* attn_drop,
+                              int normalize, const float* H, const float* rnorm, const uint8_t* amax,
+                              const float* dH, float* dHpre, void* stream);
+/* Backward part 2 (per source node of one instance): dZel[u] = [ sum_out att' dO[v] | sum_out dedge ]. */
+int srk_gat_aggregate_bwd_src(const srk_gat_inst* inst_host, int d, const srk_dropout* attn_drop, const float* dHpre,
+                              const uint8_t* amax, void* stream);
+/* dbias[h, j] += sum_v [amax[v, j] == h] dHpre[v, j]. */
+int srk_gat_bias_bwd(const float* dHpre, const uint8_t* amax, int N, int d, float* dbias, void* stream);
+/* Segment mean over contiguous segments and its backward (msgifsr.py:86-87). */
+int srk_segmean_fwd(const float* X, const int* seg, int B, int d, float* mean, void* stream);
+int srk_segmean_bwd(const float* dHpre, const int* seg, int B, int d, float* dX, int accumulate, void* stream);
+
+/* ---- optimizer (next-row: utils/train.py:70-74, torch.optim.Adam with L2-in-grad) ------------------------------
+ * Flat buffers; decay[i] per element group is given by seg_off[S+1] / seg_decay[S]. step is 1-based. */
+int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                  const long long* seg_off, const float* seg_decay, int n_seg, float lr, float beta1, float beta2,
+                  float eps, int step, void* stream);
+
+/* ---- native batch builder (host; next-row: utils/data/collate.py:61-85,87-217,219-256) ---------------------------
+ * Sessions are given as a flat item array + offsets. kind 0 = session graph (weights, self-loop rule), kind 1 =
+ * ccs heterograph of the given order. Two calls: srk_batch_size() returns the number of int32 words needed,
+ * srk_batch_build() fills `out_host` (layout documented in DESIGN.md / batch.py) . */
+long long srk_batch_size(const int* items_host, const int* offs_host, int B, int kind, int order);
+long long srk_batch_build(const int* items_host, const int* offs_host, const int* labels_host, int B, int kind,
+                          int order, int* out_host, long long out_words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SESSREC_B200_H */

@@ -1,0 +1,105 @@
+// Shared device/host helpers for the sm_100a session-rec kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sessrec_b200.h"
+
+#define SRK_WARP 32
+#define SRK_FULL 0xffffffffu
+
+void srk_set_error(const char* fmt, ...);
+
+#define SRK_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      srk_set_error(__VA_ARGS__);              \
+      return SRK_ERR_INVALID;                  \
+    }                                          \
+  } while (0)
+
+#define SRK_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      srk_set_error("%s:%d CUDA error %s (%s)", __FILE__, __LINE__, cudaGetErrorName(e__), \
+                    cudaGetErrorString(e__));                                            \
+      return SRK_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define SRK_LAUNCH_CHECK() SRK_CUDA(cudaGetLastError())
+
+#define SRK_TRY(expr)               \
+  do {                              \
+    int r__ = (expr);               \
+    if (r__ != SRK_OK) return r__;  \
+  } while (0)
+
+static inline int srk_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SRK_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(SRK_FULL, v, o));
+  return v;
+}
+
+// Counter-based dropout: 24-bit uniform from a splitmix64 finaliser of (seed, site, flat index).
+// Restated bit-for-bit in oracle/models.py::counter_uniform24 so that tests can inject the same masks.
+__device__ __forceinline__ uint32_t srk_rand24(uint64_t seed, uint32_t site, uint64_t idx) {
+  uint64_t x = seed + 0x9E3779B97F4A7C15ull * (((uint64_t)site << 40) + idx + 1ull);
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 40);
+}
+
+struct DropCfg {
+  uint64_t seed;
+  uint32_t site;
+  uint32_t thresh;  // keep iff rand24 >= thresh; 0 disables dropout
+  float scale;      // 1 / (1 - p)
+};
+
+static inline DropCfg make_drop(const srk_dropout* d, uint32_t site_offset = 0) {
+  DropCfg c;
+  c.seed = d ? d->seed : 0;
+  c.site = (d ? d->site : 0) + site_offset;
+  float p = d ? d->p : 0.f;
+  c.thresh = (p > 0.f) ? (uint32_t)floor((double)p * 16777216.0) : 0u;
+  c.scale = (p > 0.f) ? (float)(1.0 / (1.0 - (double)p)) : 1.f;
+  return c;
+}
+
+__device__ __forceinline__ float drop_mul(const DropCfg& c, uint64_t idx) {
+  if (c.thresh == 0u) return 1.f;
+  return srk_rand24(c.seed, c.site, idx) >= c.thresh ? c.scale : 0.f;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// internal launchers shared between translation units -------------------------------------------------
+struct GemmArgs {
+  int M, N, K;
+  const float* A; long long sa_m, sa_k;   // element (m, k) at A[row(m or k) ...]; see gemm.cu
+  const float* B; long long sb_k, sb_n;
+  float* C; long long ldc;
+  const int* a_idx;   // optional indirection on A's M index
+  const int* b_idx;   // optional indirection on B's K index (only for sb_n == 1 layouts)
+  const int* c_idx;   // optional indirection on C's row index
+  const float* bias;  // optional [N], added when the split index is 0
+  float alpha;
+  int accumulate;     // 0: C = result, 1: C += result
+  int split_k;        // >= 1; > 1 requires accumulate = 1 (atomicAdd epilogue)
+};
+int srk_gemm_launch(const GemmArgs& g, cudaStream_t st);
+int srk_pick_split_k(int M, int N, int K);

@@ -1,0 +1,237 @@
+// K1 / K8 / K6a: item-embedding gather (+dropout +row normalisation), deterministic scatter-add of the
+// embedding gradient, catalog pre-pass (max_norm renorm + row normalisation) and generic row normalisation.
+// All kernels are warp-per-row with 128-bit coalesced accesses (rowops.cuh); HBM/L2-bandwidth bound.
+#include "rowops.cuh"
+
+namespace {
+
+constexpr int ROW_THREADS = 256;  // 8 warps (rows) per CTA
+
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) gather_fwd_kernel(const float* __restrict__ E, const int* __restrict__ iid,
+                                                                 int P, int d, int mode, DropCfg dc,
+                                                                 float* __restrict__ X, float* __restrict__ rnorm,
+                                                                 float* __restrict__ x_first) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < P; i += warps) {
+    RowVec<NC> x, y;
+    row_load(x, E + (long long)iid[i] * d, d, lane);
+    row_dropout(x, dc, i, d, lane);
+    float n;
+    if (mode == SRK_NORM_NISER && x_first) {
+      n = sqrtf(row_dot(x, x));
+      y = x;
+      row_scale(y, 1.f / (n + 1e-12f));
+      row_store(y, x_first + (long long)i * d, d, lane);
+      float n1 = sqrtf(row_dot(y, y));
+      row_scale(y, 1.f / n1);
+    } else if (mode == SRK_NORM_NONE) {
+      n = 0.f;
+      y = x;
+    } else {
+      n = row_normalize(x, y, mode);
+    }
+    row_store(y, X + (long long)i * d, d, lane);
+    if (rnorm && lane == 0) rnorm[i] = n;
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* __restrict__ E, const int* __restrict__ perm,
+                                                                  const int* __restrict__ uoff, const int* __restrict__ uid,
+                                                                  int U, int d, int mode, DropCfg dc,
+                                                                  const float* __restrict__ rnorm,
+                                                                  const float* __restrict__ dX,
+                                                                  const float* __restrict__ dX_first,
+                                                                  float* __restrict__ dE) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < U; u += warps) {
+    const int item = uid[u];
+    RowVec<NC> erow, acc;
+    row_load(erow, E + (long long)item * d, d, lane);
+    row_zero(acc);
+    for (int j = uoff[u]; j < uoff[u + 1]; ++j) {
+      const int i = perm[j];
+      RowVec<NC> x = erow, y, dy, dx;
+      row_dropout(x, dc, i, d, lane);
+      row_load(dy, dX + (long long)i * d, d, lane);
+      if (mode == SRK_NORM_NONE) {
+        dx = dy;
+      } else {
+        const float n = rnorm[i];
+        y = x;
+        if (mode == SRK_NORM_L2) row_scale(y, 1.f / fmaxf(n, 1e-12f));
+        else if (mode == SRK_NORM_EPS) row_scale(y, 1.f / (n + 1e-12f));
+        else row_scale(y, n > 0.f ? 1.f / n : 0.f);     // NISER: y2 = x / ||x|| up to rounding
+        if (mode == SRK_NORM_NISER && dX_first) {
+          RowVec<NC> d1;
+          row_load(d1, dX_first + (long long)i * d, d, lane);
+          row_normalize_bwd(x, y, n, mode, dy, &d1, dx);
+        } else {
+          row_normalize_bwd<NC>(x, y, n, mode, dy, nullptr, dx);
+        }
+      }
+      row_dropout(dx, dc, i, d, lane);
+      row_axpy(acc, 1.f, dx);
+    }
+    row_add_store(acc, dE + (long long)item * d, d, lane);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) renorm_rows_kernel(float* __restrict__ E, const int* __restrict__ uid, int U,
+                                                                  int d, float max_norm) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < U; u += warps) {
+    float* p = E + (long long)(uid ? uid[u] : u) * d;
+    RowVec<NC> x;
+    row_load(x, p, d, lane);
+    float n = sqrtf(row_dot(x, x));
+    if (n > max_norm) {
+      row_scale(x, (float)((double)max_norm / ((double)n + 1e-7)));
+      row_store(x, p, d, lane);
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) catalog_prep_fwd_kernel(float* __restrict__ E, int V, int d, int mode,
+                                                                       float max_norm, float* __restrict__ Ehat,
+                                                                       float* __restrict__ enorm) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
+    float* p = E + (long long)v * d;
+    RowVec<NC> x, y;
+    row_load(x, p, d, lane);
+    if (max_norm > 0.f) {
+      float n0 = sqrtf(row_dot(x, x));
+      if (n0 > max_norm) {
+        row_scale(x, (float)((double)max_norm / ((double)n0 + 1e-7)));
+        row_store(x, p, d, lane);
+      }
+    }
+    float n = row_normalize(x, y, mode);
+    row_store(y, Ehat + (long long)v * d, d, lane);
+    if (lane == 0) enorm[v] = n;
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) rownorm_fwd_kernel(const float* __restrict__ X, long long ldx, int R, int d,
+                                                                  int mode, float* __restrict__ Y, long long ldy,
+                                                                  float* __restrict__ rnorm) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
+    RowVec<NC> x, y;
+    row_load(x, X + r * ldx, d, lane);
+    float n = row_normalize(x, y, mode);
+    row_store(y, Y + r * ldy, d, lane);
+    if (rnorm && lane == 0) rnorm[r] = n;
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) rownorm_bwd_kernel(const float* __restrict__ X, long long ldx,
+                                                                  const float* __restrict__ Y, long long ldy,
+                                                                  const float* __restrict__ rnorm,
+                                                                  const float* __restrict__ dY, long long lddy, int R,
+                                                                  int d, int mode, float* __restrict__ dX,
+                                                                  long long lddx, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
+    RowVec<NC> x, y, dy, dx;
+    row_load(x, X + r * ldx, d, lane);
+    row_load(y, Y + r * ldy, d, lane);
+    row_load(dy, dY + r * lddy, d, lane);
+    row_normalize_bwd<NC>(x, y, rnorm[r], mode, dy, nullptr, dx);
+    if (accumulate) row_add_store(dx, dX + r * lddx, d, lane);
+    else row_store(dx, dX + r * lddx, d, lane);
+  }
+}
+
+inline int row_grid(long long rows) {
+  long long g = (rows + 7) / 8;
+  if (g < 1) g = 1;
+  if (g > 148LL * 64) g = 148LL * 64;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d, int norm_mode, const srk_dropout* drop,
+                                    float* X, float* rnorm, float* x_first, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (P <= 0) return SRK_OK;
+  SRK_REQUIRE(norm_mode == SRK_NORM_NONE || rnorm, "embed_gather_fwd: rnorm is required when normalising");
+  DropCfg dc = make_drop(drop);
+  SRK_DISPATCH_NC(d, (gather_fwd_kernel<NC><<<row_grid(P), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                         E, iid, P, d, norm_mode, dc, X, rnorm, x_first)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid,
+                                     int U, int d, int norm_mode, const srk_dropout* drop, const float* rnorm,
+                                     const float* dX, const float* dX_first, float* dE, void* stream) {
+  (void)iid;
+  SRK_TRY(srk_check_dim(d));
+  if (U <= 0) return SRK_OK;
+  DropCfg dc = make_drop(drop);
+  SRK_DISPATCH_NC(d, (scatter_bwd_kernel<NC><<<row_grid(U), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                         E, perm, uoff, uid, U, d, norm_mode, dc, rnorm, dX, dX_first, dE)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_renorm_rows(float* E, const int* uid, int U, int d, float max_norm, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (U <= 0) return SRK_OK;
+  SRK_DISPATCH_NC(d, (renorm_rows_kernel<NC><<<row_grid(U), ROW_THREADS, 0, (cudaStream_t)stream>>>(E, uid, U, d,
+                                                                                                      max_norm)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_catalog_prep_fwd(float* E, int V, int d, int norm_mode, float max_norm, float* Ehat, float* enorm,
+                                    void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  SRK_REQUIRE(norm_mode == SRK_NORM_L2 || norm_mode == SRK_NORM_EPS, "catalog_prep: norm_mode must be L2 or EPS");
+  SRK_DISPATCH_NC(d, (catalog_prep_fwd_kernel<NC><<<row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                         E, V, d, norm_mode, max_norm, Ehat, enorm)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_catalog_prep_bwd(const float* E, const float* Ehat, const float* enorm, const float* dEhat, int V,
+                                    int d, int norm_mode, float* dE, void* stream) {
+  return srk_rownorm_bwd(E, d, Ehat, d, enorm, dEhat, d, V, d, norm_mode, dE, d, 1, stream);
+}
+
+extern "C" int srk_rownorm_fwd(const float* X, long long ldx, int R, int d, int norm_mode, float* Y, long long ldy,
+                               float* rnorm, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (R <= 0) return SRK_OK;
+  SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "rownorm: row strides must be multiples of 4");
+  SRK_DISPATCH_NC(d, (rownorm_fwd_kernel<NC><<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(X, ldx, R, d, norm_mode,
+                                                                                                      Y, ldy, rnorm)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_rownorm_bwd(const float* X, long long ldx, const float* Y, long long ldy, const float* rnorm,
+                               const float* dY, long long lddy, int R, int d, int norm_mode, float* dX, long long lddx,
+                               int accumulate, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (R <= 0) return SRK_OK;
+  SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "rownorm: strides must be multiples of 4");
+  SRK_DISPATCH_NC(d, (rownorm_bwd_kernel<NC><<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                         X, ldx, Y, ldy, rnorm, dY, lddy, R, d, norm_mode, dX, lddx, accumulate)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}

@@ -1,0 +1,232 @@
+// Generic fp32 CUDA-core GEMM used for the small dense layers of the path (GAT fc, GGNN GRU, readout,
+// fc_sr) and as the exact-fp32 catalog GEMM (the tcgen05 3xTF32 kernel in score_umma.cu takes over the
+// catalog contraction when shapes allow).
+//
+//   C[m, n] (op)= alpha * sum_k A(m, k) * B(k, n)  (+ bias[n])
+//   A(m, k) = A[ra(m) * sa_m + k * sa_k],  ra(m) = a_idx ? a_idx[m] : m
+//   B(k, n) = B[rb(k) * sb_k + n * sb_n],  rb(k) = b_idx ? b_idx[k] : k
+//   C row m is written at C[rc(m) * ldc + n]
+//
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tile, register-staged prefetch, optional split-K with
+// an atomicAdd epilogue (accumulate mode only).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4, NT = 256;
+
+enum LoadMode { LM_SCALAR = 0, LM_KVEC = 1, LM_MVEC = 2, LM_KSCAL = 3, LM_MSCAL = 4 };
+
+struct Frag {
+  float v[4];
+};
+
+// Loads this thread's 4 elements of a (64 x 16) operand tile.  `outer` indexes the 64-wide dimension
+// (m for A, n for B), `k` the 16-deep one.  so/sk are the element strides, idx the optional indirection
+// (on `outer` when idx_on_outer, else on k).
+template <bool kIdxOnOuter>
+__device__ __forceinline__ void load_frag(Frag& f, const float* __restrict__ P, long long so, long long sk,
+                                          const int* __restrict__ idx, int mode, int o0, int k0, int O, int kEnd,
+                                          int tid) {
+  if (mode == LM_KVEC || mode == LM_KSCAL) {
+    int o = o0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+    f.v[0] = f.v[1] = f.v[2] = f.v[3] = 0.f;
+    if (o < O) {
+      long long ro = kIdxOnOuter && idx ? (long long)idx[o] : (long long)o;
+      const float* p = P + ro * so;
+      if (mode == LM_KVEC && k + 3 < kEnd && !(!kIdxOnOuter && idx)) {
+        float4 t = *reinterpret_cast<const float4*>(p + k);
+        f.v[0] = t.x; f.v[1] = t.y; f.v[2] = t.z; f.v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (k + j < kEnd) {
+            long long rk = (!kIdxOnOuter && idx) ? (long long)idx[k + j] : (long long)(k + j);
+            f.v[j] = p[rk * sk];
+          }
+      }
+    }
+  } else if (mode == LM_MVEC || mode == LM_MSCAL) {
+    int k = k0 + (tid >> 4), o = o0 + (tid & 15) * 4;
+    f.v[0] = f.v[1] = f.v[2] = f.v[3] = 0.f;
+    if (k < kEnd) {
+      long long rk = (!kIdxOnOuter && idx) ? (long long)idx[k] : (long long)k;
+      const float* p = P + rk * sk;
+      if (mode == LM_MVEC && o + 3 < O && !(kIdxOnOuter && idx)) {
+        float4 t = *reinterpret_cast<const float4*>(p + o);
+        f.v[0] = t.x; f.v[1] = t.y; f.v[2] = t.z; f.v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (o + j < O) {
+            long long ro = (kIdxOnOuter && idx) ? (long long)idx[o + j] : (long long)(o + j);
+            f.v[j] = p[ro * so];
+          }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int e = tid + j * NT;
+      int o = o0 + (e & 63), k = k0 + (e >> 6);
+      float v = 0.f;
+      if (o < O && k < kEnd) {
+        long long ro = (kIdxOnOuter && idx) ? (long long)idx[o] : (long long)o;
+        long long rk = (!kIdxOnOuter && idx) ? (long long)idx[k] : (long long)k;
+        v = P[ro * so + rk * sk];
+      }
+      f.v[j] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_frag(const Frag& f, float (*S)[BM + PAD], int mode, int tid) {
+  if (mode == LM_KVEC || mode == LM_KSCAL) {
+    int o = tid >> 2, k = (tid & 3) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[k + j][o] = f.v[j];
+  } else if (mode == LM_MVEC || mode == LM_MSCAL) {
+    int k = tid >> 4, o = (tid & 15) * 4;
+    *reinterpret_cast<float4*>(&S[k][o]) = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int e = tid + j * NT;
+      S[e >> 6][e & 63] = f.v[j];
+    }
+  }
+}
+
+struct GemmParams {
+  GemmArgs g;
+  int a_mode, b_mode, k_chunk;
+};
+
+__global__ void __launch_bounds__(NT) sgemm_kernel(const GemmParams p) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const GemmArgs& g = p.g;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kBeg = blockIdx.z * p.k_chunk;
+  const int kEnd = min(g.K, kBeg + p.k_chunk);
+  const int ty = tid >> 4, tx = tid & 15;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  Frag fa, fb;
+  if (kBeg < kEnd) {
+    load_frag<true>(fa, g.A, g.sa_m, g.sa_k, g.a_idx, p.a_mode, m0, kBeg, g.M, kEnd, tid);
+    load_frag<false>(fb, g.B, g.sb_n, g.sb_k, g.b_idx, p.b_mode, n0, kBeg, g.N, kEnd, tid);
+  }
+  for (int k0 = kBeg; k0 < kEnd; k0 += BK) {
+    store_frag(fa, As, p.a_mode, tid);
+    store_frag(fb, Bs, p.b_mode, tid);
+    __syncthreads();
+    if (k0 + BK < kEnd) {
+      load_frag<true>(fa, g.A, g.sa_m, g.sa_k, g.a_idx, p.a_mode, m0, k0 + BK, g.M, kEnd, tid);
+      load_frag<false>(fb, g.B, g.sb_n, g.sb_k, g.b_idx, p.b_mode, n0, k0 + BK, g.N, kEnd, tid);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const bool first_split = blockIdx.z == 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+    long long rc = g.c_idx ? (long long)g.c_idx[m] : (long long)m;
+    float* crow = g.C + rc * g.ldc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias && first_split) v += g.bias[n];
+      if (!g.accumulate)
+        crow[n] = v;
+      else if (gridDim.z > 1)
+        atomicAdd(crow + n, v);
+      else
+        crow[n] += v;
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int srk_pick_split_k(int M, int N, int K) {
+  long long tiles = (long long)srk_cdiv(M, BM) * srk_cdiv(N, BN);
+  if (tiles >= 444 || K <= 256) return 1;
+  long long want = (592 + tiles - 1) / tiles;
+  long long cap = K / 256 > 0 ? K / 256 : 1;
+  long long s = want < cap ? want : cap;
+  if (s > 128) s = 128;
+  return (int)(s < 1 ? 1 : s);
+}
+
+int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return SRK_OK;
+  SRK_REQUIRE(g.split_k >= 1, "gemm: split_k must be >= 1");
+  SRK_REQUIRE(g.split_k == 1 || g.accumulate, "gemm: split-K needs accumulate mode");
+  SRK_REQUIRE(srk_cdiv(g.M, BM) <= 65535, "gemm: M too large for grid.y");
+  if (g.K <= 0) {
+    SRK_REQUIRE(g.accumulate, "gemm: K == 0 with overwrite mode is not supported");
+    return SRK_OK;
+  }
+  GemmParams p;
+  p.g = g;
+  // operand A: outer = m
+  if (g.sa_k == 1)
+    p.a_mode = (g.sa_m % 4 == 0 && aligned16(g.A)) ? LM_KVEC : LM_KSCAL;
+  else if (g.sa_m == 1)
+    p.a_mode = (g.sa_k % 4 == 0 && aligned16(g.A) && !g.a_idx) ? LM_MVEC : LM_MSCAL;
+  else
+    p.a_mode = LM_SCALAR;
+  // operand B: outer = n
+  if (g.sb_k == 1)
+    p.b_mode = (g.sb_n % 4 == 0 && aligned16(g.B) && !g.b_idx) ? LM_KVEC : LM_KSCAL;
+  else if (g.sb_n == 1)
+    p.b_mode = (g.sb_k % 4 == 0 && aligned16(g.B)) ? LM_MVEC : LM_MSCAL;
+  else
+    p.b_mode = LM_SCALAR;
+  int S = g.split_k;
+  int ktiles = srk_cdiv(g.K, BK);
+  int per = srk_cdiv(ktiles, S);
+  p.k_chunk = per * BK;
+  S = srk_cdiv(g.K, p.k_chunk);
+  dim3 grid(srk_cdiv(g.N, BN), srk_cdiv(g.M, BM), S);
+  sgemm_kernel<<<grid, NT, 0, st>>>(p);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_gemm(int M, int N, int K, const float* A, long long sa_m, long long sa_k, const float* B,
+                        long long sb_k, long long sb_n, float* C, long long ldc, const int* a_idx, const int* b_idx,
+                        const int* c_idx, const float* bias, float alpha, int accumulate, int split_k, void* stream) {
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.sa_m = sa_m; g.sa_k = sa_k;
+  g.B = B; g.sb_k = sb_k; g.sb_n = sb_n;
+  g.C = C; g.ldc = ldc;
+  g.a_idx = a_idx; g.b_idx = b_idx; g.c_idx = c_idx;
+  g.bias = bias; g.alpha = alpha; g.accumulate = accumulate;
+  g.split_k = split_k > 0 ? split_k : (accumulate ? srk_pick_split_k(M, N, K) : 1);
+  return srk_gemm_launch(g, (cudaStream_t)stream);
+}

@@ -1,0 +1,198 @@
+// Error channel + small elementwise / reduction helpers of the path.
+#include <stdarg.h>
+
+#include "rowops.cuh"
+
+static thread_local char g_err[512] = "";
+
+void srk_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* srk_last_error(void) { return g_err; }
+extern "C" int srk_version(void) { return 100; }
+
+namespace {
+
+__global__ void dropout_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, long long n, DropCfg dc,
+                                     int accumulate) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = X[i] * drop_mul(dc, (uint64_t)i);
+    Y[i] = accumulate ? Y[i] + v : v;
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ X, long long n, float value) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) X[i] = value;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ X, const int* __restrict__ idx, int R,
+                                                          int d, float* __restrict__ Y, long long ldy) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
+    RowVec<NC> x;
+    row_load(x, X + (long long)idx[r] * d, d, lane);
+    row_store(x, Y + r * ldy, d, lane);
+  }
+}
+
+// Y[idx[r]] += X[r]; idx entries must be distinct (one "last" node per session).
+template <int NC>
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ X, long long ldx,
+                                                               const int* __restrict__ idx, int R, int d,
+                                                               float* __restrict__ Y) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
+    RowVec<NC> x;
+    row_load(x, X + r * ldx, d, lane);
+    row_add_store(x, Y + (long long)idx[r] * d, d, lane);
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, long long ldx, int R, int d,
+                                                     int rows_per_block, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  float s = 0.f;
+  if (j < d)
+    for (int r = r0 + ty; r < r1; r += 8) s += X[r * ldx + j];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < d) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][tx];
+    atomicAdd(out + j, s);
+  }
+}
+
+__global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[0] = s / (float)n;
+  }
+}
+
+// Fused multi-tensor Adam with torch.optim.Adam semantics (L2 term folded into the gradient, bias correction,
+// denom = sqrt(v) / sqrt(bias2) + eps) over one flat parameter buffer; per-segment weight decay.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n,
+                                                   const long long* __restrict__ seg_off, const float* __restrict__ seg_decay,
+                                                   int n_seg, float lr, float b1, float b2, float eps, float bc1,
+                                                   float bc2_sqrt) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int lo = 0, hi = n_seg - 1;           // segment of element i (seg_off ascending, seg_off[n_seg] == n)
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    float grad = g[i] + seg_decay[lo] * p[i];
+    float mi = b1 * m[i] + (1.f - b1) * grad;
+    float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+  }
+}
+
+inline int flat_grid(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > 148LL * 16) g = 148LL * 16;
+  return (int)g;
+}
+inline int row_grid(long long rows) {
+  long long g = (rows + 7) / 8;
+  if (g < 1) g = 1;
+  if (g > 148LL * 64) g = 148LL * 64;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int srk_dropout_apply(const float* X, float* Y, long long n, const srk_dropout* drop, int accumulate,
+                                 void* stream) {
+  if (n <= 0) return SRK_OK;
+  dropout_apply_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(X, Y, n, make_drop(drop), accumulate);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_fill(float* X, long long n, float value, void* stream) {
+  if (n <= 0) return SRK_OK;
+  fill_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(X, n, value);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_gather_rows(const float* X, const int* idx, int R, int d, float* Y, long long ldy, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (R <= 0) return SRK_OK;
+  SRK_REQUIRE(ldy % 4 == 0, "gather_rows: ldy must be a multiple of 4");
+  SRK_DISPATCH_NC(d, (gather_rows_kernel<NC><<<row_grid(R), 256, 0, (cudaStream_t)stream>>>(X, idx, R, d, Y, ldy)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_scatter_add_rows(const float* X, long long ldx, const int* idx, int R, int d, float* Y, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (R <= 0) return SRK_OK;
+  SRK_REQUIRE(ldx % 4 == 0, "scatter_add_rows: ldx must be a multiple of 4");
+  SRK_DISPATCH_NC(d, (scatter_add_rows_kernel<NC><<<row_grid(R), 256, 0, (cudaStream_t)stream>>>(X, ldx, idx, R, d, Y)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_colsum(const float* X, long long ldx, int R, int d, float* out, int accumulate, void* stream) {
+  if (d <= 0) return SRK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) SRK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * d, st));
+  if (R <= 0) return SRK_OK;
+  int by = srk_cdiv(R, 256);
+  if (by > 64) by = 64;
+  int rows_per_block = srk_cdiv(R, by);
+  dim3 grid(srk_cdiv(d, 32), by);
+  colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, R, d, rows_per_block, out);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_mean(const float* x, int n, float* out, void* stream) {
+  SRK_REQUIRE(n > 0, "mean: n must be positive");
+  mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                             const long long* seg_off, const float* seg_decay, int n_seg, float lr, float beta1,
+                             float beta2, float eps, int step, void* stream) {
+  if (n <= 0) return SRK_OK;
+  SRK_REQUIRE(n_seg >= 1 && step >= 1, "adam: need >= 1 segment and step >= 1");
+  float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  adam_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n,
+                                                                   seg_off, seg_decay,
+                                                                   n_seg, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}

@@ -1,0 +1,266 @@
+// K5 attention readout (warp per session, online segment softmax) and the row-wise parts of the scoring
+// head: log-sum-exp / NLL / log-prob rewrite and their backward.  HBM-bound streaming kernels.
+#include <float.h>
+
+#include "rowops.cuh"
+
+namespace {
+
+template <int NC>
+__device__ __forceinline__ float attn_score(const RowVec<NC>& u, const RowVec<NC>& v, const RowVec<NC>& we) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    s += we.v[c].x * sigmoidf_(u.v[c].x + v.v[c].x) + we.v[c].y * sigmoidf_(u.v[c].y + v.v[c].y) +
+         we.v[c].z * sigmoidf_(u.v[c].z + v.v[c].z) + we.v[c].w * sigmoidf_(u.v[c].w + v.v[c].w);
+  }
+  return warp_sum(s);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) readout_fwd_kernel(const float* __restrict__ F, const float* __restrict__ u,
+                                                          const float* __restrict__ v, const float* __restrict__ we,
+                                                          const int* __restrict__ seg, const int* __restrict__ last, int B,
+                                                          int d, int with_last, float* __restrict__ e,
+                                                          float* __restrict__ ms, float* __restrict__ sr_in) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  RowVec<NC> wev;
+  row_load(wev, we, d, lane);
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+    RowVec<NC> vb, acc;
+    row_load(vb, v + (long long)b * d, d, lane);
+    row_zero(acc);
+    float m = -FLT_MAX, s = 0.f;
+    for (int i = seg[b]; i < seg[b + 1]; ++i) {
+      RowVec<NC> ui, fi;
+      row_load(ui, u + (long long)i * d, d, lane);
+      row_load(fi, F + (long long)i * d, d, lane);
+      float ei = attn_score(ui, vb, wev);
+      if (lane == 0) e[i] = ei;
+      float mn = fmaxf(m, ei);
+      float corr = expf(m - mn), pi = expf(ei - mn);
+      s = s * corr + pi;
+      row_scale(acc, corr);
+      row_axpy(acc, pi, fi);
+      m = mn;
+    }
+    row_scale(acc, 1.f / s);
+    if (lane == 0) {
+      ms[2 * b] = m;
+      ms[2 * b + 1] = s;
+    }
+    if (with_last) {
+      RowVec<NC> fl;
+      row_load(fl, F + (long long)last[b] * d, d, lane);
+      row_store(fl, sr_in + (long long)b * 2 * d, d, lane);
+    }
+    row_store(acc, sr_in + (long long)b * 2 * d + d, d, lane);
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) readout_bwd_kernel(const float* __restrict__ F, float* __restrict__ u,
+                                                          float* __restrict__ v, const float* __restrict__ we,
+                                                          const int* __restrict__ seg, const int* __restrict__ last,
+                                                          const float* __restrict__ e, const float* __restrict__ ms,
+                                                          const float* __restrict__ sr_in,
+                                                          const float* __restrict__ dsr_in, int B, int d,
+                                                          int with_last, float* __restrict__ dF,
+                                                          float* __restrict__ dwe) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  RowVec<NC> wev, dwe_acc;
+  row_load(wev, we, d, lane);
+  row_zero(dwe_acc);
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+    RowVec<NC> vb, g, dg, dl, dv;
+    row_load(vb, v + (long long)b * d, d, lane);
+    row_load(g, sr_in + (long long)b * 2 * d + d, d, lane);
+    row_load(dl, dsr_in + (long long)b * 2 * d, d, lane);
+    row_load(dg, dsr_in + (long long)b * 2 * d + d, d, lane);
+    row_zero(dv);
+    const float t = row_dot(g, dg);
+    const float m = ms[2 * b], inv_s = 1.f / ms[2 * b + 1];
+    const int lb = with_last ? last[b] : -1;
+    for (int i = seg[b]; i < seg[b + 1]; ++i) {
+      RowVec<NC> ui, fi, du, df;
+      row_load(ui, u + (long long)i * d, d, lane);
+      row_load(fi, F + (long long)i * d, d, lane);
+      const float alpha = expf(e[i] - m) * inv_s;
+      const float de = alpha * (row_dot(fi, dg) - t);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float sx = sigmoidf_(ui.v[c].x + vb.v[c].x), sy = sigmoidf_(ui.v[c].y + vb.v[c].y);
+        float sz = sigmoidf_(ui.v[c].z + vb.v[c].z), sw = sigmoidf_(ui.v[c].w + vb.v[c].w);
+        dwe_acc.v[c].x = fmaf(de, sx, dwe_acc.v[c].x); dwe_acc.v[c].y = fmaf(de, sy, dwe_acc.v[c].y);
+        dwe_acc.v[c].z = fmaf(de, sz, dwe_acc.v[c].z); dwe_acc.v[c].w = fmaf(de, sw, dwe_acc.v[c].w);
+        du.v[c].x = de * wev.v[c].x * sx * (1.f - sx); du.v[c].y = de * wev.v[c].y * sy * (1.f - sy);
+        du.v[c].z = de * wev.v[c].z * sz * (1.f - sz); du.v[c].w = de * wev.v[c].w * sw * (1.f - sw);
+      }
+      row_axpy(dv, 1.f, du);
+      row_store(du, u + (long long)i * d, d, lane);
+      df = dg;
+      row_scale(df, alpha);
+      if (i == lb) row_axpy(df, 1.f, dl);
+      row_store(df, dF + (long long)i * d, d, lane);
+    }
+    row_store(dv, v + (long long)b * d, d, lane);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    int col = (c * 32 + lane) * 4;
+    if (col < d) {
+      atomicAdd(dwe + col, dwe_acc.v[c].x); atomicAdd(dwe + col + 1, dwe_acc.v[c].y);
+      atomicAdd(dwe + col + 2, dwe_acc.v[c].z); atomicAdd(dwe + col + 3, dwe_acc.v[c].w);
+    }
+  }
+}
+
+// ---- scoring head row kernels ------------------------------------------------------------------------
+
+struct MS {
+  float m, s;
+};
+__device__ __forceinline__ MS ms_combine(MS a, MS b) {
+  MS r;
+  r.m = fmaxf(a.m, b.m);
+  r.s = a.s * expf(a.m - r.m) + b.s * expf(b.m - r.m);
+  return r;
+}
+
+__device__ __forceinline__ MS block_lse(const float* __restrict__ z, int V, MS* red) {
+  MS t;
+  t.m = -FLT_MAX;
+  t.s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    float x = z[j];
+    if (x > t.m) {
+      t.s = t.s * expf(t.m - x) + 1.f;
+      t.m = x;
+    } else {
+      t.s += expf(x - t.m);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MS other;
+    other.m = __shfl_xor_sync(SRK_FULL, t.m, o);
+    other.s = __shfl_xor_sync(SRK_FULL, t.s, o);
+    t = ms_combine(t, other);
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  MS r = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = ms_combine(r, red[w]);
+  return r;
+}
+
+__global__ void __launch_bounds__(512) ce_rows_fwd_kernel(float* __restrict__ Z, long long ldz, const int* __restrict__ labels,
+                                                          int V, int write_logp, float* __restrict__ lse,
+                                                          float* __restrict__ nll) {
+  __shared__ MS red[16];
+  float* z = Z + (long long)blockIdx.x * ldz;
+  MS r = block_lse(z, V, red);
+  const float l = r.m + logf(r.s);
+  if (threadIdx.x == 0) {
+    lse[blockIdx.x] = l;
+    if (labels) nll[blockIdx.x] = l - z[labels[blockIdx.x]];
+  }
+  if (write_logp) {
+    __syncthreads();   // thread 0 has read z[label] before anyone rewrites it
+    for (int j = threadIdx.x; j < V; j += blockDim.x) z[j] -= l;
+  }
+}
+
+__global__ void __launch_bounds__(512) ce_rows_bwd_kernel(float* __restrict__ Z, long long ldz, const int* __restrict__ labels,
+                                                          const float* __restrict__ lse, const float* __restrict__ gscale,
+                                                          float scale, int B, int V, int z_is_logp) {
+  float* z = Z + (long long)blockIdx.x * ldz;
+  const float l = z_is_logp ? 0.f : lse[blockIdx.x];
+  const float c = gscale[0] * scale / (float)B;
+  const int lab = labels[blockIdx.x];
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    float p = expf(z[j] - l);
+    z[j] = c * (p - (j == lab ? 1.f : 0.f));
+  }
+}
+
+__global__ void __launch_bounds__(512) logp_bwd_kernel(const float* __restrict__ LP, long long ldlp,
+                                                       const float* __restrict__ G, long long ldg, float scale, int V,
+                                                       float* __restrict__ DZ, long long lddz) {
+  __shared__ float red[16];
+  __shared__ float total;
+  const float* lp = LP + (long long)blockIdx.x * ldlp;
+  const float* g = G + (long long)blockIdx.x * ldg;
+  float* dz = DZ + (long long)blockIdx.x * lddz;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) s += g[j];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    total = t;
+  }
+  __syncthreads();
+  const float rs = total;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) dz[j] = scale * (g[j] - expf(lp[j]) * rs);
+}
+
+inline int row_grid(long long rows) {
+  long long g = (rows + 7) / 8;
+  if (g < 1) g = 1;
+  if (g > 148LL * 64) g = 148LL * 64;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int srk_readout_fwd(const float* F, const float* u, const float* v, const float* we, const int* seg,
+                               const int* last, int B, int d, int with_last, float* e, float* ms, float* sr_in,
+                               void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (B <= 0) return SRK_OK;
+  SRK_DISPATCH_NC(d, (readout_fwd_kernel<NC><<<row_grid(B), 256, 0, (cudaStream_t)stream>>>(F, u, v, we, seg, last, B, d,
+                                                                                            with_last, e, ms, sr_in)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_readout_bwd(const float* F, float* u, float* v, const float* we, const int* seg, const int* last,
+                               const float* e, const float* ms, const float* sr_in, const float* dsr_in, int B, int d,
+                               int with_last, float* dF, float* dwe, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (B <= 0) return SRK_OK;
+  SRK_DISPATCH_NC(d, (readout_bwd_kernel<NC><<<row_grid(B), 256, 0, (cudaStream_t)stream>>>(
+                         F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_ce_rows_fwd(float* Z, long long ldz, const int* labels, int B, int V, int write_logp, float* lse,
+                               float* nll, void* stream) {
+  if (B <= 0) return SRK_OK;
+  SRK_REQUIRE(V > 0, "ce_rows_fwd: empty catalog");
+  ce_rows_fwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, V, write_logp, lse, nll);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale,
+                               float scale, int B, int V, int z_is_logp, void* stream) {
+  if (B <= 0) return SRK_OK;
+  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V,
+                            float* DZ, long long lddz, void* stream) {
+  if (B <= 0) return SRK_OK;
+  logp_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(LP, ldlp, G, ldg, scale, V, DZ, lddz);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}

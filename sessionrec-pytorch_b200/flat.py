@@ -1,0 +1,50 @@
+"""Flat parameter storage: every nn.Parameter of a model becomes a view into one contiguous fp32 buffer (and its
+gradient a view into a twin buffer), so that the optimizer step is ONE fused kernel and the data-parallel
+gradient exchange ONE NCCL all-reduce.  Names / shapes / state_dict keys are untouched."""
+import torch
+
+ALIGN = 64   # floats (256 B): keeps every tensor 128-bit loadable and TMA-friendly
+
+
+class FlatParams:
+    def __init__(self, module):
+        named = [(n, p) for n, p in module.named_parameters()]
+        assert named, 'module has no parameters'
+        dev = named[0][1].device
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.offsets, off = [], 0
+        for p in self.params:
+            assert p.dtype == torch.float32 and p.device == dev
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.total = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            self.data[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.data[o:o + p.numel()].view(p.shape)
+        self.grad = torch.zeros_like(self.data)
+        self.index = {n: i for i, n in enumerate(self.names)}
+
+    def valid(self):
+        p0, pl = self.params[0], self.params[-1]
+        return (p0.data_ptr() == self.data.data_ptr() + 4 * self.offsets[0]
+                and pl.data_ptr() == self.data.data_ptr() + 4 * self.offsets[-1])
+
+    def views(self, flat):
+        """Per-parameter views (same order as `params`) into another flat buffer of the same layout."""
+        return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]
+
+    def view(self, flat, name):
+        i = self.index[name]
+        p, o = self.params[i], self.offsets[i]
+        return flat[o:o + p.numel()].view(p.shape)
+
+    def decay_segments(self, weight_decay):
+        """(seg_off int64[S+1], seg_decay fp32[S]) on the device: `fix_weight_decay` semantics of the reference
+        (`src/utils/train.py:12-23`): names containing bias / batch_norm / activation get no L2 term."""
+        offs = list(self.offsets) + [self.total]
+        dec = [0.0 if any(t in n for t in ('bias', 'batch_norm', 'activation')) else float(weight_decay)
+               for n in self.names]
+        dev = self.data.device
+        return (torch.tensor(offs, dtype=torch.int64, device=dev), torch.tensor(dec, dtype=torch.float32, device=dev))

@@ -1,0 +1,308 @@
+"""Drop-in MSGIFSR module on the sm_100a kernels.
+
+Constructor signature, parameter names / shapes / registration order (`state_dict` keys) follow the reference's
+`src/models/msgifsr.py:159-227` (+ `gnn_models/gatconv.py:135-176` for the GAT modules and DGL's
+`HeteroGraphConv.mods` ModuleDict); `forward(batch) -> (B, V) log-probabilities`.  Sub-modules only own
+parameters; the arithmetic is in the C-ABI kernels."""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import (HEADS, NORM_L2, SITE_EMBED, SITE_GAT_ATTN, SITE_GAT_DST, SITE_GAT_SRC, GatInst, SessRecError)
+from .base import SessRecModule
+
+SCALE = 12.0     # msgifsr.py:309
+
+
+class GATConv(nn.Module):
+    """Parameter holder of `gatconv.py:135-176` (num_heads=8, residual=Identity, bias)."""
+
+    def __init__(self, in_feats, out_feats, num_heads=HEADS):
+        super().__init__()
+        self.fc = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.bias = nn.Parameter(torch.empty(num_heads * out_feats))
+
+
+class HeteroGraphConv(nn.Module):
+    def __init__(self, mods):
+        super().__init__()
+        self.mods = nn.ModuleDict(mods)
+
+
+class MSHGNN(nn.Module):
+    """Parameter holder of `msgifsr.py:47-68` (lint/linq/link and the PReLU activation are never used by the
+    reference's forward but are part of its state_dict)."""
+
+    def __init__(self, input_dim, output_dim, order):
+        super().__init__()
+        self.activation = nn.PReLU(output_dim)
+        def mods():
+            m = {f'intra{i + 1}': GATConv(input_dim, output_dim) for i in range(order)}
+            m['inter'] = GATConv(input_dim, output_dim)
+            return m
+        self.conv1 = HeteroGraphConv(mods())
+        self.conv2 = HeteroGraphConv(mods())
+        self.lint = nn.Linear(output_dim, 1, bias=False)
+        self.linq = nn.Linear(output_dim, output_dim)
+        self.link = nn.Linear(output_dim, output_dim, bias=False)
+
+
+class SemanticExpander(nn.Module):
+    def __init__(self, input_dim, order):
+        super().__init__()
+        self.GRUs = nn.ModuleList([nn.GRU(input_dim, input_dim, 1, True, True) for _ in range(order)])
+
+
+class AttnReadout(nn.Module):
+    def __init__(self, input_dim, hidden_dim, order):
+        super().__init__()
+        self.fc_u = nn.ModuleList([nn.Linear(input_dim, hidden_dim, bias=True) for _ in range(order)])
+        self.fc_v = nn.ModuleList([nn.Linear(input_dim, hidden_dim, bias=False) for _ in range(order)])
+        self.fc_e = nn.ModuleList([nn.Linear(hidden_dim, 1, bias=False) for _ in range(order)])
+
+
+def gat_slot(layer, conv, etype, st, dt, K):
+    """Dense id of one (layer, conv, relation instance): dropout-site numbering shared with oracle/models.py."""
+    if etype == 'inter':
+        r = K + (dt - 2 if st == 1 else (K - 1) + st - 2)
+    else:
+        r = st - 1
+    return (layer * 2 + conv) * (3 * K) + r
+
+
+class MSGIFSR(SessRecModule):
+    def __init__(self, num_items, datasets, embedding_dim, num_layers, dropout=0.0, reducer='mean', order=3, norm=True,
+                 extra=True, fusion=True, device=torch.device('cpu')):
+        super().__init__()
+        if reducer != 'mean':
+            raise SessRecError('only reducer="mean" (the reference default) is built')
+        self.embeddings = nn.Embedding(num_items, embedding_dim, max_norm=1)
+        self.num_items = num_items
+        self.register_buffer('indices', torch.arange(num_items, dtype=torch.long))
+        self.embedding_dim, self.num_layers, self.order = embedding_dim, num_layers, order
+        self.reducer, self.norm = reducer, norm
+        self.layers = nn.ModuleList()          # registered before the expander, like the reference (msgifsr.py:169)
+        self.alpha = nn.Parameter(torch.empty(order))
+        self.beta = nn.Parameter(torch.empty(1))
+        self.expander = SemanticExpander(embedding_dim, order)
+        for _ in range(num_layers):
+            self.layers.append(MSHGNN(embedding_dim, embedding_dim, order))
+        self.readout = AttnReadout(embedding_dim, embedding_dim, order)
+        self.fc_sr = nn.ModuleList([nn.Linear(2 * embedding_dim, embedding_dim, bias=False) for _ in range(order)])
+        self.sc_sr = nn.ModuleList([nn.Sequential(nn.Linear(embedding_dim, embedding_dim, bias=True), nn.ReLU(),
+                                                  nn.Linear(embedding_dim, 2, bias=False), nn.Softmax(dim=-1))
+                                    for _ in range(order)])
+        self.dropout_p = float(dropout)
+        self.reset_parameters()
+        self.alpha.data = torch.zeros(order)
+        self.alpha.data[0] = 1.0
+        self.beta.data = torch.tensor(1.0)
+        self.fusion, self.extra = fusion, extra
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.embedding_dim)
+        for weight in self.parameters():
+            weight.data.uniform_(-stdv, stdv)
+
+    # ---- one MSHGNN layer ------------------------------------------------------------------------------------
+    def _instances(self, l, batch):
+        """[(conv, rel, module_name, reversed)] for every relation instance with >= 1 edge, per destination type."""
+        out = {k: [] for k in range(1, self.order + 1)}
+        for conv in (0, 1):
+            for rel in batch.rels:
+                if rel['M'] == 0:
+                    continue
+                et = 'inter' if rel['name'].startswith('inter') else rel['name']
+                st, dt = (rel['dt'], rel['st']) if conv else (rel['st'], rel['dt'])
+                out[dt].append(dict(conv=conv, rel=rel, et=et, st=st, dt=dt,
+                                    slot=gat_slot(l, conv, et, st, dt, self.order)))
+        return out
+
+    def _layer_fwd(self, l, batch, feats, p, seed, normalize, need_grad):
+        d, dev = self.embedding_dim, self.embeddings.weight.device
+        layer = self.layers[l]
+        ltape = dict(feats=feats, types={})
+        H = {}
+        ldz = HEADS * d + HEADS
+        by_dst = self._instances(l, batch)
+        dc_attn = ops.drop_cfg(p, SITE_GAT_ATTN, seed) if p > 0 else None
+        for k in range(1, self.order + 1):
+            t = batch.types[k]
+            N = t['N']
+            insts, recs = [], []
+            for it in by_dst[k]:
+                mod = getattr(layer, f'conv{it["conv"] + 1}').mods[it['et']]
+                rel, st = it['rel'], it['st']
+                Ns = batch.types[st]['N']
+                Waug = torch.empty(ldz, d, dtype=torch.float32, device=dev)
+                wr = torch.empty(HEADS, d, dtype=torch.float32, device=dev)
+                ops.gat_prep(mod.fc.weight, mod.attn_l, mod.attn_r, d, Waug, wr)
+                xs, xd, dcs, dcd = feats[st], feats[k], None, None
+                if p > 0:
+                    dcs = ops.drop_cfg(p, SITE_GAT_SRC + 4 * it['slot'], seed)
+                    dcd = ops.drop_cfg(p, SITE_GAT_DST + 4 * it['slot'], seed)
+                    xs, xd = torch.empty_like(feats[st]), torch.empty_like(feats[k])
+                    ops.dropout_apply(feats[st], xs, xs.numel(), dcs)
+                    ops.dropout_apply(feats[k], xd, xd.numel(), dcd)
+                Zel = torch.empty(Ns, ldz, dtype=torch.float32, device=dev)
+                er = torch.empty(N, HEADS, dtype=torch.float32, device=dev)
+                ops.linear_nt(xs, Waug, Zel)
+                ops.linear_nt(xd, wr, er)
+                att = torch.empty(max(rel['M'], 1), HEADS, dtype=torch.float32, device=dev)
+                gi = GatInst()
+                if it['conv'] == 0:
+                    cs = (rel['in_ptr'], rel['in_src'], rel['in_eid'], rel['out_ptr'], rel['out_dst'], rel['out_eid'])
+                else:          # reversed graph: roles of the two CSRs swap
+                    cs = (rel['out_ptr'], rel['out_dst'], rel['out_eid'], rel['in_ptr'], rel['in_src'], rel['in_eid'])
+                (gi.in_ptr, gi.in_src, gi.in_eid, gi.out_ptr, gi.out_dst, gi.out_eid) = (c.data_ptr() for c in cs)
+                gi.Zel, gi.er, gi.bias, gi.xdst, gi.att = (Zel.data_ptr(), er.data_ptr(), mod.bias.data_ptr(),
+                                                           xd.data_ptr(), att.data_ptr())
+                gi.n_src, gi.n_dst, gi.n_edges = Ns, N, rel['M']
+                gi.attn_site = SITE_GAT_ATTN + 4 * it['slot']
+                insts.append(gi)
+                recs.append(dict(it=it, mod=mod, Waug=Waug, wr=wr, xs=xs, xd=xd, dcs=dcs, dcd=dcd, Zel=Zel, er=er, att=att,
+                                 cs=cs))
+            segmean = torch.empty(batch.B, d, dtype=torch.float32, device=dev)
+            ops.segmean_fwd(feats[k], t['seg'], batch.B, d, segmean)
+            Hk = torch.empty(N, d, dtype=torch.float32, device=dev)
+            rn = torch.empty(N, dtype=torch.float32, device=dev)
+            amax = torch.empty(N, d, dtype=torch.uint8, device=dev)
+            arr = ops.gat_inst_array(insts)
+            ops.gat_aggregate_fwd(arr, len(insts), N, d, segmean, t['node2seg'], dc_attn, normalize, Hk, rn, amax)
+            H[k] = Hk
+            ltape['types'][k] = dict(insts=insts, recs=recs, arr=arr, H=Hk, rn=rn, amax=amax, normalize=normalize,
+                                     dc_attn=dc_attn)
+        return H, (ltape if need_grad else None)
+
+    def _layer_bwd(self, l, batch, ltape, dH, g):
+        """dH: {k: grad of the layer output}; returns {k: grad of the layer input}."""
+        d, dev = self.embedding_dim, self.embeddings.weight.device
+        ldz = HEADS * d + HEADS
+        feats = ltape['feats']
+        dfeat = {k: torch.empty_like(feats[k]) for k in feats}
+        pending = []
+        for k in range(1, self.order + 1):
+            t, tt = batch.types[k], ltape['types'][k]
+            N = t['N']
+            for gi, rec in zip(tt['insts'], tt['recs']):
+                M, Ns = rec['it']['rel']['M'], gi.n_src
+                rec['dedge'] = torch.empty(max(M, 1), HEADS, dtype=torch.float32, device=dev)
+                rec['der'] = torch.empty(N, HEADS, dtype=torch.float32, device=dev)
+                rec['dZel'] = torch.empty(Ns, ldz, dtype=torch.float32, device=dev)
+                gi.dedge, gi.der, gi.dZel = rec['dedge'].data_ptr(), rec['der'].data_ptr(), rec['dZel'].data_ptr()
+            arr = ops.gat_inst_array(tt['insts'])
+            dHpre = torch.empty(N, d, dtype=torch.float32, device=dev)
+            ops.gat_aggregate_bwd_dst(arr, len(tt['insts']), N, d, tt['dc_attn'], tt['normalize'], tt['H'], tt['rn'],
+                                      tt['amax'], dH[k], dHpre)
+            ops.segmean_bwd(dHpre, t['seg'], batch.B, d, dfeat[k], False)        # first writer of dfeat[k]
+            tt['dHpre'] = dHpre
+            pending.append(k)
+        for k in pending:
+            t, tt = batch.types[k], ltape['types'][k]
+            N, dHpre = t['N'], tt['dHpre']
+            for gi, rec in zip(tt['insts'], tt['recs']):
+                it, mod = rec['it'], rec['mod']
+                name = f'layers.{l}.conv{it["conv"] + 1}.mods.{it["et"]}.'
+                st, Ns = it['st'], gi.n_src
+                ops.gat_bias_bwd(dHpre, tt['amax'], N, d, g(name + 'bias'))
+                ops.gat_aggregate_bwd_src(gi, d, tt['dc_attn'], dHpre, tt['amax'])
+                dWaug = torch.zeros(ldz, d, dtype=torch.float32, device=dev)
+                dwr = torch.zeros(HEADS, d, dtype=torch.float32, device=dev)
+                ops.mm_tn(rec['dZel'], rec['xs'], dWaug)
+                ops.mm_tn(rec['der'], rec['xd'], dwr)
+                ops.gat_prep_bwd(mod.fc.weight, mod.attn_l, mod.attn_r, dWaug, dwr, d, g(name + 'fc.weight'),
+                                 g(name + 'attn_l'), g(name + 'attn_r'))
+                if rec['dcs'] is None:
+                    ops.mm_nn(rec['dZel'], rec['Waug'], dfeat[st], accumulate=True)
+                    ops.mm_nn(rec['der'], rec['wr'], dfeat[k], accumulate=True)
+                    ops.dropout_apply(dHpre, dfeat[k], dHpre.numel(), None, accumulate=True)     # residual
+                else:
+                    tmp = torch.empty(Ns, d, dtype=torch.float32, device=dev)
+                    ops.mm_nn(rec['dZel'], rec['Waug'], tmp)
+                    ops.dropout_apply(tmp, dfeat[st], tmp.numel(), rec['dcs'], accumulate=True)
+                    tmp2 = dHpre.clone()
+                    ops.mm_nn(rec['der'], rec['wr'], tmp2, accumulate=True)
+                    ops.dropout_apply(tmp2, dfeat[k], tmp2.numel(), rec['dcd'], accumulate=True)
+        return dfeat
+
+    # ---- whole model -------------------------------------------------------------------------------------------
+    def _fwd(self, batch, mode, need_grad=True):
+        if self.order != 1 or batch.K != 1:
+            raise SessRecError('MSGIFSR order > 1 is not built yet on the CUDA path (order 1 = the reference start.sh)')
+        if self.extra:
+            raise SessRecError('MSGIFSR extra=True (REnorm head) is not built; the reference scripts default to False')
+        if not self.norm:
+            raise SessRecError('MSGIFSR norm=False is not built (the reference argparse can only produce True)')
+        d, B, V, dev = self.embedding_dim, batch.B, self.num_items, self.embeddings.weight.device
+        E = self.embeddings.weight.data
+        p, seed = self._p(), self._next_seed()
+        tape = dict(batch=batch, p=p, seed=seed, mode=mode)
+        # nn.Embedding(max_norm=1): touched rows are renormed at the gather, all rows at the scoring head
+        # (msgifsr.py:247,276).  Rows are independent, so one pre-pass over the catalog does both.
+        Ehat = torch.empty_like(E)
+        enorm = torch.empty(V, dtype=torch.float32, device=dev)
+        ops.catalog_prep_fwd(E, NORM_L2, 1.0, Ehat, enorm)
+        t = batch.types[1]
+        N = t['N']
+        dc_e = ops.drop_cfg(p, SITE_EMBED + 1, seed) if p > 0 else None
+        X = torch.empty(N, d, dtype=torch.float32, device=dev)
+        rnX = torch.empty(N, dtype=torch.float32, device=dev)
+        ops.embed_gather_fwd(E, t['iid'], N, d, NORM_L2, dc_e, X, rnX)
+        h, ltapes = {1: X}, []
+        if self.num_layers == 0:
+            raise SessRecError('MSGIFSR needs num_layers >= 1')
+        for l in range(self.num_layers):
+            h, lt = self._layer_fwd(l, batch, h, p, seed, normalize=(l == self.num_layers - 1), need_grad=need_grad)
+            ltapes.append(lt)
+        F = h[1]
+        u = torch.empty(N, d, dtype=torch.float32, device=dev)
+        v = torch.empty(B, d, dtype=torch.float32, device=dev)
+        ops.linear_nt(F, self.readout.fc_u[0].weight, u, bias=self.readout.fc_u[0].bias)
+        ops.linear_nt(F, self.readout.fc_v[0].weight, v, M=B, a_idx=t['last'])
+        e = torch.empty(N, dtype=torch.float32, device=dev)
+        ms = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        sr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
+        ops.readout_fwd(F, u, v, self.readout.fc_e[0].weight, t['seg'], t['last'], B, d, True, e, ms, sr_in)
+        s = torch.empty(B, d, dtype=torch.float32, device=dev)
+        ops.linear_nt(sr_in, self.fc_sr[0].weight, s)
+        shat = torch.empty_like(s)
+        rn_s = torch.empty(B, dtype=torch.float32, device=dev)
+        ops.rownorm_fwd(s, d, B, d, NORM_L2, shat, d, rn_s)
+        tape.update(X=X, rnX=rnX, dc_e=dc_e, ltapes=ltapes, F=F, u=u, v=v, e=e, ms=ms, sr_in=sr_in, s=s, rn_s=rn_s,
+                    enorm=enorm)
+        out = self._head_fwd(shat, d, Ehat, SCALE, batch, mode, tape)
+        return out, (tape if need_grad else None)
+
+    def _bwd(self, tape, gout, gflat):
+        fp, batch = self._flat, tape['batch']
+        t = batch.types[1]
+        N, B, d, V = t['N'], batch.B, self.embedding_dim, self.num_items
+        E = self.embeddings.weight.data
+        dev = E.device
+        g = lambda name: fp.view(gflat, name)          # noqa: E731
+        gE = g('embeddings.weight')
+        dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
+        dshat = self._head_bwd(tape, batch, tape['mode'], gout, dEhat)
+        ops.catalog_prep_bwd(E, tape['Ehat'], tape['enorm'], dEhat, NORM_L2, gE)
+        ds = torch.empty(B, d, dtype=torch.float32, device=dev)
+        ops.rownorm_bwd(tape['s'], d, tape['shat'], d, tape['rn_s'], dshat, d, B, d, NORM_L2, ds, d)
+        sr_in, F, u, v = tape['sr_in'], tape['F'], tape['u'], tape['v']
+        dsr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
+        ops.mm_nn(ds, self.fc_sr[0].weight, dsr_in)
+        ops.mm_tn(ds, sr_in, g('fc_sr.0.weight'))
+        dF = torch.empty(N, d, dtype=torch.float32, device=dev)
+        ops.readout_bwd(F, u, v, self.readout.fc_e[0].weight, t['seg'], t['last'], tape['e'], tape['ms'], sr_in, dsr_in,
+                        B, d, True, dF, g('readout.fc_e.0.weight'))
+        ops.mm_nn(u, self.readout.fc_u[0].weight, dF, accumulate=True)
+        ops.mm_tn(u, F, g('readout.fc_u.0.weight'))
+        ops.colsum(u, d, N, d, g('readout.fc_u.0.bias'))
+        ops.mm_nn(v, self.readout.fc_v[0].weight, dF, c_idx=t['last'], accumulate=True)
+        ops.mm_tn(v, F, g('readout.fc_v.0.weight'), b_idx=t['last'])
+        dH = {1: dF}
+        for l in reversed(range(self.num_layers)):
+            dH = self._layer_bwd(l, batch, tape['ltapes'][l], dH, g)
+        ops.embed_scatter_bwd(E, t, d, NORM_L2, tape['dc_e'], tape['rnX'], dH[1], None, gE)

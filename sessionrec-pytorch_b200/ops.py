@@ -1,0 +1,230 @@
+"""Thin tensor-level wrappers over the C ABI (include/sessrec_b200.h).  Every function only enqueues kernels on
+the current CUDA stream.  No torch math lives here: torch is used for memory and streams only."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Dropout, GatInst, ptr
+
+_count = [0]
+
+
+def launches():
+    return _count[0]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _call(name, *args):
+    _count[0] += 1
+    return _lib.lib().call(name, *args, _stream())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.SessRecError('sessrec_b200 kernels need CUDA tensors; there is no CPU fallback')
+
+
+def drop_cfg(p, site, seed):
+    return Dropout(float(p), int(site), int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _dref(dc):
+    return None if dc is None else ctypes.cast(ctypes.pointer(dc), ctypes.c_void_p)
+
+
+# ---- GEMM forms -------------------------------------------------------------------------------------------
+
+def gemm(M, N, K, A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, a_idx=None, b_idx=None, c_idx=None, bias=None, alpha=1.0,
+         accumulate=False, split_k=0):
+    _need_cuda(A, B, C)
+    _call('srk_gemm', M, N, K, ptr(A), sa_m, sa_k, ptr(B), sb_k, sb_n, ptr(C), ldc, ptr(a_idx), ptr(b_idx), ptr(c_idx),
+          ptr(bias), float(alpha), int(bool(accumulate)), int(split_k if accumulate else 1))
+
+
+def linear_nt(X, W, C, M=None, K=None, lda=None, ldc=None, a_idx=None, c_idx=None, bias=None, alpha=1.0,
+              accumulate=False):
+    """C[M, N] (+)= alpha * X[M, K] @ W[N, K]^T (+ bias)."""
+    N, Kw = W.shape
+    K = Kw if K is None else K
+    M = X.shape[0] if M is None else M
+    gemm(M, N, K, X, X.stride(0) if lda is None else lda, 1, W, 1, W.stride(0), C, C.stride(0) if ldc is None else ldc,
+         a_idx=a_idx, c_idx=c_idx, bias=bias, alpha=alpha, accumulate=accumulate)
+
+
+def mm_nn(A, Bm, C, M=None, lda=None, ldc=None, c_idx=None, alpha=1.0, accumulate=False):
+    """C[M, N] (+)= alpha * A[M, K] @ Bm[K, N]."""
+    K, N = Bm.shape
+    M = A.shape[0] if M is None else M
+    gemm(M, N, K, A, A.stride(0) if lda is None else lda, 1, Bm, Bm.stride(0), 1, C, C.stride(0) if ldc is None else ldc,
+         c_idx=c_idx, alpha=alpha, accumulate=accumulate)
+
+
+def mm_tn(A, Bm, C, K=None, lda=None, ldb=None, ldc=None, b_idx=None, alpha=1.0, accumulate=True, M=None, N=None):
+    """C[M, N] (+)= alpha * A[K, M]^T @ Bm[K, N]  (weight-gradient form; split-K picked automatically)."""
+    K = A.shape[0] if K is None else K
+    M = A.shape[1] if M is None else M
+    N = Bm.shape[1] if N is None else N
+    gemm(M, N, K, A, 1, A.stride(0) if lda is None else lda, Bm, Bm.stride(0) if ldb is None else ldb, 1, C,
+         C.stride(0) if ldc is None else ldc, b_idx=b_idx, alpha=alpha, accumulate=accumulate, split_k=0)
+
+
+# ---- embedding ---------------------------------------------------------------------------------------------
+
+def embed_gather_fwd(E, iid, P, d, mode, dc, X, rnorm, x_first=None):
+    _need_cuda(E, iid, X)
+    _call('srk_embed_gather_fwd', ptr(E), ptr(iid), P, d, mode, _dref(dc), ptr(X), ptr(rnorm), ptr(x_first))
+
+
+def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE):
+    _call('srk_embed_scatter_bwd', ptr(E), ptr(t['iid']), ptr(t['perm']), ptr(t['uoff']), ptr(t['uid']), t['U'], d, mode,
+          _dref(dc), ptr(rnorm), ptr(dX), ptr(dX_first), ptr(dE))
+
+
+def catalog_prep_fwd(E, mode, max_norm, Ehat, enorm):
+    V, d = E.shape
+    _call('srk_catalog_prep_fwd', ptr(E), V, d, mode, float(max_norm), ptr(Ehat), ptr(enorm))
+
+
+def catalog_prep_bwd(E, Ehat, enorm, dEhat, mode, dE):
+    V, d = E.shape
+    _call('srk_catalog_prep_bwd', ptr(E), ptr(Ehat), ptr(enorm), ptr(dEhat), V, d, mode, ptr(dE))
+
+
+def renorm_rows(E, uid, U, max_norm=1.0):
+    _call('srk_renorm_rows', ptr(E), ptr(uid), U, E.shape[1], float(max_norm))
+
+
+def rownorm_fwd(X, ldx, R, d, mode, Y, ldy, rnorm):
+    _call('srk_rownorm_fwd', ptr(X), ldx, R, d, mode, ptr(Y), ldy, ptr(rnorm))
+
+
+def rownorm_bwd(X, ldx, Y, ldy, rnorm, dY, lddy, R, d, mode, dX, lddx, accumulate=False):
+    _call('srk_rownorm_bwd', ptr(X), ldx, ptr(Y), ldy, ptr(rnorm), ptr(dY), lddy, R, d, mode, ptr(dX), lddx,
+          int(bool(accumulate)))
+
+
+# ---- elementwise -------------------------------------------------------------------------------------------
+
+def dropout_apply(X, Y, n, dc, accumulate=False):
+    _call('srk_dropout_apply', ptr(X), ptr(Y), n, _dref(dc), int(bool(accumulate)))
+
+
+def fill(X, value=0.0):
+    _call('srk_fill', ptr(X), X.numel(), float(value))
+
+
+def gather_rows(X, idx, R, d, Y, ldy):
+    _call('srk_gather_rows', ptr(X), ptr(idx), R, d, ptr(Y), ldy)
+
+
+def scatter_add_rows(X, ldx, idx, R, d, Y):
+    _call('srk_scatter_add_rows', ptr(X), ldx, ptr(idx), R, d, ptr(Y))
+
+
+def colsum(X, ldx, R, d, out, accumulate=True):
+    _call('srk_colsum', ptr(X), ldx, R, d, ptr(out), int(bool(accumulate)))
+
+
+def mean(x, n, out):
+    _call('srk_mean', ptr(x), n, ptr(out))
+
+
+# ---- readout / CE ------------------------------------------------------------------------------------------
+
+def readout_fwd(F, u, v, we, seg, last, B, d, with_last, e, ms, sr_in):
+    _call('srk_readout_fwd', ptr(F), ptr(u), ptr(v), ptr(we), ptr(seg), ptr(last), B, d, int(with_last), ptr(e), ptr(ms),
+          ptr(sr_in))
+
+
+def readout_bwd(F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe):
+    _call('srk_readout_bwd', ptr(F), ptr(u), ptr(v), ptr(we), ptr(seg), ptr(last), ptr(e), ptr(ms), ptr(sr_in),
+          ptr(dsr_in), B, d, int(with_last), ptr(dF), ptr(dwe))
+
+
+def ce_rows_fwd(Z, ldz, labels, B, V, write_logp, lse, nll):
+    _call('srk_ce_rows_fwd', ptr(Z), ldz, ptr(labels), B, V, int(write_logp), ptr(lse), ptr(nll))
+
+
+def ce_rows_bwd(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp):
+    _call('srk_ce_rows_bwd', ptr(Z), ldz, ptr(labels), ptr(lse), ptr(gscale), float(scale), B, V, int(z_is_logp))
+
+
+def logp_bwd(LP, ldlp, G, ldg, scale, B, V, DZ, lddz):
+    _call('srk_logp_bwd', ptr(LP), ldlp, ptr(G), ldg, float(scale), B, V, ptr(DZ), lddz)
+
+
+# ---- GGNN ----------------------------------------------------------------------------------------------------
+
+def ggnn_aggregate_fwd(X, N, d, rel, NN, wsum):
+    _call('srk_ggnn_aggregate_fwd', ptr(X), N, d, ptr(rel['in_ptr']), ptr(rel['in_src']), ptr(rel['in_eid']),
+          ptr(rel['out_ptr']), ptr(rel['out_dst']), ptr(rel['out_eid']), ptr(rel['w']), ptr(NN), ptr(wsum))
+
+
+def ggnn_aggregate_bwd(dNN, N, d, rel, wsum, dX, accumulate):
+    _call('srk_ggnn_aggregate_bwd', ptr(dNN), N, d, ptr(rel['in_ptr']), ptr(rel['in_src']), ptr(rel['in_eid']),
+          ptr(rel['out_ptr']), ptr(rel['out_dst']), ptr(rel['out_eid']), ptr(rel['w']), ptr(wsum), ptr(dX),
+          int(bool(accumulate)))
+
+
+def gru_pointwise_fwd(gi, gh, h, N, d, hnew):
+    _call('srk_gru_pointwise_fwd', ptr(gi), ptr(gh), ptr(h), N, d, ptr(hnew))
+
+
+def gru_pointwise_bwd(gi, gh, h, dhnew, N, d, dh, accumulate):
+    _call('srk_gru_pointwise_bwd', ptr(gi), ptr(gh), ptr(h), ptr(dhnew), N, d, ptr(dh), int(bool(accumulate)))
+
+
+# ---- GAT -----------------------------------------------------------------------------------------------------
+
+def gat_prep(W, al, ar, d, Waug, wr):
+    _call('srk_gat_prep', ptr(W), ptr(al), ptr(ar), d, ptr(Waug), ptr(wr))
+
+
+def gat_prep_bwd(W, al, ar, dWaug, dwr, d, dW, dal, dar):
+    _call('srk_gat_prep_bwd', ptr(W), ptr(al), ptr(ar), ptr(dWaug), ptr(dwr), d, ptr(dW), ptr(dal), ptr(dar))
+
+
+def gat_inst_array(insts):
+    arr = (GatInst * max(len(insts), 1))()
+    for i, g in enumerate(insts):
+        arr[i] = g
+    return arr
+
+
+def gat_aggregate_fwd(arr, n_inst, N, d, segmean, node2seg, dc, normalize, H, rnorm, amax):
+    _call('srk_gat_aggregate_fwd', ctypes.cast(arr, ctypes.c_void_p), n_inst, N, d, ptr(segmean), ptr(node2seg),
+          _dref(dc), int(normalize), ptr(H), ptr(rnorm), ptr(amax))
+
+
+def gat_aggregate_bwd_dst(arr, n_inst, N, d, dc, normalize, H, rnorm, amax, dH, dHpre):
+    _call('srk_gat_aggregate_bwd_dst', ctypes.cast(arr, ctypes.c_void_p), n_inst, N, d, _dref(dc), int(normalize), ptr(H),
+          ptr(rnorm), ptr(amax), ptr(dH), ptr(dHpre))
+
+
+def gat_aggregate_bwd_src(inst, d, dc, dHpre, amax):
+    _call('srk_gat_aggregate_bwd_src', ctypes.cast(ctypes.pointer(inst), ctypes.c_void_p), d, _dref(dc), ptr(dHpre),
+          ptr(amax))
+
+
+def gat_bias_bwd(dHpre, amax, N, d, dbias):
+    _call('srk_gat_bias_bwd', ptr(dHpre), ptr(amax), N, d, ptr(dbias))
+
+
+def segmean_fwd(X, seg, B, d, out):
+    _call('srk_segmean_fwd', ptr(X), ptr(seg), B, d, ptr(out))
+
+
+def segmean_bwd(dHpre, seg, B, d, dX, accumulate):
+    _call('srk_segmean_bwd', ptr(dHpre), ptr(seg), B, d, ptr(dX), int(bool(accumulate)))
+
+
+# ---- optimizer -------------------------------------------------------------------------------------------------
+
+def adam_step(param, grad, m, v, seg_off, seg_decay, n_seg, lr, b1, b2, eps, step):
+    _call('srk_adam_step', ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), ptr(seg_off), ptr(seg_decay), n_seg,
+          float(lr), float(b1), float(b2), float(eps), int(step))

@@ -1,0 +1,280 @@
+"""Per-stage parity of the sm_100a kernels (called through the C ABI) against plain fp32/fp64 torch on the CPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as OM
+from tests.util import assert_close, assert_grad_close, golden, oracle_batch, oracle_params
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def ops(pkg):
+    from sessionrec_pytorch_b200 import ops as o
+    return o
+
+
+def _r(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).float()
+
+
+@pytest.mark.parametrize('M,N,K', [(64, 64, 16), (70, 33, 45), (512, 776, 96), (5, 3, 1000), (300, 96, 2200), (1, 1, 1)])
+def test_gemm_forms(ops, M, N, K):
+    A, B = _r(M, K), _r(N, K, seed=1)
+    ref = (A.double() @ B.double().t())
+    C = torch.empty(M, N, device=DEV)
+    ops.linear_nt(A.to(DEV), B.to(DEV), C)
+    assert_grad_close('nt', C, ref, rtol=2e-6)
+    bias = _r(N, seed=2)
+    ops.linear_nt(A.to(DEV), B.to(DEV), C, bias=bias.to(DEV), alpha=0.5)
+    assert_grad_close('nt+bias', C, 0.5 * ref + bias.double(), rtol=2e-6)
+    Bn = B.t().contiguous()                       # [K, N]
+    C2 = torch.full((M, N), 1.0, device=DEV)
+    ops.mm_nn(A.to(DEV), Bn.to(DEV), C2, accumulate=True)
+    assert_grad_close('nn+acc(split-K auto)', C2, ref + 1.0, rtol=2e-6)
+    At = A.t().contiguous()                       # [K, M]
+    C3 = torch.zeros(M, N, device=DEV)
+    ops.mm_tn(At.to(DEV), Bn.to(DEV), C3)
+    assert_grad_close('tn', C3, ref, rtol=2e-6)
+
+
+def test_gemm_indirection_and_strides(ops):
+    R, M, N, K = 90, 40, 24, 32
+    X, W = _r(R, K), _r(N, K, seed=3)
+    idx = torch.randperm(R)[:M].int()
+    C = torch.empty(M, N, device=DEV)
+    ops.linear_nt(X.to(DEV), W.to(DEV), C, M=M, a_idx=idx.to(DEV))
+    assert_grad_close('a_idx', C, X[idx.long()].double() @ W.double().t(), rtol=2e-6)
+    # scatter rows of C
+    D = torch.zeros(R, K, device=DEV)
+    G = _r(M, N, seed=4)
+    ops.mm_nn(G.to(DEV), W.to(DEV), D, c_idx=idx.to(DEV), accumulate=True)
+    ref = torch.zeros(R, K, dtype=torch.float64)
+    ref[idx.long()] = G.double() @ W.double()
+    assert_grad_close('c_idx', D, ref, rtol=2e-6)
+    # gathered B rows in the weight-gradient form: dW = G^T X[idx]
+    dW = torch.zeros(N, K, device=DEV)
+    ops.mm_tn(G.to(DEV), X.to(DEV), dW, b_idx=idx.to(DEV))
+    assert_grad_close('b_idx', dW, G.double().t() @ X[idx.long()].double(), rtol=2e-6)
+    # odd leading dimensions (catalog sizes are odd): Z[B, V] with V = 1001, transposed operand
+    Bz, V, d = 48, 1001, 16
+    Z, Eh, s = _r(Bz, V, seed=5), _r(V, d, seed=6), _r(Bz, d, seed=7)
+    out = torch.zeros(Bz, d, device=DEV)
+    ops.gemm(Bz, d, V, Z.to(DEV), V, 1, Eh.to(DEV), d, 1, out, d, accumulate=True, split_k=0)
+    assert_grad_close('dS odd ld', out, Z.double() @ Eh.double(), rtol=2e-6)
+    out2 = torch.zeros(V, d, device=DEV)
+    ops.gemm(V, d, Bz, Z.to(DEV), 1, V, s.to(DEV), d, 1, out2, d, accumulate=True, split_k=0)
+    assert_grad_close('dE odd ld', out2, Z.double().t() @ s.double(), rtol=2e-6)
+
+
+def _norm_ref(x, mode):
+    n = x.norm(dim=-1, keepdim=True)
+    if mode == 0:
+        return x
+    if mode == 1:
+        y = x / (n + 1e-12)
+        return y / y.norm(dim=-1, keepdim=True)
+    if mode == 2:
+        return torch.nn.functional.normalize(x, dim=-1)
+    return x / (n + 1e-12)
+
+
+@pytest.mark.parametrize('d', [8, 16, 96, 256, 520])
+@pytest.mark.parametrize('mode', [0, 1, 2, 3])
+@pytest.mark.parametrize('p', [0.0, 0.35])
+def test_embed_gather_scatter(pkg, ops, d, mode, p):
+    V, B = 300, 37
+    rng = np.random.default_rng(d + mode)
+    seqs = [rng.integers(0, 40, size=int(rng.integers(1, 9))).tolist() for _ in range(B)]
+    b = pkg.SessionBatch.build(seqs, [0] * B, 'session').to(DEV)
+    t = b.types[1]
+    N = t['N']
+    E = _r(V, d, seed=d) * 0.3
+    iid = t['iid'].cpu().long()
+    seed = 99
+    drop = OM.Dropout(p, True, seed)
+    Er = E.clone().requires_grad_(True)
+    ref = _norm_ref(drop(Er[iid], OM.SITE_EMBED + 1), mode)
+    G = _r(N, d, seed=11)
+    (ref * G).sum().backward()
+    dc = ops.drop_cfg(p, OM.SITE_EMBED + 1, seed) if p > 0 else None
+    X = torch.empty(N, d, device=DEV)
+    rn = torch.empty(N, device=DEV)
+    Ed = E.to(DEV)
+    ops.embed_gather_fwd(Ed, t['iid'], N, d, mode, dc, X, rn)
+    assert_close('gather', X, ref, rtol=1e-5)
+    dE = torch.zeros(V, d, device=DEV)
+    ops.embed_scatter_bwd(Ed, t, d, mode, dc, rn, G.to(DEV), None, dE)
+    assert_grad_close('scatter', dE, Er.grad, rtol=2e-5)
+
+
+def test_dropout_masks_match_oracle(ops):
+    n, p, seed, site = 5000, 0.25, 0xABCDEF12345, OM.SITE_GAT_ATTN + 8
+    x = torch.ones(n, device=DEV)
+    y = torch.empty(n, device=DEV)
+    ops.dropout_apply(x, y, n, ops.drop_cfg(p, site, seed))
+    ref = OM.Dropout(p, True, seed)(torch.ones(n), site)
+    assert torch.equal(y.cpu(), ref)
+
+
+@pytest.mark.parametrize('mode,max_norm', [(2, 1.0), (3, 0.0)])
+def test_catalog_prep(ops, mode, max_norm):
+    V, d = 257, 32
+    E = _r(V, d, seed=5) * 0.25          # norms ~1.4: some rows above 1, some below
+    Er = E.clone()
+    if max_norm > 0:
+        OM.renorm_rows_(Er, torch.arange(V), max_norm)
+    Er.requires_grad_(True)
+    ref = _norm_ref(Er, mode)
+    G = _r(V, d, seed=6)
+    (ref * G).sum().backward()
+    Ed = E.to(DEV)
+    Ehat, en = torch.empty(V, d, device=DEV), torch.empty(V, device=DEV)
+    ops.catalog_prep_fwd(Ed, mode, max_norm, Ehat, en)
+    assert_close('E renormed in place', Ed, Er, rtol=1e-6)
+    assert_close('Ehat', Ehat, ref, rtol=1e-5)
+    dE = torch.zeros(V, d, device=DEV)
+    ops.catalog_prep_bwd(Ed, Ehat, en, G.to(DEV), mode, dE)
+    assert_grad_close('dE', dE, Er.grad, rtol=2e-5)
+
+
+def test_readout(pkg, ops):
+    d, B = 32, 23
+    rng = np.random.default_rng(1)
+    seqs = [rng.integers(0, 30, size=int(rng.integers(1, 15))).tolist() for _ in range(B)]
+    b = pkg.SessionBatch.build(seqs, [0] * B, 'session').to(DEV)
+    t = b.types[1]
+    N = t['N']
+    F, Wu, Wv, bv, we, Wsr = _r(N, d), _r(d, d, seed=1) * 0.3, _r(d, d, seed=2) * 0.3, _r(d, seed=3), _r(1, d, seed=4), _r(d, 2 * d, seed=5)
+    params = {'readout.fc_u.weight': Wu, 'readout.fc_v.weight': Wv, 'readout.fc_v.bias': bv, 'readout.fc_e.weight': we}
+    params = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    Fr = F.clone().requires_grad_(True)
+    ids = OM._seg_ids(t['seg'].cpu().numpy())
+    last = t['last'].cpu().long()
+    g = OM._readout_single(params, Fr, last, ids, B)
+    sr_in_ref = torch.cat([Fr[last], g], 1)
+    G = _r(B, 2 * d, seed=9)
+    (sr_in_ref * G).sum().backward()
+    Fd = F.to(DEV)
+    u, v = torch.empty(N, d, device=DEV), torch.empty(B, d, device=DEV)
+    ops.linear_nt(Fd, Wu.to(DEV), u)
+    ops.linear_nt(Fd, Wv.to(DEV), v, M=B, a_idx=t['last'], bias=bv.to(DEV))
+    e, ms, sr_in = torch.empty(N, device=DEV), torch.empty(B, 2, device=DEV), torch.empty(B, 2 * d, device=DEV)
+    ops.readout_fwd(Fd, u, v, we.to(DEV), t['seg'], t['last'], B, d, True, e, ms, sr_in)
+    assert_close('sr_in', sr_in, sr_in_ref, rtol=1e-5)
+    dF, dwe = torch.empty(N, d, device=DEV), torch.zeros(1, d, device=DEV)
+    ops.readout_bwd(Fd, u, v, we.to(DEV), t['seg'], t['last'], e, ms, sr_in, G.to(DEV), B, d, True, dF, dwe)
+    gWu, gWv, gbv = torch.zeros(d, d, device=DEV), torch.zeros(d, d, device=DEV), torch.zeros(d, device=DEV)
+    ops.mm_nn(u, Wu.to(DEV), dF, accumulate=True)
+    ops.mm_tn(u, Fd, gWu)
+    ops.mm_nn(v, Wv.to(DEV), dF, c_idx=t['last'], accumulate=True)
+    ops.mm_tn(v, Fd, gWv, b_idx=t['last'])
+    ops.colsum(v, d, B, d, gbv)
+    assert_grad_close('dF', dF, Fr.grad, rtol=2e-5)
+    assert_grad_close('dwe', dwe, params['readout.fc_e.weight'].grad, rtol=2e-5)
+    assert_grad_close('dWu', gWu, params['readout.fc_u.weight'].grad, rtol=2e-5)
+    assert_grad_close('dWv', gWv, params['readout.fc_v.weight'].grad, rtol=2e-5)
+    assert_grad_close('dbv', gbv, params['readout.fc_v.bias'].grad, rtol=2e-5)
+
+
+@pytest.mark.parametrize('V', [257, 1000, 4099])
+def test_ce_rows(ops, V):
+    B = 19
+    ldz = (V + 3) // 4 * 4
+    Z = _r(B, V, seed=V) * 4
+    labels = torch.randint(0, V, (B,), generator=torch.Generator().manual_seed(V))
+    Zr = Z.clone().requires_grad_(True)
+    logp = torch.log_softmax(Zr, -1)
+    loss = torch.nn.functional.nll_loss(logp, labels)
+    loss.backward()
+    Zd = torch.zeros(B, ldz, device=DEV)
+    Zd[:, :V] = Z.to(DEV)
+    lab = labels.int().to(DEV)
+    lse, nll, out = torch.empty(B, device=DEV), torch.empty(B, device=DEV), torch.empty((), device=DEV)
+    ops.ce_rows_fwd(Zd, ldz, lab, B, V, False, lse, nll)
+    ops.mean(nll, B, out)
+    assert_close('lse', lse, torch.logsumexp(Z, -1), rtol=1e-6)
+    assert abs(float(out) - float(loss)) <= 1e-6 * abs(float(loss))
+    Z2 = Zd.clone()
+    ops.ce_rows_bwd(Z2, ldz, lab, lse, torch.full((1,), 2.0, device=DEV), 3.0, B, V, False)
+    assert_grad_close('dZ', Z2[:, :V], 6.0 * Zr.grad, rtol=1e-5)
+    # compat: rewrite to log-probs, then backward from an arbitrary upstream gradient
+    ops.ce_rows_fwd(Zd, ldz, None, B, V, True, lse, None)
+    assert_close('logp', Zd[:, :V], logp, rtol=1e-6)
+    G = _r(B, V, seed=3)
+    Zr.grad = None
+    (torch.log_softmax(Zr, -1) * G).sum().backward()
+    DZ = torch.empty(B, ldz, device=DEV)
+    ops.logp_bwd(Zd, ldz, G.to(DEV), V, 1.5, B, V, DZ, ldz)
+    assert_grad_close('logp_bwd', DZ[:, :V], 1.5 * Zr.grad, rtol=1e-5)
+
+
+@pytest.mark.parametrize('name', ['ggnn_d16', 'ggnn_d32'])
+@pytest.mark.parametrize('p', [0.0, 0.4])
+def test_ggnn_layer(pkg, ops, name, p):
+    from sessionrec_pytorch_b200.srgnn import SRGNNLayer, ggnn_layer_bwd, ggnn_layer_fwd
+    c = golden('ggnn_golden.pt')[name]
+    d = c['d']
+    b = pkg.SessionBatch.build([s for s, _ in c['samples']], [l for _, l in c['samples']], 'session').to(DEV)
+    layer = SRGNNLayer(d, d)
+    layer.load_state_dict({k[len('layers.0.'):]: v for k, v in c['params'].items()})
+    layer = layer.to(DEV)
+    seed = 4242
+    x = c['x'].to(DEV)
+    out, tape = ggnn_layer_fwd(layer, b, x, p, seed, OM.SITE_GGNN)
+    names = ['gru.weight_ih', 'gru.weight_hh', 'gru.bias_ih', 'gru.bias_hh', 'W1.weight', 'W2.weight']
+    g = {n: torch.zeros_like(dict(layer.named_parameters())[n]) for n in names}
+    dx = torch.empty_like(x)
+    ggnn_layer_bwd(layer, b, tape, c['rnd'].to(DEV), g, dx, False)
+    if p == 0:
+        ref_out, ref_dx, ref_g = c['out'], c['dx'], c['grads']
+    else:
+        prm = oracle_params(c['params'])
+        ob = oracle_batch(c['samples'], 'session', 1)
+        xr = c['x'].clone().requires_grad_(True)
+        ref_out = OM.ggnn_layer(prm, 'layers.0.', ob, xr, OM.Dropout(p, True, seed), OM.SITE_GGNN)
+        (ref_out * c['rnd']).sum().backward()
+        ref_dx, ref_g = xr.grad, {k: v.grad for k, v in prm.items()}
+    assert_close('ggnn.out', out, ref_out, rtol=1e-5)
+    assert_grad_close('ggnn.dx', dx, ref_dx, rtol=5e-5)
+    for n in names:
+        assert_grad_close(f'ggnn.{n}', g[n], ref_g['layers.0.' + n], rtol=5e-5)
+
+
+def test_adam_matches_torch(ops):
+    from sessionrec_pytorch_b200.flat import FlatParams
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Linear(17, 5)).to(DEV)
+    ref = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Linear(17, 5))
+    ref.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    fp = FlatParams(m)
+    seg_off, seg_dec = fp.decay_segments(1e-2)
+    mm, vv = torch.zeros_like(fp.data), torch.zeros_like(fp.data)
+    dec = [p for n, p in ref.named_parameters() if 'bias' not in n]
+    nod = [p for n, p in ref.named_parameters() if 'bias' in n]
+    opt = torch.optim.Adam([{'params': dec}, {'params': nod, 'weight_decay': 0}], lr=1e-2, weight_decay=1e-2)
+    for step in range(1, 6):
+        for (n, p), gv in zip(ref.named_parameters(), fp.views(fp.grad)):
+            gr = _r(*p.shape, seed=step)
+            p.grad = gr.clone()
+            gv.copy_(gr.to(DEV))
+        opt.step()
+        ops.adam_step(fp.data, fp.grad, mm, vv, seg_off, seg_dec, len(fp.names), 1e-2, 0.9, 0.999, 1e-8, step)
+    for (n, p), q in zip(ref.named_parameters(), m.parameters()):
+        assert_close(f'adam.{n}', q, p, rtol=2e-6)
+
+
+def test_segmean(pkg, ops):
+    d, B = 16, 9
+    seqs = [list(range(i + 1)) for i in range(B)]
+    b = pkg.SessionBatch.build(seqs, [0] * B, 'ccs', 1).to(DEV)
+    t = b.types[1]
+    X = _r(t['N'], d)
+    ids = OM._seg_ids(t['seg'].cpu().numpy())
+    ref = OM._seg_sum(X, ids, B) / torch.arange(1, B + 1).float().unsqueeze(-1)
+    out = torch.empty(B, d, device=DEV)
+    ops.segmean_fwd(X.to(DEV), t['seg'], B, d, out)
+    assert_close('segmean', out, ref, rtol=1e-6)

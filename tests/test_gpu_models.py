@@ -1,0 +1,205 @@
+"""End-to-end parity of the drop-in modules (all arithmetic in the sm_100a kernels) against the golden vectors of
+the unmodified reference and against the CPU oracle on seeded inputs.  Tolerances: north_star's 1e-4 relative on
+fp32 log-probs / loss; gradients 1e-4 of each parameter's max-norm; integer outputs (top-k ids) exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as OM
+from tests.util import (RTOL, assert_close, assert_grad_close, golden, oracle_batch, oracle_params, run_oracle)
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+MODELS = golden('models_golden.pt')
+TRAINS = golden('train_golden.pt')
+BUILT = [n for n, c in MODELS.items() if c['K'] == 1]
+
+
+def make_model(pkg, c, dropout=0.0):
+    from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+    from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
+    if c['model'] == 'MSGIFSR':
+        m = MSGIFSR(c['V'], 'golden', c['d'], c.get('L', 1), dropout=dropout, order=c['K'], extra=False,
+                    fusion=c.get('fusion', False))
+    else:
+        m = {'SRGNN': SRGNN, 'NISER': NISER}[c['model']](c['V'], c['d'], c.get('L', 1), dropout)
+    missing = m.load_state_dict(c['params'], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.to(DEV)
+
+
+def make_batch(pkg, c, samples=None):
+    samples = c['samples'] if samples is None else samples
+    kind = 'session' if c['model'] in ('SRGNN', 'NISER') else 'ccs'
+    b = pkg.SessionBatch.build([s for s, _ in samples], [l for _, l in samples], kind, c['K'])
+    return b.to(DEV), torch.tensor([l for _, l in samples], dtype=torch.long, device=DEV)
+
+
+def test_state_dict_keys_match_reference(pkg):
+    for name, c in MODELS.items():
+        from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+        from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
+        if c['model'] == 'MSGIFSR':
+            m = MSGIFSR(c['V'], 'x', c['d'], c['L'], order=c['K'], extra=False, fusion=c['fusion'])
+        else:
+            m = {'SRGNN': SRGNN, 'NISER': NISER}[c['model']](c['V'], c['d'], c['L'])
+        assert list(m.state_dict().keys()) == list(c['params'].keys()), name
+        for k, v in m.state_dict().items():
+            assert tuple(v.shape) == tuple(c['params'][k].shape), (name, k)
+
+
+@pytest.mark.parametrize('name', BUILT)
+def test_forward_backward_vs_reference_golden(pkg, name):
+    """forward() -> (B, V) log-probs, nll_loss, backward: the unmodified TrainRunner contract."""
+    c = MODELS[name]
+    m = make_model(pkg, c)
+    m.train()
+    b, labels = make_batch(pkg, c)
+    out = m(b)
+    assert out.shape == (len(c['samples']), c['V']) and out.dtype == torch.float32
+    loss = torch.nn.functional.nll_loss(out, labels)
+    loss.backward()
+    assert_close(f'{name}.logp', out, c['out'])
+    assert abs(float(loss) - c['loss']) <= RTOL * abs(c['loss'])
+    top_ref, top_got = c['out'].topk(20)[1], out.detach().cpu().topk(20)[1]
+    gap = (c['out'].topk(21)[0][:, 19] - c['out'].topk(21)[0][:, 20])
+    safe = gap > 1e-3                      # ids are compared wherever the 20/21 boundary is not a near-tie
+    assert torch.equal(top_ref[safe].sort(-1)[0], top_got[safe].sort(-1)[0])
+    params = dict(m.named_parameters())
+    for n, g in c['grads'].items():
+        assert_grad_close(f'{name}.grad[{n}]', params[n].grad, g)
+    for n, w in c['params_after_forward'].items():
+        assert_close(f'{name}.{n} after forward (max_norm renorm)', m.state_dict()[n], w, rtol=1e-6)
+
+
+@pytest.mark.parametrize('name', BUILT)
+def test_fused_loss_path_vs_reference_golden(pkg, name):
+    c = MODELS[name]
+    m = make_model(pkg, c)
+    m.train()
+    b, _ = make_batch(pkg, c)
+    loss = m.loss(b)
+    loss.backward()
+    assert abs(float(loss) - c['loss']) <= RTOL * abs(c['loss'])
+    params = dict(m.named_parameters())
+    for n, g in c['grads'].items():
+        assert_grad_close(f'{name}.grad[{n}]', params[n].grad, g)
+
+
+@pytest.mark.parametrize('name', ['srgnn', 'niser', 'msgifsr_k1', 'msgifsr_k1_inflate_L2'])
+@pytest.mark.parametrize('p', [0.2, 0.5])
+def test_dropout_with_injected_masks_vs_oracle(pkg, name, p):
+    """Training mode with dropout: the oracle consumes the same counter-based masks the kernels regenerate."""
+    c = MODELS[name]
+    seed = 20260101 + int(p * 10)
+    m = make_model(pkg, c, dropout=p)
+    m.train()
+    m.set_dropout_seed(seed)
+    b, labels = make_batch(pkg, c)
+    loss = m.loss(b)
+    loss.backward()
+    prm = oracle_params(c['params'])
+    kind = 'session' if c['model'] in ('SRGNN', 'NISER') else 'ccs'
+    ob = oracle_batch(c['samples'], kind, c['K'])
+    ref = run_oracle(c['model'], prm, ob, c['L'], c['fusion'], drop=OM.Dropout(p, True, seed))
+    rl = OM.nll(ref, ob['labels'])
+    rl.backward()
+    assert abs(float(loss) - float(rl)) <= RTOL * abs(float(rl)), (float(loss), float(rl))
+    params = dict(m.named_parameters())
+    for n in c['grads']:
+        assert_grad_close(f'{name}.p{p}.grad[{n}]', params[n].grad, prm[n].grad)
+    m.eval()
+    with torch.no_grad():
+        assert_close(f'{name}.eval logp', m(b), c['out'] if 'inflate' not in name else
+                     run_oracle(c['model'], oracle_params(c['params'], False), ob, c['L'], c['fusion']))
+
+
+@pytest.mark.parametrize('name', [n for n in sorted(TRAINS) if TRAINS[n]['K'] == 1])
+def test_fused_train_step_trajectory_vs_reference(pkg, name):
+    """train_step (fused fwd + CE + bwd + our Adam kernel) reproduces the reference TrainRunner's losses, final
+    embedding table and evaluate() metrics."""
+    c = TRAINS[name]
+    m = make_model(pkg, c)
+    m.train()
+    m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+    for it in range(c['steps']):
+        b, _ = make_batch(pkg, c, c['samples'][it * c['bs']:(it + 1) * c['bs']])
+        loss = m.train_step(b)
+        assert abs(float(loss) - c['losses'][it]) <= RTOL * abs(c['losses'][it]), (it, float(loss), c['losses'][it])
+    emb = 'embeddings.weight' if c['model'] == 'MSGIFSR' else 'embedding.weight'
+    assert_close(f'{name}.final_embedding', m.state_dict()[emb], c['final_embedding'], rtol=RTOL, floor=1e-2)
+    m.eval()
+    mrr = hit = n = 0
+    with torch.no_grad():
+        for i in range(0, len(c['test_samples']), c['bs']):
+            b, labels = make_batch(pkg, c, c['test_samples'][i:i + c['bs']])
+            r, h = OM.topk_metrics(m(b).cpu(), labels.cpu().numpy())
+            mrr, hit, n = mrr + r, hit + h, n + b.B
+    assert abs(hit / n - c['hit']) <= 1e-3 and abs(mrr / n - c['mrr']) <= 1e-3
+
+
+@pytest.mark.parametrize('name', ['srgnn', 'msgifsr_k1'])
+def test_unmodified_style_training_loop_with_torch_adam(pkg, name):
+    """The reference loop body verbatim (optimizer.zero_grad / model(*inputs) / nll_loss / backward / step) with
+    torch.optim.Adam + fix_weight_decay groups runs on the drop-in module and follows the golden trajectory."""
+    c = TRAINS[name]
+    m = make_model(pkg, c)
+    m.train()
+    named = list(m.named_parameters())
+    dec, no = OM.decay_split([n for n, _ in named])
+    pm = dict(named)
+    opt = torch.optim.Adam([{'params': [pm[n] for n in dec]}, {'params': [pm[n] for n in no], 'weight_decay': 0}],
+                           lr=1e-3, weight_decay=1e-4)
+    for it in range(c['steps']):
+        b, labels = make_batch(pkg, c, c['samples'][it * c['bs']:(it + 1) * c['bs']])
+        opt.zero_grad()
+        scores = m(b)
+        assert not torch.isnan(scores).any()
+        loss = torch.nn.functional.nll_loss(scores, labels)
+        loss.backward()
+        opt.step()
+        assert abs(loss.item() - c['losses'][it]) <= RTOL * abs(c['losses'][it]), (it, loss.item(), c['losses'][it])
+
+
+@pytest.mark.parametrize('cfg', ['cfg1', 'cfg2', 'cfg3'])
+def test_full_size_configs_vs_oracle(pkg, cfg):
+    """BASELINE.json shapes (synthetic sessions): loss and gradients against the CPU oracle, plus size-independent
+    properties: rows of exp(logp) sum to 1, loss() == nll(forward()), catalog renorm is idempotent."""
+    from sessionrec_pytorch_b200.synthetic import CONFIGS, SessionSampler
+    k = CONFIGS[cfg]
+    torch.manual_seed(5)
+    c = dict(model=k['model'], V=k['V'], d=k['d'], L=k['layers'], K=1, fusion=False)
+    from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+    from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
+    if k['model'] == 'MSGIFSR':
+        m = MSGIFSR(k['V'], 'x', k['d'], k['layers'], dropout=0.0, order=1, extra=False, fusion=False)
+        with torch.no_grad():
+            m.embeddings.weight[::5] *= 2.0            # exercise max_norm on a fifth of the catalog
+    else:
+        m = {'SRGNN': SRGNN, 'NISER': NISER}[k['model']](k['V'], k['d'], k['layers'], 0.0)
+    sd = {n: v.clone() for n, v in m.state_dict().items()}
+    m = m.to(DEV).train()
+    B = min(k['B'], 512)
+    seqs, labels = SessionSampler(k['V'], seed=123).sessions(B)
+    kind = 'session' if k['model'] in ('SRGNN', 'NISER') else 'ccs'
+    b = pkg.SessionBatch.build(seqs, labels, kind, 1).to(DEV)
+    lab = torch.tensor(labels, dtype=torch.long, device=DEV)
+    out = m(b)
+    loss = torch.nn.functional.nll_loss(out, lab)
+    loss.backward()
+    assert_close('rows of exp(logp) sum to 1', out.detach().double().exp().sum(-1).float(), torch.ones(B), rtol=2e-5)
+    grads = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    fused = m.loss(b)
+    assert abs(float(fused) - float(loss)) <= 1e-6 * abs(float(loss))
+    prm = oracle_params(sd)
+    ob = oracle_batch(list(zip(seqs, labels)), kind, 1)
+    torch.set_num_threads(8)
+    ref = run_oracle(k['model'], prm, ob, k['layers'])
+    rl = OM.nll(ref, ob['labels'])
+    rl.backward()
+    assert abs(float(loss) - float(rl)) <= RTOL * abs(float(rl)), (float(loss), float(rl))
+    assert_close(f'{cfg}.logp', out, ref)
+    for n, g in grads.items():
+        if prm[n].grad is not None:
+            assert_grad_close(f'{cfg}.grad[{n}]', g, prm[n].grad)

@@ -1,0 +1,70 @@
+"""Shared helpers of the parity tests (oracle = checker, never the product)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from oracle import collate as OC
+from oracle import models as OM
+
+GOLD = Path(__file__).resolve().parent / 'golden'
+RTOL = 1e-4      # north_star: fp32 logits / loss within 1e-4 relative
+
+
+def golden(name):
+    return torch.load(GOLD / name, weights_only=False)
+
+
+def golden_json(name):
+    return json.loads((GOLD / name).read_text())
+
+
+def oracle_params(sd, grad=True):
+    p = {}
+    for k, v in sd.items():
+        t = v.detach().clone().cpu()
+        if grad and t.is_floating_point():
+            t.requires_grad_(True)
+        p[k] = t
+    return p
+
+
+def oracle_batch(samples, kind, K):
+    return OC.build_batch([s for s, _ in samples], [l for _, l in samples], kind, K)
+
+
+def assert_close(name, got, ref, rtol=RTOL, floor=1.0):
+    """|got - ref| <= rtol * max(|ref|, floor) elementwise."""
+    got = got.detach().cpu().double()
+    ref = ref.detach().cpu().double()
+    assert got.shape == ref.shape, f'{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}'
+    assert torch.isfinite(got).all(), f'{name}: non-finite values'
+    err = (got - ref).abs()
+    tol = rtol * ref.abs().clamp(min=floor)
+    bad = err > tol
+    if bad.any():
+        i = int((err / tol).argmax())
+        raise AssertionError(f'{name}: {int(bad.sum())}/{bad.numel()} elements off; worst |d|={err.flatten()[i]:.3e} '
+                             f'ref={ref.flatten()[i]:.6e} got={got.flatten()[i]:.6e} (flat index {i})')
+
+
+def assert_grad_close(name, got, ref, rtol=RTOL):
+    """Max-norm relative: max|got - ref| <= rtol * max|ref| (absolute 1e-7 for numerically-zero grads)."""
+    if ref is None:
+        assert got is None or float(got.abs().max()) == 0.0, f'{name}: reference has no gradient'
+        return
+    assert got is not None, f'{name}: missing gradient'
+    got = got.detach().cpu().double()
+    ref = ref.detach().cpu().double()
+    assert got.shape == ref.shape, f'{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}'
+    assert torch.isfinite(got).all(), f'{name}: non-finite gradient'
+    err = float((got - ref).abs().max())
+    scale = max(float(ref.abs().max()), 1e-3)
+    assert err <= rtol * scale, f'{name}: max|d|={err:.3e} vs max|ref|={float(ref.abs().max()):.3e} (rel {err / scale:.2e})'
+
+
+def run_oracle(case_model, params, ob, L=1, fusion=False, drop=OM.NO_DROPOUT):
+    if case_model == 'MSGIFSR':
+        return OM.msgifsr_forward(params, ob, drop=drop, num_layers=L, fusion=fusion)
+    return OM.srgnn_forward(params, ob, drop=drop, num_layers=L, niser=(case_model == 'NISER'))
