@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py - train sessions/sec of the B200-native session-rec training path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1] [--impl reference]
+
+A "step" = one TrainRunner iteration (`src/utils/train.py:95-101`): forward + nll_loss + backward + Adam(L2) step
+over one synthetic batch of the named BASELINE.json configuration.  One process per GPU (torchrun sets RANK /
+LOCAL_RANK / WORLD_SIZE); data-parallel ranks own independent batches and exchange the flat gradient with one NCCL
+all-reduce per step (weak scaling).  Prints ONE JSON line on rank 0.
+
+`value`     device-timed (CUDA events per step, L2 flushed between steps), batches already resident in HBM.
+`e2e`       the same metric through the public API with HOST (pinned) batch buffers: H2D copy of the batch and a
+            D2H read of the loss inside every timed step.
+`roofline`  the dominant kernel family (catalog scoring GEMMs), timed live in isolation with CUDA events.
+`cpu_baseline` the oracle port (oracle/models.py, the restated reference) timed on this box's host cores on a bounded
+            sample of the same workload.  `--impl reference` times only that, as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+from __graft_entry__ import build, load_package  # noqa: E402
+
+METRIC = 'train sessions/sec'
+UNIT = 'sessions/s'
+
+
+def peaks():
+    f = ROOT / 'MEASURED_PEAKS.json'
+    if f.exists():
+        d = json.loads(f.read_text())
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [v for v in (num(r[0]) for r in self.rows if r) if v is not None]
+        mx = [v for v in (num(r[1]) for r in self.rows if len(r) > 1) if v is not None]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == 'Active'})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def build_model(cfg, device):
+    from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+    from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
+    torch.manual_seed(123)
+    if cfg['model'] == 'MSGIFSR':
+        m = MSGIFSR(cfg['V'], 'synthetic', cfg['d'], cfg['layers'], dropout=cfg['dropout'], order=cfg['order'],
+                    extra=False, fusion=False)
+    else:
+        m = {'SRGNN': SRGNN, 'NISER': NISER}[cfg['model']](cfg['V'], cfg['d'], cfg['layers'], cfg['dropout'])
+    return m.to(device).train()
+
+
+def kind_of(cfg):
+    return 'session' if cfg['model'] in ('SRGNN', 'NISER') else 'ccs'
+
+
+def cpu_oracle_steps(cfg, sessions, steps, warmup):
+    """The reference loop body on the host cores via the oracle port; returns (sessions/s, cores, seconds)."""
+    from oracle import collate as OC
+    from oracle import models as OM
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = build_model(cfg, 'cpu')
+    params = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    opt = OM.make_adam({k: v for k, v in params.items() if v.is_floating_point()}, 1e-3, 1e-4)
+    drop = OM.Dropout(cfg['dropout'], True, None)
+    batches = [OC.build_batch(s, l, kind_of(cfg), cfg['order']) for s, l in sessions]
+    t_total, n = 0.0, 0
+    for it in range(warmup + steps):
+        ob = batches[it % len(batches)]
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        if cfg['model'] == 'MSGIFSR':
+            out = OM.msgifsr_forward(params, ob, drop=drop, num_layers=cfg['layers'])
+        else:
+            out = OM.srgnn_forward(params, ob, drop=drop, num_layers=cfg['layers'], niser=cfg['model'] == 'NISER')
+        loss = OM.nll(out, ob['labels'])
+        loss.backward()
+        opt.step()
+        float(loss.detach())
+        if it >= warmup:
+            t_total += time.perf_counter() - t0
+            n += ob['B']
+    return n / t_total, cores, t_total
+
+
+def roofline_probe(cfg, device, pk):
+    """Times the three catalog GEMMs of one step (Z = s E^T, dS = dZ E, dE = dZ^T s) in isolation, L2 flushed."""
+    from sessionrec_pytorch_b200 import ops
+    B, V, d = cfg['B'], cfg['V'], cfg['d']
+    ldz = (V + 3) // 4 * 4
+    g = torch.Generator(device='cpu').manual_seed(1)
+    s = torch.randn(B, d, generator=g).to(device)
+    E = torch.randn(V, d, generator=g).to(device)
+    Z = torch.empty(B, ldz, device=device)
+    dS = torch.zeros(B, d, device=device)
+    dE = torch.zeros(V, d, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def run():
+        ops.gemm(B, V, d, s, d, 1, E, 1, d, Z, ldz, alpha=12.0)
+        ops.gemm(B, d, V, Z, ldz, 1, E, d, 1, dS, d, accumulate=True, split_k=0)
+        ops.gemm(V, d, B, Z, 1, ldz, s, d, 1, dE, d, accumulate=True, split_k=0)
+
+    for _ in range(3):
+        run()
+    times = []
+    for _ in range(10):
+        flush.fill_(0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = float(np.median(times))
+    flops = 6.0 * B * V * d
+    ach = flops / (ms * 1e-3) / 1e12
+    return dict(bound='tensor', kernel='catalog scoring GEMMs (Z = s E^T, dS = dZ E, dE = dZ^T s): sgemm_kernel, fp32 FFMA',
+                achieved=round(ach, 3), peak=pk['tf_burst'], unit='TFLOP/s', frac=round(ach / pk['tf_burst'], 5),
+                traffic=None, ms_for_the_3_launches=round(ms, 4), algorithmic_flops=flops,
+                peak_source=f"{pk['src']} bf16 burst (kernel timed alone)")
+
+
+def reference_arm(args, cfg, rank):
+    if rank != 0:
+        return
+    from sessionrec_pytorch_b200.synthetic import SessionSampler
+    smp = SessionSampler(cfg['V'], seed=123)
+    sessions = [smp.sessions(cfg['B']) for _ in range(min(4, args.steps + args.warmup))]
+    v, cores, secs = cpu_oracle_steps(cfg, sessions, args.steps, args.warmup)
+    sample = f"{args.steps} full steps (B={cfg['B']}) of {args.workload}, {secs:.1f} s of CPU work"
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': round(v, 2), 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': round(1e3 * cfg['B'] / v, 3), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': dict(workload=workload_name(args.workload, cfg), **{k: cfg[k] for k in ('V', 'd', 'B', 'order', 'layers', 'dropout')}),
+        'cpu_baseline': dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port', sample=sample),
+        'e2e': dict(value=round(v, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        'note': 'reference CPU path = oracle port of src/models + TrainRunner loop body (DGL is not installable here)'}))
+
+
+def workload_name(key, cfg):
+    idx = int(key[3:])
+    return (f"BASELINE.json configs[{idx}]: {cfg['model']} order {cfg['order']}, {cfg['layers']} layer(s), {cfg['note']} "
+            f"V={cfg['V']} d={cfg['d']} B={cfg['B']}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--workload', default='cfg1')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    load_package()
+    from sessionrec_pytorch_b200.synthetic import CONFIGS, SessionSampler
+    cfg = dict(CONFIGS[args.workload])
+    if args.impl == 'reference':
+        if args.steps == 30 and args.warmup == 5:
+            args.steps, args.warmup = 5, 1
+        reference_arm(args, cfg, rank)
+        return
+    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists for the product path)'
+    build()
+    pkg = load_package()
+    from sessionrec_pytorch_b200 import ops
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+        group = dist.group.WORLD
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pk = peaks()
+    model = build_model(cfg, device)
+    model.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+    smp = SessionSampler(cfg['V'], seed=123 + rank)
+    n_batches = 8
+    host = []
+    for _ in range(n_batches):
+        items, offs, labels = smp.batch(cfg['B'])
+        host.append(pkg.SessionBatch.build_flat(items, offs, labels, kind_of(cfg), cfg['order'], pin=True))
+    resident = [b.to(device, non_blocking=False) for b in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)        # 2x the 126 MB L2
+
+    # ---- device-timed region: K steps, inputs resident in HBM -------------------------------------------------
+    for i in range(args.warmup):
+        model.train_step(resident[i % n_batches], group)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    k0 = ops.kernel_launches()
+    evs = []
+    launches = 0
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kk = ops.kernel_launches()
+        a.record()
+        model.train_step(resident[(args.warmup + i) % n_batches], group)
+        b.record()
+        launches += ops.kernel_launches() - kk
+        evs.append((a, b))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    value = world * cfg['B'] * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers -----------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    h2d = 0
+    for i in range(args.steps):
+        hb = host[i % n_batches]
+        db = hb.to(device, non_blocking=True)           # H2D of the whole batch (one pinned buffer)
+        loss = model.train_step(db, group)
+        loss.item()                                     # D2H read of the step's loss (what TrainRunner does, train.py:103)
+        h2d += hb.nbytes
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = world * cfg['B'] * args.steps / float(e2e_s)
+
+    out = None
+    if rank == 0:
+        roof = roofline_probe(cfg, device, pk)
+        out = {
+            'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': round(total_ms / args.steps, 4), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(workload=workload_name(args.workload, cfg), parallelism=f'dp{world}', global_batch=world * cfg['B'],
+                           l2='flushed between timed steps (256 MB write)', timing='CUDA events per step, max over ranks',
+                           **{k: cfg[k] for k in ('V', 'd', 'B', 'order', 'layers', 'dropout')}),
+            'clocks': clk, 'gpu_launches': int(launches), 'launches_per_step': round(launches / args.steps, 1),
+            'e2e': dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=int(h2d / args.steps), d2h_bytes_per_step=4,
+                        timing='wall clock over K steps incl. H2D batch copy + loss.item() per step'),
+            'wall_s_timed_region': round(t_wall, 4), 'roofline': roof,
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            sessions = [SessionSampler(cfg['V'], seed=123).sessions(cfg['B']) for _ in range(2)]
+            v, cores, secs = cpu_oracle_steps(cfg, sessions, 3, 1)
+            out['cpu_baseline'] = dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port',
+                                       sample=f"3 full steps (B={cfg['B']}) of {args.workload} after 1 warm-up, {secs:.1f} s")
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -52,6 +52,7 @@ typedef struct srk_dropout {
 
 const char* srk_last_error(void);
 int srk_version(void);
+long long srk_launch_count(void); /* kernels launched by this library so far (process-wide) */
 
 /* ---- dense building block -------------------------------------------------------------------------
  * C[rc(m), n] (op)= alpha * sum_k A[ra(m)*sa_m + k*sa_k] * B[rb(k)*sb_k + n*sb_n] (+ bias[n]).
@@ -203,10 +204,11 @@ int srk_segmean_fwd(const float* X, const int* seg, int B, int d, float* mean, v
 int srk_segmean_bwd(const float* dHpre, const int* seg, int B, int d, float* dX, int accumulate, void* stream);
 
 /* ---- optimizer (next-row: utils/train.py:70-74, torch.optim.Adam with L2-in-grad) ------------------------------
- * Flat buffers; decay[i] per element group is given by seg_off[S+1] / seg_decay[S]. step is 1-based. */
+ * Flat buffers; decay[i] per element group is given by seg_off[S+1] / seg_decay[S]. step is 1-based; grad_scale
+ * multiplies the raw gradient first (1/world_size after a data-parallel all-reduce). */
 int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                   const long long* seg_off, const float* seg_decay, int n_seg, float lr, float beta1, float beta2,
-                  float eps, int step, void* stream);
+                  float eps, int step, float grad_scale, void* stream);
 
 /* ---- native batch builder (host; next-row: utils/data/collate.py:61-85,87-217,219-256) ---------------------------
  * Sessions are given as a flat item array + offsets. kind 0 = session graph (weights, self-loop rule), kind 1 =

@@ -114,9 +114,11 @@ class SessRecModule(nn.Module):
                          m=torch.zeros_like(fp.data), v=torch.zeros_like(fp.data), n_seg=len(fp.names))
         return self._opt
 
-    def train_step(self, batch):
+    def train_step(self, batch, group=None):
         """zero_grad + forward + nll_loss + backward + Adam step, all on the current stream; returns the loss
-        as a 0-d device tensor (no host sync)."""
+        as a 0-d device tensor (no host sync).  With a torch.distributed process group (data parallel: every rank
+        owns a slice of the global batch) the flat gradient buffer is summed with ONE NCCL all-reduce and the
+        1/world_size mean is folded into the Adam kernel."""
         fp = self._ensure_flat()
         if self._opt is None:
             self.configure_optimizer()
@@ -125,9 +127,14 @@ class SessRecModule(nn.Module):
             loss, tape = self._fwd(batch, 'loss', need_grad=True)
             ops.fill(fp.grad, 0.0)
             self._bwd(tape, self._one(), fp.grad)
+            scale = 1.0
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(fp.grad, group=group)
+                scale = 1.0 / dist.get_world_size(group)
             o['step'] += 1
             ops.adam_step(fp.data, fp.grad, o['m'], o['v'], o['seg_off'], o['seg_decay'], o['n_seg'], o['lr'],
-                          o['betas'][0], o['betas'][1], o['eps'], o['step'])
+                          o['betas'][0], o['betas'][1], o['eps'], o['step'], scale)
         return loss
 
     def _one(self):

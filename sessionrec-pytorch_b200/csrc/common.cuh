@@ -30,7 +30,12 @@ void srk_set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
-#define SRK_LAUNCH_CHECK() SRK_CUDA(cudaGetLastError())
+extern long long g_srk_launches;   // kernels launched by this library (bench.py reports it as gpu_launches)
+#define SRK_LAUNCH_CHECK()            \
+  do {                                \
+    ++g_srk_launches;                 \
+    SRK_CUDA(cudaGetLastError());     \
+  } while (0)
 
 #define SRK_TRY(expr)               \
   do {                              \

@@ -14,6 +14,8 @@ void srk_set_error(const char* fmt, ...) {
 
 extern "C" const char* srk_last_error(void) { return g_err; }
 extern "C" int srk_version(void) { return 100; }
+long long g_srk_launches = 0;
+extern "C" long long srk_launch_count(void) { return g_srk_launches; }
 
 namespace {
 
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    const long long* __restrict__ seg_off, const float* __restrict__ seg_decay,
                                                    int n_seg, float lr, float b1, float b2, float eps, float bc1,
-                                                   float bc2_sqrt) {
+                                                   float bc2_sqrt, float grad_scale) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int lo = 0, hi = n_seg - 1;           // segment of element i (seg_off ascending, seg_off[n_seg] == n)
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
       int mid = (lo + hi + 1) >> 1;
       if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    float grad = g[i] + seg_decay[lo] * p[i];
+    float grad = g[i] * grad_scale + seg_decay[lo] * p[i];
     float mi = b1 * m[i] + (1.f - b1) * grad;
     float vi = b2 * v[i] + (1.f - b2) * grad * grad;
     m[i] = mi;
@@ -185,14 +187,14 @@ extern "C" int srk_mean(const float* x, int n, float* out, void* stream) {
 
 extern "C" int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                              const long long* seg_off, const float* seg_decay, int n_seg, float lr, float beta1,
-                             float beta2, float eps, int step, void* stream) {
+                             float beta2, float eps, int step, float grad_scale, void* stream) {
   if (n <= 0) return SRK_OK;
   SRK_REQUIRE(n_seg >= 1 && step >= 1, "adam: need >= 1 segment and step >= 1");
   float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n,
                                                                    seg_off, seg_decay,
-                                                                   n_seg, lr, beta1, beta2, eps, bc1, bc2_sqrt);
+                                                                   n_seg, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

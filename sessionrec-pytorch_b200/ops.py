@@ -225,6 +225,11 @@ def segmean_bwd(dHpre, seg, B, d, dX, accumulate):
 
 # ---- optimizer -------------------------------------------------------------------------------------------------
 
-def adam_step(param, grad, m, v, seg_off, seg_decay, n_seg, lr, b1, b2, eps, step):
+def adam_step(param, grad, m, v, seg_off, seg_decay, n_seg, lr, b1, b2, eps, step, grad_scale=1.0):
     _call('srk_adam_step', ptr(param), ptr(grad), ptr(m), ptr(v), param.numel(), ptr(seg_off), ptr(seg_decay), n_seg,
-          float(lr), float(b1), float(b2), float(eps), int(step))
+          float(lr), float(b1), float(b2), float(eps), int(step), float(grad_scale))
+
+
+def kernel_launches():
+    """Kernels launched by libsessrec_b200.so so far (counted inside the library)."""
+    return int(_lib.lib().functions['srk_launch_count']())

@@ -27,18 +27,18 @@ def test_gemm_forms(ops, M, N, K):
     ref = (A.double() @ B.double().t())
     C = torch.empty(M, N, device=DEV)
     ops.linear_nt(A.to(DEV), B.to(DEV), C)
-    assert_grad_close('nt', C, ref, rtol=2e-6)
+    assert_grad_close('nt', C, ref, rtol=5e-6)
     bias = _r(N, seed=2)
     ops.linear_nt(A.to(DEV), B.to(DEV), C, bias=bias.to(DEV), alpha=0.5)
-    assert_grad_close('nt+bias', C, 0.5 * ref + bias.double(), rtol=2e-6)
+    assert_grad_close('nt+bias', C, 0.5 * ref + bias.double(), rtol=5e-6)
     Bn = B.t().contiguous()                       # [K, N]
     C2 = torch.full((M, N), 1.0, device=DEV)
     ops.mm_nn(A.to(DEV), Bn.to(DEV), C2, accumulate=True)
-    assert_grad_close('nn+acc(split-K auto)', C2, ref + 1.0, rtol=2e-6)
+    assert_grad_close('nn+acc(split-K auto)', C2, ref + 1.0, rtol=5e-6)
     At = A.t().contiguous()                       # [K, M]
     C3 = torch.zeros(M, N, device=DEV)
     ops.mm_tn(At.to(DEV), Bn.to(DEV), C3)
-    assert_grad_close('tn', C3, ref, rtol=2e-6)
+    assert_grad_close('tn', C3, ref, rtol=5e-6)
 
 
 def test_gemm_indirection_and_strides(ops):
@@ -47,27 +47,27 @@ def test_gemm_indirection_and_strides(ops):
     idx = torch.randperm(R)[:M].int()
     C = torch.empty(M, N, device=DEV)
     ops.linear_nt(X.to(DEV), W.to(DEV), C, M=M, a_idx=idx.to(DEV))
-    assert_grad_close('a_idx', C, X[idx.long()].double() @ W.double().t(), rtol=2e-6)
+    assert_grad_close('a_idx', C, X[idx.long()].double() @ W.double().t(), rtol=5e-6)
     # scatter rows of C
     D = torch.zeros(R, K, device=DEV)
     G = _r(M, N, seed=4)
     ops.mm_nn(G.to(DEV), W.to(DEV), D, c_idx=idx.to(DEV), accumulate=True)
     ref = torch.zeros(R, K, dtype=torch.float64)
     ref[idx.long()] = G.double() @ W.double()
-    assert_grad_close('c_idx', D, ref, rtol=2e-6)
+    assert_grad_close('c_idx', D, ref, rtol=5e-6)
     # gathered B rows in the weight-gradient form: dW = G^T X[idx]
     dW = torch.zeros(N, K, device=DEV)
     ops.mm_tn(G.to(DEV), X.to(DEV), dW, b_idx=idx.to(DEV))
-    assert_grad_close('b_idx', dW, G.double().t() @ X[idx.long()].double(), rtol=2e-6)
+    assert_grad_close('b_idx', dW, G.double().t() @ X[idx.long()].double(), rtol=5e-6)
     # odd leading dimensions (catalog sizes are odd): Z[B, V] with V = 1001, transposed operand
     Bz, V, d = 48, 1001, 16
     Z, Eh, s = _r(Bz, V, seed=5), _r(V, d, seed=6), _r(Bz, d, seed=7)
     out = torch.zeros(Bz, d, device=DEV)
     ops.gemm(Bz, d, V, Z.to(DEV), V, 1, Eh.to(DEV), d, 1, out, d, accumulate=True, split_k=0)
-    assert_grad_close('dS odd ld', out, Z.double() @ Eh.double(), rtol=2e-6)
+    assert_grad_close('dS odd ld', out, Z.double() @ Eh.double(), rtol=5e-6)
     out2 = torch.zeros(V, d, device=DEV)
     ops.gemm(V, d, Bz, Z.to(DEV), 1, V, s.to(DEV), d, 1, out2, d, accumulate=True, split_k=0)
-    assert_grad_close('dE odd ld', out2, Z.double().t() @ s.double(), rtol=2e-6)
+    assert_grad_close('dE odd ld', out2, Z.double().t() @ s.double(), rtol=5e-6)
 
 
 def _norm_ref(x, mode):
@@ -197,13 +197,13 @@ def test_ce_rows(ops, V):
     ops.ce_rows_fwd(Zd, ldz, lab, B, V, False, lse, nll)
     ops.mean(nll, B, out)
     assert_close('lse', lse, torch.logsumexp(Z, -1), rtol=1e-6)
-    assert abs(float(out) - float(loss)) <= 1e-6 * abs(float(loss))
+    assert abs(float(out) - float(loss)) <= 2e-6 * abs(float(loss))
     Z2 = Zd.clone()
     ops.ce_rows_bwd(Z2, ldz, lab, lse, torch.full((1,), 2.0, device=DEV), 3.0, B, V, False)
     assert_grad_close('dZ', Z2[:, :V], 6.0 * Zr.grad, rtol=1e-5)
     # compat: rewrite to log-probs, then backward from an arbitrary upstream gradient
     ops.ce_rows_fwd(Zd, ldz, None, B, V, True, lse, None)
-    assert_close('logp', Zd[:, :V], logp, rtol=1e-6)
+    assert_close('logp', Zd[:, :V], logp, rtol=3e-6)
     G = _r(B, V, seed=3)
     Zr.grad = None
     (torch.log_softmax(Zr, -1) * G).sum().backward()
@@ -264,7 +264,7 @@ def test_adam_matches_torch(ops):
         opt.step()
         ops.adam_step(fp.data, fp.grad, mm, vv, seg_off, seg_dec, len(fp.names), 1e-2, 0.9, 0.999, 1e-8, step)
     for (n, p), q in zip(ref.named_parameters(), m.parameters()):
-        assert_close(f'adam.{n}', q, p, rtol=2e-6)
+        assert_close(f'adam.{n}', q, p, rtol=5e-6)
 
 
 def test_segmean(pkg, ops):
