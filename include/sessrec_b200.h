@@ -62,6 +62,16 @@ int srk_gemm(int M, int N, int K, const float* A, long long sa_m, long long sa_k
              long long sb_n, float* C, long long ldc, const int* a_idx, const int* b_idx, const int* c_idx,
              const float* bias, float alpha, int accumulate, int split_k, void* stream);
 
+/* tcgen05 tensor-core GEMM, fp32-faithful via a 3xTF32 split (A = Ahi + Alo, B = Bhi + Blo, halves produced by
+ * srk_split_tf32 or by the producing kernels).  form 0: A[M,K] B[N,K] (Z = s E^T, srgnn.py:146); form 1: A[M,K] B[K,N]
+ * (dS = dZ E); form 2: A[K,M] B[K,N] (dE = dZ^T s).  TMA (SWIZZLE_128B) + tcgen05.mma kind::tf32 + TMEM accumulators.
+ * accumulate != 0 uses an atomicAdd epilogue (required for split_k > 1).  N <= 256 for forms 1 and 2. */
+int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, const float* Alo, long long lda, const float* Bhi,
+                  const float* Blo, long long ldb, float* C, long long ldc, float alpha, int accumulate, int split_k,
+                  void* stream);
+/* hi = x with the 13 low mantissa bits cleared (TF32-exact), lo = x - hi (exact); [rows, cols] with pitches ldx / ldo. */
+int srk_split_tf32(const float* X, long long ldx, int rows, int cols, float* hi, float* lo, long long ldo, void* stream);
+
 /* ---- item-embedding gather / scatter-add (K1 / K8) -------------------------------------------------
  * Forward: X[i] = norm_mode(dropout(E[iid[i]])), i < P.  Replaces `self.embedding(iid)` + feat_drop +
  * normalisation (srgnn.py:133; niser.py:133-135,141-142; msgifsr.py:247-253).  rnorm[i] receives the L2
@@ -80,9 +90,10 @@ int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const
  * mode SRK_NORM_L2 (MSGIFSR): renormalise IN PLACE every row of E whose norm exceeds max_norm (> 0) by
  * max_norm / (norm + 1e-7) (`nn.Embedding(max_norm=1)`, msgifsr.py:162,276), then Ehat = F.normalize(E)
  * (msgifsr.py:278-279).  mode SRK_NORM_EPS (NISER): Ehat = E / (||E|| + 1e-12) (niser.py:149-151).
- * enorm[V] receives the (post-renorm) row norms. */
+ * enorm[V] receives the (post-renorm) row norms.  Ehat_hi / Ehat_lo (optional, both or neither): TF32 split of
+ * Ehat for srk_umma_gemm. */
 int srk_catalog_prep_fwd(float* E, int V, int d, int norm_mode, float max_norm, float* Ehat, float* enorm,
-                         void* stream);
+                         float* Ehat_hi, float* Ehat_lo, void* stream);
 int srk_catalog_prep_bwd(const float* E, const float* Ehat, const float* enorm, const float* dEhat, int V, int d,
                          int norm_mode, float* dE, void* stream);
 /* In-place max_norm renorm of the rows touched by a gather (msgifsr.py:247); duplicates are safe. */
@@ -126,13 +137,14 @@ int srk_ce_rows_fwd(float* Z, long long ldz, const int* labels, int B, int V, in
                     void* stream);
 /* loss = mean(nll) (deterministic single-block reduction). */
 int srk_mean(const float* x, int n, float* out, void* stream);
-/* Fused-loss backward: Z <- dZ = gscale[0] * scale * (exp(Z - lse) - onehot) / B in place (Z = logits). */
+/* Fused-loss backward: Z <- dZ = gscale[0] * scale * (exp(Z - lse) - onehot) / B in place (Z = logits).  With Zlo != NULL
+ * the TF32 split is written instead: Z <- hi(dZ), Zlo <- dZ - hi(dZ) (operands of srk_umma_gemm). */
 int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale, float scale,
-                    int B, int V, int z_is_logp, void* stream);
+                    int B, int V, int z_is_logp, float* Zlo, void* stream);
 /* Compat backward from an arbitrary upstream gradient G[B, V] of the log-probs LP:
  * dZ = scale * (G - exp(LP) * rowsum(G)), written into DZ (may alias G). */
 int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V, float* DZ,
-                 long long lddz, void* stream);
+                 long long lddz, float* DZlo, void* stream);
 
 /* ---- GGNN layer (K2 / K3) ---------------------------------------------------------------------------------
  * Weighted-mean aggregation over in-edges and out-edges: NN[v] = [ sum_in w x[u] / sum_in w | sum_out w x[t] /

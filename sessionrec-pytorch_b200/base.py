@@ -1,6 +1,8 @@
 """Shared machinery of the drop-in modules: flat parameters, the autograd bridge (one Function per model call;
 the whole forward/backward below it is our kernels), the catalog scoring + cross-entropy head, fused training
 step with the reference's Adam/L2 semantics."""
+import os
+
 import torch
 from torch import nn
 
@@ -37,6 +39,7 @@ class SessRecModule(nn.Module):
         self._step = 0
         self._fixed_seed = None
         self._opt = None
+        self.use_tensor_cores = os.environ.get('SESSREC_NO_UMMA', '0') != '1'
 
     # ---- parameters -------------------------------------------------------------------------------------
     def _ensure_flat(self):
@@ -74,14 +77,27 @@ class SessRecModule(nn.Module):
         return _Bridge.apply(self, mg, 'loss', *self._flat.params)
 
     # ---- catalog scoring + CE head -----------------------------------------------------------------------
-    def _head_fwd(self, shat, ld_s, Ehat, scale, batch, mode, tape):
+    def _head_fwd(self, shat, ld_s, Ehat, scale, batch, mode, tape, Ehi=None, Elo=None):
+        """Z = scale * shat Ehat^T on the tcgen05 tensor cores (3xTF32, csrc/umma_gemm.cu) whenever the embedding
+        dim fits one UMMA N tile (d <= 256); otherwise on the fp32 CUDA-core GEMM."""
         B, (V, d) = batch.B, Ehat.shape
         dev = Ehat.device
-        ldz = (V + 3) // 4 * 4                      # 16-byte aligned rows: vector loads in the backward GEMMs
+        ldz = (V + 3) // 4 * 4                      # 16-byte aligned rows: TMA / vector loads in the backward GEMMs
         Z = torch.empty(B, ldz, dtype=torch.float32, device=dev)
-        ops.gemm(B, V, d, shat, ld_s, 1, Ehat, 1, d, Z, ldz, alpha=scale)
+        umma = self.use_tensor_cores and d <= 256
+        if umma:
+            if Ehi is None:
+                Ehi, Elo = torch.empty_like(Ehat), torch.empty_like(Ehat)
+                ops.split_tf32(Ehat, d, V, d, Ehi, Elo, d)
+            sh = torch.empty(B, d, dtype=torch.float32, device=dev)
+            sl = torch.empty(B, d, dtype=torch.float32, device=dev)
+            ops.split_tf32(shat, ld_s, B, d, sh, sl, d)
+            ops.umma_gemm(0, B, V, d, sh, sl, d, Ehi, Elo, d, Z, ldz, alpha=scale)
+            tape.update(Ehi=Ehi, Elo=Elo, sh=sh, sl=sl)
+        else:
+            ops.gemm(B, V, d, shat, ld_s, 1, Ehat, 1, d, Z, ldz, alpha=scale)
         lse = torch.empty(B, dtype=torch.float32, device=dev)
-        tape.update(Z=Z, ldz=ldz, lse=lse, scale=scale, Ehat=Ehat, shat=shat, ld_s=ld_s)
+        tape.update(Z=Z, ldz=ldz, lse=lse, scale=scale, Ehat=Ehat, shat=shat, ld_s=ld_s, umma=umma)
         if mode == 'loss':
             nll = torch.empty(B, dtype=torch.float32, device=dev)
             ops.ce_rows_fwd(Z, ldz, batch.labels, B, V, False, lse, nll)
@@ -91,17 +107,26 @@ class SessRecModule(nn.Module):
         ops.ce_rows_fwd(Z, ldz, None, B, V, True, lse, None)
         return Z[:, :V]
 
-    def _head_bwd(self, tape, batch, mode, gout, dEhat):
-        """Returns d shat [B, d]; accumulates the catalog gradient into dEhat [V, d]."""
+    def _head_bwd(self, tape, batch, mode, gout, dEhat, overwrite=False):
+        """Returns d shat [B, d]; adds the catalog gradient into dEhat [V, d] (overwrite=True: dEhat is a scratch
+        buffer that may be stored to directly)."""
         Z, ldz, Ehat, shat = tape['Z'], tape['ldz'], tape['Ehat'], tape['shat']
         B, (V, d) = batch.B, Ehat.shape
+        umma = tape['umma']
+        Zlo = torch.empty_like(Z) if umma else None
         if mode == 'loss':
-            ops.ce_rows_bwd(Z, ldz, batch.labels, tape['lse'], gout.reshape(1), tape['scale'], B, V, False)
+            ops.ce_rows_bwd(Z, ldz, batch.labels, tape['lse'], gout.reshape(1), tape['scale'], B, V, False, Zlo)
             dZ = Z
         else:
             dZ = torch.empty_like(Z)
-            ops.logp_bwd(Z, ldz, gout, gout.stride(0), tape['scale'], B, V, dZ, ldz)
+            ops.logp_bwd(Z, ldz, gout, gout.stride(0), tape['scale'], B, V, dZ, ldz, Zlo)
         dshat = torch.zeros(B, d, dtype=torch.float32, device=Z.device)
+        if umma:
+            nkb = (V + 31) // 32
+            split = max(1, min(nkb, 296 // ((B + 127) // 128)))
+            ops.umma_gemm(1, B, d, V, dZ, Zlo, ldz, tape['Ehi'], tape['Elo'], d, dshat, d, accumulate=True, split_k=split)
+            ops.umma_gemm(2, V, d, B, dZ, Zlo, ldz, tape['sh'], tape['sl'], d, dEhat, d, accumulate=not overwrite)
+            return dshat
         ops.gemm(B, d, V, dZ, ldz, 1, Ehat, d, 1, dshat, d, accumulate=True, split_k=0)          # dZ @ Ehat
         ops.gemm(V, d, B, dZ, 1, ldz, shat, tape['ld_s'], 1, dEhat, d, accumulate=True, split_k=0)  # dZ^T @ shat
         return dshat

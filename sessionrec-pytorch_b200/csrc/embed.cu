@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(ROW_THREADS) renorm_rows_kernel(float* __restr
 template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) catalog_prep_fwd_kernel(float* __restrict__ E, int V, int d, int mode,
                                                                        float max_norm, float* __restrict__ Ehat,
-                                                                       float* __restrict__ enorm) {
+                                                                       float* __restrict__ enorm, float* __restrict__ Ehi,
+                                                                       float* __restrict__ Elo) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
@@ -116,6 +117,12 @@ __global__ void __launch_bounds__(ROW_THREADS) catalog_prep_fwd_kernel(float* __
     }
     float n = row_normalize(x, y, mode);
     row_store(y, Ehat + (long long)v * d, d, lane);
+    if (Ehi) {
+      RowVec<NC> hi, lo;
+      row_split_tf32(y, hi, lo);
+      row_store(hi, Ehi + (long long)v * d, d, lane);
+      row_store(lo, Elo + (long long)v * d, d, lane);
+    }
     if (lane == 0) enorm[v] = n;
   }
 }
@@ -199,11 +206,11 @@ extern "C" int srk_renorm_rows(float* E, const int* uid, int U, int d, float max
 }
 
 extern "C" int srk_catalog_prep_fwd(float* E, int V, int d, int norm_mode, float max_norm, float* Ehat, float* enorm,
-                                    void* stream) {
+                                    float* Ehat_hi, float* Ehat_lo, void* stream) {
   SRK_TRY(srk_check_dim(d));
   SRK_REQUIRE(norm_mode == SRK_NORM_L2 || norm_mode == SRK_NORM_EPS, "catalog_prep: norm_mode must be L2 or EPS");
   SRK_DISPATCH_NC(d, (catalog_prep_fwd_kernel<NC><<<row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         E, V, d, norm_mode, max_norm, Ehat, enorm)));
+                         E, V, d, norm_mode, max_norm, Ehat, enorm, Ehat_hi, Ehat_lo)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

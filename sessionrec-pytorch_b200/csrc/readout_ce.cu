@@ -175,25 +175,35 @@ __global__ void __launch_bounds__(512) ce_rows_fwd_kernel(float* __restrict__ Z,
 
 __global__ void __launch_bounds__(512) ce_rows_bwd_kernel(float* __restrict__ Z, long long ldz, const int* __restrict__ labels,
                                                           const float* __restrict__ lse, const float* __restrict__ gscale,
-                                                          float scale, int B, int V, int z_is_logp) {
+                                                          float scale, int B, int V, int z_is_logp,
+                                                          float* __restrict__ Zlo) {
   float* z = Z + (long long)blockIdx.x * ldz;
+  float* zl = Zlo ? Zlo + (long long)blockIdx.x * ldz : nullptr;
   const float l = z_is_logp ? 0.f : lse[blockIdx.x];
   const float c = gscale[0] * scale / (float)B;
   const int lab = labels[blockIdx.x];
   for (int j = threadIdx.x; j < V; j += blockDim.x) {
     float p = expf(z[j] - l);
-    z[j] = c * (p - (j == lab ? 1.f : 0.f));
+    float g = c * (p - (j == lab ? 1.f : 0.f));
+    if (zl) {                                   // TF32 split for the tcgen05 backward GEMMs
+      float h = __uint_as_float(__float_as_uint(g) & 0xFFFFE000u);
+      z[j] = h;
+      zl[j] = g - h;
+    } else {
+      z[j] = g;
+    }
   }
 }
 
 __global__ void __launch_bounds__(512) logp_bwd_kernel(const float* __restrict__ LP, long long ldlp,
                                                        const float* __restrict__ G, long long ldg, float scale, int V,
-                                                       float* __restrict__ DZ, long long lddz) {
+                                                       float* __restrict__ DZ, long long lddz, float* __restrict__ DZlo) {
   __shared__ float red[16];
   __shared__ float total;
   const float* lp = LP + (long long)blockIdx.x * ldlp;
   const float* g = G + (long long)blockIdx.x * ldg;
   float* dz = DZ + (long long)blockIdx.x * lddz;
+  float* dzl = DZlo ? DZlo + (long long)blockIdx.x * lddz : nullptr;
   float s = 0.f;
   for (int j = threadIdx.x; j < V; j += blockDim.x) s += g[j];
   s = warp_sum(s);
@@ -206,7 +216,16 @@ __global__ void __launch_bounds__(512) logp_bwd_kernel(const float* __restrict__
   }
   __syncthreads();
   const float rs = total;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) dz[j] = scale * (g[j] - expf(lp[j]) * rs);
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    float v = scale * (g[j] - expf(lp[j]) * rs);
+    if (dzl) {
+      float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      dz[j] = h;
+      dzl[j] = v - h;
+    } else {
+      dz[j] = v;
+    }
+  }
 }
 
 inline int row_grid(long long rows) {
@@ -250,17 +269,17 @@ extern "C" int srk_ce_rows_fwd(float* Z, long long ldz, const int* labels, int B
 }
 
 extern "C" int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale,
-                               float scale, int B, int V, int z_is_logp, void* stream) {
+                               float scale, int B, int V, int z_is_logp, float* Zlo, void* stream) {
   if (B <= 0) return SRK_OK;
-  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp);
+  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp, Zlo);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
 
 extern "C" int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V,
-                            float* DZ, long long lddz, void* stream) {
+                            float* DZ, long long lddz, float* DZlo, void* stream) {
   if (B <= 0) return SRK_OK;
-  logp_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(LP, ldlp, G, ldg, scale, V, DZ, lddz);
+  logp_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(LP, ldlp, G, ldg, scale, V, DZ, lddz, DZlo);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -88,6 +88,18 @@ __device__ __forceinline__ void row_dropout(RowVec<NC>& r, const DropCfg& dc, lo
   }
 }
 
+// hi = r with the 13 low mantissa bits cleared (exactly TF32-representable), lo = r - hi (exact in fp32)
+template <int NC>
+__device__ __forceinline__ void row_split_tf32(const RowVec<NC>& r, RowVec<NC>& hi, RowVec<NC>& lo) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    hi.v[c].x = __uint_as_float(__float_as_uint(r.v[c].x) & 0xFFFFE000u); lo.v[c].x = r.v[c].x - hi.v[c].x;
+    hi.v[c].y = __uint_as_float(__float_as_uint(r.v[c].y) & 0xFFFFE000u); lo.v[c].y = r.v[c].y - hi.v[c].y;
+    hi.v[c].z = __uint_as_float(__float_as_uint(r.v[c].z) & 0xFFFFE000u); lo.v[c].z = r.v[c].z - hi.v[c].z;
+    hi.v[c].w = __uint_as_float(__float_as_uint(r.v[c].w) & 0xFFFFE000u); lo.v[c].w = r.v[c].w - hi.v[c].w;
+  }
+}
+
 // y = norm_mode(x): returns the L2 norm of x.  y may alias x.
 template <int NC>
 __device__ __forceinline__ float row_normalize(const RowVec<NC>& x, RowVec<NC>& y, int mode) {

@@ -1,0 +1,375 @@
+// tcgen05 (5th-gen tensor core) GEMM for the catalog contraction, fp32-faithful through a 3xTF32 split.
+//
+//   C[M, N] (op)= alpha * A * B      with A = A_hi + A_lo, B = B_hi + B_lo (both halves exactly TF32-representable)
+//   acc = A_hi B_hi + A_hi B_lo + A_lo B_hi      (fp32 accumulation in TMEM; the dropped A_lo B_lo term is ~2^-22)
+//
+// Three operand forms cover the scoring head of one training step (srgnn.py:146, niser.py:152, msgifsr.py:308 and
+// their autograd):
+//   form NT:  A[M, K] row-major, B[N, K] row-major     Z  = s E^T      (both operands K-major)
+//   form NN:  A[M, K] row-major, B[K, N] row-major     dS = dZ E       (B is MN-major)
+//   form TN:  A[K, M] row-major, B[K, N] row-major     dE = dZ^T s     (A and B are MN-major)
+//
+// Structure (one 128 x BN output tile per CTA, cta_group::1, UMMA M = 128, N = BN <= 256, K = 8 per MMA):
+//   warp 0   TMA producer: cp.async.bulk.tensor.2d boxes of 128-byte rows (SWIZZLE_128B) into a STAGES-deep ring,
+//            completion on an mbarrier (expect_tx)
+//   warp 1   TMEM allocation + single-thread tcgen05.mma issue (3 MMAs per k-step), tcgen05.commit releases the
+//            smem stage and finally signals the epilogue
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), alpha, masked store / atomicAdd (split-K)
+// Shared-memory operand layouts are the canonical UMMA SWIZZLE_128B layouts for K-major and MN-major operands
+// (8 rows x 128 B atoms, 1024 B apart), which is exactly what a TMA box with a 128-byte inner extent writes.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (TMEM lanes)
+constexpr int KB = 32;           // floats per k-block = one 128-byte swizzle row
+constexpr int UK = 8;            // TF32 UMMA K
+constexpr int THREADS = 192;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, `rows` rows of pitch `ld` floats; box = 32 floats x box_rows.
+int make_map(CUtensorMap* m, const float* base, long long inner, long long rows, long long ld, int box_rows, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  SRK_REQUIRE(enc != nullptr, "umma_gemm: cuTensorMapEncodeTiled is not available from this driver");
+  SRK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && ld % 4 == 0, "umma_gemm: operands must be 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRK_REQUIRE(r == CUDA_SUCCESS, "umma_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return SRK_OK;
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, version 1 (Blackwell).  K-major operands use SWIZZLE_128B (layout type 2: 8-row x
+// 128 B atoms, SBO = 1024); MN-major TF32 operands must use SWIZZLE_128B_BASE32B (layout type 1: 32-byte swizzle
+// granules, 4 K-rows x 128 B atoms, i.e. what TMA's SWIZZLE_128B_ATOM_32B writes).  lbo / sbo in bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+struct UmmaParams {
+  int M, N, K;            // logical problem
+  int a_mn, b_mn;         // operand major-ness (0 = K-major, 1 = MN-major)
+  int BN;                 // N tile (multiple of 16, <= 256)
+  int kb_per_split;       // k-blocks per grid.z slice
+  int stages;
+  float* C;
+  long long ldc;
+  float alpha;
+  int atomic;             // 1: atomicAdd epilogue (split-K / accumulate), 0: plain store
+  uint32_t idesc;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                 const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], acc_bar;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * p.BN;
+  const int nkb_total = (p.K + KB - 1) / KB;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(nkb_total, kb0 + p.kb_per_split);
+  const int nkb = kb1 - kb0;
+
+  const uint32_t a_bytes = BM * 128;                 // one of A_hi / A_lo for one k-block
+  const uint32_t b_bytes = (uint32_t)p.BN * 128;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer =====
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % p.stages;
+          const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          uint8_t *ah = st, *al = st + a_bytes, *bh = st + 2 * a_bytes, *bl = st + 2 * a_bytes + b_bytes;
+          mbar_expect_tx(&full_bar[s], stage_bytes);
+          const int k0 = (kb0 + i) * KB;
+          if (!p.a_mn) {
+            tma_load_2d(ah, &mAh, &full_bar[s], k0, m0);
+            tma_load_2d(al, &mAl, &full_bar[s], k0, m0);
+          } else {
+            for (int c = 0; c < BM / 32; ++c) {
+              tma_load_2d(ah + c * 4096, &mAh, &full_bar[s], m0 + c * 32, k0);
+              tma_load_2d(al + c * 4096, &mAl, &full_bar[s], m0 + c * 32, k0);
+            }
+          }
+          if (!p.b_mn) {
+            tma_load_2d(bh, &mBh, &full_bar[s], k0, n0);
+            tma_load_2d(bl, &mBl, &full_bar[s], k0, n0);
+          } else {
+            for (int c = 0; c < p.BN / 32; ++c) {
+              tma_load_2d(bh + c * 4096, &mBh, &full_bar[s], n0 + c * 32, k0);
+              tma_load_2d(bl + c * 4096, &mBl, &full_bar[s], n0 + c * 32, k0);
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ===== MMA issuer =====
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % p.stages;
+          const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t ah = st, al = st + a_bytes, bh = st + 2 * a_bytes, bl = st + 2 * a_bytes + b_bytes;
+#pragma unroll
+          for (int ks = 0; ks < KB / UK; ++ks) {
+            // K-major: advance 32 bytes inside the 128-byte swizzle row; MN-major: advance one 8-row atom (1024 B)
+            const uint32_t aoff = p.a_mn ? ks * 1024 : ks * 32;
+            const uint32_t boff = p.b_mn ? ks * 1024 : ks * 32;
+            const uint64_t dah = p.a_mn ? make_desc(ah + aoff, 4096, 512, 1) : make_desc(ah + aoff, 16, 1024, 2);
+            const uint64_t dal = p.a_mn ? make_desc(al + aoff, 4096, 512, 1) : make_desc(al + aoff, 16, 1024, 2);
+            const uint64_t dbh = p.b_mn ? make_desc(bh + boff, 4096, 512, 1) : make_desc(bh + boff, 16, 1024, 2);
+            const uint64_t dbl = p.b_mn ? make_desc(bl + boff, 4096, 512, 1) : make_desc(bl + boff, 16, 1024, 2);
+            umma_tf32(tmem_base, dah, dbh, p.idesc, (i | ks) ? 1u : 0u);
+            umma_tf32(tmem_base, dah, dbl, p.idesc, 1u);
+            umma_tf32(tmem_base, dal, dbh, p.idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);          // frees this smem stage once the MMAs above have read it
+        }
+        umma_commit(&acc_bar);                 // accumulator complete
+      }
+    } else {
+      // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+      const int q = warp & 3;
+      mbar_wait(&acc_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + q * 32 + lane;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (m < p.M) {
+          float* crow = p.C + (long long)m * p.ldc + n0 + c0;
+          const int nvalid = min(32, min(p.BN - c0, p.N - n0 - c0));
+          if (p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) atomicAdd(crow + j, p.alpha * __uint_as_float(r[j]));
+          } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(crow + j) =
+                  make_float4(p.alpha * __uint_as_float(r[j]), p.alpha * __uint_as_float(r[j + 1]),
+                              p.alpha * __uint_as_float(r[j + 2]), p.alpha * __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) crow[j] = p.alpha * __uint_as_float(r[j]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float* __restrict__ hi,
+                                  float* __restrict__ lo, long long ldo) {
+  long long total = (long long)rows * cols;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    long long r = t / cols;
+    int c = (int)(t - r * cols);
+    float x = X[r * ldx + c];
+    float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    hi[r * ldo + c] = h;
+    lo[r * ldo + c] = x - h;
+  }
+}
+
+}  // namespace
+
+// form: 0 = NT (A[M,K], B[N,K]), 1 = NN (A[M,K], B[K,N]), 2 = TN (A[K,M], B[K,N]).  All row-major with pitches lda / ldb.
+extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, const float* Alo, long long lda,
+                             const float* Bhi, const float* Blo, long long ldb, float* C, long long ldc, float alpha,
+                             int accumulate, int split_k, void* stream) {
+  SRK_REQUIRE(form >= 0 && form <= 2, "umma_gemm: bad form %d", form);
+  if (M <= 0 || N <= 0) return SRK_OK;
+  SRK_REQUIRE(K > 0, "umma_gemm: K must be positive");
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = form == 2;
+  p.b_mn = form != 0;
+  // N tile: the catalog dimension is tiled by 128; an embedding-dim N must fit one tile (multiple of 32 for the
+  // MN-major 32-float chunks, <= 256)
+  if (form == 0) {
+    p.BN = N >= 128 ? 128 : ((N + 15) / 16) * 16;
+  } else {
+    p.BN = ((N + 31) / 32) * 32;
+  }
+  SRK_REQUIRE(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "umma_gemm: N tile %d unsupported", p.BN);
+  SRK_REQUIRE(form == 0 || N <= 256, "umma_gemm: N = %d > 256 needs N tiling for MN-major B (not built)", N);
+  const int nkb = (K + KB - 1) / KB;
+  int S = split_k < 1 ? 1 : split_k;
+  if (S > nkb) S = nkb;
+  SRK_REQUIRE(S == 1 || accumulate, "umma_gemm: split-K needs accumulate mode");
+  p.kb_per_split = (nkb + S - 1) / S;
+  S = (nkb + p.kb_per_split - 1) / p.kb_per_split;
+  p.C = C; p.ldc = ldc; p.alpha = alpha;
+  p.atomic = accumulate ? 1 : 0;
+  p.tmem_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
+  // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+            ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)p.BN * 128;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages > p.kb_per_split) stages = p.kb_per_split;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024;
+
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (!p.a_mn) {          // A[M, K]: inner = K
+    SRK_TRY(make_map(&mAh, Ahi, K, M, lda, BM, false));
+    SRK_TRY(make_map(&mAl, Alo, K, M, lda, BM, false));
+  } else {                // A[K, M]: inner = M, boxes of 32 (m) x 32 (k)
+    SRK_TRY(make_map(&mAh, Ahi, M, K, lda, KB, true));
+    SRK_TRY(make_map(&mAl, Alo, M, K, lda, KB, true));
+  }
+  if (!p.b_mn) {          // B[N, K]
+    SRK_TRY(make_map(&mBh, Bhi, K, N, ldb, p.BN, false));
+    SRK_TRY(make_map(&mBl, Blo, K, N, ldb, p.BN, false));
+  } else {                // B[K, N]
+    SRK_TRY(make_map(&mBh, Bhi, N, K, ldb, KB, true));
+    SRK_TRY(make_map(&mBl, Blo, N, K, ldb, KB, true));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    attr_set = true;
+  }
+  dim3 grid(srk_cdiv(N, p.BN), srk_cdiv(M, BM), S);
+  SRK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "umma_gemm: grid too large");
+  umma_gemm_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, p);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_split_tf32(const float* X, long long ldx, int rows, int cols, float* hi, float* lo, long long ldo,
+                              void* stream) {
+  long long total = (long long)rows * cols;
+  if (total <= 0) return SRK_OK;
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  split_tf32_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, ldx, rows, cols, hi, lo, ldo);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}

@@ -245,7 +245,10 @@ class MSGIFSR(SessRecModule):
         # (msgifsr.py:247,276).  Rows are independent, so one pre-pass over the catalog does both.
         Ehat = torch.empty_like(E)
         enorm = torch.empty(V, dtype=torch.float32, device=dev)
-        ops.catalog_prep_fwd(E, NORM_L2, 1.0, Ehat, enorm)
+        Ehi = Elo = None
+        if self.use_tensor_cores and d <= 256:
+            Ehi, Elo = torch.empty_like(E), torch.empty_like(E)
+        ops.catalog_prep_fwd(E, NORM_L2, 1.0, Ehat, enorm, Ehi, Elo)
         t = batch.types[1]
         N = t['N']
         dc_e = ops.drop_cfg(p, SITE_EMBED + 1, seed) if p > 0 else None
@@ -274,7 +277,7 @@ class MSGIFSR(SessRecModule):
         ops.rownorm_fwd(s, d, B, d, NORM_L2, shat, d, rn_s)
         tape.update(X=X, rnX=rnX, dc_e=dc_e, ltapes=ltapes, F=F, u=u, v=v, e=e, ms=ms, sr_in=sr_in, s=s, rn_s=rn_s,
                     enorm=enorm)
-        out = self._head_fwd(shat, d, Ehat, SCALE, batch, mode, tape)
+        out = self._head_fwd(shat, d, Ehat, SCALE, batch, mode, tape, Ehi, Elo)
         return out, (tape if need_grad else None)
 
     def _bwd(self, tape, gout, gflat):
@@ -285,8 +288,11 @@ class MSGIFSR(SessRecModule):
         dev = E.device
         g = lambda name: fp.view(gflat, name)          # noqa: E731
         gE = g('embeddings.weight')
-        dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
-        dshat = self._head_bwd(tape, batch, tape['mode'], gout, dEhat)
+        if tape['umma']:
+            dEhat = torch.empty(V, d, dtype=torch.float32, device=dev)
+        else:
+            dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
+        dshat = self._head_bwd(tape, batch, tape['mode'], gout, dEhat, overwrite=True)
         ops.catalog_prep_bwd(E, tape['Ehat'], tape['enorm'], dEhat, NORM_L2, gE)
         ds = torch.empty(B, d, dtype=torch.float32, device=dev)
         ops.rownorm_bwd(tape['s'], d, tape['shat'], d, tape['rn_s'], dshat, d, B, d, NORM_L2, ds, d)

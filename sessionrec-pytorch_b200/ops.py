@@ -73,6 +73,16 @@ def mm_tn(A, Bm, C, K=None, lda=None, ldb=None, ldc=None, b_idx=None, alpha=1.0,
          C.stride(0) if ldc is None else ldc, b_idx=b_idx, alpha=alpha, accumulate=accumulate, split_k=0)
 
 
+def umma_gemm(form, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, alpha=1.0, accumulate=False, split_k=1):
+    _need_cuda(Ahi, Alo, Bhi, Blo, C)
+    _call('srk_umma_gemm', form, M, N, K, ptr(Ahi), ptr(Alo), lda, ptr(Bhi), ptr(Blo), ldb, ptr(C), ldc, float(alpha),
+          int(bool(accumulate)), int(split_k))
+
+
+def split_tf32(X, ldx, rows, cols, hi, lo, ldo):
+    _call('srk_split_tf32', ptr(X), ldx, rows, cols, ptr(hi), ptr(lo), ldo)
+
+
 # ---- embedding ---------------------------------------------------------------------------------------------
 
 def embed_gather_fwd(E, iid, P, d, mode, dc, X, rnorm, x_first=None):
@@ -85,9 +95,9 @@ def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE):
           _dref(dc), ptr(rnorm), ptr(dX), ptr(dX_first), ptr(dE))
 
 
-def catalog_prep_fwd(E, mode, max_norm, Ehat, enorm):
+def catalog_prep_fwd(E, mode, max_norm, Ehat, enorm, Ehi=None, Elo=None):
     V, d = E.shape
-    _call('srk_catalog_prep_fwd', ptr(E), V, d, mode, float(max_norm), ptr(Ehat), ptr(enorm))
+    _call('srk_catalog_prep_fwd', ptr(E), V, d, mode, float(max_norm), ptr(Ehat), ptr(enorm), ptr(Ehi), ptr(Elo))
 
 
 def catalog_prep_bwd(E, Ehat, enorm, dEhat, mode, dE):
@@ -150,12 +160,12 @@ def ce_rows_fwd(Z, ldz, labels, B, V, write_logp, lse, nll):
     _call('srk_ce_rows_fwd', ptr(Z), ldz, ptr(labels), B, V, int(write_logp), ptr(lse), ptr(nll))
 
 
-def ce_rows_bwd(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp):
-    _call('srk_ce_rows_bwd', ptr(Z), ldz, ptr(labels), ptr(lse), ptr(gscale), float(scale), B, V, int(z_is_logp))
+def ce_rows_bwd(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp, Zlo=None):
+    _call('srk_ce_rows_bwd', ptr(Z), ldz, ptr(labels), ptr(lse), ptr(gscale), float(scale), B, V, int(z_is_logp), ptr(Zlo))
 
 
-def logp_bwd(LP, ldlp, G, ldg, scale, B, V, DZ, lddz):
-    _call('srk_logp_bwd', ptr(LP), ldlp, ptr(G), ldg, float(scale), B, V, ptr(DZ), lddz)
+def logp_bwd(LP, ldlp, G, ldg, scale, B, V, DZ, lddz, DZlo=None):
+    _call('srk_logp_bwd', ptr(LP), ldlp, ptr(G), ldg, float(scale), B, V, ptr(DZ), lddz, ptr(DZlo))
 
 
 # ---- GGNN ----------------------------------------------------------------------------------------------------

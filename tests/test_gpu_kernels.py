@@ -209,6 +209,9 @@ def test_ce_rows(ops, V):
     (torch.log_softmax(Zr, -1) * G).sum().backward()
     DZ = torch.empty(B, ldz, device=DEV)
     ops.logp_bwd(Zd, ldz, G.to(DEV), V, 1.5, B, V, DZ, ldz)
+    DZh, DZl = torch.empty(B, ldz, device=DEV), torch.empty(B, ldz, device=DEV)
+    ops.logp_bwd(Zd, ldz, G.to(DEV), V, 1.5, B, V, DZh, ldz, DZl)
+    assert torch.equal((DZh + DZl)[:, :V], DZ[:, :V]) and bool(((DZh.view(torch.int32) & 0x1FFF) == 0)[:, :V].all())
     assert_grad_close('logp_bwd', DZ[:, :V], 1.5 * Zr.grad, rtol=1e-5)
 
 

@@ -1,0 +1,76 @@
+"""tcgen05 3xTF32 catalog GEMM (csrc/umma_gemm.cu) against fp64 on the CPU, all three operand forms, ragged sizes."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def ops(pkg):
+    from sessionrec_pytorch_b200 import ops as o
+    return o
+
+
+def _r(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g).float()
+
+
+def _split(ops, X, ld):
+    rows, cols = X.shape
+    hi = torch.zeros(rows, ld, device=DEV)
+    lo = torch.zeros(rows, ld, device=DEV)
+    Xd = torch.zeros(rows, ld, device=DEV)
+    Xd[:, :cols] = X.to(DEV)
+    ops.split_tf32(Xd, ld, rows, cols, hi, lo, ld)
+    torch.cuda.synchronize()
+    assert torch.equal((hi + lo)[:, :cols].cpu(), X), 'hi + lo must reconstruct x exactly'
+    return hi, lo
+
+
+def _check(name, got, ref):
+    err = float((got.double().cpu() - ref).abs().max())
+    scale = float(ref.abs().max())
+    print(f'{name}: max|d| = {err:.3e}, max|ref| = {scale:.3e}, rel = {err / scale:.2e}')
+    assert err <= 1e-5 * scale, f'{name}: rel err {err / scale:.2e}'
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 32), (128, 128, 96), (512, 1001, 96), (200, 300, 40), (64, 2000, 256), (512, 96, 64)])
+def test_umma_nt(ops, M, N, K):
+    A, B = _r(M, K), _r(N, K, seed=1)
+    ldk = (K + 3) // 4 * 4
+    Ah, Al = _split(ops, A, ldk)
+    Bh, Bl = _split(ops, B, ldk)
+    ldc = (N + 3) // 4 * 4
+    C = torch.full((M, ldc), 7.0, device=DEV)
+    ops.umma_gemm(0, M, N, K, Ah, Al, ldk, Bh, Bl, ldk, C, ldc, alpha=12.0)
+    torch.cuda.synchronize()
+    _check(f'nt {M}x{N}x{K}', C[:, :N], 12.0 * (A.double() @ B.double().t()))
+    assert bool((C[:, N:] == 7.0).all()), 'padding columns must stay untouched'
+
+
+@pytest.mark.parametrize('M,N,K,S', [(128, 96, 64, 1), (512, 96, 1001, 5), (200, 64, 4099, 7), (512, 256, 700, 3)])
+def test_umma_nn(ops, M, N, K, S):
+    """dS = dZ @ E: A[M, K] K-major, B[K, N] MN-major, split-K with atomic accumulation."""
+    A, B = _r(M, K), _r(K, N, seed=2)
+    lda = (K + 3) // 4 * 4
+    Ah, Al = _split(ops, A, lda)
+    Bh, Bl = _split(ops, B, N)
+    C = torch.ones(M, N, device=DEV)
+    ops.umma_gemm(1, M, N, K, Ah, Al, lda, Bh, Bl, N, C, N, alpha=0.5, accumulate=True, split_k=S)
+    torch.cuda.synchronize()
+    _check(f'nn {M}x{N}x{K}', C, 1.0 + 0.5 * (A.double() @ B.double()))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 96, 32), (1001, 96, 512), (4099, 64, 200), (300, 256, 70)])
+def test_umma_tn(ops, M, N, K):
+    """dE = dZ^T @ s: A[K, M] and B[K, N] both MN-major."""
+    A, B = _r(K, M), _r(K, N, seed=3)
+    lda = (M + 3) // 4 * 4
+    Ah, Al = _split(ops, A, lda)
+    Bh, Bl = _split(ops, B, N)
+    C = torch.zeros(M, N, device=DEV)
+    ops.umma_gemm(2, M, N, K, Ah, Al, lda, Bh, Bl, N, C, N)
+    torch.cuda.synchronize()
+    _check(f'tn {M}x{N}x{K}', C, A.double().t() @ B.double())
