@@ -79,11 +79,12 @@ int srk_split_tf32(const float* X, long long ldx, int rows, int cols, float* hi,
  * once-normalised rows that feed the GGNN layers (niser.py:136). */
 int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d, int norm_mode, const srk_dropout* drop,
                          float* X, float* rnorm, float* x_first, void* stream);
-/* Backward: dE[u] += sum over the occurrences i of item u of d(dropped row i), deterministic: `perm`
- * lists positions sorted by item id, uoff[U+1] delimits each distinct item, uid[U] is its id.  Replaces
+/* Backward: dE[u] += sum over the occurrences i of item u of d(dropped row i): `perm` lists the P gather positions
+ * sorted by item id, uoff[U+1] delimits each distinct item, uid[U] is its id.  Load-balanced over chunks of 8
+ * occurrences; only items cut by a chunk boundary use atomics.  Replaces
  * `embedding_dense_backward` (autograd of srgnn.py:133). dX_first may be NULL. */
 int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid, int U,
-                          int d, int norm_mode, const srk_dropout* drop, const float* rnorm, const float* dX,
+                          int P, int d, int norm_mode, const srk_dropout* drop, const float* rnorm, const float* dX,
                           const float* dX_first, float* dE, void* stream);
 
 /* ---- catalog pre-pass (K6a) -------------------------------------------------------------------------
@@ -221,6 +222,18 @@ int srk_segmean_bwd(const float* dHpre, const int* seg, int B, int d, float* dX,
 int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                   const long long* seg_off, const float* seg_decay, int n_seg, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, void* stream);
+
+/* ---- native training step (MSGIFSR order 1, extra=False): utils/train.py:95-101 around msgifsr.py:241-323 ----
+ * zero_grad + forward + nll_loss + backward (+ Adam) enqueued by ONE host call from a caller-provided device
+ * workspace (srk_msgifsr_workspace_bytes).  slot_off_host: float offsets of the parameters inside the flat buffers,
+ * order documented in csrc/step.cu.  phase 0 = all, 1 = up to the gradients (data parallel: all-reduce, then) 2 = Adam. */
+long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int d, int L);
+int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
+                           const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed,
+                           int use_umma, void* workspace, long long workspace_bytes, const float* one_dev, float* loss_out,
+                           int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat, const long long* seg_off_dev,
+                           const float* seg_decay_dev, int n_seg, float lr, float beta1, float beta2, float eps,
+                           int adam_step, float grad_scale, int phase, void* stream);
 
 /* ---- native batch builder (host; next-row: utils/data/collate.py:61-85,87-217,219-256) ---------------------------
  * Sessions are given as a flat item array + offsets. kind 0 = session graph (weights, self-loop rule), kind 1 =

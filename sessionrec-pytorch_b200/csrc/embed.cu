@@ -37,22 +37,57 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_fwd_kernel(const float* __
   }
 }
 
+// Embedding-gradient scatter-add, load-balanced: the occurrence list is sorted by item id (perm / uoff / uid from the
+// batch builder); every warp takes SCATTER_CHUNK consecutive occurrences, so a hot item (Zipf head, ~10% of a batch)
+// is spread over many warps instead of serialising one.  Runs of one item that lie entirely inside a warp's chunk are
+// added with a plain read-modify-write (deterministic); only items cut by a chunk boundary use atomicAdd.
+constexpr int SCATTER_CHUNK = 8;
+
+template <int NC>
+__device__ __forceinline__ void scatter_flush(const RowVec<NC>& acc, float* __restrict__ row, int d, int lane, bool whole) {
+  if (whole) {
+    row_add_store(acc, row, d, lane);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      int col = (c * 32 + lane) * 4;
+      if (col < d) {
+        atomicAdd(row + col, acc.v[c].x); atomicAdd(row + col + 1, acc.v[c].y);
+        atomicAdd(row + col + 2, acc.v[c].z); atomicAdd(row + col + 3, acc.v[c].w);
+      }
+    }
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* __restrict__ E, const int* __restrict__ perm,
                                                                   const int* __restrict__ uoff, const int* __restrict__ uid,
-                                                                  int U, int d, int mode, DropCfg dc,
+                                                                  int U, int P, int d, int mode, DropCfg dc,
                                                                   const float* __restrict__ rnorm,
                                                                   const float* __restrict__ dX,
                                                                   const float* __restrict__ dX_first,
                                                                   float* __restrict__ dE) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < U; u += warps) {
-    const int item = uid[u];
+  const int nchunks = (P + SCATTER_CHUNK - 1) / SCATTER_CHUNK;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nchunks; w += warps) {
+    const int j0 = w * SCATTER_CHUNK, j1 = min(P, j0 + SCATTER_CHUNK);
+    int lo = 0, hi = U - 1;                    // distinct item u with uoff[u] <= j0 < uoff[u + 1]
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (uoff[mid] <= j0) lo = mid; else hi = mid - 1;
+    }
+    int u = lo;
     RowVec<NC> erow, acc;
-    row_load(erow, E + (long long)item * d, d, lane);
+    row_load(erow, E + (long long)uid[u] * d, d, lane);
     row_zero(acc);
-    for (int j = uoff[u]; j < uoff[u + 1]; ++j) {
+    for (int j = j0; j < j1; ++j) {
+      while (j >= uoff[u + 1]) {
+        scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, uoff[u] >= j0);
+        ++u;
+        row_load(erow, E + (long long)uid[u] * d, d, lane);
+        row_zero(acc);
+      }
       const int i = perm[j];
       RowVec<NC> x = erow, y, dy, dx;
       row_dropout(x, dc, i, d, lane);
@@ -76,7 +111,7 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
       row_dropout(dx, dc, i, d, lane);
       row_axpy(acc, 1.f, dx);
     }
-    row_add_store(acc, dE + (long long)item * d, d, lane);
+    scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, uoff[u] >= j0 && uoff[u + 1] <= j1);
   }
 }
 
@@ -184,14 +219,15 @@ extern "C" int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d
 }
 
 extern "C" int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid,
-                                     int U, int d, int norm_mode, const srk_dropout* drop, const float* rnorm,
+                                     int U, int P, int d, int norm_mode, const srk_dropout* drop, const float* rnorm,
                                      const float* dX, const float* dX_first, float* dE, void* stream) {
   (void)iid;
   SRK_TRY(srk_check_dim(d));
-  if (U <= 0) return SRK_OK;
+  if (U <= 0 || P <= 0) return SRK_OK;
   DropCfg dc = make_drop(drop);
-  SRK_DISPATCH_NC(d, (scatter_bwd_kernel<NC><<<row_grid(U), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         E, perm, uoff, uid, U, d, norm_mode, dc, rnorm, dX, dX_first, dE)));
+  SRK_DISPATCH_NC(d, (scatter_bwd_kernel<NC><<<row_grid((P + SCATTER_CHUNK - 1) / SCATTER_CHUNK), ROW_THREADS, 0,
+                                              (cudaStream_t)stream>>>(E, perm, uoff, uid, U, P, d, norm_mode, dc, rnorm, dX,
+                                                                      dX_first, dE)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

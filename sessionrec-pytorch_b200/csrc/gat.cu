@@ -277,16 +277,29 @@ __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restric
   }
 }
 
-// Waug rows 8d..8d+7 (wl) and wr[8, d]: one CTA per head, one thread per input column.
-__global__ void gat_prep_kernel(const float* __restrict__ W, const float* __restrict__ al, const float* __restrict__ ar,
-                                int d, float* __restrict__ Waug, float* __restrict__ wr) {
-  const int h = blockIdx.x;
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    float sl = 0.f, sr = 0.f;
-    for (int j = 0; j < d; ++j) {
+// Waug rows 8d..8d+7 (wl) and wr[8, d]: CTA per (head, 32-column tile); 8 row groups x 32 columns, smem reduce.
+__global__ void __launch_bounds__(256) gat_prep_kernel(const float* __restrict__ W, const float* __restrict__ al,
+                                                       const float* __restrict__ ar, int d, float* __restrict__ Waug,
+                                                       float* __restrict__ wr) {
+  __shared__ float red[2][8][33];
+  const int h = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
+  float sl = 0.f, sr = 0.f;
+  if (i < d)
+    for (int j = ty; j < d; j += 8) {
       const float w = W[(long long)(h * d + j) * d + i];
       sl = fmaf(al[h * d + j], w, sl);
       sr = fmaf(ar[h * d + j], w, sr);
+    }
+  red[0][ty][tx] = sl;
+  red[1][ty][tx] = sr;
+  __syncthreads();
+  if (ty == 0 && i < d) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      sl += red[0][k][tx];
+      sr += red[1][k][tx];
     }
     Waug[(long long)(H * d + h) * d + i] = sl;
     wr[h * d + i] = sr;
@@ -340,7 +353,7 @@ extern "C" int srk_gat_prep(const float* W, const float* attn_l, const float* at
   SRK_TRY(srk_check_dim(d));
   cudaStream_t st = (cudaStream_t)stream;
   SRK_CUDA(cudaMemcpyAsync(Waug, W, sizeof(float) * (size_t)H * d * d, cudaMemcpyDeviceToDevice, st));
-  gat_prep_kernel<<<H, 256, 0, st>>>(W, attn_l, attn_r, d, Waug, wr);
+  gat_prep_kernel<<<dim3(srk_cdiv(d, 32), H), 256, 0, st>>>(W, attn_l, attn_r, d, Waug, wr);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

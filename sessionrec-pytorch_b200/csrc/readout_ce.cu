@@ -133,7 +133,19 @@ __device__ __forceinline__ MS block_lse(const float* __restrict__ z, int V, MS* 
   MS t;
   t.m = -FLT_MAX;
   t.s = 0.f;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+  // rows are 16-byte aligned (ldz % 4 == 0): 128-bit loads, one max-rescale per 4 elements
+  const int V4 = ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) ? (V >> 2) : 0;
+  const float4* z4 = reinterpret_cast<const float4*>(z);
+  for (int j = threadIdx.x; j < V4; j += blockDim.x) {
+    float4 x = z4[j];
+    float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+    if (mx > t.m) {
+      t.s *= expf(t.m - mx);
+      t.m = mx;
+    }
+    t.s += expf(x.x - t.m) + expf(x.y - t.m) + expf(x.z - t.m) + expf(x.w - t.m);
+  }
+  for (int j = V4 * 4 + threadIdx.x; j < V; j += blockDim.x) {
     float x = z[j];
     if (x > t.m) {
       t.s = t.s * expf(t.m - x) + 1.f;
@@ -169,7 +181,13 @@ __global__ void __launch_bounds__(512) ce_rows_fwd_kernel(float* __restrict__ Z,
   }
   if (write_logp) {
     __syncthreads();   // thread 0 has read z[label] before anyone rewrites it
-    for (int j = threadIdx.x; j < V; j += blockDim.x) z[j] -= l;
+    const int V4 = ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) ? (V >> 2) : 0;
+    float4* z4 = reinterpret_cast<float4*>(z);
+    for (int j = threadIdx.x; j < V4; j += blockDim.x) {
+      float4 x = z4[j];
+      z4[j] = make_float4(x.x - l, x.y - l, x.z - l, x.w - l);
+    }
+    for (int j = V4 * 4 + threadIdx.x; j < V; j += blockDim.x) z[j] -= l;
   }
 }
 
@@ -182,10 +200,28 @@ __global__ void __launch_bounds__(512) ce_rows_bwd_kernel(float* __restrict__ Z,
   const float l = z_is_logp ? 0.f : lse[blockIdx.x];
   const float c = gscale[0] * scale / (float)B;
   const int lab = labels[blockIdx.x];
-  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+  const bool al = (reinterpret_cast<uintptr_t>(z) & 15u) == 0 && (!zl || (reinterpret_cast<uintptr_t>(zl) & 15u) == 0);
+  const int V4 = al ? (V >> 2) : 0;
+  float4* z4 = reinterpret_cast<float4*>(z);
+  float4* zl4 = reinterpret_cast<float4*>(zl);
+  for (int j = threadIdx.x; j < V4; j += blockDim.x) {
+    float4 x = z4[j];
+    const int b = j * 4;
+    float4 g = make_float4(c * (expf(x.x - l) - (b == lab ? 1.f : 0.f)), c * (expf(x.y - l) - (b + 1 == lab ? 1.f : 0.f)),
+                           c * (expf(x.z - l) - (b + 2 == lab ? 1.f : 0.f)), c * (expf(x.w - l) - (b + 3 == lab ? 1.f : 0.f)));
+    if (zl) {                                   // TF32 split for the tcgen05 backward GEMMs
+      float4 h = make_float4(__uint_as_float(__float_as_uint(g.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(g.y) & 0xFFFFE000u),
+                             __uint_as_float(__float_as_uint(g.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(g.w) & 0xFFFFE000u));
+      z4[j] = h;
+      zl4[j] = make_float4(g.x - h.x, g.y - h.y, g.z - h.z, g.w - h.w);
+    } else {
+      z4[j] = g;
+    }
+  }
+  for (int j = V4 * 4 + threadIdx.x; j < V; j += blockDim.x) {
     float p = expf(z[j] - l);
     float g = c * (p - (j == lab ? 1.f : 0.f));
-    if (zl) {                                   // TF32 split for the tcgen05 backward GEMMs
+    if (zl) {
       float h = __uint_as_float(__float_as_uint(g) & 0xFFFFE000u);
       z[j] = h;
       zl[j] = g - h;

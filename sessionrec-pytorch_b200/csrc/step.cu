@@ -1,0 +1,330 @@
+// Native training step: zero_grad + forward + nll_loss + backward + Adam for one batch in ONE host call.
+//
+// This is the body of the reference's training loop (src/utils/train.py:95-101) with the model forward of
+// src/models/msgifsr.py:241-323 (order 1, extra=False) composed in C++ from the same kernels the Python modules
+// drive stage by stage (msgifsr.py::MSGIFSR._fwd/_bwd is the readable twin and the parity reference of this file).
+// All temporaries come from a caller-provided device workspace through a bump allocator; nothing is allocated,
+// nothing synchronises; ~60 kernel launches are enqueued back to back on the given stream.
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int H = SRK_HEADS;
+
+struct Arena {
+  uint8_t* base;
+  size_t cap, off;
+  bool ok;
+  float* f(size_t n) { return reinterpret_cast<float*>(raw(n * sizeof(float))); }
+  uint8_t* raw(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > cap) { ok = false; off = a + bytes; return base; }
+    off = a + bytes;
+    return base + a;
+  }
+};
+
+// batch buffer layout (csrc/batch_builder.cu)
+constexpr int TYPE_TAB = 16, REL_TAB = 80;
+struct BatchView {
+  int B, N, M, U, P;
+  const int *labels, *iid, *seg, *last, *node2seg, *perm, *uoff, *uid;
+  const int *in_ptr, *in_src, *in_eid, *out_ptr, *out_dst, *out_eid;
+};
+
+int parse_batch(const int* dev, const int* hdr, BatchView& b) {
+  SRK_REQUIRE(hdr[0] == 0x53524B31, "step: not a SessionBatch buffer");
+  SRK_REQUIRE(hdr[2] == 1 && hdr[3] == 1, "step: MSGIFSR step needs a ccs batch of order 1");
+  b.B = hdr[1];
+  b.labels = dev + hdr[7];
+  const int* t = hdr + TYPE_TAB;
+  b.N = t[0]; b.U = t[8]; b.P = b.N;
+  b.iid = dev + t[1]; b.seg = dev + t[2]; b.last = dev + t[3]; b.node2seg = dev + t[4];
+  b.perm = dev + t[5]; b.uoff = dev + t[6]; b.uid = dev + t[7];
+  const int* r = hdr + REL_TAB;
+  b.M = r[2];
+  b.in_ptr = dev + r[5]; b.in_src = dev + r[6]; b.in_eid = dev + r[7];
+  b.out_ptr = dev + r[8]; b.out_dst = dev + r[9]; b.out_eid = dev + r[10];
+  return SRK_OK;
+}
+
+int gemm(cudaStream_t st, int M, int N, int K, const float* A, long long sa_m, long long sa_k, const float* Bm, long long sb_k,
+         long long sb_n, float* C, long long ldc, const int* a_idx = nullptr, const int* b_idx = nullptr,
+         const int* c_idx = nullptr, const float* bias = nullptr, float alpha = 1.f, int accumulate = 0) {
+  return srk_gemm(M, N, K, A, sa_m, sa_k, Bm, sb_k, sb_n, C, ldc, a_idx, b_idx, c_idx, bias, alpha, accumulate, 0, st);
+}
+// C[M,N] = X[M,K] W[N,K]^T
+int linear_nt(cudaStream_t st, int M, int N, int K, const float* X, long long lda, const float* W, float* C, long long ldc,
+              const int* a_idx = nullptr, const float* bias = nullptr) {
+  return gemm(st, M, N, K, X, lda, 1, W, 1, K, C, ldc, a_idx, nullptr, nullptr, bias);
+}
+// C[M,N] (+)= A[M,K] Bm[K,N]
+int mm_nn(cudaStream_t st, int M, int N, int K, const float* A, long long lda, const float* Bm, long long ldb, float* C,
+          long long ldc, int accumulate, const int* c_idx = nullptr) {
+  return gemm(st, M, N, K, A, lda, 1, Bm, ldb, 1, C, ldc, nullptr, nullptr, c_idx, nullptr, 1.f, accumulate);
+}
+// C[M,N] += A[K,M]^T Bm[K,N]
+int mm_tn(cudaStream_t st, int M, int N, int K, const float* A, long long lda, const float* Bm, long long ldb, float* C,
+          long long ldc, const int* b_idx = nullptr) {
+  return gemm(st, M, N, K, A, 1, lda, Bm, ldb, 1, C, ldc, nullptr, b_idx, nullptr, nullptr, 1.f, 1);
+}
+
+struct InstRec {
+  srk_gat_inst gi;
+  const float *W, *al, *ar;
+  float *gW, *gal, *gar, *gbias;
+  float *Waug, *wr, *xs, *xd;
+  srk_dropout dcs, dcd;
+  bool drop;
+};
+
+struct LayerRec {
+  const float* in;          // layer input [N, d]
+  float *Hout, *rn;
+  uint8_t* amax;
+  int n_inst;
+  InstRec inst[2];
+  int normalize;
+};
+
+}  // namespace
+
+extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int d, int L) {
+  const long long ldz = (V + 3) / 4 * 4;
+  const long long ldzel = (long long)H * d + H;
+  long long fl = 0;
+  fl += 4LL * V * d + V;                                   // Ehat, Ehi, Elo, dEhat, enorm
+  fl += (long long)N * d + N;                              // X, rnX
+  fl += (long long)L * (2 * ((ldzel + H) * d + 2LL * N * d + N * ldzel + N * H + (long long)(M + 1) * H) + B * d + N * d + N + N * d / 4 + 64);
+  fl += 2LL * N * d + 3LL * B * d + N + 2LL * B + 4LL * B * d + B;    // u, v, e, ms, sr_in, s, shat, rn_s
+  fl += 2LL * B * ldz + 4LL * B * d + 2LL * B + 64;        // Z, Zlo, sh, sl, dshat, ds, lse, nll
+  fl += 2LL * B * d + (long long)N * d;                    // dsr_in, dF
+  // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
+  fl += 2LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
+  return fl * 5 + (1 << 20);                               // floats -> bytes with 25% head-room + alignment slack
+}
+
+// Parameter slots (offsets in floats into the flat parameter / gradient buffers), in this order:
+//   [0] embeddings.weight
+//   per layer l (8 slots each, starting at 1 + 8*l): conv1.intra1.{attn_l, attn_r, bias, fc.weight}, conv2.intra1.{...}
+//   then: readout.fc_u.0.weight, readout.fc_u.0.bias, readout.fc_v.0.weight, readout.fc_e.0.weight, fc_sr.0.weight
+extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
+                                      const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed,
+                                      int use_umma, void* workspace, long long workspace_bytes, const float* one_dev,
+                                      float* loss_out, int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat,
+                                      const long long* seg_off_dev, const float* seg_decay_dev, int n_seg, float lr,
+                                      float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase,
+                                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  BatchView b;
+  SRK_TRY(parse_batch(batch_dev, batch_hdr_host, b));
+  SRK_REQUIRE(L >= 1 && L <= 8, "step: 1..8 layers");
+  const int B = b.B, N = b.N, M = b.M;
+  const long long ldz = (V + 3) / 4 * 4;
+  const int ldzel = H * d + H;
+  const bool umma = use_umma && d <= 256;
+  const bool drop = dropout_p > 0.f;
+  Arena ar{reinterpret_cast<uint8_t*>(workspace), (size_t)workspace_bytes, 0, true};
+  auto P = [&](int slot) { return params + slot_off_host[slot]; };
+  auto G = [&](int slot) { return grads + slot_off_host[slot]; };
+  const int s_ro = 1 + 8 * L;        // readout.fc_u.0.weight, .bias, fc_v, fc_e, fc_sr
+  float* E = P(0);
+  auto dcfg = [&](uint32_t site) { srk_dropout c; c.p = dropout_p; c.site = site; c.seed = seed; return c; };
+
+  // phase: 0 = everything; 1 = zero_grad + forward + backward only (no Adam): lets the caller all-reduce the
+  // gradients; 2 = Adam only.
+  if (phase == 2) {
+    return srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2,
+                         eps, adam_step, grad_scale, st);
+  }
+  SRK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_flat, st));
+
+  // ---- forward -------------------------------------------------------------------------------------------
+  float *Ehat = ar.f((size_t)V * d), *enorm = ar.f(V);
+  float *Ehi = nullptr, *Elo = nullptr;
+  if (umma) { Ehi = ar.f((size_t)V * d); Elo = ar.f((size_t)V * d); }
+  SRK_REQUIRE(ar.ok, "step: workspace too small");
+  SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, st));
+  float *X = ar.f((size_t)N * d), *rnX = ar.f(N);
+  srk_dropout dc_e = dcfg(SRK_SITE_EMBED + 1);
+  SRK_TRY(srk_embed_gather_fwd(E, b.iid, N, d, SRK_NORM_L2, drop ? &dc_e : nullptr, X, rnX, nullptr, st));
+  srk_dropout dc_attn = dcfg(SRK_SITE_GAT_ATTN);
+
+  std::vector<LayerRec> layers(L);
+  const float* h = X;
+  for (int l = 0; l < L; ++l) {
+    LayerRec& R = layers[l];
+    R.in = h;
+    R.normalize = (l == L - 1);
+    R.n_inst = M > 0 ? 2 : 0;
+    srk_gat_inst insts[2];
+    for (int c = 0; c < R.n_inst; ++c) {
+      InstRec& I = R.inst[c];
+      const int base = 1 + 8 * l + 4 * c;        // attn_l, attn_r, bias, fc.weight
+      I.al = P(base); I.ar = P(base + 1); I.W = P(base + 3);
+      I.gal = G(base); I.gar = G(base + 1); I.gbias = G(base + 2); I.gW = G(base + 3);
+      I.Waug = ar.f((size_t)ldzel * d);
+      I.wr = ar.f((size_t)H * d);
+      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, st));
+      const uint32_t slot = (uint32_t)((l * 2 + c) * 3);
+      I.drop = drop;
+      I.xs = const_cast<float*>(h);
+      I.xd = const_cast<float*>(h);
+      if (drop) {
+        I.dcs = dcfg(SRK_SITE_GAT_SRC + 4 * slot);
+        I.dcd = dcfg(SRK_SITE_GAT_DST + 4 * slot);
+        I.xs = ar.f((size_t)N * d);
+        I.xd = ar.f((size_t)N * d);
+        SRK_TRY(srk_dropout_apply(h, I.xs, (long long)N * d, &I.dcs, 0, st));
+        SRK_TRY(srk_dropout_apply(h, I.xd, (long long)N * d, &I.dcd, 0, st));
+      }
+      float* Zel = ar.f((size_t)N * ldzel);
+      float* er = ar.f((size_t)N * H);
+      float* att = ar.f((size_t)(M + 1) * H);
+      SRK_REQUIRE(ar.ok, "step: workspace too small");
+      SRK_TRY(linear_nt(st, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
+      SRK_TRY(linear_nt(st, N, H, d, I.xd, d, I.wr, er, H));
+      srk_gat_inst& g = I.gi;
+      memset(&g, 0, sizeof(g));
+      if (c == 0) {
+        g.in_ptr = b.in_ptr; g.in_src = b.in_src; g.in_eid = b.in_eid;
+        g.out_ptr = b.out_ptr; g.out_dst = b.out_dst; g.out_eid = b.out_eid;
+      } else {            // conv2 runs on the reversed graph: the two CSRs swap roles
+        g.in_ptr = b.out_ptr; g.in_src = b.out_dst; g.in_eid = b.out_eid;
+        g.out_ptr = b.in_ptr; g.out_dst = b.in_src; g.out_eid = b.in_eid;
+      }
+      g.Zel = Zel; g.er = er; g.bias = P(base + 2); g.xdst = I.xd; g.att = att;
+      g.n_src = N; g.n_dst = N; g.n_edges = M;
+      g.attn_site = SRK_SITE_GAT_ATTN + 4 * slot;
+      insts[c] = g;
+    }
+    float* segmean = ar.f((size_t)B * d);
+    R.Hout = ar.f((size_t)N * d);
+    R.rn = ar.f(N);
+    R.amax = ar.raw((size_t)N * d);
+    SRK_REQUIRE(ar.ok, "step: workspace too small");
+    SRK_TRY(srk_segmean_fwd(h, b.seg, B, d, segmean, st));
+    SRK_TRY(srk_gat_aggregate_fwd(insts, R.n_inst, N, d, segmean, b.node2seg, drop ? &dc_attn : nullptr, R.normalize, R.Hout,
+                                  R.rn, R.amax, st));
+    h = R.Hout;
+  }
+  const float* F = h;
+  float *u = ar.f((size_t)N * d), *v = ar.f((size_t)B * d), *e = ar.f(N), *ms = ar.f(2 * (size_t)B);
+  float *sr_in = ar.f(2 * (size_t)B * d), *s = ar.f((size_t)B * d), *shat = ar.f((size_t)B * d), *rn_s = ar.f(B);
+  SRK_REQUIRE(ar.ok, "step: workspace too small");
+  SRK_TRY(linear_nt(st, N, d, d, F, d, P(s_ro), u, d, nullptr, P(s_ro + 1)));
+  SRK_TRY(linear_nt(st, B, d, d, F, d, P(s_ro + 2), v, d, b.last, nullptr));
+  SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, 1, e, ms, sr_in, st));
+  SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
+  SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
+  // scoring head + CE
+  float *Z = ar.f((size_t)B * ldz), *lse = ar.f(B), *nll = ar.f(B);
+  float *sh = nullptr, *sl = nullptr;
+  SRK_REQUIRE(ar.ok, "step: workspace too small");
+  if (umma) {
+    sh = ar.f((size_t)B * d); sl = ar.f((size_t)B * d);
+    SRK_TRY(srk_split_tf32(shat, d, B, d, sh, sl, d, st));
+    SRK_TRY(srk_umma_gemm(0, B, V, d, sh, sl, d, Ehi, Elo, d, Z, ldz, 12.0f, 0, 1, st));
+  } else {
+    SRK_TRY(gemm(st, B, V, d, shat, d, 1, Ehat, 1, d, Z, ldz, nullptr, nullptr, nullptr, nullptr, 12.0f));
+  }
+  SRK_TRY(srk_ce_rows_fwd(Z, ldz, b.labels, B, V, 0, lse, nll, st));
+  SRK_TRY(srk_mean(nll, B, loss_out, st));
+
+  // ---- backward ------------------------------------------------------------------------------------------
+  float* Zlo = umma ? ar.f((size_t)B * ldz) : nullptr;
+  float *dshat = ar.f((size_t)B * d), *dEhat = ar.f((size_t)V * d);
+  SRK_REQUIRE(ar.ok, "step: workspace too small");
+  SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, one_dev, 12.0f, B, V, 0, Zlo, st));
+  SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
+  if (umma) {
+    const int nkb = (V + 31) / 32;
+    int split = 296 / ((B + 127) / 128);
+    if (split < 1) split = 1;
+    if (split > nkb) split = nkb;
+    SRK_TRY(srk_umma_gemm(1, B, d, V, Z, Zlo, ldz, Ehi, Elo, d, dshat, d, 1.0f, 1, split, st));
+    SRK_TRY(srk_umma_gemm(2, V, d, B, Z, Zlo, ldz, sh, sl, d, dEhat, d, 1.0f, 0, 1, st));
+  } else {
+    SRK_CUDA(cudaMemsetAsync(dEhat, 0, sizeof(float) * (size_t)V * d, st));
+    SRK_TRY(gemm(st, B, d, V, Z, ldz, 1, Ehat, d, 1, dshat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
+    SRK_TRY(gemm(st, V, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
+  }
+  SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, V, d, SRK_NORM_L2, G(0), st));
+  float* ds = ar.f((size_t)B * d);
+  float* dsr_in = ar.f(2 * (size_t)B * d);
+  float* dF = ar.f((size_t)N * d);
+  SRK_REQUIRE(ar.ok, "step: workspace too small");
+  SRK_TRY(srk_rownorm_bwd(s, d, shat, d, rn_s, dshat, d, B, d, SRK_NORM_L2, ds, d, 0, st));
+  SRK_TRY(mm_nn(st, B, 2 * d, d, ds, d, P(s_ro + 4), 2 * d, dsr_in, 2 * d, 0));
+  SRK_TRY(mm_tn(st, d, 2 * d, B, ds, d, sr_in, 2 * d, G(s_ro + 4), 2 * d));
+  SRK_TRY(srk_readout_bwd(F, u, v, P(s_ro + 3), b.seg, b.last, e, ms, sr_in, dsr_in, B, d, 1, dF, G(s_ro + 3), st));
+  SRK_TRY(mm_nn(st, N, d, d, u, d, P(s_ro), d, dF, d, 1));                      // u holds du
+  SRK_TRY(mm_tn(st, d, d, N, u, d, F, d, G(s_ro), d));
+  SRK_TRY(srk_colsum(u, d, N, d, G(s_ro + 1), 1, st));
+  SRK_TRY(mm_nn(st, B, d, d, v, d, P(s_ro + 2), d, dF, d, 1, b.last));          // v holds dv
+  SRK_TRY(mm_tn(st, d, d, B, v, d, F, d, G(s_ro + 2), d, b.last));
+
+  // layers, last to first.  Scratch below is re-carved per layer from a fixed mark.
+  const size_t mark = ar.off;
+  const float* dH = dF;
+  float* dfeat = nullptr;
+  for (int l = L - 1; l >= 0; --l) {
+    LayerRec& R = layers[l];
+    // dfeat must outlive this iteration (it is the next layer's dH): alternate two halves of the scratch region
+    ar.off = mark;
+    float* bufA = ar.f((size_t)N * d);
+    float* bufB = ar.f((size_t)N * d);
+    dfeat = ((L - 1 - l) & 1) ? bufB : bufA;
+    float* dHpre = ar.f((size_t)N * d);
+    srk_gat_inst insts[2];
+    float *dedge[2], *der[2], *dZel[2];
+    for (int c = 0; c < R.n_inst; ++c) {
+      dedge[c] = ar.f((size_t)(M + 1) * H);
+      der[c] = ar.f((size_t)N * H);
+      dZel[c] = ar.f((size_t)N * ldzel);
+      R.inst[c].gi.dedge = dedge[c]; R.inst[c].gi.der = der[c]; R.inst[c].gi.dZel = dZel[c];
+      insts[c] = R.inst[c].gi;
+    }
+    SRK_REQUIRE(ar.ok, "step: workspace too small");
+    SRK_TRY(srk_gat_aggregate_bwd_dst(insts, R.n_inst, N, d, drop ? &dc_attn : nullptr, R.normalize, R.Hout, R.rn, R.amax, dH,
+                                      dHpre, st));
+    SRK_TRY(srk_segmean_bwd(dHpre, b.seg, B, d, dfeat, 0, st));
+    for (int c = 0; c < R.n_inst; ++c) {
+      InstRec& I = R.inst[c];
+      SRK_TRY(srk_gat_bias_bwd(dHpre, R.amax, N, d, I.gbias, st));
+      SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, st));
+      float* dWaug = ar.f((size_t)ldzel * d);
+      float* dwr = ar.f((size_t)H * d);
+      SRK_REQUIRE(ar.ok, "step: workspace too small");
+      SRK_CUDA(cudaMemsetAsync(dWaug, 0, sizeof(float) * (size_t)ldzel * d, st));
+      SRK_CUDA(cudaMemsetAsync(dwr, 0, sizeof(float) * (size_t)H * d, st));
+      SRK_TRY(mm_tn(st, ldzel, d, N, dZel[c], ldzel, I.xs, d, dWaug, d));
+      SRK_TRY(mm_tn(st, H, d, N, der[c], H, I.xd, d, dwr, d));
+      SRK_TRY(srk_gat_prep_bwd(I.W, I.al, I.ar, dWaug, dwr, d, I.gW, I.gal, I.gar, st));
+      if (!I.drop) {
+        SRK_TRY(mm_nn(st, N, d, ldzel, dZel[c], ldzel, I.Waug, d, dfeat, d, 1));
+        SRK_TRY(mm_nn(st, N, d, H, der[c], H, I.wr, d, dfeat, d, 1));
+        SRK_TRY(srk_dropout_apply(dHpre, dfeat, (long long)N * d, nullptr, 1, st));       // residual
+      } else {
+        float* tmp = ar.f((size_t)N * d);
+        float* tmp2 = ar.f((size_t)N * d);
+        SRK_REQUIRE(ar.ok, "step: workspace too small");
+        SRK_TRY(mm_nn(st, N, d, ldzel, dZel[c], ldzel, I.Waug, d, tmp, d, 0));
+        SRK_TRY(srk_dropout_apply(tmp, dfeat, (long long)N * d, &I.dcs, 1, st));
+        SRK_CUDA(cudaMemcpyAsync(tmp2, dHpre, sizeof(float) * (size_t)N * d, cudaMemcpyDeviceToDevice, st));
+        SRK_TRY(mm_nn(st, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
+        SRK_TRY(srk_dropout_apply(tmp2, dfeat, (long long)N * d, &I.dcd, 1, st));
+      }
+    }
+    dH = dfeat;
+  }
+  SRK_TRY(srk_embed_scatter_bwd(E, b.iid, b.perm, b.uoff, b.uid, b.U, b.P, d, SRK_NORM_L2, drop ? &dc_e : nullptr, rnX, dH,
+                                nullptr, G(0), st));
+  if (phase == 0 && do_adam) {
+    SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
+                          adam_step, grad_scale, st));
+  }
+  return SRK_OK;
+}

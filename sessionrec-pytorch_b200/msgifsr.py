@@ -102,6 +102,7 @@ class MSGIFSR(SessRecModule):
         self.alpha.data[0] = 1.0
         self.beta.data = torch.tensor(1.0)
         self.fusion, self.extra = fusion, extra
+        self.native_step = True
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.embedding_dim)
@@ -228,6 +229,68 @@ class MSGIFSR(SessRecModule):
                     ops.mm_nn(rec['der'], rec['wr'], tmp2, accumulate=True)
                     ops.dropout_apply(tmp2, dfeat[k], tmp2.numel(), rec['dcd'], accumulate=True)
         return dfeat
+
+    # ---- native fused step (csrc/step.cu) ------------------------------------------------------------------------
+    def _native_ok(self, batch):
+        return self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
+
+    def _slot_offsets(self):
+        import numpy as np
+        fp = self._flat
+        names = ['embeddings.weight']
+        for l in range(self.num_layers):
+            for c in (1, 2):
+                names += [f'layers.{l}.conv{c}.mods.intra1.{n}' for n in ('attn_l', 'attn_r', 'bias', 'fc.weight')]
+        names += ['readout.fc_u.0.weight', 'readout.fc_u.0.bias', 'readout.fc_v.0.weight', 'readout.fc_e.0.weight',
+                  'fc_sr.0.weight']
+        return np.ascontiguousarray([fp.offsets[fp.index[n]] for n in names], dtype=np.int64)
+
+    def train_step(self, batch, group=None):
+        """One TrainRunner iteration in ONE C call (srk_msgifsr_train_step): zero_grad, forward, nll_loss, backward,
+        Adam.  Falls back to the staged Python composition for configurations the native step does not cover."""
+        fp = self._ensure_flat()
+        if not self._native_ok(batch) or not self.native_step:
+            return super().train_step(batch, group)
+        import ctypes
+        from ._lib import lib, ptr
+        if self._opt is None:
+            self.configure_optimizer()
+        o = self._opt
+        st = getattr(self, '_native', None)
+        if st is None or st['flat'] is not fp:
+            st = self._native = dict(flat=fp, slots=self._slot_offsets(), ws=None, ws_bytes=0,
+                                     loss=torch.zeros((), dtype=torch.float32, device=fp.data.device))
+        t, rel = batch.types[1], batch.rels[0]
+        L = lib()
+        need = L.call('srk_msgifsr_workspace_bytes', batch.B, t['N'], rel['M'], self.num_items, self.embedding_dim,
+                      self.num_layers)
+        if need > st['ws_bytes']:
+            st['ws_bytes'] = int(need * 1.2)
+            st['ws'] = torch.empty(st['ws_bytes'], dtype=torch.uint8, device=fp.data.device)
+        p, seed = self._p(), self._next_seed()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        world = 1
+        if group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+        o['step'] += 1
+        loss = torch.empty((), dtype=torch.float32, device=fp.data.device)
+
+        def call(phase):
+            ops._count[0] += 1
+            L.call('srk_msgifsr_train_step', ptr(batch.buf), ctypes.c_void_p(batch.hdr.ctypes.data), ptr(fp.data),
+                   ptr(fp.grad), ctypes.c_void_p(st['slots'].ctypes.data), self.num_items, self.embedding_dim,
+                   self.num_layers, float(p), ctypes.c_uint64(seed), int(self.use_tensor_cores), ptr(st['ws']),
+                   st['ws_bytes'], ptr(self._one()), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
+                   ptr(o['seg_off']), ptr(o['seg_decay']), o['n_seg'], float(o['lr']), float(o['betas'][0]),
+                   float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0 / world, phase, stream)
+        if world == 1:
+            call(0)
+        else:
+            call(1)
+            dist.all_reduce(fp.grad, group=group)
+            call(2)
+        return loss
 
     # ---- whole model -------------------------------------------------------------------------------------------
     def _fwd(self, batch, mode, need_grad=True):

@@ -91,7 +91,7 @@ def embed_gather_fwd(E, iid, P, d, mode, dc, X, rnorm, x_first=None):
 
 
 def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE):
-    _call('srk_embed_scatter_bwd', ptr(E), ptr(t['iid']), ptr(t['perm']), ptr(t['uoff']), ptr(t['uid']), t['U'], d, mode,
+    _call('srk_embed_scatter_bwd', ptr(E), ptr(t['iid']), ptr(t['perm']), ptr(t['uoff']), ptr(t['uid']), t['U'], t['P'], d, mode,
           _dref(dc), ptr(rnorm), ptr(dX), ptr(dX_first), ptr(dE))
 
 

@@ -203,3 +203,44 @@ def test_full_size_configs_vs_oracle(pkg, cfg):
     for n, g in grads.items():
         if prm[n].grad is not None:
             assert_grad_close(f'{cfg}.grad[{n}]', g, prm[n].grad)
+
+
+@pytest.mark.parametrize('p', [0.0, 0.3])
+def test_native_step_matches_staged_composition(pkg, p):
+    """csrc/step.cu (one C call per training step) against the stage-by-stage Python composition of the same
+    kernels: same losses and same parameters after a few Adam steps (dropout masks included)."""
+    c = TRAINS['msgifsr_k1']
+    models = []
+    for native in (True, False):
+        m = make_model(pkg, c, dropout=p)
+        m.train()
+        m.native_step = native
+        m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+        losses = []
+        for it in range(4):
+            m.set_dropout_seed(777 + it)
+            b, _ = make_batch(pkg, c, c['samples'][it * c['bs']:(it + 1) * c['bs']])
+            losses.append(float(m.train_step(b)))
+        models.append((m, losses))
+    (m1, l1), (m2, l2) = models
+    for a, b_ in zip(l1, l2):
+        assert abs(a - b_) <= 2e-6 * abs(b_), (l1, l2)
+    for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert_close(f'native vs staged {n}', q1, q2, rtol=2e-5, floor=0.1)
+
+
+def test_native_step_two_layers_and_sgemm_head(pkg):
+    c = MODELS['msgifsr_k1_inflate_L2']
+    outs = []
+    for native, tc in ((True, True), (False, True), (True, False)):
+        m = make_model(pkg, c, dropout=0.2)
+        m.train()
+        m.native_step, m.use_tensor_cores = native, tc
+        m.set_dropout_seed(5)
+        m.configure_optimizer()
+        b, _ = make_batch(pkg, c)
+        loss = float(m.train_step(b))
+        outs.append((loss, m.embeddings.weight.detach().clone()))
+    for loss, w in outs[1:]:
+        assert abs(loss - outs[0][0]) <= 1e-5 * abs(outs[0][0])
+        assert_close('embedding after 1 step', w, outs[0][1], rtol=2e-5, floor=0.1)
