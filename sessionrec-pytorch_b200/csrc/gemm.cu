@@ -171,11 +171,14 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 }  // namespace
 
+// The dense layers of this path are small (N ~ 2k rows, d ~ 100-256): with one 64x64 tile per CTA most of them
+// launch far fewer CTAs than the 148 SMs and are bound by the latency of their serial K loop.  Split K until about
+// two CTAs per SM are in flight, never below 2 k-iterations (32) per CTA.
 int srk_pick_split_k(int M, int N, int K) {
   long long tiles = (long long)srk_cdiv(M, BM) * srk_cdiv(N, BN);
-  if (tiles >= 444 || K <= 256) return 1;
-  long long want = (592 + tiles - 1) / tiles;
-  long long cap = K / 256 > 0 ? K / 256 : 1;
+  if (tiles >= 296 || K < 128) return 1;
+  long long want = (296 + tiles - 1) / tiles;
+  long long cap = K / 32;
   long long s = want < cap ? want : cap;
   if (s > 128) s = 128;
   return (int)(s < 1 ? 1 : s);
@@ -185,6 +188,17 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return SRK_OK;
   SRK_REQUIRE(g.split_k >= 1, "gemm: split_k must be >= 1");
   SRK_REQUIRE(g.split_k == 1 || g.accumulate, "gemm: split-K needs accumulate mode");
+  if (!g.accumulate && !g.c_idx && g.K >= 256) {
+    // overwrite mode with a long K loop and few tiles: zero C, then run the split-K accumulate path
+    int s = srk_pick_split_k(g.M, g.N, g.K);
+    if (s > 1) {
+      SRK_CUDA(cudaMemset2DAsync(g.C, sizeof(float) * (size_t)g.ldc, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
+      GemmArgs h = g;
+      h.accumulate = 1;
+      h.split_k = s;
+      return srk_gemm_launch(h, st);
+    }
+  }
   SRK_REQUIRE(srk_cdiv(g.M, BM) <= 65535, "gemm: M too large for grid.y");
   if (g.K <= 0) {
     SRK_REQUIRE(g.accumulate, "gemm: K == 0 with overwrite mode is not supported");
