@@ -108,6 +108,13 @@ int srk_rownorm_bwd(const float* X, long long ldx, const float* Y, long long ldy
                     long long lddy, int R, int d, int norm_mode, float* dX, long long lddx, int accumulate,
                     void* stream);
 
+/* ---- SemanticExpander tail (msgifsr.py:32-45 with reducer 'mean', then F.normalize :252-253) -----------------------
+ * out[n] = normalize(0.5 * mean_t X[n, t, :] + 0.5 * h[n, :]); X = dropped gather [N, k, d], h = final GRU state.
+ * Backward writes dh = 0.5 dpre and dX[n, t, :] = 0.5 / k dpre (the GRU BPTT then accumulates into dX). */
+int srk_expander_combine_fwd(const float* X, const float* h, int N, int k, int d, float* out, float* rnorm, void* stream);
+int srk_expander_combine_bwd(const float* out, const float* rnorm, const float* dout, int N, int k, int d, float* dh,
+                             float* dX, void* stream);
+
 /* ---- elementwise helpers -------------------------------------------------------------------------------
  * Y = dropout(X) over n elements (flat index = element index); accumulate: Y += dropout_mask * X. */
 int srk_dropout_apply(const float* X, float* Y, long long n, const srk_dropout* drop, int accumulate, void* stream);

@@ -39,7 +39,7 @@ class SessionBatch:
             self.types[k] = dict(N=N, U=U, P=N * k, iid=self._sec(t[1], N * k), seg=self._sec(t[2], self.B + 1),
                                  last=self._sec(t[3], self.B), node2seg=self._sec(t[4], N),
                                  perm=self._sec(t[5], N * k), uoff=self._sec(t[6], U + 1), uid=self._sec(t[7], U),
-                                 last_row=self._sec(t[9], self.B))
+                                 last_row=self._sec(t[9], self.B), row_of=self._sec(t[10], N))
         self.rels = []
         for r in range(int(h[5])):
             t = h[_REL_TAB + _TAB_W * r:]

@@ -9,7 +9,7 @@
 //   [0] magic 'SRK1'  [1] B  [2] kind  [3] K  [4] words used  [5] n_rel  [6] R (rows of all types)
 //   [7] off_labels  [8] off_row_seg  [9] off_row_type  [10] off_row_node
 //   type table  at word 16 + 16*(k-1):  N, off_iid, off_seg, off_last, off_node2seg, off_perm, off_uoff,
-//                                        off_uid, U, off_last_row
+//                                        off_uid, U, off_last_row, off_row_of (mixed-row index of every node)
 //   rel table   at word 80 + 16*r:      st, dt, M, off_src, off_dst, off_in_ptr, off_in_src, off_in_eid,
 //                                        off_out_ptr, off_out_dst, off_out_eid, off_w (float bits, kind 0), code
 //   rel order: intra1..intraK, then for k = 2..K: inter1_k, interk_1.  code = k for intra_k, 100+k for
@@ -207,6 +207,7 @@ long long emit(const Work& wk, const int* labels, int* out, long long cap) {
     std::vector<int> last_row(B);
     for (int b = 0; b < B; ++b) last_row[b] = row_of[k][wk.last[k][b]];
     t[9] = w.put(last_row);
+    t[10] = w.put(row_of[k]);
   }
   std::vector<int> ptr, nbr, eid;
   for (size_t r = 0; r < wk.rels.size(); ++r) {
@@ -243,7 +244,7 @@ extern "C" long long srk_batch_size(const int* items_host, const int* offs_host,
   long long T = offs_host[B] - offs_host[0];
   // nodes <= T per type (+B dummies), gram rows carry k items, edges <= T per relation (+B self-loops)
   long long per_type = 0;
-  for (int k = 1; k <= K; ++k) per_type += (T + B) * (long long)(4 * k + 2) + 4LL * (B + 1);
+  for (int k = 1; k <= K; ++k) per_type += (T + B) * (long long)(4 * k + 3) + 4LL * (B + 1);
   long long per_rel = 8LL * (T + B) + 2LL * (T + B + 1);
   return DATA0 + B + 3LL * (T + B) * K + (B + 1) + per_type + per_rel * (3LL * K - 2) + 64;
 }

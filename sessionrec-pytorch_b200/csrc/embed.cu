@@ -197,6 +197,58 @@ __global__ void __launch_bounds__(ROW_THREADS) rownorm_bwd_kernel(const float* _
   }
 }
 
+// SemanticExpander (msgifsr.py:32-45, reducer = mean) tail: pre = 0.5 * mean_t X[n, t, :] + 0.5 * h[n, :], then
+// F.normalize (msgifsr.py:252-253).  X is the dropped gather [N, k, d], h the final GRU state.
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) expander_combine_fwd_kernel(const float* __restrict__ X, const float* __restrict__ h,
+                                                                           int N, int k, int d, float* __restrict__ out,
+                                                                           float* __restrict__ rnorm) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+    RowVec<NC> acc, x;
+    row_zero(acc);
+    for (int t = 0; t < k; ++t) {
+      row_load(x, X + ((long long)n * k + t) * d, d, lane);
+      row_axpy(acc, 1.f, x);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      acc.v[c].x /= (float)k; acc.v[c].y /= (float)k; acc.v[c].z /= (float)k; acc.v[c].w /= (float)k;
+    }
+    row_load(x, h + (long long)n * d, d, lane);
+    row_scale(acc, 0.5f);
+    row_axpy(acc, 0.5f, x);
+    RowVec<NC> y;
+    float nn = row_normalize(acc, y, SRK_NORM_L2);
+    row_store(y, out + (long long)n * d, d, lane);
+    if (lane == 0) rnorm[n] = nn;
+  }
+}
+
+// dpre = d F.normalize applied to dout (pre is rebuilt as out * max(rnorm, eps)); dh = 0.5 dpre; dX[n, t] = 0.5/k dpre
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) expander_combine_bwd_kernel(const float* __restrict__ out,
+                                                                           const float* __restrict__ rnorm,
+                                                                           const float* __restrict__ dout, int N, int k, int d,
+                                                                           float* __restrict__ dh, float* __restrict__ dX) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
+    RowVec<NC> y, dy, dx, pre;
+    row_load(y, out + (long long)n * d, d, lane);
+    row_load(dy, dout + (long long)n * d, d, lane);
+    const float nn = rnorm[n];
+    pre = y;
+    row_scale(pre, fmaxf(nn, 1e-12f));
+    row_normalize_bwd<NC>(pre, y, nn, SRK_NORM_L2, dy, nullptr, dx);
+    row_scale(dx, 0.5f);
+    row_store(dx, dh + (long long)n * d, d, lane);
+    row_scale(dx, 1.f / (float)k);
+    for (int t = 0; t < k; ++t) row_store(dx, dX + ((long long)n * k + t) * d, d, lane);
+  }
+}
+
 inline int row_grid(long long rows) {
   long long g = (rows + 7) / 8;
   if (g < 1) g = 1;
@@ -275,6 +327,26 @@ extern "C" int srk_rownorm_bwd(const float* X, long long ldx, const float* Y, lo
   SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "rownorm: strides must be multiples of 4");
   SRK_DISPATCH_NC(d, (rownorm_bwd_kernel<NC><<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(
                          X, ldx, Y, ldy, rnorm, dY, lddy, R, d, norm_mode, dX, lddx, accumulate)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_expander_combine_fwd(const float* X, const float* h, int N, int k, int d, float* out, float* rnorm,
+                                        void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (N <= 0) return SRK_OK;
+  SRK_DISPATCH_NC(d, (expander_combine_fwd_kernel<NC><<<row_grid(N), ROW_THREADS, 0, (cudaStream_t)stream>>>(X, h, N, k, d, out,
+                                                                                                               rnorm)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_expander_combine_bwd(const float* out, const float* rnorm, const float* dout, int N, int k, int d,
+                                        float* dh, float* dX, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (N <= 0) return SRK_OK;
+  SRK_DISPATCH_NC(d, (expander_combine_bwd_kernel<NC><<<row_grid(N), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                         out, rnorm, dout, N, k, d, dh, dX)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

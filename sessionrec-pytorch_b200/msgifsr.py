@@ -292,15 +292,68 @@ class MSGIFSR(SessRecModule):
             call(2)
         return loss
 
+    # ---- SemanticExpander for the k-gram node types (msgifsr.py:32-45) --------------------------------------------
+    def _expander_fwd(self, k, batch, E, p, seed, need_grad):
+        t = batch.types[k]
+        N, d, dev = t['N'], self.embedding_dim, E.device
+        gru = self.expander.GRUs[k - 2]
+        dc = ops.drop_cfg(p, SITE_EMBED + k, seed) if p > 0 else None
+        Xk = torch.empty(N * k, d, dtype=torch.float32, device=dev)
+        ops.embed_gather_fwd(E, t['iid'], N * k, d, 0, dc, Xk, None)
+        Xv = Xk.view(N, k * d)
+        hs = [torch.zeros(N, d, dtype=torch.float32, device=dev)]
+        gis, ghs = [], []
+        for step in range(k):
+            gi = torch.empty(N, 3 * d, dtype=torch.float32, device=dev)
+            gh = torch.empty(N, 3 * d, dtype=torch.float32, device=dev)
+            ops.linear_nt(Xv[:, step * d:(step + 1) * d], gru.weight_ih_l0, gi, bias=gru.bias_ih_l0)
+            ops.linear_nt(hs[-1], gru.weight_hh_l0, gh, bias=gru.bias_hh_l0)
+            hn = torch.empty(N, d, dtype=torch.float32, device=dev)
+            ops.gru_pointwise_fwd(gi, gh, hs[-1], N, d, hn)
+            hs.append(hn)
+            gis.append(gi)
+            ghs.append(gh)
+        out = torch.empty(N, d, dtype=torch.float32, device=dev)
+        rn = torch.empty(N, dtype=torch.float32, device=dev)
+        ops.expander_combine_fwd(Xk, hs[-1], N, k, d, out, rn)
+        return out, (dict(Xk=Xk, hs=hs, gis=gis, ghs=ghs, out=out, rn=rn, dc=dc) if need_grad else None)
+
+    def _expander_bwd(self, k, batch, E, et, dout, g, gE):
+        t = batch.types[k]
+        N, d, dev = t['N'], self.embedding_dim, E.device
+        gru = self.expander.GRUs[k - 2]
+        name = f'expander.GRUs.{k - 2}.'
+        dXk = torch.empty(N * k, d, dtype=torch.float32, device=dev)
+        dh = torch.empty(N, d, dtype=torch.float32, device=dev)
+        ops.expander_combine_bwd(et['out'], et['rn'], dout, N, k, d, dh, dXk)
+        Xv, dXv = et['Xk'].view(N, k * d), dXk.view(N, k * d)
+        for step in reversed(range(k)):
+            gi, gh, hprev = et['gis'][step], et['ghs'][step], et['hs'][step]
+            dprev = torch.empty(N, d, dtype=torch.float32, device=dev)
+            ops.gru_pointwise_bwd(gi, gh, hprev, dh, N, d, dprev, False)           # gi, gh <- their gradients
+            xs = Xv[:, step * d:(step + 1) * d]
+            ops.mm_tn(gi, xs, g(name + 'weight_ih_l0'))
+            ops.colsum(gi, 3 * d, N, 3 * d, g(name + 'bias_ih_l0'))
+            ops.mm_nn(gi, gru.weight_ih_l0, dXv[:, step * d:(step + 1) * d], accumulate=True)
+            ops.mm_tn(gh, hprev, g(name + 'weight_hh_l0'))
+            ops.colsum(gh, 3 * d, N, 3 * d, g(name + 'bias_hh_l0'))
+            ops.mm_nn(gh, gru.weight_hh_l0, dprev, accumulate=True)
+            dh = dprev
+        ops.embed_scatter_bwd(E, t, d, 0, et['dc'], None, dXk, None, gE)
+
     # ---- whole model -------------------------------------------------------------------------------------------
     def _fwd(self, batch, mode, need_grad=True):
-        if self.order != 1 or batch.K != 1:
-            raise SessRecError('MSGIFSR order > 1 is not built yet on the CUDA path (order 1 = the reference start.sh)')
+        if batch.K != self.order:
+            raise SessRecError(f'batch built for order {batch.K}, model has order {self.order}')
         if self.extra:
             raise SessRecError('MSGIFSR extra=True (REnorm head) is not built; the reference scripts default to False')
         if not self.norm:
             raise SessRecError('MSGIFSR norm=False is not built (the reference argparse can only produce True)')
-        d, B, V, dev = self.embedding_dim, batch.B, self.num_items, self.embeddings.weight.device
+        if self.order > 1 and self.fusion:
+            raise SessRecError('MSGIFSR fusion=True is not built yet (reference scripts default to False)')
+        if self.num_layers == 0:
+            raise SessRecError('MSGIFSR needs num_layers >= 1')
+        K, d, B, V, dev = self.order, self.embedding_dim, batch.B, self.num_items, self.embeddings.weight.device
         E = self.embeddings.weight.data
         p, seed = self._p(), self._next_seed()
         tape = dict(batch=batch, p=p, seed=seed, mode=mode)
@@ -312,41 +365,51 @@ class MSGIFSR(SessRecModule):
         if self.use_tensor_cores and d <= 256:
             Ehi, Elo = torch.empty_like(E), torch.empty_like(E)
         ops.catalog_prep_fwd(E, NORM_L2, 1.0, Ehat, enorm, Ehi, Elo)
-        t = batch.types[1]
-        N = t['N']
+        t1 = batch.types[1]
+        N = t1['N']
         dc_e = ops.drop_cfg(p, SITE_EMBED + 1, seed) if p > 0 else None
         X = torch.empty(N, d, dtype=torch.float32, device=dev)
         rnX = torch.empty(N, dtype=torch.float32, device=dev)
-        ops.embed_gather_fwd(E, t['iid'], N, d, NORM_L2, dc_e, X, rnX)
-        h, ltapes = {1: X}, []
-        if self.num_layers == 0:
-            raise SessRecError('MSGIFSR needs num_layers >= 1')
+        ops.embed_gather_fwd(E, t1['iid'], N, d, NORM_L2, dc_e, X, rnX)
+        h, etapes = {1: X}, {}
+        for k in range(2, K + 1):
+            h[k], etapes[k] = self._expander_fwd(k, batch, E, p, seed, need_grad)
+        ltapes = []
         for l in range(self.num_layers):
             h, lt = self._layer_fwd(l, batch, h, p, seed, normalize=(l == self.num_layers - 1), need_grad=need_grad)
             ltapes.append(lt)
-        F = h[1]
-        u = torch.empty(N, d, dtype=torch.float32, device=dev)
+        # readout over the per-session concatenation of all orders' rows (msgifsr.py:127-146).  Without fusion only
+        # order 1's score is returned (msgifsr.py:316-317): the other heads are dead code and get exact-zero grads.
+        if K == 1:
+            rows, seg, last_row = h[1], t1['seg'], t1['last']
+        else:
+            rows = torch.zeros(batch.R, d, dtype=torch.float32, device=dev)
+            for k in range(1, K + 1):
+                ops.scatter_add_rows(h[k], d, batch.types[k]['row_of'], batch.types[k]['N'], d, rows)
+            seg, last_row = batch.row_seg, t1['last_row']
+        R = rows.shape[0]
+        u = torch.empty(R, d, dtype=torch.float32, device=dev)
         v = torch.empty(B, d, dtype=torch.float32, device=dev)
-        ops.linear_nt(F, self.readout.fc_u[0].weight, u, bias=self.readout.fc_u[0].bias)
-        ops.linear_nt(F, self.readout.fc_v[0].weight, v, M=B, a_idx=t['last'])
-        e = torch.empty(N, dtype=torch.float32, device=dev)
+        ops.linear_nt(rows, self.readout.fc_u[0].weight, u, bias=self.readout.fc_u[0].bias)
+        ops.linear_nt(h[1], self.readout.fc_v[0].weight, v, M=B, a_idx=t1['last'])
+        e = torch.empty(R, dtype=torch.float32, device=dev)
         ms = torch.empty(B, 2, dtype=torch.float32, device=dev)
         sr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
-        ops.readout_fwd(F, u, v, self.readout.fc_e[0].weight, t['seg'], t['last'], B, d, True, e, ms, sr_in)
+        ops.readout_fwd(rows, u, v, self.readout.fc_e[0].weight, seg, last_row, B, d, True, e, ms, sr_in)
         s = torch.empty(B, d, dtype=torch.float32, device=dev)
         ops.linear_nt(sr_in, self.fc_sr[0].weight, s)
         shat = torch.empty_like(s)
         rn_s = torch.empty(B, dtype=torch.float32, device=dev)
         ops.rownorm_fwd(s, d, B, d, NORM_L2, shat, d, rn_s)
-        tape.update(X=X, rnX=rnX, dc_e=dc_e, ltapes=ltapes, F=F, u=u, v=v, e=e, ms=ms, sr_in=sr_in, s=s, rn_s=rn_s,
-                    enorm=enorm)
+        tape.update(X=X, rnX=rnX, dc_e=dc_e, etapes=etapes, ltapes=ltapes, h=h, rows=rows, seg=seg, last_row=last_row, u=u,
+                    v=v, e=e, ms=ms, sr_in=sr_in, s=s, rn_s=rn_s, enorm=enorm)
         out = self._head_fwd(shat, d, Ehat, SCALE, batch, mode, tape, Ehi, Elo)
         return out, (tape if need_grad else None)
 
     def _bwd(self, tape, gout, gflat):
         fp, batch = self._flat, tape['batch']
-        t = batch.types[1]
-        N, B, d, V = t['N'], batch.B, self.embedding_dim, self.num_items
+        t1 = batch.types[1]
+        K, B, d, V = self.order, batch.B, self.embedding_dim, self.num_items
         E = self.embeddings.weight.data
         dev = E.device
         g = lambda name: fp.view(gflat, name)          # noqa: E731
@@ -359,19 +422,29 @@ class MSGIFSR(SessRecModule):
         ops.catalog_prep_bwd(E, tape['Ehat'], tape['enorm'], dEhat, NORM_L2, gE)
         ds = torch.empty(B, d, dtype=torch.float32, device=dev)
         ops.rownorm_bwd(tape['s'], d, tape['shat'], d, tape['rn_s'], dshat, d, B, d, NORM_L2, ds, d)
-        sr_in, F, u, v = tape['sr_in'], tape['F'], tape['u'], tape['v']
+        sr_in, rows, u, v, h = tape['sr_in'], tape['rows'], tape['u'], tape['v'], tape['h']
+        R = rows.shape[0]
         dsr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
         ops.mm_nn(ds, self.fc_sr[0].weight, dsr_in)
         ops.mm_tn(ds, sr_in, g('fc_sr.0.weight'))
-        dF = torch.empty(N, d, dtype=torch.float32, device=dev)
-        ops.readout_bwd(F, u, v, self.readout.fc_e[0].weight, t['seg'], t['last'], tape['e'], tape['ms'], sr_in, dsr_in,
-                        B, d, True, dF, g('readout.fc_e.0.weight'))
-        ops.mm_nn(u, self.readout.fc_u[0].weight, dF, accumulate=True)
-        ops.mm_tn(u, F, g('readout.fc_u.0.weight'))
-        ops.colsum(u, d, N, d, g('readout.fc_u.0.bias'))
-        ops.mm_nn(v, self.readout.fc_v[0].weight, dF, c_idx=t['last'], accumulate=True)
-        ops.mm_tn(v, F, g('readout.fc_v.0.weight'), b_idx=t['last'])
-        dH = {1: dF}
+        drows = torch.empty(R, d, dtype=torch.float32, device=dev)
+        ops.readout_bwd(rows, u, v, self.readout.fc_e[0].weight, tape['seg'], tape['last_row'], tape['e'], tape['ms'], sr_in,
+                        dsr_in, B, d, True, drows, g('readout.fc_e.0.weight'))
+        ops.mm_nn(u, self.readout.fc_u[0].weight, drows, accumulate=True)
+        ops.mm_tn(u, rows, g('readout.fc_u.0.weight'))
+        ops.colsum(u, d, R, d, g('readout.fc_u.0.bias'))
+        if K == 1:
+            dH = {1: drows}
+        else:
+            dH = {}
+            for k in range(1, K + 1):
+                Nk = batch.types[k]['N']
+                dH[k] = torch.empty(Nk, d, dtype=torch.float32, device=dev)
+                ops.gather_rows(drows, batch.types[k]['row_of'], Nk, d, dH[k], d)
+        ops.mm_nn(v, self.readout.fc_v[0].weight, dH[1], c_idx=t1['last'], accumulate=True)
+        ops.mm_tn(v, h[1], g('readout.fc_v.0.weight'), b_idx=t1['last'])
         for l in reversed(range(self.num_layers)):
             dH = self._layer_bwd(l, batch, tape['ltapes'][l], dH, g)
-        ops.embed_scatter_bwd(E, t, d, NORM_L2, tape['dc_e'], tape['rnX'], dH[1], None, gE)
+        for k in range(2, K + 1):
+            self._expander_bwd(k, batch, E, tape['etapes'][k], dH[k], g, gE)
+        ops.embed_scatter_bwd(E, t1, d, NORM_L2, tape['dc_e'], tape['rnX'], dH[1], None, gE)

@@ -118,6 +118,14 @@ def rownorm_bwd(X, ldx, Y, ldy, rnorm, dY, lddy, R, d, mode, dX, lddx, accumulat
           int(bool(accumulate)))
 
 
+def expander_combine_fwd(X, h, N, k, d, out, rnorm):
+    _call('srk_expander_combine_fwd', ptr(X), ptr(h), N, k, d, ptr(out), ptr(rnorm))
+
+
+def expander_combine_bwd(out, rnorm, dout, N, k, d, dh, dX):
+    _call('srk_expander_combine_bwd', ptr(out), ptr(rnorm), ptr(dout), N, k, d, ptr(dh), ptr(dX))
+
+
 # ---- elementwise -------------------------------------------------------------------------------------------
 
 def dropout_apply(X, Y, n, dc, accumulate=False):
