@@ -147,7 +147,7 @@ def roofline_probe(cfg, device, pk):
         ops.split_tf32(s, d, B, d, sh, sl, d)
         ops.split_tf32(E, d, V, d, Eh, El, d)
         ops.split_tf32(Z, ldz, B, V, Zh, Zl, ldz)
-        split = max(1, min((V + 31) // 32, 296 // ((B + 127) // 128)))
+        split = max(1, min((V + 31) // 32, 148 // ((B + 127) // 128)))
 
         def run():
             ops.umma_gemm(0, B, V, d, sh, sl, d, Eh, El, d, Z, ldz, alpha=12.0)

@@ -154,6 +154,10 @@ int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse
 int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V, float* DZ,
                  long long lddz, float* DZlo, void* stream);
 
+/* Fused evaluation head (next-row: evaluate(), utils/train.py:36-55): per row the ids (and optionally values) of the k
+ * largest logits, sorted descending, ties by ascending id.  Replaces materialising log-probs + `logits.topk(k)`. */
+int srk_topk_rows(const float* Z, long long ldz, int B, int V, int k, int* out_idx, float* out_val, void* stream);
+
 /* ---- GGNN layer (K2 / K3) ---------------------------------------------------------------------------------
  * Weighted-mean aggregation over in-edges and out-edges: NN[v] = [ sum_in w x[u] / sum_in w | sum_out w x[t] /
  * sum_out w ] (row stride 2d; 0 where a node has no such edge).  CSR by destination (in_*) and by source

@@ -7,6 +7,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops
+from ._lib import NORM_NONE
 from .flat import FlatParams
 
 
@@ -40,6 +41,7 @@ class SessRecModule(nn.Module):
         self._fixed_seed = None
         self._opt = None
         self.use_tensor_cores = os.environ.get('SESSREC_NO_UMMA', '0') != '1'
+        self._shard = None
 
     # ---- parameters -------------------------------------------------------------------------------------
     def _ensure_flat(self):
@@ -76,59 +78,152 @@ class SessRecModule(nn.Module):
         self._ensure_flat()
         return _Bridge.apply(self, mg, 'loss', *self._flat.params)
 
+    @torch.no_grad()
+    def topk(self, mg, k=20):
+        """Ids [B, k] (int64, best first) of the k highest-scoring items per session: the `logits.topk(k)[1]` of the
+        reference's evaluate() (`utils/train.py:49`) without materialising (B, V) log-probabilities."""
+        self._ensure_flat()
+        Zv, _ = self._fwd(mg, 'logits', need_grad=False)
+        B, V = Zv.shape
+        idx = torch.empty(B, k, dtype=torch.int32, device=Zv.device)
+        ops.topk_rows(Zv, Zv.stride(0), B, V, k, idx)
+        return idx.long()
+
     # ---- catalog scoring + CE head -----------------------------------------------------------------------
-    def _head_fwd(self, shat, ld_s, Ehat, scale, batch, mode, tape, Ehi=None, Elo=None):
+    def shard_catalog(self, group):
+        """Catalog-row sharding (BASELINE config 5): this rank scores only rows [lo, hi) of the item table; per session
+        the soft-max statistics + label logit cross NVLink in one small all-reduce, dS in a second one, and the head's
+        share of the table gradient in a third.  The session encoder stays replicated."""
+        self._shard = group
+
+    def _rows(self, V):
+        if self._shard is None:
+            return 0, V
+        import torch.distributed as dist
+        from .parallel import shard_slice
+        return shard_slice(V, dist.get_rank(self._shard), dist.get_world_size(self._shard))
+
+    def _catalog_fwd(self, E, norm_mode, max_norm, tape):
+        """Catalog pre-pass: in-place max_norm renorm (MSGIFSR) + row normalisation of the rows this rank scores, with
+        the TF32 hi/lo split for the tcgen05 GEMM emitted by the same kernel."""
+        V, d = E.shape
+        lo, hi = self._rows(V)
+        dev = E.device
+        umma = self.use_tensor_cores and d <= 256
+        if self._shard is not None and max_norm > 0:
+            ops.renorm_rows(E, None, V, max_norm)          # every replica renorms every row (the reference does too)
+            max_norm = 0.0
+        El = E[lo:hi]
+        Ehi = Elo = enorm = None
+        if norm_mode == NORM_NONE:
+            Ehat = El
+            if umma:
+                Ehi, Elo = torch.empty_like(El), torch.empty_like(El)
+                ops.split_tf32(El, d, hi - lo, d, Ehi, Elo, d)
+        else:
+            Ehat = torch.empty_like(El)
+            enorm = torch.empty(hi - lo, dtype=torch.float32, device=dev)
+            if umma:
+                Ehi, Elo = torch.empty_like(El), torch.empty_like(El)
+            ops.catalog_prep_fwd(El, norm_mode, max_norm, Ehat, enorm, Ehi, Elo)
+        tape['cat'] = dict(lo=lo, hi=hi, Ehat=Ehat, enorm=enorm, Ehi=Ehi, Elo=Elo, norm_mode=norm_mode, umma=umma)
+
+    def _head_fwd(self, shat, ld_s, scale, batch, mode, tape):
         """Z = scale * shat Ehat^T on the tcgen05 tensor cores (3xTF32, csrc/umma_gemm.cu) whenever the embedding
-        dim fits one UMMA N tile (d <= 256); otherwise on the fp32 CUDA-core GEMM."""
-        B, (V, d) = batch.B, Ehat.shape
+        dim fits one UMMA N tile (d <= 256), else on the fp32 CUDA-core GEMM; then log-sum-exp / NLL / log-probs."""
+        cat = tape['cat']
+        Ehat, umma = cat['Ehat'], cat['umma']
+        B, (V, d) = batch.B, Ehat.shape                 # V = rows scored by this rank
         dev = Ehat.device
         ldz = (V + 3) // 4 * 4                      # 16-byte aligned rows: TMA / vector loads in the backward GEMMs
         Z = torch.empty(B, ldz, dtype=torch.float32, device=dev)
-        umma = self.use_tensor_cores and d <= 256
         if umma:
-            if Ehi is None:
-                Ehi, Elo = torch.empty_like(Ehat), torch.empty_like(Ehat)
-                ops.split_tf32(Ehat, d, V, d, Ehi, Elo, d)
             sh = torch.empty(B, d, dtype=torch.float32, device=dev)
             sl = torch.empty(B, d, dtype=torch.float32, device=dev)
             ops.split_tf32(shat, ld_s, B, d, sh, sl, d)
-            ops.umma_gemm(0, B, V, d, sh, sl, d, Ehi, Elo, d, Z, ldz, alpha=scale)
-            tape.update(Ehi=Ehi, Elo=Elo, sh=sh, sl=sl)
+            ops.umma_gemm(0, B, V, d, sh, sl, d, cat['Ehi'], cat['Elo'], d, Z, ldz, alpha=scale)
+            tape.update(sh=sh, sl=sl)
         else:
             ops.gemm(B, V, d, shat, ld_s, 1, Ehat, 1, d, Z, ldz, alpha=scale)
         lse = torch.empty(B, dtype=torch.float32, device=dev)
-        tape.update(Z=Z, ldz=ldz, lse=lse, scale=scale, Ehat=Ehat, shat=shat, ld_s=ld_s, umma=umma)
+        tape.update(Z=Z, ldz=ldz, lse=lse, scale=scale, shat=shat, ld_s=ld_s)
+        if mode == 'logits':
+            if self._shard is not None:
+                raise _lib.SessRecError('catalog-sharded mode returns the loss only (each rank holds a slice of the logits)')
+            return Z[:, :V]
+        if self._shard is not None:
+            return self._head_fwd_sharded(Z, ldz, lse, batch, mode, tape)
         if mode == 'loss':
             nll = torch.empty(B, dtype=torch.float32, device=dev)
             ops.ce_rows_fwd(Z, ldz, batch.labels, B, V, False, lse, nll)
             out = torch.empty((), dtype=torch.float32, device=dev)
             ops.mean(nll, B, out)
+            tape['labels'] = batch.labels
             return out
         ops.ce_rows_fwd(Z, ldz, None, B, V, True, lse, None)
         return Z[:, :V]
 
-    def _head_bwd(self, tape, batch, mode, gout, dEhat, overwrite=False):
-        """Returns d shat [B, d]; adds the catalog gradient into dEhat [V, d] (overwrite=True: dEhat is a scratch
-        buffer that may be stored to directly)."""
-        Z, ldz, Ehat, shat = tape['Z'], tape['ldz'], tape['Ehat'], tape['shat']
+    def _head_fwd_sharded(self, Z, ldz, lse_local, batch, mode, tape):
+        import torch.distributed as dist
+        if mode != 'loss':
+            raise _lib.SessRecError('catalog-sharded mode supports loss() / train_step() only')
+        cat, B = tape['cat'], batch.B
+        lo, hi = cat['lo'], cat['hi']
+        lab = batch.labels
+        own = (lab >= lo) & (lab < hi)
+        ll = torch.where(own, lab - lo, torch.full_like(lab, -1))          # label column inside this shard, else -1
+        nll = torch.empty(B, dtype=torch.float32, device=Z.device)
+        ops.ce_rows_fwd(Z, ldz, ll, B, hi - lo, False, lse_local, nll)      # local log-sum-exp; nll = 0 where not owned
+        m = lse_local.clone()
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self._shard)
+        pack = torch.stack([torch.exp(lse_local - m), torch.where(own, lse_local - nll, torch.zeros_like(nll))])
+        dist.all_reduce(pack, group=self._shard)                           # [2, B]: sum of exp, label logit
+        lse = m + torch.log(pack[0])
+        tape['lse'], tape['labels'] = lse, ll
+        return (lse - pack[1]).mean()
+
+    def _head_bwd(self, tape, batch, mode, gout, gE, E):
+        """Backward of the head: returns d shat [B, d] and adds the catalog's share of the table gradient into gE."""
+        cat = tape['cat']
+        Z, ldz, Ehat, shat, umma = tape['Z'], tape['ldz'], cat['Ehat'], tape['shat'], cat['umma']
+        lo, hi = cat['lo'], cat['hi']
         B, (V, d) = batch.B, Ehat.shape
-        umma = tape['umma']
+        dev = Z.device
         Zlo = torch.empty_like(Z) if umma else None
         if mode == 'loss':
-            ops.ce_rows_bwd(Z, ldz, batch.labels, tape['lse'], gout.reshape(1), tape['scale'], B, V, False, Zlo)
+            ops.ce_rows_bwd(Z, ldz, tape['labels'], tape['lse'], gout.reshape(1), tape['scale'], B, V, False, Zlo)
             dZ = Z
         else:
             dZ = torch.empty_like(Z)
             ops.logp_bwd(Z, ldz, gout, gout.stride(0), tape['scale'], B, V, dZ, ldz, Zlo)
-        dshat = torch.zeros(B, d, dtype=torch.float32, device=Z.device)
+        direct = cat['norm_mode'] == NORM_NONE and self._shard is None       # SRGNN: dE accumulates straight into gE
+        if direct:
+            dEhat = gE
+        elif umma:
+            dEhat = torch.empty(V, d, dtype=torch.float32, device=dev)
+        else:
+            dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
+        dshat = torch.zeros(B, d, dtype=torch.float32, device=dev)
         if umma:
             nkb = (V + 31) // 32
-            split = max(1, min(nkb, 296 // ((B + 127) // 128)))
-            ops.umma_gemm(1, B, d, V, dZ, Zlo, ldz, tape['Ehi'], tape['Elo'], d, dshat, d, accumulate=True, split_k=split)
-            ops.umma_gemm(2, V, d, B, dZ, Zlo, ldz, tape['sh'], tape['sl'], d, dEhat, d, accumulate=not overwrite)
-            return dshat
-        ops.gemm(B, d, V, dZ, ldz, 1, Ehat, d, 1, dshat, d, accumulate=True, split_k=0)          # dZ @ Ehat
-        ops.gemm(V, d, B, dZ, 1, ldz, shat, tape['ld_s'], 1, dEhat, d, accumulate=True, split_k=0)  # dZ^T @ shat
+            split = max(1, min(nkb, 148 // ((B + 127) // 128)))
+            ops.umma_gemm(1, B, d, V, dZ, Zlo, ldz, cat['Ehi'], cat['Elo'], d, dshat, d, accumulate=True, split_k=split)
+            ops.umma_gemm(2, V, d, B, dZ, Zlo, ldz, tape['sh'], tape['sl'], d, dEhat, d, accumulate=direct)
+        else:
+            ops.gemm(B, d, V, dZ, ldz, 1, Ehat, d, 1, dshat, d, accumulate=True, split_k=0)          # dZ @ Ehat
+            ops.gemm(V, d, B, dZ, 1, ldz, shat, tape['ld_s'], 1, dEhat, d, accumulate=True, split_k=0)  # dZ^T @ shat
+        if self._shard is not None:
+            import torch.distributed as dist
+            dist.all_reduce(dshat, group=self._shard)
+            ghead = torch.zeros_like(gE)
+            if cat['norm_mode'] == NORM_NONE:
+                ops.dropout_apply(dEhat, ghead[lo:hi], dEhat.numel(), None, accumulate=True)
+            else:
+                ops.catalog_prep_bwd(E[lo:hi], Ehat, cat['enorm'], dEhat, cat['norm_mode'], ghead[lo:hi])
+            dist.all_reduce(ghead, group=self._shard)
+            ops.dropout_apply(ghead, gE, ghead.numel(), None, accumulate=True)
+        elif not direct:
+            ops.catalog_prep_bwd(E, Ehat, cat['enorm'], dEhat, cat['norm_mode'], gE)
         return dshat
 
     # ---- fused training step (body of `TrainRunner.train`, utils/train.py:95-101) ---------------------------

@@ -177,7 +177,10 @@ __global__ void __launch_bounds__(512) ce_rows_fwd_kernel(float* __restrict__ Z,
   const float l = r.m + logf(r.s);
   if (threadIdx.x == 0) {
     lse[blockIdx.x] = l;
-    if (labels) nll[blockIdx.x] = l - z[labels[blockIdx.x]];
+    if (labels) {                       // label < 0: the label's column lives on another rank (catalog sharding)
+      const int lab = labels[blockIdx.x];
+      nll[blockIdx.x] = lab >= 0 ? l - z[lab] : 0.f;
+    }
   }
   if (write_logp) {
     __syncthreads();   // thread 0 has read z[label] before anyone rewrites it

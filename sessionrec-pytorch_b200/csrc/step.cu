@@ -241,7 +241,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
   if (umma) {
     const int nkb = (V + 31) / 32;
-    int split = 296 / ((B + 127) / 128);
+    int split = 148 / ((B + 127) / 128);      // one wave of CTAs
     if (split < 1) split = 1;
     if (split > nkb) split = nkb;
     SRK_TRY(srk_umma_gemm(1, B, d, V, Z, Zlo, ldz, Ehi, Elo, d, dshat, d, 1.0f, 1, split, st));

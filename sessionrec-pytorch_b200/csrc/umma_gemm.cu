@@ -310,7 +310,9 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
   // N tile: the catalog dimension is tiled by 128; an embedding-dim N must fit one tile (multiple of 32 for the
   // MN-major 32-float chunks, <= 256)
   if (form == 0) {
-    p.BN = N >= 128 ? 128 : ((N + 15) / 16) * 16;
+    // wide tiles halve the A re-reads and the per-CTA prologue/teardown count; they need K small enough that two
+    // 96 KB stages cover most of the K loop
+    p.BN = N >= 256 && K <= 128 ? 256 : (N >= 128 ? 128 : ((N + 15) / 16) * 16);
   } else {
     p.BN = ((N + 31) / 32) * 32;
   }

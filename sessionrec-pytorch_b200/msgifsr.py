@@ -359,12 +359,7 @@ class MSGIFSR(SessRecModule):
         tape = dict(batch=batch, p=p, seed=seed, mode=mode)
         # nn.Embedding(max_norm=1): touched rows are renormed at the gather, all rows at the scoring head
         # (msgifsr.py:247,276).  Rows are independent, so one pre-pass over the catalog does both.
-        Ehat = torch.empty_like(E)
-        enorm = torch.empty(V, dtype=torch.float32, device=dev)
-        Ehi = Elo = None
-        if self.use_tensor_cores and d <= 256:
-            Ehi, Elo = torch.empty_like(E), torch.empty_like(E)
-        ops.catalog_prep_fwd(E, NORM_L2, 1.0, Ehat, enorm, Ehi, Elo)
+        self._catalog_fwd(E, NORM_L2, 1.0, tape)
         t1 = batch.types[1]
         N = t1['N']
         dc_e = ops.drop_cfg(p, SITE_EMBED + 1, seed) if p > 0 else None
@@ -402,8 +397,9 @@ class MSGIFSR(SessRecModule):
         rn_s = torch.empty(B, dtype=torch.float32, device=dev)
         ops.rownorm_fwd(s, d, B, d, NORM_L2, shat, d, rn_s)
         tape.update(X=X, rnX=rnX, dc_e=dc_e, etapes=etapes, ltapes=ltapes, h=h, rows=rows, seg=seg, last_row=last_row, u=u,
-                    v=v, e=e, ms=ms, sr_in=sr_in, s=s, rn_s=rn_s, enorm=enorm)
-        out = self._head_fwd(shat, d, Ehat, SCALE, batch, mode, tape, Ehi, Elo)
+                    v=v, e=e, ms=ms, sr_in=sr_in, s=s, rn_s=rn_s)
+        tape['shat_out'] = shat
+        out = self._head_fwd(shat, d, SCALE, batch, mode, tape)
         return out, (tape if need_grad else None)
 
     def _bwd(self, tape, gout, gflat):
@@ -414,12 +410,7 @@ class MSGIFSR(SessRecModule):
         dev = E.device
         g = lambda name: fp.view(gflat, name)          # noqa: E731
         gE = g('embeddings.weight')
-        if tape['umma']:
-            dEhat = torch.empty(V, d, dtype=torch.float32, device=dev)
-        else:
-            dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
-        dshat = self._head_bwd(tape, batch, tape['mode'], gout, dEhat, overwrite=True)
-        ops.catalog_prep_bwd(E, tape['Ehat'], tape['enorm'], dEhat, NORM_L2, gE)
+        dshat = self._head_bwd(tape, batch, tape['mode'], gout, gE, E)
         ds = torch.empty(B, d, dtype=torch.float32, device=dev)
         ops.rownorm_bwd(tape['s'], d, tape['shat'], d, tape['rn_s'], dshat, d, B, d, NORM_L2, ds, d)
         sr_in, rows, u, v, h = tape['sr_in'], tape['rows'], tape['u'], tape['v'], tape['h']

@@ -176,6 +176,10 @@ def logp_bwd(LP, ldlp, G, ldg, scale, B, V, DZ, lddz, DZlo=None):
     _call('srk_logp_bwd', ptr(LP), ldlp, ptr(G), ldg, float(scale), B, V, ptr(DZ), lddz, ptr(DZlo))
 
 
+def topk_rows(Z, ldz, B, V, k, out_idx, out_val=None):
+    _call('srk_topk_rows', ptr(Z), ldz, B, V, k, ptr(out_idx), ptr(out_val))
+
+
 # ---- GGNN ----------------------------------------------------------------------------------------------------
 
 def ggnn_aggregate_fwd(X, N, d, rel, NN, wsum):

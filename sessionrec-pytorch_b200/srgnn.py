@@ -146,21 +146,17 @@ class SRGNN(SessRecModule):
             ops.gather_rows(X, t['last'], B, d, sr_in, 2 * d)          # sr_l uses the once-dropped rows
         s = torch.empty(B, d, dtype=torch.float32, device=dev)
         ops.linear_nt(sr_in, self.fc_sr.weight, s)
-        Ehi = Elo = None
         if self.niser:
             shat = torch.empty_like(s)
             rn_s = torch.empty(B, dtype=torch.float32, device=dev)
             ops.rownorm_fwd(s, d, B, d, NORM_EPS, shat, d, rn_s)
-            Ehat = torch.empty_like(E)
-            enorm = torch.empty(self.num_items, dtype=torch.float32, device=dev)
-            if self.use_tensor_cores and d <= 256:
-                Ehi, Elo = torch.empty_like(E), torch.empty_like(E)
-            ops.catalog_prep_fwd(E, NORM_EPS, 0.0, Ehat, enorm, Ehi, Elo)
-            tape.update(s=s, rn_s=rn_s, enorm=enorm)
+            self._catalog_fwd(E, NORM_EPS, 0.0, tape)
+            tape.update(s=s, rn_s=rn_s)
         else:
-            shat, Ehat = s, E
+            shat = s
+            self._catalog_fwd(E, NORM_NONE, 0.0, tape)
         tape.update(X=X, rn=rn, F=F, u=u, v=v, e=e, ms=ms, sr_in=sr_in, dc_e=dc_e, dc_r=dc_r, emb_mode=emb_mode)
-        out = self._head_fwd(shat, d, Ehat, float(self.scale) if self.scale else 1.0, batch, mode, tape, Ehi, Elo)
+        out = self._head_fwd(shat, d, float(self.scale) if self.scale else 1.0, batch, mode, tape)
         return out, (tape if need_grad else None)
 
     def _bwd(self, tape, gout, gflat):
@@ -172,13 +168,11 @@ class SRGNN(SessRecModule):
         g = lambda name: fp.view(gflat, name)          # noqa: E731
         gE = g('embedding.weight')
         if self.niser:
-            dEhat = (torch.empty if tape['umma'] else torch.zeros)(V, d, dtype=torch.float32, device=dev)
-            dshat = self._head_bwd(tape, batch, tape['mode'], gout, dEhat, overwrite=True)
-            ops.catalog_prep_bwd(E, tape['Ehat'], tape['enorm'], dEhat, NORM_EPS, gE)
+            dshat = self._head_bwd(tape, batch, tape['mode'], gout, gE, E)
             ds = torch.empty(B, d, dtype=torch.float32, device=dev)
             ops.rownorm_bwd(tape['s'], d, tape['shat'], d, tape['rn_s'], dshat, d, B, d, NORM_EPS, ds, d)
         else:
-            ds = self._head_bwd(tape, batch, tape['mode'], gout, gE)
+            ds = self._head_bwd(tape, batch, tape['mode'], gout, gE, E)
         sr_in, F, u, v = tape['sr_in'], tape['F'], tape['u'], tape['v']
         dsr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
         ops.mm_nn(ds, self.fc_sr.weight, dsr_in)

@@ -281,3 +281,28 @@ def test_segmean(pkg, ops):
     out = torch.empty(B, d, device=DEV)
     ops.segmean_fwd(X.to(DEV), t['seg'], B, d, out)
     assert_close('segmean', out, ref, rtol=1e-6)
+
+
+@pytest.mark.parametrize('V', [300, 4099, 43097])
+def test_topk_rows(ops, V):
+    B, k = 33, 20
+    ldz = (V + 3) // 4 * 4
+    g = torch.Generator().manual_seed(V)
+    Z = torch.randn(B, V, generator=g) * 3
+    Z[0, :50] = 1.25                      # exact ties: lowest ids win
+    Z[1] = -7.0                           # fully degenerate row
+    Z[2, 17] = float('inf')
+    Zd = torch.zeros(B, ldz, device=DEV)
+    Zd[:, :V] = Z.to(DEV)
+    idx = torch.empty(B, k, dtype=torch.int32, device=DEV)
+    val = torch.empty(B, k, device=DEV)
+    ops.topk_rows(Zd, ldz, B, V, k, idx, val)
+    rv, ri = Z.topk(k)
+    assert torch.equal(val.cpu(), rv), 'top-k values must match torch.topk exactly'
+    got = idx.cpu().long()
+    for b in range(B):
+        if b in (0, 1):
+            continue
+        assert torch.equal(got[b], ri[b]), (b, got[b], ri[b])
+    assert got[1].tolist() == list(range(k))
+    assert set(got[0].tolist()) == set(Z[0].topk(k)[1].tolist()) or (Z[0][got[0]] >= Z[0].topk(k)[0][-1]).all()

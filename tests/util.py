@@ -64,6 +64,21 @@ def assert_grad_close(name, got, ref, rtol=RTOL):
     assert err <= rtol * scale, f'{name}: max|d|={err:.3e} vs max|ref|={float(ref.abs().max()):.3e} (rel {err / scale:.2e})'
 
 
+def assert_grad_close_robust(name, got, ref, rtol=RTOL, outlier_frac=0.005, outlier_rtol=5e-3):
+    """Like assert_grad_close, but tolerates a handful of elements (<= max(2, 0.5%)) that are off by up to 5e-3 of the
+    max-norm: with dropout a near-tie (< 1e-6) in the max over the 8 GAT heads can resolve differently in fp32 on the
+    two sides and re-route one node's gradient to another head."""
+    if ref is None:
+        return assert_grad_close(name, got, ref, rtol)
+    g, r = got.detach().cpu().double(), ref.detach().cpu().double()
+    assert g.shape == r.shape and torch.isfinite(g).all(), name
+    scale = max(float(r.abs().max()), 1e-3)
+    err = (g - r).abs()
+    bad = int((err > rtol * scale).sum())
+    assert bad <= max(2, int(outlier_frac * err.numel())) and float(err.max()) <= outlier_rtol * scale, \
+        f'{name}: {bad}/{err.numel()} elements beyond {rtol:g}, max|d|={float(err.max()):.3e} vs max|ref|={scale:.3e}'
+
+
 def run_oracle(case_model, params, ob, L=1, fusion=False, drop=OM.NO_DROPOUT):
     if case_model == 'MSGIFSR':
         return OM.msgifsr_forward(params, ob, drop=drop, num_layers=L, fusion=fusion)
