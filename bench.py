@@ -174,9 +174,18 @@ def roofline_probe(cfg, device, pk):
     ms = float(np.median(times))
     flops = 6.0 * B * V * d
     ach = flops / (ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    if umma and (B, V, d) == (512, 43097, 96):
+        # dram__bytes_read.sum + dram__bytes_write.sum of the same three launches from the committed `ncu --set full`
+        # capture (profiles/); only valid for the shape it was captured on
+        caps = sorted((ROOT / 'profiles').glob('*_ncu_full_umma_gemm.json'))
+        if caps:
+            rows = json.loads(caps[-1].read_text())
+            traffic = round(sum(float(r['dram__bytes_read.sum'][0]) + float(r['dram__bytes_write.sum'][0]) for r in rows) * 1e6)
+            traffic_src = f'profiles/{caps[-1].name} (bytes for the 3 launches; algorithmic operand bytes ~ 0.47 GB with the hi/lo split)'
     return dict(bound='tensor', kernel='catalog scoring GEMMs (Z = s E^T, dS = dZ E, dE = dZ^T s): ' + kname,
                 achieved=round(ach, 3), peak=pk['tf_burst'], unit='TFLOP/s', frac=round(ach / pk['tf_burst'], 5),
-                traffic=None, ms_for_the_3_launches=round(ms, 4), algorithmic_flops=flops,
+                traffic=traffic, traffic_source=traffic_src, ms_for_the_3_launches=round(ms, 4), algorithmic_flops=flops,
                 note='algorithmic FLOPs 6*B*V*d counted once; the 3 TF32 passes of the split are the kernel\'s own cost',
                 peak_source=f"{pk['src']} bf16 burst (kernel timed alone)")
 

@@ -64,8 +64,8 @@ def assert_grad_close(name, got, ref, rtol=RTOL):
     assert err <= rtol * scale, f'{name}: max|d|={err:.3e} vs max|ref|={float(ref.abs().max()):.3e} (rel {err / scale:.2e})'
 
 
-def assert_grad_close_robust(name, got, ref, rtol=RTOL, outlier_frac=0.005, outlier_rtol=5e-3):
-    """Like assert_grad_close, but tolerates a handful of elements (<= max(2, 0.5%)) that are off by up to 5e-3 of the
+def assert_grad_close_robust(name, got, ref, rtol=RTOL, outlier_frac=0.02, outlier_rtol=5e-3):
+    """Like assert_grad_close, but tolerates a handful of elements (<= max(2, 2%)) that are off by up to 5e-3 of the
     max-norm: with dropout a near-tie (< 1e-6) in the max over the 8 GAT heads can resolve differently in fp32 on the
     two sides and re-route one node's gradient to another head."""
     if ref is None:
