@@ -190,6 +190,56 @@ def roofline_probe(cfg, device, pk):
                 peak_source=f"{pk['src']} bf16 burst (kernel timed alone)")
 
 
+def gather_scatter_probe(device, pk, shapes=None):
+    """HBM roofline of the embedding gather (K1) and the gradient scatter-add (K8) kernels, timed alone with CUDA
+    events: the BASELINE config-2 shape (table L2-resident) and a stress shape whose table is far larger than L2.
+    Algorithmic bytes: gather N*(4 + 2*4d), scatter N*(4 + 4d) + 2*U*4d (int32 indices)."""
+    from sessionrec_pytorch_b200 import ops
+    out = []
+    shapes = shapes or [('cfg2 shape: V=17000 d=256 N=9000 (table 17 MB, L2-resident)', 17000, 256, 9000),
+                        ('stress: V=4M d=256 N=1M (table 4.1 GB >> 126 MB L2)', 4_000_000, 256, 1_000_000)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    for name, V, d, N in shapes:
+        g = torch.Generator().manual_seed(7)
+        E = torch.empty(V, d, device=device).normal_()
+        iid_h = torch.randint(0, V, (N,), generator=g, dtype=torch.int32)
+        order = torch.argsort(iid_h.long(), stable=True).int()
+        uid_h, cnt = torch.unique(iid_h.long(), return_counts=True)
+        uoff_h = torch.zeros(uid_h.numel() + 1, dtype=torch.int32)
+        uoff_h[1:] = torch.cumsum(cnt, 0).int()
+        t = dict(iid=iid_h.to(device), perm=order.to(device), uoff=uoff_h.to(device), uid=uid_h.int().to(device),
+                 U=int(uid_h.numel()), P=N)
+        X = torch.empty(N, d, device=device)
+        rn = torch.empty(N, device=device)
+        dE = torch.zeros(V, d, device=device)
+
+        def timeit(fn):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(7):
+                flush.fill_(0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.median(ts))
+        ms_g = timeit(lambda: ops.embed_gather_fwd(E, t['iid'], N, d, 2, None, X, rn))
+        ms_s = timeit(lambda: ops.embed_scatter_bwd(E, t, d, 2, None, rn, X, None, dE))
+        bg = N * (4 + 2 * 4 * d)
+        bs = N * (4 + 4 * d) + 2 * t['U'] * 4 * d
+        for kname, ms, by in (('gather_fwd_kernel (K1: gather + L2 normalise)', ms_g, bg),
+                              ('scatter_bwd_kernel (K8: normalise-backward + scatter-add)', ms_s, bs)):
+            ach = by / (ms * 1e-3) / 1e9
+            out.append(dict(bound='hbm', kernel=kname, shape=name, achieved=round(ach, 1), peak=pk['hbm'], unit='GB/s',
+                            frac=round(ach / pk['hbm'], 4), ms=round(ms, 4), algorithmic_bytes=by, traffic=None))
+        del E, X, dE
+        torch.cuda.empty_cache()
+    return out
+
+
 def reference_arm(args, cfg, rank):
     if rank != 0:
         return
@@ -222,6 +272,7 @@ def main():
     ap.add_argument('--workload', default='cfg1')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gather-probe', action='store_true')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -317,6 +368,7 @@ def main():
     out = None
     if rank == 0:
         roof = roofline_probe(cfg, device, pk)
+        roof_gs = gather_scatter_probe(device, pk) if not args.no_gather_probe else None
         out = {
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': round(total_ms / args.steps, 4), 'higher_is_better': True,
@@ -328,7 +380,7 @@ def main():
             'e2e': dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=int(h2d / args.steps), d2h_bytes_per_step=4,
                         timing='wall clock over K steps incl. H2D batch copy + loss.item() per step'),
             'wall_s_timed_region': round(t_wall, 4), 'host_enqueue_ms_per_step': round(1e3 * enqueue_s / args.steps, 4),
-            'roofline': roof,
+            'roofline': roof, 'roofline_gather_scatter': roof_gs,
         }
     if world > 1:
         dist.barrier()

@@ -154,6 +154,20 @@ int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse
 int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V, float* DZ,
                  long long lddz, float* DZlo, void* stream);
 
+/* ---- order-fusion head of MSGIFSR (msgifsr.py:311-315,321): out = log sum_k a_k softmax(Z_k), a = softmax(alpha) ----
+ * Zall[K][B][ldz] (head_stride floats apart) are the per-order scaled logits, lse[K][B] their row log-sum-exps, alpha[K]
+ * the un-normalised mixture logits on the DEVICE (softmax taken in-kernel, no host sync).  srk_mix_bwd rewrites Zall in place with d loss / d Z_k (optionally as a TF32 hi/lo pair)
+ * from an upstream gradient G[B, ldg] of the log-probs, or (G == NULL) from the labels of the fused mean-NLL loss; rsum[K][B]
+ * receives sum_v G q_k, from which d alpha follows. */
+int srk_mix_logp_fwd(const float* Zall, long long head_stride, long long ldz, const float* lse, const float* alpha, int K,
+                     int B, int V, float* out, long long ldo, void* stream);
+int srk_mix_loss_fwd(const float* nll, const float* alpha, int K, int B, float* loss_out, void* stream);
+int srk_mix_bwd(float* Zall, float* Zlo_all, long long head_stride, long long ldz, const float* lse, const float* alpha,
+                int K, int B, int V, const float* G, long long ldg, const int* labels, const float* gscale, float scale,
+                float* rsum, void* stream);
+
+int srk_mix_alpha_bwd(const float* rsum, const float* alpha, int K, int B, float* dalpha, void* stream);
+
 /* Fused evaluation head (next-row: evaluate(), utils/train.py:36-55): per row the ids (and optionally values) of the k
  * largest logits, sorted descending, ties by ascending id.  Replaces materialising log-probs + `logits.topk(k)`. */
 int srk_topk_rows(const float* Z, long long ldz, int B, int V, int k, int* out_idx, float* out_val, void* stream);

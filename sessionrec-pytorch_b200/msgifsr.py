@@ -349,8 +349,6 @@ class MSGIFSR(SessRecModule):
             raise SessRecError('MSGIFSR extra=True (REnorm head) is not built; the reference scripts default to False')
         if not self.norm:
             raise SessRecError('MSGIFSR norm=False is not built (the reference argparse can only produce True)')
-        if self.order > 1 and self.fusion:
-            raise SessRecError('MSGIFSR fusion=True is not built yet (reference scripts default to False)')
         if self.num_layers == 0:
             raise SessRecError('MSGIFSR needs num_layers >= 1')
         K, d, B, V, dev = self.order, self.embedding_dim, batch.B, self.num_items, self.embeddings.weight.device
@@ -383,24 +381,90 @@ class MSGIFSR(SessRecModule):
                 ops.scatter_add_rows(h[k], d, batch.types[k]['row_of'], batch.types[k]['N'], d, rows)
             seg, last_row = batch.row_seg, t1['last_row']
         R = rows.shape[0]
-        u = torch.empty(R, d, dtype=torch.float32, device=dev)
-        v = torch.empty(B, d, dtype=torch.float32, device=dev)
-        ops.linear_nt(rows, self.readout.fc_u[0].weight, u, bias=self.readout.fc_u[0].bias)
-        ops.linear_nt(h[1], self.readout.fc_v[0].weight, v, M=B, a_idx=t1['last'])
-        e = torch.empty(R, dtype=torch.float32, device=dev)
-        ms = torch.empty(B, 2, dtype=torch.float32, device=dev)
-        sr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
-        ops.readout_fwd(rows, u, v, self.readout.fc_e[0].weight, seg, last_row, B, d, True, e, ms, sr_in)
-        s = torch.empty(B, d, dtype=torch.float32, device=dev)
-        ops.linear_nt(sr_in, self.fc_sr[0].weight, s)
-        shat = torch.empty_like(s)
-        rn_s = torch.empty(B, dtype=torch.float32, device=dev)
-        ops.rownorm_fwd(s, d, B, d, NORM_L2, shat, d, rn_s)
-        tape.update(X=X, rnX=rnX, dc_e=dc_e, etapes=etapes, ltapes=ltapes, h=h, rows=rows, seg=seg, last_row=last_row, u=u,
-                    v=v, e=e, ms=ms, sr_in=sr_in, s=s, rn_s=rn_s)
-        tape['shat_out'] = shat
-        out = self._head_fwd(shat, d, SCALE, batch, mode, tape)
+        heads = list(range(K)) if (K > 1 and self.fusion) else [0]
+        hd = []
+        for i in heads:
+            ti = batch.types[i + 1]
+            u = torch.empty(R, d, dtype=torch.float32, device=dev)
+            v = torch.empty(B, d, dtype=torch.float32, device=dev)
+            ops.linear_nt(rows, self.readout.fc_u[i].weight, u, bias=self.readout.fc_u[i].bias)
+            ops.linear_nt(h[i + 1], self.readout.fc_v[i].weight, v, M=B, a_idx=ti['last'])
+            e = torch.empty(R, dtype=torch.float32, device=dev)
+            ms = torch.empty(B, 2, dtype=torch.float32, device=dev)
+            sr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
+            last_row = ti['last'] if K == 1 else ti['last_row']
+            ops.readout_fwd(rows, u, v, self.readout.fc_e[i].weight, seg, last_row, B, d, True, e, ms, sr_in)
+            s = torch.empty(B, d, dtype=torch.float32, device=dev)
+            ops.linear_nt(sr_in, self.fc_sr[i].weight, s)
+            shat = torch.empty_like(s)
+            rn_s = torch.empty(B, dtype=torch.float32, device=dev)
+            ops.rownorm_fwd(s, d, B, d, NORM_L2, shat, d, rn_s)
+            hd.append(dict(i=i, u=u, v=v, e=e, ms=ms, sr_in=sr_in, s=s, shat=shat, rn_s=rn_s, last_row=last_row))
+        tape.update(X=X, rnX=rnX, dc_e=dc_e, etapes=etapes, ltapes=ltapes, h=h, rows=rows, seg=seg, heads=hd)
+        if len(heads) == 1:
+            out = self._head_fwd(hd[0]['shat'], d, SCALE, batch, mode, tape)
+        else:
+            out = self._fusion_head_fwd(hd, batch, mode, tape)
         return out, (tape if need_grad else None)
+
+    # ---- order-fusion head (msgifsr.py:311-315): log sum_k softmax(alpha)_k softmax(12 sr_k E^T) --------------------
+    def _fusion_head_fwd(self, hd, batch, mode, tape):
+        if self._shard is not None:
+            raise SessRecError('catalog sharding with the order-fusion head is not built')
+        cat = tape['cat']
+        Ehat, umma = cat['Ehat'], cat['umma']
+        K, B, (V, d) = len(hd), batch.B, Ehat.shape
+        dev = Ehat.device
+        ldz = (V + 3) // 4 * 4
+        Zall = torch.empty(K, B, ldz, dtype=torch.float32, device=dev)
+        lse = torch.empty(K, B, dtype=torch.float32, device=dev)
+        nll = torch.empty(K, B, dtype=torch.float32, device=dev)
+        for k, hk in enumerate(hd):
+            if umma:
+                hk['sh'], hk['sl'] = torch.empty_like(hk['shat']), torch.empty_like(hk['shat'])
+                ops.split_tf32(hk['shat'], d, B, d, hk['sh'], hk['sl'], d)
+                ops.umma_gemm(0, B, V, d, hk['sh'], hk['sl'], d, cat['Ehi'], cat['Elo'], d, Zall[k], ldz, alpha=SCALE)
+            else:
+                ops.gemm(B, V, d, hk['shat'], d, 1, Ehat, 1, d, Zall[k], ldz, alpha=SCALE)
+            ops.ce_rows_fwd(Zall[k], ldz, batch.labels if mode == 'loss' else None, B, V, False, lse[k], nll[k])
+        tape.update(Zall=Zall, ldz=ldz, lse_all=lse, fusion=True)
+        if mode == 'loss':
+            out = torch.empty((), dtype=torch.float32, device=dev)
+            ops.mix_loss_fwd(nll, self.alpha, K, B, out)
+            return out
+        out = torch.empty(B, ldz, dtype=torch.float32, device=dev)
+        ops.mix_logp_fwd(Zall, B * ldz, ldz, lse, self.alpha, K, B, V, out, ldz)
+        return out[:, :V]
+
+    def _fusion_head_bwd(self, tape, batch, mode, gout, gE, E, g):
+        cat, hd = tape['cat'], tape['heads']
+        Ehat, umma = cat['Ehat'], cat['umma']
+        K, B, (V, d) = len(hd), batch.B, Ehat.shape
+        dev = Ehat.device
+        Zall, ldz = tape['Zall'], tape['ldz']
+        Zlo = torch.empty_like(Zall) if umma else None
+        rsum = torch.empty(K, B, dtype=torch.float32, device=dev)
+        if mode == 'loss':
+            ops.mix_bwd(Zall, Zlo, B * ldz, ldz, tape['lse_all'], self.alpha, K, B, V, None, 0, batch.labels, gout.reshape(1),
+                        SCALE, rsum)
+        else:
+            ops.mix_bwd(Zall, Zlo, B * ldz, ldz, tape['lse_all'], self.alpha, K, B, V, gout, gout.stride(0), None, None, SCALE,
+                        rsum)
+        ops.mix_alpha_bwd(rsum, self.alpha, K, B, g('alpha'))
+        dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
+        out = []
+        for k, hk in enumerate(hd):
+            dshat = torch.zeros(B, d, dtype=torch.float32, device=dev)
+            if umma:
+                split = max(1, min((V + 31) // 32, 148 // ((B + 127) // 128)))
+                ops.umma_gemm(1, B, d, V, Zall[k], Zlo[k], ldz, cat['Ehi'], cat['Elo'], d, dshat, d, accumulate=True, split_k=split)
+                ops.umma_gemm(2, V, d, B, Zall[k], Zlo[k], ldz, hk['sh'], hk['sl'], d, dEhat, d, accumulate=True)
+            else:
+                ops.gemm(B, d, V, Zall[k], ldz, 1, Ehat, d, 1, dshat, d, accumulate=True, split_k=0)
+                ops.gemm(V, d, B, Zall[k], 1, ldz, hk['shat'], d, 1, dEhat, d, accumulate=True, split_k=0)
+            out.append(dshat)
+        ops.catalog_prep_bwd(E, Ehat, cat['enorm'], dEhat, NORM_L2, gE)
+        return out
 
     def _bwd(self, tape, gout, gflat):
         fp, batch = self._flat, tape['batch']
@@ -410,20 +474,30 @@ class MSGIFSR(SessRecModule):
         dev = E.device
         g = lambda name: fp.view(gflat, name)          # noqa: E731
         gE = g('embeddings.weight')
-        dshat = self._head_bwd(tape, batch, tape['mode'], gout, gE, E)
-        ds = torch.empty(B, d, dtype=torch.float32, device=dev)
-        ops.rownorm_bwd(tape['s'], d, tape['shat'], d, tape['rn_s'], dshat, d, B, d, NORM_L2, ds, d)
-        sr_in, rows, u, v, h = tape['sr_in'], tape['rows'], tape['u'], tape['v'], tape['h']
+        hd, rows, h = tape['heads'], tape['rows'], tape['h']
+        if tape.get('fusion'):
+            dshats = self._fusion_head_bwd(tape, batch, tape['mode'], gout, gE, E, g)
+        else:
+            dshats = [self._head_bwd(tape, batch, tape['mode'], gout, gE, E)]
         R = rows.shape[0]
-        dsr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
-        ops.mm_nn(ds, self.fc_sr[0].weight, dsr_in)
-        ops.mm_tn(ds, sr_in, g('fc_sr.0.weight'))
-        drows = torch.empty(R, d, dtype=torch.float32, device=dev)
-        ops.readout_bwd(rows, u, v, self.readout.fc_e[0].weight, tape['seg'], tape['last_row'], tape['e'], tape['ms'], sr_in,
-                        dsr_in, B, d, True, drows, g('readout.fc_e.0.weight'))
-        ops.mm_nn(u, self.readout.fc_u[0].weight, drows, accumulate=True)
-        ops.mm_tn(u, rows, g('readout.fc_u.0.weight'))
-        ops.colsum(u, d, R, d, g('readout.fc_u.0.bias'))
+        drows = None
+        for hk, dshat in zip(hd, dshats):
+            i = hk['i']
+            ds = torch.empty(B, d, dtype=torch.float32, device=dev)
+            ops.rownorm_bwd(hk['s'], d, hk['shat'], d, hk['rn_s'], dshat, d, B, d, NORM_L2, ds, d)
+            dsr_in = torch.empty(B, 2 * d, dtype=torch.float32, device=dev)
+            ops.mm_nn(ds, self.fc_sr[i].weight, dsr_in)
+            ops.mm_tn(ds, hk['sr_in'], g(f'fc_sr.{i}.weight'))
+            dr = torch.empty(R, d, dtype=torch.float32, device=dev)
+            ops.readout_bwd(rows, hk['u'], hk['v'], self.readout.fc_e[i].weight, tape['seg'], hk['last_row'], hk['e'], hk['ms'],
+                            hk['sr_in'], dsr_in, B, d, True, dr, g(f'readout.fc_e.{i}.weight'))
+            ops.mm_nn(hk['u'], self.readout.fc_u[i].weight, dr, accumulate=True)            # u holds du
+            ops.mm_tn(hk['u'], rows, g(f'readout.fc_u.{i}.weight'))
+            ops.colsum(hk['u'], d, R, d, g(f'readout.fc_u.{i}.bias'))
+            if drows is None:
+                drows = dr
+            else:
+                ops.dropout_apply(dr, drows, dr.numel(), None, accumulate=True)
         if K == 1:
             dH = {1: drows}
         else:
@@ -432,8 +506,11 @@ class MSGIFSR(SessRecModule):
                 Nk = batch.types[k]['N']
                 dH[k] = torch.empty(Nk, d, dtype=torch.float32, device=dev)
                 ops.gather_rows(drows, batch.types[k]['row_of'], Nk, d, dH[k], d)
-        ops.mm_nn(v, self.readout.fc_v[0].weight, dH[1], c_idx=t1['last'], accumulate=True)
-        ops.mm_tn(v, h[1], g('readout.fc_v.0.weight'), b_idx=t1['last'])
+        for hk in hd:
+            i = hk['i']
+            ti = batch.types[i + 1]
+            ops.mm_nn(hk['v'], self.readout.fc_v[i].weight, dH[i + 1], c_idx=ti['last'], accumulate=True)     # v holds dv
+            ops.mm_tn(hk['v'], h[i + 1], g(f'readout.fc_v.{i}.weight'), b_idx=ti['last'])
         for l in reversed(range(self.num_layers)):
             dH = self._layer_bwd(l, batch, tape['ltapes'][l], dH, g)
         for k in range(2, K + 1):

@@ -180,6 +180,23 @@ def topk_rows(Z, ldz, B, V, k, out_idx, out_val=None):
     _call('srk_topk_rows', ptr(Z), ldz, B, V, k, ptr(out_idx), ptr(out_val))
 
 
+def mix_logp_fwd(Zall, head_stride, ldz, lse, alpha, K, B, V, out, ldo):
+    _call('srk_mix_logp_fwd', ptr(Zall), head_stride, ldz, ptr(lse), ptr(alpha), K, B, V, ptr(out), ldo)
+
+
+def mix_loss_fwd(nll, alpha, K, B, out):
+    _call('srk_mix_loss_fwd', ptr(nll), ptr(alpha), K, B, ptr(out))
+
+
+def mix_bwd(Zall, Zlo, head_stride, ldz, lse, alpha, K, B, V, G, ldg, labels, gscale, scale, rsum):
+    _call('srk_mix_bwd', ptr(Zall), ptr(Zlo), head_stride, ldz, ptr(lse), ptr(alpha), K, B, V, ptr(G), ldg, ptr(labels),
+          ptr(gscale), float(scale), ptr(rsum))
+
+
+def mix_alpha_bwd(rsum, alpha, K, B, dalpha):
+    _call('srk_mix_alpha_bwd', ptr(rsum), ptr(alpha), K, B, ptr(dalpha))
+
+
 # ---- GGNN ----------------------------------------------------------------------------------------------------
 
 def ggnn_aggregate_fwd(X, N, d, rel, NN, wsum):

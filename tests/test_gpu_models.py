@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 MODELS = golden('models_golden.pt')
 TRAINS = golden('train_golden.pt')
-BUILT = [n for n, c in MODELS.items() if not c['fusion']]      # order-fusion head: not built yet
+BUILT = list(MODELS)
 
 
 def make_model(pkg, c, dropout=0.0):
@@ -87,7 +87,8 @@ def test_fused_loss_path_vs_reference_golden(pkg, name):
         assert_grad_close(f'{name}.grad[{n}]', params[n].grad, g)
 
 
-@pytest.mark.parametrize('name', ['srgnn', 'niser', 'msgifsr_k1', 'msgifsr_k1_inflate_L2', 'msgifsr_k2', 'msgifsr_k3'])
+@pytest.mark.parametrize('name', ['srgnn', 'niser', 'msgifsr_k1', 'msgifsr_k1_inflate_L2', 'msgifsr_k2', 'msgifsr_k3',
+                                  'msgifsr_k2_fusion'])
 @pytest.mark.parametrize('p', [0.2, 0.5])
 def test_dropout_with_injected_masks_vs_oracle(pkg, name, p):
     """Training mode with dropout: the oracle consumes the same counter-based masks the kernels regenerate."""
