@@ -149,6 +149,10 @@ int srk_mean(const float* x, int n, float* out, void* stream);
  * the TF32 split is written instead: Z <- hi(dZ), Zlo <- dZ - hi(dZ) (operands of srk_umma_gemm). */
 int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale, float scale,
                     int B, int V, int z_is_logp, float* Zlo, void* stream);
+/* Same, restricted to the catalog columns [col0, col0 + ncols): lets the caller run the backward of the head chunk by
+ * chunk so that each chunk's dZ hi/lo pair is still L2-resident when the two GEMMs consume it. */
+int srk_ce_rows_bwd_cols(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale, float scale,
+                         int B, int col0, int ncols, float* Zlo, void* stream);
 /* Compat backward from an arbitrary upstream gradient G[B, V] of the log-probs LP:
  * dZ = scale * (G - exp(LP) * rowsum(G)), written into DZ (may alias G). */
 int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V, float* DZ,
@@ -258,7 +262,7 @@ int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, floa
                            int use_umma, void* workspace, long long workspace_bytes, const float* one_dev, float* loss_out,
                            int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat, const long long* seg_off_dev,
                            const float* seg_decay_dev, int n_seg, float lr, float beta1, float beta2, float eps,
-                           int adam_step, float grad_scale, int phase, void* stream);
+                           int adam_step, float grad_scale, int phase, int head_chunks, void* stream);
 
 /* ---- native batch builder (host; next-row: utils/data/collate.py:61-85,87-217,219-256) ---------------------------
  * Sessions are given as a flat item array + offsets. kind 0 = session graph (weights, self-loop rule), kind 1 =

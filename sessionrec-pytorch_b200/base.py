@@ -42,6 +42,7 @@ class SessRecModule(nn.Module):
         self._opt = None
         self.use_tensor_cores = os.environ.get('SESSREC_NO_UMMA', '0') != '1'
         self._shard = None
+        self.head_chunks = int(os.environ.get('SESSREC_HEAD_CHUNKS', '1')    # > 1 measured slower on B200 (profiles/r1g))
 
     # ---- parameters -------------------------------------------------------------------------------------
     def _ensure_flat(self):
@@ -190,8 +191,10 @@ class SessRecModule(nn.Module):
         B, (V, d) = batch.B, Ehat.shape
         dev = Z.device
         Zlo = torch.empty_like(Z) if umma else None
+        chunked = mode == 'loss' and umma and self.head_chunks > 1
         if mode == 'loss':
-            ops.ce_rows_bwd(Z, ldz, tape['labels'], tape['lse'], gout.reshape(1), tape['scale'], B, V, False, Zlo)
+            if not chunked:
+                ops.ce_rows_bwd(Z, ldz, tape['labels'], tape['lse'], gout.reshape(1), tape['scale'], B, V, False, Zlo)
             dZ = Z
         else:
             dZ = torch.empty_like(Z)
@@ -205,10 +208,18 @@ class SessRecModule(nn.Module):
             dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
         dshat = torch.zeros(B, d, dtype=torch.float32, device=dev)
         if umma:
-            nkb = (V + 31) // 32
-            split = max(1, min(nkb, 148 // ((B + 127) // 128)))
-            ops.umma_gemm(1, B, d, V, dZ, Zlo, ldz, cat['Ehi'], cat['Elo'], d, dshat, d, accumulate=True, split_k=split)
-            ops.umma_gemm(2, V, d, B, dZ, Zlo, ldz, tape['sh'], tape['sl'], d, dEhat, d, accumulate=direct)
+            # chunked over catalog columns (fused-loss mode): each chunk's dZ hi/lo pair stays L2-resident between the
+            # CE-backward pass that writes it and the two tensor-core GEMMs that read it
+            Vc = ((V + self.head_chunks - 1) // self.head_chunks + 255) // 256 * 256 if chunked else V
+            for c0 in range(0, V, Vc):
+                nc = min(Vc, V - c0)
+                if chunked:
+                    ops.ce_rows_bwd_cols(Z, ldz, tape['labels'], tape['lse'], gout.reshape(1), tape['scale'], B, c0, nc, Zlo)
+                split = max(1, min((nc + 31) // 32, 148 // ((B + 127) // 128)))
+                ops.umma_gemm(1, B, d, nc, dZ[:, c0:], Zlo[:, c0:], ldz, cat['Ehi'][c0:], cat['Elo'][c0:], d, dshat, d,
+                              accumulate=True, split_k=split)
+                ops.umma_gemm(2, nc, d, B, dZ[:, c0:], Zlo[:, c0:], ldz, tape['sh'], tape['sl'], d, dEhat[c0:], d,
+                              accumulate=direct)
         else:
             ops.gemm(B, d, V, dZ, ldz, 1, Ehat, d, 1, dshat, d, accumulate=True, split_k=0)          # dZ @ Ehat
             ops.gemm(V, d, B, dZ, 1, ldz, shat, tape['ld_s'], 1, dEhat, d, accumulate=True, split_k=0)  # dZ^T @ shat

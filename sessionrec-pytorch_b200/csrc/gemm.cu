@@ -99,7 +99,7 @@ __device__ __forceinline__ void store_frag(const Frag& f, float (*S)[BM + PAD], 
 
 struct GemmParams {
   GemmArgs g;
-  int a_mode, b_mode, k_chunk;
+  int a_mode, b_mode, k_chunk, k_chunk_pad;
 };
 
 __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmParams p) {
@@ -167,6 +167,84 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmParams p) {
   }
 }
 
+// Single-shot variant for short K extents (k_chunk <= 256): the whole K range of the A and B tiles is brought into
+// shared memory with ALL global loads in flight at once (one latency exposure, one barrier), then the 64x64 tile is
+// computed without further synchronisation.  The dense layers of this path (K = d ~ 100-256, or a split-K chunk of a
+// weight-gradient GEMM) are latency-bound in the pipelined kernel above: ~1 us per 16-deep k-iteration.
+constexpr int SS_MAXK = 256;
+constexpr int SS_BATCH = 8;          // k-tiles (of 16) loaded per register batch
+
+__global__ void __launch_bounds__(NT) sgemm_singleshot_kernel(const GemmParams p) {
+  extern __shared__ __align__(16) float ss_smem[];
+  const GemmArgs& g = p.g;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kBeg = blockIdx.z * p.k_chunk;
+  const int kEnd = min(g.K, kBeg + p.k_chunk);
+  const int kc = ((kEnd - kBeg) + BK - 1) / BK * BK;              // rows actually used (multiple of 16)
+  float (*As)[BM + PAD] = reinterpret_cast<float (*)[BM + PAD]>(ss_smem);
+  float (*Bs)[BN + PAD] = reinterpret_cast<float (*)[BN + PAD]>(ss_smem + (size_t)p.k_chunk_pad * (BM + PAD));
+  const int ty = tid >> 4, tx = tid & 15;
+
+  for (int kb = 0; kb < kc; kb += BK * SS_BATCH) {
+    Frag fa[SS_BATCH], fb[SS_BATCH];
+#pragma unroll
+    for (int t = 0; t < SS_BATCH; ++t) {
+      const int k0 = kBeg + kb + t * BK;
+      if (kb + t * BK < kc) {
+        load_frag<true>(fa[t], g.A, g.sa_m, g.sa_k, g.a_idx, p.a_mode, m0, k0, g.M, kEnd, tid);
+        load_frag<false>(fb[t], g.B, g.sb_n, g.sb_k, g.b_idx, p.b_mode, n0, k0, g.N, kEnd, tid);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < SS_BATCH; ++t) {
+      if (kb + t * BK < kc) {
+        store_frag(fa[t], As + kb + t * BK, p.a_mode, tid);
+        store_frag(fb[t], Bs + kb + t * BK, p.b_mode, tid);
+      }
+    }
+  }
+  __syncthreads();
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kc; ++k) {
+    float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+    float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+
+  const bool first_split = blockIdx.z == 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+    long long rc = g.c_idx ? (long long)g.c_idx[m] : (long long)m;
+    float* crow = g.C + rc * g.ldc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias && first_split) v += g.bias[n];
+      if (!g.accumulate)
+        crow[n] = v;
+      else if (gridDim.z > 1)
+        atomicAdd(crow + n, v);
+      else
+        crow[n] += v;
+    }
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -178,6 +256,8 @@ int srk_pick_split_k(int M, int N, int K) {
   long long tiles = (long long)srk_cdiv(M, BM) * srk_cdiv(N, BN);
   if (tiles >= 296 || K < 128) return 1;
   long long want = (296 + tiles - 1) / tiles;
+  long long fit = (K + 255) / 256;      // enough splits for the single-shot kernel (k chunk <= 256)
+  if (want < fit) want = fit;
   long long cap = K / 32;
   long long s = want < cap ? want : cap;
   if (s > 128) s = 128;
@@ -226,7 +306,19 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   p.k_chunk = per * BK;
   S = srk_cdiv(g.K, p.k_chunk);
   dim3 grid(srk_cdiv(g.N, BN), srk_cdiv(g.M, BM), S);
-  sgemm_kernel<<<grid, NT, 0, st>>>(p);
+  if (p.k_chunk <= SS_MAXK) {
+    p.k_chunk_pad = p.k_chunk;                      // multiple of 16 by construction
+    const size_t smem = sizeof(float) * 2 * (size_t)p.k_chunk_pad * (BM + PAD);
+    static bool attr_set = false;
+    if (!attr_set) {
+      SRK_CUDA(cudaFuncSetAttribute(sgemm_singleshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(float) * 2 * SS_MAXK * (BM + PAD))));
+      attr_set = true;
+    }
+    sgemm_singleshot_kernel<<<grid, NT, smem, st>>>(p);
+  } else {
+    sgemm_kernel<<<grid, NT, 0, st>>>(p);
+  }
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -197,12 +197,13 @@ __global__ void __launch_bounds__(512) ce_rows_fwd_kernel(float* __restrict__ Z,
 __global__ void __launch_bounds__(512) ce_rows_bwd_kernel(float* __restrict__ Z, long long ldz, const int* __restrict__ labels,
                                                           const float* __restrict__ lse, const float* __restrict__ gscale,
                                                           float scale, int B, int V, int z_is_logp,
-                                                          float* __restrict__ Zlo) {
-  float* z = Z + (long long)blockIdx.x * ldz;
-  float* zl = Zlo ? Zlo + (long long)blockIdx.x * ldz : nullptr;
+                                                          float* __restrict__ Zlo, int col0) {
+  // columns [col0, col0 + V) of every row (col0 = 0, V = catalog size for the whole matrix)
+  float* z = Z + (long long)blockIdx.x * ldz + col0;
+  float* zl = Zlo ? Zlo + (long long)blockIdx.x * ldz + col0 : nullptr;
   const float l = z_is_logp ? 0.f : lse[blockIdx.x];
   const float c = gscale[0] * scale / (float)B;
-  const int lab = labels[blockIdx.x];
+  const int lab = labels[blockIdx.x] - col0;
   const bool al = (reinterpret_cast<uintptr_t>(z) & 15u) == 0 && (!zl || (reinterpret_cast<uintptr_t>(zl) & 15u) == 0);
   const int V4 = al ? (V >> 2) : 0;
   float4* z4 = reinterpret_cast<float4*>(z);
@@ -310,7 +311,7 @@ extern "C" int srk_ce_rows_fwd(float* Z, long long ldz, const int* labels, int B
 extern "C" int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale,
                                float scale, int B, int V, int z_is_logp, float* Zlo, void* stream) {
   if (B <= 0) return SRK_OK;
-  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp, Zlo);
+  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp, Zlo, 0);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -319,6 +320,14 @@ extern "C" int srk_logp_bwd(const float* LP, long long ldlp, const float* G, lon
                             float* DZ, long long lddz, float* DZlo, void* stream) {
   if (B <= 0) return SRK_OK;
   logp_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(LP, ldlp, G, ldg, scale, V, DZ, lddz, DZlo);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_ce_rows_bwd_cols(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale,
+                                    float scale, int B, int col0, int ncols, float* Zlo, void* stream) {
+  if (B <= 0 || ncols <= 0) return SRK_OK;
+  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, ncols, 0, Zlo, col0);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -116,7 +116,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
                                       float* loss_out, int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat,
                                       const long long* seg_off_dev, const float* seg_decay_dev, int n_seg, float lr,
                                       float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase,
-                                      void* stream) {
+                                      int head_chunks, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BatchView b;
   SRK_TRY(parse_batch(batch_dev, batch_hdr_host, b));
@@ -237,16 +237,25 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   float* Zlo = umma ? ar.f((size_t)B * ldz) : nullptr;
   float *dshat = ar.f((size_t)B * d), *dEhat = ar.f((size_t)V * d);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
-  SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, one_dev, 12.0f, B, V, 0, Zlo, st));
   SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
   if (umma) {
-    const int nkb = (V + 31) / 32;
-    int split = 148 / ((B + 127) / 128);      // one wave of CTAs
-    if (split < 1) split = 1;
-    if (split > nkb) split = nkb;
-    SRK_TRY(srk_umma_gemm(1, B, d, V, Z, Zlo, ldz, Ehi, Elo, d, dshat, d, 1.0f, 1, split, st));
-    SRK_TRY(srk_umma_gemm(2, V, d, B, Z, Zlo, ldz, sh, sl, d, dEhat, d, 1.0f, 0, 1, st));
+    // Backward of the head, chunked over catalog columns so that each chunk's dZ hi/lo pair (2 x B x Vc x 4 bytes) is
+    // still L2-resident when the two tensor-core GEMMs read it (the whole pair, 2 x 88 MB at cfg1, is not).
+    int chunks = head_chunks < 1 ? 1 : head_chunks;
+    int Vc = ((V + chunks - 1) / chunks + 255) / 256 * 256;
+    for (int c0 = 0; c0 < V; c0 += Vc) {
+      const int nc = V - c0 < Vc ? V - c0 : Vc;
+      SRK_TRY(srk_ce_rows_bwd_cols(Z, ldz, b.labels, lse, one_dev, 12.0f, B, c0, nc, Zlo, st));
+      const int nkb = (nc + 31) / 32;
+      int split = 148 / ((B + 127) / 128);      // one wave of CTAs
+      if (split < 1) split = 1;
+      if (split > nkb) split = nkb;
+      SRK_TRY(srk_umma_gemm(1, B, d, nc, Z + c0, Zlo + c0, ldz, Ehi + (size_t)c0 * d, Elo + (size_t)c0 * d, d, dshat, d, 1.0f, 1,
+                            split, st));
+      SRK_TRY(srk_umma_gemm(2, nc, d, B, Z + c0, Zlo + c0, ldz, sh, sl, d, dEhat + (size_t)c0 * d, d, 1.0f, 0, 1, st));
+    }
   } else {
+    SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, one_dev, 12.0f, B, V, 0, Zlo, st));
     SRK_CUDA(cudaMemsetAsync(dEhat, 0, sizeof(float) * (size_t)V * d, st));
     SRK_TRY(gemm(st, B, d, V, Z, ldz, 1, Ehat, d, 1, dshat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
     SRK_TRY(gemm(st, V, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));

@@ -283,7 +283,7 @@ class MSGIFSR(SessRecModule):
                    self.num_layers, float(p), ctypes.c_uint64(seed), int(self.use_tensor_cores), ptr(st['ws']),
                    st['ws_bytes'], ptr(self._one()), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
                    ptr(o['seg_off']), ptr(o['seg_decay']), o['n_seg'], float(o['lr']), float(o['betas'][0]),
-                   float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0 / world, phase, stream)
+                   float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0 / world, phase, int(self.head_chunks), stream)
         if world == 1:
             call(0)
         else:

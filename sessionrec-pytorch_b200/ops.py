@@ -172,6 +172,10 @@ def ce_rows_bwd(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp, Zlo=None):
     _call('srk_ce_rows_bwd', ptr(Z), ldz, ptr(labels), ptr(lse), ptr(gscale), float(scale), B, V, int(z_is_logp), ptr(Zlo))
 
 
+def ce_rows_bwd_cols(Z, ldz, labels, lse, gscale, scale, B, col0, ncols, Zlo=None):
+    _call('srk_ce_rows_bwd_cols', ptr(Z), ldz, ptr(labels), ptr(lse), ptr(gscale), float(scale), B, col0, ncols, ptr(Zlo))
+
+
 def logp_bwd(LP, ldlp, G, ldg, scale, B, V, DZ, lddz, DZlo=None):
     _call('srk_logp_bwd', ptr(LP), ldlp, ptr(G), ldg, float(scale), B, V, ptr(DZ), lddz, ptr(DZlo))
 
