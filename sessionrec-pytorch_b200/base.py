@@ -42,6 +42,7 @@ class SessRecModule(nn.Module):
         self._opt = None
         self.use_tensor_cores = os.environ.get('SESSREC_NO_UMMA', '0') != '1'
         self._shard = None
+        self.fused_lse = os.environ.get('SESSREC_NO_FUSED_LSE', '0') != '1'
         self.head_chunks = int(os.environ.get('SESSREC_HEAD_CHUNKS', '1')    # > 1 measured slower on B200 (profiles/r1g))
 
     # ---- parameters -------------------------------------------------------------------------------------
@@ -138,16 +139,31 @@ class SessRecModule(nn.Module):
         dev = Ehat.device
         ldz = (V + 3) // 4 * 4                      # 16-byte aligned rows: TMA / vector loads in the backward GEMMs
         Z = torch.empty(B, ldz, dtype=torch.float32, device=dev)
+        lse = torch.empty(B, dtype=torch.float32, device=dev)
+        fused_lse = umma and self.fused_lse and self._shard is None and mode in ('loss', 'logits')
         if umma:
             sh = torch.empty(B, d, dtype=torch.float32, device=dev)
             sl = torch.empty(B, d, dtype=torch.float32, device=dev)
             ops.split_tf32(shat, ld_s, B, d, sh, sl, d)
-            ops.umma_gemm(0, B, V, d, sh, sl, d, cat['Ehi'], cat['Elo'], d, Z, ldz, alpha=scale)
             tape.update(sh=sh, sl=sl)
+            if fused_lse:
+                # persistent tcgen05 kernel: Z and its row log-sum-exp (+ label logit) in one pass over the catalog
+                part = torch.empty(2 * ((V + 255) // 256) * B + B, dtype=torch.float32, device=dev)
+                nll = torch.empty(B, dtype=torch.float32, device=dev) if mode == 'loss' else None
+                ops.umma_score_fwd(B, V, d, sh, sl, d, cat['Ehi'], cat['Elo'], d, Z, ldz, scale,
+                                   batch.labels if mode == 'loss' else None, lse, nll, part)
+            else:
+                ops.umma_gemm(0, B, V, d, sh, sl, d, cat['Ehi'], cat['Elo'], d, Z, ldz, alpha=scale)
         else:
             ops.gemm(B, V, d, shat, ld_s, 1, Ehat, 1, d, Z, ldz, alpha=scale)
-        lse = torch.empty(B, dtype=torch.float32, device=dev)
         tape.update(Z=Z, ldz=ldz, lse=lse, scale=scale, shat=shat, ld_s=ld_s)
+        if fused_lse:
+            if mode == 'logits':
+                return Z[:, :V]
+            out = torch.empty((), dtype=torch.float32, device=dev)
+            ops.mean(nll, B, out)
+            tape['labels'] = batch.labels
+            return out
         if mode == 'logits':
             if self._shard is not None:
                 raise _lib.SessRecError('catalog-sharded mode returns the loss only (each rank holds a slice of the logits)')

@@ -279,6 +279,199 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
   }
 }
 
+// ---- persistent forward scoring kernel with a fused log-sum-exp epilogue ------------------------------------------
+// Z = alpha * A B^T (form NT) for the whole catalog in ONE persistent launch (one CTA per SM, static tile schedule
+// ordered so that CTAs working at the same time share the catalog tile in L2), 128 x 256 tiles, two smem stages and
+// TWO TMEM accumulators (2 x 256 columns = the whole TMEM) so that the epilogue of tile t overlaps TMA + MMA of tile
+// t + 1.  The epilogue stores Z and, per row, the running (max, sum exp) of its 256 columns plus the label's logit:
+// the separate 88 MB log-sum-exp pass over Z disappears (lse_finalize_kernel combines ntn partials per row).
+constexpr int FBN = 256;
+
+struct FwdParams {
+  int M, N, K, ntm, ntn;
+  float* Z;
+  long long ldz;
+  float alpha;
+  uint32_t idesc;
+  const int* labels;     // optional
+  float* part;           // [ntn][M][2] (max, sum)
+  float* zlab;           // [M] label logit
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                      const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.K + KB - 1) / KB;
+  const int ntiles = p.ntm * p.ntn;
+  constexpr uint32_t a_bytes = BM * 128, b_bytes = FBN * 128, stage_bytes = 2 * a_bytes + 2 * b_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t % p.ntm) * BM, n0 = (t / p.ntm) * FBN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it & 1;
+          mbar_wait(&empty_bar[s], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], stage_bytes);
+          tma_load_2d(st, &mAh, &full_bar[s], kb * KB, m0);
+          tma_load_2d(st + a_bytes, &mAl, &full_bar[s], kb * KB, m0);
+          tma_load_2d(st + 2 * a_bytes, &mBh, &full_bar[s], kb * KB, n0);
+          tma_load_2d(st + 2 * a_bytes + b_bytes, &mBl, &full_bar[s], kb * KB, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0, tc = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+        const int buf = tc & 1;
+        mbar_wait(&tempty_bar[buf], ((uint32_t)(tc >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)buf * FBN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it & 1;
+          mbar_wait(&full_bar[s], (uint32_t)(it >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t ah = st, al = st + a_bytes, bh = st + 2 * a_bytes, bl = st + 2 * a_bytes + b_bytes;
+#pragma unroll
+          for (int ks = 0; ks < KB / UK; ++ks) {
+            const uint64_t dah = make_desc(ah + ks * 32, 16, 1024, 2), dal = make_desc(al + ks * 32, 16, 1024, 2);
+            const uint64_t dbh = make_desc(bh + ks * 32, 16, 1024, 2), dbl = make_desc(bl + ks * 32, 16, 1024, 2);
+            umma_tf32(tacc, dah, dbh, p.idesc, (kb | ks) ? 1u : 0u);
+            umma_tf32(tacc, dah, dbl, p.idesc, 1u);
+            umma_tf32(tacc, dal, dbh, p.idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int tc = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
+      const int buf = tc & 1;
+      const int mt = t % p.ntm, nt = t / p.ntm;
+      const int m = mt * BM + q * 32 + lane, n0 = nt * FBN;
+      mbar_wait(&tfull_bar[buf], (uint32_t)(tc >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int lab = (p.labels && m < p.M) ? p.labels[m] - n0 : -1;
+      float rmax = -3.0e38f, rsum = 0.f, zl = 0.f;
+      bool has = false;
+      for (int c0 = 0; c0 < FBN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FBN + c0), r);
+        const int nvalid = min(32, p.N - n0 - c0);
+        if (m < p.M && nvalid > 0) {
+          float v[32];
+          float cm = -3.0e38f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = p.alpha * __uint_as_float(r[j]);
+            if (j < nvalid) cm = fmaxf(cm, v[j]);
+          }
+          if (cm > rmax) {
+            rsum *= __expf(rmax - cm);
+            rmax = cm;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) rsum += __expf(v[j] - rmax);
+          if (lab >= c0 && lab < c0 + 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == lab - c0) zl = v[j];
+            has = true;
+          }
+          float* crow = p.Z + (long long)m * p.ldz + n0 + c0;
+          if (nvalid == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) crow[j] = v[j];
+          }
+        }
+      }
+      // accumulator fully read: hand the TMEM buffer back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (m < p.M) {
+        float* pp = p.part + ((long long)nt * p.M + m) * 2;
+        pp[0] = rmax;
+        pp[1] = rsum;
+        if (has) p.zlab[m] = zl;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// lse[m] = log sum over the ntn tile partials; nll[m] = lse[m] - zlab[m].  Warp per row.
+__global__ void __launch_bounds__(256) lse_finalize_kernel(const float* __restrict__ part, const float* __restrict__ zlab,
+                                                           int M, int ntn, float* __restrict__ lse, float* __restrict__ nll) {
+  const int lane = threadIdx.x & 31;
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  float mx = -3.0e38f, s = 0.f;
+  for (int t = lane; t < ntn; t += 32) {
+    const float pm = part[((long long)t * M + m) * 2], ps = part[((long long)t * M + m) * 2 + 1];
+    const float nm = fmaxf(mx, pm);
+    s = s * expf(mx - nm) + ps * expf(pm - nm);
+    mx = nm;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(SRK_FULL, mx, o), os = __shfl_xor_sync(SRK_FULL, s, o);
+    const float nm = fmaxf(mx, om);
+    s = s * expf(mx - nm) + os * expf(om - nm);
+    mx = nm;
+  }
+  if (lane == 0) {
+    const float l = mx + logf(s);
+    lse[m] = l;
+    if (nll) nll[m] = l - zlab[m];
+  }
+}
+
 __global__ void split_tf32_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float* __restrict__ hi,
                                   float* __restrict__ lo, long long ldo) {
   long long total = (long long)rows * cols;
@@ -372,6 +565,45 @@ extern "C" int srk_split_tf32(const float* X, long long ldx, int rows, int cols,
   long long g = (total + 255) / 256;
   if (g > 148LL * 16) g = 148LL * 16;
   split_tf32_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, ldx, rows, cols, hi, lo, ldo);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+// Z[M, ldz] = alpha * A B^T with A[M, K], B[N, K] given as TF32 hi/lo pairs; lse[M] = row log-sum-exp of Z, nll[M] =
+// lse - Z[m, labels[m]] (labels / nll optional).  part: scratch of 2 * ceil(N / 256) * M + M floats.
+extern "C" int srk_umma_score_fwd(int M, int N, int K, const float* Ahi, const float* Alo, long long lda, const float* Bhi,
+                                  const float* Blo, long long ldb, float* Z, long long ldz, float alpha, const int* labels,
+                                  float* lse, float* nll, float* part, void* stream) {
+  if (M <= 0 || N <= 0) return SRK_OK;
+  SRK_REQUIRE(K > 0 && (nll == nullptr || labels != nullptr), "umma_score_fwd: bad arguments");
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.ntm = srk_cdiv(M, BM);
+  p.ntn = srk_cdiv(N, FBN);
+  p.Z = Z; p.ldz = ldz; p.alpha = alpha; p.labels = labels;
+  p.part = part;
+  p.zlab = part + 2LL * p.ntn * M;
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FBN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  CUtensorMap mAh, mAl, mBh, mBl;
+  SRK_TRY(make_map(&mAh, Ahi, K, M, lda, BM, false));
+  SRK_TRY(make_map(&mAl, Alo, K, M, lda, BM, false));
+  SRK_TRY(make_map(&mBh, Bhi, K, N, ldb, FBN, false));
+  SRK_TRY(make_map(&mBl, Blo, K, N, ldb, FBN, false));
+  const size_t smem = 2 * (2 * (size_t)BM * 128 + 2 * (size_t)FBN * 128) + 1024;
+  static bool attr_set = false;
+  static int sms = 148;
+  if (!attr_set) {
+    SRK_CUDA(cudaFuncSetAttribute(umma_score_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    int dev = 0;
+    SRK_CUDA(cudaGetDevice(&dev));
+    SRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int ntiles = p.ntm * p.ntn;
+  umma_score_fwd_kernel<<<ntiles < sms ? ntiles : sms, THREADS, smem, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, p);
+  SRK_LAUNCH_CHECK();
+  lse_finalize_kernel<<<srk_cdiv((long long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(p.part, p.zlab, M, p.ntn, lse, nll);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

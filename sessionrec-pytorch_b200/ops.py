@@ -79,6 +79,11 @@ def umma_gemm(form, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, alpha=1.0, ac
           int(bool(accumulate)), int(split_k))
 
 
+def umma_score_fwd(M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, Z, ldz, alpha, labels, lse, nll, part):
+    _call('srk_umma_score_fwd', M, N, K, ptr(Ahi), ptr(Alo), lda, ptr(Bhi), ptr(Blo), ldb, ptr(Z), ldz, float(alpha),
+          ptr(labels), ptr(lse), ptr(nll), ptr(part))
+
+
 def split_tf32(X, ldx, rows, cols, hi, lo, ldo):
     _call('srk_split_tf32', ptr(X), ldx, rows, cols, ptr(hi), ptr(lo), ldo)
 

@@ -74,3 +74,27 @@ def test_umma_tn(ops, M, N, K):
     ops.umma_gemm(2, M, N, K, Ah, Al, lda, Bh, Bl, N, C, N)
     torch.cuda.synchronize()
     _check(f'tn {M}x{N}x{K}', C, A.double().t() @ B.double())
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 32), (512, 4099, 96), (200, 1001, 40), (512, 43097, 96), (2048, 3000, 256)])
+def test_umma_score_fwd_fused_lse(ops, M, N, K):
+    """Persistent forward kernel: Z, row log-sum-exp and label NLL in one pass."""
+    A = torch.nn.functional.normalize(_r(M, K), dim=-1)
+    B = torch.nn.functional.normalize(_r(N, K, seed=1), dim=-1)
+    labels = torch.randint(0, N, (M,), generator=torch.Generator().manual_seed(M + N))
+    ldk = (K + 3) // 4 * 4
+    Ah, Al = _split(ops, A, ldk)
+    Bh, Bl = _split(ops, B, ldk)
+    ldz = (N + 3) // 4 * 4
+    Z = torch.full((M, ldz), 7.0, device=DEV)
+    lse, nll = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    part = torch.empty(2 * ((N + 255) // 256) * M + M, device=DEV)
+    ops.umma_score_fwd(M, N, K, Ah, Al, ldk, Bh, Bl, ldk, Z, ldz, 12.0, labels.int().to(DEV), lse, nll, part)
+    torch.cuda.synchronize()
+    ref = 12.0 * (A.double() @ B.double().t())
+    _check(f'score Z {M}x{N}x{K}', Z[:, :N], ref)
+    rl = torch.logsumexp(ref, -1)
+    assert float((lse.cpu().double() - rl).abs().max()) < 2e-5, float((lse.cpu().double() - rl).abs().max())
+    rn = rl - ref.gather(1, labels.unsqueeze(1)).squeeze(1)
+    assert float((nll.cpu().double() - rn).abs().max()) < 3e-5
+    assert bool((Z[:, N:] == 7.0).all())
