@@ -43,7 +43,7 @@ class SessRecModule(nn.Module):
         self.use_tensor_cores = os.environ.get('SESSREC_NO_UMMA', '0') != '1'
         self._shard = None
         self.fused_lse = os.environ.get('SESSREC_NO_FUSED_LSE', '0') != '1'
-        self.head_chunks = int(os.environ.get('SESSREC_HEAD_CHUNKS', '1')    # > 1 measured slower on B200 (profiles/r1g))
+        self.head_chunks = int(os.environ.get('SESSREC_HEAD_CHUNKS', '1'))   # > 1 measured slower on B200 (r1g sweep)
 
     # ---- parameters -------------------------------------------------------------------------------------
     def _ensure_flat(self):
