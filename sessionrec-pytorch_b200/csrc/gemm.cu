@@ -9,6 +9,8 @@
 //
 // 64x64x16 tiles, 256 threads, 4x4 register micro-tile, register-staged prefetch, optional split-K with
 // an atomicAdd epilogue (accumulate mode only).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -256,8 +258,6 @@ int srk_pick_split_k(int M, int N, int K) {
   long long tiles = (long long)srk_cdiv(M, BM) * srk_cdiv(N, BN);
   if (tiles >= 296 || K < 128) return 1;
   long long want = (296 + tiles - 1) / tiles;
-  long long fit = (K + 255) / 256;      // enough splits for the single-shot kernel (k chunk <= 256)
-  if (want < fit) want = fit;
   long long cap = K / 32;
   long long s = want < cap ? want : cap;
   if (s > 128) s = 128;
@@ -306,7 +306,10 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   p.k_chunk = per * BK;
   S = srk_cdiv(g.K, p.k_chunk);
   dim3 grid(srk_cdiv(g.N, BN), srk_cdiv(g.M, BM), S);
-  if (p.k_chunk <= SS_MAXK) {
+  // Measured on B200 (profiles/r1g): every launch that asks for > 48 KB of dynamic shared memory pays ~5 us more than
+  // the static-smem pipelined kernel in this stream of tiny kernels, which eats the gain; opt-in only.
+  static const bool use_ss = getenv("SESSREC_SGEMM_SINGLESHOT") && getenv("SESSREC_SGEMM_SINGLESHOT")[0] == '1';
+  if (use_ss && p.k_chunk <= SS_MAXK) {
     p.k_chunk_pad = p.k_chunk;                      // multiple of 16 by construction
     const size_t smem = sizeof(float) * 2 * (size_t)p.k_chunk_pad * (BM + PAD);
     static bool attr_set = false;

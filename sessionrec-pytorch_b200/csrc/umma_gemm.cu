@@ -129,6 +129,42 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return d;
 }
 
+// Epilogue store of one 32 x 32 accumulator chunk (lane = row) with coalesced global accesses: the chunk is transposed
+// through a padded per-warp shared-memory tile so that every store instruction covers 4 rows x 128 contiguous bytes
+// (the naive lane-per-row store touches 32 different cache lines with 16 bytes each and is LSU-bound).
+__device__ __forceinline__ void store_chunk(float* __restrict__ stile, const float* v, float* __restrict__ C, long long ldc,
+                                            int m_base, int M, int nvalid, int lane, bool atomic) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stile[lane * 33 + j] = v[j];
+  __syncwarp();
+  const int c = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (lane >> 3) + 4 * i;
+    const int m = m_base + r;
+    if (m < M && c < nvalid) {
+      const float x0 = stile[r * 33 + c], x1 = stile[r * 33 + c + 1], x2 = stile[r * 33 + c + 2], x3 = stile[r * 33 + c + 3];
+      float* dst = C + (long long)m * ldc + c;
+      if (atomic) {
+        atomicAdd(dst, x0);
+        if (c + 1 < nvalid) atomicAdd(dst + 1, x1);
+        if (c + 2 < nvalid) atomicAdd(dst + 2, x2);
+        if (c + 3 < nvalid) atomicAdd(dst + 3, x3);
+      } else if (c + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+      } else {
+        dst[0] = x0;
+        if (c + 1 < nvalid) dst[1] = x1;
+        if (c + 2 < nvalid) dst[2] = x2;
+        if (c + 3 < nvalid) dst[3] = x3;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+constexpr size_t EPI_SMEM = 4 * 32 * 33 * sizeof(float);      // one padded 32 x 32 tile per epilogue warp
+
 struct UmmaParams {
   int M, N, K;            // logical problem
   int a_mn, b_mn;         // operand major-ness (0 = K-major, 1 = MN-major)
@@ -245,28 +281,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
       const int q = warp & 3;
       mbar_wait(&acc_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int m = m0 + q * 32 + lane;
+      float* stile = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) + (warp - 2) * 32 * 33;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        if (m < p.M) {
-          float* crow = p.C + (long long)m * p.ldc + n0 + c0;
-          const int nvalid = min(32, min(p.BN - c0, p.N - n0 - c0));
-          if (p.atomic) {
+        const int nvalid = min(32, min(p.BN - c0, p.N - n0 - c0));
+        if (nvalid > 0) {
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) atomicAdd(crow + j, p.alpha * __uint_as_float(r[j]));
-          } else if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(crow + j) =
-                  make_float4(p.alpha * __uint_as_float(r[j]), p.alpha * __uint_as_float(r[j + 1]),
-                              p.alpha * __uint_as_float(r[j + 2]), p.alpha * __uint_as_float(r[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) crow[j] = p.alpha * __uint_as_float(r[j]);
-          }
+          for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
+          store_chunk(stile, v, p.C + n0 + c0, p.ldc, m0 + q * 32, p.M, nvalid, lane, p.atomic != 0);
         }
       }
     }
@@ -379,6 +403,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
     }
   } else {
     const int q = warp & 3;
+    float* stile = reinterpret_cast<float*>(smem + 2 * (size_t)stage_bytes) + (warp - 2) * 32 * 33;
     int tc = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
       const int buf = tc & 1;
@@ -414,15 +439,12 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
               if (j == lab - c0) zl = v[j];
             has = true;
           }
-          float* crow = p.Z + (long long)m * p.ldz + n0 + c0;
-          if (nvalid == 32) {
+        }
+        if (nvalid > 0) {        // warp-uniform: coalesced store through the per-warp transpose tile
+          float v2[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) crow[j] = v[j];
-          }
+          for (int j = 0; j < 32; ++j) v2[j] = p.alpha * __uint_as_float(r[j]);
+          store_chunk(stile, v2, p.Z + n0 + c0, p.ldz, mt * BM + q * 32, p.M, nvalid, lane, false);
         }
       }
       // accumulator fully read: hand the TMEM buffer back to the MMA warp
@@ -524,12 +546,12 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)p.BN * 128;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  int stages = (int)((206 * 1024 - EPI_SMEM) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages > p.kb_per_split) stages = p.kb_per_split;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024;
+  const size_t smem = stages * stage_bytes + EPI_SMEM + 1024;
 
   CUtensorMap mAh, mAl, mBh, mBl;
   if (!p.a_mn) {          // A[M, K]: inner = K
@@ -590,7 +612,7 @@ extern "C" int srk_umma_score_fwd(int M, int N, int K, const float* Ahi, const f
   SRK_TRY(make_map(&mAl, Alo, K, M, lda, BM, false));
   SRK_TRY(make_map(&mBh, Bhi, K, N, ldb, FBN, false));
   SRK_TRY(make_map(&mBl, Blo, K, N, ldb, FBN, false));
-  const size_t smem = 2 * (2 * (size_t)BM * 128 + 2 * (size_t)FBN * 128) + 1024;
+  const size_t smem = 2 * (2 * (size_t)BM * 128 + 2 * (size_t)FBN * 128) + EPI_SMEM + 1024;
   static bool attr_set = false;
   static int sms = 148;
   if (!attr_set) {
