@@ -71,7 +71,7 @@ int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, const float* 
                   void* stream);
 /* Persistent forward scoring kernel with a fused log-sum-exp epilogue: Z[M, ldz] = alpha * A B^T (A[M,K], B[N,K] as TF32
  * hi/lo pairs), lse[M] = row log-sum-exp, nll[M] = lse - Z[m, labels[m]] (labels / nll may be NULL).  One CTA per SM,
- * 128 x 256 tiles, double-buffered TMEM.  part = scratch of 2 * ceil(N/256) * M + M floats.  Replaces srk_umma_gemm(form 0)
+ * 128 x 256 tiles, double-buffered TMEM.  part = scratch of 4 * ceil(N/256) * M + M floats.  Replaces srk_umma_gemm(form 0)
  * + srk_ce_rows_fwd (srgnn.py:146-147 / msgifsr.py:308-309 + train.py:99). */
 int srk_umma_score_fwd(int M, int N, int K, const float* Ahi, const float* Alo, long long lda, const float* Bhi,
                        const float* Blo, long long ldb, float* Z, long long ldz, float alpha, const int* labels, float* lse,

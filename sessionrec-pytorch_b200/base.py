@@ -148,7 +148,7 @@ class SessRecModule(nn.Module):
             tape.update(sh=sh, sl=sl)
             if fused_lse:
                 # persistent tcgen05 kernel: Z and its row log-sum-exp (+ label logit) in one pass over the catalog
-                part = torch.empty(2 * ((V + 255) // 256) * B + B, dtype=torch.float32, device=dev)
+                part = torch.empty(4 * ((V + 255) // 256) * B + B, dtype=torch.float32, device=dev)
                 nll = torch.empty(B, dtype=torch.float32, device=dev) if mode == 'loss' else None
                 ops.umma_score_fwd(B, V, d, sh, sl, d, cat['Ehi'], cat['Elo'], d, Z, ldz, scale,
                                    batch.labels if mode == 'loss' else None, lse, nll, part)

@@ -99,7 +99,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   fl += (long long)N * d + N;                              // X, rnX
   fl += (long long)L * (2 * ((ldzel + H) * d + 2LL * N * d + N * ldzel + N * H + (long long)(M + 1) * H) + B * d + N * d + N + N * d / 4 + 64);
   fl += 2LL * N * d + 3LL * B * d + N + 2LL * B + 4LL * B * d + B;    // u, v, e, ms, sr_in, s, shat, rn_s
-  fl += 2LL * B * ldz + 4LL * B * d + 2LL * B + 64 + 2LL * ((V + 255) / 256) * B + B;        // Z, Zlo, sh, sl, dshat, ds, lse, nll
+  fl += 2LL * B * ldz + 4LL * B * d + 2LL * B + 64 + 4LL * ((V + 255) / 256) * B + B;        // Z, Zlo, sh, sl, dshat, ds, lse, nll
   fl += 2LL * B * d + (long long)N * d;                    // dsr_in, dF
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
   fl += 2LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
@@ -228,7 +228,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     sh = ar.f((size_t)B * d); sl = ar.f((size_t)B * d);
     SRK_TRY(srk_split_tf32(shat, d, B, d, sh, sl, d, st));
     if (fused_lse) {
-      float* part = ar.f(2 * (size_t)((V + 255) / 256) * B + B);
+      float* part = ar.f(4 * (size_t)((V + 255) / 256) * B + B);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
       SRK_TRY(srk_umma_score_fwd(B, V, d, sh, sl, d, Ehi, Elo, d, Z, ldz, 12.0f, b.labels, lse, nll, part, st));
     } else {

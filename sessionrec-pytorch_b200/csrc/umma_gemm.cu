@@ -163,7 +163,9 @@ __device__ __forceinline__ void store_chunk(float* __restrict__ stile, const flo
   __syncwarp();
 }
 
-constexpr size_t EPI_SMEM = 4 * 32 * 33 * sizeof(float);      // one padded 32 x 32 tile per epilogue warp
+constexpr size_t EPI_TILE = 32 * 33 * sizeof(float);          // one padded 32 x 32 transpose tile per epilogue warp
+constexpr size_t EPI_SMEM = 4 * EPI_TILE;                     // generic kernel: 4 epilogue warps
+constexpr size_t MAX_DYN_SMEM = 227 * 1024 - 512;
 
 struct UmmaParams {
   int M, N, K;            // logical problem
@@ -310,6 +312,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
 // t + 1.  The epilogue stores Z and, per row, the running (max, sum exp) of its 256 columns plus the label's logit:
 // the separate 88 MB log-sum-exp pass over Z disappears (lse_finalize_kernel combines ntn partials per row).
 constexpr int FBN = 256;
+constexpr int FWD_EPI_WARPS = 8;                       // 2 per TMEM lane quadrant (latency hiding: 2 warps per SMSP)
+constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
 
 struct FwdParams {
   int M, N, K, ntm, ntn;
@@ -318,7 +322,7 @@ struct FwdParams {
   float alpha;
   uint32_t idesc;
   const int* labels;     // optional
-  float* part;           // [ntn][M][2] (max, sum)
+  float* part;           // [2 * ntn][M][2] (max, sum) per half tile
   float* zlab;           // [M] label logit
 };
 
@@ -326,7 +330,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                       const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -343,7 +347,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], FWD_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -402,7 +406,8 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
       }
     }
   } else {
-    const int q = warp & 3;
+    // epilogue warps 2..9: TMEM lane quadrant q = warp % 4, column half = (warp - 2) / 4 (128 of the 256 columns each)
+    const int q = warp & 3, half = (warp - 2) >> 2;
     float* stile = reinterpret_cast<float*>(smem + 2 * (size_t)stage_bytes) + (warp - 2) * 32 * 33;
     int tc = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
@@ -414,7 +419,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
       const int lab = (p.labels && m < p.M) ? p.labels[m] - n0 : -1;
       float rmax = -3.0e38f, rsum = 0.f, zl = 0.f;
       bool has = false;
-      for (int c0 = 0; c0 < FBN; c0 += 32) {
+      for (int c0 = half * (FBN / 2); c0 < (half + 1) * (FBN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * FBN + c0), r);
         const int nvalid = min(32, p.N - n0 - c0);
@@ -452,7 +457,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       if (m < p.M) {
-        float* pp = p.part + ((long long)nt * p.M + m) * 2;
+        float* pp = p.part + ((long long)(nt * 2 + half) * p.M + m) * 2;
         pp[0] = rmax;
         pp[1] = rsum;
         if (has) p.zlab[m] = zl;
@@ -546,7 +551,7 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const size_t stage_bytes = 2 * (size_t)BM * 128 + 2 * (size_t)p.BN * 128;
-  int stages = (int)((206 * 1024 - EPI_SMEM) / stage_bytes);
+  int stages = (int)((MAX_DYN_SMEM - 1024 - EPI_SMEM) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages > p.kb_per_split) stages = p.kb_per_split;
   if (stages < 1) stages = 1;
@@ -570,7 +575,7 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SRK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    SRK_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM));
     attr_set = true;
   }
   dim3 grid(srk_cdiv(N, p.BN), srk_cdiv(M, BM), S);
@@ -592,7 +597,7 @@ extern "C" int srk_split_tf32(const float* X, long long ldx, int rows, int cols,
 }
 
 // Z[M, ldz] = alpha * A B^T with A[M, K], B[N, K] given as TF32 hi/lo pairs; lse[M] = row log-sum-exp of Z, nll[M] =
-// lse - Z[m, labels[m]] (labels / nll optional).  part: scratch of 2 * ceil(N / 256) * M + M floats.
+// lse - Z[m, labels[m]] (labels / nll optional).  part: scratch of 4 * ceil(N / 256) * M + M floats.
 extern "C" int srk_umma_score_fwd(int M, int N, int K, const float* Ahi, const float* Alo, long long lda, const float* Bhi,
                                   const float* Blo, long long ldb, float* Z, long long ldz, float alpha, const int* labels,
                                   float* lse, float* nll, float* part, void* stream) {
@@ -605,27 +610,28 @@ extern "C" int srk_umma_score_fwd(int M, int N, int K, const float* Ahi, const f
   p.ntn = srk_cdiv(N, FBN);
   p.Z = Z; p.ldz = ldz; p.alpha = alpha; p.labels = labels;
   p.part = part;
-  p.zlab = part + 2LL * p.ntn * M;
+  p.zlab = part + 4LL * p.ntn * M;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FBN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   CUtensorMap mAh, mAl, mBh, mBl;
   SRK_TRY(make_map(&mAh, Ahi, K, M, lda, BM, false));
   SRK_TRY(make_map(&mAl, Alo, K, M, lda, BM, false));
   SRK_TRY(make_map(&mBh, Bhi, K, N, ldb, FBN, false));
   SRK_TRY(make_map(&mBl, Blo, K, N, ldb, FBN, false));
-  const size_t smem = 2 * (2 * (size_t)BM * 128 + 2 * (size_t)FBN * 128) + EPI_SMEM + 1024;
+  const size_t smem = 2 * (2 * (size_t)BM * 128 + 2 * (size_t)FBN * 128) + FWD_EPI_WARPS * EPI_TILE + 1024;
+  static_assert(2 * (2 * (size_t)BM * 128 + 2 * (size_t)FBN * 128) + FWD_EPI_WARPS * EPI_TILE + 1024 <= MAX_DYN_SMEM, "smem budget");
   static bool attr_set = false;
   static int sms = 148;
   if (!attr_set) {
-    SRK_CUDA(cudaFuncSetAttribute(umma_score_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    SRK_CUDA(cudaFuncSetAttribute(umma_score_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM));
     int dev = 0;
     SRK_CUDA(cudaGetDevice(&dev));
     SRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
   const int ntiles = p.ntm * p.ntn;
-  umma_score_fwd_kernel<<<ntiles < sms ? ntiles : sms, THREADS, smem, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, p);
+  umma_score_fwd_kernel<<<ntiles < sms ? ntiles : sms, FWD_THREADS, smem, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, p);
   SRK_LAUNCH_CHECK();
-  lse_finalize_kernel<<<srk_cdiv((long long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(p.part, p.zlab, M, p.ntn, lse, nll);
+  lse_finalize_kernel<<<srk_cdiv((long long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(p.part, p.zlab, M, 2 * p.ntn, lse, nll);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

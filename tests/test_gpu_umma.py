@@ -88,7 +88,7 @@ def test_umma_score_fwd_fused_lse(ops, M, N, K):
     ldz = (N + 3) // 4 * 4
     Z = torch.full((M, ldz), 7.0, device=DEV)
     lse, nll = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
-    part = torch.empty(2 * ((N + 255) // 256) * M + M, device=DEV)
+    part = torch.empty(4 * ((N + 255) // 256) * M + M, device=DEV)
     ops.umma_score_fwd(M, N, K, Ah, Al, ldk, Bh, Bl, ldk, Z, ldz, 12.0, labels.int().to(DEV), lse, nll, part)
     torch.cuda.synchronize()
     ref = 12.0 * (A.double() @ B.double().t())
