@@ -5,6 +5,8 @@
 // drive stage by stage (msgifsr.py::MSGIFSR._fwd/_bwd is the readable twin and the parity reference of this file).
 // All temporaries come from a caller-provided device workspace through a bump allocator; nothing is allocated,
 // nothing synchronises; ~60 kernel launches are enqueued back to back on the given stream.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -12,6 +14,42 @@
 namespace {
 
 constexpr int H = SRK_HEADS;
+
+// Debug aid (SESSREC_STEP_TIMING=1): CUDA events at the stage boundaries of one step, printed after a sync.  Gives the
+// in-pipeline (warm-cache, back-to-back) time of every stage, which the cold-cache ncu launch list cannot.
+struct StageTimer {
+  bool on;
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+  explicit StageTimer(cudaStream_t s) : st(s) {
+    const char* e = getenv("SESSREC_STEP_TIMING");
+    on = e && e[0] == '1';
+    mark("start");
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+    names.push_back(name);
+  }
+  void report() {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    float total = 0.f;
+    cudaEventElapsedTime(&total, ev.front(), ev.back());
+    fprintf(stderr, "[step timing] total %.1f us:", total * 1e3f);
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, " %s=%.1f", names[i], ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
 
 struct Arena {
   uint8_t* base;
@@ -140,7 +178,9 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     return srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2,
                          eps, adam_step, grad_scale, st);
   }
+  StageTimer tm(st);
   SRK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_flat, st));
+  tm.mark("zero_grad");
 
   // ---- forward -------------------------------------------------------------------------------------------
   float *Ehat = ar.f((size_t)V * d), *enorm = ar.f(V);
@@ -148,11 +188,13 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   if (umma) { Ehi = ar.f((size_t)V * d); Elo = ar.f((size_t)V * d); }
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, st));
+  tm.mark("catalog_prep");
   float *X = ar.f((size_t)N * d), *rnX = ar.f(N);
   srk_dropout dc_e = dcfg(SRK_SITE_EMBED + 1);
   SRK_TRY(srk_embed_gather_fwd(E, b.iid, N, d, SRK_NORM_L2, drop ? &dc_e : nullptr, X, rnX, nullptr, st));
   srk_dropout dc_attn = dcfg(SRK_SITE_GAT_ATTN);
 
+  tm.mark("gather");
   std::vector<LayerRec> layers(L);
   const float* h = X;
   for (int l = 0; l < L; ++l) {
@@ -211,6 +253,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
                                   R.rn, R.amax, st));
     h = R.Hout;
   }
+  tm.mark("gat_fwd");
   const float* F = h;
   float *u = ar.f((size_t)N * d), *v = ar.f((size_t)B * d), *e = ar.f(N), *ms = ar.f(2 * (size_t)B);
   float *sr_in = ar.f(2 * (size_t)B * d), *s = ar.f((size_t)B * d), *shat = ar.f((size_t)B * d), *rn_s = ar.f(B);
@@ -220,6 +263,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, 1, e, ms, sr_in, st));
   SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
   SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
+  tm.mark("readout_fwd");
   // scoring head + CE
   float *Z = ar.f((size_t)B * ldz), *lse = ar.f(B), *nll = ar.f(B);
   float *sh = nullptr, *sl = nullptr;
@@ -241,6 +285,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   }
   SRK_TRY(srk_mean(nll, B, loss_out, st));
 
+  tm.mark("score_fwd+lse");
   // ---- backward ------------------------------------------------------------------------------------------
   float* Zlo = umma ? ar.f((size_t)B * ldz) : nullptr;
   float *dshat = ar.f((size_t)B * d), *dEhat = ar.f((size_t)V * d);
@@ -268,7 +313,9 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     SRK_TRY(gemm(st, B, d, V, Z, ldz, 1, Ehat, d, 1, dshat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
     SRK_TRY(gemm(st, V, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
   }
+  tm.mark("ce_bwd+dS+dE");
   SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, V, d, SRK_NORM_L2, G(0), st));
+  tm.mark("catalog_bwd");
   float* ds = ar.f((size_t)B * d);
   float* dsr_in = ar.f(2 * (size_t)B * d);
   float* dF = ar.f((size_t)N * d);
@@ -283,6 +330,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   SRK_TRY(mm_nn(st, B, d, d, v, d, P(s_ro + 2), d, dF, d, 1, b.last));          // v holds dv
   SRK_TRY(mm_tn(st, d, d, B, v, d, F, d, G(s_ro + 2), d, b.last));
 
+  tm.mark("readout_bwd");
   // layers, last to first.  Scratch below is re-carved per layer from a fixed mark.
   const size_t mark = ar.off;
   const float* dH = dF;
@@ -337,11 +385,15 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     }
     dH = dfeat;
   }
+  tm.mark("gat_bwd");
   SRK_TRY(srk_embed_scatter_bwd(E, b.iid, b.perm, b.uoff, b.uid, b.U, b.P, d, SRK_NORM_L2, drop ? &dc_e : nullptr, rnX, dH,
                                 nullptr, G(0), st));
+  tm.mark("scatter");
   if (phase == 0 && do_adam) {
     SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
                           adam_step, grad_scale, st));
   }
+  tm.mark("adam");
+  tm.report();
   return SRK_OK;
 }

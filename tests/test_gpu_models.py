@@ -93,7 +93,9 @@ def test_fused_loss_path_vs_reference_golden(pkg, name):
 def test_dropout_with_injected_masks_vs_oracle(pkg, name, p):
     """Training mode with dropout: the oracle consumes the same counter-based masks the kernels regenerate."""
     c = MODELS[name]
-    seed = 20260101 + int(p * 10)
+    # seed picked so that no near-tie (< 1e-6) occurs in the max over GAT heads: with 20260101 + 2 the order-2 model
+    # has one, the two sides pick different heads for one node and every upstream gradient moves by ~1e-3 relative
+    seed = 20260111 + int(p * 10)
     m = make_model(pkg, c, dropout=p)
     m.train()
     m.set_dropout_seed(seed)
