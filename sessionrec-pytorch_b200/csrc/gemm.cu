@@ -247,6 +247,139 @@ __global__ void __launch_bounds__(NT) sgemm_singleshot_kernel(const GemmParams p
   }
 }
 
+// ---- small-K kernel --------------------------------------------------------------------------------------------
+// The dense layers of this path have K = d ~ 100 (or a split-K chunk of that size) and a few thousand rows: in the
+// pipelined kernel above they spend their time in ~6 serial k-iterations of ~1 us each (global-load latency that one
+// resident tile per CTA cannot hide).  This variant brings the WHOLE K extent (<= 160) of a 32 x 32 tile into static
+// shared memory with all global loads in flight at once (one latency exposure, one barrier), then computes.  4x more
+// CTAs than with 64 x 64 tiles, which these tiny problems need anyway; static smem (46 KB) so that no shared-memory
+// carve-out change is triggered between launches.
+constexpr int SB = 32, SKMAX = 160, SPAD = 4;
+
+template <bool kIdxOnOuter>
+__device__ __forceinline__ void small_load(float (*S)[SB + SPAD], const float* __restrict__ P, long long so, long long sk,
+                                           const int* __restrict__ idx, int mode, int o0, int kBeg, int kEnd, int O, int tid) {
+  const int kc = kEnd - kBeg;
+  const int kc4 = (kc + 3) >> 2;
+  if (mode == LM_KVEC || mode == LM_KSCAL) {
+    // K contiguous: one float4 = 4 consecutive k of one row
+    float4 reg[5];
+    const int total = SB * kc4;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int e = tid + i * NT;
+      reg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < total) {
+        const int o = o0 + e / kc4, k = kBeg + (e % kc4) * 4;
+        if (o < O) {
+          const long long ro = (kIdxOnOuter && idx) ? (long long)idx[o] : (long long)o;
+          const float* p = P + ro * so;
+          if (mode == LM_KVEC && k + 3 < kEnd && !(!kIdxOnOuter && idx)) {
+            reg[i] = *reinterpret_cast<const float4*>(p + k);
+          } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (k + j < kEnd) {
+                const long long rk = (!kIdxOnOuter && idx) ? (long long)idx[k + j] : (long long)(k + j);
+                t[j] = p[rk * sk];
+              }
+            reg[i] = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int e = tid + i * NT;
+      if (e < total) {
+        const int o = e / kc4, k = (e % kc4) * 4;
+        S[k][o] = reg[i].x; S[k + 1][o] = reg[i].y; S[k + 2][o] = reg[i].z; S[k + 3][o] = reg[i].w;
+      }
+    }
+  } else {
+    // outer dimension contiguous (or generic strides): one float4 = 4 consecutive outer indices of one k
+    float4 reg[5];
+    const int total = kc * (SB / 4);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int e = tid + i * NT;
+      reg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < total) {
+        const int k = kBeg + e / (SB / 4), o = o0 + (e % (SB / 4)) * 4;
+        const long long rk = (!kIdxOnOuter && idx) ? (long long)idx[k] : (long long)k;
+        const float* p = P + rk * sk;
+        if (mode == LM_MVEC && o + 3 < O && !(kIdxOnOuter && idx)) {
+          reg[i] = *reinterpret_cast<const float4*>(p + o);
+        } else {
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (o + j < O) {
+              const long long ro = (kIdxOnOuter && idx) ? (long long)idx[o + j] : (long long)(o + j);
+              t[j] = p[ro * so];
+            }
+          reg[i] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int e = tid + i * NT;
+      if (e < total) {
+        const int k = e / (SB / 4), o = (e % (SB / 4)) * 4;
+        *reinterpret_cast<float4*>(&S[k][o]) = reg[i];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) sgemm_small_kernel(const GemmParams p) {
+  __shared__ __align__(16) float As[SKMAX + 4][SB + SPAD];
+  __shared__ __align__(16) float Bs[SKMAX + 4][SB + SPAD];
+  const GemmArgs& g = p.g;
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SB, n0 = blockIdx.x * SB;
+  const int kBeg = blockIdx.z * p.k_chunk;
+  const int kEnd = min(g.K, kBeg + p.k_chunk);
+  const int kc = kEnd - kBeg;
+  // generic-stride operands go through the scalar branch of the "outer contiguous" loader
+  small_load<true>(As, g.A, g.sa_m, g.sa_k, g.a_idx, p.a_mode == LM_SCALAR ? LM_MSCAL : p.a_mode, m0, kBeg, kEnd, g.M, tid);
+  small_load<false>(Bs, g.B, g.sb_n, g.sb_k, g.b_idx, p.b_mode == LM_SCALAR ? LM_MSCAL : p.b_mode, n0, kBeg, kEnd, g.N, tid);
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kc; ++k) {
+    const float2 a = *reinterpret_cast<const float2*>(&As[k][ty * 2]);
+    const float2 b = *reinterpret_cast<const float2*>(&Bs[k][tx * 2]);
+    a00 = fmaf(a.x, b.x, a00); a01 = fmaf(a.x, b.y, a01);
+    a10 = fmaf(a.y, b.x, a10); a11 = fmaf(a.y, b.y, a11);
+  }
+  const float acc[2][2] = {{a00, a01}, {a10, a11}};
+  const bool first_split = blockIdx.z == 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= g.M) continue;
+    const long long rc = g.c_idx ? (long long)g.c_idx[m] : (long long)m;
+    float* crow = g.C + rc * g.ldc;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + tx * 2 + j;
+      if (n >= g.N) continue;
+      float v = g.alpha * acc[i][j];
+      if (g.bias && first_split) v += g.bias[n];
+      if (!g.accumulate)
+        crow[n] = v;
+      else if (gridDim.z > 1)
+        atomicAdd(crow + n, v);
+      else
+        crow[n] += v;
+    }
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -256,8 +389,11 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // two CTAs per SM are in flight, never below 2 k-iterations (32) per CTA.
 int srk_pick_split_k(int M, int N, int K) {
   long long tiles = (long long)srk_cdiv(M, BM) * srk_cdiv(N, BN);
-  if (tiles >= 296 || K < 128) return 1;
+  if (K <= SKMAX) return 1;                             // one small-K launch covers it
+  if (tiles >= 296) return 1;
   long long want = (296 + tiles - 1) / tiles;
+  long long fit = (K + SKMAX - 1) / SKMAX;              // chunks that fit the small-K kernel
+  if (want < fit) want = fit;
   long long cap = K / 32;
   long long s = want < cap ? want : cap;
   if (s > 128) s = 128;
@@ -268,7 +404,7 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return SRK_OK;
   SRK_REQUIRE(g.split_k >= 1, "gemm: split_k must be >= 1");
   SRK_REQUIRE(g.split_k == 1 || g.accumulate, "gemm: split-K needs accumulate mode");
-  if (!g.accumulate && !g.c_idx && g.K >= 256) {
+  if (!g.accumulate && !g.c_idx && g.K > SKMAX) {
     // overwrite mode with a long K loop and few tiles: zero C, then run the split-K accumulate path
     int s = srk_pick_split_k(g.M, g.N, g.K);
     if (s > 1) {
@@ -305,6 +441,13 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   int per = srk_cdiv(ktiles, S);
   p.k_chunk = per * BK;
   S = srk_cdiv(g.K, p.k_chunk);
+  static const bool no_small = getenv("SESSREC_SGEMM_NO_SMALL") && getenv("SESSREC_SGEMM_NO_SMALL")[0] == '1';
+  if (!no_small && p.k_chunk <= SKMAX && srk_cdiv(g.M, SB) <= 65535) {
+    dim3 sgrid(srk_cdiv(g.N, SB), srk_cdiv(g.M, SB), S);
+    sgemm_small_kernel<<<sgrid, NT, 0, st>>>(p);
+    SRK_LAUNCH_CHECK();
+    return SRK_OK;
+  }
   dim3 grid(srk_cdiv(g.N, BN), srk_cdiv(g.M, BM), S);
   // Measured on B200 (profiles/r1g): every launch that asks for > 48 KB of dynamic shared memory pays ~5 us more than
   // the static-smem pipelined kernel in this stream of tiny kernels, which eats the gain; opt-in only.
