@@ -149,11 +149,17 @@ def roofline_probe(cfg, device, pk):
         ops.split_tf32(Z, ldz, B, V, Zh, Zl, ldz)
         split = max(1, min((V + 31) // 32, 148 // ((B + 127) // 128)))
 
+        lse, nll = torch.empty(B, device=device), torch.empty(B, device=device)
+        part = torch.empty(4 * ((V + 255) // 256) * B + B, device=device)
+        lab = torch.zeros(B, dtype=torch.int32, device=device)
+
         def run():
-            ops.umma_gemm(0, B, V, d, sh, sl, d, Eh, El, d, Z, ldz, alpha=12.0)
+            # forward: persistent kernel, Z + fused row log-sum-exp / label logit; backward: dS (split-K) and dE
+            ops.umma_score_fwd(B, V, d, sh, sl, d, Eh, El, d, Z, ldz, 12.0, lab, lse, nll, part)
             ops.umma_gemm(1, B, d, V, Zh, Zl, ldz, Eh, El, d, dS, d, accumulate=True, split_k=split)
             ops.umma_gemm(2, V, d, B, Zh, Zl, ldz, sh, sl, d, dE, d)
-        kname = 'umma_gemm_kernel: tcgen05.mma kind::tf32 (3xTF32 split), TMA SWIZZLE_128B operands, TMEM accumulators'
+        kname = ('umma_score_fwd_kernel (persistent, fused LSE) + umma_gemm_kernel x2: tcgen05.mma kind::tf32 (3xTF32 split), '
+                 'TMA SWIZZLE_128B operands, TMEM accumulators')
     else:
         def run():
             ops.gemm(B, V, d, s, d, 1, E, 1, d, Z, ldz, alpha=12.0)

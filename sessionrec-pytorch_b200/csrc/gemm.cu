@@ -389,10 +389,11 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // two CTAs per SM are in flight, never below 2 k-iterations (32) per CTA.
 int srk_pick_split_k(int M, int N, int K) {
   long long tiles = (long long)srk_cdiv(M, BM) * srk_cdiv(N, BN);
-  if (K <= SKMAX) return 1;                             // one small-K launch covers it
-  if (tiles >= 296) return 1;
+  const bool small = 2.0 * M * N * K < 1.0e8;           // handled by the small-K kernel (chunks of <= 160)
+  if (small && K <= SKMAX) return 1;
+  if (tiles >= 296 || K < 128) return 1;
   long long want = (296 + tiles - 1) / tiles;
-  long long fit = (K + SKMAX - 1) / SKMAX;              // chunks that fit the small-K kernel
+  long long fit = small ? (K + SKMAX - 1) / SKMAX : 1;
   if (want < fit) want = fit;
   long long cap = K / 32;
   long long s = want < cap ? want : cap;
@@ -404,7 +405,7 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return SRK_OK;
   SRK_REQUIRE(g.split_k >= 1, "gemm: split_k must be >= 1");
   SRK_REQUIRE(g.split_k == 1 || g.accumulate, "gemm: split-K needs accumulate mode");
-  if (!g.accumulate && !g.c_idx && g.K > SKMAX) {
+  if (!g.accumulate && !g.c_idx && g.K > SKMAX && (g.K >= 256 || 2.0 * g.M * g.N * g.K < 1.0e8)) {
     // overwrite mode with a long K loop and few tiles: zero C, then run the split-K accumulate path
     int s = srk_pick_split_k(g.M, g.N, g.K);
     if (s > 1) {
@@ -442,7 +443,10 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   p.k_chunk = per * BK;
   S = srk_cdiv(g.K, p.k_chunk);
   static const bool no_small = getenv("SESSREC_SGEMM_NO_SMALL") && getenv("SESSREC_SGEMM_NO_SMALL")[0] == '1';
-  if (!no_small && p.k_chunk <= SKMAX && srk_cdiv(g.M, SB) <= 65535) {
+  // 32 x 32 tiles lose to 64 x 64 once the problem is big enough to fill the machine (measured: the 261 MFLOP GAT
+  // projections run 19 us pipelined vs 30 us here), so the small-K kernel only takes the small problems
+  const double flops = 2.0 * g.M * g.N * g.K;
+  if (!no_small && p.k_chunk <= SKMAX && flops < 1.0e8 && srk_cdiv(g.M, SB) <= 65535) {
     dim3 sgrid(srk_cdiv(g.N, SB), srk_cdiv(g.M, SB), S);
     sgemm_small_kernel<<<sgrid, NT, 0, st>>>(p);
     SRK_LAUNCH_CHECK();
