@@ -141,7 +141,51 @@ def roofline_probe(cfg, device, pk):
     dE = torch.zeros(V, d, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     umma = d <= 256 and os.environ.get('SESSREC_NO_UMMA', '0') != '1'
-    if umma:
+    flash = umma and ops.flash_ce_supported(d) and os.environ.get('SESSREC_NO_FLASH_CE', '0') != '1'
+    per_kernel = None
+    if flash:
+        # fused head (csrc/flash_ce.cu): forward = soft-max statistics only, backward recomputes the logit tiles and
+        # runs both gradient products from shared memory; the (B, V) logits never exist in HBM
+        sn = torch.nn.functional.normalize(s, dim=-1)
+        En = torch.nn.functional.normalize(E, dim=-1)
+        Sh, Sl = (torch.empty(B, d, dtype=torch.int16, device=device) for _ in range(2))
+        Eh, El = (torch.empty(V, d, dtype=torch.int16, device=device) for _ in range(2))
+        ops.split_bf16(sn, d, B, d, Sh, Sl, d)
+        ops.split_bf16(En, d, V, d, Eh, El, d)
+        lse, nll = torch.empty(B, device=device), torch.empty(B, device=device)
+        part = torch.empty(ops.flash_ce_part_floats(B, V), device=device)
+        lab = torch.zeros(B, dtype=torch.int32, device=device)
+        parts = ops.flash_ce_bwd_parts(B)
+        dEp = torch.empty(parts, V, d, device=device)
+        one = torch.ones(1, device=device)
+
+        def run_f():
+            ops.flash_ce_fwd(B, V, d, Sh, Sl, d, Eh, El, d, 12.0, lab, lse, nll, part)
+
+        def run_b():
+            ops.flash_ce_bwd(B, V, d, Sh, Sl, d, Eh, El, d, 12.0, lab, lse, one, dS, dEp)
+
+        def run():
+            run_f()
+            run_b()
+        per_kernel = {}
+        for nm, fn in (('fce_fwd_kernel (+ finalize)', run_f), ('fce_bwd_kernel (+ dS memset)', run_b)):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(10):
+                flush.fill_(0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            per_kernel[nm] = round(float(np.median(ts)), 4)
+        kname = ('fce_fwd_kernel + fce_bwd_kernel (flash CE: logits recomputed in the backward, never stored): tcgen05.mma '
+                 'kind::f16 on bf16 hi/lo pairs (3 products), TMA SWIZZLE_128B operands, TMEM accumulators, dZ fed back '
+                 'to the tensor cores from shared memory')
+    elif umma:
         sh, sl, Eh, El = (torch.empty_like(x) for x in (s, s, E, E))
         Zh, Zl = torch.empty_like(Z), torch.empty_like(Z)
         ops.split_tf32(s, d, B, d, sh, sl, d)
@@ -181,7 +225,13 @@ def roofline_probe(cfg, device, pk):
     flops = 6.0 * B * V * d
     ach = flops / (ms * 1e-3) / 1e12
     traffic, traffic_src = None, None
-    if umma and (B, V, d) == (512, 43097, 96):
+    if flash:
+        caps = sorted((ROOT / 'profiles').glob('*_ncu_full_flash_ce.json'))
+        if caps and (B, V, d) == (512, 43097, 96):
+            rows = json.loads(caps[-1].read_text())
+            traffic = round(sum(float(r['dram_bytes_read']) + float(r['dram_bytes_write']) for r in rows))
+            traffic_src = f'profiles/{caps[-1].name} (bytes of the forward + backward launches)'
+    elif umma and (B, V, d) == (512, 43097, 96):
         # dram__bytes_read.sum + dram__bytes_write.sum of the same three launches from the committed `ncu --set full`
         # capture (profiles/); only valid for the shape it was captured on
         caps = sorted((ROOT / 'profiles').glob('*_ncu_full_umma_gemm.json'))
@@ -191,8 +241,10 @@ def roofline_probe(cfg, device, pk):
             traffic_src = f'profiles/{caps[-1].name} (bytes for the 3 launches; algorithmic operand bytes ~ 0.47 GB with the hi/lo split)'
     return dict(bound='tensor', kernel='catalog scoring GEMMs (Z = s E^T, dS = dZ E, dE = dZ^T s): ' + kname,
                 achieved=round(ach, 3), peak=pk['tf_burst'], unit='TFLOP/s', frac=round(ach / pk['tf_burst'], 5),
-                traffic=traffic, traffic_source=traffic_src, ms_for_the_3_launches=round(ms, 4), algorithmic_flops=flops,
-                note='algorithmic FLOPs 6*B*V*d counted once; the 3 TF32 passes of the split are the kernel\'s own cost',
+                traffic=traffic, traffic_source=traffic_src, ms_for_the_head=round(ms, 4), ms_per_kernel=per_kernel,
+                algorithmic_flops=flops,
+                note='algorithmic FLOPs 6*B*V*d (Z = s E^T, dS = dZ E, dE = dZ^T s) counted once; the 3 passes of the hi/lo '
+                     'split and the logit recomputation in the backward are the kernels\' own cost',
                 peak_source=f"{pk['src']} bf16 burst (kernel timed alone)")
 
 
@@ -392,10 +444,11 @@ def main():
         dist.barrier()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            sessions = [SessionSampler(cfg['V'], seed=123).sessions(cfg['B']) for _ in range(2)]
-            v, cores, secs = cpu_oracle_steps(cfg, sessions, 3, 1)
+            sessions = [SessionSampler(cfg['V'], seed=123).sessions(cfg['B']) for _ in range(4)]
+            nst = max(3, min(120, int(12.0 * 5000 / cfg['B'])))          # ~10-20 s of CPU work at ~5 k sessions/s
+            v, cores, secs = cpu_oracle_steps(cfg, sessions, nst, 1)
             out['cpu_baseline'] = dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port',
-                                       sample=f"3 full steps (B={cfg['B']}) of {args.workload} after 1 warm-up, {secs:.1f} s")
+                                       sample=f"{nst} full steps (B={cfg['B']}) of {args.workload} after 1 warm-up, {secs:.1f} s")
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

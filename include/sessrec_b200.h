@@ -79,6 +79,31 @@ int srk_umma_score_fwd(int M, int N, int K, const float* Ahi, const float* Alo, 
 /* hi = x with the 13 low mantissa bits cleared (TF32-exact), lo = x - hi (exact); [rows, cols] with pitches ldx / ldo. */
 int srk_split_tf32(const float* X, long long ldx, int rows, int cols, float* hi, float* lo, long long ldo, void* stream);
 
+/* ---- fused scoring + cross-entropy head ("flash CE", csrc/flash_ce.cu) ---------------------------------
+ * logits = scale * shat Ehat^T, loss = mean(logsumexp - label logit) (srgnn.py:145-147, niser.py:149-156,
+ * msgifsr.py:276-309 + utils/train.py:99) WITHOUT writing the (B, V) logits: tcgen05.mma kind::f16 on bf16 hi/lo
+ * pairs (x = hi + lo, products as hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; ~1e-5 relative).  16 <= d <= 128,
+ * d % 16 == 0.  Operands are bf16 bit patterns (uint16_t) with row pitches lds / lde (multiples of 8). */
+/* hi = bf16(x) (round to nearest even), lo = bf16(x - hi); [rows, cols] with pitches ldx / ldo. */
+int srk_split_bf16(const float* X, long long ldx, int rows, int cols, uint16_t* hi, uint16_t* lo, long long ldo, void* stream);
+/* floats of scratch (`part`) srk_flash_ce_fwd needs */
+long long srk_flash_ce_part_floats(int B, int V);
+/* lse[B] = row log-sum-exp of the logits; nll[B] (optional) = lse - logit of labels[b] (0 where the label lies outside
+ * [0, V): catalog sharding). */
+int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                     const uint16_t* Elo, long long lde, float scale, const int* labels, float* lse, float* nll, float* part,
+                     void* stream);
+/* number of [V, d] partial buffers srk_flash_ce_bwd writes (= ceil(B / 128)) */
+int srk_flash_ce_bwd_parts(int B);
+/* Backward of the mean loss: recomputes every 128 x 128 logit tile, dZ = gout[0] * scale * (softmax - onehot) / B
+ * (gout NULL = 1), and returns dS[B, d] = dZ Ehat (overwritten) and dEpart[parts][V, d]: the sum over `parts` is
+ * dEhat = dZ^T shat (srk_catalog_prep_bwd / srk_sum_parts add them up; every element of dEpart is written). */
+int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                     const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,
+                     float* dS, float* dEpart, void* stream);
+/* out[n] (+)= sum_p parts[p * stride + i] */
+int srk_sum_parts(const float* parts, long long stride, int nparts, long long n, float* out, int accumulate, void* stream);
+
 /* ---- item-embedding gather / scatter-add (K1 / K8) -------------------------------------------------
  * Forward: X[i] = norm_mode(dropout(E[iid[i]])), i < P.  Replaces `self.embedding(iid)` + feat_drop +
  * normalisation (srgnn.py:133; niser.py:133-135,141-142; msgifsr.py:247-253).  rnorm[i] receives the L2
@@ -99,10 +124,12 @@ int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const
  * max_norm / (norm + 1e-7) (`nn.Embedding(max_norm=1)`, msgifsr.py:162,276), then Ehat = F.normalize(E)
  * (msgifsr.py:278-279).  mode SRK_NORM_EPS (NISER): Ehat = E / (||E|| + 1e-12) (niser.py:149-151).
  * enorm[V] receives the (post-renorm) row norms.  Ehat_hi / Ehat_lo (optional, both or neither): TF32 split of
- * Ehat for srk_umma_gemm. */
+ * Ehat for srk_umma_gemm.  Ebf_hi / Ebf_lo (optional, both or neither): bf16 hi/lo split for srk_flash_ce_*. */
 int srk_catalog_prep_fwd(float* E, int V, int d, int norm_mode, float max_norm, float* Ehat, float* enorm,
-                         float* Ehat_hi, float* Ehat_lo, void* stream);
-int srk_catalog_prep_bwd(const float* E, const float* Ehat, const float* enorm, const float* dEhat, int V, int d,
+                         float* Ehat_hi, float* Ehat_lo, uint16_t* Ebf_hi, uint16_t* Ebf_lo, void* stream);
+/* dE += backward of the row normalisation; dEhat is given as `nparts` partial sums, [V, d] each, V * d floats apart
+ * (nparts = 1: a plain gradient). */
+int srk_catalog_prep_bwd(const float* E, const float* Ehat, const float* enorm, const float* dEhat, int nparts, int V, int d,
                          int norm_mode, float* dE, void* stream);
 /* In-place max_norm renorm of the rows touched by a gather (msgifsr.py:247); duplicates are safe. */
 int srk_renorm_rows(float* E, const int* uid, int U, int d, float max_norm, void* stream);

@@ -44,6 +44,8 @@ class SessRecModule(nn.Module):
         self._shard = None
         self.fused_lse = os.environ.get('SESSREC_NO_FUSED_LSE', '0') != '1'
         self.head_chunks = int(os.environ.get('SESSREC_HEAD_CHUNKS', '1'))   # > 1 measured slower on B200 (r1g sweep)
+        # fused scoring + CE head (csrc/flash_ce.cu): loss() / train_step() never materialise the (B, V) logits
+        self.flash_ce = os.environ.get('SESSREC_NO_FLASH_CE', '0') != '1'
 
     # ---- parameters -------------------------------------------------------------------------------------
     def _ensure_flat(self):
@@ -105,30 +107,45 @@ class SessRecModule(nn.Module):
         from .parallel import shard_slice
         return shard_slice(V, dist.get_rank(self._shard), dist.get_world_size(self._shard))
 
+    def _single_head(self):
+        """False when the model scores several session representations against the catalog (order-fusion head)."""
+        return True
+
+    def _use_flash(self, d, mode):
+        return (self.use_tensor_cores and self.flash_ce and self._shard is None and mode == 'loss'
+                and self._single_head() and ops.flash_ce_supported(d))
+
     def _catalog_fwd(self, E, norm_mode, max_norm, tape):
         """Catalog pre-pass: in-place max_norm renorm (MSGIFSR) + row normalisation of the rows this rank scores, with
         the TF32 hi/lo split for the tcgen05 GEMM emitted by the same kernel."""
         V, d = E.shape
         lo, hi = self._rows(V)
         dev = E.device
-        umma = self.use_tensor_cores and d <= 256
+        flash = self._use_flash(d, tape.get('mode'))
+        umma = self.use_tensor_cores and d <= 256 and not flash
         if self._shard is not None and max_norm > 0:
             ops.renorm_rows(E, None, V, max_norm)          # every replica renorms every row (the reference does too)
             max_norm = 0.0
         El = E[lo:hi]
-        Ehi = Elo = enorm = None
+        Ehi = Elo = enorm = Bhi = Blo = None
+        if flash:                                          # bf16 hi/lo pair of the scored rows (bit patterns)
+            Bhi = torch.empty(hi - lo, d, dtype=torch.int16, device=dev)
+            Blo = torch.empty(hi - lo, d, dtype=torch.int16, device=dev)
         if norm_mode == NORM_NONE:
             Ehat = El
             if umma:
                 Ehi, Elo = torch.empty_like(El), torch.empty_like(El)
                 ops.split_tf32(El, d, hi - lo, d, Ehi, Elo, d)
+            if flash:
+                ops.split_bf16(El, d, hi - lo, d, Bhi, Blo, d)
         else:
             Ehat = torch.empty_like(El)
             enorm = torch.empty(hi - lo, dtype=torch.float32, device=dev)
             if umma:
                 Ehi, Elo = torch.empty_like(El), torch.empty_like(El)
-            ops.catalog_prep_fwd(El, norm_mode, max_norm, Ehat, enorm, Ehi, Elo)
-        tape['cat'] = dict(lo=lo, hi=hi, Ehat=Ehat, enorm=enorm, Ehi=Ehi, Elo=Elo, norm_mode=norm_mode, umma=umma)
+            ops.catalog_prep_fwd(El, norm_mode, max_norm, Ehat, enorm, Ehi, Elo, Bhi, Blo)
+        tape['cat'] = dict(lo=lo, hi=hi, Ehat=Ehat, enorm=enorm, Ehi=Ehi, Elo=Elo, Bhi=Bhi, Blo=Blo, norm_mode=norm_mode,
+                           umma=umma, flash=flash)
 
     def _head_fwd(self, shat, ld_s, scale, batch, mode, tape):
         """Z = scale * shat Ehat^T on the tcgen05 tensor cores (3xTF32, csrc/umma_gemm.cu) whenever the embedding
@@ -137,6 +154,19 @@ class SessRecModule(nn.Module):
         Ehat, umma = cat['Ehat'], cat['umma']
         B, (V, d) = batch.B, Ehat.shape                 # V = rows scored by this rank
         dev = Ehat.device
+        if cat['flash']:
+            # fused head: soft-max statistics and the label logit straight from the tensor-core tiles
+            Shi = torch.empty(B, d, dtype=torch.int16, device=dev)
+            Slo = torch.empty(B, d, dtype=torch.int16, device=dev)
+            ops.split_bf16(shat, ld_s, B, d, Shi, Slo, d)
+            lse = torch.empty(B, dtype=torch.float32, device=dev)
+            nll = torch.empty(B, dtype=torch.float32, device=dev)
+            part = torch.empty(ops.flash_ce_part_floats(B, V), dtype=torch.float32, device=dev)
+            ops.flash_ce_fwd(B, V, d, Shi, Slo, d, cat['Bhi'], cat['Blo'], d, scale, batch.labels, lse, nll, part)
+            out = torch.empty((), dtype=torch.float32, device=dev)
+            ops.mean(nll, B, out)
+            tape.update(Shi=Shi, Slo=Slo, lse=lse, scale=scale, shat=shat, ld_s=ld_s, labels=batch.labels)
+            return out
         ldz = (V + 3) // 4 * 4                      # 16-byte aligned rows: TMA / vector loads in the backward GEMMs
         Z = torch.empty(B, ldz, dtype=torch.float32, device=dev)
         lse = torch.empty(B, dtype=torch.float32, device=dev)
@@ -202,6 +232,19 @@ class SessRecModule(nn.Module):
     def _head_bwd(self, tape, batch, mode, gout, gE, E):
         """Backward of the head: returns d shat [B, d] and adds the catalog's share of the table gradient into gE."""
         cat = tape['cat']
+        if cat['flash']:
+            Ehat = cat['Ehat']
+            B, (V, d) = batch.B, Ehat.shape
+            parts = ops.flash_ce_bwd_parts(B)
+            dEpart = torch.empty(parts, V, d, dtype=torch.float32, device=Ehat.device)
+            dshat = torch.empty(B, d, dtype=torch.float32, device=Ehat.device)
+            ops.flash_ce_bwd(B, V, d, tape['Shi'], tape['Slo'], d, cat['Bhi'], cat['Blo'], d, tape['scale'], tape['labels'],
+                             tape['lse'], gout.reshape(1), dshat, dEpart)
+            if cat['norm_mode'] == NORM_NONE:            # SRGNN: the table itself is scored
+                ops.sum_parts(dEpart, V * d, parts, V * d, gE, accumulate=True)
+            else:
+                ops.catalog_prep_bwd(E, Ehat, cat['enorm'], dEpart, cat['norm_mode'], gE, nparts=parts)
+            return dshat
         Z, ldz, Ehat, shat, umma = tape['Z'], tape['ldz'], cat['Ehat'], tape['shat'], cat['umma']
         lo, hi = cat['lo'], cat['hi']
         B, (V, d) = batch.B, Ehat.shape

@@ -136,7 +136,8 @@ template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) catalog_prep_fwd_kernel(float* __restrict__ E, int V, int d, int mode,
                                                                        float max_norm, float* __restrict__ Ehat,
                                                                        float* __restrict__ enorm, float* __restrict__ Ehi,
-                                                                       float* __restrict__ Elo) {
+                                                                       float* __restrict__ Elo, uint16_t* __restrict__ Bhi,
+                                                                       uint16_t* __restrict__ Blo) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(ROW_THREADS) catalog_prep_fwd_kernel(float* __
       row_store(hi, Ehi + (long long)v * d, d, lane);
       row_store(lo, Elo + (long long)v * d, d, lane);
     }
+    if (Bhi) row_store_bf16_split(y, Bhi + (long long)v * d, Blo + (long long)v * d, d, lane);
     if (lane == 0) enorm[v] = n;
   }
 }
@@ -183,7 +185,8 @@ __global__ void __launch_bounds__(ROW_THREADS) rownorm_bwd_kernel(const float* _
                                                                   const float* __restrict__ rnorm,
                                                                   const float* __restrict__ dY, long long lddy, int R,
                                                                   int d, int mode, float* __restrict__ dX,
-                                                                  long long lddx, int accumulate) {
+                                                                  long long lddx, int accumulate, int nparts,
+                                                                  long long part_stride) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -191,6 +194,11 @@ __global__ void __launch_bounds__(ROW_THREADS) rownorm_bwd_kernel(const float* _
     row_load(x, X + r * ldx, d, lane);
     row_load(y, Y + r * ldy, d, lane);
     row_load(dy, dY + r * lddy, d, lane);
+    for (int pt = 1; pt < nparts; ++pt) {        // dY given as partial sums (flash CE backward: one per session tile)
+      RowVec<NC> t;
+      row_load(t, dY + pt * part_stride + r * lddy, d, lane);
+      row_axpy(dy, 1.f, t);
+    }
     row_normalize_bwd<NC>(x, y, rnorm[r], mode, dy, nullptr, dx);
     if (accumulate) row_add_store(dx, dX + r * lddx, d, lane);
     else row_store(dx, dX + r * lddx, d, lane);
@@ -294,18 +302,24 @@ extern "C" int srk_renorm_rows(float* E, const int* uid, int U, int d, float max
 }
 
 extern "C" int srk_catalog_prep_fwd(float* E, int V, int d, int norm_mode, float max_norm, float* Ehat, float* enorm,
-                                    float* Ehat_hi, float* Ehat_lo, void* stream) {
+                                    float* Ehat_hi, float* Ehat_lo, uint16_t* Ebf_hi, uint16_t* Ebf_lo, void* stream) {
   SRK_TRY(srk_check_dim(d));
   SRK_REQUIRE(norm_mode == SRK_NORM_L2 || norm_mode == SRK_NORM_EPS, "catalog_prep: norm_mode must be L2 or EPS");
   SRK_DISPATCH_NC(d, (catalog_prep_fwd_kernel<NC><<<row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         E, V, d, norm_mode, max_norm, Ehat, enorm, Ehat_hi, Ehat_lo)));
+                         E, V, d, norm_mode, max_norm, Ehat, enorm, Ehat_hi, Ehat_lo, Ebf_hi, Ebf_lo)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
 
-extern "C" int srk_catalog_prep_bwd(const float* E, const float* Ehat, const float* enorm, const float* dEhat, int V,
-                                    int d, int norm_mode, float* dE, void* stream) {
-  return srk_rownorm_bwd(E, d, Ehat, d, enorm, dEhat, d, V, d, norm_mode, dE, d, 1, stream);
+extern "C" int srk_catalog_prep_bwd(const float* E, const float* Ehat, const float* enorm, const float* dEhat, int nparts,
+                                    int V, int d, int norm_mode, float* dE, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (V <= 0) return SRK_OK;
+  SRK_REQUIRE(nparts >= 1, "catalog_prep_bwd: nparts must be >= 1");
+  SRK_DISPATCH_NC(d, (rownorm_bwd_kernel<NC><<<row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                         E, d, Ehat, d, enorm, dEhat, d, V, d, norm_mode, dE, d, 1, nparts, (long long)V * d)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
 }
 
 extern "C" int srk_rownorm_fwd(const float* X, long long ldx, int R, int d, int norm_mode, float* Y, long long ldy,
@@ -326,7 +340,7 @@ extern "C" int srk_rownorm_bwd(const float* X, long long ldx, const float* Y, lo
   if (R <= 0) return SRK_OK;
   SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "rownorm: strides must be multiples of 4");
   SRK_DISPATCH_NC(d, (rownorm_bwd_kernel<NC><<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         X, ldx, Y, ldy, rnorm, dY, lddy, R, d, norm_mode, dX, lddx, accumulate)));
+                         X, ldx, Y, ldy, rnorm, dY, lddy, R, d, norm_mode, dX, lddx, accumulate, 1, 0)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -1,0 +1,627 @@
+// Fused catalog scoring + cross-entropy head on tcgen05 tensor cores ("flash CE"): the (B, V) logit matrix of
+//   logits = scale * shat Ehat^T ; loss = mean_b (logsumexp_v logits[b, :] - logits[b, y_b])
+// (srgnn.py:145-147, niser.py:149-156, msgifsr.py:276-309 + utils/train.py:99 and their autograd) is never written to
+// HBM.  The forward kernel keeps only per-row soft-max statistics; the backward kernel RECOMPUTES each 128 x 128
+// logit tile on the tensor cores, turns it into dZ = coef * (softmax - onehot) in registers, stores dZ as a bf16
+// hi/lo pair in shared memory and feeds it straight back to the tensor cores for both gradient products:
+//   dS[b, :]  += dZ[b, v] Ehat[v, :]      (accumulated in TMEM over the CTA's catalog range)
+//   dE[v, :]   = dZ[b, v]^T shat[b, :]    (one 128-session partial per CTA; partials are summed by catalog_prep_bwd)
+//
+// Arithmetic: every fp32 operand x is split as x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits in
+// total) and every product is evaluated as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM ("bf16 x 3"): relative
+// error ~1e-5 per product, inside the 1e-4 parity bar, at twice the tensor rate of the 3xTF32 scheme of umma_gemm.cu
+// and with operands that take no more shared memory than one fp32 copy.
+//
+// Work decomposition: CTA = (128-session tile, contiguous range of 128-row catalog tiles); grid = #session tiles x
+// #ranges ~ one CTA per SM.  Roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2-9
+// = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
+// Shared memory (all tiles are 128 rows x 128-byte swizzled rows, SWIZZLE_128B, so the SAME bytes serve as a K-major
+// operand of one product and as an MN-major operand of another):
+//   S  = shat tile   hi/lo  [128 b x d]   resident         A (K-major) of the logit tile, B (MN-major) of dE
+//   E  = Ehat tile   hi/lo  [128 v x d]   1-4 stages       B (K-major) of the logit tile, B (MN-major) of dS
+//   D  = dZ tile     hi/lo  [128 b x 128 v]                A (K-major) of dS, A (MN-major) of dE; doubles as the
+//                                                          fp32 staging area of the TMA stores of dE / dS
+// TMEM (512 columns): logit tile x 2 (double buffer) | dS accumulator (d <= 128 columns) | dE accumulator.
+#include <cuda_bf16.h>
+
+#include "umma.cuh"
+
+using namespace umma;
+
+namespace {
+
+constexpr int TB = 128;                     // sessions per tile (UMMA M of the logit tile, TMEM lanes)
+constexpr int TV = 128;                     // catalog rows per tile
+constexpr uint32_t CHUNK = 128 * 128;       // bytes of one 128-row x 128-byte operand chunk (64 bf16 or 32 fp32 per row)
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int THREADS = 64 + EPI_THREADS;
+constexpr uint32_t D_BYTES = 4 * CHUNK;     // dZ hi (2 chunks of 64 columns) + dZ lo
+constexpr size_t FCE_MAX_SMEM = 227 * 1024 - 1024;
+constexpr int MAX_STAGES = 4;
+constexpr uint32_t TM_Z = 0, TM_DS = 256, TM_DE = 384;     // TMEM column offsets
+
+struct FceParams {
+  int B, V, d;
+  int nch;                 // 64-column bf16 chunks per operand row = ceil(d / 64)
+  int ntm, nvr, nvt;       // session tiles, catalog ranges, catalog tiles
+  int estages;
+  float scale;
+  const int* labels;
+  float* part;             // fwd: [2 * nvr][B][2] (max, sum exp) per (range, column half)
+  float* zlab;             // fwd: [B] label logit
+  const float* lse;        // bwd: [B]
+  const float* gout;       // bwd: upstream gradient of the mean loss (device scalar) or null
+  uint32_t idesc_z, idesc_ds, idesc_de;
+};
+
+__device__ __forceinline__ uint64_t kdesc(uint32_t addr) { return make_desc(addr, 16, 1024, 2); }        // K-major SW128
+__device__ __forceinline__ uint64_t mdesc(uint32_t addr) { return make_desc(addr, CHUNK, 1024, 2); }     // MN-major SW128
+
+// acc (+)= A B with both operands split hi/lo: hi*hi + hi*lo + lo*hi
+__device__ __forceinline__ void mma3(uint32_t tacc, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
+                                     uint32_t accum) {
+  umma_bf16(tacc, ah, bh, idesc, accum);
+  umma_bf16(tacc, ah, bl, idesc, 1u);
+  umma_bf16(tacc, al, bh, idesc, 1u);
+}
+
+// logit tile: Z[128 b x 128 v] = S E^T, K = d in steps of 16 (32 bytes inside the 128-byte swizzle row)
+__device__ __forceinline__ void issue_logits(uint32_t tz, uint32_t S, uint32_t E, uint32_t op_bytes, int d, uint32_t idesc) {
+  const int nks = d >> 4;
+  for (int ks = 0; ks < nks; ++ks) {
+    const uint32_t off = (uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32;
+    mma3(tz, kdesc(S + off), kdesc(S + op_bytes + off), kdesc(E + off), kdesc(E + op_bytes + off), idesc, ks ? 1u : 0u);
+  }
+}
+
+struct TileSched {
+  int tb, t0, t1;
+  __device__ TileSched(const FceParams& p) {
+    tb = blockIdx.x % p.ntm;
+    const int vr = blockIdx.x / p.ntm;
+    t0 = (int)((long long)vr * p.nvt / p.nvr);
+    t1 = (int)((long long)(vr + 1) * p.nvt / p.nvr);
+  }
+};
+
+__device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* hi, const CUtensorMap* lo, uint64_t* bar,
+                                             int nch, uint32_t op_bytes, int row0) {
+  for (int c = 0; c < nch; ++c) {
+    tma_load_2d(dst + c * CHUNK, hi, bar, c * 64, row0);
+    tma_load_2d(dst + op_bytes + c * CHUNK, lo, bar, c * 64, row0);
+  }
+}
+
+// ---- forward: per-row (max, sum exp) partials + label logit, nothing else leaves the SM ---------------------------------
+__global__ void __launch_bounds__(THREADS, 1)
+fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
+               const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl, const FceParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full, e_full[MAX_STAGES], e_empty[MAX_STAGES], z_full[2], z_empty[2];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t op_bytes = (uint32_t)p.nch * CHUNK;
+  uint8_t* S = smem;
+  uint8_t* E0 = smem + 2 * op_bytes;
+  const TileSched ts(p);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_full, 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&e_full[s], 1);
+      mbar_init(&e_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_tc_before();
+  __syncthreads();
+  fence_tc_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&s_full, 2 * op_bytes);
+      load_operand(S, &mSh, &mSl, &s_full, p.nch, op_bytes, ts.tb * TB);
+      int it = 0;
+      for (int t = ts.t0; t < ts.t1; ++t, ++it) {
+        const int s = it % p.estages;
+        mbar_wait(&e_empty[s], ((uint32_t)(it / p.estages) & 1u) ^ 1u);
+        mbar_expect_tx(&e_full[s], 2 * op_bytes);
+        load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, op_bytes, t * TV);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(&s_full, 0);
+      int it = 0;
+      for (int t = ts.t0; t < ts.t1; ++t, ++it) {
+        const int s = it % p.estages, zb = it & 1;
+        mbar_wait(&e_full[s], (uint32_t)(it / p.estages) & 1u);
+        mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        fence_tc_after();
+        issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, smem_u32(S), smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p.d,
+                     p.idesc_z);
+        umma_commit(&e_empty[s]);
+        umma_commit(&z_full[zb]);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int b = ts.tb * TB + q * 32 + lane;
+    const int lab = b < p.B ? p.labels[b] : -1;
+    float rmax = -3.0e38f, rsum = 0.f, zl = 0.f;
+    bool has = false;
+    int it = 0;
+    for (int t = ts.t0; t < ts.t1; ++t, ++it) {
+      const int zb = it & 1;
+      mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
+      fence_tc_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TM_Z + (uint32_t)(zb * TV + c0), r);
+        const int v0 = t * TV + c0;
+        const int nvalid = min(32, p.V - v0);
+        if (nvalid > 0) {
+          float z[32];
+          float cm = -3.0e38f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            z[j] = p.scale * __uint_as_float(r[j]);
+            if (j < nvalid) cm = fmaxf(cm, z[j]);
+          }
+          if (cm > rmax) {
+            rsum *= __expf(rmax - cm);
+            rmax = cm;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) rsum += __expf(z[j] - rmax);
+          if (lab >= v0 && lab < v0 + nvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == lab - v0) zl = z[j];
+            has = true;
+          }
+        }
+      }
+      fence_tc_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&z_empty[zb]);
+    }
+    if (b < p.B) {
+      const int vr = blockIdx.x / p.ntm;
+      float* pp = p.part + ((long long)(vr * 2 + half) * p.B + b) * 2;
+      pp[0] = rmax;
+      pp[1] = rsum;
+      if (has) p.zlab[b] = zl;
+    }
+  }
+  fence_tc_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// lse[b] = log sum over the partials; nll[b] = lse[b] - zlab[b].  Warp per row.
+__global__ void __launch_bounds__(256) fce_finalize_kernel(const float* __restrict__ part, const float* __restrict__ zlab,
+                                                           const int* __restrict__ labels, int B, int V, int nparts,
+                                                           float* __restrict__ lse, float* __restrict__ nll) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float mx = -3.0e38f, s = 0.f;
+  for (int t = lane; t < nparts; t += 32) {
+    const float pm = part[((long long)t * B + b) * 2], ps = part[((long long)t * B + b) * 2 + 1];
+    const float nm = fmaxf(mx, pm);
+    s = s * expf(mx - nm) + ps * expf(pm - nm);
+    mx = nm;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(SRK_FULL, mx, o), os = __shfl_xor_sync(SRK_FULL, s, o);
+    const float nm = fmaxf(mx, om);
+    s = s * expf(mx - nm) + os * expf(om - nm);
+    mx = nm;
+  }
+  if (lane == 0) {
+    const float l = mx + logf(s);
+    lse[b] = l;
+    if (nll) {                          // label outside [0, V): its column lives on another rank (catalog sharding)
+      const int lab = labels[b];
+      nll[b] = (lab >= 0 && lab < V) ? l - zlab[b] : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_parts_kernel(const float4* __restrict__ parts, long long stride4, int nparts, long long n4,
+                                                        float4* __restrict__ out, int accumulate) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    float4 a = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pt = 0; pt < nparts; ++pt) {
+      const float4 x = parts[pt * stride4 + i];
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+    }
+    out[i] = a;
+  }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------------------
+// 32 consecutive dZ values of tile row r (columns c0 .. c0 + 31) -> bf16 hi/lo, 128-byte-swizzled rows of the D tile
+__device__ __forceinline__ void store_dz(uint8_t* Dhi, uint8_t* Dlo, int r, int c0, const float* dz) {
+  const uint32_t base = (uint32_t)(c0 >> 6) * CHUNK + (uint32_t)r * 128;
+  const uint32_t u0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x0 = dz[8 * j + 2 * k], x1 = dz[8 * j + 2 * k + 1];
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+      const float2 hf = __bfloat1622float2(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+      h[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[k] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    const uint32_t pu = ((u0 + j) ^ ((uint32_t)r & 7u)) * 16;
+    *reinterpret_cast<uint4*>(Dhi + base + pu) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(Dlo + base + pu) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// 32 fp32 accumulator columns of tile row r -> swizzled fp32 staging chunk (128 rows x 128 B) for a TMA store
+__device__ __forceinline__ void stage_row(uint8_t* chunk, int r, const uint32_t* v) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint32_t pu = ((uint32_t)u ^ ((uint32_t)r & 7u)) * 16;
+    *reinterpret_cast<uint4*>(chunk + (uint32_t)r * 128 + pu) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
+               const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl,
+               const __grid_constant__ CUtensorMap mdE, const __grid_constant__ CUtensorMap mdS, const FceParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full, e_full[MAX_STAGES], e_empty[MAX_STAGES], z_full[2], z_empty[2], d_full, d_empty;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t op_bytes = (uint32_t)p.nch * CHUNK;
+  uint8_t* S = smem;
+  uint8_t* Dt = smem + 2 * op_bytes;                // dZ hi (2 chunks) | dZ lo (2 chunks); also the fp32 staging area
+  uint8_t* E0 = Dt + D_BYTES;
+  const TileSched ts(p);
+  const int ntiles = ts.t1 - ts.t0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_full, 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&e_full[s], 1);
+      mbar_init(&e_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], EPI_WARPS);
+    }
+    mbar_init(&d_full, EPI_WARPS);
+    mbar_init(&d_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_tc_before();
+  __syncthreads();
+  fence_tc_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&s_full, 2 * op_bytes);
+      load_operand(S, &mSh, &mSl, &s_full, p.nch, op_bytes, ts.tb * TB);
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % p.estages;
+        mbar_wait(&e_empty[s], ((uint32_t)(it / p.estages) & 1u) ^ 1u);
+        mbar_expect_tx(&e_full[s], 2 * op_bytes);
+        load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, op_bytes, (ts.t0 + it) * TV);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t Sa = smem_u32(S), Da = smem_u32(Dt);
+      const uint32_t tds = tmem_base + TM_DS, tde = tmem_base + TM_DE;
+      auto logits = [&](int it) {
+        const int s = it % p.estages, zb = it & 1;
+        mbar_wait(&e_full[s], (uint32_t)(it / p.estages) & 1u);
+        mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        fence_tc_after();
+        issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, Sa, smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p.d, p.idesc_z);
+        umma_commit(&z_full[zb]);
+      };
+      mbar_wait(&s_full, 0);
+      logits(0);
+      for (int it = 0; it < ntiles; ++it) {
+        // with more than one catalog stage the next logit tile does not depend on this tile's gradient products
+        if (p.estages > 1 && it + 1 < ntiles) logits(it + 1);
+        const int s = it % p.estages;
+        const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * op_bytes);
+        mbar_wait(&d_full, (uint32_t)it & 1u);
+        fence_tc_after();
+        // dS[128 b x d] += dZ[128 b x 128 v] E[128 v x d]: A = D K-major, B = E MN-major, K = v in steps of 16 rows
+#pragma unroll 1
+        for (int ks = 0; ks < TV / 16; ++ks) {
+          const uint32_t aoff = (uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32, boff = (uint32_t)ks * 2048;
+          mma3(tds, kdesc(Da + aoff), kdesc(Da + 2 * CHUNK + aoff), mdesc(Ea + boff), mdesc(Ea + op_bytes + boff), p.idesc_ds,
+               (it | ks) ? 1u : 0u);
+        }
+        umma_commit(&e_empty[s]);
+        // dE[128 v x d] = dZ^T[128 v x 128 b] S[128 b x d]: A = D MN-major, B = S MN-major, K = b in steps of 16 rows
+#pragma unroll 1
+        for (int ks = 0; ks < TB / 16; ++ks) {
+          const uint32_t off = (uint32_t)ks * 2048;
+          mma3(tde, mdesc(Da + off), mdesc(Da + 2 * CHUNK + off), mdesc(Sa + off), mdesc(Sa + op_bytes + off), p.idesc_de,
+               ks ? 1u : 0u);
+        }
+        umma_commit(&d_empty);
+        if (p.estages == 1 && it + 1 < ntiles) logits(it + 1);
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;                     // row of the tile owned by this thread (= TMEM lane)
+    const int b = ts.tb * TB + r;
+    const bool bvalid = b < p.B;
+    const float lse_b = bvalid ? p.lse[b] : 0.f;
+    const int lab = bvalid ? p.labels[b] : -1;
+    const float coef = p.scale * (p.gout ? p.gout[0] : 1.f) / (float)p.B;
+    const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+    const int nc32 = (p.d + 31) >> 5;                // 32-column fp32 chunks of the dS / dE accumulators
+    const bool elected = (warp == 2 && lane == 0);
+    uint8_t* Dhi = Dt;
+    uint8_t* Dlo = Dt + 2 * CHUNK;
+    for (int it = 0; it < ntiles; ++it) {
+      const int t = ts.t0 + it, zb = it & 1;
+      mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
+      fence_tc_after();
+      // the previous tile's TMA stores must have finished reading the staging area (= the D tile) before it is rewritten
+      if (elected) tma_wait_group_read0();
+      named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + lanebits + TM_Z + (uint32_t)(zb * TV + c0), acc);
+        const int v0 = t * TV + c0;
+        float dz[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pr = __expf(p.scale * __uint_as_float(acc[j]) - lse_b);
+          const float g = coef * (pr - (v0 + j == lab ? 1.f : 0.f));
+          dz[j] = (bvalid && v0 + j < p.V) ? g : 0.f;
+        }
+        store_dz(Dhi, Dlo, r, c0, dz);
+      }
+      fence_tc_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&z_empty[zb]);
+        mbar_arrive(&d_full);
+      }
+      // both gradient products of this tile are complete: drain the dE accumulator (rows = catalog rows of the tile)
+      mbar_wait(&d_empty, (uint32_t)it & 1u);
+      fence_tc_after();
+      for (int cc = half; cc < nc32; cc += 2) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + lanebits + TM_DE + (uint32_t)(cc * 32), acc);
+        stage_row(Dt + (uint32_t)cc * CHUNK, r, acc);
+      }
+      fence_tc_before();
+      fence_async_smem();
+      named_bar_sync(1, EPI_THREADS);
+      if (elected) {
+        for (int cc = 0; cc < nc32; ++cc) tma_store_3d(&mdE, Dt + (uint32_t)cc * CHUNK, cc * 32, t * TV, ts.tb);
+        tma_commit_group();
+      }
+    }
+    // dS accumulator of this CTA's catalog range -> reduce-add into dS[B, d]
+    if (elected) tma_wait_group_read0();
+    named_bar_sync(1, EPI_THREADS);
+    for (int cc = half; cc < nc32; cc += 2) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + lanebits + TM_DS + (uint32_t)(cc * 32), acc);
+      stage_row(Dt + (uint32_t)cc * CHUNK, r, acc);
+    }
+    fence_tc_before();
+    fence_async_smem();
+    named_bar_sync(1, EPI_THREADS);
+    if (elected) {
+      for (int cc = 0; cc < nc32; ++cc) tma_reduce_add_2d(&mdS, Dt + (uint32_t)cc * CHUNK, cc * 32, ts.tb * TB);
+      tma_commit_group();
+      tma_wait_group0();
+    }
+  }
+  fence_tc_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long ldo) {
+  const long long total = (long long)rows * cols;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long r = t / cols;
+    const int c = (int)(t - r * cols);
+    const float x = X[r * ldx + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[r * ldo + c] = h;
+    lo[r * ldo + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+int bf16_map(CUtensorMap* m, const uint16_t* base, int d, int rows, long long ld) {
+  SRK_REQUIRE(ld % 8 == 0, "flash_ce: bf16 operand pitch must be a multiple of 8 elements");
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 128};
+  return make_map_nd(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box);
+}
+
+int fill_params(FceParams& p, int B, int V, int d, float scale, const int* labels, bool bwd) {
+  SRK_REQUIRE(d >= 16 && d <= 128 && d % 16 == 0, "flash_ce: d = %d unsupported (multiple of 16 in [16, 128])", d);
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.V = V; p.d = d;
+  p.nch = (d + 63) / 64;
+  p.ntm = srk_cdiv(B, TB);
+  p.nvt = srk_cdiv(V, TV);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    SRK_CUDA(cudaGetDevice(&dev));
+    SRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int nvr = sms / p.ntm;
+  if (nvr < 1) nvr = 1;
+  if (nvr > p.nvt) nvr = p.nvt;
+  p.nvr = nvr;
+  const size_t op = (size_t)p.nch * CHUNK;
+  const size_t fixed = 2 * op + (bwd ? D_BYTES : 0);
+  int st = (int)((FCE_MAX_SMEM - 1024 - fixed) / (2 * op));
+  if (st > (bwd ? 3 : MAX_STAGES)) st = bwd ? 3 : MAX_STAGES;
+  SRK_REQUIRE(st >= 1, "flash_ce: shared-memory budget exceeded");
+  p.estages = st;
+  p.scale = scale;
+  p.labels = labels;
+  // instruction descriptors: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), majors (bit 15 / 16: 1 = MN-major), N >> 3, M >> 4
+  const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 4) << 24);
+  p.idesc_z = base | ((uint32_t)(TV >> 3) << 17);
+  p.idesc_ds = base | (1u << 16) | ((uint32_t)(d >> 3) << 17);
+  p.idesc_de = base | (1u << 15) | (1u << 16) | ((uint32_t)(d >> 3) << 17);
+  return SRK_OK;
+}
+
+size_t smem_bytes(const FceParams& p, bool bwd) {
+  const size_t op = (size_t)p.nch * CHUNK;
+  return 2 * op + (bwd ? D_BYTES : 0) + (size_t)p.estages * 2 * op + 1024;
+}
+
+}  // namespace
+
+extern "C" int srk_split_bf16(const float* X, long long ldx, int rows, int cols, uint16_t* hi, uint16_t* lo, long long ldo,
+                              void* stream) {
+  const long long total = (long long)rows * cols;
+  if (total <= 0) return SRK_OK;
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  split_bf16_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, ldx, rows, cols, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                              reinterpret_cast<__nv_bfloat16*>(lo), ldo);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" long long srk_flash_ce_part_floats(int B, int V) {
+  // upper bound that does not depend on the SM count: 2 partial pairs per (catalog tile, row) + label logits
+  return 4LL * srk_cdiv(V, TV) * B + B;
+}
+
+extern "C" int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds,
+                                const uint16_t* Ehi, const uint16_t* Elo, long long lde, float scale, const int* labels,
+                                float* lse, float* nll, float* part, void* stream) {
+  if (B <= 0) return SRK_OK;
+  SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && part != nullptr, "flash_ce_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  FceParams p;
+  SRK_TRY(fill_params(p, B, V, d, scale, labels, false));
+  p.part = part;
+  p.zlab = part + 4LL * p.nvr * B;
+  CUtensorMap mSh, mSl, mEh, mEl;
+  SRK_TRY(bf16_map(&mSh, Shi, d, B, lds));
+  SRK_TRY(bf16_map(&mSl, Slo, d, B, lds));
+  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde));
+  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    attr_set = true;
+  }
+  fce_fwd_kernel<<<p.ntm * p.nvr, THREADS, smem_bytes(p, false), st>>>(mSh, mSl, mEh, mEl, p);
+  SRK_LAUNCH_CHECK();
+  fce_finalize_kernel<<<srk_cdiv((long long)B * 32, 256), 256, 0, st>>>(p.part, p.zlab, labels, B, V, 2 * p.nvr, lse, nll);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_flash_ce_bwd_parts(int B) { return srk_cdiv(B, TB); }
+
+extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds,
+                                const uint16_t* Ehi, const uint16_t* Elo, long long lde, float scale, const int* labels,
+                                const float* lse, const float* gout, float* dS, float* dEpart, void* stream) {
+  if (B <= 0) return SRK_OK;
+  SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && dS != nullptr && dEpart != nullptr, "flash_ce_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  FceParams p;
+  SRK_TRY(fill_params(p, B, V, d, scale, labels, true));
+  p.lse = lse;
+  p.gout = gout;
+  CUtensorMap mSh, mSl, mEh, mEl, mdE, mdS;
+  SRK_TRY(bf16_map(&mSh, Shi, d, B, lds));
+  SRK_TRY(bf16_map(&mSl, Slo, d, B, lds));
+  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde));
+  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde));
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)V, (cuuint64_t)p.ntm};
+    cuuint64_t strides[2] = {(cuuint64_t)d * 4, (cuuint64_t)V * d * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    SRK_TRY(make_map_nd(&mdE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dEpart, dims, strides, box));
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+    cuuint32_t box[2] = {32, 128};
+    SRK_TRY(make_map_nd(&mdS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dS, dims, strides, box));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CUDA(cudaFuncSetAttribute(fce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    attr_set = true;
+  }
+  SRK_CUDA(cudaMemsetAsync(dS, 0, sizeof(float) * (size_t)B * d, st));
+  fce_bwd_kernel<<<p.ntm * p.nvr, THREADS, smem_bytes(p, true), st>>>(mSh, mSl, mEh, mEl, mdE, mdS, p);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_sum_parts(const float* parts, long long stride, int nparts, long long n, float* out, int accumulate,
+                             void* stream) {
+  if (n <= 0) return SRK_OK;
+  SRK_REQUIRE(n % 4 == 0 && stride % 4 == 0 && ((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+              "sum_parts: n / stride must be multiples of 4 and the buffers 16-byte aligned");
+  long long g = (n / 4 + 255) / 256;
+  if (g > 148LL * 8) g = 148LL * 8;
+  sum_parts_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(parts), stride / 4, nparts, n / 4,
+                                                             reinterpret_cast<float4*>(out), accumulate);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}

@@ -2,6 +2,8 @@
 // lane, lane l owning columns (c*32 + l)*4 .. +3.  All global accesses are 128-bit and fully coalesced
 // (a warp touches 512 contiguous bytes per chunk).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 template <int NC>
@@ -97,6 +99,24 @@ __device__ __forceinline__ void row_split_tf32(const RowVec<NC>& r, RowVec<NC>& 
     hi.v[c].y = __uint_as_float(__float_as_uint(r.v[c].y) & 0xFFFFE000u); lo.v[c].y = r.v[c].y - hi.v[c].y;
     hi.v[c].z = __uint_as_float(__float_as_uint(r.v[c].z) & 0xFFFFE000u); lo.v[c].z = r.v[c].z - hi.v[c].z;
     hi.v[c].w = __uint_as_float(__float_as_uint(r.v[c].w) & 0xFFFFE000u); lo.v[c].w = r.v[c].w - hi.v[c].w;
+  }
+}
+
+// bf16 hi/lo split of a row (hi = bf16(x), lo = bf16(x - hi)) stored as 8-byte vectors (4 bf16 per lane per chunk)
+template <int NC>
+__device__ __forceinline__ void row_store_bf16_split(const RowVec<NC>& r, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                     int d, int lane) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    int col = (c * 32 + lane) * 4;
+    if (col < d) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(r.v[c].x, r.v[c].y), h1 = __floats2bfloat162_rn(r.v[c].z, r.v[c].w);
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(r.v[c].x - f0.x, r.v[c].y - f0.y);
+      const __nv_bfloat162 l1 = __floats2bfloat162_rn(r.v[c].z - f1.x, r.v[c].w - f1.y);
+      *reinterpret_cast<uint2*>(hi + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(lo + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
   }
 }
 

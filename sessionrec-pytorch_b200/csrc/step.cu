@@ -139,6 +139,8 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   fl += 2LL * N * d + 3LL * B * d + N + 2LL * B + 4LL * B * d + B;    // u, v, e, ms, sr_in, s, shat, rn_s
   fl += 2LL * B * ldz + 4LL * B * d + 2LL * B + 64 + 4LL * ((V + 255) / 256) * B + B;        // Z, Zlo, sh, sl, dshat, ds, lse, nll
   fl += 2LL * B * d + (long long)N * d;                    // dsr_in, dF
+  // flash CE head: bf16 hi/lo of Ehat and shat, soft-max partials, one [V, d] dE partial per 128-session tile
+  fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
   fl += 2LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
   return fl * 5 + (1 << 20);                               // floats -> bytes with 25% head-room + alignment slack
@@ -164,6 +166,8 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   const int ldzel = H * d + H;
   const bool umma = (use_umma & 1) && d <= 256;
   const bool fused_lse = (use_umma & 2) != 0;      // bit 1: persistent forward kernel with the fused LSE epilogue
+  // bit 2: fused scoring + CE head (csrc/flash_ce.cu): no (B, V) logits in memory, bf16 x 3 tensor-core products
+  const bool flash = umma && (use_umma & 4) != 0 && d >= 16 && d <= 128 && d % 16 == 0;
   const bool drop = dropout_p > 0.f;
   Arena ar{reinterpret_cast<uint8_t*>(workspace), (size_t)workspace_bytes, 0, true};
   auto P = [&](int slot) { return params + slot_off_host[slot]; };
@@ -185,9 +189,16 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   // ---- forward -------------------------------------------------------------------------------------------
   float *Ehat = ar.f((size_t)V * d), *enorm = ar.f(V);
   float *Ehi = nullptr, *Elo = nullptr;
-  if (umma) { Ehi = ar.f((size_t)V * d); Elo = ar.f((size_t)V * d); }
+  uint16_t *Ebh = nullptr, *Ebl = nullptr;
+  if (flash) {
+    Ebh = reinterpret_cast<uint16_t*>(ar.raw((size_t)V * d * 2));
+    Ebl = reinterpret_cast<uint16_t*>(ar.raw((size_t)V * d * 2));
+  } else if (umma) {
+    Ehi = ar.f((size_t)V * d);
+    Elo = ar.f((size_t)V * d);
+  }
   SRK_REQUIRE(ar.ok, "step: workspace too small");
-  SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, st));
+  SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, Ebh, Ebl, st));
   tm.mark("catalog_prep");
   float *X = ar.f((size_t)N * d), *rnX = ar.f(N);
   srk_dropout dc_e = dcfg(SRK_SITE_EMBED + 1);
@@ -265,10 +276,18 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
   tm.mark("readout_fwd");
   // scoring head + CE
-  float *Z = ar.f((size_t)B * ldz), *lse = ar.f(B), *nll = ar.f(B);
+  float *Z = flash ? nullptr : ar.f((size_t)B * ldz), *lse = ar.f(B), *nll = ar.f(B);
   float *sh = nullptr, *sl = nullptr;
+  uint16_t *Sbh = nullptr, *Sbl = nullptr;
   SRK_REQUIRE(ar.ok, "step: workspace too small");
-  if (umma) {
+  if (flash) {
+    Sbh = reinterpret_cast<uint16_t*>(ar.raw((size_t)B * d * 2));
+    Sbl = reinterpret_cast<uint16_t*>(ar.raw((size_t)B * d * 2));
+    float* part = ar.f((size_t)srk_flash_ce_part_floats(B, V));
+    SRK_REQUIRE(ar.ok, "step: workspace too small");
+    SRK_TRY(srk_split_bf16(shat, d, B, d, Sbh, Sbl, d, st));
+    SRK_TRY(srk_flash_ce_fwd(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, b.labels, lse, nll, part, st));
+  } else if (umma) {
     sh = ar.f((size_t)B * d); sl = ar.f((size_t)B * d);
     SRK_TRY(srk_split_tf32(shat, d, B, d, sh, sl, d, st));
     if (fused_lse) {
@@ -287,11 +306,14 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
 
   tm.mark("score_fwd+lse");
   // ---- backward ------------------------------------------------------------------------------------------
-  float* Zlo = umma ? ar.f((size_t)B * ldz) : nullptr;
-  float *dshat = ar.f((size_t)B * d), *dEhat = ar.f((size_t)V * d);
+  const int de_parts = flash ? srk_flash_ce_bwd_parts(B) : 1;
+  float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;
+  float *dshat = ar.f((size_t)B * d), *dEhat = ar.f((size_t)de_parts * V * d);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
-  SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
-  if (umma) {
+  if (flash) {
+    SRK_TRY(srk_flash_ce_bwd(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, b.labels, lse, one_dev, dshat, dEhat, st));
+  } else if (umma) {
+    SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
     // Backward of the head, chunked over catalog columns so that each chunk's dZ hi/lo pair (2 x B x Vc x 4 bytes) is
     // still L2-resident when the two tensor-core GEMMs read it (the whole pair, 2 x 88 MB at cfg1, is not).
     int chunks = head_chunks < 1 ? 1 : head_chunks;
@@ -308,13 +330,14 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
       SRK_TRY(srk_umma_gemm(2, nc, d, B, Z + c0, Zlo + c0, ldz, sh, sl, d, dEhat + (size_t)c0 * d, d, 1.0f, 0, 1, st));
     }
   } else {
+    SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
     SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, one_dev, 12.0f, B, V, 0, Zlo, st));
     SRK_CUDA(cudaMemsetAsync(dEhat, 0, sizeof(float) * (size_t)V * d, st));
     SRK_TRY(gemm(st, B, d, V, Z, ldz, 1, Ehat, d, 1, dshat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
     SRK_TRY(gemm(st, V, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
   }
   tm.mark("ce_bwd+dS+dE");
-  SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, V, d, SRK_NORM_L2, G(0), st));
+  SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, de_parts, V, d, SRK_NORM_L2, G(0), st));
   tm.mark("catalog_bwd");
   float* ds = ar.f((size_t)B * d);
   float* dsr_in = ar.f(2 * (size_t)B * d);

@@ -230,6 +230,9 @@ class MSGIFSR(SessRecModule):
                     ops.dropout_apply(tmp2, dfeat[k], tmp2.numel(), rec['dcd'], accumulate=True)
         return dfeat
 
+    def _single_head(self):
+        return not (self.order > 1 and self.fusion)
+
     # ---- native fused step (csrc/step.cu) ------------------------------------------------------------------------
     def _native_ok(self, batch):
         return self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
@@ -281,7 +284,7 @@ class MSGIFSR(SessRecModule):
             L.call('srk_msgifsr_train_step', ptr(batch.buf), ctypes.c_void_p(batch.hdr.ctypes.data), ptr(fp.data),
                    ptr(fp.grad), ctypes.c_void_p(st['slots'].ctypes.data), self.num_items, self.embedding_dim,
                    self.num_layers, float(p), ctypes.c_uint64(seed),
-                   int(self.use_tensor_cores) | (2 if self.fused_lse else 0), ptr(st['ws']),
+                   int(self.use_tensor_cores) | (2 if self.fused_lse else 0) | (4 if self.flash_ce else 0), ptr(st['ws']),
                    st['ws_bytes'], ptr(self._one()), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
                    ptr(o['seg_off']), ptr(o['seg_decay']), o['n_seg'], float(o['lr']), float(o['betas'][0]),
                    float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0 / world, phase, int(self.head_chunks), stream)

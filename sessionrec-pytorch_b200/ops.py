@@ -88,6 +88,40 @@ def split_tf32(X, ldx, rows, cols, hi, lo, ldo):
     _call('srk_split_tf32', ptr(X), ldx, rows, cols, ptr(hi), ptr(lo), ldo)
 
 
+# ---- fused scoring + cross-entropy head (csrc/flash_ce.cu) ---------------------------------------------------
+
+def flash_ce_supported(d):
+    return 16 <= d <= 128 and d % 16 == 0
+
+
+def split_bf16(X, ldx, rows, cols, hi, lo, ldo):
+    _call('srk_split_bf16', ptr(X), ldx, rows, cols, ptr(hi), ptr(lo), ldo)
+
+
+def flash_ce_part_floats(B, V):
+    return int(_lib.lib().functions['srk_flash_ce_part_floats'](B, V))
+
+
+def flash_ce_bwd_parts(B):
+    return int(_lib.lib().functions['srk_flash_ce_bwd_parts'](B))
+
+
+def flash_ce_fwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, nll, part):
+    _need_cuda(Shi, Slo, Ehi, Elo, labels, lse, part)
+    _call('srk_flash_ce_fwd', B, V, d, ptr(Shi), ptr(Slo), lds, ptr(Ehi), ptr(Elo), lde, float(scale), ptr(labels), ptr(lse),
+          ptr(nll), ptr(part))
+
+
+def flash_ce_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart):
+    _need_cuda(Shi, Slo, Ehi, Elo, labels, lse, dS, dEpart)
+    _call('srk_flash_ce_bwd', B, V, d, ptr(Shi), ptr(Slo), lds, ptr(Ehi), ptr(Elo), lde, float(scale), ptr(labels), ptr(lse),
+          ptr(gout), ptr(dS), ptr(dEpart))
+
+
+def sum_parts(parts, stride, nparts, n, out, accumulate=False):
+    _call('srk_sum_parts', ptr(parts), stride, nparts, n, ptr(out), int(bool(accumulate)))
+
+
 # ---- embedding ---------------------------------------------------------------------------------------------
 
 def embed_gather_fwd(E, iid, P, d, mode, dc, X, rnorm, x_first=None):
@@ -100,14 +134,16 @@ def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE):
           _dref(dc), ptr(rnorm), ptr(dX), ptr(dX_first), ptr(dE))
 
 
-def catalog_prep_fwd(E, mode, max_norm, Ehat, enorm, Ehi=None, Elo=None):
+def catalog_prep_fwd(E, mode, max_norm, Ehat, enorm, Ehi=None, Elo=None, Bhi=None, Blo=None):
     V, d = E.shape
-    _call('srk_catalog_prep_fwd', ptr(E), V, d, mode, float(max_norm), ptr(Ehat), ptr(enorm), ptr(Ehi), ptr(Elo))
+    _call('srk_catalog_prep_fwd', ptr(E), V, d, mode, float(max_norm), ptr(Ehat), ptr(enorm), ptr(Ehi), ptr(Elo),
+          ptr(Bhi), ptr(Blo))
 
 
-def catalog_prep_bwd(E, Ehat, enorm, dEhat, mode, dE):
+def catalog_prep_bwd(E, Ehat, enorm, dEhat, mode, dE, nparts=1):
+    """dE += rownorm-backward of dEhat; dEhat may be `nparts` stacked [V, d] partial sums (flash CE backward)."""
     V, d = E.shape
-    _call('srk_catalog_prep_bwd', ptr(E), ptr(Ehat), ptr(enorm), ptr(dEhat), V, d, mode, ptr(dE))
+    _call('srk_catalog_prep_bwd', ptr(E), ptr(Ehat), ptr(enorm), ptr(dEhat), int(nparts), V, d, mode, ptr(dE))
 
 
 def renorm_rows(E, uid, U, max_norm=1.0):
