@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import models as OM
-from tests.util import (RTOL, assert_close, assert_grad_close, assert_grad_close_robust, golden, oracle_batch,
+from tests.util import (RTOL, assert_close, assert_close_after_adam, assert_grad_close, assert_grad_close_robust, golden, oracle_batch,
                         oracle_params, run_oracle)
 
 pytestmark = pytest.mark.gpu
@@ -117,12 +117,15 @@ def test_dropout_with_injected_masks_vs_oracle(pkg, name, p):
         assert_close(f'{name}.eval logp', m(b), run_oracle(c['model'], oracle_params(c['params'], False), ob, c['L'], c['fusion']))
 
 
+@pytest.mark.parametrize('head', ['flash', 'tf32'])
 @pytest.mark.parametrize('name', sorted(TRAINS))
-def test_fused_train_step_trajectory_vs_reference(pkg, name):
+def test_fused_train_step_trajectory_vs_reference(pkg, name, head):
     """train_step (fused fwd + CE + bwd + our Adam kernel) reproduces the reference TrainRunner's losses, final
-    embedding table and evaluate() metrics."""
+    embedding table and evaluate() metrics.  head: 'flash' = fused bf16 x 3 scoring + CE head (gradients ~1e-5 relative),
+    'tf32' = materialised logits on the 3xTF32 GEMMs (~1e-6)."""
     c = TRAINS[name]
     m = make_model(pkg, c)
+    m.flash_ce = head == 'flash'
     m.train()
     m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
     for it in range(c['steps']):
@@ -130,7 +133,10 @@ def test_fused_train_step_trajectory_vs_reference(pkg, name):
         loss = m.train_step(b)
         assert abs(float(loss) - c['losses'][it]) <= RTOL * abs(c['losses'][it]), (it, float(loss), c['losses'][it])
     emb = 'embeddings.weight' if c['model'] == 'MSGIFSR' else 'embedding.weight'
-    assert_close(f'{name}.final_embedding', m.state_dict()[emb], c['final_embedding'], rtol=RTOL, floor=0.1)   # Adam steps are lr-sized: 1e-5 abs
+    if head == 'tf32':
+        assert_close(f'{name}.final_embedding', m.state_dict()[emb], c['final_embedding'], rtol=RTOL, floor=0.1)   # Adam steps are lr-sized: 1e-5 abs
+    else:
+        assert_close_after_adam(f'{name}.final_embedding', m.state_dict()[emb], c['final_embedding'], 1e-3, c['steps'])
     m.eval()
     mrr = hit = n = 0
     with torch.no_grad():
@@ -246,7 +252,8 @@ def test_native_step_two_layers_and_sgemm_head(pkg):
         outs.append((loss, m.embeddings.weight.detach().clone()))
     for loss, w in outs[1:]:
         assert abs(loss - outs[0][0]) <= 1e-5 * abs(outs[0][0])
-        assert_close('embedding after 1 step', w, outs[0][1], rtol=1e-4, floor=0.5)
+        # (True, False) compares the fused bf16 x 3 head with the fp32 FFMA head: one Adam step, see assert_close_after_adam
+        assert_close_after_adam('embedding after 1 step', w, outs[0][1], 1e-3, 1, rtol=1e-4, floor=0.5)
 
 
 @pytest.mark.parametrize('name', ['srgnn', 'niser', 'msgifsr_k1', 'msgifsr_k3'])

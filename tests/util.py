@@ -49,6 +49,20 @@ def assert_close(name, got, ref, rtol=RTOL, floor=1.0):
                              f'ref={ref.flatten()[i]:.6e} got={got.flatten()[i]:.6e} (flat index {i})')
 
 
+def assert_close_after_adam(name, got, ref, lr, steps, rtol=RTOL, floor=0.1, max_frac=2e-3):
+    """Parameters after `steps` Adam updates.  Adam's update lr * m / (sqrt(v) + eps) is sign-like: an element whose
+    gradient is within rounding of zero (|g| ~ eps = 1e-8) moves by up to lr per step in a direction that 1e-9 of
+    gradient noise decides.  So: every element within rtol * max(|ref|, floor), except at most `max_frac` of them,
+    and those no further than steps * lr away."""
+    g, r = got.detach().cpu().double(), ref.detach().cpu().double()
+    assert g.shape == r.shape and torch.isfinite(g).all(), name
+    err = (g - r).abs()
+    bad = err > rtol * r.abs().clamp(min=floor)
+    nbad = int(bad.sum())
+    assert nbad <= max_frac * bad.numel(), f'{name}: {nbad}/{bad.numel()} elements off (worst {float(err.max()):.3e})'
+    assert float(err.max()) <= steps * lr * 1.001, f'{name}: an element moved {float(err.max()):.3e} > steps * lr'
+
+
 def assert_grad_close(name, got, ref, rtol=RTOL):
     """Max-norm relative: max|got - ref| <= rtol * max|ref| (absolute 1e-7 for numerically-zero grads)."""
     if ref is None:
