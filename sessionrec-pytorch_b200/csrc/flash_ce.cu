@@ -23,6 +23,7 @@
 //                                                          fp32 staging area of the TMA stores of dE / dS
 // TMEM (512 columns): logit tile x 2 (double buffer) | dS accumulator (d <= 128 columns) | dE accumulator.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "umma.cuh"
 
@@ -53,10 +54,22 @@ struct FceParams {
   const float* lse;        // bwd: [B]
   const float* gout;       // bwd: upstream gradient of the mean loss (device scalar) or null
   uint32_t idesc_z, idesc_ds, idesc_de;
+  long long* trace;        // debug: clock64 stamps of CTA 0, [role 0..2][tile < 64][8] (srk_flash_ce_set_trace), else null
 };
 
-__device__ __forceinline__ uint64_t kdesc(uint32_t addr) { return make_desc(addr, 16, 1024, 2); }        // K-major SW128
-__device__ __forceinline__ uint64_t mdesc(uint32_t addr) { return make_desc(addr, CHUNK, 1024, 2); }     // MN-major SW128
+// role: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue (warp 2 lane 0)
+__device__ __forceinline__ void tr(const FceParams& p, int role, int it, int k) {
+  if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[(role * 64 + it) * 8 + k] = clock64();
+}
+
+// UMMA shared-memory descriptors (SWIZZLE_128B, version 1): constant high part | (address >> 4).  K-major operands step
+// 32 bytes inside the 128-byte swizzle row per UMMA K (16 bf16); MN-major operands step 16 rows (2 KB) per UMMA K and find
+// the next 64-column chunk at LBO = CHUNK.  The descriptors are built with one shift + one OR per MMA: the issuing
+// thread is a single lane and every instruction it spends between two tcgen05.mma shows up as tensor-pipe idle time.
+constexpr uint64_t KDESC_HI = (uint64_t(16 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+constexpr uint64_t MDESC_HI = (uint64_t(CHUNK >> 4) << 16) | (uint64_t(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t kdesc(uint32_t addr) { return KDESC_HI | (uint64_t)((addr >> 4) & 0x3FFFu); }
+__device__ __forceinline__ uint64_t mdesc(uint32_t addr) { return MDESC_HI | (uint64_t)((addr >> 4) & 0x3FFFu); }
 
 // acc (+)= A B with both operands split hi/lo: hi*hi + hi*lo + lo*hi
 __device__ __forceinline__ void mma3(uint32_t tacc, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
@@ -69,10 +82,29 @@ __device__ __forceinline__ void mma3(uint32_t tacc, uint64_t ah, uint64_t al, ui
 // logit tile: Z[128 b x 128 v] = S E^T, K = d in steps of 16 (32 bytes inside the 128-byte swizzle row)
 __device__ __forceinline__ void issue_logits(uint32_t tz, uint32_t S, uint32_t E, uint32_t op_bytes, int d, uint32_t idesc) {
   const int nks = d >> 4;
+  const uint64_t sh = kdesc(S), sl = kdesc(S + op_bytes), eh = kdesc(E), el = kdesc(E + op_bytes);
+#pragma unroll 1
   for (int ks = 0; ks < nks; ++ks) {
-    const uint32_t off = (uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32;
-    mma3(tz, kdesc(S + off), kdesc(S + op_bytes + off), kdesc(E + off), kdesc(E + op_bytes + off), idesc, ks ? 1u : 0u);
+    const uint64_t off = (uint64_t)(((uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32) >> 4);
+    mma3(tz, sh + off, sl + off, eh + off, el + off, idesc, ks ? 1u : 0u);
   }
+}
+
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2f(float x) {           // 2^x on the SFU (MUFU.EX2), flush-to-zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// label logit of a row whose label column lies in the 32 accumulator columns at `taddr` (rare path: once per row)
+__device__ __noinline__ float pick_column(uint32_t taddr, int j) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  float x = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) x = (k == j) ? __uint_as_float(r[k]) : x;
+  return x;
 }
 
 struct TileSched {
@@ -137,8 +169,10 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       for (int t = ts.t0; t < ts.t1; ++t, ++it) {
         const int s = it % p.estages;
         mbar_wait(&e_empty[s], ((uint32_t)(it / p.estages) & 1u) ^ 1u);
+        tr(p, 0, it, 0);
         mbar_expect_tx(&e_full[s], 2 * op_bytes);
         load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, op_bytes, t * TV);
+        tr(p, 0, it, 1);
       }
     }
   } else if (warp == 1) {
@@ -148,51 +182,84 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       for (int t = ts.t0; t < ts.t1; ++t, ++it) {
         const int s = it % p.estages, zb = it & 1;
         mbar_wait(&e_full[s], (uint32_t)(it / p.estages) & 1u);
+        tr(p, 1, it, 0);
         mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tr(p, 1, it, 1);
         fence_tc_after();
         issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, smem_u32(S), smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p.d,
                      p.idesc_z);
         umma_commit(&e_empty[s]);
         umma_commit(&z_full[zb]);
+        tr(p, 1, it, 2);
       }
     }
   } else {
+    // Per-row online soft-max in base 2: t = acc * (scale * log2 e), running maximum m2 and s = sum 2^(t - m2) in four
+    // independent partial sums (the chain of dependent FADDs would otherwise leave the two warps per scheduler idle).
+    // Per element: FMNMX, FFMA, MUFU.EX2, FADD.
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int b = ts.tb * TB + q * 32 + lane;
     const int lab = b < p.B ? p.labels[b] : -1;
-    float rmax = -3.0e38f, rsum = 0.f, zl = 0.f;
+    const float c2 = p.scale * LOG2E;
+    const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+    float m2 = -3.0e38f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, zl = 0.f;
     bool has = false;
     int it = 0;
     for (int t = ts.t0; t < ts.t1; ++t, ++it) {
       const int zb = it & 1;
       mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
+      if (warp == 2 && lane == 0) tr(p, 2, it, 0);
       fence_tc_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c0 = half * 64 + cc * 32;
+        const uint32_t taddr = tmem_base + lanebits + TM_Z + (uint32_t)(zb * TV + c0);
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TM_Z + (uint32_t)(zb * TV + c0), r);
+        tmem_ld32(taddr, r);
         const int v0 = t * TV + c0;
         const int nvalid = min(32, p.V - v0);
-        if (nvalid > 0) {
-          float z[32];
+        if (nvalid == 32) {
+          float a0 = __uint_as_float(r[0]), a1 = __uint_as_float(r[1]), a2 = __uint_as_float(r[2]), a3 = __uint_as_float(r[3]);
+#pragma unroll
+          for (int j = 4; j < 32; j += 4) {
+            a0 = fmaxf(a0, __uint_as_float(r[j]));
+            a1 = fmaxf(a1, __uint_as_float(r[j + 1]));
+            a2 = fmaxf(a2, __uint_as_float(r[j + 2]));
+            a3 = fmaxf(a3, __uint_as_float(r[j + 3]));
+          }
+          const float cm2 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * c2;
+          if (cm2 > m2) {
+            const float f = ex2f(m2 - cm2);
+            s0 *= f; s1 *= f; s2 *= f; s3 *= f;
+            m2 = cm2;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            s0 += ex2f(fmaf(__uint_as_float(r[j]), c2, -m2));
+            s1 += ex2f(fmaf(__uint_as_float(r[j + 1]), c2, -m2));
+            s2 += ex2f(fmaf(__uint_as_float(r[j + 2]), c2, -m2));
+            s3 += ex2f(fmaf(__uint_as_float(r[j + 3]), c2, -m2));
+          }
+        } else if (nvalid > 0) {                 // ragged last catalog tile
           float cm = -3.0e38f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            z[j] = p.scale * __uint_as_float(r[j]);
-            if (j < nvalid) cm = fmaxf(cm, z[j]);
-          }
-          if (cm > rmax) {
-            rsum *= __expf(rmax - cm);
-            rmax = cm;
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) cm = fmaxf(cm, __uint_as_float(r[j]));
+          const float cm2 = cm * c2;
+          if (cm2 > m2) {
+            const float f = ex2f(m2 - cm2);
+            s0 *= f; s1 *= f; s2 *= f; s3 *= f;
+            m2 = cm2;
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < nvalid) rsum += __expf(z[j] - rmax);
-          if (lab >= v0 && lab < v0 + nvalid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j == lab - v0) zl = z[j];
+            if (j < nvalid) s0 += ex2f(fmaf(__uint_as_float(r[j]), c2, -m2));
+        }
+        const bool mine = lab >= v0 && lab < v0 + nvalid;
+        if (__any_sync(SRK_FULL, mine)) {          // tcgen05.ld is warp-collective: every lane re-reads, owners keep
+          const float x = p.scale * pick_column(taddr, lab - v0);
+          if (mine) {
+            zl = x;
             has = true;
           }
         }
@@ -200,12 +267,13 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       fence_tc_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&z_empty[zb]);
+      if (warp == 2 && lane == 0) tr(p, 2, it, 1);
     }
     if (b < p.B) {
       const int vr = blockIdx.x / p.ntm;
       float* pp = p.part + ((long long)(vr * 2 + half) * p.B + b) * 2;
-      pp[0] = rmax;
-      pp[1] = rsum;
+      pp[0] = m2 * LN2;                          // natural-log units: max logit, sum exp(logit - max)
+      pp[1] = (s0 + s1) + (s2 + s3);
       if (has) p.zlab[b] = zl;
     }
   }
@@ -262,7 +330,8 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const float4* __restrict
 }
 
 // ---- backward ---------------------------------------------------------------------------------------------------------
-// 32 consecutive dZ values of tile row r (columns c0 .. c0 + 31) -> bf16 hi/lo, 128-byte-swizzled rows of the D tile
+// 32 consecutive dZ values of tile row r (columns c0 .. c0 + 31) -> bf16 hi/lo, 128-byte-swizzled rows of the D tile.
+// hi = the upper 16 bits of the fp32 value (truncation: one PRMT packs two of them), lo = bf16_rn(x - hi) (x - hi is exact).
 __device__ __forceinline__ void store_dz(uint8_t* Dhi, uint8_t* Dlo, int r, int c0, const float* dz) {
   const uint32_t base = (uint32_t)(c0 >> 6) * CHUNK + (uint32_t)r * 128;
   const uint32_t u0 = (uint32_t)(c0 & 63) >> 3;
@@ -271,17 +340,29 @@ __device__ __forceinline__ void store_dz(uint8_t* Dhi, uint8_t* Dlo, int r, int 
     uint32_t h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float x0 = dz[8 * j + 2 * k], x1 = dz[8 * j + 2 * k + 1];
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
-      const float2 hf = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-      h[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      const uint32_t x0 = __float_as_uint(dz[8 * j + 2 * k]), x1 = __float_as_uint(dz[8 * j + 2 * k + 1]);
+      h[k] = __byte_perm(x0, x1, 0x7632);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(dz[8 * j + 2 * k] - __uint_as_float(x0 & 0xFFFF0000u),
+                                                      dz[8 * j + 2 * k + 1] - __uint_as_float(x1 & 0xFFFF0000u));
       l[k] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     const uint32_t pu = ((u0 + j) ^ ((uint32_t)r & 7u)) * 16;
     *reinterpret_cast<uint4*>(Dhi + base + pu) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(Dlo + base + pu) = make_uint4(l[0], l[1], l[2], l[3]);
   }
+}
+
+// dZ[r, c] -= x for one element already stored by store_dz (the onehot term of the label column: once per row)
+__device__ __noinline__ void fix_dz(uint8_t* Dhi, uint8_t* Dlo, int r, int c, float x) {
+  const uint32_t off = (uint32_t)(c >> 6) * CHUNK + (uint32_t)r * 128 + ((((uint32_t)(c & 63) >> 3) ^ ((uint32_t)r & 7u)) * 16) +
+                       (uint32_t)(c & 7) * 2;
+  uint16_t* ph = reinterpret_cast<uint16_t*>(Dhi + off);
+  uint16_t* pl = reinterpret_cast<uint16_t*>(Dlo + off);
+  const float g = __uint_as_float((uint32_t)*ph << 16) + __uint_as_float((uint32_t)*pl << 16) - x;
+  const uint32_t gb = __float_as_uint(g);
+  *ph = (uint16_t)(gb >> 16);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(g - __uint_as_float(gb & 0xFFFF0000u));
+  *pl = *reinterpret_cast<const uint16_t*>(&lo);
 }
 
 // 32 fp32 accumulator columns of tile row r -> swizzled fp32 staging chunk (128 rows x 128 B) for a TMA store
@@ -340,8 +421,10 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       for (int it = 0; it < ntiles; ++it) {
         const int s = it % p.estages;
         mbar_wait(&e_empty[s], ((uint32_t)(it / p.estages) & 1u) ^ 1u);
+        tr(p, 0, it, 0);
         mbar_expect_tx(&e_full[s], 2 * op_bytes);
         load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, op_bytes, (ts.t0 + it) * TV);
+        tr(p, 0, it, 1);
       }
     }
   } else if (warp == 1) {
@@ -351,10 +434,12 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       auto logits = [&](int it) {
         const int s = it % p.estages, zb = it & 1;
         mbar_wait(&e_full[s], (uint32_t)(it / p.estages) & 1u);
+        tr(p, 1, it, 0);
         mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_tc_after();
         issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, Sa, smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p.d, p.idesc_z);
         umma_commit(&z_full[zb]);
+        tr(p, 1, it, 1);
       };
       mbar_wait(&s_full, 0);
       logits(0);
@@ -364,23 +449,30 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         const int s = it % p.estages;
         const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * op_bytes);
         mbar_wait(&d_full, (uint32_t)it & 1u);
+        tr(p, 1, it, 2);
         fence_tc_after();
         // dS[128 b x d] += dZ[128 b x 128 v] E[128 v x d]: A = D K-major, B = E MN-major, K = v in steps of 16 rows
-#pragma unroll 1
-        for (int ks = 0; ks < TV / 16; ++ks) {
-          const uint32_t aoff = (uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32, boff = (uint32_t)ks * 2048;
-          mma3(tds, kdesc(Da + aoff), kdesc(Da + 2 * CHUNK + aoff), mdesc(Ea + boff), mdesc(Ea + op_bytes + boff), p.idesc_ds,
-               (it | ks) ? 1u : 0u);
+        {
+          const uint64_t ah = kdesc(Da), al = kdesc(Da + 2 * CHUNK), bh = mdesc(Ea), bl = mdesc(Ea + op_bytes);
+#pragma unroll
+          for (int ks = 0; ks < TV / 16; ++ks) {
+            const uint64_t aoff = (uint64_t)(((uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32) >> 4);
+            const uint64_t boff = (uint64_t)((uint32_t)ks * 2048 >> 4);
+            mma3(tds, ah + aoff, al + aoff, bh + boff, bl + boff, p.idesc_ds, (it | ks) ? 1u : 0u);
+          }
         }
         umma_commit(&e_empty[s]);
         // dE[128 v x d] = dZ^T[128 v x 128 b] S[128 b x d]: A = D MN-major, B = S MN-major, K = b in steps of 16 rows
-#pragma unroll 1
-        for (int ks = 0; ks < TB / 16; ++ks) {
-          const uint32_t off = (uint32_t)ks * 2048;
-          mma3(tde, mdesc(Da + off), mdesc(Da + 2 * CHUNK + off), mdesc(Sa + off), mdesc(Sa + op_bytes + off), p.idesc_de,
-               ks ? 1u : 0u);
+        {
+          const uint64_t ah = mdesc(Da), al = mdesc(Da + 2 * CHUNK), bh = mdesc(Sa), bl = mdesc(Sa + op_bytes);
+#pragma unroll
+          for (int ks = 0; ks < TB / 16; ++ks) {
+            const uint64_t off = (uint64_t)((uint32_t)ks * 2048 >> 4);
+            mma3(tde, ah + off, al + off, bh + off, bl + off, p.idesc_de, ks ? 1u : 0u);
+          }
         }
         umma_commit(&d_empty);
+        tr(p, 1, it, 3);
         if (p.estages == 1 && it + 1 < ntiles) logits(it + 1);
       }
     }
@@ -389,9 +481,15 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
     const int r = q * 32 + lane;                     // row of the tile owned by this thread (= TMEM lane)
     const int b = ts.tb * TB + r;
     const bool bvalid = b < p.B;
-    const float lse_b = bvalid ? p.lse[b] : 0.f;
     const int lab = bvalid ? p.labels[b] : -1;
-    const float coef = p.scale * (p.gout ? p.gout[0] : 1.f) / (float)p.B;
+    // dZ = coef * (softmax - onehot) with softmax = 2^(acc * c2 - lse2); rows beyond B get coef = 0
+    const float c2 = p.scale * LOG2E;
+    // lse * log2(e) is kept as hi + lo (lo = the rounding residual of the product): a 1e-6 relative error of lse2 would
+    // be a systematic 1e-5 relative error of every soft-max value of the row; 2^-lo is folded into the row's coefficient
+    const float lse_b = bvalid ? p.lse[b] : 0.f;
+    const float lse2 = lse_b * LOG2E;
+    const float coef = bvalid ? p.scale * (p.gout ? p.gout[0] : 1.f) / (float)p.B : 0.f;
+    const float coef_p = coef * ex2f(-fmaf(lse_b, LOG2E, -lse2));
     const uint32_t lanebits = (uint32_t)(q * 32) << 16;
     const int nc32 = (p.d + 31) >> 5;                // 32-column fp32 chunks of the dS / dE accumulators
     const bool elected = (warp == 2 && lane == 0);
@@ -400,10 +498,12 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
     for (int it = 0; it < ntiles; ++it) {
       const int t = ts.t0 + it, zb = it & 1;
       mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
+      if (elected) tr(p, 2, it, 0);
       fence_tc_after();
       // the previous tile's TMA stores must have finished reading the staging area (= the D tile) before it is rewritten
       if (elected) tma_wait_group_read0();
       named_bar_sync(1, EPI_THREADS);
+      if (elected) tr(p, 2, it, 1);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c0 = half * 64 + cc * 32;
@@ -412,12 +512,14 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         const int v0 = t * TV + c0;
         float dz[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float pr = __expf(p.scale * __uint_as_float(acc[j]) - lse_b);
-          const float g = coef * (pr - (v0 + j == lab ? 1.f : 0.f));
-          dz[j] = (bvalid && v0 + j < p.V) ? g : 0.f;
+        for (int j = 0; j < 32; ++j) dz[j] = coef_p * ex2f(fmaf(__uint_as_float(acc[j]), c2, -lse2));
+        if (v0 + 32 > p.V) {                      // ragged last catalog tile: columns beyond V carry no gradient
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (v0 + j >= p.V) dz[j] = 0.f;
         }
         store_dz(Dhi, Dlo, r, c0, dz);
+        if (lab >= v0 && lab < v0 + 32) fix_dz(Dhi, Dlo, r, lab - t * TV, coef);
       }
       fence_tc_before();
       fence_async_smem();
@@ -426,8 +528,10 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         mbar_arrive(&z_empty[zb]);
         mbar_arrive(&d_full);
       }
+      if (elected) tr(p, 2, it, 2);
       // both gradient products of this tile are complete: drain the dE accumulator (rows = catalog rows of the tile)
       mbar_wait(&d_empty, (uint32_t)it & 1u);
+      if (elected) tr(p, 2, it, 3);
       fence_tc_after();
       for (int cc = half; cc < nc32; cc += 2) {
         uint32_t acc[32];
@@ -440,6 +544,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       if (elected) {
         for (int cc = 0; cc < nc32; ++cc) tma_store_3d(&mdE, Dt + (uint32_t)cc * CHUNK, cc * 32, t * TV, ts.tb);
         tma_commit_group();
+        tr(p, 2, it, 4);
       }
     }
     // dS accumulator of this CTA's catalog range -> reduce-add into dS[B, d]
@@ -481,12 +586,24 @@ __global__ void split_bf16_kernel(const float* __restrict__ X, long long ldx, in
   }
 }
 
+long long* g_trace = nullptr;
+
 int bf16_map(CUtensorMap* m, const uint16_t* base, int d, int rows, long long ld) {
   SRK_REQUIRE(ld % 8 == 0, "flash_ce: bf16 operand pitch must be a multiple of 8 elements");
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64, 128};
-  return make_map_nd(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box);
+  // operand rows are 2 * d bytes apart and every 128-byte box row is consumed whole: L2 promotion beyond the box row only
+  // multiplies the L2 -> SM sector traffic (measured: 3x with L2_256B at d = 96).  SESSREC_FCE_L2PROMO = 0..3 overrides.
+  static int promo = -1;
+  if (promo < 0) {
+    const char* e = getenv("SESSREC_FCE_L2PROMO");
+    promo = e ? atoi(e) : 0;
+    if (promo < 0 || promo > 3) promo = 0;
+  }
+  const CUtensorMapL2promotion pm[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
+  return make_map_nd(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, pm[promo]);
 }
 
 int fill_params(FceParams& p, int B, int V, int d, float scale, const int* labels, bool bwd) {
@@ -512,8 +629,10 @@ int fill_params(FceParams& p, int B, int V, int d, float scale, const int* label
   if (st > (bwd ? 3 : MAX_STAGES)) st = bwd ? 3 : MAX_STAGES;
   SRK_REQUIRE(st >= 1, "flash_ce: shared-memory budget exceeded");
   p.estages = st;
+  SRK_REQUIRE(scale > 0.f, "flash_ce: scale must be positive");
   p.scale = scale;
   p.labels = labels;
+  p.trace = g_trace;
   // instruction descriptors: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), majors (bit 15 / 16: 1 = MN-major), N >> 3, M >> 4
   const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 4) << 24);
   p.idesc_z = base | ((uint32_t)(TV >> 3) << 17);
@@ -623,5 +742,11 @@ extern "C" int srk_sum_parts(const float* parts, long long stride, int nparts, l
   sum_parts_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(parts), stride / 4, nparts, n / 4,
                                                              reinterpret_cast<float4*>(out), accumulate);
   SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+/* Debug aid: device buffer of 3 * 64 * 8 int64 that receives clock64() stamps of CTA 0's three roles (NULL = off). */
+extern "C" int srk_flash_ce_set_trace(long long* trace_dev) {
+  g_trace = trace_dev;
   return SRK_OK;
 }

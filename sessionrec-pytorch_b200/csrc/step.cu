@@ -51,6 +51,48 @@ struct StageTimer {
   }
 };
 
+// Side streams of the native step.  The session encoder is a tree of small, latency-bound kernels (N ~ 2 k nodes): the
+// two GAT convolutions of a layer (graph / reversed graph), the weight-gradient GEMMs and the catalog backward are
+// independent of each other, so they are enqueued on side streams (fork / join with events) and overlap on the 148 SMs.
+// SESSREC_STREAMS=0 keeps everything on the caller's stream.
+struct SideStreams {
+  static constexpr int NS = 4, NE = 32;
+  cudaStream_t s[NS];
+  cudaEvent_t ev[NE];
+  int next = 0;
+  bool ok = false;
+  int init() {
+    for (int i = 0; i < NS; ++i) SRK_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+    for (int i = 0; i < NE; ++i) SRK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    ok = true;
+    return SRK_OK;
+  }
+  // everything enqueued on `to` after this call waits for what is on `from` now
+  int order(cudaStream_t from, cudaStream_t to) {
+    if (from == to) return SRK_OK;
+    cudaEvent_t e = ev[next];
+    next = (next + 1) % NE;
+    SRK_CUDA(cudaEventRecord(e, from));
+    SRK_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return SRK_OK;
+  }
+};
+
+SideStreams* side_streams() {
+  static SideStreams per_dev[16];
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SESSREC_STREAMS");
+    enabled = !(e && e[0] == '0');
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStreams* ss = &per_dev[dev];
+  if (!ss->ok && ss->init() != SRK_OK) return nullptr;
+  return ss;
+}
+
 struct Arena {
   uint8_t* base;
   size_t cap, off;
@@ -142,7 +184,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   // flash CE head: bf16 hi/lo of Ehat and shat, soft-max partials, one [V, d] dE partial per 128-session tile
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
-  fl += 2LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
+  fl += 3LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
   return fl * 5 + (1 << 20);                               // floats -> bytes with 25% head-room + alignment slack
 }
 
@@ -183,7 +225,12 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
                          eps, adam_step, grad_scale, st);
   }
   StageTimer tm(st);
-  SRK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_flat, st));
+  SideStreams* ss = side_streams();
+  cudaStream_t s1 = ss ? ss->s[0] : st, s2 = ss ? ss->s[1] : st, s3 = ss ? ss->s[2] : st, s4 = ss ? ss->s[3] : st;
+  auto order = [&](cudaStream_t from, cudaStream_t to) { return ss ? ss->order(from, to) : (int)SRK_OK; };
+  // zero_grad runs beside the forward pass; the first gradient is written after the head's backward
+  SRK_TRY(order(st, s4));
+  SRK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_flat, s4));
   tm.mark("zero_grad");
 
   // ---- forward -------------------------------------------------------------------------------------------
@@ -214,14 +261,17 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     R.normalize = (l == L - 1);
     R.n_inst = M > 0 ? 2 : 0;
     srk_gat_inst insts[2];
+    SRK_TRY(order(st, s1));                      // the layer input is ready on the main stream
+    SRK_TRY(order(st, s2));
     for (int c = 0; c < R.n_inst; ++c) {
+      cudaStream_t sc = c == 0 ? st : s1;        // conv1 (graph) on the main stream, conv2 (reversed graph) beside it
       InstRec& I = R.inst[c];
       const int base = 1 + 8 * l + 4 * c;        // attn_l, attn_r, bias, fc.weight
       I.al = P(base); I.ar = P(base + 1); I.W = P(base + 3);
       I.gal = G(base); I.gar = G(base + 1); I.gbias = G(base + 2); I.gW = G(base + 3);
       I.Waug = ar.f((size_t)ldzel * d);
       I.wr = ar.f((size_t)H * d);
-      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, st));
+      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, sc));
       const uint32_t slot = (uint32_t)((l * 2 + c) * 3);
       I.drop = drop;
       I.xs = const_cast<float*>(h);
@@ -231,15 +281,15 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
         I.dcd = dcfg(SRK_SITE_GAT_DST + 4 * slot);
         I.xs = ar.f((size_t)N * d);
         I.xd = ar.f((size_t)N * d);
-        SRK_TRY(srk_dropout_apply(h, I.xs, (long long)N * d, &I.dcs, 0, st));
-        SRK_TRY(srk_dropout_apply(h, I.xd, (long long)N * d, &I.dcd, 0, st));
+        SRK_TRY(srk_dropout_apply(h, I.xs, (long long)N * d, &I.dcs, 0, sc));
+        SRK_TRY(srk_dropout_apply(h, I.xd, (long long)N * d, &I.dcd, 0, sc));
       }
       float* Zel = ar.f((size_t)N * ldzel);
       float* er = ar.f((size_t)N * H);
       float* att = ar.f((size_t)(M + 1) * H);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_TRY(linear_nt(st, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
-      SRK_TRY(linear_nt(st, N, H, d, I.xd, d, I.wr, er, H));
+      SRK_TRY(linear_nt(sc, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
+      SRK_TRY(linear_nt(sc, N, H, d, I.xd, d, I.wr, er, H));
       srk_gat_inst& g = I.gi;
       memset(&g, 0, sizeof(g));
       if (c == 0) {
@@ -259,7 +309,9 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     R.rn = ar.f(N);
     R.amax = ar.raw((size_t)N * d);
     SRK_REQUIRE(ar.ok, "step: workspace too small");
-    SRK_TRY(srk_segmean_fwd(h, b.seg, B, d, segmean, st));
+    SRK_TRY(srk_segmean_fwd(h, b.seg, B, d, segmean, s2));
+    SRK_TRY(order(s1, st));
+    SRK_TRY(order(s2, st));
     SRK_TRY(srk_gat_aggregate_fwd(insts, R.n_inst, N, d, segmean, b.node2seg, drop ? &dc_attn : nullptr, R.normalize, R.Hout,
                                   R.rn, R.amax, st));
     h = R.Hout;
@@ -269,8 +321,10 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   float *u = ar.f((size_t)N * d), *v = ar.f((size_t)B * d), *e = ar.f(N), *ms = ar.f(2 * (size_t)B);
   float *sr_in = ar.f(2 * (size_t)B * d), *s = ar.f((size_t)B * d), *shat = ar.f((size_t)B * d), *rn_s = ar.f(B);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
+  SRK_TRY(order(st, s1));
   SRK_TRY(linear_nt(st, N, d, d, F, d, P(s_ro), u, d, nullptr, P(s_ro + 1)));
-  SRK_TRY(linear_nt(st, B, d, d, F, d, P(s_ro + 2), v, d, b.last, nullptr));
+  SRK_TRY(linear_nt(s1, B, d, d, F, d, P(s_ro + 2), v, d, b.last, nullptr));
+  SRK_TRY(order(s1, st));
   SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, 1, e, ms, sr_in, st));
   SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
   SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
@@ -337,21 +391,28 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     SRK_TRY(gemm(st, V, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
   }
   tm.mark("ce_bwd+dS+dE");
-  SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, de_parts, V, d, SRK_NORM_L2, G(0), st));
+  // gradients start here: zero_grad (s4) must be complete; the catalog backward (a [V, d] pass) stays on s4 and runs
+  // beside the whole encoder backward, it only has to finish before the scatter-add touches the same rows
+  SRK_TRY(order(s4, st));
+  SRK_TRY(order(st, s4));
+  SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, de_parts, V, d, SRK_NORM_L2, G(0), s4));
   tm.mark("catalog_bwd");
   float* ds = ar.f((size_t)B * d);
   float* dsr_in = ar.f(2 * (size_t)B * d);
   float* dF = ar.f((size_t)N * d);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
+  // data gradients on the main stream, weight gradients (mm_tn / colsum into the flat gradient buffer) on s2
   SRK_TRY(srk_rownorm_bwd(s, d, shat, d, rn_s, dshat, d, B, d, SRK_NORM_L2, ds, d, 0, st));
+  SRK_TRY(order(st, s2));
   SRK_TRY(mm_nn(st, B, 2 * d, d, ds, d, P(s_ro + 4), 2 * d, dsr_in, 2 * d, 0));
-  SRK_TRY(mm_tn(st, d, 2 * d, B, ds, d, sr_in, 2 * d, G(s_ro + 4), 2 * d));
+  SRK_TRY(mm_tn(s2, d, 2 * d, B, ds, d, sr_in, 2 * d, G(s_ro + 4), 2 * d));
   SRK_TRY(srk_readout_bwd(F, u, v, P(s_ro + 3), b.seg, b.last, e, ms, sr_in, dsr_in, B, d, 1, dF, G(s_ro + 3), st));
+  SRK_TRY(order(st, s2));
   SRK_TRY(mm_nn(st, N, d, d, u, d, P(s_ro), d, dF, d, 1));                      // u holds du
-  SRK_TRY(mm_tn(st, d, d, N, u, d, F, d, G(s_ro), d));
-  SRK_TRY(srk_colsum(u, d, N, d, G(s_ro + 1), 1, st));
+  SRK_TRY(mm_tn(s2, d, d, N, u, d, F, d, G(s_ro), d));
+  SRK_TRY(srk_colsum(u, d, N, d, G(s_ro + 1), 1, s2));
   SRK_TRY(mm_nn(st, B, d, d, v, d, P(s_ro + 2), d, dF, d, 1, b.last));          // v holds dv
-  SRK_TRY(mm_tn(st, d, d, B, v, d, F, d, G(s_ro + 2), d, b.last));
+  SRK_TRY(mm_tn(s2, d, d, B, v, d, F, d, G(s_ro + 2), d, b.last));
 
   tm.mark("readout_bwd");
   // layers, last to first.  Scratch below is re-carved per layer from a fixed mark.
@@ -365,6 +426,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     float* bufA = ar.f((size_t)N * d);
     float* bufB = ar.f((size_t)N * d);
     dfeat = ((L - 1 - l) & 1) ? bufB : bufA;
+    float* dfeat1 = ar.f((size_t)N * d);        // conv2's share of d(layer input): summed into dfeat after the join
     float* dHpre = ar.f((size_t)N * d);
     srk_gat_inst insts[2];
     float *dedge[2], *der[2], *dZel[2];
@@ -378,39 +440,54 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     SRK_REQUIRE(ar.ok, "step: workspace too small");
     SRK_TRY(srk_gat_aggregate_bwd_dst(insts, R.n_inst, N, d, drop ? &dc_attn : nullptr, R.normalize, R.Hout, R.rn, R.amax, dH,
                                       dHpre, st));
+    SRK_TRY(order(st, s1));
     SRK_TRY(srk_segmean_bwd(dHpre, b.seg, B, d, dfeat, 0, st));
     for (int c = 0; c < R.n_inst; ++c) {
+      // conv c: data-gradient chain on dsc (conv1: main stream, conv2: s1), its weight gradients on wsc (s2 / s3)
+      cudaStream_t dsc = c == 0 ? st : s1, wsc = c == 0 ? s2 : s3;
+      float* dfc = c == 0 ? dfeat : dfeat1;
+      const int acc0 = c == 0 ? 1 : 0;           // dfeat already holds the segment-mean term; dfeat1 starts empty
       InstRec& I = R.inst[c];
-      SRK_TRY(srk_gat_bias_bwd(dHpre, R.amax, N, d, I.gbias, st));
-      SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, st));
+      SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, dsc));
+      SRK_TRY(order(dsc, wsc));
+      SRK_TRY(srk_gat_bias_bwd(dHpre, R.amax, N, d, I.gbias, wsc));
       float* dWaug = ar.f((size_t)ldzel * d);
       float* dwr = ar.f((size_t)H * d);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_CUDA(cudaMemsetAsync(dWaug, 0, sizeof(float) * (size_t)ldzel * d, st));
-      SRK_CUDA(cudaMemsetAsync(dwr, 0, sizeof(float) * (size_t)H * d, st));
-      SRK_TRY(mm_tn(st, ldzel, d, N, dZel[c], ldzel, I.xs, d, dWaug, d));
-      SRK_TRY(mm_tn(st, H, d, N, der[c], H, I.xd, d, dwr, d));
-      SRK_TRY(srk_gat_prep_bwd(I.W, I.al, I.ar, dWaug, dwr, d, I.gW, I.gal, I.gar, st));
+      SRK_CUDA(cudaMemsetAsync(dWaug, 0, sizeof(float) * (size_t)ldzel * d, wsc));
+      SRK_CUDA(cudaMemsetAsync(dwr, 0, sizeof(float) * (size_t)H * d, wsc));
+      SRK_TRY(mm_tn(wsc, ldzel, d, N, dZel[c], ldzel, I.xs, d, dWaug, d));
+      SRK_TRY(mm_tn(wsc, H, d, N, der[c], H, I.xd, d, dwr, d));
+      SRK_TRY(srk_gat_prep_bwd(I.W, I.al, I.ar, dWaug, dwr, d, I.gW, I.gal, I.gar, wsc));
       if (!I.drop) {
-        SRK_TRY(mm_nn(st, N, d, ldzel, dZel[c], ldzel, I.Waug, d, dfeat, d, 1));
-        SRK_TRY(mm_nn(st, N, d, H, der[c], H, I.wr, d, dfeat, d, 1));
-        SRK_TRY(srk_dropout_apply(dHpre, dfeat, (long long)N * d, nullptr, 1, st));       // residual
+        SRK_TRY(mm_nn(dsc, N, d, ldzel, dZel[c], ldzel, I.Waug, d, dfc, d, acc0));
+        SRK_TRY(mm_nn(dsc, N, d, H, der[c], H, I.wr, d, dfc, d, 1));
+        SRK_TRY(srk_dropout_apply(dHpre, dfc, (long long)N * d, nullptr, 1, dsc));       // residual
       } else {
         float* tmp = ar.f((size_t)N * d);
         float* tmp2 = ar.f((size_t)N * d);
         SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(mm_nn(st, N, d, ldzel, dZel[c], ldzel, I.Waug, d, tmp, d, 0));
-        SRK_TRY(srk_dropout_apply(tmp, dfeat, (long long)N * d, &I.dcs, 1, st));
-        SRK_CUDA(cudaMemcpyAsync(tmp2, dHpre, sizeof(float) * (size_t)N * d, cudaMemcpyDeviceToDevice, st));
-        SRK_TRY(mm_nn(st, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
-        SRK_TRY(srk_dropout_apply(tmp2, dfeat, (long long)N * d, &I.dcd, 1, st));
+        SRK_TRY(mm_nn(dsc, N, d, ldzel, dZel[c], ldzel, I.Waug, d, tmp, d, 0));
+        SRK_TRY(srk_dropout_apply(tmp, dfc, (long long)N * d, &I.dcs, acc0, dsc));
+        SRK_CUDA(cudaMemcpyAsync(tmp2, dHpre, sizeof(float) * (size_t)N * d, cudaMemcpyDeviceToDevice, dsc));
+        SRK_TRY(mm_nn(dsc, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
+        SRK_TRY(srk_dropout_apply(tmp2, dfc, (long long)N * d, &I.dcd, 1, dsc));
       }
+    }
+    SRK_TRY(order(s1, st));
+    if (R.n_inst > 1) SRK_TRY(srk_dropout_apply(dfeat1, dfeat, (long long)N * d, nullptr, 1, st));
+    if (l > 0) {                                 // the scratch region is re-carved by the next layer
+      SRK_TRY(order(s2, st));
+      SRK_TRY(order(s3, st));
     }
     dH = dfeat;
   }
   tm.mark("gat_bwd");
+  SRK_TRY(order(s4, st));                        // catalog backward done: the scatter-add updates the same table rows
   SRK_TRY(srk_embed_scatter_bwd(E, b.iid, b.perm, b.uoff, b.uid, b.U, b.P, d, SRK_NORM_L2, drop ? &dc_e : nullptr, rnX, dH,
                                 nullptr, G(0), st));
+  SRK_TRY(order(s2, st));
+  SRK_TRY(order(s3, st));
   tm.mark("scatter");
   if (phase == 0 && do_adam) {
     SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,

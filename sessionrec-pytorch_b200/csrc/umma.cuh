@@ -114,7 +114,8 @@ static __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lb
 // Generic tiled tensor map (rank <= 3), SWIZZLE_128B, zero fill out of bounds.  dims / box in elements (innermost
 // first), strides in bytes for dims 1.. (dim 0 is contiguous).
 static inline int make_map_nd(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
-                              const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                              const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                              CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
   EncodeTiledFn enc = get_encode();
   SRK_REQUIRE(enc != nullptr, "umma: cuTensorMapEncodeTiled is not available from this driver");
   SRK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "umma: tensor-map base must be 16-byte aligned");
@@ -122,7 +123,7 @@ static inline int make_map_nd(CUtensorMap* m, CUtensorMapDataType dt, int rank, 
     SRK_REQUIRE(strides_bytes[i] % 16 == 0, "umma: tensor-map strides must be multiples of 16 bytes");
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SRK_REQUIRE(r == CUDA_SUCCESS, "umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return SRK_OK;
 }
