@@ -101,7 +101,7 @@ int srk_flash_ce_bwd_parts(int B);
 int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
                      const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,
                      float* dS, float* dEpart, void* stream);
-/* Debug aid: device buffer of 3 * 64 * 8 int64 receiving clock64() stamps of CTA 0's roles per tile (NULL = off). */
+/* Debug aid: device buffer of 11 * 64 * 8 int64 receiving clock64() stamps of CTA 0's roles per tile (NULL = off). */
 int srk_flash_ce_set_trace(long long* trace_dev);
 /* out[n] (+)= sum_p parts[p * stride + i] */
 int srk_sum_parts(const float* parts, long long stride, int nparts, long long n, float* out, int accumulate, void* stream);

@@ -29,7 +29,7 @@ part = torch.empty(ops.flash_ce_part_floats(B, V), device=dev)
 dS = torch.empty(B, d, device=dev)
 dEp = torch.empty(ops.flash_ce_bwd_parts(B), V, d, device=dev)
 one = torch.ones(1, device=dev)
-trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(11 * 64 * 8, dtype=torch.int64, device=dev)
 fn = _lib.lib().functions['srk_flash_ce_set_trace']
 
 
@@ -42,19 +42,19 @@ def run(name, f, cols):
     f()
     torch.cuda.synchronize()
     fn(None)
-    t = trace.cpu().view(3, 64, 8)
+    t = trace.cpu().view(11, 64, 8)
     t0 = int(t[t > 0].min())
     print(f'== {name}: CTA 0, cycles since its first stamp')
-    for role, rn in enumerate(('tma ', 'mma ', 'epi ')):
+    for role, rn in enumerate(('tma ', 'mma ') + tuple(f'ep{w} ' for w in range(8)) + ('drn ',)):
         for it in range(64):
             row = t[role, it]
             if int(row.max()) == 0:
                 continue
-            print(f'  {rn} tile {it:2d}: ' + '  '.join(f'{c}={int(row[k]) - t0:7d}' for k, c in enumerate(cols[role]) if int(row[k]) > 0))
+            print(f'  {rn} tile {it:2d}: ' + '  '.join(f'{c}={int(row[k]) - t0:7d}' for k, c in enumerate(cols[2 if 2 <= role < 10 else min(role, 3)]) if int(row[k]) > 0))
 
 
 run('fwd', lambda: ops.flash_ce_fwd(B, V, d, Sh, Sl, d, Eh, El, d, 12.0, lab, lse, nll, part),
-    (('slot_free', 'issued'), ('e_full', 'z_empty', 'mma_issued'), ('z_full', 'done')))
+    (('slot_free', 'issued'), ('e_full', 'z_empty', 'mma_issued'), ('z_full', 'done'), ()))
 run('bwd', lambda: ops.flash_ce_bwd(B, V, d, Sh, Sl, d, Eh, El, d, 12.0, lab, lse, one, dS, dEp),
     (('slot_free', 'issued'), ('e_full', 'logits_issued', 'd_full', 'grads_issued'),
-     ('z_full', 'staging_free', 'dz_written', 'grads_done', 'stores_issued')))
+     ('z_full', 'math_done', 'd_free', 'dz_written'), ('w0_start', 'w1_start', 'w2_start', 'w3_start')))

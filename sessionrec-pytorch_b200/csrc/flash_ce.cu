@@ -37,14 +37,26 @@ constexpr uint32_t CHUNK = 128 * 128;       // bytes of one 128-row x 128-byte o
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
+constexpr int DRAIN_WARPS = 4;                    // backward kernel only: one warp per TMEM lane quadrant drains dE / dS
+constexpr int DRAIN_THREADS = 32 * DRAIN_WARPS;
+constexpr int THREADS_BWD = THREADS + DRAIN_THREADS;
 constexpr uint32_t D_BYTES = 4 * CHUNK;     // dZ hi (2 chunks of 64 columns) + dZ lo
 constexpr size_t FCE_MAX_SMEM = 227 * 1024 - 1024;
 constexpr int MAX_STAGES = 4;
-constexpr uint32_t TM_Z = 0, TM_DS = 256, TM_DE = 384;     // TMEM column offsets
+constexpr uint32_t TM_Z = 0, TM_DS = 256, TM_DE = 384;     // TMEM column offsets (backward)
+constexpr uint32_t TM_SA = 256;                            // forward: shat hi at [256, 320), lo at [320, 384) (bf16 pairs)
 
 struct FceParams {
   int B, V, d;
-  int nch;                 // 64-column bf16 chunks per operand row = ceil(d / 64)
+  // Operand (S, E) tiles are stored as column chunks of 128 rows: 64 bf16 per row under SWIZZLE_128B, or 32 bf16 per
+  // row under SWIZZLE_64B.  The narrow chunks waste nothing when d is a multiple of 32 but not of 64 (d = 96: 48 KB per
+  // hi/lo operand pair instead of 64 KB), which buys a second catalog stage in the backward kernel.
+  int nch;                 // chunks per operand row = ceil(d / chunk columns)
+  int cw;                  // chunk columns (64 or 32)
+  int kpc_log2;            // UMMA K steps (16 columns) per chunk, log2
+  uint32_t chunk_bytes;    // 128 rows x row_bytes
+  uint32_t row_bytes;      // 128 or 64
+  uint64_t okd_hi, omd_hi; // operand descriptor constants: K-major / MN-major
   int ntm, nvr, nvt;       // session tiles, catalog ranges, catalog tiles
   int estages;
   float scale;
@@ -53,11 +65,15 @@ struct FceParams {
   float* zlab;             // fwd: [B] label logit
   const float* lse;        // bwd: [B]
   const float* gout;       // bwd: upstream gradient of the mean loss (device scalar) or null
+  float* dEpart;           // bwd: [ntm][V][d] partial table gradients, one per session tile
   uint32_t idesc_z, idesc_ds, idesc_de;
-  long long* trace;        // debug: clock64 stamps of CTA 0, [role 0..2][tile < 64][8] (srk_flash_ce_set_trace), else null
+  int a_tmem;              // fwd: the session operand (A of the logit product) lives in TMEM instead of shared memory
+  const uint16_t *Shi, *Slo;   // fwd, a_tmem: bf16 hi / lo of shat in global memory, row pitch lds
+  long long lds;
+  long long* trace;        // debug: clock64 stamps of CTA 0, [role 0..10][tile < 64][8] (srk_flash_ce_set_trace), else null
 };
 
-// role: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue (warp 2 lane 0)
+// role: 0 = TMA producer, 1 = MMA issuer, 2 + w = epilogue warp w (lane 0)
 __device__ __forceinline__ void tr(const FceParams& p, int role, int it, int k) {
   if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[(role * 64 + it) * 8 + k] = clock64();
 }
@@ -71,6 +87,8 @@ constexpr uint64_t MDESC_HI = (uint64_t(CHUNK >> 4) << 16) | (uint64_t(1024 >> 4
 __device__ __forceinline__ uint64_t kdesc(uint32_t addr) { return KDESC_HI | (uint64_t)((addr >> 4) & 0x3FFFu); }
 __device__ __forceinline__ uint64_t mdesc(uint32_t addr) { return MDESC_HI | (uint64_t)((addr >> 4) & 0x3FFFu); }
 
+__device__ __forceinline__ uint64_t odesc(uint64_t hi, uint32_t addr) { return hi | (uint64_t)((addr >> 4) & 0x3FFFu); }
+
 // acc (+)= A B with both operands split hi/lo: hi*hi + hi*lo + lo*hi
 __device__ __forceinline__ void mma3(uint32_t tacc, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
                                      uint32_t accum) {
@@ -79,14 +97,32 @@ __device__ __forceinline__ void mma3(uint32_t tacc, uint64_t ah, uint64_t al, ui
   umma_bf16(tacc, al, bh, idesc, 1u);
 }
 
-// logit tile: Z[128 b x 128 v] = S E^T, K = d in steps of 16 (32 bytes inside the 128-byte swizzle row)
-__device__ __forceinline__ void issue_logits(uint32_t tz, uint32_t S, uint32_t E, uint32_t op_bytes, int d, uint32_t idesc) {
-  const int nks = d >> 4;
-  const uint64_t sh = kdesc(S), sl = kdesc(S + op_bytes), eh = kdesc(E), el = kdesc(E + op_bytes);
+// logit tile: Z[128 b x 128 v] = S E^T, K = d in steps of 16 (32 bytes inside the swizzled chunk row)
+__device__ __forceinline__ void issue_logits(uint32_t tz, uint32_t S, uint32_t E, uint32_t op_bytes, const FceParams& p) {
+  const int nks = p.d >> 4;
+  const uint64_t sh = odesc(p.okd_hi, S), sl = odesc(p.okd_hi, S + op_bytes), eh = odesc(p.okd_hi, E), el = odesc(p.okd_hi, E + op_bytes);
+  const int kmask = (1 << p.kpc_log2) - 1;
 #pragma unroll 1
   for (int ks = 0; ks < nks; ++ks) {
-    const uint64_t off = (uint64_t)(((uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32) >> 4);
-    mma3(tz, sh + off, sl + off, eh + off, el + off, idesc, ks ? 1u : 0u);
+    const uint64_t off = (uint64_t)(((uint32_t)(ks >> p.kpc_log2) * p.chunk_bytes + (uint32_t)(ks & kmask) * 32) >> 4);
+    mma3(tz, sh + off, sl + off, eh + off, el + off, p.idesc_z, ks ? 1u : 0u);
+  }
+}
+
+// same product with the A operand (shat hi / lo, K-major bf16 pairs) resident in TMEM: the tensor core then reads only the
+// catalog tile from shared memory - with both operands in shared memory the three products per K step run at the
+// 128 B/clk shared-memory limit, not at the tensor-pipe rate
+__device__ __forceinline__ void issue_logits_ts(uint32_t tz, uint32_t ta, uint32_t E, uint32_t op_bytes, const FceParams& p) {
+  const int nks = p.d >> 4;
+  const uint64_t eh = odesc(p.okd_hi, E), el = odesc(p.okd_hi, E + op_bytes);
+  const int kmask = (1 << p.kpc_log2) - 1;
+#pragma unroll 1
+  for (int ks = 0; ks < nks; ++ks) {
+    const uint64_t off = (uint64_t)(((uint32_t)(ks >> p.kpc_log2) * p.chunk_bytes + (uint32_t)(ks & kmask) * 32) >> 4);
+    const uint32_t ah = ta + (uint32_t)ks * 8, al = ah + 64;
+    umma_bf16_ts(tz, ah, eh + off, p.idesc_z, ks ? 1u : 0u);
+    umma_bf16_ts(tz, ah, el + off, p.idesc_z, 1u);
+    umma_bf16_ts(tz, al, eh + off, p.idesc_z, 1u);
   }
 }
 
@@ -118,10 +154,10 @@ struct TileSched {
 };
 
 __device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* hi, const CUtensorMap* lo, uint64_t* bar,
-                                             int nch, uint32_t op_bytes, int row0) {
+                                             int nch, uint32_t chunk_bytes, int cw, uint32_t op_bytes, int row0) {
   for (int c = 0; c < nch; ++c) {
-    tma_load_2d(dst + c * CHUNK, hi, bar, c * 64, row0);
-    tma_load_2d(dst + op_bytes + c * CHUNK, lo, bar, c * 64, row0);
+    tma_load_2d(dst + c * chunk_bytes, hi, bar, c * cw, row0);
+    tma_load_2d(dst + op_bytes + c * chunk_bytes, lo, bar, c * cw, row0);
   }
 }
 
@@ -134,13 +170,14 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t op_bytes = (uint32_t)p.nch * CHUNK;
+  const uint32_t op_bytes = (uint32_t)p.nch * p.chunk_bytes;
+  const bool ats = p.a_tmem != 0;
   uint8_t* S = smem;
-  uint8_t* E0 = smem + 2 * op_bytes;
+  uint8_t* E0 = smem + (ats ? 0 : 2 * op_bytes);
   const TileSched ts(p);
 
   if (threadIdx.x == 0) {
-    mbar_init(&s_full, 1);
+    mbar_init(&s_full, ats ? EPI_WARPS : 1);
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&e_full[s], 1);
       mbar_init(&e_empty[s], 1);
@@ -163,21 +200,24 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&s_full, 2 * op_bytes);
-      load_operand(S, &mSh, &mSl, &s_full, p.nch, op_bytes, ts.tb * TB);
+      if (!ats) {
+        mbar_expect_tx(&s_full, 2 * op_bytes);
+        load_operand(S, &mSh, &mSl, &s_full, p.nch, p.chunk_bytes, p.cw, op_bytes, ts.tb * TB);
+      }
       int it = 0;
       for (int t = ts.t0; t < ts.t1; ++t, ++it) {
         const int s = it % p.estages;
         mbar_wait(&e_empty[s], ((uint32_t)(it / p.estages) & 1u) ^ 1u);
         tr(p, 0, it, 0);
         mbar_expect_tx(&e_full[s], 2 * op_bytes);
-        load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, op_bytes, t * TV);
+        load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, p.chunk_bytes, p.cw, op_bytes, t * TV);
         tr(p, 0, it, 1);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       mbar_wait(&s_full, 0);
+      fence_tc_after();
       int it = 0;
       for (int t = ts.t0; t < ts.t1; ++t, ++it) {
         const int s = it % p.estages, zb = it & 1;
@@ -186,8 +226,8 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tr(p, 1, it, 1);
         fence_tc_after();
-        issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, smem_u32(S), smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p.d,
-                     p.idesc_z);
+        if (ats) issue_logits_ts(tmem_base + TM_Z + (uint32_t)zb * TV, tmem_base + TM_SA, smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p);
+        else issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, smem_u32(S), smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p);
         umma_commit(&e_empty[s]);
         umma_commit(&z_full[zb]);
         tr(p, 1, it, 2);
@@ -202,6 +242,24 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
     const int lab = b < p.B ? p.labels[b] : -1;
     const float c2 = p.scale * LOG2E;
     const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+    if (ats) {
+      // this thread's row of shat (hi for the warps of column half 0, lo for half 1) -> TMEM, 8 packed bf16 pairs at a time
+      const uint16_t* src = (half == 0 ? p.Shi : p.Slo) + (long long)b * p.lds;
+      const uint32_t dst = tmem_base + lanebits + TM_SA + (uint32_t)half * 64;
+      for (int w = 0; w < (p.d >> 1); w += 8) {
+        uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
+        if (b < p.B) {
+          x0 = *reinterpret_cast<const uint4*>(src + 2 * w);
+          x1 = *reinterpret_cast<const uint4*>(src + 2 * w + 8);
+        }
+        const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        tmem_st8(dst + (uint32_t)w, v);
+      }
+      tmem_wait_st();
+      fence_tc_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full);
+    }
     float m2 = -3.0e38f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, zl = 0.f;
     bool has = false;
     int it = 0;
@@ -330,25 +388,28 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const float4* __restrict
 }
 
 // ---- backward ---------------------------------------------------------------------------------------------------------
-// 32 consecutive dZ values of tile row r (columns c0 .. c0 + 31) -> bf16 hi/lo, 128-byte-swizzled rows of the D tile.
-// hi = the upper 16 bits of the fp32 value (truncation: one PRMT packs two of them), lo = bf16_rn(x - hi) (x - hi is exact).
-__device__ __forceinline__ void store_dz(uint8_t* Dhi, uint8_t* Dlo, int r, int c0, const float* dz) {
+// 32 consecutive dZ values -> 16 + 16 packed bf16 pairs.  hi = the upper 16 bits of the fp32 value (truncation: one PRMT
+// packs two of them), lo = bf16_rn(x - hi) (x - hi is exact).
+__device__ __forceinline__ void pack_dz(const float* dz, uint32_t* h, uint32_t* l) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t x0 = __float_as_uint(dz[2 * k]), x1 = __float_as_uint(dz[2 * k + 1]);
+    h[k] = __byte_perm(x0, x1, 0x7632);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(dz[2 * k] - __uint_as_float(x0 & 0xFFFF0000u),
+                                                    dz[2 * k + 1] - __uint_as_float(x1 & 0xFFFF0000u));
+    l[k] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+}
+
+// packed dZ of tile row r, columns c0 .. c0 + 31 -> the 128-byte-swizzled rows of the D tile (hi and lo halves)
+__device__ __forceinline__ void store_dz(uint8_t* Dhi, uint8_t* Dlo, int r, int c0, const uint32_t* h, const uint32_t* l) {
   const uint32_t base = (uint32_t)(c0 >> 6) * CHUNK + (uint32_t)r * 128;
   const uint32_t u0 = (uint32_t)(c0 & 63) >> 3;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t x0 = __float_as_uint(dz[8 * j + 2 * k]), x1 = __float_as_uint(dz[8 * j + 2 * k + 1]);
-      h[k] = __byte_perm(x0, x1, 0x7632);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(dz[8 * j + 2 * k] - __uint_as_float(x0 & 0xFFFF0000u),
-                                                      dz[8 * j + 2 * k + 1] - __uint_as_float(x1 & 0xFFFF0000u));
-      l[k] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
     const uint32_t pu = ((u0 + j) ^ ((uint32_t)r & 7u)) * 16;
-    *reinterpret_cast<uint4*>(Dhi + base + pu) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(Dlo + base + pu) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(Dhi + base + pu) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    *reinterpret_cast<uint4*>(Dlo + base + pu) = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
   }
 }
 
@@ -374,19 +435,20 @@ __device__ __forceinline__ void stage_row(uint8_t* chunk, int r, const uint32_t*
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_BWD, 1)
 fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
                const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl,
                const __grid_constant__ CUtensorMap mdE, const __grid_constant__ CUtensorMap mdS, const FceParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full, e_full[MAX_STAGES], e_empty[MAX_STAGES], z_full[2], z_empty[2], d_full, d_empty;
+  __shared__ __align__(8) uint64_t s_full, e_full[MAX_STAGES], e_empty[MAX_STAGES], z_full[2], z_empty[2], d_full, d_empty, de_free;
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t op_bytes = (uint32_t)p.nch * CHUNK;
+  const uint32_t op_bytes = (uint32_t)p.nch * p.chunk_bytes;
   uint8_t* S = smem;
-  uint8_t* Dt = smem + 2 * op_bytes;                // dZ hi (2 chunks) | dZ lo (2 chunks); also the fp32 staging area
+  uint8_t* Dt = smem + 2 * op_bytes;                // dZ hi (2 chunks) | dZ lo (2 chunks); fp32 staging of the final dS drain
   uint8_t* E0 = Dt + D_BYTES;
+  uint8_t* Stg = E0 + (size_t)p.estages * 2 * op_bytes;     // one 128-row x 32-column fp32 chunk: staging of the dE stores
   const TileSched ts(p);
   const int ntiles = ts.t1 - ts.t0;
 
@@ -402,6 +464,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
     }
     mbar_init(&d_full, EPI_WARPS);
     mbar_init(&d_empty, 1);
+    mbar_init(&de_free, DRAIN_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -417,13 +480,13 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(&s_full, 2 * op_bytes);
-      load_operand(S, &mSh, &mSl, &s_full, p.nch, op_bytes, ts.tb * TB);
+      load_operand(S, &mSh, &mSl, &s_full, p.nch, p.chunk_bytes, p.cw, op_bytes, ts.tb * TB);
       for (int it = 0; it < ntiles; ++it) {
         const int s = it % p.estages;
         mbar_wait(&e_empty[s], ((uint32_t)(it / p.estages) & 1u) ^ 1u);
         tr(p, 0, it, 0);
         mbar_expect_tx(&e_full[s], 2 * op_bytes);
-        load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, op_bytes, (ts.t0 + it) * TV);
+        load_operand(E0 + (size_t)s * 2 * op_bytes, &mEh, &mEl, &e_full[s], p.nch, p.chunk_bytes, p.cw, op_bytes, (ts.t0 + it) * TV);
         tr(p, 0, it, 1);
       }
     }
@@ -437,7 +500,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         tr(p, 1, it, 0);
         mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_tc_after();
-        issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, Sa, smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p.d, p.idesc_z);
+        issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, Sa, smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p);
         umma_commit(&z_full[zb]);
         tr(p, 1, it, 1);
       };
@@ -453,22 +516,29 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         fence_tc_after();
         // dS[128 b x d] += dZ[128 b x 128 v] E[128 v x d]: A = D K-major, B = E MN-major, K = v in steps of 16 rows
         {
-          const uint64_t ah = kdesc(Da), al = kdesc(Da + 2 * CHUNK), bh = mdesc(Ea), bl = mdesc(Ea + op_bytes);
+          const uint64_t ah = kdesc(Da), al = kdesc(Da + 2 * CHUNK), bh = odesc(p.omd_hi, Ea), bl = odesc(p.omd_hi, Ea + op_bytes);
+          const uint32_t kstep = 16 * p.row_bytes;          // 16 operand rows per UMMA K
 #pragma unroll
           for (int ks = 0; ks < TV / 16; ++ks) {
             const uint64_t aoff = (uint64_t)(((uint32_t)(ks >> 2) * CHUNK + (uint32_t)(ks & 3) * 32) >> 4);
-            const uint64_t boff = (uint64_t)((uint32_t)ks * 2048 >> 4);
+            const uint64_t boff = (uint64_t)((uint32_t)ks * kstep >> 4);
             mma3(tds, ah + aoff, al + aoff, bh + boff, bl + boff, p.idesc_ds, (it | ks) ? 1u : 0u);
           }
         }
         umma_commit(&e_empty[s]);
+        // the drain warps have read the previous tile's dE accumulator out of TMEM
+        if (it > 0) {
+          mbar_wait(&de_free, (uint32_t)(it - 1) & 1u);
+          fence_tc_after();
+        }
         // dE[128 v x d] = dZ^T[128 v x 128 b] S[128 b x d]: A = D MN-major, B = S MN-major, K = b in steps of 16 rows
         {
-          const uint64_t ah = mdesc(Da), al = mdesc(Da + 2 * CHUNK), bh = mdesc(Sa), bl = mdesc(Sa + op_bytes);
+          const uint64_t ah = mdesc(Da), al = mdesc(Da + 2 * CHUNK), bh = odesc(p.omd_hi, Sa), bl = odesc(p.omd_hi, Sa + op_bytes);
+          const uint32_t kstep = 16 * p.row_bytes;
 #pragma unroll
           for (int ks = 0; ks < TB / 16; ++ks) {
-            const uint64_t off = (uint64_t)((uint32_t)ks * 2048 >> 4);
-            mma3(tde, ah + off, al + off, bh + off, bl + off, p.idesc_de, ks ? 1u : 0u);
+            const uint64_t aoff = (uint64_t)((uint32_t)ks * 2048 >> 4), boff = (uint64_t)((uint32_t)ks * kstep >> 4);
+            mma3(tde, ah + aoff, al + aoff, bh + boff, bl + boff, p.idesc_de, ks ? 1u : 0u);
           }
         }
         umma_commit(&d_empty);
@@ -476,13 +546,14 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         if (p.estages == 1 && it + 1 < ntiles) logits(it + 1);
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS) {
+    // ===== math warps (2..9): logit tile -> dZ = coef * (softmax - onehot) -> bf16 hi/lo pairs -> D tile =====
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                     // row of the tile owned by this thread (= TMEM lane)
     const int b = ts.tb * TB + r;
     const bool bvalid = b < p.B;
     const int lab = bvalid ? p.labels[b] : -1;
-    // dZ = coef * (softmax - onehot) with softmax = 2^(acc * c2 - lse2); rows beyond B get coef = 0
+    // softmax = 2^(acc * c2 - lse2); rows beyond B get coef = 0
     const float c2 = p.scale * LOG2E;
     // lse * log2(e) is kept as hi + lo (lo = the rounding residual of the product): a 1e-6 relative error of lse2 would
     // be a systematic 1e-5 relative error of every soft-max value of the row; 2^-lo is folded into the row's coefficient
@@ -491,19 +562,16 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
     const float coef = bvalid ? p.scale * (p.gout ? p.gout[0] : 1.f) / (float)p.B : 0.f;
     const float coef_p = coef * ex2f(-fmaf(lse_b, LOG2E, -lse2));
     const uint32_t lanebits = (uint32_t)(q * 32) << 16;
-    const int nc32 = (p.d + 31) >> 5;                // 32-column fp32 chunks of the dS / dE accumulators
-    const bool elected = (warp == 2 && lane == 0);
     uint8_t* Dhi = Dt;
     uint8_t* Dlo = Dt + 2 * CHUNK;
     for (int it = 0; it < ntiles; ++it) {
       const int t = ts.t0 + it, zb = it & 1;
       mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
-      if (elected) tr(p, 2, it, 0);
+      if (lane == 0) tr(p, warp, it, 0);
       fence_tc_after();
-      // the previous tile's TMA stores must have finished reading the staging area (= the D tile) before it is rewritten
-      if (elected) tma_wait_group_read0();
-      named_bar_sync(1, EPI_THREADS);
-      if (elected) tr(p, 2, it, 1);
+      // dZ of this thread's 64 columns, packed to bf16 hi/lo pairs and HELD IN REGISTERS: the D tile in shared memory is
+      // still being read by the previous tile's gradient products while this runs
+      uint32_t hw[32], lw[32];
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c0 = half * 64 + cc * 32;
@@ -518,51 +586,82 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
           for (int j = 0; j < 32; ++j)
             if (v0 + j >= p.V) dz[j] = 0.f;
         }
-        store_dz(Dhi, Dlo, r, c0, dz);
+        pack_dz(dz, hw + 16 * cc, lw + 16 * cc);
+      }
+      fence_tc_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&z_empty[zb]);
+      if (lane == 0) tr(p, warp, it, 1);
+      // previous tile's gradient products complete: the D tile is free
+      if (it > 0) mbar_wait(&d_empty, (uint32_t)(it - 1) & 1u);
+      if (lane == 0) tr(p, warp, it, 2);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        store_dz(Dhi, Dlo, r, c0, hw + 16 * cc, lw + 16 * cc);
+        const int v0 = t * TV + c0;
         if (lab >= v0 && lab < v0 + 32) fix_dz(Dhi, Dlo, r, lab - t * TV, coef);
       }
-      fence_tc_before();
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&z_empty[zb]);
-        mbar_arrive(&d_full);
-      }
-      if (elected) tr(p, 2, it, 2);
-      // both gradient products of this tile are complete: drain the dE accumulator (rows = catalog rows of the tile)
-      mbar_wait(&d_empty, (uint32_t)it & 1u);
-      if (elected) tr(p, 2, it, 3);
-      fence_tc_after();
-      for (int cc = half; cc < nc32; cc += 2) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + lanebits + TM_DE + (uint32_t)(cc * 32), acc);
-        stage_row(Dt + (uint32_t)cc * CHUNK, r, acc);
-      }
-      fence_tc_before();
+      if (lane == 0) mbar_arrive(&d_full);
+      if (lane == 0) tr(p, warp, it, 3);
+    }
+  } else {
+    // ===== drain warps (10..13, TMEM lane quadrant = warp % 4): accumulators -> registers -> 32-column chunks through
+    // ONE 16 KB swizzled staging buffer -> TMA tensor store (dE partial of this session tile) / TMA reduce-add (dS).
+    // Scattered per-lane global stores would occupy the load/store unit for ~2000 cycles per tile and delay every
+    // mbarrier / shared-memory operation of the CTA (measured); the bulk-copy engine reads shared memory on its own. =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+    const int nc32 = (p.d + 31) >> 5;                // 32-column fp32 chunks of the dS / dE accumulators (<= 4)
+    const bool elected = (warp == 2 + EPI_WARPS && lane == 0);
+    // stage one chunk and hand it to the bulk-copy engine
+    auto put_chunk = [&](const uint32_t* v, int cc, int row0, bool reduce) {
+      if (elected) tma_wait_group_read0();         // the previous chunk's store has read the staging buffer
+      named_bar_sync(2, DRAIN_THREADS);
+      stage_row(Stg, r, v);
       fence_async_smem();
-      named_bar_sync(1, EPI_THREADS);
+      named_bar_sync(2, DRAIN_THREADS);
       if (elected) {
-        for (int cc = 0; cc < nc32; ++cc) tma_store_3d(&mdE, Dt + (uint32_t)cc * CHUNK, cc * 32, t * TV, ts.tb);
+        if (reduce) tma_reduce_add_2d(&mdS, Stg, cc * 32, row0);
+        else tma_store_3d(&mdE, Stg, cc * 32, row0, ts.tb);
         tma_commit_group();
-        tr(p, 2, it, 4);
       }
+    };
+    auto drain = [&](uint32_t tcol, int row0, bool reduce, bool release) {
+      uint32_t a0[32], a1[32], a2[32];
+      tmem_ld32(tmem_base + lanebits + tcol, a0);
+      if (nc32 > 1) tmem_ld32(tmem_base + lanebits + tcol + 32, a1);
+      if (nc32 > 2) tmem_ld32(tmem_base + lanebits + tcol + 64, a2);
+      if (release && nc32 <= 3) {                  // accumulator is in registers: the next dE product may overwrite it
+        fence_tc_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&de_free);
+      }
+      put_chunk(a0, 0, row0, reduce);
+      if (nc32 > 1) put_chunk(a1, 1, row0, reduce);
+      if (nc32 > 2) put_chunk(a2, 2, row0, reduce);
+      if (nc32 > 3) {
+        tmem_ld32(tmem_base + lanebits + tcol + 96, a0);
+        if (release) {
+          fence_tc_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&de_free);
+        }
+        put_chunk(a0, 3, row0, reduce);
+      }
+    };
+    for (int it = 0; it < ntiles; ++it) {
+      mbar_wait(&d_empty, (uint32_t)it & 1u);      // both gradient products of tile `it` are complete
+      fence_tc_after();
+      if (lane == 0) tr(p, 2 + EPI_WARPS, it, warp - 2 - EPI_WARPS);
+      drain(TM_DE, (ts.t0 + it) * TV, false, true);
     }
-    // dS accumulator of this CTA's catalog range -> reduce-add into dS[B, d]
-    if (elected) tma_wait_group_read0();
-    named_bar_sync(1, EPI_THREADS);
-    for (int cc = half; cc < nc32; cc += 2) {
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + lanebits + TM_DS + (uint32_t)(cc * 32), acc);
-      stage_row(Dt + (uint32_t)cc * CHUNK, r, acc);
-    }
-    fence_tc_before();
-    fence_async_smem();
-    named_bar_sync(1, EPI_THREADS);
-    if (elected) {
-      for (int cc = 0; cc < nc32; ++cc) tma_reduce_add_2d(&mdS, Dt + (uint32_t)cc * CHUNK, cc * 32, ts.tb * TB);
-      tma_commit_group();
-      tma_wait_group0();
-    }
+    // dS accumulator of this CTA's whole catalog range -> reduce-add into dS[B, d]
+    drain(TM_DS, ts.tb * TB, true, false);
+    if (elected) tma_wait_group0();
   }
   fence_tc_before();
   __syncthreads();
@@ -588,11 +687,11 @@ __global__ void split_bf16_kernel(const float* __restrict__ X, long long ldx, in
 
 long long* g_trace = nullptr;
 
-int bf16_map(CUtensorMap* m, const uint16_t* base, int d, int rows, long long ld) {
+int bf16_map(CUtensorMap* m, const uint16_t* base, int d, int rows, long long ld, int cw) {
   SRK_REQUIRE(ld % 8 == 0, "flash_ce: bf16 operand pitch must be a multiple of 8 elements");
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {(cuuint32_t)cw, 128};
   // operand rows are 2 * d bytes apart and every 128-byte box row is consumed whole: L2 promotion beyond the box row only
   // multiplies the L2 -> SM sector traffic (measured: 3x with L2_256B at d = 96).  SESSREC_FCE_L2PROMO = 0..3 overrides.
   static int promo = -1;
@@ -603,14 +702,37 @@ int bf16_map(CUtensorMap* m, const uint16_t* base, int d, int rows, long long ld
   }
   const CUtensorMapL2promotion pm[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
-  return make_map_nd(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, pm[promo]);
+  return make_map_nd(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, pm[promo],
+                     cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int fill_params(FceParams& p, int B, int V, int d, float scale, const int* labels, bool bwd) {
+  static int use_ts = -1;
+  if (use_ts < 0) {
+    const char* e = getenv("SESSREC_FCE_TS");
+    use_ts = !(e && e[0] == '0');
+  }
   SRK_REQUIRE(d >= 16 && d <= 128 && d % 16 == 0, "flash_ce: d = %d unsupported (multiple of 16 in [16, 128])", d);
   memset(&p, 0, sizeof(p));
   p.B = B; p.V = V; p.d = d;
-  p.nch = (d + 63) / 64;
+  // chunk geometry: 32-column chunks (SWIZZLE_64B) when that shrinks the operand tiles, else 64 (SWIZZLE_128B);
+  // SESSREC_FCE_CW = 32 / 64 forces one
+  static int force_cw = -1;
+  if (force_cw < 0) {
+    const char* e = getenv("SESSREC_FCE_CW");
+    force_cw = e ? atoi(e) : 0;
+  }
+  p.cw = (force_cw == 32 || force_cw == 64) ? force_cw : ((d % 64 != 0 && d % 32 == 0) ? 32 : 64);
+  p.row_bytes = (uint32_t)p.cw * 2;
+  p.chunk_bytes = 128 * p.row_bytes;
+  p.kpc_log2 = p.cw == 64 ? 2 : 1;
+  p.nch = (d + p.cw - 1) / p.cw;
+  {
+    const uint64_t type = p.cw == 64 ? 2ull : 4ull;          // SWIZZLE_128B : SWIZZLE_64B
+    const uint64_t sbo = 8ull * p.row_bytes;                 // 8-row swizzle atom
+    p.okd_hi = (uint64_t(16 >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (type << 61);
+    p.omd_hi = (uint64_t(p.chunk_bytes >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (type << 61);
+  }
   p.ntm = srk_cdiv(B, TB);
   p.nvt = srk_cdiv(V, TV);
   static int sms = 0;
@@ -623,8 +745,9 @@ int fill_params(FceParams& p, int B, int V, int d, float scale, const int* label
   if (nvr < 1) nvr = 1;
   if (nvr > p.nvt) nvr = p.nvt;
   p.nvr = nvr;
-  const size_t op = (size_t)p.nch * CHUNK;
-  const size_t fixed = 2 * op + (bwd ? D_BYTES : 0);
+  p.a_tmem = (!bwd && use_ts) ? 1 : 0;
+  const size_t op = (size_t)p.nch * p.chunk_bytes;
+  const size_t fixed = (p.a_tmem ? 0 : 2 * op) + (bwd ? D_BYTES + CHUNK : 0);
   int st = (int)((FCE_MAX_SMEM - 1024 - fixed) / (2 * op));
   if (st > (bwd ? 3 : MAX_STAGES)) st = bwd ? 3 : MAX_STAGES;
   SRK_REQUIRE(st >= 1, "flash_ce: shared-memory budget exceeded");
@@ -642,8 +765,8 @@ int fill_params(FceParams& p, int B, int V, int d, float scale, const int* label
 }
 
 size_t smem_bytes(const FceParams& p, bool bwd) {
-  const size_t op = (size_t)p.nch * CHUNK;
-  return 2 * op + (bwd ? D_BYTES : 0) + (size_t)p.estages * 2 * op + 1024;
+  const size_t op = (size_t)p.nch * p.chunk_bytes;
+  return (p.a_tmem ? 0 : 2 * op) + (bwd ? D_BYTES + CHUNK : 0) + (size_t)p.estages * 2 * op + 1024;
 }
 
 }  // namespace
@@ -675,11 +798,14 @@ extern "C" int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const 
   SRK_TRY(fill_params(p, B, V, d, scale, labels, false));
   p.part = part;
   p.zlab = part + 4LL * p.nvr * B;
+  p.Shi = Shi; p.Slo = Slo; p.lds = lds;
+  SRK_REQUIRE(!p.a_tmem || ((reinterpret_cast<uintptr_t>(Shi) | reinterpret_cast<uintptr_t>(Slo)) & 15u) == 0,
+              "flash_ce_fwd: shat operands must be 16-byte aligned");
   CUtensorMap mSh, mSl, mEh, mEl;
-  SRK_TRY(bf16_map(&mSh, Shi, d, B, lds));
-  SRK_TRY(bf16_map(&mSl, Slo, d, B, lds));
-  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde));
-  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde));
+  SRK_TRY(bf16_map(&mSh, Shi, d, B, lds, p.cw));
+  SRK_TRY(bf16_map(&mSl, Slo, d, B, lds, p.cw));
+  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde, p.cw));
+  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde, p.cw));
   static bool attr_set = false;
   if (!attr_set) {
     SRK_CUDA(cudaFuncSetAttribute(fce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
@@ -704,17 +830,18 @@ extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const 
   SRK_TRY(fill_params(p, B, V, d, scale, labels, true));
   p.lse = lse;
   p.gout = gout;
+  p.dEpart = dEpart;
   CUtensorMap mSh, mSl, mEh, mEl, mdE, mdS;
-  SRK_TRY(bf16_map(&mSh, Shi, d, B, lds));
-  SRK_TRY(bf16_map(&mSl, Slo, d, B, lds));
-  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde));
-  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde));
   {
     cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)V, (cuuint64_t)p.ntm};
     cuuint64_t strides[2] = {(cuuint64_t)d * 4, (cuuint64_t)V * d * 4};
     cuuint32_t box[3] = {32, 128, 1};
     SRK_TRY(make_map_nd(&mdE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dEpart, dims, strides, box));
   }
+  SRK_TRY(bf16_map(&mSh, Shi, d, B, lds, p.cw));
+  SRK_TRY(bf16_map(&mSl, Slo, d, B, lds, p.cw));
+  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde, p.cw));
+  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde, p.cw));
   {
     cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)B};
     cuuint64_t strides[1] = {(cuuint64_t)d * 4};
@@ -727,7 +854,7 @@ extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const 
     attr_set = true;
   }
   SRK_CUDA(cudaMemsetAsync(dS, 0, sizeof(float) * (size_t)B * d, st));
-  fce_bwd_kernel<<<p.ntm * p.nvr, THREADS, smem_bytes(p, true), st>>>(mSh, mSl, mEh, mEl, mdE, mdS, p);
+  fce_bwd_kernel<<<p.ntm * p.nvr, THREADS_BWD, smem_bytes(p, true), st>>>(mSh, mSl, mEh, mEl, mdE, mdS, p);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -745,7 +872,7 @@ extern "C" int srk_sum_parts(const float* parts, long long stride, int nparts, l
   return SRK_OK;
 }
 
-/* Debug aid: device buffer of 3 * 64 * 8 int64 that receives clock64() stamps of CTA 0's three roles (NULL = off). */
+/* Debug aid: device buffer of 11 * 64 * 8 int64 that receives clock64() stamps of CTA 0's three roles (NULL = off). */
 extern "C" int srk_flash_ce_set_trace(long long* trace_dev) {
   g_trace = trace_dev;
   return SRK_OK;

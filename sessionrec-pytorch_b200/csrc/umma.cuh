@@ -111,11 +111,12 @@ static __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lb
 }
 
 
-// Generic tiled tensor map (rank <= 3), SWIZZLE_128B, zero fill out of bounds.  dims / box in elements (innermost
+// Generic tiled tensor map (rank <= 3), SWIZZLE_128B unless told otherwise, zero fill out of bounds.  dims / box in elements (innermost
 // first), strides in bytes for dims 1.. (dim 0 is contiguous).
 static inline int make_map_nd(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
                               const cuuint64_t* strides_bytes, const cuuint32_t* box,
-                              CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
+                              CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   SRK_REQUIRE(enc != nullptr, "umma: cuTensorMapEncodeTiled is not available from this driver");
   SRK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "umma: tensor-map base must be 16-byte aligned");
@@ -123,7 +124,7 @@ static inline int make_map_nd(CUtensorMap* m, CUtensorMapDataType dt, int rank, 
     SRK_REQUIRE(strides_bytes[i] % 16 == 0, "umma: tensor-map strides must be multiples of 16 bytes");
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SRK_REQUIRE(r == CUDA_SUCCESS, "umma: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return SRK_OK;
 }
@@ -142,6 +143,24 @@ static __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] B[smem]: A = 128 lanes (rows) x K packed bf16 pairs per 32-bit column, K-major
+static __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// registers -> TMEM: lane i of the warp writes 8 consecutive 32-bit columns of TMEM lane (quadrant base + i)
+static __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+static __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 static __device__ __forceinline__ void fence_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 static __device__ __forceinline__ void fence_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand reads, TMA stores)
