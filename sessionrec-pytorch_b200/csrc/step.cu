@@ -56,13 +56,19 @@ struct StageTimer {
 // independent of each other, so they are enqueued on side streams (fork / join with events) and overlap on the 148 SMs.
 // SESSREC_STREAMS=0 keeps everything on the caller's stream.
 struct SideStreams {
-  static constexpr int NS = 4, NE = 32;
-  cudaStream_t s[NS];
+  static constexpr int NS = 7, NE = 64;
+  cudaStream_t s[NS];     // [0] critical path, [1..3] parallel encoder chains, [4] [5] weight gradients, [6] bulk catalog passes
   cudaEvent_t ev[NE];
   int next = 0;
   bool ok = false;
   int init() {
-    for (int i = 0; i < NS; ++i) SRK_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+    // The latency-bound encoder chain gets the highest priority: its few-CTA kernels must not queue behind the
+    // thousands of CTAs of the catalog-wide passes (row normalisation backward, zero_grad) that run beside it.
+    int least = 0, greatest = 0;
+    SRK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    const int mid = greatest + (least - greatest) / 2;
+    const int prio[NS] = {greatest, greatest, greatest, greatest, mid, mid, least};
+    for (int i = 0; i < NS; ++i) SRK_CUDA(cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, prio[i]));
     for (int i = 0; i < NE; ++i) SRK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     ok = true;
     return SRK_OK;
@@ -184,7 +190,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   // flash CE head: bf16 hi/lo of Ehat and shat, soft-max partials, one [V, d] dE partial per 128-session tile
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
-  fl += 3LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
+  fl += 8LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
   return fl * 5 + (1 << 20);                               // floats -> bytes with 25% head-room + alignment slack
 }
 
@@ -224,9 +230,17 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     return srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2,
                          eps, adam_step, grad_scale, st);
   }
-  StageTimer tm(st);
   SideStreams* ss = side_streams();
-  cudaStream_t s1 = ss ? ss->s[0] : st, s2 = ss ? ss->s[1] : st, s3 = ss ? ss->s[2] : st, s4 = ss ? ss->s[3] : st;
+  cudaStream_t caller = st;
+  if (ss) {                                      // the whole step runs on our own high-priority stream
+    SRK_TRY(ss->order(caller, ss->s[0]));
+    st = ss->s[0];
+  }
+  StageTimer tm(st);
+  // h1..h3: high-priority chains beside the critical path; s2 / s3: weight gradients; s4: catalog-wide bulk passes
+  cudaStream_t h1 = ss ? ss->s[1] : st, h2 = ss ? ss->s[2] : st, h3 = ss ? ss->s[3] : st;
+  cudaStream_t s2 = ss ? ss->s[4] : st, s3 = ss ? ss->s[5] : st, s4 = ss ? ss->s[6] : st;
+  cudaStream_t s1 = h1;
   auto order = [&](cudaStream_t from, cudaStream_t to) { return ss ? ss->order(from, to) : (int)SRK_OK; };
   // zero_grad runs beside the forward pass; the first gradient is written after the head's backward
   SRK_TRY(order(st, s4));
@@ -245,33 +259,57 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     Elo = ar.f((size_t)V * d);
   }
   SRK_REQUIRE(ar.ok, "step: workspace too small");
-  SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, Ebh, Ebl, st));
+  // nn.Embedding(max_norm=1) renorms the rows a lookup touches (msgifsr.py:247) and, at the scoring head, every row
+  // (msgifsr.py:276).  The gather only needs the touched rows: they are renormed first on the critical path; the
+  // catalog-wide pass (renorm of the remaining rows + normalisation + bf16 split) starts once the gather has read the
+  // table and runs beside the encoder.
+  if (ss) SRK_TRY(srk_renorm_rows(E, b.uid, b.U, d, 1.0f, st));
+  else SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, Ebh, Ebl, st));
   tm.mark("catalog_prep");
   float *X = ar.f((size_t)N * d), *rnX = ar.f(N);
   srk_dropout dc_e = dcfg(SRK_SITE_EMBED + 1);
   SRK_TRY(srk_embed_gather_fwd(E, b.iid, N, d, SRK_NORM_L2, drop ? &dc_e : nullptr, X, rnX, nullptr, st));
+  if (ss) {
+    SRK_TRY(order(st, s4));
+    SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, Ebh, Ebl, s4));
+  }
   srk_dropout dc_attn = dcfg(SRK_SITE_GAT_ATTN);
 
   tm.mark("gather");
   std::vector<LayerRec> layers(L);
-  const float* h = X;
+  // W_aug = [W ; a_l-contracted rows] and w_r depend on the parameters only: built beside the gather (s2)
   for (int l = 0; l < L; ++l) {
     LayerRec& R = layers[l];
-    R.in = h;
-    R.normalize = (l == L - 1);
     R.n_inst = M > 0 ? 2 : 0;
-    srk_gat_inst insts[2];
-    SRK_TRY(order(st, s1));                      // the layer input is ready on the main stream
-    SRK_TRY(order(st, s2));
     for (int c = 0; c < R.n_inst; ++c) {
-      cudaStream_t sc = c == 0 ? st : s1;        // conv1 (graph) on the main stream, conv2 (reversed graph) beside it
       InstRec& I = R.inst[c];
       const int base = 1 + 8 * l + 4 * c;        // attn_l, attn_r, bias, fc.weight
       I.al = P(base); I.ar = P(base + 1); I.W = P(base + 3);
       I.gal = G(base); I.gar = G(base + 1); I.gbias = G(base + 2); I.gW = G(base + 3);
       I.Waug = ar.f((size_t)ldzel * d);
       I.wr = ar.f((size_t)H * d);
-      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, sc));
+      SRK_REQUIRE(ar.ok, "step: workspace too small");
+      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, s2));
+    }
+  }
+  SRK_TRY(order(s2, st));
+  const float* h = X;
+  for (int l = 0; l < L; ++l) {
+    LayerRec& R = layers[l];
+    R.in = h;
+    R.normalize = (l == L - 1);
+    srk_gat_inst insts[2];
+    // the layer input is ready on the main stream: four projection chains (conv x {source, destination} copy) and the
+    // segment mean run side by side
+    SRK_TRY(order(st, h1));
+    SRK_TRY(order(st, h2));
+    SRK_TRY(order(st, h3));
+    SRK_TRY(order(st, s2));
+    for (int c = 0; c < R.n_inst; ++c) {
+      cudaStream_t zs = c == 0 ? st : h1;        // source copy: Z | el = x_s W_aug^T   (conv1 = graph, conv2 = reversed graph)
+      cudaStream_t es = c == 0 ? h2 : h3;        // destination copy: er = x_d w_r^T
+      InstRec& I = R.inst[c];
+      const int base = 1 + 8 * l + 4 * c;
       const uint32_t slot = (uint32_t)((l * 2 + c) * 3);
       I.drop = drop;
       I.xs = const_cast<float*>(h);
@@ -281,15 +319,16 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
         I.dcd = dcfg(SRK_SITE_GAT_DST + 4 * slot);
         I.xs = ar.f((size_t)N * d);
         I.xd = ar.f((size_t)N * d);
-        SRK_TRY(srk_dropout_apply(h, I.xs, (long long)N * d, &I.dcs, 0, sc));
-        SRK_TRY(srk_dropout_apply(h, I.xd, (long long)N * d, &I.dcd, 0, sc));
+        SRK_REQUIRE(ar.ok, "step: workspace too small");
+        SRK_TRY(srk_dropout_apply(h, I.xs, (long long)N * d, &I.dcs, 0, zs));
+        SRK_TRY(srk_dropout_apply(h, I.xd, (long long)N * d, &I.dcd, 0, es));
       }
       float* Zel = ar.f((size_t)N * ldzel);
       float* er = ar.f((size_t)N * H);
       float* att = ar.f((size_t)(M + 1) * H);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_TRY(linear_nt(sc, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
-      SRK_TRY(linear_nt(sc, N, H, d, I.xd, d, I.wr, er, H));
+      SRK_TRY(linear_nt(zs, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
+      SRK_TRY(linear_nt(es, N, H, d, I.xd, d, I.wr, er, H));
       srk_gat_inst& g = I.gi;
       memset(&g, 0, sizeof(g));
       if (c == 0) {
@@ -310,7 +349,9 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     R.amax = ar.raw((size_t)N * d);
     SRK_REQUIRE(ar.ok, "step: workspace too small");
     SRK_TRY(srk_segmean_fwd(h, b.seg, B, d, segmean, s2));
-    SRK_TRY(order(s1, st));
+    SRK_TRY(order(h1, st));
+    SRK_TRY(order(h2, st));
+    SRK_TRY(order(h3, st));
     SRK_TRY(order(s2, st));
     SRK_TRY(srk_gat_aggregate_fwd(insts, R.n_inst, N, d, segmean, b.node2seg, drop ? &dc_attn : nullptr, R.normalize, R.Hout,
                                   R.rn, R.amax, st));
@@ -329,7 +370,8 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
   SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
   tm.mark("readout_fwd");
-  // scoring head + CE
+  // scoring head + CE (needs the catalog pass)
+  SRK_TRY(order(s4, st));
   float *Z = flash ? nullptr : ar.f((size_t)B * ldz), *lse = ar.f(B), *nll = ar.f(B);
   float *sh = nullptr, *sl = nullptr;
   uint16_t *Sbh = nullptr, *Sbl = nullptr;
@@ -426,8 +468,11 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     float* bufA = ar.f((size_t)N * d);
     float* bufB = ar.f((size_t)N * d);
     dfeat = ((L - 1 - l) & 1) ? bufB : bufA;
-    float* dfeat1 = ar.f((size_t)N * d);        // conv2's share of d(layer input): summed into dfeat after the join
-    float* dHpre = ar.f((size_t)N * d);
+    // d(layer input) = segment-mean term + per conv {source-copy term, destination-copy + residual term}: every term
+    // is produced on its own stream into its own [N, d] slice and one pass adds them up
+    float* parts = ar.f(5 * (size_t)N * d);
+    const size_t nd = (size_t)N * d;
+    float* dHpre = ar.f(nd);
     srk_gat_inst insts[2];
     float *dedge[2], *der[2], *dZel[2];
     for (int c = 0; c < R.n_inst; ++c) {
@@ -440,16 +485,18 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     SRK_REQUIRE(ar.ok, "step: workspace too small");
     SRK_TRY(srk_gat_aggregate_bwd_dst(insts, R.n_inst, N, d, drop ? &dc_attn : nullptr, R.normalize, R.Hout, R.rn, R.amax, dH,
                                       dHpre, st));
-    SRK_TRY(order(st, s1));
-    SRK_TRY(srk_segmean_bwd(dHpre, b.seg, B, d, dfeat, 0, st));
+    SRK_TRY(order(st, h1));
+    SRK_TRY(order(st, h3));
+    SRK_TRY(srk_segmean_bwd(dHpre, b.seg, B, d, parts, 0, h3));
     for (int c = 0; c < R.n_inst; ++c) {
-      // conv c: data-gradient chain on dsc (conv1: main stream, conv2: s1), its weight gradients on wsc (s2 / s3)
-      cudaStream_t dsc = c == 0 ? st : s1, wsc = c == 0 ? s2 : s3;
-      float* dfc = c == 0 ? dfeat : dfeat1;
-      const int acc0 = c == 0 ? 1 : 0;           // dfeat already holds the segment-mean term; dfeat1 starts empty
+      cudaStream_t zs = c == 0 ? st : h1, es = c == 0 ? h2 : h3, wsc = c == 0 ? s2 : s3;
+      float* pz = parts + (1 + 2 * c) * nd;      // source-copy term
+      float* pe = parts + (2 + 2 * c) * nd;      // destination-copy term + identity residual
       InstRec& I = R.inst[c];
-      SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, dsc));
-      SRK_TRY(order(dsc, wsc));
+      SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, zs));
+      SRK_TRY(order(zs, es));
+      SRK_TRY(order(zs, wsc));
+      // weight gradients
       SRK_TRY(srk_gat_bias_bwd(dHpre, R.amax, N, d, I.gbias, wsc));
       float* dWaug = ar.f((size_t)ldzel * d);
       float* dwr = ar.f((size_t)H * d);
@@ -459,23 +506,26 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
       SRK_TRY(mm_tn(wsc, ldzel, d, N, dZel[c], ldzel, I.xs, d, dWaug, d));
       SRK_TRY(mm_tn(wsc, H, d, N, der[c], H, I.xd, d, dwr, d));
       SRK_TRY(srk_gat_prep_bwd(I.W, I.al, I.ar, dWaug, dwr, d, I.gW, I.gal, I.gar, wsc));
+      // data gradients
       if (!I.drop) {
-        SRK_TRY(mm_nn(dsc, N, d, ldzel, dZel[c], ldzel, I.Waug, d, dfc, d, acc0));
-        SRK_TRY(mm_nn(dsc, N, d, H, der[c], H, I.wr, d, dfc, d, 1));
-        SRK_TRY(srk_dropout_apply(dHpre, dfc, (long long)N * d, nullptr, 1, dsc));       // residual
+        SRK_TRY(mm_nn(zs, N, d, ldzel, dZel[c], ldzel, I.Waug, d, pz, d, 0));
+        SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, pe, d, 0));
+        SRK_TRY(srk_dropout_apply(dHpre, pe, (long long)nd, nullptr, 1, es));            // residual
       } else {
-        float* tmp = ar.f((size_t)N * d);
-        float* tmp2 = ar.f((size_t)N * d);
+        float* tmp = ar.f(nd);
+        float* tmp2 = ar.f(nd);
         SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(mm_nn(dsc, N, d, ldzel, dZel[c], ldzel, I.Waug, d, tmp, d, 0));
-        SRK_TRY(srk_dropout_apply(tmp, dfc, (long long)N * d, &I.dcs, acc0, dsc));
-        SRK_CUDA(cudaMemcpyAsync(tmp2, dHpre, sizeof(float) * (size_t)N * d, cudaMemcpyDeviceToDevice, dsc));
-        SRK_TRY(mm_nn(dsc, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
-        SRK_TRY(srk_dropout_apply(tmp2, dfc, (long long)N * d, &I.dcd, 1, dsc));
+        SRK_TRY(mm_nn(zs, N, d, ldzel, dZel[c], ldzel, I.Waug, d, tmp, d, 0));
+        SRK_TRY(srk_dropout_apply(tmp, pz, (long long)nd, &I.dcs, 0, zs));
+        SRK_CUDA(cudaMemcpyAsync(tmp2, dHpre, sizeof(float) * nd, cudaMemcpyDeviceToDevice, es));
+        SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
+        SRK_TRY(srk_dropout_apply(tmp2, pe, (long long)nd, &I.dcd, 0, es));
       }
     }
-    SRK_TRY(order(s1, st));
-    if (R.n_inst > 1) SRK_TRY(srk_dropout_apply(dfeat1, dfeat, (long long)N * d, nullptr, 1, st));
+    SRK_TRY(order(h1, st));
+    SRK_TRY(order(h2, st));
+    SRK_TRY(order(h3, st));
+    SRK_TRY(srk_sum_parts(parts, (long long)nd, 1 + 2 * R.n_inst, (long long)nd, dfeat, 0, st));
     if (l > 0) {                                 // the scratch region is re-carved by the next layer
       SRK_TRY(order(s2, st));
       SRK_TRY(order(s3, st));
@@ -494,6 +544,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
                           adam_step, grad_scale, st));
   }
   tm.mark("adam");
+  SRK_TRY(order(st, caller));
   tm.report();
   return SRK_OK;
 }
