@@ -298,7 +298,7 @@ def gather_scatter_probe(device, pk, shapes=None):
     return out
 
 
-def reference_arm(args, cfg, rank):
+def reference_arm(args, cfg, rank, guard):
     if rank != 0:
         return
     from sessionrec_pytorch_b200.synthetic import SessionSampler
@@ -306,14 +306,14 @@ def reference_arm(args, cfg, rank):
     sessions = [smp.sessions(cfg['B']) for _ in range(min(4, args.steps + args.warmup))]
     v, cores, secs = cpu_oracle_steps(cfg, sessions, args.steps, args.warmup)
     sample = f"{args.steps} full steps (B={cfg['B']}) of {args.workload}, {secs:.1f} s of CPU work"
-    print(json.dumps({
+    guard.emit({
         'impl': 'reference', 'metric': METRIC, 'value': round(v, 2), 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(1e3 * cfg['B'] / v, 3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': dict(workload=workload_name(args.workload, cfg), **{k: cfg[k] for k in ('V', 'd', 'B', 'order', 'layers', 'dropout')}),
         'cpu_baseline': dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port', sample=sample),
         'e2e': dict(value=round(v, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-        'note': 'reference CPU path = oracle port of src/models + TrainRunner loop body (DGL is not installable here)'}))
+        'note': 'reference CPU path = oracle port of src/models + TrainRunner loop body (DGL is not installable here)'})
 
 
 def workload_name(key, cfg):
@@ -322,7 +322,24 @@ def workload_name(key, cfg):
             f"V={cfg['V']} d={cfg['d']} B={cfg['B']}")
 
 
+class StdoutGuard:
+    """Library chatter on fd 1 (NCCL prints its version banner there) must not precede the ONE JSON line: everything
+    written to stdout while the guard is active goes to stderr; `emit` restores fd 1 and prints the line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
+
 def main():
+    guard = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)
@@ -342,7 +359,7 @@ def main():
     if args.impl == 'reference':
         if args.steps == 30 and args.warmup == 5:
             args.steps, args.warmup = 5, 1
-        reference_arm(args, cfg, rank)
+        reference_arm(args, cfg, rank, guard)
         return
     assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists for the product path)'
@@ -449,7 +466,7 @@ def main():
             v, cores, secs = cpu_oracle_steps(cfg, sessions, nst, 1)
             out['cpu_baseline'] = dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port',
                                        sample=f"{nst} full steps (B={cfg['B']}) of {args.workload} after 1 warm-up, {secs:.1f} s")
-        print(json.dumps(out))
+        guard.emit(out)
     if world > 1:
         dist.destroy_process_group()
 

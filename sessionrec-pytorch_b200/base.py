@@ -112,8 +112,8 @@ class SessRecModule(nn.Module):
         return True
 
     def _use_flash(self, d, mode):
-        return (self.use_tensor_cores and self.flash_ce and self._shard is None and mode == 'loss'
-                and self._single_head() and ops.flash_ce_supported(d))
+        return (self.use_tensor_cores and self.flash_ce and mode == 'loss' and self._single_head()
+                and ops.flash_ce_supported(d))
 
     def _catalog_fwd(self, E, norm_mode, max_norm, tape):
         """Catalog pre-pass: in-place max_norm renorm (MSGIFSR) + row normalisation of the rows this rank scores, with
@@ -162,10 +162,13 @@ class SessRecModule(nn.Module):
             lse = torch.empty(B, dtype=torch.float32, device=dev)
             nll = torch.empty(B, dtype=torch.float32, device=dev)
             part = torch.empty(ops.flash_ce_part_floats(B, V), dtype=torch.float32, device=dev)
+            tape.update(Shi=Shi, Slo=Slo, scale=scale, shat=shat, ld_s=ld_s)
+            if self._shard is not None:
+                return self._flash_fwd_sharded(B, V, d, scale, batch, lse, nll, part, tape)
             ops.flash_ce_fwd(B, V, d, Shi, Slo, d, cat['Bhi'], cat['Blo'], d, scale, batch.labels, lse, nll, part)
             out = torch.empty((), dtype=torch.float32, device=dev)
             ops.mean(nll, B, out)
-            tape.update(Shi=Shi, Slo=Slo, lse=lse, scale=scale, shat=shat, ld_s=ld_s, labels=batch.labels)
+            tape.update(lse=lse, labels=batch.labels)
             return out
         ldz = (V + 3) // 4 * 4                      # 16-byte aligned rows: TMA / vector loads in the backward GEMMs
         Z = torch.empty(B, ldz, dtype=torch.float32, device=dev)
@@ -210,6 +213,31 @@ class SessRecModule(nn.Module):
         ops.ce_rows_fwd(Z, ldz, None, B, V, True, lse, None)
         return Z[:, :V]
 
+    def _flash_fwd_sharded(self, B, V, d, scale, batch, lse_local, nll, part, tape):
+        """Catalog-sharded fused head: this rank's rows give a local log-sum-exp and, where it owns the label, the label
+        logit.  Cosine heads (|z| <= scale) exchange them in ONE [2, B] SUM all-reduce with a constant shift; unbounded
+        logits (SRGNN) need a MAX all-reduce first."""
+        import torch.distributed as dist
+        cat = tape['cat']
+        lo, hi = cat['lo'], cat['hi']
+        lab = batch.labels
+        own = (lab >= lo) & (lab < hi)
+        ll = torch.where(own, lab - lo, torch.full_like(lab, -1))          # label column inside this shard, else -1
+        ops.flash_ce_fwd(B, V, d, tape['Shi'], tape['Slo'], d, cat['Bhi'], cat['Blo'], d, scale, ll, lse_local, nll, part)
+        zlab = torch.where(own, lse_local - nll, torch.zeros_like(nll))    # nll = lse_local - label logit where owned
+        if cat['norm_mode'] != NORM_NONE:
+            pack = torch.stack([torch.exp(lse_local - scale), zlab])
+            dist.all_reduce(pack, group=self._shard)
+            lse = scale + torch.log(pack[0])
+        else:
+            m = lse_local.clone()
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self._shard)
+            pack = torch.stack([torch.exp(lse_local - m), zlab])
+            dist.all_reduce(pack, group=self._shard)
+            lse = m + torch.log(pack[0])
+        tape.update(lse=lse, labels=ll)
+        return (lse - pack[1]).mean()
+
     def _head_fwd_sharded(self, Z, ldz, lse_local, batch, mode, tape):
         import torch.distributed as dist
         if mode != 'loss':
@@ -240,7 +268,18 @@ class SessRecModule(nn.Module):
             dshat = torch.empty(B, d, dtype=torch.float32, device=Ehat.device)
             ops.flash_ce_bwd(B, V, d, tape['Shi'], tape['Slo'], d, cat['Bhi'], cat['Blo'], d, tape['scale'], tape['labels'],
                              tape['lse'], gout.reshape(1), dshat, dEpart)
-            if cat['norm_mode'] == NORM_NONE:            # SRGNN: the table itself is scored
+            if self._shard is not None:
+                import torch.distributed as dist
+                lo, hi = cat['lo'], cat['hi']
+                dist.all_reduce(dshat, group=self._shard)     # every rank needs the full d shat for the replicated encoder
+                ghead = torch.zeros_like(gE)
+                if cat['norm_mode'] == NORM_NONE:
+                    ops.sum_parts(dEpart, V * d, parts, V * d, ghead[lo:hi], accumulate=False)
+                else:
+                    ops.catalog_prep_bwd(E[lo:hi], Ehat, cat['enorm'], dEpart, cat['norm_mode'], ghead[lo:hi], nparts=parts)
+                dist.all_reduce(ghead, group=self._shard)
+                ops.dropout_apply(ghead, gE, ghead.numel(), None, accumulate=True)
+            elif cat['norm_mode'] == NORM_NONE:          # SRGNN: the table itself is scored
                 ops.sum_parts(dEpart, V * d, parts, V * d, gE, accumulate=True)
             else:
                 ops.catalog_prep_bwd(E, Ehat, cat['enorm'], dEpart, cat['norm_mode'], gE, nparts=parts)

@@ -235,7 +235,8 @@ class MSGIFSR(SessRecModule):
 
     # ---- native fused step (csrc/step.cu) ------------------------------------------------------------------------
     def _native_ok(self, batch):
-        return self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
+        return (self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
+                and self._shard is None)          # the catalog-sharded head is composed from the staged kernels
 
     def _slot_offsets(self):
         import numpy as np
