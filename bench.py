@@ -288,11 +288,17 @@ def gather_scatter_probe(device, pk, shapes=None):
         ms_s = timeit(lambda: ops.embed_scatter_bwd(E, t, d, 2, None, rn, X, None, dE))
         bg = N * (4 + 2 * 4 * d)
         bs = N * (4 + 4 * d) + 2 * t['U'] * 4 * d
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
+        # stress shape (profiles/*_ncu_full_gather_scatter.json); the L2-resident shape has no capture
+        caps = sorted((ROOT / 'profiles').glob('*_ncu_full_gather_scatter.json'))
+        cap = json.loads(caps[-1].read_text()) if caps and name.startswith('stress') else []
         for kname, ms, by in (('gather_fwd_kernel (K1: gather + L2 normalise)', ms_g, bg),
                               ('scatter_bwd_kernel (K8: normalise-backward + scatter-add)', ms_s, bs)):
             ach = by / (ms * 1e-3) / 1e9
+            tr = [round(r['dram_bytes_read'] + r['dram_bytes_write']) for r in cap if kname.split(' ')[0][:-7] in r['kernel']]
             out.append(dict(bound='hbm', kernel=kname, shape=name, achieved=round(ach, 1), peak=pk['hbm'], unit='GB/s',
-                            frac=round(ach / pk['hbm'], 4), ms=round(ms, 4), algorithmic_bytes=by, traffic=None))
+                            frac=round(ach / pk['hbm'], 4), ms=round(ms, 4), algorithmic_bytes=by,
+                            traffic=tr[0] if tr else None, traffic_source=f'profiles/{caps[-1].name}' if tr else None))
         del E, X, dE
         torch.cuda.empty_cache()
     return out
