@@ -287,6 +287,14 @@ int srk_segmean_bwd(const float* dHpre, const int* seg, int B, int d, float* dX,
 int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                   const long long* seg_off, const float* seg_decay, int n_seg, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, void* stream);
+/* The same update in two launches around one [rows, d] table that starts `tab` floats into the flat buffer and spans
+ * tab_span floats (rows * d + alignment padding).  part 0: the table rows NOT listed in rows_sorted[n_rows] (ascending);
+ * part 1: every other element (outside the table + the listed rows).  Both parts together update every element exactly
+ * once with the arithmetic of srk_adam_step; part 0 can run as soon as the gradient of the un-gathered rows is final. */
+int srk_adam_step_split(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                        const long long* seg_off, const float* seg_decay, int n_seg, long long tab, int rows, int d,
+                        long long tab_span, const int* rows_sorted, int n_rows, int part, float lr, float beta1,
+                        float beta2, float eps, int step, float grad_scale, void* stream);
 
 /* ---- native training step (MSGIFSR order 1, extra=False): utils/train.py:95-101 around msgifsr.py:241-323 ----
  * zero_grad + forward + nll_loss + backward (+ Adam) enqueued by ONE host call from a caller-provided device

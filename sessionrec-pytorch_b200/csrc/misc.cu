@@ -92,6 +92,18 @@ __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x,
   }
 }
 
+__device__ __forceinline__ void adam_update(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                            float* __restrict__ v, long long i, float decay, float lr, float b1, float b2,
+                                            float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  float grad = g[i] * grad_scale + decay * p[i];
+  float mi = b1 * m[i] + (1.f - b1) * grad;
+  float vi = b2 * v[i] + (1.f - b2) * grad * grad;
+  m[i] = mi;
+  v[i] = vi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - (lr / bc1) * (mi / denom);
+}
+
 // Fused multi-tensor Adam with torch.optim.Adam semantics (L2 term folded into the gradient, bias correction,
 // denom = sqrt(v) / sqrt(bias2) + eps) over one flat parameter buffer; per-segment weight decay.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -106,13 +118,82 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
       int mid = (lo + hi + 1) >> 1;
       if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    float grad = g[i] * grad_scale + seg_decay[lo] * p[i];
-    float mi = b1 * m[i] + (1.f - b1) * grad;
-    float vi = b2 * v[i] + (1.f - b2) * grad * grad;
-    m[i] = mi;
-    v[i] = vi;
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - (lr / bc1) * (mi / denom);
+    adam_update(p, g, m, v, i, seg_decay[lo], lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale);
+  }
+}
+
+__device__ __forceinline__ bool in_sorted(const int* __restrict__ a, int n, int x) {
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    int mid = (lo + hi) >> 1;
+    int y = a[mid];
+    if (y == x) return true;
+    if (y < x) lo = mid + 1; else hi = mid - 1;
+  }
+  return false;
+}
+
+// The same element-wise update split in two launches around one [rows, d] table that starts at element `tab`:
+//   part 0: the table rows NOT listed in rows_sorted[n_rows] (their gradient is final as soon as the catalog backward is,
+//           so this launch runs beside the encoder backward);
+//   part 1: everything else = the elements outside the table + the listed rows (the rows the batch gathered, whose
+//           gradient the scatter-add completes last).  Every element is updated exactly once, by the same arithmetic.
+__global__ void __launch_bounds__(256) adam_split_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v, long long n,
+                                                         const long long* __restrict__ seg_off,
+                                                         const float* __restrict__ seg_decay, int n_seg, long long tab,
+                                                         int rows, int d, long long tab_span,
+                                                         const int* __restrict__ rows_sorted, int n_rows, int part, float lr,
+                                                         float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                                                         float grad_scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (part == 0) {
+    // one float4 per thread and NO grid-stride loop: this launch runs beside latency-critical kernels on higher-priority
+    // streams, and the block scheduler can only hand an SM slot to them when one of these CTAs retires
+    int lo = 0, hi = n_seg - 1;           // the table is one segment
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (seg_off[mid] <= tab) lo = mid; else hi = mid - 1;
+    }
+    const float decay = seg_decay[lo];
+    const long long t4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = t4 * 4;
+    if (t >= (long long)rows * d) return;
+    if (in_sorted(rows_sorted, n_rows, (int)(t / d))) return;
+    const long long i = tab + t;
+    float4 pp = *reinterpret_cast<const float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+    float4 mm = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
+    const float step_size = lr / bc1;
+#define SRK_ADAM1(c)                                                   \
+    {                                                                  \
+      const float grad = gg.c * grad_scale + decay * pp.c;             \
+      mm.c = b1 * mm.c + (1.f - b1) * grad;                            \
+      vv.c = b2 * vv.c + (1.f - b2) * grad * grad;                     \
+      pp.c = pp.c - step_size * (mm.c / (sqrtf(vv.c) / bc2_sqrt + eps)); \
+    }
+    SRK_ADAM1(x) SRK_ADAM1(y) SRK_ADAM1(z) SRK_ADAM1(w)
+#undef SRK_ADAM1
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    *reinterpret_cast<float4*>(p + i) = pp;
+  } else {
+    const long long listed = (long long)n_rows * d;
+    const long long total = n - tab_span + listed;       // virtual index space: [0, tab) | listed rows | [tab + tab_span, n)
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+      long long i;
+      if (t < tab) i = t;
+      else if (t < tab + listed) {
+        const long long q = t - tab;
+        i = tab + (long long)rows_sorted[q / d] * d + q % d;
+      } else i = t - listed + tab_span;
+      if (i >= tab + (long long)rows * d && i < tab + tab_span) continue;       // alignment padding behind the table
+      int lo = 0, hi = n_seg - 1;
+      while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      adam_update(p, g, m, v, i, seg_decay[lo], lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale);
+    }
   }
 }
 
@@ -181,6 +262,28 @@ extern "C" int srk_colsum(const float* X, long long ldx, int R, int d, float* ou
 extern "C" int srk_mean(const float* x, int n, float* out, void* stream) {
   SRK_REQUIRE(n > 0, "mean: n must be positive");
   mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_adam_step_split(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                   const long long* seg_off, const float* seg_decay, int n_seg, long long tab, int rows,
+                                   int d, long long tab_span, const int* rows_sorted, int n_rows, int part, float lr,
+                                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  if (n <= 0) return SRK_OK;
+  SRK_REQUIRE(n_seg >= 1 && step >= 1 && (part == 0 || part == 1), "adam_split: bad arguments");
+  SRK_REQUIRE(tab >= 0 && rows >= 0 && d > 0 && tab_span >= (long long)rows * d && tab + tab_span <= n && n_rows >= 0,
+              "adam_split: table [%lld, +%lld) outside the flat buffer", tab, tab_span);
+  float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  const long long work = part == 0 ? (long long)rows * d : n - tab_span + (long long)n_rows * d;
+  if (work <= 0) return SRK_OK;
+  SRK_REQUIRE(part == 1 || (d % 4 == 0 && tab % 4 == 0), "adam_split: table rows must be 16-byte aligned");
+  const int grid = part == 0 ? srk_cdiv(work / 4, 256) : flat_grid(work, 256);
+  adam_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, seg_off,
+                                                                            seg_decay, n_seg, tab, rows, d, tab_span,
+                                                                            rows_sorted, n_rows, part, lr, beta1, beta2, eps,
+                                                                            bc1, bc2_sqrt, grad_scale);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
