@@ -167,6 +167,24 @@ int srk_colsum(const float* X, long long ldx, int R, int d, float* out, int accu
  * at srgnn.py:141-142, msgifsr.py:269-270). last[B] = row index of each segment's "last" node. */
 int srk_readout_fwd(const float* F, const float* u, const float* v, const float* we, const int* seg,
                     const int* last, int B, int d, int with_last, float* e, float* ms, float* sr_in, void* stream);
+/* Fused per-session tail of the readout, forward (csrc/readout_fused.cu): given u = F Wu^T (+bu) [R, d] and v [B, d]
+ * (srk_gemm), e / alpha / g as srk_readout_fwd, sr_in = [F[last] | g], s = sr_in Wsr^T, shat = norm_mode(s)
+ * (SRK_NORM_NONE / L2 / EPS), rn_s = ||s|| (optional), sbh / sbl = bf16 hi/lo of shat (optional pair): one launch instead
+ * of srk_readout_fwd + srk_gemm + srk_rownorm_fwd + srk_split_bf16 (srgnn.py:82-91,141-143; msgifsr.py:141-146,269-273).
+ * WsrT[2d, d] = Wsr^T (srk_transpose): the lanes read consecutive output columns. */
+int srk_readout_tail_fwd(const float* F, const float* u, const float* v, const float* we, const float* WsrT, const int* seg,
+                         const int* last, int B, int d, int norm_mode, float* e, float* ms, float* sr_in, float* s,
+                         float* shat, float* rn_s, uint16_t* sbh, uint16_t* sbl, void* stream);
+/* Y[cols, rows] = X[rows, cols]^T */
+int srk_transpose(const float* X, int rows, int cols, float* Y, void* stream);
+/* Fused per-session head of the readout backward: d shat [B, d] -> ds = normalise-backward (written out) -> d sr_in =
+ * ds Wsr -> attention backward: u / v are overwritten with d u / d v, dwe[d] accumulated, dF[R, d] = alpha d g (+ d l on
+ * the last row) - one launch instead of srk_rownorm_bwd + srk_gemm + srk_readout_bwd.  The caller finishes with the
+ * node-parallel GEMMs (dF += du Wu, dF[last] += dv Wv, and the weight gradients). */
+int srk_readout_head_bwd(const float* F, const float* we, const float* Wsr, const int* seg, const int* last, int B, int d,
+                         int norm_mode, const float* s, const float* shat, const float* rn_s, const float* sr_in,
+                         const float* e, const float* ms, const float* dshat, float* u, float* v, float* ds, float* dF,
+                         float* dwe, void* stream);
 /* Backward: given d sr_in [B, 2d], overwrites u with du and v with dv IN PLACE, writes dF[R, d] = alpha_i *
  * dg_b, adds into dwe[d]. The caller finishes with GEMMs (dF += du Wu, dWu += du^T F, ...). */
 int srk_readout_bwd(const float* F, float* u, float* v, const float* we, const int* seg, const int* last,

@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_fwd_kernel(const float* __
 // batch builder); every warp takes SCATTER_CHUNK consecutive occurrences, so a hot item (Zipf head, ~10% of a batch)
 // is spread over many warps instead of serialising one.  Runs of one item that lie entirely inside a warp's chunk are
 // added with a plain read-modify-write (deterministic); only items cut by a chunk boundary use atomicAdd.
-constexpr int SCATTER_CHUNK = 8;
+constexpr int SCATTER_CHUNK = 8;            // large tables / batches: long register-accumulated runs, few atomics
+constexpr int SCATTER_CHUNK_SMALL = 2;      // a training batch (P ~ 2 k): the kernel is a latency chain, not a bandwidth
+                                            // problem - 4x more warps with 4x shorter per-warp loops
 
 template <int NC>
 __device__ __forceinline__ void scatter_flush(const RowVec<NC>& acc, float* __restrict__ row, int d, int lane, bool whole) {
@@ -62,16 +64,16 @@ __device__ __forceinline__ void scatter_flush(const RowVec<NC>& acc, float* __re
 template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* __restrict__ E, const int* __restrict__ perm,
                                                                   const int* __restrict__ uoff, const int* __restrict__ uid,
-                                                                  int U, int P, int d, int mode, DropCfg dc,
+                                                                  int U, int P, int d, int mode, int chunk, DropCfg dc,
                                                                   const float* __restrict__ rnorm,
                                                                   const float* __restrict__ dX,
                                                                   const float* __restrict__ dX_first,
                                                                   float* __restrict__ dE) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int nchunks = (P + SCATTER_CHUNK - 1) / SCATTER_CHUNK;
+  const int nchunks = (P + chunk - 1) / chunk;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nchunks; w += warps) {
-    const int j0 = w * SCATTER_CHUNK, j1 = min(P, j0 + SCATTER_CHUNK);
+    const int j0 = w * chunk, j1 = min(P, j0 + chunk);
     int lo = 0, hi = U - 1;                    // distinct item u with uoff[u] <= j0 < uoff[u + 1]
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
@@ -285,9 +287,9 @@ extern "C" int srk_embed_scatter_bwd(const float* E, const int* iid, const int* 
   SRK_TRY(srk_check_dim(d));
   if (U <= 0 || P <= 0) return SRK_OK;
   DropCfg dc = make_drop(drop);
-  SRK_DISPATCH_NC(d, (scatter_bwd_kernel<NC><<<row_grid((P + SCATTER_CHUNK - 1) / SCATTER_CHUNK), ROW_THREADS, 0,
-                                              (cudaStream_t)stream>>>(E, perm, uoff, uid, U, P, d, norm_mode, dc, rnorm, dX,
-                                                                      dX_first, dE)));
+  const int chunk = P >= 65536 ? SCATTER_CHUNK : SCATTER_CHUNK_SMALL;
+  SRK_DISPATCH_NC(d, (scatter_bwd_kernel<NC><<<row_grid((P + chunk - 1) / chunk), ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                         E, perm, uoff, uid, U, P, d, norm_mode, chunk, dc, rnorm, dX, dX_first, dE)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -15,39 +15,66 @@ namespace {
 
 constexpr int H = SRK_HEADS;
 
-// Debug aid (SESSREC_STEP_TIMING=1): CUDA events at the stage boundaries of one step, printed after a sync.  Gives the
-// in-pipeline (warm-cache, back-to-back) time of every stage, which the cold-cache ncu launch list cannot.
+// Debug aid (SESSREC_STEP_TIMING=1): CUDA events at the stage boundaries of the critical-path stream.  The events of
+// a step are read back a few steps LATER (when they have completed anyway), so the host keeps running ahead of the GPU
+// and the numbers are the steady-state in-pipeline stage times, which neither the cold-cache ncu launch list nor a
+// synchronised step can give.  SESSREC_STEP_TIMING=2 synchronises after every step instead.
 struct StageTimer {
-  bool on;
+  static constexpr int RING = 4, MAXEV = 24;
+  struct Slot {
+    cudaEvent_t ev[MAXEV];
+    const char* names[MAXEV];
+    int n = 0;
+    bool made = false;
+  };
+  int mode;
   cudaStream_t st;
-  std::vector<cudaEvent_t> ev;
-  std::vector<const char*> names;
+  Slot* cur = nullptr;
+  static Slot* ring() {
+    static Slot r[RING];
+    return r;
+  }
+  static int& counter() {
+    static int c = 0;
+    return c;
+  }
+  static void print(Slot& s) {
+    if (s.n < 2) return;
+    float total = 0.f;
+    if (cudaEventElapsedTime(&total, s.ev[0], s.ev[s.n - 1]) != cudaSuccess) return;
+    fprintf(stderr, "[step timing] total %.1f us:", total * 1e3f);
+    for (int i = 1; i < s.n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, s.ev[i - 1], s.ev[i]);
+      fprintf(stderr, " %s=%.1f", s.names[i], ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+  }
   explicit StageTimer(cudaStream_t s) : st(s) {
     const char* e = getenv("SESSREC_STEP_TIMING");
-    on = e && e[0] == '1';
+    mode = e ? atoi(e) : 0;
+    if (!mode) return;
+    cur = &ring()[counter() % RING];
+    if (!cur->made) {
+      for (int i = 0; i < MAXEV; ++i) cudaEventCreate(&cur->ev[i]);
+      cur->made = true;
+    } else if (mode == 1) {
+      if (cudaEventQuery(cur->ev[cur->n - 1]) == cudaSuccess) print(*cur);     // the step recorded RING steps ago
+    }
+    cur->n = 0;
+    ++counter();
     mark("start");
   }
   void mark(const char* name) {
-    if (!on) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, st);
-    ev.push_back(e);
-    names.push_back(name);
+    if (!mode || cur->n >= MAXEV) return;
+    cudaEventRecord(cur->ev[cur->n], st);
+    cur->names[cur->n] = name;
+    ++cur->n;
   }
   void report() {
-    if (!on) return;
+    if (mode != 2) return;
     cudaStreamSynchronize(st);
-    float total = 0.f;
-    cudaEventElapsedTime(&total, ev.front(), ev.back());
-    fprintf(stderr, "[step timing] total %.1f us:", total * 1e3f);
-    for (size_t i = 1; i < ev.size(); ++i) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-      fprintf(stderr, " %s=%.1f", names[i], ms * 1e3f);
-    }
-    fprintf(stderr, "\n");
-    for (auto e : ev) cudaEventDestroy(e);
+    print(*cur);
   }
 };
 
@@ -188,7 +215,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   fl += (long long)L * (2 * ((ldzel + H) * d + 2LL * N * d + N * ldzel + N * H + (long long)(M + 1) * H) + B * d + N * d + N + N * d / 4 + 64);
   fl += 2LL * N * d + 3LL * B * d + N + 2LL * B + 4LL * B * d + B;    // u, v, e, ms, sr_in, s, shat, rn_s
   fl += 2LL * B * ldz + 4LL * B * d + 2LL * B + 64 + 4LL * ((V + 255) / 256) * B + B;        // Z, Zlo, sh, sl, dshat, ds, lse, nll
-  fl += 2LL * B * d + (long long)N * d;                    // dsr_in, dF
+  fl += 2LL * B * d + (long long)N * d + 2LL * d * d;      // dsr_in, dF, W_sr^T
   // flash CE head: bf16 hi/lo of Ehat and shat, soft-max partials, one [V, d] dE partial per 128-session tile
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
@@ -294,6 +321,17 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
       SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, s2));
     }
   }
+  // W_sr^T for the fused read-out tail (the lanes read consecutive output columns)
+  // opt-in (SESSREC_FUSED_READOUT=1): measured 2 % SLOWER than the unfused chain at cfg1 (0.437 vs 0.429 ms/step) although
+  // it saves 4 launches - the per-session mat-vecs run through a cold L1 on 64 CTAs while the GEMM launches fill the machine
+  const char* fro = getenv("SESSREC_FUSED_READOUT");
+  const bool fused_ro = fro && fro[0] == '1';
+  float* WsrT = nullptr;
+  if (fused_ro) {
+    WsrT = ar.f(2 * (size_t)d * d);
+    SRK_REQUIRE(ar.ok, "step: workspace too small");
+    SRK_TRY(srk_transpose(P(s_ro + 4), d, 2 * d, WsrT, s2));
+  }
   SRK_TRY(order(s2, st));
   const float* h = X;
   for (int l = 0; l < L; ++l) {
@@ -364,26 +402,35 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   float *u = ar.f((size_t)N * d), *v = ar.f((size_t)B * d), *e = ar.f(N), *ms = ar.f(2 * (size_t)B);
   float *sr_in = ar.f(2 * (size_t)B * d), *s = ar.f((size_t)B * d), *shat = ar.f((size_t)B * d), *rn_s = ar.f(B);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
+  uint16_t *Sbh = nullptr, *Sbl = nullptr;
+  if (flash) {
+    Sbh = reinterpret_cast<uint16_t*>(ar.raw((size_t)B * d * 2));
+    Sbl = reinterpret_cast<uint16_t*>(ar.raw((size_t)B * d * 2));
+    SRK_REQUIRE(ar.ok, "step: workspace too small");
+  }
   SRK_TRY(order(st, s1));
   SRK_TRY(linear_nt(st, N, d, d, F, d, P(s_ro), u, d, nullptr, P(s_ro + 1)));
   SRK_TRY(linear_nt(s1, B, d, d, F, d, P(s_ro + 2), v, d, b.last, nullptr));
   SRK_TRY(order(s1, st));
-  SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, 1, e, ms, sr_in, st));
-  SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
-  SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
+  if (fused_ro) {
+    // one launch: attention scores, segment soft-max, fc_sr, normalisation, bf16 split (csrc/readout_fused.cu)
+    SRK_TRY(srk_readout_tail_fwd(F, u, v, P(s_ro + 3), WsrT, b.seg, b.last, B, d, SRK_NORM_L2, e, ms, sr_in, s, shat, rn_s, Sbh,
+                                 Sbl, st));
+  } else {
+    SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, 1, e, ms, sr_in, st));
+    SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
+    SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
+    if (flash) SRK_TRY(srk_split_bf16(shat, d, B, d, Sbh, Sbl, d, st));
+  }
   tm.mark("readout_fwd");
   // scoring head + CE (needs the catalog pass)
   SRK_TRY(order(s4, st));
   float *Z = flash ? nullptr : ar.f((size_t)B * ldz), *lse = ar.f(B), *nll = ar.f(B);
   float *sh = nullptr, *sl = nullptr;
-  uint16_t *Sbh = nullptr, *Sbl = nullptr;
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   if (flash) {
-    Sbh = reinterpret_cast<uint16_t*>(ar.raw((size_t)B * d * 2));
-    Sbl = reinterpret_cast<uint16_t*>(ar.raw((size_t)B * d * 2));
     float* part = ar.f((size_t)srk_flash_ce_part_floats(B, V));
     SRK_REQUIRE(ar.ok, "step: workspace too small");
-    SRK_TRY(srk_split_bf16(shat, d, B, d, Sbh, Sbl, d, st));
     SRK_TRY(srk_flash_ce_fwd(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, b.labels, lse, nll, part, st));
   } else if (umma) {
     sh = ar.f((size_t)B * d); sl = ar.f((size_t)B * d);
@@ -456,17 +503,30 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   float* dF = ar.f((size_t)N * d);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   // data gradients on the main stream, weight gradients (mm_tn / colsum into the flat gradient buffer) on s2
-  SRK_TRY(srk_rownorm_bwd(s, d, shat, d, rn_s, dshat, d, B, d, SRK_NORM_L2, ds, d, 0, st));
-  SRK_TRY(order(st, s2));
-  SRK_TRY(mm_nn(st, B, 2 * d, d, ds, d, P(s_ro + 4), 2 * d, dsr_in, 2 * d, 0));
-  SRK_TRY(mm_tn(s2, d, 2 * d, B, ds, d, sr_in, 2 * d, G(s_ro + 4), 2 * d));
-  SRK_TRY(srk_readout_bwd(F, u, v, P(s_ro + 3), b.seg, b.last, e, ms, sr_in, dsr_in, B, d, 1, dF, G(s_ro + 3), st));
-  SRK_TRY(order(st, s2));
-  SRK_TRY(mm_nn(st, N, d, d, u, d, P(s_ro), d, dF, d, 1));                      // u holds du
-  SRK_TRY(mm_tn(s2, d, d, N, u, d, F, d, G(s_ro), d));
-  SRK_TRY(srk_colsum(u, d, N, d, G(s_ro + 1), 1, s2));
-  SRK_TRY(mm_nn(st, B, d, d, v, d, P(s_ro + 2), d, dF, d, 1, b.last));          // v holds dv
-  SRK_TRY(mm_tn(s2, d, d, B, v, d, F, d, G(s_ro + 2), d, b.last));
+  if (fused_ro) {
+    // one launch: normalise backward, d sr_in = d s W_sr, attention backward (csrc/readout_fused.cu); then the projections
+    SRK_TRY(srk_readout_head_bwd(F, P(s_ro + 3), P(s_ro + 4), b.seg, b.last, B, d, SRK_NORM_L2, s, shat, rn_s, sr_in, e, ms, dshat,
+                                 u, v, ds, dF, G(s_ro + 3), st));
+    SRK_TRY(order(st, s2));
+    SRK_TRY(mm_nn(st, N, d, d, u, d, P(s_ro), d, dF, d, 1));                      // u holds du
+    SRK_TRY(mm_nn(st, B, d, d, v, d, P(s_ro + 2), d, dF, d, 1, b.last));          // v holds dv
+    SRK_TRY(mm_tn(s2, d, 2 * d, B, ds, d, sr_in, 2 * d, G(s_ro + 4), 2 * d));
+    SRK_TRY(mm_tn(s2, d, d, N, u, d, F, d, G(s_ro), d));
+    SRK_TRY(srk_colsum(u, d, N, d, G(s_ro + 1), 1, s2));
+    SRK_TRY(mm_tn(s2, d, d, B, v, d, F, d, G(s_ro + 2), d, b.last));
+  } else {
+    SRK_TRY(srk_rownorm_bwd(s, d, shat, d, rn_s, dshat, d, B, d, SRK_NORM_L2, ds, d, 0, st));
+    SRK_TRY(order(st, s2));
+    SRK_TRY(mm_nn(st, B, 2 * d, d, ds, d, P(s_ro + 4), 2 * d, dsr_in, 2 * d, 0));
+    SRK_TRY(mm_tn(s2, d, 2 * d, B, ds, d, sr_in, 2 * d, G(s_ro + 4), 2 * d));
+    SRK_TRY(srk_readout_bwd(F, u, v, P(s_ro + 3), b.seg, b.last, e, ms, sr_in, dsr_in, B, d, 1, dF, G(s_ro + 3), st));
+    SRK_TRY(order(st, s2));
+    SRK_TRY(mm_nn(st, N, d, d, u, d, P(s_ro), d, dF, d, 1));                      // u holds du
+    SRK_TRY(mm_tn(s2, d, d, N, u, d, F, d, G(s_ro), d));
+    SRK_TRY(srk_colsum(u, d, N, d, G(s_ro + 1), 1, s2));
+    SRK_TRY(mm_nn(st, B, d, d, v, d, P(s_ro + 2), d, dF, d, 1, b.last));          // v holds dv
+    SRK_TRY(mm_tn(s2, d, d, B, v, d, F, d, G(s_ro + 2), d, b.last));
+  }
 
   tm.mark("readout_bwd");
   // layers, last to first.  Scratch below is re-carved per layer from a fixed mark.

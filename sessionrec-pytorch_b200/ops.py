@@ -200,6 +200,23 @@ def readout_fwd(F, u, v, we, seg, last, B, d, with_last, e, ms, sr_in):
           ptr(sr_in))
 
 
+def transpose(X, rows, cols, Y):
+    _call('srk_transpose', ptr(X), rows, cols, ptr(Y))
+
+
+def readout_tail_fwd(F, u, v, we, WsrT, seg, last, B, d, norm_mode, e, ms, sr_in, s, shat, rn_s, sbh=None, sbl=None):
+    """WsrT = Wsr^T ([2d, d], ops.transpose)."""
+    _need_cuda(F, u, v, we, WsrT, e, ms, sr_in, s, shat)
+    _call('srk_readout_tail_fwd', ptr(F), ptr(u), ptr(v), ptr(we), ptr(WsrT), ptr(seg), ptr(last), B, d, int(norm_mode), ptr(e),
+          ptr(ms), ptr(sr_in), ptr(s), ptr(shat), ptr(rn_s), ptr(sbh), ptr(sbl))
+
+
+def readout_head_bwd(F, we, Wsr, seg, last, B, d, norm_mode, s, shat, rn_s, sr_in, e, ms, dshat, u, v, ds, dF, dwe):
+    _need_cuda(F, we, Wsr, s, shat, sr_in, e, ms, dshat, u, v, ds, dF, dwe)
+    _call('srk_readout_head_bwd', ptr(F), ptr(we), ptr(Wsr), ptr(seg), ptr(last), B, d, int(norm_mode), ptr(s), ptr(shat),
+          ptr(rn_s), ptr(sr_in), ptr(e), ptr(ms), ptr(dshat), ptr(u), ptr(v), ptr(ds), ptr(dF), ptr(dwe))
+
+
 def readout_bwd(F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe):
     _call('srk_readout_bwd', ptr(F), ptr(u), ptr(v), ptr(we), ptr(seg), ptr(last), ptr(e), ptr(ms), ptr(sr_in),
           ptr(dsr_in), B, d, int(with_last), ptr(dF), ptr(dwe))
