@@ -31,11 +31,53 @@ void srk_set_error(const char* fmt, ...);
   } while (0)
 
 extern long long g_srk_launches;   // kernels launched by this library (bench.py reports it as gpu_launches)
-#define SRK_LAUNCH_CHECK()            \
+// after a raw `kernel<<<...>>>(...)` launch
+#define SRK_LAUNCH_CHECK_RAW()        \
   do {                                \
     ++g_srk_launches;                 \
     SRK_CUDA(cudaGetLastError());     \
   } while (0)
+
+// ---- launch layer --------------------------------------------------------------------------------------------------
+// Every kernel of the training step is launched through srk_launch().  Normally that is cudaLaunchKernel.  Inside the
+// native step (csrc/step.cu) the same call sites can instead (a) be captured, once, into a CUDA graph whose kernel
+// nodes are remembered in launch order, or (b) on later steps only UPDATE the parameters of those nodes
+// (cudaGraphExecKernelNodeSetParams, ~1 us, against ~2.7 us per launch plus the event traffic of the multi-stream
+// fork / join), after which the whole step is ONE cudaGraphLaunch.  Shapes (grid sizes, pointers) may change from step
+// to step; the kernel sequence may not - a mismatch makes the step fall back to plain launches.  SKIP drops the launch
+// (used to replay only the host-side bookkeeping of a part of the step that has already been enqueued).
+enum { SRK_LAUNCH_DIRECT = 0, SRK_LAUNCH_CAPTURE = 1, SRK_LAUNCH_UPDATE = 2, SRK_LAUNCH_SKIP = 3 };
+int srk_launch_mode();             // of the calling thread
+int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args);
+extern thread_local int g_srk_launch_rc;      // result of the last srk_launch on this thread
+
+#ifdef __CUDACC__
+#include <tuple>
+#include <utility>
+template <typename Tuple, size_t... I>
+inline int srk_launch_packed(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Tuple& pack,
+                             std::index_sequence<I...>) {
+  void* ptrs[] = {static_cast<void*>(&std::get<I>(pack))...};
+  return srk_launch_raw(func, grid, block, smem, st, ptrs);
+}
+template <typename... KArgs, typename... Args>
+inline void srk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static_assert(sizeof...(KArgs) == sizeof...(Args), "srk_launch: argument count differs from the kernel's");
+  std::tuple<KArgs...> pack(static_cast<KArgs>(args)...);
+  g_srk_launch_rc = srk_launch_packed(reinterpret_cast<const void*>(kernel), grid, block, smem, st, pack,
+                                      std::index_sequence_for<KArgs...>{});
+}
+#endif
+// after srk_launch(...)
+#define SRK_LAUNCH_CHECK()                                   \
+  do {                                                       \
+    if (g_srk_launch_rc != SRK_OK) return g_srk_launch_rc;   \
+  } while (0)
+
+// stream-ordered zero fill / device copy as kernels (graph-capturable as plain kernel nodes; short-lived CTAs)
+int srk_zero_async(void* p, size_t bytes, cudaStream_t st);
+int srk_copy_async(void* dst, const void* src, size_t bytes, cudaStream_t st);
+int srk_zero2d_async(float* C, long long ldc, int rows, int cols, cudaStream_t st);
 
 #define SRK_TRY(expr)               \
   do {                              \

@@ -274,8 +274,7 @@ extern "C" int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d
   if (P <= 0) return SRK_OK;
   SRK_REQUIRE(norm_mode == SRK_NORM_NONE || rnorm, "embed_gather_fwd: rnorm is required when normalising");
   DropCfg dc = make_drop(drop);
-  SRK_DISPATCH_NC(d, (gather_fwd_kernel<NC><<<row_grid(P), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         E, iid, P, d, norm_mode, dc, X, rnorm, x_first)));
+  SRK_DISPATCH_NC(d, (srk_launch(gather_fwd_kernel<NC>, row_grid(P), ROW_THREADS, 0, (cudaStream_t)stream, E, iid, P, d, norm_mode, dc, X, rnorm, x_first)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -288,8 +287,7 @@ extern "C" int srk_embed_scatter_bwd(const float* E, const int* iid, const int* 
   if (U <= 0 || P <= 0) return SRK_OK;
   DropCfg dc = make_drop(drop);
   const int chunk = P >= 65536 ? SCATTER_CHUNK : SCATTER_CHUNK_SMALL;
-  SRK_DISPATCH_NC(d, (scatter_bwd_kernel<NC><<<row_grid((P + chunk - 1) / chunk), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         E, perm, uoff, uid, U, P, d, norm_mode, chunk, dc, rnorm, dX, dX_first, dE)));
+  SRK_DISPATCH_NC(d, (srk_launch(scatter_bwd_kernel<NC>, row_grid((P + chunk - 1) / chunk), ROW_THREADS, 0, (cudaStream_t)stream, E, perm, uoff, uid, U, P, d, norm_mode, chunk, dc, rnorm, dX, dX_first, dE)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -297,7 +295,7 @@ extern "C" int srk_embed_scatter_bwd(const float* E, const int* iid, const int* 
 extern "C" int srk_renorm_rows(float* E, const int* uid, int U, int d, float max_norm, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (U <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (renorm_rows_kernel<NC><<<row_grid(U), ROW_THREADS, 0, (cudaStream_t)stream>>>(E, uid, U, d,
+  SRK_DISPATCH_NC(d, (srk_launch(renorm_rows_kernel<NC>, row_grid(U), ROW_THREADS, 0, (cudaStream_t)stream, E, uid, U, d,
                                                                                                       max_norm)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -307,8 +305,7 @@ extern "C" int srk_catalog_prep_fwd(float* E, int V, int d, int norm_mode, float
                                     float* Ehat_hi, float* Ehat_lo, uint16_t* Ebf_hi, uint16_t* Ebf_lo, void* stream) {
   SRK_TRY(srk_check_dim(d));
   SRK_REQUIRE(norm_mode == SRK_NORM_L2 || norm_mode == SRK_NORM_EPS, "catalog_prep: norm_mode must be L2 or EPS");
-  SRK_DISPATCH_NC(d, (catalog_prep_fwd_kernel<NC><<<row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         E, V, d, norm_mode, max_norm, Ehat, enorm, Ehat_hi, Ehat_lo, Ebf_hi, Ebf_lo)));
+  SRK_DISPATCH_NC(d, (srk_launch(catalog_prep_fwd_kernel<NC>, row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream, E, V, d, norm_mode, max_norm, Ehat, enorm, Ehat_hi, Ehat_lo, Ebf_hi, Ebf_lo)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -318,8 +315,7 @@ extern "C" int srk_catalog_prep_bwd(const float* E, const float* Ehat, const flo
   SRK_TRY(srk_check_dim(d));
   if (V <= 0) return SRK_OK;
   SRK_REQUIRE(nparts >= 1, "catalog_prep_bwd: nparts must be >= 1");
-  SRK_DISPATCH_NC(d, (rownorm_bwd_kernel<NC><<<row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         E, d, Ehat, d, enorm, dEhat, d, V, d, norm_mode, dE, d, 1, nparts, (long long)V * d)));
+  SRK_DISPATCH_NC(d, (srk_launch(rownorm_bwd_kernel<NC>, row_grid(V), ROW_THREADS, 0, (cudaStream_t)stream, E, d, Ehat, d, enorm, dEhat, d, V, d, norm_mode, dE, d, 1, nparts, (long long)V * d)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -329,7 +325,7 @@ extern "C" int srk_rownorm_fwd(const float* X, long long ldx, int R, int d, int 
   SRK_TRY(srk_check_dim(d));
   if (R <= 0) return SRK_OK;
   SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "rownorm: row strides must be multiples of 4");
-  SRK_DISPATCH_NC(d, (rownorm_fwd_kernel<NC><<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(X, ldx, R, d, norm_mode,
+  SRK_DISPATCH_NC(d, (srk_launch(rownorm_fwd_kernel<NC>, row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream, X, ldx, R, d, norm_mode,
                                                                                                       Y, ldy, rnorm)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -341,8 +337,7 @@ extern "C" int srk_rownorm_bwd(const float* X, long long ldx, const float* Y, lo
   SRK_TRY(srk_check_dim(d));
   if (R <= 0) return SRK_OK;
   SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "rownorm: strides must be multiples of 4");
-  SRK_DISPATCH_NC(d, (rownorm_bwd_kernel<NC><<<row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         X, ldx, Y, ldy, rnorm, dY, lddy, R, d, norm_mode, dX, lddx, accumulate, 1, 0)));
+  SRK_DISPATCH_NC(d, (srk_launch(rownorm_bwd_kernel<NC>, row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream, X, ldx, Y, ldy, rnorm, dY, lddy, R, d, norm_mode, dX, lddx, accumulate, 1, 0)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -351,7 +346,7 @@ extern "C" int srk_expander_combine_fwd(const float* X, const float* h, int N, i
                                         void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (N <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (expander_combine_fwd_kernel<NC><<<row_grid(N), ROW_THREADS, 0, (cudaStream_t)stream>>>(X, h, N, k, d, out,
+  SRK_DISPATCH_NC(d, (srk_launch(expander_combine_fwd_kernel<NC>, row_grid(N), ROW_THREADS, 0, (cudaStream_t)stream, X, h, N, k, d, out,
                                                                                                                rnorm)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -361,8 +356,7 @@ extern "C" int srk_expander_combine_bwd(const float* out, const float* rnorm, co
                                         float* dh, float* dX, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (N <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (expander_combine_bwd_kernel<NC><<<row_grid(N), ROW_THREADS, 0, (cudaStream_t)stream>>>(
-                         out, rnorm, dout, N, k, d, dh, dX)));
+  SRK_DISPATCH_NC(d, (srk_launch(expander_combine_bwd_kernel<NC>, row_grid(N), ROW_THREADS, 0, (cudaStream_t)stream, out, rnorm, dout, N, k, d, dh, dX)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

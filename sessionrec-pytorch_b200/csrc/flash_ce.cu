@@ -777,7 +777,7 @@ extern "C" int srk_split_bf16(const float* X, long long ldx, int rows, int cols,
   if (total <= 0) return SRK_OK;
   long long g = (total + 255) / 256;
   if (g > 148LL * 16) g = 148LL * 16;
-  split_bf16_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, ldx, rows, cols, reinterpret_cast<__nv_bfloat16*>(hi),
+  srk_launch(split_bf16_kernel, (int)g, 256, 0, (cudaStream_t)stream, X, ldx, rows, cols, reinterpret_cast<__nv_bfloat16*>(hi),
                                                               reinterpret_cast<__nv_bfloat16*>(lo), ldo);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -811,9 +811,9 @@ extern "C" int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const 
     SRK_CUDA(cudaFuncSetAttribute(fce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
     attr_set = true;
   }
-  fce_fwd_kernel<<<p.ntm * p.nvr, THREADS, smem_bytes(p, false), st>>>(mSh, mSl, mEh, mEl, p);
+  srk_launch(fce_fwd_kernel, p.ntm * p.nvr, THREADS, smem_bytes(p, false), st, mSh, mSl, mEh, mEl, p);
   SRK_LAUNCH_CHECK();
-  fce_finalize_kernel<<<srk_cdiv((long long)B * 32, 256), 256, 0, st>>>(p.part, p.zlab, labels, B, V, 2 * p.nvr, lse, nll);
+  srk_launch(fce_finalize_kernel, srk_cdiv((long long)B * 32, 256), 256, 0, st, p.part, p.zlab, labels, B, V, 2 * p.nvr, lse, nll);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -853,8 +853,8 @@ extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const 
     SRK_CUDA(cudaFuncSetAttribute(fce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
     attr_set = true;
   }
-  SRK_CUDA(cudaMemsetAsync(dS, 0, sizeof(float) * (size_t)B * d, st));
-  fce_bwd_kernel<<<p.ntm * p.nvr, THREADS_BWD, smem_bytes(p, true), st>>>(mSh, mSl, mEh, mEl, mdE, mdS, p);
+  SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
+  srk_launch(fce_bwd_kernel, p.ntm * p.nvr, THREADS_BWD, smem_bytes(p, true), st, mSh, mSl, mEh, mEl, mdE, mdS, p);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -866,7 +866,7 @@ extern "C" int srk_sum_parts(const float* parts, long long stride, int nparts, l
               "sum_parts: n / stride must be multiples of 4 and the buffers 16-byte aligned");
   long long g = (n / 4 + 255) / 256;
   if (g > 148LL * 8) g = 148LL * 8;
-  sum_parts_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(parts), stride / 4, nparts, n / 4,
+  srk_launch(sum_parts_kernel, (int)g, 256, 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(parts), stride / 4, nparts, n / 4,
                                                              reinterpret_cast<float4*>(out), accumulate);
   SRK_LAUNCH_CHECK();
   return SRK_OK;

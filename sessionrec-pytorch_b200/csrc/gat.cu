@@ -352,8 +352,8 @@ extern "C" int srk_gat_prep(const float* W, const float* attn_l, const float* at
                             void* stream) {
   SRK_TRY(srk_check_dim(d));
   cudaStream_t st = (cudaStream_t)stream;
-  SRK_CUDA(cudaMemcpyAsync(Waug, W, sizeof(float) * (size_t)H * d * d, cudaMemcpyDeviceToDevice, st));
-  gat_prep_kernel<<<dim3(srk_cdiv(d, 32), H), 256, 0, st>>>(W, attn_l, attn_r, d, Waug, wr);
+  SRK_TRY(srk_copy_async(Waug, W, sizeof(float) * (size_t)H * d * d, st));
+  srk_launch(gat_prep_kernel, dim3(srk_cdiv(d, 32), H), 256, 0, st, W, attn_l, attn_r, d, Waug, wr);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -361,8 +361,7 @@ extern "C" int srk_gat_prep(const float* W, const float* attn_l, const float* at
 extern "C" int srk_gat_prep_bwd(const float* W, const float* attn_l, const float* attn_r, const float* dWaug,
                                 const float* dwr, int d, float* dW, float* dattn_l, float* dattn_r, void* stream) {
   SRK_TRY(srk_check_dim(d));
-  SRK_DISPATCH_NC(d, (gat_prep_bwd_kernel<NC><<<row_grid((long long)H * d), 256, 0, (cudaStream_t)stream>>>(
-                         W, attn_l, attn_r, dWaug, dwr, d, dW, dattn_l, dattn_r)));
+  SRK_DISPATCH_NC(d, (srk_launch(gat_prep_bwd_kernel<NC>, row_grid((long long)H * d), 256, 0, (cudaStream_t)stream, W, attn_l, attn_r, dWaug, dwr, d, dW, dattn_l, dattn_r)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -376,7 +375,7 @@ extern "C" int srk_gat_aggregate_fwd(const srk_gat_inst* inst_host, int n_inst, 
   SRK_TRY(fill_params(P, inst_host, n_inst));
   DropCfg dc = make_drop(attn_drop);
   size_t smem = sizeof(float) * (size_t)H * d;
-  SRK_DISPATCH_NC(d, (gat_agg_fwd_kernel<NC><<<N, 256, smem, (cudaStream_t)stream>>>(P, N, d, segmean, node2seg, dc,
+  SRK_DISPATCH_NC(d, (srk_launch(gat_agg_fwd_kernel<NC>, N, 256, smem, (cudaStream_t)stream, P, N, d, segmean, node2seg, dc,
                                                                                      normalize, Hout, rnorm, amax)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -390,7 +389,7 @@ extern "C" int srk_gat_aggregate_bwd_dst(const srk_gat_inst* inst_host, int n_in
   GatParams P;
   SRK_TRY(fill_params(P, inst_host, n_inst));
   DropCfg dc = make_drop(attn_drop);
-  SRK_DISPATCH_NC(d, (gat_bwd_dst_kernel<NC><<<N, 256, 0, (cudaStream_t)stream>>>(P, N, d, dc, normalize, Hn, rnorm, amax,
+  SRK_DISPATCH_NC(d, (srk_launch(gat_bwd_dst_kernel<NC>, N, 256, 0, (cudaStream_t)stream, P, N, d, dc, normalize, Hn, rnorm, amax,
                                                                                   dH, dHpre)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -403,7 +402,7 @@ extern "C" int srk_gat_aggregate_bwd_src(const srk_gat_inst* inst_host, int d, c
   if (I.n_src <= 0) return SRK_OK;
   DropCfg dc = make_drop(attn_drop);
   dc.site = I.attn_site;
-  SRK_DISPATCH_NC(d, (gat_bwd_src_kernel<NC><<<I.n_src, 256, 0, (cudaStream_t)stream>>>(I, d, dc, dHpre, amax)));
+  SRK_DISPATCH_NC(d, (srk_launch(gat_bwd_src_kernel<NC>, I.n_src, 256, 0, (cudaStream_t)stream, I, d, dc, dHpre, amax)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -414,7 +413,7 @@ extern "C" int srk_gat_bias_bwd(const float* dHpre, const uint8_t* amax, int N, 
   if (by > 64) by = 64;
   int rows_per_block = srk_cdiv(N, by);
   dim3 grid(srk_cdiv(d, 32), by);
-  gat_bias_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dHpre, amax, N, d, rows_per_block, dbias);
+  srk_launch(gat_bias_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dHpre, amax, N, d, rows_per_block, dbias);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -422,7 +421,7 @@ extern "C" int srk_gat_bias_bwd(const float* dHpre, const uint8_t* amax, int N, 
 extern "C" int srk_segmean_fwd(const float* X, const int* seg, int B, int d, float* mean, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (B <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (segmean_fwd_kernel<NC><<<row_grid(B), 256, 0, (cudaStream_t)stream>>>(X, seg, B, d, mean)));
+  SRK_DISPATCH_NC(d, (srk_launch(segmean_fwd_kernel<NC>, row_grid(B), 256, 0, (cudaStream_t)stream, X, seg, B, d, mean)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -430,7 +429,7 @@ extern "C" int srk_segmean_fwd(const float* X, const int* seg, int B, int d, flo
 extern "C" int srk_segmean_bwd(const float* dHpre, const int* seg, int B, int d, float* dX, int accumulate, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (B <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (segmean_bwd_kernel<NC><<<row_grid(B), 256, 0, (cudaStream_t)stream>>>(dHpre, seg, B, d, dX,
+  SRK_DISPATCH_NC(d, (srk_launch(segmean_bwd_kernel<NC>, row_grid(B), 256, 0, (cudaStream_t)stream, dHpre, seg, B, d, dX,
                                                                                             accumulate)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;

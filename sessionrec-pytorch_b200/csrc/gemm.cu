@@ -409,7 +409,7 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
     // overwrite mode with a long K loop and few tiles: zero C, then run the split-K accumulate path
     int s = srk_pick_split_k(g.M, g.N, g.K);
     if (s > 1) {
-      SRK_CUDA(cudaMemset2DAsync(g.C, sizeof(float) * (size_t)g.ldc, 0, sizeof(float) * (size_t)g.N, (size_t)g.M, st));
+      SRK_TRY(srk_zero2d_async(g.C, g.ldc, g.M, g.N, st));
       GemmArgs h = g;
       h.accumulate = 1;
       h.split_k = s;
@@ -448,7 +448,7 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
   const double flops = 2.0 * g.M * g.N * g.K;
   if (!no_small && p.k_chunk <= SKMAX && flops < 1.0e8 && srk_cdiv(g.M, SB) <= 65535) {
     dim3 sgrid(srk_cdiv(g.N, SB), srk_cdiv(g.M, SB), S);
-    sgemm_small_kernel<<<sgrid, NT, 0, st>>>(p);
+    srk_launch(sgemm_small_kernel, sgrid, NT, 0, st, p);
     SRK_LAUNCH_CHECK();
     return SRK_OK;
   }
@@ -465,9 +465,9 @@ int srk_gemm_launch(const GemmArgs& g, cudaStream_t st) {
                                     (int)(sizeof(float) * 2 * SS_MAXK * (BM + PAD))));
       attr_set = true;
     }
-    sgemm_singleshot_kernel<<<grid, NT, smem, st>>>(p);
+    srk_launch(sgemm_singleshot_kernel, grid, NT, smem, st, p);
   } else {
-    sgemm_kernel<<<grid, NT, 0, st>>>(p);
+    srk_launch(sgemm_kernel, grid, NT, 0, st, p);
   }
   SRK_LAUNCH_CHECK();
   return SRK_OK;

@@ -131,8 +131,7 @@ extern "C" int srk_ggnn_aggregate_fwd(const float* X, int N, int d, const int* i
                                       const float* w, float* NN, float* wsum, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (N <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (ggnn_agg_fwd_kernel<NC><<<row_grid(N), 256, 0, (cudaStream_t)stream>>>(
-                         X, N, d, in_ptr, in_src, in_eid, out_ptr, out_dst, out_eid, w, NN, wsum)));
+  SRK_DISPATCH_NC(d, (srk_launch(ggnn_agg_fwd_kernel<NC>, row_grid(N), 256, 0, (cudaStream_t)stream, X, N, d, in_ptr, in_src, in_eid, out_ptr, out_dst, out_eid, w, NN, wsum)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -142,8 +141,7 @@ extern "C" int srk_ggnn_aggregate_bwd(const float* dNN, int N, int d, const int*
                                       const float* w, const float* wsum, float* dX, int accumulate, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (N <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (ggnn_agg_bwd_kernel<NC><<<row_grid(N), 256, 0, (cudaStream_t)stream>>>(
-                         dNN, N, d, in_ptr, in_src, in_eid, out_ptr, out_dst, out_eid, w, wsum, dX, accumulate)));
+  SRK_DISPATCH_NC(d, (srk_launch(ggnn_agg_bwd_kernel<NC>, row_grid(N), 256, 0, (cudaStream_t)stream, dNN, N, d, in_ptr, in_src, in_eid, out_ptr, out_dst, out_eid, w, wsum, dX, accumulate)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -152,7 +150,7 @@ extern "C" int srk_gru_pointwise_fwd(const float* gi, const float* gh, const flo
                                      void* stream) {
   long long total = (long long)N * d;
   if (total <= 0) return SRK_OK;
-  gru_fwd_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(gi, gh, h, total, d, hnew);
+  srk_launch(gru_fwd_kernel, flat_grid(total), 256, 0, (cudaStream_t)stream, gi, gh, h, total, d, hnew);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -161,7 +159,7 @@ extern "C" int srk_gru_pointwise_bwd(float* gi, float* gh, const float* h, const
                                      int accumulate, void* stream) {
   long long total = (long long)N * d;
   if (total <= 0) return SRK_OK;
-  gru_bwd_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(gi, gh, h, dhnew, total, d, dh, accumulate);
+  srk_launch(gru_bwd_kernel, flat_grid(total), 256, 0, (cudaStream_t)stream, gi, gh, h, dhnew, total, d, dh, accumulate);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

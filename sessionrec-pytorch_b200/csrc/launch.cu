@@ -1,0 +1,103 @@
+// Launch layer: plain launch, capture (remember the graph node of every launch) or update (re-parameterise the node).
+#include "launch.cuh"
+
+thread_local int g_srk_launch_rc = SRK_OK;
+static thread_local SrkLaunchCtx* g_ctx = nullptr;
+
+void srk_set_launch_ctx(SrkLaunchCtx* ctx) { g_ctx = ctx; }
+SrkLaunchCtx* srk_get_launch_ctx() { return g_ctx; }
+int srk_launch_mode() { return g_ctx ? g_ctx->mode : SRK_LAUNCH_DIRECT; }
+
+int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+  SrkLaunchCtx* c = g_ctx;
+  if (c && c->mode == SRK_LAUNCH_SKIP) return SRK_OK;
+  ++g_srk_launches;
+  if (c && c->mode == SRK_LAUNCH_UPDATE) {
+    if (c->failed) return SRK_OK;                       // the step will be re-run with plain launches
+    if (c->cursor >= c->g->nodes.size() || c->g->nodes[c->cursor].func != func) {
+      c->failed = true;
+      return SRK_OK;
+    }
+    cudaKernelNodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.func = const_cast<void*>(func);
+    p.gridDim = grid;
+    p.blockDim = block;
+    p.sharedMemBytes = (unsigned int)smem;
+    p.kernelParams = args;
+    if (cudaGraphExecKernelNodeSetParams(c->g->exec, c->g->nodes[c->cursor].node, &p) != cudaSuccess) {
+      cudaGetLastError();
+      c->failed = true;
+      return SRK_OK;
+    }
+    ++c->cursor;
+    return SRK_OK;
+  }
+  SRK_CUDA(cudaLaunchKernel(func, grid, block, args, smem, st));
+  if (c && c->mode == SRK_LAUNCH_CAPTURE) {
+    cudaStreamCaptureStatus status;
+    unsigned long long id = 0;
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    if (cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps) != cudaSuccess ||
+        status != cudaStreamCaptureStatusActive || ndeps != 1) {
+      cudaGetLastError();
+      c->failed = true;                                 // not capturing after all: the caller discards the graph
+      return SRK_OK;
+    }
+    c->g->nodes.push_back(SrkGraphNode{deps[0], func});
+  }
+  return SRK_OK;
+}
+
+namespace {
+
+__global__ void __launch_bounds__(256) zero_kernel(uint4* __restrict__ p, long long n16, unsigned char* __restrict__ tail, int ntail) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (i < ntail) tail[i] = 0;
+}
+__global__ void __launch_bounds__(256) copy_kernel(uint4* __restrict__ d, const uint4* __restrict__ s, long long n16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(256) zero2d_kernel(float* __restrict__ C, long long ldc, int rows, int cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)rows * cols) C[(i / cols) * ldc + i % cols] = 0.f;
+}
+
+}  // namespace
+
+int srk_zero2d_async(float* C, long long ldc, int rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return SRK_OK;
+  if (ldc == cols && (reinterpret_cast<uintptr_t>(C) & 15u) == 0) return srk_zero_async(C, sizeof(float) * (size_t)rows * cols, st);
+  const long long n = (long long)rows * cols;
+  srk_launch(zero2d_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, C, ldc, rows, cols);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+int srk_zero_async(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return SRK_OK;
+  SRK_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15u) == 0, "zero_async: pointer must be 16-byte aligned");
+  const long long n16 = (long long)(bytes / 16);
+  const int ntail = (int)(bytes % 16);
+  const long long work = n16 > ntail ? n16 : ntail;
+  srk_launch(zero_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, st, reinterpret_cast<uint4*>(p), n16,
+             reinterpret_cast<unsigned char*>(p) + n16 * 16, ntail);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+int srk_copy_async(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return SRK_OK;
+  SRK_REQUIRE(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0 && bytes % 16 == 0,
+              "copy_async: 16-byte aligned buffers and size required");
+  const long long n16 = (long long)(bytes / 16);
+  srk_launch(copy_kernel, dim3((unsigned)((n16 + 255) / 256)), dim3(256), 0, st, reinterpret_cast<uint4*>(dst),
+             reinterpret_cast<const uint4*>(src), n16);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}

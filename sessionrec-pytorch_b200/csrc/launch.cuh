@@ -1,0 +1,38 @@
+// Graph context of the launch layer (common.cuh): used by csrc/step.cu only.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct SrkGraphNode {
+  cudaGraphNode_t node;
+  const void* func;
+};
+
+struct SrkStepGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<SrkGraphNode> nodes;      // kernel nodes in launch order
+  void destroy() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr;
+    graph = nullptr;
+    nodes.clear();
+  }
+};
+
+struct SrkLaunchCtx {
+  int mode = SRK_LAUNCH_DIRECT;
+  SrkStepGraph* g = nullptr;
+  size_t cursor = 0;
+  bool failed = false;                  // update pass: kernel sequence differs from the captured one
+  // what the step switches to at its forward / backward boundary (csrc/step.cu) and on which stream a capture starts
+  int mode_after_boundary = SRK_LAUNCH_DIRECT;
+  cudaStream_t capture_stream = nullptr;
+  bool capturing = false;
+};
+SrkLaunchCtx* srk_get_launch_ctx();
+
+// installs `ctx` for the calling thread (nullptr = plain launches)
+void srk_set_launch_ctx(SrkLaunchCtx* ctx);

@@ -215,14 +215,14 @@ inline int row_grid(long long rows) {
 extern "C" int srk_dropout_apply(const float* X, float* Y, long long n, const srk_dropout* drop, int accumulate,
                                  void* stream) {
   if (n <= 0) return SRK_OK;
-  dropout_apply_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(X, Y, n, make_drop(drop), accumulate);
+  srk_launch(dropout_apply_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, X, Y, n, make_drop(drop), accumulate);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
 
 extern "C" int srk_fill(float* X, long long n, float value, void* stream) {
   if (n <= 0) return SRK_OK;
-  fill_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(X, n, value);
+  srk_launch(fill_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, X, n, value);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -231,7 +231,7 @@ extern "C" int srk_gather_rows(const float* X, const int* idx, int R, int d, flo
   SRK_TRY(srk_check_dim(d));
   if (R <= 0) return SRK_OK;
   SRK_REQUIRE(ldy % 4 == 0, "gather_rows: ldy must be a multiple of 4");
-  SRK_DISPATCH_NC(d, (gather_rows_kernel<NC><<<row_grid(R), 256, 0, (cudaStream_t)stream>>>(X, idx, R, d, Y, ldy)));
+  SRK_DISPATCH_NC(d, (srk_launch(gather_rows_kernel<NC>, row_grid(R), 256, 0, (cudaStream_t)stream, X, idx, R, d, Y, ldy)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -240,7 +240,7 @@ extern "C" int srk_scatter_add_rows(const float* X, long long ldx, const int* id
   SRK_TRY(srk_check_dim(d));
   if (R <= 0) return SRK_OK;
   SRK_REQUIRE(ldx % 4 == 0, "scatter_add_rows: ldx must be a multiple of 4");
-  SRK_DISPATCH_NC(d, (scatter_add_rows_kernel<NC><<<row_grid(R), 256, 0, (cudaStream_t)stream>>>(X, ldx, idx, R, d, Y)));
+  SRK_DISPATCH_NC(d, (srk_launch(scatter_add_rows_kernel<NC>, row_grid(R), 256, 0, (cudaStream_t)stream, X, ldx, idx, R, d, Y)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -248,20 +248,20 @@ extern "C" int srk_scatter_add_rows(const float* X, long long ldx, const int* id
 extern "C" int srk_colsum(const float* X, long long ldx, int R, int d, float* out, int accumulate, void* stream) {
   if (d <= 0) return SRK_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!accumulate) SRK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * d, st));
+  if (!accumulate) SRK_TRY(srk_zero_async(out, sizeof(float) * d, st));
   if (R <= 0) return SRK_OK;
   int by = srk_cdiv(R, 256);
   if (by > 64) by = 64;
   int rows_per_block = srk_cdiv(R, by);
   dim3 grid(srk_cdiv(d, 32), by);
-  colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, R, d, rows_per_block, out);
+  srk_launch(colsum_kernel, grid, 256, 0, st, X, ldx, R, d, rows_per_block, out);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
 
 extern "C" int srk_mean(const float* x, int n, float* out, void* stream) {
   SRK_REQUIRE(n > 0, "mean: n must be positive");
-  mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, out);
+  srk_launch(mean_kernel, 1, 1024, 0, (cudaStream_t)stream, x, n, out);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -280,7 +280,7 @@ extern "C" int srk_adam_step_split(float* param, const float* grad, float* exp_a
   if (work <= 0) return SRK_OK;
   SRK_REQUIRE(part == 1 || (d % 4 == 0 && tab % 4 == 0), "adam_split: table rows must be 16-byte aligned");
   const int grid = part == 0 ? srk_cdiv(work / 4, 256) : flat_grid(work, 256);
-  adam_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, seg_off,
+  srk_launch(adam_split_kernel, grid, 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, seg_off,
                                                                             seg_decay, n_seg, tab, rows, d, tab_span,
                                                                             rows_sorted, n_rows, part, lr, beta1, beta2, eps,
                                                                             bc1, bc2_sqrt, grad_scale);
@@ -295,7 +295,7 @@ extern "C" int srk_adam_step(float* param, const float* grad, float* exp_avg, fl
   SRK_REQUIRE(n_seg >= 1 && step >= 1, "adam: need >= 1 segment and step >= 1");
   float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-  adam_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n,
+  srk_launch(adam_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n,
                                                                    seg_off, seg_decay,
                                                                    n_seg, lr, beta1, beta2, eps, bc1, bc2_sqrt, grad_scale);
   SRK_LAUNCH_CHECK();

@@ -203,7 +203,7 @@ extern "C" int srk_mix_logp_fwd(const float* Zall, long long head_stride, long l
   if (B <= 0) return SRK_OK;
   MixArgs m;
   SRK_TRY(fill_args(m, const_cast<float*>(Zall), nullptr, head_stride, ldz, lse, alpha, K, B, V));
-  mix_logp_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(m, out, ldo);
+  srk_launch(mix_logp_kernel, B, 512, 0, (cudaStream_t)stream, m, out, ldo);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -211,7 +211,7 @@ extern "C" int srk_mix_logp_fwd(const float* Zall, long long head_stride, long l
 extern "C" int srk_mix_loss_fwd(const float* nll, const float* alpha, int K, int B, float* loss_out, void* stream) {
   MixArgs m;
   SRK_TRY(fill_args(m, nullptr, nullptr, 0, 0, nullptr, alpha, K, B, 0));
-  mix_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nll, m, loss_out);
+  srk_launch(mix_loss_kernel, 1, 1024, 0, (cudaStream_t)stream, nll, m, loss_out);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -223,7 +223,7 @@ extern "C" int srk_mix_bwd(float* Zall, float* Zlo_all, long long head_stride, l
   SRK_REQUIRE((G != nullptr) != (labels != nullptr), "mix_bwd: give either G or labels (+ gscale)");
   MixArgs m;
   SRK_TRY(fill_args(m, Zall, Zlo_all, head_stride, ldz, lse, alpha, K, B, V));
-  mix_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(m, G, ldg, labels, gscale, scale, rsum);
+  srk_launch(mix_bwd_kernel, B, 512, 0, (cudaStream_t)stream, m, G, ldg, labels, gscale, scale, rsum);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -231,7 +231,7 @@ extern "C" int srk_mix_bwd(float* Zall, float* Zlo_all, long long head_stride, l
 extern "C" int srk_mix_alpha_bwd(const float* rsum, const float* alpha, int K, int B, float* dalpha, void* stream) {
   MixArgs m;
   SRK_TRY(fill_args(m, nullptr, nullptr, 0, 0, nullptr, alpha, K, B, 0));
-  mix_alpha_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rsum, m, dalpha);
+  srk_launch(mix_alpha_bwd_kernel, 1, 256, 0, (cudaStream_t)stream, rsum, m, dalpha);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -282,7 +282,7 @@ extern "C" int srk_readout_fwd(const float* F, const float* u, const float* v, c
                                void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (B <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (readout_fwd_kernel<NC><<<row_grid(B), 256, 0, (cudaStream_t)stream>>>(F, u, v, we, seg, last, B, d,
+  SRK_DISPATCH_NC(d, (srk_launch(readout_fwd_kernel<NC>, row_grid(B), 256, 0, (cudaStream_t)stream, F, u, v, we, seg, last, B, d,
                                                                                             with_last, e, ms, sr_in)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -293,8 +293,7 @@ extern "C" int srk_readout_bwd(const float* F, float* u, float* v, const float* 
                                int with_last, float* dF, float* dwe, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (B <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (readout_bwd_kernel<NC><<<row_grid(B), 256, 0, (cudaStream_t)stream>>>(
-                         F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe)));
+  SRK_DISPATCH_NC(d, (srk_launch(readout_bwd_kernel<NC>, row_grid(B), 256, 0, (cudaStream_t)stream, F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -303,7 +302,7 @@ extern "C" int srk_ce_rows_fwd(float* Z, long long ldz, const int* labels, int B
                                float* nll, void* stream) {
   if (B <= 0) return SRK_OK;
   SRK_REQUIRE(V > 0, "ce_rows_fwd: empty catalog");
-  ce_rows_fwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, V, write_logp, lse, nll);
+  srk_launch(ce_rows_fwd_kernel, B, 512, 0, (cudaStream_t)stream, Z, ldz, labels, V, write_logp, lse, nll);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -311,7 +310,7 @@ extern "C" int srk_ce_rows_fwd(float* Z, long long ldz, const int* labels, int B
 extern "C" int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale,
                                float scale, int B, int V, int z_is_logp, float* Zlo, void* stream) {
   if (B <= 0) return SRK_OK;
-  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp, Zlo, 0);
+  srk_launch(ce_rows_bwd_kernel, B, 512, 0, (cudaStream_t)stream, Z, ldz, labels, lse, gscale, scale, B, V, z_is_logp, Zlo, 0);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -319,7 +318,7 @@ extern "C" int srk_ce_rows_bwd(float* Z, long long ldz, const int* labels, const
 extern "C" int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V,
                             float* DZ, long long lddz, float* DZlo, void* stream) {
   if (B <= 0) return SRK_OK;
-  logp_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(LP, ldlp, G, ldg, scale, V, DZ, lddz, DZlo);
+  srk_launch(logp_bwd_kernel, B, 512, 0, (cudaStream_t)stream, LP, ldlp, G, ldg, scale, V, DZ, lddz, DZlo);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -327,7 +326,7 @@ extern "C" int srk_logp_bwd(const float* LP, long long ldlp, const float* G, lon
 extern "C" int srk_ce_rows_bwd_cols(float* Z, long long ldz, const int* labels, const float* lse, const float* gscale,
                                     float scale, int B, int col0, int ncols, float* Zlo, void* stream) {
   if (B <= 0 || ncols <= 0) return SRK_OK;
-  ce_rows_bwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(Z, ldz, labels, lse, gscale, scale, B, ncols, 0, Zlo, col0);
+  srk_launch(ce_rows_bwd_kernel, B, 512, 0, (cudaStream_t)stream, Z, ldz, labels, lse, gscale, scale, B, ncols, 0, Zlo, col0);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -205,7 +205,7 @@ inline int session_grid(int B) {
 
 extern "C" int srk_transpose(const float* X, int rows, int cols, float* Y, void* stream) {
   if (rows <= 0 || cols <= 0) return SRK_OK;
-  transpose_kernel<<<dim3(srk_cdiv(cols, 32), srk_cdiv(rows, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, rows, cols, Y);
+  srk_launch(transpose_kernel, dim3(srk_cdiv(cols, 32), srk_cdiv(rows, 32)), dim3(32, 8), 0, (cudaStream_t)stream, X, rows, cols, Y);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -221,8 +221,7 @@ extern "C" int srk_readout_tail_fwd(const float* F, const float* u, const float*
   SRK_REQUIRE((sbh == nullptr) == (sbl == nullptr), "readout_tail_fwd: bf16 outputs come as a pair");
   const size_t smem = (size_t)(RT_THREADS / 32) * 2 * d * sizeof(float);
   SRK_REQUIRE(smem <= 48 * 1024, "readout_tail_fwd: d = %d too wide for the per-warp staging rows", d);
-  SRK_DISPATCH_NC(d, (readout_tail_fwd_kernel<NC><<<session_grid(B), RT_THREADS, smem, (cudaStream_t)stream>>>(
-                         F, u, v, we, WsrT, seg, last, B, d, norm_mode, e, ms, sr_in, s, shat, rn_s, sbh, sbl)));
+  SRK_DISPATCH_NC(d, (srk_launch(readout_tail_fwd_kernel<NC>, session_grid(B), RT_THREADS, smem, (cudaStream_t)stream, F, u, v, we, WsrT, seg, last, B, d, norm_mode, e, ms, sr_in, s, shat, rn_s, sbh, sbl)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -238,8 +237,7 @@ extern "C" int srk_readout_head_bwd(const float* F, const float* we, const float
   SRK_REQUIRE(norm_mode == SRK_NORM_NONE || rn_s != nullptr, "readout_head_bwd: rn_s is required for a normalised head");
   const size_t smem = (size_t)(RT_THREADS / 32) * d * sizeof(float);
   SRK_REQUIRE(smem <= 48 * 1024, "readout_head_bwd: d = %d too wide for the per-warp staging rows", d);
-  SRK_DISPATCH_NC(d, (readout_head_bwd_kernel<NC><<<session_grid(B), RT_THREADS, smem, (cudaStream_t)stream>>>(
-                         F, we, Wsr, seg, last, B, d, norm_mode, s, shat, rn_s, sr_in, e, ms, dshat, u, v, ds, dF, dwe)));
+  SRK_DISPATCH_NC(d, (srk_launch(readout_head_bwd_kernel<NC>, session_grid(B), RT_THREADS, smem, (cudaStream_t)stream, F, we, Wsr, seg, last, B, d, norm_mode, s, shat, rn_s, sr_in, e, ms, dshat, u, v, ds, dF, dwe)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -9,7 +9,10 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include <map>
+#include <mutex>
+
+#include "launch.cuh"
 
 namespace {
 
@@ -52,7 +55,7 @@ struct StageTimer {
   }
   explicit StageTimer(cudaStream_t s) : st(s) {
     const char* e = getenv("SESSREC_STEP_TIMING");
-    mode = e ? atoi(e) : 0;
+    mode = (e && srk_launch_mode() == SRK_LAUNCH_DIRECT) ? atoi(e) : 0;
     if (!mode) return;
     cur = &ring()[counter() % RING];
     if (!cur->made) {
@@ -104,6 +107,11 @@ struct SideStreams {
   }
   // everything enqueued on `to` after this call waits for what is on `from` now
   int order(cudaStream_t from, cudaStream_t to) {
+    const int mode = srk_launch_mode();
+    if (mode == SRK_LAUNCH_UPDATE || mode == SRK_LAUNCH_SKIP) return SRK_OK;     // the graph already holds the edge
+    return order_always(from, to);
+  }
+  int order_always(cudaStream_t from, cudaStream_t to) {
     if (from == to) return SRK_OK;
     cudaEvent_t e = ev[next];
     next = (next + 1) % NE;
@@ -227,13 +235,14 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
 //   [0] embeddings.weight
 //   per layer l (8 slots each, starting at 1 + 8*l): conv1.intra1.{attn_l, attn_r, bias, fc.weight}, conv2.intra1.{...}
 //   then: readout.fc_u.0.weight, readout.fc_u.0.bias, readout.fc_v.0.weight, readout.fc_e.0.weight, fc_sr.0.weight
-extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
-                                      const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed,
-                                      int use_umma, void* workspace, long long workspace_bytes, const float* one_dev,
-                                      float* loss_out, int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat,
-                                      const long long* seg_off_dev, const float* seg_decay_dev, int n_seg, float lr,
-                                      float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase,
-                                      int head_chunks, void* stream) {
+// The step as a sequence of srk_launch() calls.  Re-runnable: depending on the launch context of the calling thread it
+// launches, is captured into a graph, or only re-parameterises the nodes of a captured graph (common.cuh).
+static int step_body(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
+                     const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed, int use_umma,
+                     void* workspace, long long workspace_bytes, const float* one_dev, float* loss_out, int do_adam,
+                     float* exp_avg, float* exp_avg_sq, long long n_flat, const long long* seg_off_dev,
+                     const float* seg_decay_dev, int n_seg, float lr, float beta1, float beta2, float eps, int adam_step,
+                     float grad_scale, int phase, int head_chunks, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   BatchView b;
   SRK_TRY(parse_batch(batch_dev, batch_hdr_host, b));
@@ -253,18 +262,8 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   float* E = P(0);
   auto dcfg = [&](uint32_t site) { srk_dropout c; c.p = dropout_p; c.site = site; c.seed = seed; return c; };
 
-  // phase: 0 = everything; 1 = zero_grad + forward + backward only (no Adam): lets the caller all-reduce the
-  // gradients; 2 = Adam only.
-  if (phase == 2) {
-    return srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2,
-                         eps, adam_step, grad_scale, st);
-  }
+  // with side streams the caller passes our own high-priority stream s[0] and orders it against the user's stream
   SideStreams* ss = side_streams();
-  cudaStream_t caller = st;
-  if (ss) {                                      // the whole step runs on our own high-priority stream
-    SRK_TRY(ss->order(caller, ss->s[0]));
-    st = ss->s[0];
-  }
   StageTimer tm(st);
   // h1..h3: high-priority chains beside the critical path; s2 / s3: weight gradients; s4: catalog-wide bulk passes
   cudaStream_t h1 = ss ? ss->s[1] : st, h2 = ss ? ss->s[2] : st, h3 = ss ? ss->s[3] : st;
@@ -273,7 +272,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   auto order = [&](cudaStream_t from, cudaStream_t to) { return ss ? ss->order(from, to) : (int)SRK_OK; };
   // zero_grad runs beside the forward pass; the first gradient is written after the head's backward
   SRK_TRY(order(st, s4));
-  SRK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_flat, s4));
+  SRK_TRY(srk_zero_async(grads, sizeof(float) * (size_t)n_flat, s4));
   tm.mark("zero_grad");
 
   // ---- forward -------------------------------------------------------------------------------------------
@@ -307,6 +306,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   tm.mark("gather");
   std::vector<LayerRec> layers(L);
   // W_aug = [W ; a_l-contracted rows] and w_r depend on the parameters only: built beside the gather (s2)
+  SRK_TRY(order(st, s2));                        // after the previous step's optimizer update
   for (int l = 0; l < L; ++l) {
     LayerRec& R = layers[l];
     R.n_inst = M > 0 ? 2 : 0;
@@ -450,6 +450,16 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   SRK_TRY(srk_mean(nll, B, loss_out, st));
 
   tm.mark("score_fwd+lse");
+  // ---- forward / backward boundary: every side stream has been joined into `st` -------------------------------------
+  // The forward half is always launched kernel by kernel (the GPU starts working while the host is still enqueueing);
+  // the backward half is what gets captured into / replayed from a CUDA graph (see srk_msgifsr_train_step).
+  if (SrkLaunchCtx* lc = srk_get_launch_ctx()) {
+    if (lc->mode_after_boundary == SRK_LAUNCH_CAPTURE) {
+      SRK_CUDA(cudaStreamBeginCapture(lc->capture_stream, cudaStreamCaptureModeThreadLocal));
+      lc->capturing = true;
+    }
+    lc->mode = lc->mode_after_boundary;
+  }
   // ---- backward ------------------------------------------------------------------------------------------
   const int de_parts = flash ? srk_flash_ce_bwd_parts(B) : 1;
   float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;
@@ -458,7 +468,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   if (flash) {
     SRK_TRY(srk_flash_ce_bwd(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, b.labels, lse, one_dev, dshat, dEhat, st));
   } else if (umma) {
-    SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
+    SRK_TRY(srk_zero_async(dshat, sizeof(float) * (size_t)B * d, st));
     // Backward of the head, chunked over catalog columns so that each chunk's dZ hi/lo pair (2 x B x Vc x 4 bytes) is
     // still L2-resident when the two tensor-core GEMMs read it (the whole pair, 2 x 88 MB at cfg1, is not).
     int chunks = head_chunks < 1 ? 1 : head_chunks;
@@ -475,19 +485,20 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
       SRK_TRY(srk_umma_gemm(2, nc, d, B, Z + c0, Zlo + c0, ldz, sh, sl, d, dEhat + (size_t)c0 * d, d, 1.0f, 0, 1, st));
     }
   } else {
-    SRK_CUDA(cudaMemsetAsync(dshat, 0, sizeof(float) * (size_t)B * d, st));
+    SRK_TRY(srk_zero_async(dshat, sizeof(float) * (size_t)B * d, st));
     SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, one_dev, 12.0f, B, V, 0, Zlo, st));
-    SRK_CUDA(cudaMemsetAsync(dEhat, 0, sizeof(float) * (size_t)V * d, st));
+    SRK_TRY(srk_zero_async(dEhat, sizeof(float) * (size_t)V * d, st));
     SRK_TRY(gemm(st, B, d, V, Z, ldz, 1, Ehat, d, 1, dshat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
     SRK_TRY(gemm(st, V, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
   }
   tm.mark("ce_bwd+dS+dE");
   // gradients start here: zero_grad (s4) must be complete; the catalog backward (a [V, d] pass) stays on s4 and runs
   // beside the whole encoder backward, it only has to finish before the scatter-add touches the same rows
-  SRK_TRY(order(s4, st));
+  // (zero_grad and the catalog pass on s4 were joined before the head's forward)
   SRK_TRY(order(st, s4));
   SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, de_parts, V, d, SRK_NORM_L2, G(0), s4));
-  if (ss) SRK_CUDA(cudaEventRecord(ss->ev_cat, s4));
+  const bool live = srk_launch_mode() == SRK_LAUNCH_DIRECT || srk_launch_mode() == SRK_LAUNCH_CAPTURE;
+  if (ss && live) SRK_CUDA(cudaEventRecord(ss->ev_cat, s4));
   // Adam in two parts: the table rows this batch did not gather have their final gradient now (the scatter-add only
   // touches gathered rows, and only those rows of E are read again by the backward), so their update - 95 % of the
   // optimizer's bytes - runs on s4 beside the encoder backward; the gathered rows and all other parameters follow at the end
@@ -573,8 +584,8 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
       float* dWaug = ar.f((size_t)ldzel * d);
       float* dwr = ar.f((size_t)H * d);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_CUDA(cudaMemsetAsync(dWaug, 0, sizeof(float) * (size_t)ldzel * d, wsc));
-      SRK_CUDA(cudaMemsetAsync(dwr, 0, sizeof(float) * (size_t)H * d, wsc));
+      SRK_TRY(srk_zero_async(dWaug, sizeof(float) * (size_t)ldzel * d, wsc));
+      SRK_TRY(srk_zero_async(dwr, sizeof(float) * (size_t)H * d, wsc));
       SRK_TRY(mm_tn(wsc, ldzel, d, N, dZel[c], ldzel, I.xs, d, dWaug, d));
       SRK_TRY(mm_tn(wsc, H, d, N, der[c], H, I.xd, d, dwr, d));
       SRK_TRY(srk_gat_prep_bwd(I.W, I.al, I.ar, dWaug, dwr, d, I.gW, I.gal, I.gar, wsc));
@@ -589,7 +600,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
         SRK_REQUIRE(ar.ok, "step: workspace too small");
         SRK_TRY(mm_nn(zs, N, d, ldzel, dZel[c], ldzel, I.Waug, d, tmp, d, 0));
         SRK_TRY(srk_dropout_apply(tmp, pz, (long long)nd, &I.dcs, 0, zs));
-        SRK_CUDA(cudaMemcpyAsync(tmp2, dHpre, sizeof(float) * nd, cudaMemcpyDeviceToDevice, es));
+        SRK_TRY(srk_copy_async(tmp2, dHpre, sizeof(float) * nd, es));
         SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
         SRK_TRY(srk_dropout_apply(tmp2, pe, (long long)nd, &I.dcd, 0, es));
       }
@@ -606,7 +617,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   }
   tm.mark("gat_bwd");
   // catalog backward done (not the early Adam part queued behind it): the scatter-add updates the same table rows
-  if (ss) SRK_CUDA(cudaStreamWaitEvent(st, ss->ev_cat, 0));
+  if (ss && live) SRK_CUDA(cudaStreamWaitEvent(st, ss->ev_cat, 0));
   SRK_TRY(srk_embed_scatter_bwd(E, b.iid, b.perm, b.uoff, b.uid, b.U, b.P, d, SRK_NORM_L2, drop ? &dc_e : nullptr, rnX, dH,
                                 nullptr, G(0), st));
   SRK_TRY(order(s2, st));
@@ -621,7 +632,137 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   }
   tm.mark("adam");
   SRK_TRY(order(s4, st));
-  SRK_TRY(order(st, caller));
   tm.report();
   return SRK_OK;
 }
+
+namespace {
+
+int g_graphs_on = -1;                  // -1: read SESSREC_GRAPH on first use
+long long g_graph_launches = 0;        // steps issued as one cudaGraphLaunch
+long long g_graph_fallbacks = 0;       // update passes that found a different kernel sequence
+
+struct GraphEntry {
+  int seen = 0, fails = 0;
+  bool bad = false;
+  SrkStepGraph g;
+};
+
+}  // namespace
+
+// phase: 0 = everything; 1 = zero_grad + forward + backward only (no Adam): lets the caller all-reduce the gradients;
+// 2 = Adam only.
+//
+// Host cost: the step is ~60 kernels on 7 streams.  Launched one by one that is ~0.36 ms of CPU per step (2.7 us per
+// launch + ~60 event record / wait calls + memsets), more than the GPU needs once several ranks share the host.  After two
+// warm-up steps the sequence is therefore captured ONCE into a CUDA graph (per model configuration); every later step
+// only rewrites the kernel-node parameters (shapes and pointers change with the batch, the sequence does not) and issues
+// one cudaGraphLaunch.  SESSREC_GRAPH=0 disables it; any mismatch falls back to plain launches for that step.
+extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
+                                      const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed,
+                                      int use_umma, void* workspace, long long workspace_bytes, const float* one_dev,
+                                      float* loss_out, int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat,
+                                      const long long* seg_off_dev, const float* seg_decay_dev, int n_seg, float lr,
+                                      float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase,
+                                      int head_chunks, void* stream) {
+  cudaStream_t caller = (cudaStream_t)stream;
+  if (phase == 2) {
+    return srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2,
+                         eps, adam_step, grad_scale, caller);
+  }
+  // The step runs on our own high-priority stream s[0] (the user's stream may be the legacy default stream, which can
+  // neither be prioritised nor captured); it is ordered after / before the user's stream with events.
+  SideStreams* ss0 = side_streams();
+  cudaStream_t run = ss0 ? ss0->s[0] : caller;
+  auto body_on_run = [&]() {
+    return step_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, dropout_p, seed, use_umma, workspace,
+                     workspace_bytes, one_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg,
+                     lr, beta1, beta2, eps, adam_step, grad_scale, phase, head_chunks, (void*)run);
+  };
+  auto body = [&]() {                     // plain launches
+    if (ss0) SRK_TRY(ss0->order_always(caller, run));
+    SRK_TRY(body_on_run());
+    if (ss0) SRK_TRY(ss0->order_always(run, caller));
+    return (int)SRK_OK;
+  };
+  if (g_graphs_on < 0) {
+    const char* e = getenv("SESSREC_GRAPH");
+    g_graphs_on = !(e && e[0] == '0');
+  }
+  const char* timing = getenv("SESSREC_STEP_TIMING");
+  if (!g_graphs_on || side_streams() == nullptr || (timing && timing[0] != '0')) return body();
+
+  static std::mutex mu;
+  static std::map<unsigned long long, GraphEntry> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  SRK_CUDA(cudaGetDevice(&dev));
+  const int has_edges = batch_hdr_host[REL_TAB + 2] > 0;
+  const unsigned long long key = ((unsigned long long)(batch_hdr_host[1] & 0xFFFFF) << 44) | ((unsigned long long)(d & 0x3FF) << 34) |
+                                 ((unsigned long long)(V & 0x3FFFF) << 16) | ((unsigned long long)(dev & 15) << 12) |
+                                 ((unsigned long long)(L & 15) << 8) | ((unsigned long long)(use_umma & 7) << 5) |
+                                 ((unsigned long long)(dropout_p > 0.f) << 4) | ((unsigned long long)(phase & 1) << 3) |
+                                 ((unsigned long long)(do_adam != 0) << 2) | ((unsigned long long)has_edges << 1) |
+                                 (unsigned long long)(head_chunks > 1);
+  GraphEntry& e = cache[key];
+  ++e.seen;
+  if (e.bad || e.seen <= 2) return body();          // warm-up steps also run every one-time cudaFuncSetAttribute
+
+  // forward: plain launches; backward: captured once, afterwards its kernel nodes are re-parameterised and replayed
+  SrkLaunchCtx ctx;
+  ctx.g = &e.g;
+  ctx.capture_stream = run;
+  const bool capture = e.g.exec == nullptr;
+  ctx.mode_after_boundary = capture ? SRK_LAUNCH_CAPTURE : SRK_LAUNCH_UPDATE;
+  SRK_TRY(ss0->order_always(caller, run));
+  srk_set_launch_ctx(&ctx);
+  int rc = body_on_run();
+  srk_set_launch_ctx(nullptr);
+  bool ok = rc == SRK_OK && !ctx.failed;
+  if (capture) {
+    if (ctx.capturing) {
+      const cudaError_t ce = cudaStreamEndCapture(run, &e.g.graph);
+      ok = ok && ce == cudaSuccess && e.g.graph != nullptr && cudaGraphInstantiate(&e.g.exec, e.g.graph, 0) == cudaSuccess;
+    } else {
+      ok = false;
+    }
+    if (!ok) {
+      cudaGetLastError();
+      e.g.destroy();
+      e.bad = true;
+    }
+  } else {
+    ok = ok && ctx.cursor == e.g.nodes.size();
+    if (!ok) {
+      ++g_graph_fallbacks;
+      if (++e.fails > 3) {                            // this configuration keeps changing its kernel sequence
+        e.g.destroy();
+        e.bad = true;
+      }
+    }
+  }
+  if (ok) {
+    SRK_CUDA(cudaGraphLaunch(e.g.exec, run));
+    ++g_graph_launches;
+  } else {
+    // The forward half is already enqueued.  Re-run the step's bookkeeping with the forward launches dropped and launch
+    // the backward half kernel by kernel.
+    SrkLaunchCtx redo;
+    redo.mode = SRK_LAUNCH_SKIP;
+    redo.mode_after_boundary = SRK_LAUNCH_DIRECT;
+    srk_set_launch_ctx(&redo);
+    rc = body_on_run();
+    srk_set_launch_ctx(nullptr);
+    if (rc != SRK_OK) return rc;
+  }
+  SRK_TRY(ss0->order_always(run, caller));
+  return SRK_OK;
+}
+
+extern "C" int srk_set_graph_mode(int on) {
+  g_graphs_on = on ? 1 : 0;
+  return SRK_OK;
+}
+
+extern "C" long long srk_graph_launches(void) { return g_graph_launches; }
+extern "C" long long srk_graph_fallbacks(void) { return g_graph_fallbacks; }

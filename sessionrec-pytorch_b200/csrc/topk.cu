@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(TK_THREADS) topk_rows_kernel(const float* __re
 extern "C" int srk_topk_rows(const float* Z, long long ldz, int B, int V, int k, int* out_idx, float* out_val, void* stream) {
   if (B <= 0) return SRK_OK;
   SRK_REQUIRE(k >= 1 && k <= 256 && k <= V, "topk: need 1 <= k <= min(256, V), got k=%d V=%d", k, V);
-  topk_rows_kernel<<<B, TK_THREADS, 0, (cudaStream_t)stream>>>(Z, ldz, V, k, out_idx, out_val);
+  srk_launch(topk_rows_kernel, B, TK_THREADS, 0, (cudaStream_t)stream, Z, ldz, V, k, out_idx, out_val);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

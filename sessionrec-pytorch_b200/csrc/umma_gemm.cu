@@ -476,7 +476,7 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
   }
   dim3 grid(srk_cdiv(N, p.BN), srk_cdiv(M, BM), S);
   SRK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "umma_gemm: grid too large");
-  umma_gemm_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, p);
+  srk_launch(umma_gemm_kernel, grid, THREADS, smem, (cudaStream_t)stream, mAh, mAl, mBh, mBl, p);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -487,7 +487,7 @@ extern "C" int srk_split_tf32(const float* X, long long ldx, int rows, int cols,
   if (total <= 0) return SRK_OK;
   long long g = (total + 255) / 256;
   if (g > 148LL * 16) g = 148LL * 16;
-  split_tf32_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(X, ldx, rows, cols, hi, lo, ldo);
+  srk_launch(split_tf32_kernel, (int)g, 256, 0, (cudaStream_t)stream, X, ldx, rows, cols, hi, lo, ldo);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
@@ -525,9 +525,9 @@ extern "C" int srk_umma_score_fwd(int M, int N, int K, const float* Ahi, const f
     attr_set = true;
   }
   const int ntiles = p.ntm * p.ntn;
-  umma_score_fwd_kernel<<<ntiles < sms ? ntiles : sms, FWD_THREADS, smem, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, p);
+  srk_launch(umma_score_fwd_kernel, ntiles < sms ? ntiles : sms, FWD_THREADS, smem, (cudaStream_t)stream, mAh, mAl, mBh, mBl, p);
   SRK_LAUNCH_CHECK();
-  lse_finalize_kernel<<<srk_cdiv((long long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(p.part, p.zlab, M, 2 * p.ntn, lse, nll);
+  srk_launch(lse_finalize_kernel, srk_cdiv((long long)M * 32, 256), 256, 0, (cudaStream_t)stream, p.part, p.zlab, M, 2 * p.ntn, lse, nll);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -238,6 +238,41 @@ def test_native_step_matches_staged_composition(pkg, p):
         assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)   # Adam turns 1e-9 gradient noise (atomics) into lr-sized steps
 
 
+@pytest.mark.parametrize('p', [0.0, 0.2])
+def test_native_step_graph_replay_matches_plain_launches(pkg, p):
+    """The native step replayed as ONE CUDA graph (kernel-node parameters rewritten per batch: different batch shapes,
+    pointers, dropout seeds) against the same steps issued as plain launches: same losses, same parameters."""
+    from sessionrec_pytorch_b200._lib import lib
+    L = lib().functions
+    c = TRAINS['msgifsr_k1']
+    nsteps = 8
+    res = []
+    try:
+        for graphs in (1, 0):
+            L['srk_set_graph_mode'](graphs)
+            g0, f0 = L['srk_graph_launches'](), L['srk_graph_fallbacks']()
+            m = make_model(pkg, c, dropout=p)
+            m.train()
+            m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+            losses = []
+            for it in range(nsteps):
+                m.set_dropout_seed(4242 + it)
+                lo = (it % 3) * c['bs']
+                # batches of different sizes: the graph is captured on one shape and replayed on others
+                b, _ = make_batch(pkg, c, c['samples'][lo:lo + c['bs'] - 3 * (it % 2)])
+                losses.append(float(m.train_step(b)))
+            res.append((m, losses, L['srk_graph_launches']() - g0, L['srk_graph_fallbacks']() - f0))
+    finally:
+        L['srk_set_graph_mode'](1)
+    (m1, l1, n1, fb1), (m2, l2, n2, _) = res
+    assert n1 >= nsteps - 3 and n2 == 0, (n1, n2)          # two warm-up steps, then capture + replays
+    assert fb1 == 0, fb1
+    for a, b_ in zip(l1, l2):
+        assert abs(a - b_) <= 2e-6 * abs(b_), (l1, l2)
+    for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert_close(f'graph vs plain {n}', q1, q2, rtol=1e-4, floor=0.5)
+
+
 def test_native_step_two_layers_and_sgemm_head(pkg):
     c = MODELS['msgifsr_k1_inflate_L2']
     outs = []
