@@ -318,9 +318,10 @@ int srk_adam_step_split(float* param, const float* grad, float* exp_avg, float* 
  * zero_grad + forward + nll_loss + backward (+ Adam) enqueued by ONE host call from a caller-provided device
  * workspace (srk_msgifsr_workspace_bytes).  slot_off_host: float offsets of the parameters inside the flat buffers,
  * order documented in csrc/step.cu.  phase 0 = all, 1 = up to the gradients (data parallel: all-reduce, then) 2 = Adam. */
-/* CUDA-graph replay of the native step (default on, SESSREC_GRAPH=0 turns it off): after two warm-up steps per model
- * configuration the ~60 launches of a step are captured once; later steps only rewrite the kernel-node parameters and
- * issue one cudaGraphLaunch.  srk_set_graph_mode(0 / 1) overrides the environment; the counters tell how many steps were
+/* CUDA-graph replay of the native step's backward half: after two warm-up steps per model configuration its ~40
+ * launches (7 streams) are captured once; later steps only rewrite the kernel-node parameters and issue one
+ * cudaGraphLaunch.  Default: on for data-parallel steps (phase 1), where the ranks share the host CPU; SESSREC_GRAPH=1
+ * forces it for every step, SESSREC_GRAPH=0 turns it off.  srk_set_graph_mode(0 / 1) overrides the environment; the counters tell how many steps were
  * replayed and how many update passes had to fall back to plain launches. */
 int srk_set_graph_mode(int on);
 long long srk_graph_launches(void);

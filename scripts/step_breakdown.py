@@ -8,10 +8,10 @@ rows = list(csv.DictReader(lines))
 def us(x):
     t = float(x['Metric Value'].replace(',', '')); u = x['Metric Unit']
     return t / 1e3 if u == 'ns' else (t * 1e3 if u == 'ms' else t)
-idx = [i for i, x in enumerate(rows) if 'catalog_prep_fwd' in x['Kernel Name'] or 'gather_fwd_kernel' in x['Kernel Name']]
-ad = [i for i, x in enumerate(rows) if 'adam_kernel' in x['Kernel Name']]
-e = ad[-1]; s = max(i for i in idx if i < e and (not ad[:-1] or i > ad[-2]))
-s = min(i for i in idx if i > (ad[-2] if len(ad) > 1 else -1))
+# one step = from one "first kernel of a step" to the launch before the next one
+first = 'renorm_rows_kernel' if any('renorm_rows_kernel' in x['Kernel Name'] for x in rows) else 'catalog_prep_fwd'
+starts = [i for i, x in enumerate(rows) if first in x['Kernel Name']]
+s, e = starts[-2], starts[-1] - 1
 agg = collections.OrderedDict(); tot = 0
 detail = '-v' in sys.argv
 for x in rows[s:e + 1]:
