@@ -1,3 +1,5 @@
+// Build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o scripts/exp/graph_update_cost scripts/exp/graph_update_cost.cu
+// Measured on B200 (r1s): 60 direct launches 162.7 us, 60 node updates + cudaGraphLaunch 59.6 us, cudaGraphLaunch alone 0.9 us.
 // Host cost of (a) 60 direct kernel launches vs (b) 60 x cudaGraphExecKernelNodeSetParams + one cudaGraphLaunch.
 #include <chrono>
 #include <cstdio>
