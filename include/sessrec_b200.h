@@ -321,9 +321,12 @@ int srk_adam_step_split(float* param, const float* grad, float* exp_avg, float* 
 /* CUDA-graph replay of the native step's backward half: after two warm-up steps per model configuration its ~40
  * launches (7 streams) are captured once; later steps only rewrite the kernel-node parameters and issue one
  * cudaGraphLaunch.  Default: on for data-parallel steps (phase 1), where the ranks share the host CPU; SESSREC_GRAPH=1
- * forces it for every step, SESSREC_GRAPH=0 turns it off.  srk_set_graph_mode(0 / 1) overrides the environment; the counters tell how many steps were
+ * forces it for every step, SESSREC_GRAPH=0 turns it off.  srk_set_graph_mode(0 never / 1 always / 2 auto) overrides the environment; the counters tell how many steps were
  * replayed and how many update passes had to fall back to plain launches. */
 int srk_set_graph_mode(int on);
+/* Test hook: the nth_update-th next replay finds a "different kernel sequence" half-way through its update pass and must
+ * fall back to plain launches for the backward half (0 = off). */
+int srk_graph_inject_mismatch(int nth_update);
 long long srk_graph_launches(void);
 long long srk_graph_fallbacks(void);
 long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int d, int L);

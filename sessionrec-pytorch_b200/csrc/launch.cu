@@ -14,7 +14,7 @@ int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
   ++g_srk_launches;
   if (c && c->mode == SRK_LAUNCH_UPDATE) {
     if (c->failed) return SRK_OK;                       // the step will be re-run with plain launches
-    if (c->cursor >= c->g->nodes.size() || c->g->nodes[c->cursor].func != func) {
+    if (c->cursor >= c->g->nodes.size() || c->g->nodes[c->cursor].func != func || c->cursor == c->fail_at) {
       c->failed = true;
       return SRK_OK;
     }

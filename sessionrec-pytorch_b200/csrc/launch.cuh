@@ -31,6 +31,7 @@ struct SrkLaunchCtx {
   int mode_after_boundary = SRK_LAUNCH_DIRECT;
   cudaStream_t capture_stream = nullptr;
   bool capturing = false;
+  size_t fail_at = (size_t)-1;          // test hook: pretend the kernel sequence differs at this node
 };
 SrkLaunchCtx* srk_get_launch_ctx();
 

@@ -641,6 +641,7 @@ namespace {
 int g_graphs_on = -1;                  // -1: read SESSREC_GRAPH on first use; 0 never, 1 always, 2 auto (data-parallel steps)
 long long g_graph_launches = 0;        // steps issued as one cudaGraphLaunch
 long long g_graph_fallbacks = 0;       // update passes that found a different kernel sequence
+int g_inject_mismatch = 0;             // test hook: the n-th next update pass is made to fail half-way (0 = off)
 
 struct GraphEntry {
   int seen = 0, fails = 0;
@@ -718,6 +719,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   ctx.capture_stream = run;
   const bool capture = e.g.exec == nullptr;
   ctx.mode_after_boundary = capture ? SRK_LAUNCH_CAPTURE : SRK_LAUNCH_UPDATE;
+  if (!capture && g_inject_mismatch > 0 && --g_inject_mismatch == 0) ctx.fail_at = e.g.nodes.size() / 2;
   SRK_TRY(ss0->order_always(caller, run));
   srk_set_launch_ctx(&ctx);
   int rc = body_on_run();
@@ -764,7 +766,12 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
 }
 
 extern "C" int srk_set_graph_mode(int on) {
-  g_graphs_on = on ? 1 : 0;
+  g_graphs_on = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 never, 1 always, 2 auto (data-parallel steps only)
+  return SRK_OK;
+}
+
+extern "C" int srk_graph_inject_mismatch(int nth_update) {
+  g_inject_mismatch = nth_update;
   return SRK_OK;
 }
 

@@ -238,18 +238,21 @@ def test_native_step_matches_staged_composition(pkg, p):
         assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)   # Adam turns 1e-9 gradient noise (atomics) into lr-sized steps
 
 
-@pytest.mark.parametrize('p', [0.0, 0.2])
-def test_native_step_graph_replay_matches_plain_launches(pkg, p):
-    """The native step replayed as ONE CUDA graph (kernel-node parameters rewritten per batch: different batch shapes,
-    pointers, dropout seeds) against the same steps issued as plain launches: same losses, same parameters."""
+@pytest.mark.parametrize('p,inject', [(0.0, 0), (0.2, 0), (0.2, 3)])
+def test_native_step_graph_replay_matches_plain_launches(pkg, p, inject):
+    """The native step with its backward half replayed as ONE CUDA graph (kernel-node parameters rewritten per batch:
+    different batch shapes, pointers, dropout seeds) against the same steps issued as plain launches: same losses, same
+    parameters.  inject > 0: one replay hits a (forced) kernel-sequence mismatch half-way and must finish the step with
+    plain launches."""
     from sessionrec_pytorch_b200._lib import lib
     L = lib().functions
     c = TRAINS['msgifsr_k1']
-    nsteps = 8
+    nsteps = 12
     res = []
     try:
         for graphs in (1, 0):
             L['srk_set_graph_mode'](graphs)
+            L['srk_graph_inject_mismatch'](inject if graphs else 0)      # one replay must fall back half-way
             g0, f0 = L['srk_graph_launches'](), L['srk_graph_fallbacks']()
             m = make_model(pkg, c, dropout=p)
             m.train()
@@ -263,10 +266,12 @@ def test_native_step_graph_replay_matches_plain_launches(pkg, p):
                 losses.append(float(m.train_step(b)))
             res.append((m, losses, L['srk_graph_launches']() - g0, L['srk_graph_fallbacks']() - f0))
     finally:
-        L['srk_set_graph_mode'](1)
+        L['srk_set_graph_mode'](2)                      # back to the default (replay for data-parallel steps only)
+        L['srk_graph_inject_mismatch'](0)
     (m1, l1, n1, fb1), (m2, l2, n2, _) = res
-    assert n1 >= nsteps - 3 and n2 == 0, (n1, n2)          # two warm-up steps, then capture + replays
-    assert fb1 == 0, fb1
+    # two batch sizes = two graphs; each takes two warm-up steps, then capture (+ launch) and replays
+    assert n1 >= nsteps - 4 - (1 if inject else 0) and n2 == 0, (n1, n2)
+    assert fb1 == (1 if inject else 0), fb1
     for a, b_ in zip(l1, l2):
         assert abs(a - b_) <= 2e-6 * abs(b_), (l1, l2)
     for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
