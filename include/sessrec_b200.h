@@ -140,6 +140,9 @@ int srk_renorm_rows(float* E, const int* uid, int U, int d, float max_norm, void
  * Y = norm_mode(X) row-wise over [R, d] (ldx/ldy row strides); rnorm[R] keeps ||x||. */
 int srk_rownorm_fwd(const float* X, long long ldx, int R, int d, int norm_mode, float* Y, long long ldy, float* rnorm,
                     void* stream);
+/* srk_rownorm_fwd + srk_split_bf16 of the result in one launch: Ybf_hi / Ybf_lo [R, d] (dense) = bf16 hi / lo of Y. */
+int srk_rownorm_split_fwd(const float* X, long long ldx, int R, int d, int norm_mode, float* Y, long long ldy, float* rnorm,
+                          uint16_t* Ybf_hi, uint16_t* Ybf_lo, void* stream);
 int srk_rownorm_bwd(const float* X, long long ldx, const float* Y, long long ldy, const float* rnorm, const float* dY,
                     long long lddy, int R, int d, int norm_mode, float* dX, long long lddx, int accumulate,
                     void* stream);

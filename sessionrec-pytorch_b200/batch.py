@@ -21,6 +21,11 @@ def _rel_name(code):
 
 
 class SessionBatch:
+    """Header fields (B, K, node / edge counts) are plain ints read from the host copy of the header; the per-section
+    tensor views (`labels`, `types[k][...]`, `rels[r][...]`) are built on first use - the native training step only needs
+    `buf` + `hdr`, and `.to(device)` sits inside the timed end-to-end loop."""
+    _LAZY = ('labels', 'row_seg', 'row_type', 'row_node', 'types', 'rels')
+
     def __init__(self, buf, hdr=None):
         self.buf = buf                                            # int32 tensor (host or device)
         self.hdr = np.asarray(buf[:_DATA0].cpu().numpy() if hdr is None else hdr).copy()
@@ -28,6 +33,17 @@ class SessionBatch:
         assert int(h[0]) == _MAGIC, 'not a SessionBatch buffer'
         self.B, self.K, self.R = int(h[1]), int(h[3]), int(h[6])
         self.kind = 'session' if int(h[2]) == 0 else 'ccs'
+        self.N1 = int(h[_TYPE_TAB])                               # nodes of type s1
+        self.M1 = int(h[_REL_TAB + 2]) if int(h[5]) > 0 else 0    # edges of the first relation
+
+    def __getattr__(self, name):
+        if name in SessionBatch._LAZY:
+            self._build_views()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _build_views(self):
+        h = self.hdr
         self.labels = self._sec(h[7], self.B)
         self.row_seg = self._sec(h[8], self.B + 1)
         self.row_type = self._sec(h[9], self.R)

@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(ROW_THREADS) catalog_prep_fwd_kernel(float* __
 template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) rownorm_fwd_kernel(const float* __restrict__ X, long long ldx, int R, int d,
                                                                   int mode, float* __restrict__ Y, long long ldy,
-                                                                  float* __restrict__ rnorm) {
+                                                                  float* __restrict__ rnorm, uint16_t* __restrict__ Bhi,
+                                                                  uint16_t* __restrict__ Blo) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rownorm_fwd_kernel(const float* _
     float n = row_normalize(x, y, mode);
     row_store(y, Y + r * ldy, d, lane);
     if (rnorm && lane == 0) rnorm[r] = n;
+    if (Bhi) row_store_bf16_split(y, Bhi + (long long)r * d, Blo + (long long)r * d, d, lane);     // dense [R, d] pair
   }
 }
 
@@ -326,7 +328,19 @@ extern "C" int srk_rownorm_fwd(const float* X, long long ldx, int R, int d, int 
   if (R <= 0) return SRK_OK;
   SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "rownorm: row strides must be multiples of 4");
   SRK_DISPATCH_NC(d, (srk_launch(rownorm_fwd_kernel<NC>, row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream, X, ldx, R, d, norm_mode,
-                                                                                                      Y, ldy, rnorm)));
+                                 Y, ldy, rnorm, nullptr, nullptr)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_rownorm_split_fwd(const float* X, long long ldx, int R, int d, int norm_mode, float* Y, long long ldy,
+                                     float* rnorm, uint16_t* Ybf_hi, uint16_t* Ybf_lo, void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  if (R <= 0) return SRK_OK;
+  SRK_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "rownorm: row strides must be multiples of 4");
+  SRK_REQUIRE(Ybf_hi != nullptr && Ybf_lo != nullptr, "rownorm_split: the bf16 pair is required");
+  SRK_DISPATCH_NC(d, (srk_launch(rownorm_fwd_kernel<NC>, row_grid(R), ROW_THREADS, 0, (cudaStream_t)stream, X, ldx, R, d, norm_mode,
+                                 Y, ldy, rnorm, Ybf_hi, Ybf_lo)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -419,8 +419,8 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   } else {
     SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, 1, e, ms, sr_in, st));
     SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
-    SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
-    if (flash) SRK_TRY(srk_split_bf16(shat, d, B, d, Sbh, Sbl, d, st));
+    if (flash) SRK_TRY(srk_rownorm_split_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, Sbh, Sbl, st));
+    else SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
   }
   tm.mark("readout_fwd");
   // scoring head + CE (needs the catalog pass)
@@ -447,7 +447,6 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
     SRK_TRY(gemm(st, B, V, d, shat, d, 1, Ehat, 1, d, Z, ldz, nullptr, nullptr, nullptr, nullptr, 12.0f));
     SRK_TRY(srk_ce_rows_fwd(Z, ldz, b.labels, B, V, 0, lse, nll, st));
   }
-  SRK_TRY(srk_mean(nll, B, loss_out, st));
 
   tm.mark("score_fwd+lse");
   // ---- forward / backward boundary: every side stream has been joined into `st` -------------------------------------
@@ -460,6 +459,10 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
     }
     lc->mode = lc->mode_after_boundary;
   }
+  // the backward needs the row log-sum-exps, not their mean: the loss reduction runs beside the head's backward (s2 is
+  // joined before the optimizer step)
+  SRK_TRY(order(st, s2));
+  SRK_TRY(srk_mean(nll, B, loss_out, s2));
   // ---- backward ------------------------------------------------------------------------------------------
   const int de_parts = flash ? srk_flash_ce_bwd_parts(B) : 1;
   float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;

@@ -264,9 +264,8 @@ class MSGIFSR(SessRecModule):
         if st is None or st['flat'] is not fp:
             st = self._native = dict(flat=fp, slots=self._slot_offsets(), ws=None, ws_bytes=0,
                                      loss=torch.zeros((), dtype=torch.float32, device=fp.data.device))
-        t, rel = batch.types[1], batch.rels[0]
         L = lib()
-        need = L.call('srk_msgifsr_workspace_bytes', batch.B, t['N'], rel['M'], self.num_items, self.embedding_dim,
+        need = L.call('srk_msgifsr_workspace_bytes', batch.B, batch.N1, batch.M1, self.num_items, self.embedding_dim,
                       self.num_layers)
         if need > st['ws_bytes']:
             st['ws_bytes'] = int(need * 1.2)
