@@ -14,14 +14,21 @@
 //
 // Work decomposition: CTA = (128-session tile, contiguous range of 128-row catalog tiles); grid = #session tiles x
 // #ranges ~ one CTA per SM.  Roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2-9
-// = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
-// Shared memory (all tiles are 128 rows x 128-byte swizzled rows, SWIZZLE_128B, so the SAME bytes serve as a K-major
-// operand of one product and as an MN-major operand of another):
+// = soft-max math on the logit tile (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4); the backward kernel
+// adds warps 10-13, which drain the dE / dS accumulators through a 16 KB staging buffer and TMA tensor stores.
+// Shared memory: operand tiles are 128 rows of swizzled 128-byte (64 bf16, SWIZZLE_128B) or 64-byte (32 bf16,
+// SWIZZLE_64B, when d is a multiple of 32 but not of 64) column chunks, so the SAME bytes serve as a K-major operand of
+// one product and as an MN-major operand of another:
 //   S  = shat tile   hi/lo  [128 b x d]   resident         A (K-major) of the logit tile, B (MN-major) of dE
+//                                                          (forward: held in TMEM instead, TS-form MMA)
 //   E  = Ehat tile   hi/lo  [128 v x d]   1-4 stages       B (K-major) of the logit tile, B (MN-major) of dS
-//   D  = dZ tile     hi/lo  [128 b x 128 v]                A (K-major) of dS, A (MN-major) of dE; doubles as the
-//                                                          fp32 staging area of the TMA stores of dE / dS
-// TMEM (512 columns): logit tile x 2 (double buffer) | dS accumulator (d <= 128 columns) | dE accumulator.
+//   D  = dZ tile     hi/lo  [128 b x 128 v]                A (K-major) of dS, A (MN-major) of dE (the math warps keep dZ
+//                                                          in registers until the previous tile's products have read D)
+// TMEM (512 columns): logit tile x 2 (double buffer) | dS accumulator (d <= 128 columns) | dE accumulator
+// (forward: logit tile x 2 | shat hi | shat lo).
+// What bounds the kernels (clock-stamp traces, srk_flash_ce_set_trace + scripts/head_trace.py): forward = L2 -> SM
+// bandwidth of the catalog tiles (each is pulled by every session-tile CTA); backward = shared-memory operand bandwidth
+// of the 66 MMAs per tile (480 KB at 128 B/clk against 3456 cycles of tensor work).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
