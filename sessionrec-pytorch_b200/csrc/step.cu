@@ -199,6 +199,7 @@ struct InstRec {
   const float *W, *al, *ar;
   float *gW, *gal, *gar, *gbias;
   float *Waug, *wr, *xs, *xd;
+  float *Wh, *Wl, *xh, *xl;    // TF32 hi / lo of W_aug and of the source copy x_s (tensor-core projections)
   srk_dropout dcs, dcd;
   bool drop;
 };
@@ -228,6 +229,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
   fl += 8LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
+  fl += (long long)L * 2 * (2 * ldzel * d + 2LL * N * d) + 2 * (2LL * N * ldzel);     // opt-in tensor-core projections: hi / lo copies
   return fl * 5 + (1 << 20);                               // floats -> bytes with 25% head-room + alignment slack
 }
 
@@ -305,6 +307,11 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
 
   tm.mark("gather");
   std::vector<LayerRec> layers(L);
+  // The N x d x 8d projections of the GAT layers (Z | el = x_s W_aug^T, its data gradient dZel W_aug and its weight gradient
+  // dZel^T x_s) run on the tcgen05 3xTF32 GEMM instead of the fp32 CUDA-core kernel (measured 0.441 -> 0.419 ms/step at
+  // cfg1 for the two on the critical path); SESSREC_TC_ENCODER=0 switches back.
+  const char* tce = getenv("SESSREC_TC_ENCODER");
+  const bool tc_enc = umma && d <= 128 && d % 32 == 0 && !(tce && tce[0] == '0');
   // W_aug = [W ; a_l-contracted rows] and w_r depend on the parameters only: built beside the gather (s2)
   SRK_TRY(order(st, s2));                        // after the previous step's optimizer update
   for (int l = 0; l < L; ++l) {
@@ -319,6 +326,13 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       I.wr = ar.f((size_t)H * d);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
       SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, s2));
+      I.Wh = I.Wl = nullptr;
+      if (tc_enc) {
+        I.Wh = ar.f((size_t)ldzel * d);
+        I.Wl = ar.f((size_t)ldzel * d);
+        SRK_REQUIRE(ar.ok, "step: workspace too small");
+        SRK_TRY(srk_split_tf32(I.Waug, d, ldzel, d, I.Wh, I.Wl, d, s2));
+      }
     }
   }
   // W_sr^T for the fused read-out tail (the lanes read consecutive output columns)
@@ -367,7 +381,15 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       float* er = ar.f((size_t)N * H);
       float* att = ar.f((size_t)(M + 1) * H);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_TRY(linear_nt(zs, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
+      if (tc_enc) {
+        I.xh = ar.f((size_t)N * d);
+        I.xl = ar.f((size_t)N * d);
+        SRK_REQUIRE(ar.ok, "step: workspace too small");
+        SRK_TRY(srk_split_tf32(I.xs, d, N, d, I.xh, I.xl, d, zs));
+        SRK_TRY(srk_umma_gemm(0, N, ldzel, d, I.xh, I.xl, d, I.Wh, I.Wl, d, Zel, ldzel, 1.0f, 0, 1, zs));
+      } else {
+        SRK_TRY(linear_nt(zs, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
+      }
       SRK_TRY(linear_nt(es, N, H, d, I.xd, d, I.wr, er, H));
       srk_gat_inst& g = I.gi;
       memset(&g, 0, sizeof(g));
@@ -580,6 +602,13 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       float* pe = parts + (2 + 2 * c) * nd;      // destination-copy term + identity residual
       InstRec& I = R.inst[c];
       SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, zs));
+      float *zh = nullptr, *zl = nullptr;
+      if (tc_enc) {                               // TF32 hi / lo of dZel, shared by the data and the weight gradient
+        zh = ar.f((size_t)N * ldzel);
+        zl = ar.f((size_t)N * ldzel);
+        SRK_REQUIRE(ar.ok, "step: workspace too small");
+        SRK_TRY(srk_split_tf32(dZel[c], ldzel, N, ldzel, zh, zl, ldzel, zs));
+      }
       SRK_TRY(order(zs, es));
       SRK_TRY(order(zs, wsc));
       // weight gradients
@@ -589,19 +618,31 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       SRK_REQUIRE(ar.ok, "step: workspace too small");
       SRK_TRY(srk_zero_async(dWaug, sizeof(float) * (size_t)ldzel * d, wsc));
       SRK_TRY(srk_zero_async(dwr, sizeof(float) * (size_t)H * d, wsc));
-      SRK_TRY(mm_tn(wsc, ldzel, d, N, dZel[c], ldzel, I.xs, d, dWaug, d));
+      if (tc_enc) {                               // dW_aug[8d + 8, d] = dZel^T x_s, split over the N rows
+        int split = 148 / ((ldzel + 127) / 128);
+        SRK_TRY(srk_umma_gemm(2, ldzel, d, N, zh, zl, ldzel, I.xh, I.xl, d, dWaug, d, 1.0f, 1, split < 1 ? 1 : split, wsc));
+      } else {
+        SRK_TRY(mm_tn(wsc, ldzel, d, N, dZel[c], ldzel, I.xs, d, dWaug, d));
+      }
       SRK_TRY(mm_tn(wsc, H, d, N, der[c], H, I.xd, d, dwr, d));
       SRK_TRY(srk_gat_prep_bwd(I.W, I.al, I.ar, dWaug, dwr, d, I.gW, I.gal, I.gar, wsc));
       // data gradients
+      auto dz_times_waug = [&](float* out) -> int {          // out[N, d] = dZel[N, 8d + 8] W_aug[8d + 8, d]
+        if (!tc_enc) return mm_nn(zs, N, d, ldzel, dZel[c], ldzel, I.Waug, d, out, d, 0);
+        SRK_TRY(srk_zero_async(out, sizeof(float) * (size_t)N * d, zs));
+        int split = 148 / ((N + 127) / 128);
+        if (split < 1) split = 1;
+        return srk_umma_gemm(1, N, d, ldzel, zh, zl, ldzel, I.Wh, I.Wl, d, out, d, 1.0f, 1, split, zs);
+      };
       if (!I.drop) {
-        SRK_TRY(mm_nn(zs, N, d, ldzel, dZel[c], ldzel, I.Waug, d, pz, d, 0));
+        SRK_TRY(dz_times_waug(pz));
         SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, pe, d, 0));
         SRK_TRY(srk_dropout_apply(dHpre, pe, (long long)nd, nullptr, 1, es));            // residual
       } else {
         float* tmp = ar.f(nd);
         float* tmp2 = ar.f(nd);
         SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(mm_nn(zs, N, d, ldzel, dZel[c], ldzel, I.Waug, d, tmp, d, 0));
+        SRK_TRY(dz_times_waug(tmp));
         SRK_TRY(srk_dropout_apply(tmp, pz, (long long)nd, &I.dcs, 0, zs));
         SRK_TRY(srk_copy_async(tmp2, dHpre, sizeof(float) * nd, es));
         SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
