@@ -157,6 +157,9 @@ int srk_expander_combine_bwd(const float* out, const float* rnorm, const float* 
 /* ---- elementwise helpers -------------------------------------------------------------------------------
  * Y = dropout(X) over n elements (flat index = element index); accumulate: Y += dropout_mask * X. */
 int srk_dropout_apply(const float* X, float* Y, long long n, const srk_dropout* drop, int accumulate, void* stream);
+/* Y = dropout(X) plus its TF32 hi / lo split (Yhi + Ylo == Y exactly; operands of srk_umma_gemm) in one launch. */
+int srk_dropout_apply_split(const float* X, float* Y, float* Yhi, float* Ylo, long long n, const srk_dropout* drop,
+                            void* stream);
 int srk_fill(float* X, long long n, float value, void* stream);
 int srk_gather_rows(const float* X, const int* idx, int R, int d, float* Y, long long ldy, void* stream);
 int srk_scatter_add_rows(const float* X, long long ldx, const int* idx, int R, int d, float* Y, void* stream);
@@ -296,6 +299,9 @@ int srk_gat_aggregate_bwd_dst(const srk_gat_inst* inst_host, int n_inst, int N, 
 /* Backward part 2 (per source node of one instance): dZel[u] = [ sum_out att' dO[v] | sum_out dedge ]. */
 int srk_gat_aggregate_bwd_src(const srk_gat_inst* inst_host, int d, const srk_dropout* attn_drop, const float* dHpre,
                               const uint8_t* amax, void* stream);
+/* Same, and additionally writes the TF32 hi / lo split of dZel ([n_src, 8d + 8] each) for srk_umma_gemm. */
+int srk_gat_aggregate_bwd_src_split(const srk_gat_inst* inst_host, int d, const srk_dropout* attn_drop, const float* dHpre,
+                                    const uint8_t* amax, float* dZel_hi, float* dZel_lo, void* stream);
 /* dbias[h, j] += sum_v [amax[v, j] == h] dHpre[v, j]. */
 int srk_gat_bias_bwd(const float* dHpre, const uint8_t* amax, int N, int d, float* dbias, void* stream);
 /* Segment mean over contiguous segments and its backward (msgifsr.py:86-87). */

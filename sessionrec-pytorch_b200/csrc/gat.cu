@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(256) gat_bwd_dst_kernel(const GatParams P, int
 template <int NC>
 __global__ void __launch_bounds__(256) gat_bwd_src_kernel(const srk_gat_inst I, int d, DropCfg dc,
                                                           const float* __restrict__ dHpre,
-                                                          const uint8_t* __restrict__ amax) {
+                                                          const uint8_t* __restrict__ amax, float* __restrict__ Zhi,
+                                                          float* __restrict__ Zlo) {
   const int u = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ldz = H * d + H;
@@ -200,6 +201,17 @@ __global__ void __launch_bounds__(256) gat_bwd_src_kernel(const srk_gat_inst I, 
   }
   row_store(acc, I.dZel + (long long)u * ldz + h * d, d, lane);
   if (lane == 0) I.dZel[(long long)u * ldz + H * d + h] = del;
+  if (Zhi) {                 // TF32 hi / lo copy for the tensor-core GEMMs that consume dZel (saves a separate split pass)
+    RowVec<NC> hi, lo;
+    row_split_tf32(acc, hi, lo);
+    row_store(hi, Zhi + (long long)u * ldz + h * d, d, lane);
+    row_store(lo, Zlo + (long long)u * ldz + h * d, d, lane);
+    if (lane == 0) {
+      const float dh = __uint_as_float(__float_as_uint(del) & 0xFFFFE000u);
+      Zhi[(long long)u * ldz + H * d + h] = dh;
+      Zlo[(long long)u * ldz + H * d + h] = del - dh;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) gat_bias_bwd_kernel(const float* __restrict__ dHpre, const uint8_t* __restrict__ amax,
@@ -402,7 +414,23 @@ extern "C" int srk_gat_aggregate_bwd_src(const srk_gat_inst* inst_host, int d, c
   if (I.n_src <= 0) return SRK_OK;
   DropCfg dc = make_drop(attn_drop);
   dc.site = I.attn_site;
-  SRK_DISPATCH_NC(d, (srk_launch(gat_bwd_src_kernel<NC>, I.n_src, 256, 0, (cudaStream_t)stream, I, d, dc, dHpre, amax)));
+  SRK_DISPATCH_NC(d, (srk_launch(gat_bwd_src_kernel<NC>, I.n_src, 256, 0, (cudaStream_t)stream, I, d, dc, dHpre, amax, nullptr,
+                                 nullptr)));
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_gat_aggregate_bwd_src_split(const srk_gat_inst* inst_host, int d, const srk_dropout* attn_drop,
+                                               const float* dHpre, const uint8_t* amax, float* dZel_hi, float* dZel_lo,
+                                               void* stream) {
+  SRK_TRY(srk_check_dim(d));
+  SRK_REQUIRE(dZel_hi != nullptr && dZel_lo != nullptr, "gat_aggregate_bwd_src_split: the hi / lo pair is required");
+  const srk_gat_inst& I = *inst_host;
+  if (I.n_src <= 0) return SRK_OK;
+  DropCfg dc = make_drop(attn_drop);
+  dc.site = I.attn_site;
+  SRK_DISPATCH_NC(d, (srk_launch(gat_bwd_src_kernel<NC>, I.n_src, 256, 0, (cudaStream_t)stream, I, d, dc, dHpre, amax, dZel_hi,
+                                 dZel_lo)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -28,6 +28,19 @@ __global__ void dropout_apply_kernel(const float* __restrict__ X, float* __restr
   }
 }
 
+// Y = dropout(X) together with its TF32 hi / lo split (operands of the tensor-core projection that consumes Y)
+__global__ void dropout_split_kernel(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ Yhi,
+                                     float* __restrict__ Ylo, long long n, DropCfg dc) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = X[i] * drop_mul(dc, (uint64_t)i);
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    Y[i] = v;
+    Yhi[i] = h;
+    Ylo[i] = v - h;
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ X, long long n, float value) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) X[i] = value;
@@ -216,6 +229,15 @@ extern "C" int srk_dropout_apply(const float* X, float* Y, long long n, const sr
                                  void* stream) {
   if (n <= 0) return SRK_OK;
   srk_launch(dropout_apply_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, X, Y, n, make_drop(drop), accumulate);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_dropout_apply_split(const float* X, float* Y, float* Yhi, float* Ylo, long long n, const srk_dropout* drop,
+                                       void* stream) {
+  if (n <= 0) return SRK_OK;
+  SRK_REQUIRE(Y != nullptr && Yhi != nullptr && Ylo != nullptr, "dropout_apply_split: all three outputs are required");
+  srk_launch(dropout_split_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, X, Y, Yhi, Ylo, n, make_drop(drop));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

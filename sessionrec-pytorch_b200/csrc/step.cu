@@ -374,7 +374,14 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
         I.xs = ar.f((size_t)N * d);
         I.xd = ar.f((size_t)N * d);
         SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(srk_dropout_apply(h, I.xs, (long long)N * d, &I.dcs, 0, zs));
+        if (tc_enc) {                             // the source copy together with its TF32 split
+          I.xh = ar.f((size_t)N * d);
+          I.xl = ar.f((size_t)N * d);
+          SRK_REQUIRE(ar.ok, "step: workspace too small");
+          SRK_TRY(srk_dropout_apply_split(h, I.xs, I.xh, I.xl, (long long)N * d, &I.dcs, zs));
+        } else {
+          SRK_TRY(srk_dropout_apply(h, I.xs, (long long)N * d, &I.dcs, 0, zs));
+        }
         SRK_TRY(srk_dropout_apply(h, I.xd, (long long)N * d, &I.dcd, 0, es));
       }
       float* Zel = ar.f((size_t)N * ldzel);
@@ -382,10 +389,12 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       float* att = ar.f((size_t)(M + 1) * H);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
       if (tc_enc) {
-        I.xh = ar.f((size_t)N * d);
-        I.xl = ar.f((size_t)N * d);
-        SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(srk_split_tf32(I.xs, d, N, d, I.xh, I.xl, d, zs));
+        if (!drop) {
+          I.xh = ar.f((size_t)N * d);
+          I.xl = ar.f((size_t)N * d);
+          SRK_REQUIRE(ar.ok, "step: workspace too small");
+          SRK_TRY(srk_split_tf32(I.xs, d, N, d, I.xh, I.xl, d, zs));
+        }
         SRK_TRY(srk_umma_gemm(0, N, ldzel, d, I.xh, I.xl, d, I.Wh, I.Wl, d, Zel, ldzel, 1.0f, 0, 1, zs));
       } else {
         SRK_TRY(linear_nt(zs, N, ldzel, d, I.xs, d, I.Waug, Zel, ldzel));
@@ -601,13 +610,14 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       float* pz = parts + (1 + 2 * c) * nd;      // source-copy term
       float* pe = parts + (2 + 2 * c) * nd;      // destination-copy term + identity residual
       InstRec& I = R.inst[c];
-      SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, zs));
       float *zh = nullptr, *zl = nullptr;
-      if (tc_enc) {                               // TF32 hi / lo of dZel, shared by the data and the weight gradient
+      if (tc_enc) {                               // dZel together with its TF32 hi / lo (data and weight gradient GEMMs)
         zh = ar.f((size_t)N * ldzel);
         zl = ar.f((size_t)N * ldzel);
         SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(srk_split_tf32(dZel[c], ldzel, N, ldzel, zh, zl, ldzel, zs));
+        SRK_TRY(srk_gat_aggregate_bwd_src_split(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, zh, zl, zs));
+      } else {
+        SRK_TRY(srk_gat_aggregate_bwd_src(&insts[c], d, drop ? &dc_attn : nullptr, dHpre, R.amax, zs));
       }
       SRK_TRY(order(zs, es));
       SRK_TRY(order(zs, wsc));
