@@ -218,6 +218,25 @@ int srk_ce_rows_bwd_cols(float* Z, long long ldz, const int* labels, const float
 int srk_logp_bwd(const float* LP, long long ldlp, const float* G, long long ldg, float scale, int B, int V, float* DZ,
                  long long lddz, float* DZlo, void* stream);
 
+/* ---- REnorm head of MSGIFSR (`--extra`, msgifsr.py:281-305) ----
+ * score[b, v] = phi[b, 0] * softmax_{v in session b}(Z) + phi[b, 1] * softmax_{v not in session b}(Z): replaces the O(B)
+ * Python mask loop and the two masked (B, V) soft-maxes.  The session's items are its order-1 nodes iid[seg[b] .. seg[b+1])
+ * (unique within the session).  srk_renorm_head_fwd rewrites the scaled logits Z[B, ldz] in place into log score, given
+ * lphi[B, 2] = log phi; zin[N] is scratch (N = seg[B]).  srk_renorm_head_bwd: from an upstream gradient G[B, ldg] of the
+ * log-probs LP, or (G == NULL) from the labels of the mean-NLL loss times gscale[0], writes
+ * DZ = scale * d loss / d Z (DZ may alias LP or G; optional TF32 lo part in DZlo) and dlphi[B, 2] = dl_scale * d loss / d log phi
+ * (dl_scale = 1 / scale when G already carries the logit scale); tmp[2 N] scratch.
+ * srk_gate_fwd / srk_gate_bwd: phi = softmax(W2 relu(h)) of `sc_sr[0]` (msgifsr.py:206,283): H[B, d] holds h = W1 s + b1 on
+ * entry and relu(h) on exit, W2[2, d]; the backward returns da[B, 2] (gradient at the two gate logits) and dH[B, d]. */
+int srk_renorm_head_fwd(float* Z, long long ldz, int B, int V, const int* iid, const int* seg, const float* lphi, float* zin,
+                        void* stream);
+int srk_renorm_head_bwd(const float* LP, long long ldlp, const float* G, long long ldg, const int* labels, const float* gscale,
+                        float scale, float dl_scale, int B, int V, const int* iid, const int* seg, const float* lphi, float* tmp,
+                        float* DZ, long long lddz, float* DZlo, float* dlphi, void* stream);
+int srk_gate_fwd(float* H, const float* W2, int B, int d, float* lphi, void* stream);
+int srk_gate_bwd(const float* Hr, const float* W2, const float* lphi, const float* dlphi, int B, int d, float* da, float* dH,
+                 void* stream);
+
 /* ---- order-fusion head of MSGIFSR (msgifsr.py:311-315,321): out = log sum_k a_k softmax(Z_k), a = softmax(alpha) ----
  * Zall[K][B][ldz] (head_stride floats apart) are the per-order scaled logits, lse[K][B] their row log-sum-exps, alpha[K]
  * the un-normalised mixture logits on the DEVICE (softmax taken in-kernel, no host sync).  srk_mix_bwd rewrites Zall in place with d loss / d Z_k (optionally as a TF32 hi/lo pair)

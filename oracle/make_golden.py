@@ -100,12 +100,12 @@ def oracle_params(sd, grad=True):
     return p
 
 
-def model_case(R, name, samples, V, d, L, K=1, fusion=False, inflate=False, seed=123):
+def model_case(R, name, samples, V, d, L, K=1, fusion=False, inflate=False, seed=123, extra=False):
     kind = 'session' if name in ('SRGNN', 'NISER') else 'ccs'
     inputs, labels, flat = ref_collate(R, samples, kind, K)
     th.manual_seed(seed)
     if name == 'MSGIFSR':
-        m = R.MSGIFSR(V, 'golden', d, L, dropout=0.0, order=K, extra=False, fusion=fusion)
+        m = R.MSGIFSR(V, 'golden', d, L, dropout=0.0, order=K, extra=extra, fusion=fusion)
     else:
         m = getattr(R, name)(V, d, L, 0.0)
     if inflate:   # push some rows over norm 1 so that the max_norm renorm path is exercised
@@ -120,7 +120,7 @@ def model_case(R, name, samples, V, d, L, K=1, fusion=False, inflate=False, seed
     loss = th.nn.functional.nll_loss(out, labels)
     loss.backward()
     grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in m.named_parameters()}
-    case = dict(model=name, V=V, d=d, L=L, K=K, fusion=fusion, samples=[(list(map(int, s)), int(l)) for s, l in samples],
+    case = dict(model=name, V=V, d=d, L=L, K=K, fusion=fusion, extra=extra, samples=[(list(map(int, s)), int(l)) for s, l in samples],
                 params=sd0, out=out.detach().clone(), loss=float(loss.detach()), grads=grads,
                 params_after_forward={k: v for k, v in params_of(m).items() if 'embedding' in k})
     # restatement cross-check (oracle vs reference, same weights)
@@ -128,7 +128,7 @@ def model_case(R, name, samples, V, d, L, K=1, fusion=False, inflate=False, seed
     ob = OC.build_batch([s for s, _ in samples], [l for _, l in samples], kind, K)
     assert_same_flat(flat, ob, f'{name} K={K}')
     if name == 'MSGIFSR':
-        o = OM.msgifsr_forward(p, ob, num_layers=L, fusion=fusion)
+        o = OM.msgifsr_forward(p, ob, num_layers=L, fusion=fusion, extra=extra)
     else:
         o = OM.srgnn_forward(p, ob, num_layers=L, niser=(name == 'NISER'))
     ol = OM.nll(o, ob['labels'])
@@ -141,7 +141,7 @@ def model_case(R, name, samples, V, d, L, K=1, fusion=False, inflate=False, seed
             assert og is None or og.abs().max() == 0, f'{name}: oracle has grad for {n}, reference has none'
             continue
         gerr = max(gerr, ((og - g).abs().max() / max(g.abs().max().item(), 1e-6)).item())   # numerically-zero grads: absolute
-    print(f'  {name:8s} K={K} L={L} fusion={fusion} inflate={inflate}: loss {float(loss.detach()):.6f}  |out-oracle| {err:.2e}  max rel grad err {gerr:.2e}')
+    print(f'  {name:8s} K={K} L={L} fusion={fusion} extra={extra} inflate={inflate}: loss {float(loss.detach()):.6f}  |out-oracle| {err:.2e}  max rel grad err {gerr:.2e}')
     assert err < 2e-5 and gerr < 2e-4, 'oracle restatement disagrees with the reference'
     if name == 'MSGIFSR':
         assert th.equal(p['embeddings.weight'].detach(), m.embeddings.weight.detach()) or \
@@ -212,11 +212,28 @@ def train_case(R, name, samples, test_samples, V, d, K, bs, steps, seed=123):
                 final_embedding=m.state_dict()[emb].detach().clone(), mrr=float(mrr), hit=float(hit))
 
 
+def extra_cases(R, small):
+    """REnorm head (`--extra`, msgifsr.py:281-305): kept in its own file so that the other fixtures stay byte-stable."""
+    print('models, REnorm head (V=%d, d=%d):' % (V_SMALL, D_SMALL))
+    b0, b1 = small[:48], small[200:264]
+    models = {
+        'msgifsr_k1_extra': model_case(R, 'MSGIFSR', b0, V_SMALL, D_SMALL, 1, K=1, extra=True),
+        'msgifsr_k1_extra_inflate_L2': model_case(R, 'MSGIFSR', b1, V_SMALL, D_SMALL, 2, K=1, extra=True, inflate=True),
+        'msgifsr_k2_extra': model_case(R, 'MSGIFSR', b0, V_SMALL, D_SMALL, 1, K=2, extra=True),
+        'msgifsr_k2_extra_fusion': model_case(R, 'MSGIFSR', b1, V_SMALL, D_SMALL, 1, K=2, extra=True, fusion=True, inflate=True),
+        'msgifsr_k1_extra_d32': model_case(R, 'MSGIFSR', small[300:332], V_SMALL, 32, 1, K=1, extra=True),
+    }
+    th.save(models, GOLD / 'models_extra_golden.pt')
+
+
 def main():
     th.set_num_threads(1)
     R = ref_import.load()
     GOLD.mkdir(parents=True, exist_ok=True)
     sessions = ref_import.read_sessions(ref_import.REFERENCE_ROOT / 'datasets' / 'sample' / 'train.txt')
+    if '--only-extra' in sys.argv:
+        extra_cases(R, OC.augmented_samples(sessions[:N_SESS]))
+        return
     ds = R.AugmentedDataset(np.array(sessions, dtype=object))
     all_samples = [(list(map(int, ds[i][0])), int(ds[i][1])) for i in range(len(ds))]
     mine = OC.augmented_samples(sessions)
@@ -265,6 +282,7 @@ def main():
         'msgifsr_k1_d32': model_case(R, 'MSGIFSR', small[300:332], V_SMALL, 32, 1, K=1),
     }
     th.save(models, GOLD / 'models_golden.pt')
+    extra_cases(R, small)
     th.save(dict(ggnn_d16=ggnn_case(R, b0, V_SMALL, D_SMALL), ggnn_d32=ggnn_case(R, b1, V_SMALL, 32)), GOLD / 'ggnn_golden.pt')
 
     print('training trajectories:')

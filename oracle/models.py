@@ -288,10 +288,10 @@ def mixed_rows(batch):
     return np.concatenate(kk), np.concatenate(nn_), tot
 
 
-def msgifsr_forward(params, batch, drop=NO_DROPOUT, num_layers=1, fusion=False, norm=True, return_aux=False):
-    """`MSGIFSR.forward` with extra=False (`msgifsr.py:241-323`).  Mutates params['embeddings.weight'] in
-    place exactly like `nn.Embedding(max_norm=1)` does (touched rows at the gather, all rows at the
-    scoring head)."""
+def msgifsr_forward(params, batch, drop=NO_DROPOUT, num_layers=1, fusion=False, norm=True, return_aux=False, extra=False):
+    """`MSGIFSR.forward` (`msgifsr.py:241-323`), with or without the REnorm head (`extra`, `:281-305`).  Mutates
+    params['embeddings.weight'] in place exactly like `nn.Embedding(max_norm=1)` does (touched rows at the
+    gather, all rows at the scoring head)."""
     E = params['embeddings.weight']
     K, B = batch['K'], batch['B']
     feats = {}
@@ -326,7 +326,23 @@ def msgifsr_forward(params, batch, drop=NO_DROPOUT, num_layers=1, fusion=False, 
         sr = TF.normalize(sr, dim=-1)
     renorm_rows_(E, th.arange(E.shape[0]))
     target = TF.normalize(E, dim=-1) if norm else E
-    score = th.softmax(SCALE * (sr @ target.t()), -1)                    # [B, K, V]
+    logits = sr @ target.t()                                             # [B, K, V]
+    if extra:
+        # REnorm (`msgifsr.py:281-305`): items of the session (its order-1 nodes) and all other items get their own
+        # soft-max; a 2-way gate phi = sc_sr[0](sr) mixes the two distributions.
+        hid = th.relu(sr @ params['sc_sr.0.0.weight'].t() + params['sc_sr.0.0.bias'])
+        phi = th.softmax(hid @ params['sc_sr.0.2.weight'].t(), -1)       # [B, K, 2]
+        seg1, iid1 = batch['seg'][1], _t(batch['iid'][1])
+        mask = th.zeros(B, E.shape[0], dtype=th.bool)
+        for b in range(B):
+            mask[b, iid1[seg1[b]:seg1[b + 1]]] = True
+        m3 = mask.unsqueeze(1)
+        s_in = th.softmax(SCALE * logits.masked_fill(~m3, float('-inf')), -1)
+        s_ex = th.softmax(SCALE * logits.masked_fill(m3, float('-inf')), -1)
+        s_ex = s_ex.masked_fill(s_ex != s_ex, 0)                         # a session that holds the whole catalog
+        score = phi[..., 0:1] * s_in + phi[..., 1:2] * s_ex
+    else:
+        score = th.softmax(SCALE * logits, -1)
     if K > 1 and fusion:
         score = (score * th.softmax(params['alpha'], -1).view(1, K, 1)).sum(1)
     else:

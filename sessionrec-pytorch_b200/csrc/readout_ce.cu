@@ -129,7 +129,23 @@ __device__ __forceinline__ MS ms_combine(MS a, MS b) {
   return r;
 }
 
-__device__ __forceinline__ MS block_lse(const float* __restrict__ z, int V, MS* red) {
+// (max, sum of exp) of the whole block; `red` holds one entry per warp and must not be reused before a barrier
+__device__ __forceinline__ MS block_ms_reduce(MS t, MS* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MS other;
+    other.m = __shfl_xor_sync(SRK_FULL, t.m, o);
+    other.s = __shfl_xor_sync(SRK_FULL, t.s, o);
+    t = ms_combine(t, other);
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  MS r = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = ms_combine(r, red[w]);
+  return r;
+}
+
+__device__ __forceinline__ MS block_lse(const float* z, int V, MS* red) {
   MS t;
   t.m = -FLT_MAX;
   t.s = 0.f;
@@ -154,18 +170,7 @@ __device__ __forceinline__ MS block_lse(const float* __restrict__ z, int V, MS* 
       t.s += expf(x - t.m);
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    MS other;
-    other.m = __shfl_xor_sync(SRK_FULL, t.m, o);
-    other.s = __shfl_xor_sync(SRK_FULL, t.s, o);
-    t = ms_combine(t, other);
-  }
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
-  __syncthreads();
-  MS r = red[0];
-  for (int w = 1; w < (blockDim.x >> 5); ++w) r = ms_combine(r, red[w]);
-  return r;
+  return block_ms_reduce(t, red);
 }
 
 __global__ void __launch_bounds__(512) ce_rows_fwd_kernel(float* __restrict__ Z, long long ldz, const int* __restrict__ labels,
@@ -268,6 +273,161 @@ __global__ void __launch_bounds__(512) logp_bwd_kernel(const float* __restrict__
   }
 }
 
+// ---- REnorm head of MSGIFSR (msgifsr.py:281-305) ----------------------------------------------------------------------
+// score[b, v] = phi[b, 0] * softmax over the session's own items (v in the session) + phi[b, 1] * softmax over all other
+// items; log score[b, v] = z[b, v] + log phi[b, g] - lse_g[b] with g the group of v.  The session's items are exactly its
+// order-1 nodes (iid[seg[b] .. seg[b + 1]), unique within the session), so the mask never exists as a matrix.
+
+__device__ __forceinline__ void store_split(float* dz, float* dzl, long long j, float v) {
+  if (dzl) {                                    // TF32 hi / lo pair for the tcgen05 backward GEMMs
+    float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    dz[j] = h;
+    dzl[j] = v - h;
+  } else {
+    dz[j] = v;
+  }
+}
+
+__global__ void __launch_bounds__(512) renorm_head_fwd_kernel(float* Z, long long ldz, int V, const int* __restrict__ iid,
+                                                              const int* __restrict__ seg, const float* __restrict__ lphi,
+                                                              float* __restrict__ zin) {
+  __shared__ MS red_in[16];
+  __shared__ MS red_ex[16];
+  float* z = Z + (long long)blockIdx.x * ldz;
+  const int s0 = seg[blockIdx.x], n = seg[blockIdx.x + 1] - s0;
+  MS t;
+  t.m = -FLT_MAX;
+  t.s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = z[iid[s0 + i]];
+    zin[s0 + i] = x;
+    MS o;
+    o.m = x;
+    o.s = 1.f;
+    t = ms_combine(t, o);
+  }
+  const MS rin = block_ms_reduce(t, red_in);           // barrier inside: every in-set logit has been read
+  for (int i = threadIdx.x; i < n; i += blockDim.x) z[iid[s0 + i]] = -INFINITY;
+  __syncthreads();
+  const MS rex = block_lse(z, V, red_ex);
+  const float c_in = lphi[2 * blockIdx.x] - (rin.m + logf(rin.s));
+  const float c_ex = rex.s > 0.f ? lphi[2 * blockIdx.x + 1] - (rex.m + logf(rex.s)) : 0.f;   // no other item: all -inf
+  __syncthreads();
+  for (int j = threadIdx.x; j < V; j += blockDim.x) z[j] += c_ex;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) z[iid[s0 + i]] = zin[s0 + i] + c_in;
+}
+
+// Backward of the map above.  Upstream gradient of the log-probs: G[B, ldg], or (G == NULL) the mean-NLL loss of `labels`
+// scaled by gscale[0] (g[b, v] = -gscale / B at the label).  With s_g = sum of g over group g:
+//   dZ[b, v] = scale * (g[b, v] - exp(LP[b, v] - log phi[b, g(v)]) * s_g(v)),   d log phi[b, g] = s_g.
+// d log phi is returned times dl_scale (callers whose G already carries `scale` pass 1 / scale).  DZ may alias LP or G: the
+// session's own entries of both are parked in tmp[2 N] before anything is written.
+__global__ void __launch_bounds__(512) renorm_head_bwd_kernel(const float* LP, long long ldlp, const float* __restrict__ G,
+                                                              long long ldg, const int* __restrict__ labels,
+                                                              const float* __restrict__ gscale, float scale, float dl_scale,
+                                                              int B, int V, const int* __restrict__ iid,
+                                                              const int* __restrict__ seg, const float* __restrict__ lphi,
+                                                              float* __restrict__ tmp, float* DZ, long long lddz, float* DZlo,
+                                                              float* __restrict__ dlphi) {
+  __shared__ float red[2][16];
+  __shared__ float tot[2];
+  const float* lp = LP + (long long)blockIdx.x * ldlp;
+  const float* g = G ? G + (long long)blockIdx.x * ldg : nullptr;
+  float* dz = DZ + (long long)blockIdx.x * lddz;
+  float* dzl = DZlo ? DZlo + (long long)blockIdx.x * lddz : nullptr;
+  const int s0 = seg[blockIdx.x], n = seg[blockIdx.x + 1] - s0;
+  float* tlp = tmp + 2 * (long long)s0;
+  float* tg = tlp + n;
+  const int lab = g ? -1 : labels[blockIdx.x];
+  const float c = g ? 0.f : gscale[0] / (float)B;
+  float s_all = 0.f, s_in = 0.f;
+  if (g) {
+    for (int j = threadIdx.x; j < V; j += blockDim.x) s_all += g[j];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float x = g[iid[s0 + i]];
+      tg[i] = x;
+      s_in += x;
+    }
+  } else {
+    if (threadIdx.x == 0) s_all = -c;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (iid[s0 + i] == lab) s_in = -c;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tlp[i] = lp[iid[s0 + i]];
+  s_all = warp_sum(s_all);
+  s_in = warp_sum(s_in);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s_all;
+    red[1][threadIdx.x >> 5] = s_in;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  const float sum_in = tot[1], sum_ex = tot[0] - tot[1];
+  const float lp_in = lphi[2 * blockIdx.x], lp_ex = lphi[2 * blockIdx.x + 1];
+  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+    const float gj = g ? g[j] : (j == lab ? -c : 0.f);
+    store_split(dz, dzl, j, scale * (gj - expf(lp[j] - lp_ex) * sum_ex));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int v = iid[s0 + i];
+    const float gj = g ? tg[i] : (v == lab ? -c : 0.f);
+    store_split(dz, dzl, v, scale * (gj - expf(tlp[i] - lp_in) * sum_in));
+  }
+  if (threadIdx.x == 0) {
+    dlphi[2 * blockIdx.x] = dl_scale * sum_in;
+    dlphi[2 * blockIdx.x + 1] = dl_scale * sum_ex;
+  }
+}
+
+// Gate of the REnorm head: phi = softmax(W2 relu(h)) with h = W1 shat + b1 already in H (msgifsr.py:206,283).
+// Warp per session; H is rewritten with relu(h), lphi[b, :] = log phi.
+__global__ void __launch_bounds__(256) gate_fwd_kernel(float* __restrict__ H, const float* __restrict__ W2, int B, int d,
+                                                       float* __restrict__ lphi) {
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.x * (blockDim.x >> 5)) {
+    float* h = H + (long long)b * d;
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float r = fmaxf(h[i], 0.f);
+      h[i] = r;
+      a0 += r * W2[i];
+      a1 += r * W2[d + i];
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    const float m = fmaxf(a0, a1);
+    const float l = m + logf(expf(a0 - m) + expf(a1 - m));
+    if (lane == 0) {
+      lphi[2 * b] = a0 - l;
+      lphi[2 * b + 1] = a1 - l;
+    }
+  }
+}
+
+// da = dlphi - phi * (dlphi_0 + dlphi_1) (gradient at the two gate logits), dH = relu'(h) * (W2^T da).
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ Hr, const float* __restrict__ W2,
+                                                       const float* __restrict__ lphi, const float* __restrict__ dlphi, int B,
+                                                       int d, float* __restrict__ da, float* __restrict__ dH) {
+  const int lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.x * (blockDim.x >> 5)) {
+    const float g0 = dlphi[2 * b], g1 = dlphi[2 * b + 1];
+    const float d0 = g0 - expf(lphi[2 * b]) * (g0 + g1), d1 = g1 - expf(lphi[2 * b + 1]) * (g0 + g1);
+    if (lane == 0) {
+      da[2 * b] = d0;
+      da[2 * b + 1] = d1;
+    }
+    for (int i = lane; i < d; i += 32)
+      dH[(long long)b * d + i] = Hr[(long long)b * d + i] > 0.f ? d0 * W2[i] + d1 * W2[d + i] : 0.f;
+  }
+}
+
 inline int row_grid(long long rows) {
   long long g = (rows + 7) / 8;
   if (g < 1) g = 1;
@@ -327,6 +487,42 @@ extern "C" int srk_ce_rows_bwd_cols(float* Z, long long ldz, const int* labels, 
                                     float scale, int B, int col0, int ncols, float* Zlo, void* stream) {
   if (B <= 0 || ncols <= 0) return SRK_OK;
   srk_launch(ce_rows_bwd_kernel, B, 512, 0, (cudaStream_t)stream, Z, ldz, labels, lse, gscale, scale, B, ncols, 0, Zlo, col0);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_renorm_head_fwd(float* Z, long long ldz, int B, int V, const int* iid, const int* seg, const float* lphi,
+                                   float* zin, void* stream) {
+  if (B <= 0) return SRK_OK;
+  SRK_REQUIRE(V > 0, "renorm_head_fwd: empty catalog");
+  srk_launch(renorm_head_fwd_kernel, B, 512, 0, (cudaStream_t)stream, Z, ldz, V, iid, seg, lphi, zin);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_renorm_head_bwd(const float* LP, long long ldlp, const float* G, long long ldg, const int* labels,
+                                   const float* gscale, float scale, float dl_scale, int B, int V, const int* iid,
+                                   const int* seg, const float* lphi, float* tmp, float* DZ, long long lddz, float* DZlo,
+                                   float* dlphi, void* stream) {
+  if (B <= 0) return SRK_OK;
+  SRK_REQUIRE(G != nullptr || (labels != nullptr && gscale != nullptr), "renorm_head_bwd: needs G or (labels, gscale)");
+  srk_launch(renorm_head_bwd_kernel, B, 512, 0, (cudaStream_t)stream, LP, ldlp, G, ldg, labels, gscale, scale, dl_scale, B, V, iid,
+             seg, lphi, tmp, DZ, lddz, DZlo, dlphi);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_gate_fwd(float* H, const float* W2, int B, int d, float* lphi, void* stream) {
+  if (B <= 0) return SRK_OK;
+  srk_launch(gate_fwd_kernel, row_grid(B), 256, 0, (cudaStream_t)stream, H, W2, B, d, lphi);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_gate_bwd(const float* Hr, const float* W2, const float* lphi, const float* dlphi, int B, int d, float* da,
+                            float* dH, void* stream) {
+  if (B <= 0) return SRK_OK;
+  srk_launch(gate_bwd_kernel, row_grid(B), 256, 0, (cudaStream_t)stream, Hr, W2, lphi, dlphi, B, d, da, dH);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

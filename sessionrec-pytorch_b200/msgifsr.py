@@ -233,6 +233,10 @@ class MSGIFSR(SessRecModule):
     def _single_head(self):
         return not (self.order > 1 and self.fusion)
 
+    def _use_flash(self, d, mode):
+        # the REnorm head needs the session's own logits apart from the rest: it runs on the materialised scores
+        return not self.extra and super()._use_flash(d, mode)
+
     # ---- native fused step (csrc/step.cu) ------------------------------------------------------------------------
     def _native_ok(self, batch):
         return (self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
@@ -349,8 +353,8 @@ class MSGIFSR(SessRecModule):
     def _fwd(self, batch, mode, need_grad=True):
         if batch.K != self.order:
             raise SessRecError(f'batch built for order {batch.K}, model has order {self.order}')
-        if self.extra:
-            raise SessRecError('MSGIFSR extra=True (REnorm head) is not built; the reference scripts default to False')
+        if self.extra and self._shard is not None:
+            raise SessRecError('catalog sharding with the REnorm head (extra=True) is not built')
         if not self.norm:
             raise SessRecError('MSGIFSR norm=False is not built (the reference argparse can only produce True)')
         if self.num_layers == 0:
@@ -405,11 +409,103 @@ class MSGIFSR(SessRecModule):
             ops.rownorm_fwd(s, d, B, d, NORM_L2, shat, d, rn_s)
             hd.append(dict(i=i, u=u, v=v, e=e, ms=ms, sr_in=sr_in, s=s, shat=shat, rn_s=rn_s, last_row=last_row))
         tape.update(X=X, rnX=rnX, dc_e=dc_e, etapes=etapes, ltapes=ltapes, h=h, rows=rows, seg=seg, heads=hd)
-        if len(heads) == 1:
+        if len(heads) == 1 and self.extra:
+            out = self._renorm_head_fwd(hd[0], batch, mode, tape)
+        elif len(heads) == 1:
             out = self._head_fwd(hd[0]['shat'], d, SCALE, batch, mode, tape)
         else:
             out = self._fusion_head_fwd(hd, batch, mode, tape)
         return out, (tape if need_grad else None)
+
+    # ---- REnorm head (`--extra`, msgifsr.py:281-305) -----------------------------------------------------------------
+    def _scores(self, hk, cat, B, V, d, Z, ldz):
+        """Z = 12 * shat Ehat^T, materialised (3xTF32 tcgen05 GEMM, or the fp32 CUDA-core GEMM without tensor cores)."""
+        if cat['umma']:
+            hk['sh'], hk['sl'] = torch.empty_like(hk['shat']), torch.empty_like(hk['shat'])
+            ops.split_tf32(hk['shat'], d, B, d, hk['sh'], hk['sl'], d)
+            ops.umma_gemm(0, B, V, d, hk['sh'], hk['sl'], d, cat['Ehi'], cat['Elo'], d, Z, ldz, alpha=SCALE)
+        else:
+            ops.gemm(B, V, d, hk['shat'], d, 1, cat['Ehat'], 1, d, Z, ldz, alpha=SCALE)
+
+    def _scores_bwd(self, hk, cat, B, V, d, dZ, Zlo, ldz, dshat, dEhat):
+        """dshat += dZ Ehat, dEhat += dZ^T shat (dZ as a TF32 hi/lo pair on the tensor-core path)."""
+        if cat['umma']:
+            split = max(1, min((V + 31) // 32, 148 // ((B + 127) // 128)))
+            ops.umma_gemm(1, B, d, V, dZ, Zlo, ldz, cat['Ehi'], cat['Elo'], d, dshat, d, accumulate=True, split_k=split)
+            ops.umma_gemm(2, V, d, B, dZ, Zlo, ldz, hk['sh'], hk['sl'], d, dEhat, d, accumulate=True)
+        else:
+            ops.gemm(B, d, V, dZ, ldz, 1, cat['Ehat'], d, 1, dshat, d, accumulate=True, split_k=0)
+            ops.gemm(V, d, B, dZ, 1, ldz, hk['shat'], d, 1, dEhat, d, accumulate=True, split_k=0)
+
+    def _renorm_fwd(self, hk, batch, Z, ldz, V):
+        """Gate phi = sc_sr[0](shat) (every order uses module 0, msgifsr.py:283) and the in place rewrite of the scaled
+        logits Z into log(phi_0 softmax_in + phi_1 softmax_ex)."""
+        B, d, dev = batch.B, self.embedding_dim, Z.device
+        t1 = batch.types[1]
+        lin1, lin2 = self.sc_sr[0][0], self.sc_sr[0][2]
+        hk['gate_h'] = torch.empty(B, d, dtype=torch.float32, device=dev)
+        hk['lphi'] = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        ops.linear_nt(hk['shat'], lin1.weight, hk['gate_h'], bias=lin1.bias)
+        ops.gate_fwd(hk['gate_h'], lin2.weight, B, d, hk['lphi'])
+        zin = torch.empty(max(t1['N'], 1), dtype=torch.float32, device=dev)
+        ops.renorm_head_fwd(Z, ldz, B, V, t1['iid'], t1['seg'], hk['lphi'], zin)
+
+    def _renorm_bwd(self, hk, batch, LP, ldz, V, G, ldg, labels, gscale, scale, dl_scale, dZ, Zlo):
+        """dZ (may alias LP or G) and the gradient at log phi of one REnorm head."""
+        t1 = batch.types[1]
+        dlphi = torch.empty(batch.B, 2, dtype=torch.float32, device=LP.device)
+        tmp = torch.empty(2 * max(t1['N'], 1), dtype=torch.float32, device=LP.device)
+        ops.renorm_head_bwd(LP, ldz, G, ldg, labels, gscale, scale, dl_scale, batch.B, V, t1['iid'], t1['seg'], hk['lphi'], tmp,
+                            dZ, ldz, Zlo, dlphi)
+        return dlphi
+
+    def _gate_bwd(self, hk, dlphi, dshat, g):
+        B, d, dev = dlphi.shape[0], self.embedding_dim, dlphi.device
+        lin1, lin2 = self.sc_sr[0][0], self.sc_sr[0][2]
+        da = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        dH = torch.empty(B, d, dtype=torch.float32, device=dev)
+        ops.gate_bwd(hk['gate_h'], lin2.weight, hk['lphi'], dlphi, B, d, da, dH)
+        ops.mm_tn(da, hk['gate_h'], g('sc_sr.0.2.weight'))
+        ops.mm_tn(dH, hk['shat'], g('sc_sr.0.0.weight'))
+        ops.colsum(dH, d, B, d, g('sc_sr.0.0.bias'))
+        ops.mm_nn(dH, lin1.weight, dshat, accumulate=True)
+
+    def _renorm_head_fwd(self, hk, batch, mode, tape):
+        cat = tape['cat']
+        B, (V, d) = batch.B, cat['Ehat'].shape
+        dev = cat['Ehat'].device
+        ldz = (V + 3) // 4 * 4
+        Z = torch.empty(B, ldz, dtype=torch.float32, device=dev)
+        self._scores(hk, cat, B, V, d, Z, ldz)
+        self._renorm_fwd(hk, batch, Z, ldz, V)
+        tape.update(Z=Z, ldz=ldz, renorm=True)
+        if mode != 'loss':                    # 'logp' and 'logits' (top-k ranks the final score) are the same matrix here
+            return Z[:, :V]
+        lse = torch.empty(B, dtype=torch.float32, device=dev)        # ~ 0: the rewritten rows are log-probabilities
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        ops.ce_rows_fwd(Z, ldz, batch.labels, B, V, False, lse, nll)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        ops.mean(nll, B, out)
+        return out
+
+    def _renorm_head_bwd(self, tape, batch, mode, gout, gE, E, g):
+        cat, hk = tape['cat'], tape['heads'][0]
+        B, (V, d) = batch.B, cat['Ehat'].shape
+        dev = cat['Ehat'].device
+        Z, ldz = tape['Z'], tape['ldz']
+        Zlo = torch.empty_like(Z) if cat['umma'] else None
+        if mode == 'loss':
+            dZ = Z                                # nobody else holds the log-probs: rewrite them in place
+            dlphi = self._renorm_bwd(hk, batch, Z, ldz, V, None, 0, batch.labels, gout.reshape(1), SCALE, 1.0, dZ, Zlo)
+        else:
+            dZ = torch.empty_like(Z)              # Z is the tensor forward() returned to the caller
+            dlphi = self._renorm_bwd(hk, batch, Z, ldz, V, gout, gout.stride(0), None, None, SCALE, 1.0, dZ, Zlo)
+        dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
+        dshat = torch.zeros(B, d, dtype=torch.float32, device=dev)
+        self._scores_bwd(hk, cat, B, V, d, dZ, Zlo, ldz, dshat, dEhat)
+        ops.catalog_prep_bwd(E, cat['Ehat'], cat['enorm'], dEhat, NORM_L2, gE)
+        self._gate_bwd(hk, dlphi, dshat, g)
+        return dshat
 
     # ---- order-fusion head (msgifsr.py:311-315): log sum_k softmax(alpha)_k softmax(12 sr_k E^T) --------------------
     def _fusion_head_fwd(self, hd, batch, mode, tape):
@@ -430,8 +526,12 @@ class MSGIFSR(SessRecModule):
                 ops.umma_gemm(0, B, V, d, hk['sh'], hk['sl'], d, cat['Ehi'], cat['Elo'], d, Zall[k], ldz, alpha=SCALE)
             else:
                 ops.gemm(B, V, d, hk['shat'], d, 1, Ehat, 1, d, Zall[k], ldz, alpha=SCALE)
+            if self.extra:                      # REnorm inside every order's head: Zall[k] becomes log score_k (lse ~ 0)
+                self._renorm_fwd(hk, batch, Zall[k], ldz, V)
             ops.ce_rows_fwd(Zall[k], ldz, batch.labels if mode == 'loss' else None, B, V, False, lse[k], nll[k])
         tape.update(Zall=Zall, ldz=ldz, lse_all=lse, fusion=True)
+        if self.extra:
+            tape['LPall'] = Zall.clone()        # mix_bwd rewrites Zall in place; the REnorm backward needs log score_k
         if mode == 'loss':
             out = torch.empty((), dtype=torch.float32, device=dev)
             ops.mix_loss_fwd(nll, self.alpha, K, B, out)
@@ -447,18 +547,23 @@ class MSGIFSR(SessRecModule):
         dev = Ehat.device
         Zall, ldz = tape['Zall'], tape['ldz']
         Zlo = torch.empty_like(Zall) if umma else None
+        mix_lo = None if self.extra else Zlo     # REnorm: the mixture's gradient stays one fp32 matrix, split afterwards
         rsum = torch.empty(K, B, dtype=torch.float32, device=dev)
         if mode == 'loss':
-            ops.mix_bwd(Zall, Zlo, B * ldz, ldz, tape['lse_all'], self.alpha, K, B, V, None, 0, batch.labels, gout.reshape(1),
+            ops.mix_bwd(Zall, mix_lo, B * ldz, ldz, tape['lse_all'], self.alpha, K, B, V, None, 0, batch.labels, gout.reshape(1),
                         SCALE, rsum)
         else:
-            ops.mix_bwd(Zall, Zlo, B * ldz, ldz, tape['lse_all'], self.alpha, K, B, V, gout, gout.stride(0), None, None, SCALE,
+            ops.mix_bwd(Zall, mix_lo, B * ldz, ldz, tape['lse_all'], self.alpha, K, B, V, gout, gout.stride(0), None, None, SCALE,
                         rsum)
         ops.mix_alpha_bwd(rsum, self.alpha, K, B, g('alpha'))
         dEhat = torch.zeros(V, d, dtype=torch.float32, device=dev)
         out = []
         for k, hk in enumerate(hd):
             dshat = torch.zeros(B, d, dtype=torch.float32, device=dev)
+            if self.extra:                      # Zall[k] holds SCALE * d loss / d log score_k
+                dlphi = self._renorm_bwd(hk, batch, tape['LPall'][k], ldz, V, Zall[k], ldz, None, None, 1.0, 1.0 / SCALE,
+                                         Zall[k], Zlo[k] if umma else None)
+                self._gate_bwd(hk, dlphi, dshat, g)
             if umma:
                 split = max(1, min((V + 31) // 32, 148 // ((B + 127) // 128)))
                 ops.umma_gemm(1, B, d, V, Zall[k], Zlo[k], ldz, cat['Ehi'], cat['Elo'], d, dshat, d, accumulate=True, split_k=split)
@@ -481,6 +586,8 @@ class MSGIFSR(SessRecModule):
         hd, rows, h = tape['heads'], tape['rows'], tape['h']
         if tape.get('fusion'):
             dshats = self._fusion_head_bwd(tape, batch, tape['mode'], gout, gE, E, g)
+        elif tape.get('renorm'):
+            dshats = [self._renorm_head_bwd(tape, batch, tape['mode'], gout, gE, E, g)]
         else:
             dshats = [self._head_bwd(tape, batch, tape['mode'], gout, gE, E)]
         R = rows.shape[0]

@@ -238,6 +238,26 @@ def logp_bwd(LP, ldlp, G, ldg, scale, B, V, DZ, lddz, DZlo=None):
     _call('srk_logp_bwd', ptr(LP), ldlp, ptr(G), ldg, float(scale), B, V, ptr(DZ), lddz, ptr(DZlo))
 
 
+def renorm_head_fwd(Z, ldz, B, V, iid, seg, lphi, zin):
+    """REnorm head (msgifsr.py:281-305): scaled logits Z -> log(phi_0 softmax_in + phi_1 softmax_ex), in place."""
+    _need_cuda(Z, iid, seg, lphi, zin)
+    _call('srk_renorm_head_fwd', ptr(Z), ldz, B, V, ptr(iid), ptr(seg), ptr(lphi), ptr(zin))
+
+
+def renorm_head_bwd(LP, ldlp, G, ldg, labels, gscale, scale, dl_scale, B, V, iid, seg, lphi, tmp, DZ, lddz, DZlo, dlphi):
+    _need_cuda(LP, iid, seg, lphi, tmp, DZ, dlphi)
+    _call('srk_renorm_head_bwd', ptr(LP), ldlp, ptr(G), ldg, ptr(labels), ptr(gscale), float(scale), float(dl_scale), B, V,
+          ptr(iid), ptr(seg), ptr(lphi), ptr(tmp), ptr(DZ), lddz, ptr(DZlo), ptr(dlphi))
+
+
+def gate_fwd(H, W2, B, d, lphi):
+    _call('srk_gate_fwd', ptr(H), ptr(W2), B, d, ptr(lphi))
+
+
+def gate_bwd(Hr, W2, lphi, dlphi, B, d, da, dH):
+    _call('srk_gate_bwd', ptr(Hr), ptr(W2), ptr(lphi), ptr(dlphi), B, d, ptr(da), ptr(dH))
+
+
 def topk_rows(Z, ldz, B, V, k, out_idx, out_val=None):
     _call('srk_topk_rows', ptr(Z), ldz, B, V, k, ptr(out_idx), ptr(out_val))
 

@@ -11,7 +11,7 @@ from tests.util import (RTOL, assert_close, assert_close_after_adam, assert_grad
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
-MODELS = golden('models_golden.pt')
+MODELS = {**golden('models_golden.pt'), **golden('models_extra_golden.pt')}     # the second file: REnorm head (--extra)
 TRAINS = golden('train_golden.pt')
 BUILT = list(MODELS)
 
@@ -20,7 +20,7 @@ def make_model(pkg, c, dropout=0.0):
     from sessionrec_pytorch_b200.msgifsr import MSGIFSR
     from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
     if c['model'] == 'MSGIFSR':
-        m = MSGIFSR(c['V'], 'golden', c['d'], c.get('L', 1), dropout=dropout, order=c['K'], extra=False,
+        m = MSGIFSR(c['V'], 'golden', c['d'], c.get('L', 1), dropout=dropout, order=c['K'], extra=c.get('extra', False),
                     fusion=c.get('fusion', False))
     else:
         m = {'SRGNN': SRGNN, 'NISER': NISER}[c['model']](c['V'], c['d'], c.get('L', 1), dropout)
@@ -41,7 +41,7 @@ def test_state_dict_keys_match_reference(pkg):
         from sessionrec_pytorch_b200.msgifsr import MSGIFSR
         from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
         if c['model'] == 'MSGIFSR':
-            m = MSGIFSR(c['V'], 'x', c['d'], c['L'], order=c['K'], extra=False, fusion=c['fusion'])
+            m = MSGIFSR(c['V'], 'x', c['d'], c['L'], order=c['K'], extra=c.get('extra', False), fusion=c['fusion'])
         else:
             m = {'SRGNN': SRGNN, 'NISER': NISER}[c['model']](c['V'], c['d'], c['L'])
         assert list(m.state_dict().keys()) == list(c['params'].keys()), name
@@ -88,7 +88,7 @@ def test_fused_loss_path_vs_reference_golden(pkg, name):
 
 
 @pytest.mark.parametrize('name', ['srgnn', 'niser', 'msgifsr_k1', 'msgifsr_k1_inflate_L2', 'msgifsr_k2', 'msgifsr_k3',
-                                  'msgifsr_k2_fusion'])
+                                  'msgifsr_k2_fusion', 'msgifsr_k1_extra', 'msgifsr_k2_extra_fusion'])
 @pytest.mark.parametrize('p', [0.2, 0.5])
 def test_dropout_with_injected_masks_vs_oracle(pkg, name, p):
     """Training mode with dropout: the oracle consumes the same counter-based masks the kernels regenerate."""
@@ -105,7 +105,7 @@ def test_dropout_with_injected_masks_vs_oracle(pkg, name, p):
     prm = oracle_params(c['params'])
     kind = 'session' if c['model'] in ('SRGNN', 'NISER') else 'ccs'
     ob = oracle_batch(c['samples'], kind, c['K'])
-    ref = run_oracle(c['model'], prm, ob, c['L'], c['fusion'], drop=OM.Dropout(p, True, seed))
+    ref = run_oracle(c['model'], prm, ob, c['L'], c['fusion'], drop=OM.Dropout(p, True, seed), extra=c.get('extra', False))
     rl = OM.nll(ref, ob['labels'])
     rl.backward()
     assert abs(float(loss) - float(rl)) <= RTOL * abs(float(rl)), (float(loss), float(rl))
@@ -114,7 +114,8 @@ def test_dropout_with_injected_masks_vs_oracle(pkg, name, p):
         assert_grad_close_robust(f'{name}.p{p}.grad[{n}]', params[n].grad, prm[n].grad)
     m.eval()
     with torch.no_grad():
-        assert_close(f'{name}.eval logp', m(b), run_oracle(c['model'], oracle_params(c['params'], False), ob, c['L'], c['fusion']))
+        assert_close(f'{name}.eval logp', m(b), run_oracle(c['model'], oracle_params(c['params'], False), ob, c['L'], c['fusion'],
+                                                                 extra=c.get('extra', False)))
 
 
 @pytest.mark.parametrize('head', ['flash', 'tf32'])

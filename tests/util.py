@@ -95,7 +95,7 @@ def assert_grad_close_robust(name, got, ref, rtol=RTOL, l2_rtol=1e-2):
     assert l2 <= l2_rtol, f'{name}: max|d|={float(err.max()):.3e} vs max|ref|={scale:.3e}, relative L2 error {l2:.2e}'
 
 
-def run_oracle(case_model, params, ob, L=1, fusion=False, drop=OM.NO_DROPOUT):
+def run_oracle(case_model, params, ob, L=1, fusion=False, drop=OM.NO_DROPOUT, extra=False):
     if case_model == 'MSGIFSR':
-        return OM.msgifsr_forward(params, ob, drop=drop, num_layers=L, fusion=fusion)
+        return OM.msgifsr_forward(params, ob, drop=drop, num_layers=L, fusion=fusion, extra=extra)
     return OM.srgnn_forward(params, ob, drop=drop, num_layers=L, niser=(case_model == 'NISER'))
