@@ -174,12 +174,12 @@ def ggnn_case(R, samples, V, d, seed=7):
                 grads={'layers.0.' + n: g for n, g in grads.items()})
 
 
-def train_case(R, name, samples, test_samples, V, d, K, bs, steps, seed=123):
+def train_case(R, name, samples, test_samples, V, d, K, bs, steps, seed=123, extra=False):
     """A few iterations of the reference's own TrainRunner loop body (Adam lr 1e-3, L2 1e-4 with
     fix_weight_decay) and its evaluate(); dropout 0 so that the trajectory is deterministic."""
     kind = 'session' if name in ('SRGNN', 'NISER') else 'ccs'
     th.manual_seed(seed)
-    m = R.MSGIFSR(V, 'golden', d, 1, dropout=0.0, order=K, extra=False, fusion=False) if name == 'MSGIFSR' \
+    m = R.MSGIFSR(V, 'golden', d, 1, dropout=0.0, order=K, extra=extra, fusion=False) if name == 'MSGIFSR' \
         else getattr(R, name)(V, d, 1, 0.0)
     sd0 = params_of(m)
     runner = R.train.TrainRunner('golden', m, [], [], th.device('cpu'), lr=1e-3, weight_decay=1e-4, patience=3)
@@ -197,23 +197,23 @@ def train_case(R, name, samples, test_samples, V, d, K, bs, steps, seed=123):
         runner.optimizer.step()
         losses.append(float(loss.detach()))
         opt.zero_grad()
-        o = OM.msgifsr_forward(p, flat) if name == 'MSGIFSR' else OM.srgnn_forward(p, flat, niser=(name == 'NISER'))
+        o = OM.msgifsr_forward(p, flat, extra=extra) if name == 'MSGIFSR' else OM.srgnn_forward(p, flat, niser=(name == 'NISER'))
         ol = OM.nll(o, flat['labels'])
         ol.backward()
         opt.step()
         assert abs(float(ol.detach()) - losses[-1]) < 1e-4 * max(1.0, abs(losses[-1])), (it, float(ol.detach()), losses[-1])
     tl = [ref_collate(R, test_samples[i:i + bs], kind, K)[:2] for i in range(0, len(test_samples), bs)]
     mrr, hit = R.train.evaluate(m, tl, th.device('cpu'))
-    print(f'  train {name} K={K}: losses {losses[0]:.5f} -> {losses[-1]:.5f}   MRR@20 {mrr:.5f} HR@20 {hit:.5f}')
+    print(f'  train {name} K={K} extra={extra}: losses {losses[0]:.5f} -> {losses[-1]:.5f}   MRR@20 {mrr:.5f} HR@20 {hit:.5f}')
     emb = 'embeddings.weight' if name == 'MSGIFSR' else 'embedding.weight'
-    return dict(model=name, V=V, d=d, K=K, bs=bs, steps=steps, params=sd0, losses=losses,
+    return dict(model=name, V=V, d=d, K=K, bs=bs, steps=steps, extra=extra, params=sd0, losses=losses,
                 samples=[(list(map(int, s)), int(l)) for s, l in samples[:steps * bs]],
                 test_samples=[(list(map(int, s)), int(l)) for s, l in test_samples],
                 final_embedding=m.state_dict()[emb].detach().clone(), mrr=float(mrr), hit=float(hit))
 
 
-def extra_cases(R, small):
-    """REnorm head (`--extra`, msgifsr.py:281-305): kept in its own file so that the other fixtures stay byte-stable."""
+def extra_cases(R, small, test_small):
+    """REnorm head (`--extra`, msgifsr.py:281-305): kept in its own files so that the other fixtures stay byte-stable."""
     print('models, REnorm head (V=%d, d=%d):' % (V_SMALL, D_SMALL))
     b0, b1 = small[:48], small[200:264]
     models = {
@@ -224,6 +224,13 @@ def extra_cases(R, small):
         'msgifsr_k1_extra_d32': model_case(R, 'MSGIFSR', small[300:332], V_SMALL, 32, 1, K=1, extra=True),
     }
     th.save(models, GOLD / 'models_extra_golden.pt')
+    th.save({'msgifsr_k1_extra': train_case(R, 'MSGIFSR', small, test_small, V_SMALL, D_SMALL, 1, 32, 6, extra=True)},
+            GOLD / 'train_extra_golden.pt')
+
+
+def test_split(sessions):
+    t = OC.augmented_samples(sessions[N_SESS:N_SESS + 60])
+    return [(s, l) for s, l in t if max(s + [l]) < V_SMALL]
 
 
 def main():
@@ -232,7 +239,7 @@ def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     sessions = ref_import.read_sessions(ref_import.REFERENCE_ROOT / 'datasets' / 'sample' / 'train.txt')
     if '--only-extra' in sys.argv:
-        extra_cases(R, OC.augmented_samples(sessions[:N_SESS]))
+        extra_cases(R, OC.augmented_samples(sessions[:N_SESS]), test_split(sessions))
         return
     ds = R.AugmentedDataset(np.array(sessions, dtype=object))
     all_samples = [(list(map(int, ds[i][0])), int(ds[i][1])) for i in range(len(ds))]
@@ -282,12 +289,11 @@ def main():
         'msgifsr_k1_d32': model_case(R, 'MSGIFSR', small[300:332], V_SMALL, 32, 1, K=1),
     }
     th.save(models, GOLD / 'models_golden.pt')
-    extra_cases(R, small)
+    extra_cases(R, small, test_split(sessions))
     th.save(dict(ggnn_d16=ggnn_case(R, b0, V_SMALL, D_SMALL), ggnn_d32=ggnn_case(R, b1, V_SMALL, 32)), GOLD / 'ggnn_golden.pt')
 
     print('training trajectories:')
-    test_small = OC.augmented_samples(sessions[N_SESS:N_SESS + 60])
-    test_small = [(s, l) for s, l in test_small if max(s + [l]) < V_SMALL]
+    test_small = test_split(sessions)
     trains = {
         'srgnn': train_case(R, 'SRGNN', small, test_small, V_SMALL, D_SMALL, 1, 32, 6),
         'niser': train_case(R, 'NISER', small, test_small, V_SMALL, D_SMALL, 1, 32, 6),

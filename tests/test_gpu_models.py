@@ -12,7 +12,7 @@ from tests.util import (RTOL, assert_close, assert_close_after_adam, assert_grad
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 MODELS = {**golden('models_golden.pt'), **golden('models_extra_golden.pt')}     # the second file: REnorm head (--extra)
-TRAINS = golden('train_golden.pt')
+TRAINS = {**golden('train_golden.pt'), **golden('train_extra_golden.pt')}
 BUILT = list(MODELS)
 
 
@@ -148,7 +148,7 @@ def test_fused_train_step_trajectory_vs_reference(pkg, name, head):
     assert abs(hit / n - c['hit']) <= 1e-3 and abs(mrr / n - c['mrr']) <= 1e-3
 
 
-@pytest.mark.parametrize('name', ['srgnn', 'msgifsr_k1'])
+@pytest.mark.parametrize('name', ['srgnn', 'msgifsr_k1', 'msgifsr_k1_extra'])
 def test_unmodified_style_training_loop_with_torch_adam(pkg, name):
     """The reference loop body verbatim (optimizer.zero_grad / model(*inputs) / nll_loss / backward / step) with
     torch.optim.Adam + fix_weight_decay groups runs on the drop-in module and follows the golden trajectory."""
