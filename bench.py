@@ -304,6 +304,25 @@ def gather_scatter_probe(device, pk, shapes=None):
     return out
 
 
+def builder_probe(pkg, cfg, n=40):
+    """Host-side cost of the native batch builder (`srk_batch_build`, the collate_fn replacement, collate.py:219-256) on
+    one thread: the end-to-end loop above starts from built, pinned batches (a DataLoader worker's output), so this says
+    whether one worker keeps up with the device step.  Never fatal: returns None on any problem."""
+    try:
+        from sessionrec_pytorch_b200.synthetic import SessionSampler
+        smp = SessionSampler(cfg['V'], seed=321)
+        raw = [smp.batch(cfg['B']) for _ in range(n)]
+        pkg.SessionBatch.build_flat(*raw[0], kind_of(cfg), cfg['order'], pin=False)
+        t0 = time.perf_counter()
+        for items, offs, labels in raw:
+            pkg.SessionBatch.build_flat(items, offs, labels, kind_of(cfg), cfg['order'], pin=False)
+        dt = (time.perf_counter() - t0) / n
+        return dict(ms_per_batch=round(1e3 * dt, 4), sessions_per_s=round(cfg['B'] / dt, 1), threads=1,
+                    what='SessionBatch.build_flat: flat item ids -> graph batch buffer (host, not inside any timed region)')
+    except Exception as e:                                        # noqa: BLE001
+        return dict(error=f'{type(e).__name__}: {e}')
+
+
 def reference_arm(args, cfg, rank, guard):
     if rank != 0:
         return
@@ -462,6 +481,7 @@ def main():
                         timing='wall clock over K steps incl. H2D batch copy + loss.item() per step'),
             'wall_s_timed_region': round(t_wall, 4), 'host_enqueue_ms_per_step': round(1e3 * enqueue_s / args.steps, 4),
             'roofline': roof, 'roofline_gather_scatter': roof_gs,
+            'batch_builder': builder_probe(pkg, cfg) if world == 1 else None,
         }
     if world > 1:
         dist.barrier()

@@ -23,6 +23,7 @@ namespace {
 
 constexpr int HDR = 16, TYPE_TAB = 16, REL_TAB = 80, TAB_W = 16, MAXK = 4, MAXREL = 3 * MAXK - 2;
 constexpr int DATA0 = REL_TAB + TAB_W * MAXREL;
+constexpr int SMALL_L = 32;   // sessions up to this many clicks take the branch-free path of build()
 
 struct Rel {
   int st, dt, code;
@@ -48,31 +49,60 @@ inline void add_unique_pair(std::vector<int>& ps, std::vector<int>& pd, std::vec
 
 int build(const int* items, const int* offs, int B, int kind, int K, Work& wk) {
   wk.B = B; wk.kind = kind; wk.K = K;
-  wk.rels.clear();
-  for (int k = 1; k <= K; ++k) wk.rels.push_back(Rel{k, k, k, {}, {}, {}});
+  // the work area is thread-local and keeps its capacity from batch to batch: no allocation in steady state
+  wk.rels.resize(3 * K - 2);
+  auto reset = [](Rel& r, int st, int dt, int code) {
+    r.st = st; r.dt = dt; r.code = code;
+    r.src.clear(); r.dst.clear(); r.w.clear();
+  };
+  for (int k = 1; k <= K; ++k) reset(wk.rels[k - 1], k, k, k);
   for (int k = 2; k <= K; ++k) {
-    wk.rels.push_back(Rel{1, k, 100 + k, {}, {}, {}});
-    wk.rels.push_back(Rel{k, 1, 200 + k, {}, {}, {}});
+    reset(wk.rels[K + 2 * (k - 2)], 1, k, 100 + k);
+    reset(wk.rels[K + 2 * (k - 2) + 1], k, 1, 200 + k);
   }
   for (int k = 0; k < K; ++k) {
     wk.iid[k].clear(); wk.last[k].clear();
     wk.seg[k].assign(1, 0);
   }
-  std::vector<int> uniq, s, gid[MAXK];
+  static thread_local std::vector<int> uniq, s, gid[MAXK];
   for (int b = 0; b < B; ++b) {
     const int* seq = items + offs[b];
     const int L = offs[b + 1] - offs[b];
     SRK_REQUIRE(L >= 1, "batch: session %d is empty", b);
-    uniq.assign(seq, seq + L);
-    std::sort(uniq.begin(), uniq.end());
-    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
     s.resize(L);
-    for (int i = 0; i < L; ++i) s[i] = (int)(std::lower_bound(uniq.begin(), uniq.end(), seq[i]) - uniq.begin());
+    const bool small = L <= SMALL_L;
+    if (small) {
+      // Short session (the common case): rank every click among the session's distinct items by counting, with no
+      // data-dependent branch - on real sessions the compare branches of sort / unique / lower_bound mispredict every
+      // other time and cost more than the O(L^2) counts.
+      int first[SMALL_L];
+      int nu = 0;
+      for (int i = 0; i < L; ++i) {
+        const int x = seq[i];
+        int seen = 0;
+        for (int j = 0; j < i; ++j) seen += (seq[j] == x);
+        first[i] = (seen == 0);
+        nu += first[i];
+      }
+      uniq.resize(nu);
+      for (int i = 0; i < L; ++i) {
+        const int x = seq[i];
+        int less = 0;
+        for (int j = 0; j < L; ++j) less += (seq[j] < x) & first[j];
+        s[i] = less;
+        uniq[less] = x;
+      }
+    } else {
+      uniq.assign(seq, seq + L);
+      std::sort(uniq.begin(), uniq.end());
+      uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+      for (int i = 0; i < L; ++i) s[i] = (int)(std::lower_bound(uniq.begin(), uniq.end(), seq[i]) - uniq.begin());
+    }
     const int base1 = wk.seg[0].back();
     wk.iid[0].insert(wk.iid[0].end(), uniq.begin(), uniq.end());
     wk.seg[0].push_back(base1 + (int)uniq.size());
     wk.last[0].push_back(base1 + s[L - 1]);
-    gid[0] = s;
+    gid[0].assign(s.begin(), s.end());
     // k-gram node types
     for (int k = 2; k <= K; ++k) {
       std::vector<int>& g = gid[k - 1];
@@ -107,8 +137,25 @@ int build(const int* items, const int* offs, int B, int kind, int K, Work& wk) {
       const std::vector<int>& g = gid[k - 1];
       const int basek = wk.seg[k - 1][b];
       const size_t e0 = r.src.size();
-      for (int i = 0; i + 1 < (int)g.size(); ++i)
-        add_unique_pair(r.src, r.dst, kind == 0 ? &r.w : nullptr, e0, basek + g[i], basek + g[i + 1]);
+      if (k == 1 && small) {
+        // consecutive-click pairs of a short session: one small key per pair, duplicates found by counting
+        int key[SMALL_L];
+        const int ne = L - 1;
+        for (int i = 0; i < ne; ++i) key[i] = g[i] * SMALL_L + g[i + 1];
+        for (int i = 0; i < ne; ++i) {
+          int before = 0, total = 0;
+          for (int j = 0; j < i; ++j) before += (key[j] == key[i]);
+          for (int j = 0; j < ne; ++j) total += (key[j] == key[i]);
+          if (before == 0) {                  // first occurrence keeps the edge (and, for the session graph, the count)
+            r.src.push_back(basek + g[i]);
+            r.dst.push_back(basek + g[i + 1]);
+            if (kind == 0) r.w.push_back(total);
+          }
+        }
+      } else {
+        for (int i = 0; i + 1 < (int)g.size(); ++i)
+          add_unique_pair(r.src, r.dst, kind == 0 ? &r.w : nullptr, e0, basek + g[i], basek + g[i + 1]);
+      }
       if (kind == 0 && r.src.size() == e0) {   // single click: self-loop, weight 1
         r.src.push_back(basek); r.dst.push_back(basek); r.w.push_back(1);
       }
@@ -157,6 +204,37 @@ void csr(const std::vector<int>& key, const std::vector<int>& other, int n, std:
   }
 }
 
+// perm = positions 0..P-1 ordered by ids[] (stable).  LSD radix on 11-bit digits: a batch holds a few thousand
+// positions, where std::stable_sort with an indirect comparator costs ~100 ns per element.
+void order_by_id(const std::vector<int>& ids, std::vector<int>& perm, std::vector<int>& tmp) {
+  const int P = (int)ids.size();
+  perm.resize(P);
+  tmp.resize(P);
+  int mx = 0, mn = 0;
+  for (int i = 0; i < P; ++i) {
+    perm[i] = i;
+    mx = std::max(mx, ids[i]);
+    mn = std::min(mn, ids[i]);
+  }
+  if (mn < 0) {                            // not an item id; keep the ordering defined anyway
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int c) { return ids[a] < ids[c]; });
+    return;
+  }
+  int* a = perm.data();
+  int* b = tmp.data();
+  for (int shift = 0; shift < 31 && (mx >> shift) > 0; shift += 11) {
+    int cnt[2049] = {0};
+    for (int i = 0; i < P; ++i) cnt[((ids[a[i]] >> shift) & 2047) + 1]++;
+    for (int i = 0; i < 2048; ++i) cnt[i + 1] += cnt[i];
+    for (int i = 0; i < P; ++i) {
+      const int p = a[i];
+      b[cnt[(ids[p] >> shift) & 2047]++] = p;
+    }
+    std::swap(a, b);
+  }
+  if (a != perm.data()) memcpy(perm.data(), a, sizeof(int) * P);
+}
+
 long long emit(const Work& wk, const int* labels, int* out, long long cap) {
   Writer w{out, cap, DATA0, true};
   std::vector<int> hdr(DATA0, 0);
@@ -191,10 +269,9 @@ long long emit(const Work& wk, const int* labels, int* out, long long cap) {
     t[4] = w.put(n2s);
     // scatter permutation: gather positions sorted by item id (stable), distinct ids and their ranges
     const int P = N * kk;
-    std::vector<int> perm(P);
-    for (int i = 0; i < P; ++i) perm[i] = i;
     const std::vector<int>& ids = wk.iid[k];
-    std::stable_sort(perm.begin(), perm.end(), [&](int a, int c) { return ids[a] < ids[c]; });
+    static thread_local std::vector<int> perm, perm_tmp;
+    order_by_id(ids, perm, perm_tmp);
     std::vector<int> uoff, uid;
     for (int i = 0; i < P; ++i)
       if (i == 0 || ids[perm[i]] != ids[perm[i - 1]]) {
