@@ -83,7 +83,9 @@ class SessionBatch:
         return SessionBatch.build_flat(items, offs, np.asarray(labels, np.int32), kind, order, pin)
 
     @staticmethod
-    def build_flat(items, offs, labels, kind='session', order=1, pin=False):
+    def build_flat(items, offs, labels, kind='session', order=1, pin=False, out=None):
+        """items int32[T] (all sessions back to back), offs int32[B + 1], labels int32[B].  `out`: a host int32 tensor to
+        build into (e.g. a reused pinned buffer, see loader.BatchPrefetcher); it must hold `batch_words(...)` words."""
         L = _lib.lib()
         B = len(offs) - 1
         kind_i = 0 if kind == 'session' else 1
@@ -91,10 +93,22 @@ class SessionBatch:
         offs = np.ascontiguousarray(offs, np.int32)
         labels = np.ascontiguousarray(labels, np.int32)
         ip, op, lp = (a.ctypes.data_as(ctypes.c_void_p) for a in (items, offs, labels))
-        cap = L.call('srk_batch_size', ip, op, B, kind_i, order)
-        buf = torch.empty(cap, dtype=torch.int32, pin_memory=pin)
+        if out is None:
+            cap = L.call('srk_batch_size', ip, op, B, kind_i, order)
+            buf = torch.empty(cap, dtype=torch.int32, pin_memory=pin)
+        else:
+            if out.dtype != torch.int32 or out.is_cuda or not out.is_contiguous():
+                raise _lib.SessRecError('build_flat: `out` must be a contiguous host int32 tensor')
+            buf, cap = out, out.numel()
         used = L.call('srk_batch_build', ip, op, lp, B, kind_i, order, ctypes.c_void_p(buf.data_ptr()), cap)
         return SessionBatch(buf[:used])
+
+    @staticmethod
+    def batch_words(n_items, B, kind='session', order=1):
+        """Upper bound of the buffer size (int32 words) of a batch of B sessions with n_items clicks in total."""
+        offs = np.array([0] * B + [n_items], np.int32)
+        return int(_lib.lib().call('srk_batch_size', None, offs.ctypes.data_as(ctypes.c_void_p), B,
+                                   0 if kind == 'session' else 1, order))
 
     # ---- the DGLGraph-like surface `prepare_batch` relies on ----------------------------------------
     def to(self, device, non_blocking=True):
