@@ -28,7 +28,11 @@ class SessionBatch:
 
     def __init__(self, buf, hdr=None):
         self.buf = buf                                            # int32 tensor (host or device)
-        self.hdr = np.asarray(buf[:_DATA0].cpu().numpy() if hdr is None else hdr).copy()
+        if hdr is None:                                           # host copy of the header words
+            assert buf.numel() >= _DATA0, 'not a SessionBatch buffer'
+            hdr = (np.ctypeslib.as_array((ctypes.c_int32 * _DATA0).from_address(buf.data_ptr())) if not buf.is_cuda
+                   else buf[:_DATA0].cpu().numpy())
+        self.hdr = np.array(hdr, dtype=np.int32)
         h = self.hdr
         assert int(h[0]) == _MAGIC, 'not a SessionBatch buffer'
         self.B, self.K, self.R = int(h[1]), int(h[3]), int(h[6])
@@ -92,7 +96,7 @@ class SessionBatch:
         items = np.ascontiguousarray(items, np.int32)
         offs = np.ascontiguousarray(offs, np.int32)
         labels = np.ascontiguousarray(labels, np.int32)
-        ip, op, lp = (a.ctypes.data_as(ctypes.c_void_p) for a in (items, offs, labels))
+        ip, op, lp = (a.__array_interface__['data'][0] for a in (items, offs, labels))      # plain ints: c_void_p arguments
         if out is None:
             cap = L.call('srk_batch_size', ip, op, B, kind_i, order)
             buf = torch.empty(cap, dtype=torch.int32, pin_memory=pin)
@@ -100,14 +104,15 @@ class SessionBatch:
             if out.dtype != torch.int32 or out.is_cuda or not out.is_contiguous():
                 raise _lib.SessRecError('build_flat: `out` must be a contiguous host int32 tensor')
             buf, cap = out, out.numel()
-        used = L.call('srk_batch_build', ip, op, lp, B, kind_i, order, ctypes.c_void_p(buf.data_ptr()), cap)
+        used = L.call('srk_batch_build', ip, op, lp, B, kind_i, order, buf.data_ptr(), cap)
         return SessionBatch(buf[:used])
 
     @staticmethod
     def batch_words(n_items, B, kind='session', order=1):
         """Upper bound of the buffer size (int32 words) of a batch of B sessions with n_items clicks in total."""
-        offs = np.array([0] * B + [n_items], np.int32)
-        return int(_lib.lib().call('srk_batch_size', None, offs.ctypes.data_as(ctypes.c_void_p), B,
+        offs = np.zeros(B + 1, np.int32)
+        offs[B] = n_items
+        return int(_lib.lib().call('srk_batch_size', None, offs.__array_interface__['data'][0], B,
                                    0 if kind == 'session' else 1, order))
 
     # ---- the DGLGraph-like surface `prepare_batch` relies on ----------------------------------------
