@@ -16,6 +16,7 @@ int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
     if (c->failed) return SRK_OK;                       // the step will be re-run with plain launches
     if (c->cursor >= c->g->nodes.size() || c->g->nodes[c->cursor].func != func || c->cursor == c->fail_at) {
       c->failed = true;
+      c->fail_reason = c->cursor >= c->g->nodes.size() ? 1 : (c->cursor == c->fail_at ? 3 : 2);
       return SRK_OK;
     }
     cudaKernelNodeParams p;
@@ -25,9 +26,12 @@ int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
     p.blockDim = block;
     p.sharedMemBytes = (unsigned int)smem;
     p.kernelParams = args;
-    if (cudaGraphExecKernelNodeSetParams(c->g->exec, c->g->nodes[c->cursor].node, &p) != cudaSuccess) {
+    const cudaError_t ue = cudaGraphExecKernelNodeSetParams(c->g->exec, c->g->nodes[c->cursor].node, &p);
+    if (ue != cudaSuccess) {
       cudaGetLastError();
       c->failed = true;
+      c->fail_reason = 4;
+      c->fail_cuda = (int)ue;
       return SRK_OK;
     }
     ++c->cursor;
@@ -44,6 +48,7 @@ int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
         status != cudaStreamCaptureStatusActive || ndeps != 1) {
       cudaGetLastError();
       c->failed = true;                                 // not capturing after all: the caller discards the graph
+      c->fail_reason = 5;
       return SRK_OK;
     }
     c->g->nodes.push_back(SrkGraphNode{deps[0], func});

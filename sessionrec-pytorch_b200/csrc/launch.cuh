@@ -32,6 +32,10 @@ struct SrkLaunchCtx {
   cudaStream_t capture_stream = nullptr;
   bool capturing = false;
   size_t fail_at = (size_t)-1;          // test hook: pretend the kernel sequence differs at this node
+  // why the pass failed (SESSREC_GRAPH_DEBUG): 1 more launches than nodes, 2 other kernel, 3 test hook, 4 node update
+  // refused (fail_cuda = the CUDA error), 5 launch outside the capture
+  int fail_reason = 0;
+  int fail_cuda = 0;
 };
 SrkLaunchCtx* srk_get_launch_ctx();
 

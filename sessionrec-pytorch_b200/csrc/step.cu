@@ -779,12 +779,18 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   int rc = body_on_run();
   srk_set_launch_ctx(nullptr);
   bool ok = rc == SRK_OK && !ctx.failed;
+  static const bool debug = getenv("SESSREC_GRAPH_DEBUG") != nullptr;
   if (capture) {
     if (ctx.capturing) {
       const cudaError_t ce = cudaStreamEndCapture(run, &e.g.graph);
-      ok = ok && ce == cudaSuccess && e.g.graph != nullptr && cudaGraphInstantiate(&e.g.exec, e.g.graph, 0) == cudaSuccess;
+      cudaError_t ie = cudaSuccess;
+      ok = ok && ce == cudaSuccess && e.g.graph != nullptr && (ie = cudaGraphInstantiate(&e.g.exec, e.g.graph, 0)) == cudaSuccess;
+      if (debug)
+        fprintf(stderr, "[sessrec graph] capture: rc %d failed %d reason %d end-capture %d instantiate %d nodes %zu -> %s\n", rc,
+                (int)ctx.failed, ctx.fail_reason, (int)ce, (int)ie, e.g.nodes.size(), ok ? "ok" : "discarded");
     } else {
       ok = false;
+      if (debug) fprintf(stderr, "[sessrec graph] capture: the step never reached its capture boundary (rc %d)\n", rc);
     }
     if (!ok) {
       cudaGetLastError();
@@ -795,6 +801,9 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
     ok = ok && ctx.cursor == e.g.nodes.size();
     if (!ok) {
       ++g_graph_fallbacks;
+      if (debug)
+        fprintf(stderr, "[sessrec graph] update pass failed: rc %d reason %d cuda %d at launch %zu of %zu\n", rc, ctx.fail_reason,
+                ctx.fail_cuda, ctx.cursor, e.g.nodes.size());
       if (++e.fails > 3) {                            // this configuration keeps changing its kernel sequence
         e.g.destroy();
         e.bad = true;
