@@ -499,6 +499,8 @@ def main():
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': round(total_ms / args.steps, 4), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'dtype_note': 'fp32 parameters, activations and accumulation; each fp32 product of the catalog head runs as 3 bf16 '
+                          'tcgen05 MMAs (hi/lo split, ~1e-5 relative against fp64; parity bar 1e-4)',
             'config': dict(workload=workload_name(args.workload, cfg), parallelism=f'dp{world}', global_batch=world * cfg['B'],
                            l2='flushed between timed steps (256 MB write)', timing='CUDA events per step, max over ranks',
                            **{k: cfg[k] for k in ('V', 'd', 'B', 'order', 'layers', 'dropout')}),
