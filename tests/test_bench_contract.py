@@ -47,3 +47,15 @@ def test_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['value'] == d['value'] and d['cpu_baseline']['kind'] in ('port', 'reference')
     gpu = _last_line(sorted((ROOT / 'profiles').glob('r*_bench_cfg1.json'))[-1])
     assert d['config']['workload'] == gpu['config']['workload']                                  # both arms: same workload
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """The driver launches both arms the same way for N > 1: rank 0 alone times the CPU path, the other ranks exit 0."""
+    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29617', str(ROOT / 'bench.py'), '--impl', 'reference', '--gpus', '2',
+                        '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip().startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['value'] > 0
