@@ -97,3 +97,79 @@ class BatchPrefetcher:
             self.close()
         except Exception:                                        # noqa: BLE001
             pass
+
+
+class EpochBatches:
+    """Every batch of one pass over a dataset, built ONCE into one host buffer (optionally pinned) by a few threads, and
+    movable to the device in ONE copy: the batches of the pass are then contiguous slices of device memory and the training
+    loop does no per-step collate and no per-step H2D at all.  The reference's train loaders for SRGNN / MSGIFSR sample
+    sequentially (`main_msgifsr.py:156`), so the pass is the same every epoch; for a shuffled loader (`main_niser.py:86`)
+    build the next epoch's pass in the background from the permuted sample arrays.
+
+    items int32[T] / offs int32[n + 1] / labels int32[n]: all samples back to back (see `flatten_samples`)."""
+
+    ALIGN = 64                       # words: every batch starts on a 256-byte boundary of the buffer
+
+    def __init__(self, items, offs, labels, batch_size, kind='session', order=1, threads=4, pin=False, drop_last=False):
+        import numpy as np
+        from concurrent.futures import ThreadPoolExecutor
+        items = np.ascontiguousarray(items, np.int32)
+        offs = np.ascontiguousarray(offs, np.int32)
+        labels = np.ascontiguousarray(labels, np.int32)
+        n = len(offs) - 1
+        assert len(labels) == n and batch_size >= 1
+        bounds = [(lo, min(lo + batch_size, n)) for lo in range(0, n, batch_size)]
+        if drop_last and bounds and bounds[-1][1] - bounds[-1][0] < batch_size:
+            bounds.pop()
+        starts, pos = [], 0
+        for lo, hi in bounds:
+            starts.append(pos)
+            need = SessionBatch.batch_words(int(offs[hi]) - int(offs[lo]), hi - lo, kind, order)
+            pos += (need + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.buf = torch.empty(max(pos, 1), dtype=torch.int32, pin_memory=pin)
+        ends = starts[1:] + [pos]
+
+        def one(i):
+            lo, hi = bounds[i]
+            # offs keeps its absolute click positions: the builder indexes `items` with them, no per-batch copy
+            return SessionBatch.build_flat(items, offs[lo:hi + 1], labels[lo:hi], kind, order, out=self.buf[starts[i]:ends[i]])
+
+        if threads > 1 and len(bounds) > 1:
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                built = list(ex.map(one, range(len(bounds))))
+        else:
+            built = [one(i) for i in range(len(bounds))]
+        self._spans = [(s, s + b.buf.numel()) for s, b in zip(starts, built)]
+        self._hdrs = [b.hdr for b in built]
+
+    def __len__(self):
+        return len(self._spans)
+
+    def __getitem__(self, i):
+        s, e = self._spans[i]
+        return SessionBatch(self.buf[s:e], self._hdrs[i])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    @property
+    def nbytes(self):
+        return self.buf.numel() * 4
+
+    def to(self, device, non_blocking=True):
+        out = object.__new__(EpochBatches)
+        out.buf = self.buf.to(device, non_blocking=non_blocking)
+        out._spans, out._hdrs = self._spans, self._hdrs
+        return out
+
+
+def flatten_samples(samples):
+    """[(click sequence, label), ...] (e.g. an `AugmentedDataset`) -> (items int32[T], offs int32[n + 1], labels int32[n])."""
+    import numpy as np
+    n = len(samples)
+    lens = np.fromiter((len(samples[i][0]) for i in range(n)), dtype=np.int64, count=n)
+    offs = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=offs[1:])
+    items = np.fromiter((int(x) for i in range(n) for x in samples[i][0]), dtype=np.int32, count=int(offs[-1]))
+    labels = np.fromiter((int(samples[i][1]) for i in range(n)), dtype=np.int32, count=n)
+    return items, offs, labels

@@ -54,3 +54,27 @@ def test_build_flat_into_caller_buffer(pkg):
         pkg.SessionBatch.build_flat(items, offs, labels, 'ccs', 2, out=torch.empty(100, dtype=torch.int32))
     with pytest.raises(pkg._lib.SessRecError):
         pkg.SessionBatch.build_flat(items, offs, labels, 'ccs', 2, out=torch.empty(words, dtype=torch.int64))
+
+
+@pytest.mark.parametrize('kind,order,threads', [('session', 1, 1), ('ccs', 1, 4), ('ccs', 3, 3)])
+def test_epoch_batches_equal_per_batch_builds(pkg, kind, order, threads):
+    """One buffer for the whole pass: every slice is bit-identical to building that batch alone (also the short last one),
+    starts on a 256-byte boundary, and the pass survives `.to()` as one copy."""
+    from sessionrec_pytorch_b200.dataset import AugmentedDataset
+    from sessionrec_pytorch_b200.loader import EpochBatches, flatten_samples
+    from sessionrec_pytorch_b200.synthetic import SessionSampler
+    seqs, _ = SessionSampler(300, seed=9).sessions(40)
+    ds = AugmentedDataset([s + [1] for s in seqs])                 # every prefix of every session
+    samples = [ds[i] for i in range(len(ds))]
+    items, offs, labels = flatten_samples(ds)
+    assert len(offs) - 1 == len(ds) == len(labels)
+    ep = EpochBatches(items, offs, labels, 32, kind, order, threads=threads)
+    assert len(ep) == (len(ds) + 31) // 32
+    for i, b in enumerate(ep):
+        chunk = samples[i * 32:(i + 1) * 32]
+        ref = pkg.SessionBatch.build([s for s, _ in chunk], [l for _, l in chunk], kind, order)
+        assert b.B == len(chunk) == ref.B and torch.equal(b.buf, ref.buf)
+        assert (b.buf.data_ptr() - ep.buf.data_ptr()) % 256 == 0
+    moved = ep.to('cpu')
+    assert len(moved) == len(ep) and torch.equal(moved[len(ep) - 1].buf, ep[len(ep) - 1].buf)
+    assert len(EpochBatches(items, offs, labels, 32, kind, order, drop_last=True)) == len(ds) // 32
