@@ -228,6 +228,25 @@ def extra_cases(R, small, test_small):
             GOLD / 'train_extra_golden.pt')
 
 
+def edge_cases(R):
+    """Degenerate batches the reference still runs: only single-click sessions (a ccs graph without any edge, every k-gram
+    type reduced to its dummy node, SRGNN's self-loops), and a two-session batch (B == 1 breaks the reference's own
+    `squeeze()`, msgifsr.py:308)."""
+    print('models, edge-case batches (V=%d, d=%d):' % (V_SMALL, D_SMALL))
+    singles = [([5], 7), ([9], 3), ([5], 2), ([100], 5), ([7], 7), ([3], 1), ([250], 9), ([11], 4)]
+    two = [([4, 8, 4], 2), ([6], 1)]
+    models = {
+        'msgifsr_k1_single_clicks': model_case(R, 'MSGIFSR', singles, V_SMALL, D_SMALL, 1, K=1),
+        'msgifsr_k2_single_clicks': model_case(R, 'MSGIFSR', singles, V_SMALL, D_SMALL, 1, K=2),
+        'msgifsr_k1_extra_single_clicks': model_case(R, 'MSGIFSR', singles, V_SMALL, D_SMALL, 1, K=1, extra=True),
+        'msgifsr_k1_two_sessions': model_case(R, 'MSGIFSR', two, V_SMALL, D_SMALL, 1, K=1),
+        'msgifsr_k3_two_sessions': model_case(R, 'MSGIFSR', two, V_SMALL, D_SMALL, 1, K=3),
+        'srgnn_single_clicks': model_case(R, 'SRGNN', singles, V_SMALL, D_SMALL, 1),
+        'niser_two_sessions': model_case(R, 'NISER', two, V_SMALL, D_SMALL, 1),
+    }
+    th.save(models, GOLD / 'models_edge_golden.pt')
+
+
 def test_split(sessions):
     t = OC.augmented_samples(sessions[N_SESS:N_SESS + 60])
     return [(s, l) for s, l in t if max(s + [l]) < V_SMALL]
@@ -238,6 +257,9 @@ def main():
     R = ref_import.load()
     GOLD.mkdir(parents=True, exist_ok=True)
     sessions = ref_import.read_sessions(ref_import.REFERENCE_ROOT / 'datasets' / 'sample' / 'train.txt')
+    if '--only-edge' in sys.argv:
+        edge_cases(R)
+        return
     if '--only-extra' in sys.argv:
         extra_cases(R, OC.augmented_samples(sessions[:N_SESS]), test_split(sessions))
         return
@@ -290,6 +312,7 @@ def main():
     }
     th.save(models, GOLD / 'models_golden.pt')
     extra_cases(R, small, test_split(sessions))
+    edge_cases(R)
     th.save(dict(ggnn_d16=ggnn_case(R, b0, V_SMALL, D_SMALL), ggnn_d32=ggnn_case(R, b1, V_SMALL, 32)), GOLD / 'ggnn_golden.pt')
 
     print('training trajectories:')
