@@ -60,3 +60,83 @@ def test_models_refuse_to_run_on_cpu(pkg):
         m(b)
     with pytest.raises(pkg._lib.SessRecError, match='no CPU fallback'):
         m.train_step(b)
+
+
+class _FakeBatch:
+    def __init__(self, labels):
+        self.labels = labels
+
+    def to(self, device):
+        return self
+
+
+class _FakeModel:
+    """Stands in for a drop-in module: records the learning rate of every step, ranks the label at a scripted position."""
+
+    def __init__(self, rank_per_eval):
+        self.rank_per_eval, self.evals, self.lrs, self._opt = rank_per_eval, 0, [], None
+        self.training = True
+
+    def configure_optimizer(self, lr=1e-3, weight_decay=1e-4):
+        self._opt = dict(lr=lr, weight_decay=weight_decay)
+        return self._opt
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    def train_step(self, batch):
+        self.lrs.append(self._opt['lr'])
+        return torch.tensor(float(len(self.lrs)))
+
+    def topk(self, batch, k=20):
+        r = self.rank_per_eval[min(self.evals, len(self.rank_per_eval) - 1)]
+        out = torch.full((len(batch.labels), k), -1, dtype=torch.long)
+        if r <= k:
+            out[:, r - 1] = batch.labels
+        return out
+
+
+def _loaders(n_train=5, n_test=2):
+    lab = torch.arange(4)
+    return ([([_FakeBatch(lab)], lab) for _ in range(n_train)], [([_FakeBatch(lab)], lab) for _ in range(n_test)])
+
+
+def test_train_runner_follows_the_reference_epoch_loop(pkg):
+    """StepLR(3, 0.1) per epoch, evaluation before and after every epoch, early stop after `patience` epochs in which MRR and
+    HR both fell (`utils/train.py:57-127`)."""
+    from sessionrec_pytorch_b200.train import TrainRunner
+
+    class Counting(_FakeModel):
+        def topk(self, batch, k=20):
+            out = super().topk(batch, k)
+            self.calls = getattr(self, 'calls', 0) + 1
+            if self.calls % 2 == 0:            # two test batches per evaluate()
+                self.evals += 1
+            return out
+
+    # label rank per evaluate(): initial, then after epochs 0..: improving, then three epochs where the label leaves the top 20
+    m = Counting([5, 4, 2, 1, 30, 30, 30, 30, 30])
+    train, test = _loaders()
+    logs = []
+    r = TrainRunner('x', m, train, test, 'cpu', lr=1e-2, weight_decay=1e-4, patience=3)
+    assert m._opt == dict(lr=1e-2, weight_decay=1e-4)
+    mrr, hit = r.train(20, log_interval=2, log=logs.append)
+    assert (mrr, hit) == (1.0, 1.0)                                   # best epoch: rank 1
+    # epochs 0-2 improve, epochs 3-5 are bad -> stop inside epoch index 5 (6 epochs trained)
+    assert len(m.lrs) == 6 * 5 and r.epoch == 5
+    expect = [1e-2] * 15 + [1e-3] * 15
+    assert all(abs(a - b) < 1e-12 for a, b in zip(m.lrs, expect)), m.lrs
+    assert sum(s.startswith('Epoch') for s in logs) == 6 and any(s.startswith('Batch 2:') for s in logs)
+    assert m.training is False                                        # left in eval mode by the last evaluate()
+
+
+def test_train_runner_accepts_bare_batches(pkg):
+    from sessionrec_pytorch_b200.train import TrainRunner
+    m = _FakeModel([1])
+    lab = torch.arange(3)
+    r = TrainRunner('x', m, [_FakeBatch(lab)] * 4, [([_FakeBatch(lab)], lab)], 'cpu', lr=1e-3, weight_decay=0, patience=2)
+    r.train(1, log=lambda s: None)
+    assert len(m.lrs) == 4 and m._opt['weight_decay'] == 0 and abs(m._opt['lr'] - 1e-3) < 1e-15
