@@ -56,10 +56,12 @@ class AugmentedDataset:
         lo = int(self._start[s])
         return self._clicks[lo:lo + p].tolist(), int(self._clicks[lo + p])
 
-    def flat(self):
+    def flat(self, order=None):
         """(items int32[T], offs int32[n + 1], labels int32[n]) of all samples in index order: what
-        `SessionBatch.build_flat` / `loader.EpochBatches` take."""
-        sid, pos = self.index[:, 0], self.index[:, 1]
+        `SessionBatch.build_flat` / `loader.EpochBatches` take.  `order`: sample ids in the order a sampler would draw them
+        (e.g. `torch.randperm(len(ds))` for the shuffled loader of `main_niser.py:86`)."""
+        index = self.index if order is None else self.index[np.asarray(order, dtype=np.int64)]
+        sid, pos = index[:, 0], index[:, 1]
         offs = np.zeros(len(pos) + 1, np.int64)
         np.cumsum(pos, out=offs[1:])
         assert offs[-1] < 2 ** 31, 'more than 2^31 clicks in one pass: build it in pieces'
