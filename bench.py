@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py - train sessions/sec of the B200-native session-rec training path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1] [--also cfg2] [--parallelism dp|shard]
+                  [--impl reference]
 
 A "step" = one TrainRunner iteration (`src/utils/train.py:95-101`): forward + nll_loss + backward + Adam(L2) step
 over one synthetic batch of the named BASELINE.json configuration.  One process per GPU (torchrun sets RANK /
@@ -12,8 +13,12 @@ all-reduce per step (weak scaling).  Prints ONE JSON line on rank 0.
 `e2e`       the same metric through the public API with HOST (pinned) batch buffers: H2D copy of the batch and a
             D2H read of the loss inside every timed step.
 `roofline`  the dominant kernel family (catalog scoring GEMMs), timed live in isolation with CUDA events.
-`cpu_baseline` the oracle port (oracle/models.py, the restated reference) timed on this box's host cores on a bounded
-            sample of the same workload.  `--impl reference` times only that, as the reference arm.
+`cpu_baseline` the reference's own CPU implementation of the path timed on this box's host cores on a bounded sample
+            of the same workload: the UNMODIFIED reference sources (oracle/_ref, a byte-identical copy of
+            /root/reference/src made by oracle/build_ref.py) over oracle/dgl_shim, kind "reference"; the restated port
+            (oracle/models.py, kind "port") only when that copy is absent.  `--impl reference` times only that.
+`workloads` (N = 1) the same measurements for the other single-GPU configuration of BASELINE.json (cfg2 = SRGNN on the
+            Yoochoose1/64 shape, B = 2048, d = 256); the top-level keys are the headline workload named in `config`.
 """
 import argparse
 import json
@@ -125,6 +130,70 @@ def cpu_oracle_steps(cfg, sessions, steps, warmup):
             t_total += time.perf_counter() - t0
             n += ob['B']
     return n / t_total, cores, t_total
+
+
+def cpu_reference_steps(cfg, raw, steps, warmup):
+    """The UNMODIFIED reference on the host cores: its own model classes, its own collate_fn and the loop body of its own
+    `TrainRunner.train` (`src/utils/train.py:95-103`: zero_grad / model(*inputs) / isnan assert / nll_loss / backward /
+    optimizer.step / loss.item()) with the optimizer its `TrainRunner.__init__` builds, imported from oracle/_ref over
+    oracle/dgl_shim.  raw: [(seqs, labels)] python lists.  Returns dict(compute-only sessions/s, collate ms/batch, ...)."""
+    from oracle import ref_import
+    R = ref_import.load()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(123)
+    if cfg['model'] == 'MSGIFSR':
+        m = R.MSGIFSR(cfg['V'], 'synthetic', cfg['d'], cfg['layers'], dropout=cfg['dropout'], order=cfg['order'], extra=False,
+                      fusion=False)
+        fn = R.collate.collate_fn_factory_ccs((R.collate.seq_to_ccs_graph,), order=cfg['order'])
+    else:
+        m = getattr(R, cfg['model'])(cfg['V'], cfg['d'], cfg['layers'], cfg['dropout'])
+        fn = R.collate.collate_fn_factory(R.collate.seq_to_session_graph)
+    runner = R.train.TrainRunner('synthetic', m, [], [], torch.device('cpu'), lr=1e-3, weight_decay=1e-4, patience=3)
+    t0 = time.perf_counter()
+    batches = [fn(list(zip(s, l))) for s, l in raw]
+    collate_s = (time.perf_counter() - t0) / len(raw)
+    m.train()
+    t_total, n = 0.0, 0
+    for it in range(warmup + steps):
+        batch = batches[it % len(batches)]
+        t0 = time.perf_counter()
+        inputs, labels = R.train.prepare_batch(batch, torch.device('cpu'))
+        runner.optimizer.zero_grad()
+        scores = m(*inputs)
+        assert not torch.isnan(scores).any()
+        loss = torch.nn.functional.nll_loss(scores, labels)
+        loss.backward()
+        runner.optimizer.step()
+        loss.item()
+        if it >= warmup:
+            t_total += time.perf_counter() - t0
+            n += len(labels)
+    step_s = t_total / steps
+    return dict(value=n / t_total, cores=cores, seconds=t_total, collate_ms_per_batch=1e3 * collate_s,
+                with_collate=cfg['B'] / (step_s + collate_s), root=str(ref_import.REFERENCE_ROOT))
+
+
+def cpu_arm(cfg, workload, steps, warmup):
+    """cpu_baseline object for one workload: the unmodified reference when oracle/_ref (or /root/reference) is there, else
+    the restated port."""
+    from sessionrec_pytorch_b200.synthetic import SessionSampler
+    from oracle import ref_import
+    smp = SessionSampler(cfg['V'], seed=123)
+    raw = [smp.sessions(cfg['B']) for _ in range(min(4, steps + warmup))]
+    if ref_import.available():
+        r = cpu_reference_steps(cfg, raw, steps, warmup)
+        return dict(value=round(r['value'], 2), unit=UNIT, cores=r['cores'], kind='reference',
+                    sample=f"{steps} full steps (B={cfg['B']}) of {workload} after {warmup} warm-up, {r['seconds']:.1f} s of CPU work; "
+                           f"batches pre-collated (compute only, like the GPU arm's resident batches)",
+                    what='unmodified reference src/models + TrainRunner loop body + torch.optim.Adam over oracle/dgl_shim '
+                         '(DGL 0.7.2 is not installable offline), imported from ' + r['root'],
+                    collate_ms_per_batch=round(r['collate_ms_per_batch'], 2),
+                    value_with_reference_collate=round(r['with_collate'], 2))
+    v, cores, secs = cpu_oracle_steps(cfg, raw, steps, warmup)
+    return dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port',
+                sample=f"{steps} full steps (B={cfg['B']}) of {workload} after {warmup} warm-up, {secs:.1f} s",
+                what='oracle/models.py restatement (oracle/_ref absent)')
 
 
 def roofline_probe(cfg, device, pk):
@@ -326,19 +395,16 @@ def builder_probe(pkg, cfg, n=40):
 def reference_arm(args, cfg, rank, guard):
     if rank != 0:
         return
-    from sessionrec_pytorch_b200.synthetic import SessionSampler
-    smp = SessionSampler(cfg['V'], seed=123)
-    sessions = [smp.sessions(cfg['B']) for _ in range(min(4, args.steps + args.warmup))]
-    v, cores, secs = cpu_oracle_steps(cfg, sessions, args.steps, args.warmup)
-    sample = f"{args.steps} full steps (B={cfg['B']}) of {args.workload}, {secs:.1f} s of CPU work"
+    cb = cpu_arm(cfg, args.workload, args.steps, args.warmup)
+    v = cb['value']
     guard.emit({
         'impl': 'reference', 'metric': METRIC, 'value': round(v, 2), 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(1e3 * cfg['B'] / v, 3), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': dict(workload=workload_name(args.workload, cfg), **{k: cfg[k] for k in ('V', 'd', 'B', 'order', 'layers', 'dropout')}),
-        'cpu_baseline': dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port', sample=sample),
+        'cpu_baseline': cb,
         'e2e': dict(value=round(v, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-        'note': 'reference CPU path = oracle port of src/models + TrainRunner loop body (DGL is not installable here)'})
+        'note': cb['what']})
 
 
 def workload_name(key, cfg):
@@ -363,52 +429,28 @@ class StdoutGuard:
         os.dup2(2, 1)
 
 
-def main():
-    guard = StdoutGuard()
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--workload', default='cfg1')
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-gather-probe', action='store_true')
-    args = ap.parse_args()
-
-    rank = int(os.environ.get('RANK', 0))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    load_package()
-    from sessionrec_pytorch_b200.synthetic import CONFIGS, SessionSampler
-    cfg = dict(CONFIGS[args.workload])
-    if args.impl == 'reference':
-        if args.steps == 30 and args.warmup == 5:
-            args.steps, args.warmup = 5, 1
-        reference_arm(args, cfg, rank, guard)
-        return
-    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists for the product path)'
-    build()
-    pkg = load_package()
+def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
+    """Device-timed loop, end-to-end loop, roofline and CPU arm of ONE workload; returns the JSON object of that workload
+    (None on the ranks that do not print).  primary: also sample the clocks over a continuation, time the native batch
+    builder and the gather / scatter kernels."""
     from sessionrec_pytorch_b200 import ops
-    device = torch.device('cuda', local_rank)
-    torch.cuda.set_device(device)
-    group = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
-        group = dist.group.WORLD
+    from sessionrec_pytorch_b200.synthetic import SessionSampler
+    import torch.distributed as dist
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    pk = peaks()
+    shard = args.parallelism == 'shard' and world > 1
     model = build_model(cfg, device)
     model.configure_optimizer(lr=1e-3, weight_decay=1e-4)
-    smp = SessionSampler(cfg['V'], seed=123 + rank)
+    if shard:
+        model.shard_catalog(group)
+    step_group = None if shard else group
+    # data parallel: every rank draws its own sessions (weak scaling); catalog sharding: every rank sees the SAME global
+    # batch and scores its slice of the catalog (strong scaling)
+    smp = SessionSampler(cfg['V'], seed=123 + (0 if shard else rank))
     n_batches = 8
     host = []
     for _ in range(n_batches):
@@ -419,11 +461,10 @@ def main():
 
     # ---- device-timed region: K steps, inputs resident in HBM -------------------------------------------------
     for i in range(args.warmup):
-        model.train_step(resident[i % n_batches], group)
+        model.train_step(resident[i % n_batches], step_group)
     barrier()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(device.index)
     clocks.start()
-    k0 = ops.kernel_launches()
     evs = []
     launches = 0
     enqueue_s = 0.0
@@ -434,7 +475,7 @@ def main():
         kk = ops.kernel_launches()
         a.record()
         tq = time.perf_counter()
-        model.train_step(resident[(args.warmup + i) % n_batches], group)
+        model.train_step(resident[(args.warmup + i) % n_batches], step_group)
         enqueue_s += time.perf_counter() - tq
         b.record()
         launches += ops.kernel_launches() - kk
@@ -447,12 +488,13 @@ def main():
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms)
-    value = world * cfg['B'] * args.steps / (total_ms * 1e-3)
+    units = cfg['B'] if shard else world * cfg['B']              # sessions all ranks processed per step
+    value = units * args.steps / (total_ms * 1e-3)
     # The timed region lasts a few milliseconds, shorter than one nvidia-smi sampling period: take the clocks line again
     # over an untimed continuation of the same step loop (single process only - no collective may depend on it).
-    if world == 1:
+    if world == 1 and primary:
         try:
-            more = ClockSampler(local_rank)
+            more = ClockSampler(device.index)
             more.start()
             for i in range(1500):
                 model.train_step(resident[i % n_batches])
@@ -475,18 +517,18 @@ def main():
     for i in range(args.steps):
         hb = host[i % n_batches]
         db = hb.to(device, non_blocking=True)           # H2D of the whole batch (one pinned buffer)
-        loss = model.train_step(db, group)
+        loss = model.train_step(db, step_group)
         loss.item()                                     # D2H read of the step's loss (what TrainRunner does, train.py:103)
         h2d += hb.nbytes
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e = world * cfg['B'] * args.steps / float(e2e_s)
+    e2e = units * args.steps / float(e2e_s)
 
     # ---- the same loop fed by the native batch builder (raw clicks -> graph batch on one background thread) --------
     e2e_build = None
-    if world == 1:                      # single process only: no collective inside, so a failure here cannot desynchronise ranks
+    if world == 1 and primary:          # single process only: no collective inside, so a failure here cannot desynchronise ranks
         try:
             from sessionrec_pytorch_b200.loader import BatchPrefetcher
             raw_smp = SessionSampler(cfg['V'], seed=777)
@@ -512,33 +554,98 @@ def main():
 
     out = None
     if rank == 0:
-        roof = roofline_probe(cfg, device, pk)
-        roof_gs = gather_scatter_probe(device, pk) if not args.no_gather_probe else None
+        par = f'catalog-sharded x{world} (session encoder replicated, every rank scores V/{world} rows)' if shard else f'dp{world}'
         out = {
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': round(total_ms / args.steps, 4), 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': 'strong' if shard else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'dtype_note': 'fp32 parameters, activations and accumulation; each fp32 product of the catalog head runs as 3 bf16 '
                           'tcgen05 MMAs (hi/lo split, ~1e-5 relative against fp64; parity bar 1e-4)',
-            'config': dict(workload=workload_name(args.workload, cfg), parallelism=f'dp{world}', global_batch=world * cfg['B'],
+            'config': dict(workload=workload_name(key, cfg), parallelism=par, global_batch=units,
                            l2='flushed between timed steps (256 MB write)', timing='CUDA events per step, max over ranks',
                            **{k: cfg[k] for k in ('V', 'd', 'B', 'order', 'layers', 'dropout')}),
             'clocks': clk, 'gpu_launches': int(launches), 'launches_per_step': round(launches / args.steps, 1),
             'e2e': dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=int(h2d / args.steps), d2h_bytes_per_step=4,
                         timing='wall clock over K steps incl. H2D batch copy + loss.item() per step'),
             'wall_s_timed_region': round(t_wall, 4), 'host_enqueue_ms_per_step': round(1e3 * enqueue_s / args.steps, 4),
-            'roofline': roof, 'roofline_gather_scatter': roof_gs,
-            'batch_builder': builder_probe(pkg, cfg) if world == 1 else None, 'e2e_with_batch_build': e2e_build,
+            'roofline': roofline_probe(cfg, device, pk),
         }
+        if shard or world > 1:
+            out['collectives'] = getattr(model, 'collectives_per_step', lambda: None)()
+        if primary:
+            out['roofline_gather_scatter'] = gather_scatter_probe(device, pk) if not args.no_gather_probe else None
+            out['batch_builder'] = builder_probe(pkg, cfg) if world == 1 else None
+            out['e2e_with_batch_build'] = e2e_build
+    del model, resident, flush
+    torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        nst = max(3, min(120, int(12.0 * 5000 / cfg['B'])))          # ~10-20 s of CPU work at ~5 k sessions/s
+        out['cpu_baseline'] = cpu_arm(cfg, key, nst, 1)
+    return out
+
+
+def main():
+    guard = StdoutGuard()
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--workload', default=None, help='cfg1 (default; cfg4 with --parallelism shard)')
+    ap.add_argument('--also', default=None, help='comma list of further workloads measured into the `workloads` block '
+                                                 '(default: cfg2 on a single-GPU run of cfg1)')
+    ap.add_argument('--parallelism', default='dp', choices=['dp', 'shard'],
+                    help='N > 1: dp = data parallel, weak scaling (default); shard = item-catalog rows sharded across the ranks, '
+                         'strong scaling on BASELINE configs[4]')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gather-probe', action='store_true')
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = 'cfg4' if args.parallelism == 'shard' else 'cfg1'
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    load_package()
+    from sessionrec_pytorch_b200.synthetic import CONFIGS
+    cfg = dict(CONFIGS[args.workload])
+    if args.impl == 'reference':
+        if args.steps == 30 and args.warmup == 5:
+            args.steps, args.warmup = 5, 1
+        reference_arm(args, cfg, rank, guard)
+        return
+    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback exists for the product path)'
+    build()
+    pkg = load_package()
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+        group = dist.group.WORLD
+    pk = peaks()
+    also = args.also
+    if also is None:
+        also = 'cfg2' if (world == 1 and args.workload == 'cfg1') else ''
+    out = measure(args.workload, cfg, args, pkg, device, group, world, rank, pk, True)
+    extra = {}
+    for key in [k for k in also.split(',') if k and k != args.workload]:
+        try:
+            extra[key] = measure(key, dict(CONFIGS[key]), args, pkg, device, group, world, rank, pk, False)
+        except Exception as e:                                  # noqa: BLE001 - a secondary workload never costs the headline
+            if world > 1:
+                raise                                             # a rank that stops would leave the others in a collective
+            extra[key] = dict(error=f'{type(e).__name__}: {e}')
+            torch.cuda.synchronize()
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
-            sessions = [SessionSampler(cfg['V'], seed=123).sessions(cfg['B']) for _ in range(4)]
-            nst = max(3, min(120, int(12.0 * 5000 / cfg['B'])))          # ~10-20 s of CPU work at ~5 k sessions/s
-            v, cores, secs = cpu_oracle_steps(cfg, sessions, nst, 1)
-            out['cpu_baseline'] = dict(value=round(v, 2), unit=UNIT, cores=cores, kind='port',
-                                       sample=f"{nst} full steps (B={cfg['B']}) of {args.workload} after 1 warm-up, {secs:.1f} s")
+        if extra:
+            out['headline_workload'] = args.workload
+            out['workloads'] = extra
         guard.emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -329,7 +329,10 @@ int srk_segmean_bwd(const float* dHpre, const int* seg, int B, int d, float* dX,
 
 /* ---- optimizer (next-row: utils/train.py:70-74, torch.optim.Adam with L2-in-grad) ------------------------------
  * Flat buffers; decay[i] per element group is given by seg_off[S+1] / seg_decay[S]. step is 1-based; grad_scale
- * multiplies the raw gradient first (1/world_size after a data-parallel all-reduce). */
+ * multiplies the raw gradient first (1/world_size after a data-parallel all-reduce).  A segment with seg_decay < 0 is
+ * INACTIVE and left untouched (parameter, moments): torch.optim.Adam skips parameters whose .grad is None, which is what
+ * the reference's forward leaves on every parameter it never reaches (SRGNN's dead GGNN layers, MSGIFSR's lint / linq /
+ * link / beta / unused GRU ...). */
 int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                   const long long* seg_off, const float* seg_decay, int n_seg, float lr, float beta1, float beta2,
                   float eps, int step, float grad_scale, void* stream);

@@ -209,7 +209,10 @@ def train_case(R, name, samples, test_samples, V, d, K, bs, steps, seed=123, ext
     return dict(model=name, V=V, d=d, K=K, bs=bs, steps=steps, extra=extra, params=sd0, losses=losses,
                 samples=[(list(map(int, s)), int(l)) for s, l in samples[:steps * bs]],
                 test_samples=[(list(map(int, s)), int(l)) for s, l in test_samples],
-                final_embedding=m.state_dict()[emb].detach().clone(), mrr=float(mrr), hit=float(hit))
+                final_embedding=m.state_dict()[emb].detach().clone(), mrr=float(mrr), hit=float(hit),
+                # every tensor of the reference's state_dict after the last step: parameters the forward never reaches
+                # (grad None) must still sit at their initial values - torch.optim.Adam skips them
+                final_state={k: v.detach().clone() for k, v in m.state_dict().items() if k != emb and v.is_floating_point()})
 
 
 def extra_cases(R, small, test_small):

@@ -1,16 +1,23 @@
 """Import the UNMODIFIED reference (`/root/reference/src/...`) on top of `oracle/dgl_shim`.
 
-TEST INFRASTRUCTURE ONLY, and only usable in the build container: `/root/reference` does not exist on
-the GPU box, so nothing under `tests/ -m gpu`, `bench.py` or `__graft_entry__.smoke()` may call this.
-It exists to (1) validate the restatement in `oracle/models.py` / `oracle/collate.py` and (2) generate
-the golden vectors committed under `tests/golden/` (`oracle/make_golden.py`).
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  `/root/reference` exists in the build container only; on the GPU box
+the one caller is the reference arm of `bench.py` (`--impl reference` / `cpu_baseline`), which times the reference's
+own code from the byte-identical copy under the git-ignored `oracle/_ref/` (`oracle/build_ref.py`).  Nothing under
+`tests/ -m gpu`, `__graft_entry__.smoke()` or the product package calls this.  It exists to (1) validate the
+restatement in `oracle/models.py` / `oracle/collate.py`, (2) generate the golden vectors committed under
+`tests/golden/` (`oracle/make_golden.py`, `oracle/make_convergence_golden.py`) and (3) be the CPU baseline.
 """
 import os
 import sys
 from pathlib import Path
 
+_HERE = Path(__file__).resolve().parent
+_SHIM = _HERE / 'dgl_shim'
+# /root/reference in the build container; on the GPU box the byte-identical copy of the hot-path sources that
+# oracle/build_ref.py placed under the git-ignored oracle/_ref/ (bench.py's reference arm only)
 REFERENCE_ROOT = Path(os.environ.get('SESSREC_REFERENCE_ROOT', '/root/reference'))
-_SHIM = Path(__file__).resolve().parent / 'dgl_shim'
+if not (REFERENCE_ROOT / 'src' / 'models' / 'srgnn.py').is_file() and (_HERE / '_ref' / 'src' / 'models' / 'srgnn.py').is_file():
+    REFERENCE_ROOT = _HERE / '_ref'
 
 
 def available():

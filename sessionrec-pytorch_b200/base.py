@@ -54,8 +54,14 @@ class SessRecModule(nn.Module):
             raise _lib.SessRecError(f'{type(self).__name__}: parameters live on {p0.device}; this path only runs on '
                                     'CUDA (sm_100a) and has no CPU fallback - call model.to("cuda") first')
         if self._flat is None or not self._flat.valid():
+            # the parameters were moved / re-assigned (model.to(), load_state_dict(assign=True), p.data = ...): re-flatten and
+            # carry the optimizer over by parameter name - hyper-parameters, step count and both moments survive
+            old = self.optimizer_state_dict() if self._opt is not None else None
             self._flat = FlatParams(self)
             self._opt = None
+            self._native = None
+            if old is not None:
+                self.load_optimizer_state_dict(old)
         return self._flat
 
     def set_dropout_seed(self, seed):
@@ -336,35 +342,104 @@ class SessRecModule(nn.Module):
         return dshat
 
     # ---- fused training step (body of `TrainRunner.train`, utils/train.py:95-101) ---------------------------
+    def _inactive_params(self, batch=None):
+        """Names of the parameters the reference's forward never reaches in this configuration (their .grad stays None, so
+        torch.optim.Adam never touches them: no update, no weight decay).  batch: some are data dependent."""
+        return frozenset()
+
     def configure_optimizer(self, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        """torch.optim.Adam(fix_weight_decay(model), lr, weight_decay) of `TrainRunner.__init__` (`utils/train.py:70-74`)
+        for the fused train_step: one flat buffer per moment, per-parameter decay / activity as segments."""
         fp = self._ensure_flat()
-        seg_off, seg_decay = fp.decay_segments(weight_decay)
-        self._opt = dict(lr=lr, betas=betas, eps=eps, step=0, seg_off=seg_off, seg_decay=seg_decay,
+        seg_off, _ = fp.decay_segments(weight_decay)
+        self._opt = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, step=0, seg_off=seg_off, seg_decay={},
                          m=torch.zeros_like(fp.data), v=torch.zeros_like(fp.data), n_seg=len(fp.names))
         return self._opt
 
-    def train_step(self, batch, group=None):
+    def set_lr(self, lr):
+        """`scheduler.step()` of the reference loop (`utils/train.py:111`): the learning rate of the following steps."""
+        self._ensure_flat()
+        if self._opt is None:
+            self.configure_optimizer(lr=lr)
+        self._opt['lr'] = float(lr)
+
+    def _seg_decay(self, batch=None):
+        """Per-segment decay (negative = inactive) for this batch's set of unreached parameters; cached on the device."""
+        o = self._opt
+        key = self._inactive_params(batch)
+        t = o['seg_decay'].get(key)
+        if t is None:
+            t = o['seg_decay'][key] = self._flat.decay_segments(o['weight_decay'], key)[1]
+        return t
+
+    def optimizer_state_dict(self):
+        """Hyper-parameters, step count and the Adam moments keyed by parameter name (checkpoint / resume; the reference
+        itself never saves anything)."""
+        o, fp = self._opt, self._flat
+        if o is None:
+            raise _lib.SessRecError('optimizer_state_dict: call configure_optimizer() first')
+        return dict(lr=o['lr'], betas=o['betas'], eps=o['eps'], weight_decay=o['weight_decay'], step=o['step'],
+                    exp_avg={n: v.detach().clone() for n, v in zip(fp.names, fp.views(o['m']))},
+                    exp_avg_sq={n: v.detach().clone() for n, v in zip(fp.names, fp.views(o['v']))})
+
+    def load_optimizer_state_dict(self, sd):
+        o = self.configure_optimizer(lr=sd['lr'], weight_decay=sd['weight_decay'], betas=sd['betas'], eps=sd['eps'])
+        fp = self._flat
+        missing = [n for n in fp.names if n not in sd['exp_avg'] or n not in sd['exp_avg_sq']]
+        if missing:
+            raise _lib.SessRecError(f'load_optimizer_state_dict: no moments for {missing[:3]} ...')
+        for n, m, v in zip(fp.names, fp.views(o['m']), fp.views(o['v'])):
+            m.copy_(sd['exp_avg'][n])
+            v.copy_(sd['exp_avg_sq'][n])
+        o['step'] = int(sd['step'])
+        return o
+
+    def train_step(self, batch, group=None, global_batch=None):
         """zero_grad + forward + nll_loss + backward + Adam step, all on the current stream; returns the loss
         as a 0-d device tensor (no host sync).  With a torch.distributed process group (data parallel: every rank
-        owns a slice of the global batch) the flat gradient buffer is summed with ONE NCCL all-reduce and the
-        1/world_size mean is folded into the Adam kernel."""
+        owns a slice of the global batch) the flat gradient buffer is summed with ONE NCCL all-reduce.  Every rank's
+        backward is seeded with B_local / B_global, so the sum is the gradient of the GLOBAL-batch mean loss - the
+        reference's single-device step - also when the shards are uneven (last batch of an epoch); a rank whose shard
+        is empty (batch None or B == 0) contributes zeros and still joins the collective.  global_batch: B_global when
+        the caller knows it (equal shards: world * B); otherwise it is all-reduced (one extra 4-byte collective)."""
         fp = self._ensure_flat()
         if self._opt is None:
             self.configure_optimizer()
         o = self._opt
         with torch.no_grad():
-            loss, tape = self._fwd(batch, 'loss', need_grad=True)
-            ops.fill(fp.grad, 0.0)
-            self._bwd(tape, self._one(), fp.grad)
-            scale = 1.0
+            seed = self._dp_weight(batch, group, global_batch)
+            if batch is None or batch.B == 0:
+                loss = torch.zeros((), dtype=torch.float32, device=fp.data.device)
+                ops.fill(fp.grad, 0.0)
+            else:
+                loss, tape = self._fwd(batch, 'loss', need_grad=True)
+                ops.fill(fp.grad, 0.0)
+                self._bwd(tape, seed, fp.grad)
             if group is not None:
                 import torch.distributed as dist
                 dist.all_reduce(fp.grad, group=group)
-                scale = 1.0 / dist.get_world_size(group)
             o['step'] += 1
-            ops.adam_step(fp.data, fp.grad, o['m'], o['v'], o['seg_off'], o['seg_decay'], o['n_seg'], o['lr'],
-                          o['betas'][0], o['betas'][1], o['eps'], o['step'], scale)
+            ops.adam_step(fp.data, fp.grad, o['m'], o['v'], o['seg_off'], self._seg_decay(batch), o['n_seg'], o['lr'],
+                          o['betas'][0], o['betas'][1], o['eps'], o['step'], 1.0)
         return loss
+
+    def _dp_weight(self, batch, group, global_batch):
+        """Device scalar the backward is seeded with: 1 on a single device, B_local / B_global under data parallelism."""
+        if group is None:
+            return self._one()
+        import torch.distributed as dist
+        dev = self._flat.data.device
+        b_local = 0 if batch is None else batch.B
+        if global_batch is None:
+            cnt = torch.tensor([float(b_local)], dtype=torch.float32, device=dev)
+            tot = cnt.clone()
+            dist.all_reduce(tot, group=group)
+            return cnt / tot
+        cache = self.__dict__.setdefault('_dp_w', {})
+        key = (b_local, int(global_batch), str(dev))
+        if key not in cache:
+            cache[key] = torch.tensor([b_local / float(global_batch)], dtype=torch.float32, device=dev)
+        return cache[key]
 
     def _one(self):
         if getattr(self, '_one_t', None) is None or self._one_t.device != self._flat.data.device:

@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
       int mid = (lo + hi + 1) >> 1;
       if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    adam_update(p, g, m, v, i, seg_decay[lo], lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale);
+    const float dec = seg_decay[lo];
+    if (dec < 0.f) continue;              // parameter the reference's forward never reaches (grad is None): Adam skips it
+    adam_update(p, g, m, v, i, dec, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale);
   }
 }
 
@@ -205,7 +207,9 @@ __global__ void __launch_bounds__(256) adam_split_kernel(float* __restrict__ p, 
         int mid = (lo + hi + 1) >> 1;
         if (seg_off[mid] <= i) lo = mid; else hi = mid - 1;
       }
-      adam_update(p, g, m, v, i, seg_decay[lo], lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale);
+      const float dec = seg_decay[lo];
+      if (dec < 0.f) continue;            // inactive segment (see adam_kernel)
+      adam_update(p, g, m, v, i, dec, lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale);
     }
   }
 }

@@ -58,6 +58,43 @@ __global__ void __launch_bounds__(TK_THREADS) topk_rows_kernel(const float* __re
     }
   }
   __syncthreads();
+  if (s_count > TK_CAP) {
+    // More than TK_CAP - k values tie EXACTLY with the k-th largest (constant / saturated rows): the unordered collection
+    // above may have dropped values strictly greater than the k-th.  Exact slow path: every key > kth first (fewer than k
+    // of them), then the ties in ascending index order until k candidates are there (what the sort below would pick).
+    __syncthreads();
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int j = tid; j < V; j += TK_THREADS) {
+      uint32_t u = f2key(z[j]);
+      if (u > kth) {
+        int slot = atomicAdd(&s_count, 1);
+        cand_u[slot] = u; cand_i[slot] = j;
+      }
+    }
+    __syncthreads();
+    int have = s_count;                          // < k
+    __syncthreads();
+    for (int j0 = 0; j0 < V && have < k; j0 += TK_THREADS) {
+      const int j = j0 + tid;
+      const bool tie = j < V && f2key(z[j]) == kth;
+      const uint32_t bal = __ballot_sync(SRK_FULL, tie);
+      if ((tid & 31) == 0) hist[tid >> 5] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int w = 0; w < TK_THREADS / 32; ++w) {
+        const int c = hist[w];
+        if (w < (tid >> 5)) before += c;
+        total += c;
+      }
+      const int slot = have + before + __popc(bal & ((1u << (tid & 31)) - 1u));
+      if (tie && slot < k) { cand_u[slot] = kth; cand_i[slot] = j; }
+      have = min(k, have + total);
+      __syncthreads();
+    }
+    if (tid == 0) s_count = have;
+    __syncthreads();
+  }
   const int n = min(s_count, TK_CAP);
   for (int i = n + tid; i < TK_CAP; i += TK_THREADS) { cand_u[i] = 0u; cand_i[i] = 0x7fffffff; }
   __syncthreads();

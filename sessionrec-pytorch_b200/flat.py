@@ -40,11 +40,13 @@ class FlatParams:
         p, o = self.params[i], self.offsets[i]
         return flat[o:o + p.numel()].view(p.shape)
 
-    def decay_segments(self, weight_decay):
+    def decay_segments(self, weight_decay, inactive=()):
         """(seg_off int64[S+1], seg_decay fp32[S]) on the device: `fix_weight_decay` semantics of the reference
-        (`src/utils/train.py:12-23`): names containing bias / batch_norm / activation get no L2 term."""
+        (`src/utils/train.py:12-23`): names containing bias / batch_norm / activation get no L2 term.  Names in `inactive`
+        get -1: the Adam kernels leave such a segment untouched, like torch.optim.Adam skips a parameter whose grad is None."""
         offs = list(self.offsets) + [self.total]
-        dec = [0.0 if any(t in n for t in ('bias', 'batch_norm', 'activation')) else float(weight_decay)
+        dec = [-1.0 if n in inactive else
+               (0.0 if any(t in n for t in ('bias', 'batch_norm', 'activation')) else float(weight_decay))
                for n in self.names]
         dev = self.data.device
         return (torch.tensor(offs, dtype=torch.int64, device=dev), torch.tensor(dec, dtype=torch.float32, device=dev))

@@ -237,6 +237,36 @@ class MSGIFSR(SessRecModule):
         # the REnorm head needs the session's own logits apart from the rest: it runs on the materialised scores
         return not self.extra and super()._use_flash(d, mode)
 
+    def _inactive_params(self, batch=None):
+        """Parameters whose .grad stays None in the reference (SURVEY.md section 0 / 9): lint / linq / link, the PReLU, beta;
+        alpha unless the order-fusion head runs; sc_sr unless the REnorm head runs (which only ever uses module 0,
+        msgifsr.py:283); the GRU of the last order (GRUs[k - 2] serves order k); the `inter` convolutions at order 1; and,
+        batch dependent, every convolution whose relation has no edge in this batch (HeteroGraphConv skips it)."""
+        K = self.order
+        rel_edges = None
+        if batch is not None:
+            rel_edges = {}
+            for r in batch.rels:
+                et = 'inter' if r['name'].startswith('inter') else r['name']
+                rel_edges[et] = rel_edges.get(et, 0) + int(r['M'])
+        out = []
+        for n, _ in self.named_parameters():
+            dead = False
+            if n == 'beta' or '.lint.' in n or '.linq.' in n or '.link.' in n or '.activation.' in n:
+                dead = True
+            elif n == 'alpha':
+                dead = not (K > 1 and self.fusion)
+            elif n.startswith('sc_sr.'):
+                dead = not (self.extra and n.startswith('sc_sr.0.'))
+            elif n.startswith('expander.GRUs.'):
+                dead = int(n.split('.')[2]) > K - 2
+            elif '.mods.' in n:
+                et = n.split('.mods.')[1].split('.')[0]
+                dead = (et == 'inter' and K == 1) or (rel_edges is not None and rel_edges.get(et, 0) == 0)
+            if dead:
+                out.append(n)
+        return frozenset(out)
+
     # ---- native fused step (csrc/step.cu) ------------------------------------------------------------------------
     def _native_ok(self, batch):
         return (self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
@@ -253,12 +283,12 @@ class MSGIFSR(SessRecModule):
                   'fc_sr.0.weight']
         return np.ascontiguousarray([fp.offsets[fp.index[n]] for n in names], dtype=np.int64)
 
-    def train_step(self, batch, group=None):
+    def train_step(self, batch, group=None, global_batch=None):
         """One TrainRunner iteration in ONE C call (srk_msgifsr_train_step): zero_grad, forward, nll_loss, backward,
         Adam.  Falls back to the staged Python composition for configurations the native step does not cover."""
         fp = self._ensure_flat()
-        if not self._native_ok(batch) or not self.native_step:
-            return super().train_step(batch, group)
+        if batch is None or batch.B == 0 or not self._native_ok(batch) or not self.native_step:
+            return super().train_step(batch, group, global_batch)
         import ctypes
         from ._lib import lib, ptr
         if self._opt is None:
@@ -280,6 +310,8 @@ class MSGIFSR(SessRecModule):
         if group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(group)
+        gseed = self._dp_weight(batch, group, global_batch)       # B_local / B_global: the all-reduced sum is the global mean
+        seg_decay = self._seg_decay(batch)
         o['step'] += 1
         loss = torch.empty((), dtype=torch.float32, device=fp.data.device)
 
@@ -289,9 +321,9 @@ class MSGIFSR(SessRecModule):
                    ptr(fp.grad), ctypes.c_void_p(st['slots'].ctypes.data), self.num_items, self.embedding_dim,
                    self.num_layers, float(p), ctypes.c_uint64(seed),
                    int(self.use_tensor_cores) | (2 if self.fused_lse else 0) | (4 if self.flash_ce else 0), ptr(st['ws']),
-                   st['ws_bytes'], ptr(self._one()), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
-                   ptr(o['seg_off']), ptr(o['seg_decay']), o['n_seg'], float(o['lr']), float(o['betas'][0]),
-                   float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0 / world, phase, int(self.head_chunks), stream)
+                   st['ws_bytes'], ptr(gseed), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
+                   ptr(o['seg_off']), ptr(seg_decay), o['n_seg'], float(o['lr']), float(o['betas'][0]),
+                   float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0, phase, int(self.head_chunks), stream)
         if world == 1:
             call(0)
         else:

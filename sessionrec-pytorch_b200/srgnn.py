@@ -110,6 +110,10 @@ class SRGNN(SessRecModule):
         for weight in self.parameters():
             weight.data.uniform_(-stdv, stdv)
 
+    def _inactive_params(self, batch=None):
+        # the GGNN layers are evaluated and discarded (srgnn.py:135-142): their parameters never get a gradient
+        return frozenset(n for n, _ in self.named_parameters() if n.startswith('layers.'))
+
     # ---- forward / backward over the kernels -----------------------------------------------------------------
     def _fwd(self, batch, mode, need_grad=True):
         t = batch.types[1]

@@ -65,7 +65,7 @@ class TrainRunner:
                     t = time.time()
                     acc = None
                 self.batch += 1
-            self.model._opt['lr'] = self._lr(self.epoch + 1)           # scheduler.step() (`:111`)
+            self.model.set_lr(self._lr(self.epoch + 1))           # scheduler.step() (`:111`)
             mrr, hit = evaluate(self.model, self.test_loader, self.device)
             log(f'Epoch {self.epoch}: MRR = {mrr * 100:.3f}%, Hit = {hit * 100:.3f}%')
             if mrr < max_mrr and hit < max_hit:

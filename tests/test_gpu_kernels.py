@@ -292,6 +292,8 @@ def test_topk_rows(ops, V):
     Z[0, :50] = 1.25                      # exact ties: lowest ids win
     Z[1] = -7.0                           # fully degenerate row
     Z[2, 17] = float('inf')
+    Z[3] = 0.5                            # > 1024 exact ties at the k-th value and five larger values at the END of the row:
+    Z[3, V - 5:] = torch.tensor([1.0, 5.0, 3.0, 2.0, 4.0])       # the unordered candidate collection would drop them
     Zd = torch.zeros(B, ldz, device=DEV)
     Zd[:, :V] = Z.to(DEV)
     idx = torch.empty(B, k, dtype=torch.int32, device=DEV)
@@ -301,8 +303,9 @@ def test_topk_rows(ops, V):
     assert torch.equal(val.cpu(), rv), 'top-k values must match torch.topk exactly'
     got = idx.cpu().long()
     for b in range(B):
-        if b in (0, 1):
+        if b in (0, 1, 3):
             continue
         assert torch.equal(got[b], ri[b]), (b, got[b], ri[b])
     assert got[1].tolist() == list(range(k))
+    assert got[3].tolist() == [V - 4, V - 1, V - 3, V - 2, V - 5] + list(range(k - 5))
     assert set(got[0].tolist()) == set(Z[0].topk(k)[1].tolist()) or (Z[0][got[0]] >= Z[0].topk(k)[0][-1]).all()

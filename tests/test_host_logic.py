@@ -87,6 +87,9 @@ class _FakeModel:
     def eval(self):
         self.training = False
 
+    def set_lr(self, lr):
+        self._opt['lr'] = lr
+
     def train_step(self, batch):
         self.lrs.append(self._opt['lr'])
         return torch.tensor(float(len(self.lrs)))
