@@ -69,6 +69,14 @@ int srk_gemm(int M, int N, int K, const float* A, long long sa_m, long long sa_k
 int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, const float* Alo, long long lda, const float* Bhi,
                   const float* Blo, long long ldb, float* C, long long ldc, float alpha, int accumulate, int split_k,
                   void* stream);
+/* The same tensor-core GEMM from PLAIN fp32 operands (every nn.Linear / `@` of the session encoder once the node count
+ * makes it worth a tensor-core launch: srgnn.py:42-45,80-81,143; msgifsr.py:139-140,271; gatconv.py:273-274): one launch
+ * splits both operands into dense TF32 hi / lo copies inside `scratch` (srk_tc_gemm_scratch_floats floats, 16-byte aligned),
+ * then srk_umma_gemm's kernel runs.  bias[N] (optional) is added once.  Any N (forms 1 / 2 are tiled over 256 columns);
+ * split_k <= 0 picks a split that fills the SMs when accumulate != 0. */
+long long srk_tc_gemm_scratch_floats(int form, int M, int N, int K);
+int srk_tc_gemm(int form, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, float* C,
+                long long ldc, const float* bias, float alpha, int accumulate, int split_k, float* scratch, void* stream);
 /* Persistent forward scoring kernel with a fused log-sum-exp epilogue: Z[M, ldz] = alpha * A B^T (A[M,K], B[N,K] as TF32
  * hi/lo pairs), lse[M] = row log-sum-exp, nll[M] = lse - Z[m, labels[m]] (labels / nll may be NULL).  One CTA per SM,
  * 128 x 256 tiles, double-buffered TMEM.  part = scratch of 4 * ceil(N/256) * M + M floats.  Replaces srk_umma_gemm(form 0)
@@ -86,6 +94,8 @@ int srk_split_tf32(const float* X, long long ldx, int rows, int cols, float* hi,
  * d % 16 == 0.  Operands are bf16 bit patterns (uint16_t) with row pitches lds / lde (multiples of 8). */
 /* hi = bf16(x) (round to nearest even), lo = bf16(x - hi); [rows, cols] with pitches ldx / ldo. */
 int srk_split_bf16(const float* X, long long ldx, int rows, int cols, uint16_t* hi, uint16_t* lo, long long ldo, void* stream);
+/* 1 when the fused head is built for this embedding dim, else 0 */
+int srk_flash_ce_supported(int d);
 /* floats of scratch (`part`) srk_flash_ce_fwd needs */
 long long srk_flash_ce_part_floats(int B, int V);
 /* lse[B] = row log-sum-exp of the logits; nll[B] (optional) = lse - logit of labels[b] (0 where the label lies outside
@@ -367,6 +377,23 @@ int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, floa
                            int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat, const long long* seg_off_dev,
                            const float* seg_decay_dev, int n_seg, float lr, float beta1, float beta2, float eps,
                            int adam_step, float grad_scale, int phase, int head_chunks, void* stream);
+
+/* ---- native training step (SRGNN / NISER+): utils/train.py:95-101 around srgnn.py:131-148 / niser.py:130-157 ----
+ * Same contract as srk_msgifsr_train_step for a session-graph batch (kind 'session').  slot_off_host: offsets (floats) into
+ * the flat parameter / gradient buffers of embedding.weight; per layer gru.weight_ih, gru.weight_hh, gru.bias_ih,
+ * gru.bias_hh, W1.weight, W2.weight; readout.fc_u.weight, readout.fc_v.weight, readout.fc_v.bias, readout.fc_e.weight,
+ * fc_sr.weight.  niser: double-normalised gather, normalised session / catalog rows, logits x scale (niser.py:134-156).
+ * dead_layers: evaluate the GGNN layers whose output the reference discards (srgnn.py:135-142) on a side stream.
+ * gseed_dev: device scalar the backward is seeded with (1, or B_local / B_global under data parallelism).  flags / phase /
+ * the optimizer arguments as in srk_msgifsr_train_step. */
+long long srk_srgnn_workspace_bytes(int B, int N, int M, int V, int d, int L);
+int srk_srgnn_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
+                         const long long* slot_off_host, int V, int d, int L, int niser, float scale, int dead_layers,
+                         float dropout_p, uint64_t seed, int flags, void* workspace, long long workspace_bytes,
+                         const float* gseed_dev, float* loss_out, int do_adam, float* exp_avg, float* exp_avg_sq,
+                         long long n_flat, const long long* seg_off_dev, const float* seg_decay_dev, int n_seg, float lr,
+                         float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase, void* stream);
+
 
 /* ---- native batch builder (host; next-row: utils/data/collate.py:61-85,87-217,219-256) ---------------------------
  * Sessions are given as a flat item array + offsets. kind 0 = session graph (weights, self-loop rule), kind 1 =

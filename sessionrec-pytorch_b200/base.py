@@ -364,12 +364,13 @@ class SessRecModule(nn.Module):
         self._opt['lr'] = float(lr)
 
     def _seg_decay(self, batch=None):
-        """Per-segment decay (negative = inactive) for this batch's set of unreached parameters; cached on the device."""
+        """Per-segment decay (negative = inactive) for this batch's set of unreached parameters; cached on the device by
+        the batch's set of edge-less relations (the only data-dependent input), so a step pays one dict lookup."""
         o = self._opt
-        key = self._inactive_params(batch)
+        key = batch.empty_relations() if batch is not None else None
         t = o['seg_decay'].get(key)
         if t is None:
-            t = o['seg_decay'][key] = self._flat.decay_segments(o['weight_decay'], key)[1]
+            t = o['seg_decay'][key] = self._flat.decay_segments(o['weight_decay'], self._inactive_params(batch))[1]
         return t
 
     def optimizer_state_dict(self):

@@ -40,6 +40,18 @@ class SessionBatch:
         self.N1 = int(h[_TYPE_TAB])                               # nodes of type s1
         self.M1 = int(h[_REL_TAB + 2]) if int(h[5]) > 0 else 0    # edges of the first relation
 
+    def rel_edge_counts(self):
+        """{relation name: number of edges}, read from the host header only (no tensor views are built)."""
+        h = self.hdr
+        return {_rel_name(int(h[_REL_TAB + _TAB_W * r + 12])): int(h[_REL_TAB + _TAB_W * r + 2]) for r in range(int(h[5]))}
+
+    def empty_relations(self):
+        """Names of the relations without a single edge in this batch (hashable; cached)."""
+        e = self.__dict__.get('_empty_rels')
+        if e is None:
+            e = self.__dict__['_empty_rels'] = frozenset(n for n, m in self.rel_edge_counts().items() if m == 0)
+        return e
+
     def __getattr__(self, name):
         if name in SessionBatch._LAZY:
             self._build_views()

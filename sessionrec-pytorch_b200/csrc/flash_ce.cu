@@ -790,6 +790,8 @@ extern "C" int srk_split_bf16(const float* X, long long ldx, int rows, int cols,
   return SRK_OK;
 }
 
+extern "C" int srk_flash_ce_supported(int d) { return d >= 16 && d <= 128 && d % 16 == 0; }
+
 extern "C" long long srk_flash_ce_part_floats(int B, int V) {
   // upper bound that does not depend on the SM count: 2 partial pairs per (catalog tile, row) + label logits
   return 4LL * srk_cdiv(V, TV) * B + B;

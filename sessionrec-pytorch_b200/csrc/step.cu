@@ -5,123 +5,12 @@
 // drive stage by stage (msgifsr.py::MSGIFSR._fwd/_bwd is the readable twin and the parity reference of this file).
 // All temporaries come from a caller-provided device workspace through a bump allocator; nothing is allocated,
 // nothing synchronises; ~60 kernel launches are enqueued back to back on the given stream.
-#include <stdlib.h>
-
-#include <vector>
-
 #include <map>
 #include <mutex>
 
-#include "launch.cuh"
+#include "step_common.cuh"
 
-namespace {
-
-constexpr int H = SRK_HEADS;
-
-// Debug aid (SESSREC_STEP_TIMING=1): CUDA events at the stage boundaries of the critical-path stream.  The events of
-// a step are read back a few steps LATER (when they have completed anyway), so the host keeps running ahead of the GPU
-// and the numbers are the steady-state in-pipeline stage times, which neither the cold-cache ncu launch list nor a
-// synchronised step can give.  SESSREC_STEP_TIMING=2 synchronises after every step instead.
-struct StageTimer {
-  static constexpr int RING = 4, MAXEV = 24;
-  struct Slot {
-    cudaEvent_t ev[MAXEV];
-    const char* names[MAXEV];
-    int n = 0;
-    bool made = false;
-  };
-  int mode;
-  cudaStream_t st;
-  Slot* cur = nullptr;
-  static Slot* ring() {
-    static Slot r[RING];
-    return r;
-  }
-  static int& counter() {
-    static int c = 0;
-    return c;
-  }
-  static void print(Slot& s) {
-    if (s.n < 2) return;
-    float total = 0.f;
-    if (cudaEventElapsedTime(&total, s.ev[0], s.ev[s.n - 1]) != cudaSuccess) return;
-    fprintf(stderr, "[step timing] total %.1f us:", total * 1e3f);
-    for (int i = 1; i < s.n; ++i) {
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, s.ev[i - 1], s.ev[i]);
-      fprintf(stderr, " %s=%.1f", s.names[i], ms * 1e3f);
-    }
-    fprintf(stderr, "\n");
-  }
-  explicit StageTimer(cudaStream_t s) : st(s) {
-    const char* e = getenv("SESSREC_STEP_TIMING");
-    mode = (e && srk_launch_mode() == SRK_LAUNCH_DIRECT) ? atoi(e) : 0;
-    if (!mode) return;
-    cur = &ring()[counter() % RING];
-    if (!cur->made) {
-      for (int i = 0; i < MAXEV; ++i) cudaEventCreate(&cur->ev[i]);
-      cur->made = true;
-    } else if (mode == 1) {
-      if (cudaEventQuery(cur->ev[cur->n - 1]) == cudaSuccess) print(*cur);     // the step recorded RING steps ago
-    }
-    cur->n = 0;
-    ++counter();
-    mark("start");
-  }
-  void mark(const char* name) {
-    if (!mode || cur->n >= MAXEV) return;
-    cudaEventRecord(cur->ev[cur->n], st);
-    cur->names[cur->n] = name;
-    ++cur->n;
-  }
-  void report() {
-    if (mode != 2) return;
-    cudaStreamSynchronize(st);
-    print(*cur);
-  }
-};
-
-// Side streams of the native step.  The session encoder is a tree of small, latency-bound kernels (N ~ 2 k nodes): the
-// two GAT convolutions of a layer (graph / reversed graph), the weight-gradient GEMMs and the catalog backward are
-// independent of each other, so they are enqueued on side streams (fork / join with events) and overlap on the 148 SMs.
-// SESSREC_STREAMS=0 keeps everything on the caller's stream.
-struct SideStreams {
-  static constexpr int NS = 7, NE = 64;
-  cudaStream_t s[NS];     // [0] critical path, [1..3] parallel encoder chains, [4] [5] weight gradients, [6] bulk catalog passes
-  cudaEvent_t ev[NE];
-  cudaEvent_t ev_cat;     // "catalog backward done" (recorded early, waited for late: not from the round-robin pool)
-  int next = 0;
-  bool ok = false;
-  int init() {
-    // The latency-bound encoder chain gets the highest priority: its few-CTA kernels must not queue behind the
-    // thousands of CTAs of the catalog-wide passes (row normalisation backward, zero_grad) that run beside it.
-    int least = 0, greatest = 0;
-    SRK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    const int mid = greatest + (least - greatest) / 2;
-    const int prio[NS] = {greatest, greatest, greatest, greatest, mid, mid, least};
-    for (int i = 0; i < NS; ++i) SRK_CUDA(cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, prio[i]));
-    for (int i = 0; i < NE; ++i) SRK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
-    SRK_CUDA(cudaEventCreateWithFlags(&ev_cat, cudaEventDisableTiming));
-    ok = true;
-    return SRK_OK;
-  }
-  // everything enqueued on `to` after this call waits for what is on `from` now
-  int order(cudaStream_t from, cudaStream_t to) {
-    const int mode = srk_launch_mode();
-    if (mode == SRK_LAUNCH_UPDATE || mode == SRK_LAUNCH_SKIP) return SRK_OK;     // the graph already holds the edge
-    return order_always(from, to);
-  }
-  int order_always(cudaStream_t from, cudaStream_t to) {
-    if (from == to) return SRK_OK;
-    cudaEvent_t e = ev[next];
-    next = (next + 1) % NE;
-    SRK_CUDA(cudaEventRecord(e, from));
-    SRK_CUDA(cudaStreamWaitEvent(to, e, 0));
-    return SRK_OK;
-  }
-};
-
-SideStreams* side_streams() {
+SideStreams* srk_side_streams() {
   static SideStreams per_dev[16];
   static int enabled = -1;
   if (enabled < 0) {
@@ -136,18 +25,10 @@ SideStreams* side_streams() {
   return ss;
 }
 
-struct Arena {
-  uint8_t* base;
-  size_t cap, off;
-  bool ok;
-  float* f(size_t n) { return reinterpret_cast<float*>(raw(n * sizeof(float))); }
-  uint8_t* raw(size_t bytes) {
-    size_t a = (off + 255) & ~(size_t)255;
-    if (a + bytes > cap) { ok = false; off = a + bytes; return base; }
-    off = a + bytes;
-    return base + a;
-  }
-};
+
+namespace {
+
+constexpr int H = SRK_HEADS;
 
 // batch buffer layout (csrc/batch_builder.cu)
 constexpr int TYPE_TAB = 16, REL_TAB = 80;
@@ -255,7 +136,7 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   const bool umma = (use_umma & 1) && d <= 256;
   const bool fused_lse = (use_umma & 2) != 0;      // bit 1: persistent forward kernel with the fused LSE epilogue
   // bit 2: fused scoring + CE head (csrc/flash_ce.cu): no (B, V) logits in memory, bf16 x 3 tensor-core products
-  const bool flash = umma && (use_umma & 4) != 0 && d >= 16 && d <= 128 && d % 16 == 0;
+  const bool flash = umma && (use_umma & 4) != 0 && srk_flash_ce_supported(d);
   const bool drop = dropout_p > 0.f;
   Arena ar{reinterpret_cast<uint8_t*>(workspace), (size_t)workspace_bytes, 0, true};
   auto P = [&](int slot) { return params + slot_off_host[slot]; };
@@ -265,7 +146,7 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   auto dcfg = [&](uint32_t site) { srk_dropout c; c.p = dropout_p; c.site = site; c.seed = seed; return c; };
 
   // with side streams the caller passes our own high-priority stream s[0] and orders it against the user's stream
-  SideStreams* ss = side_streams();
+  SideStreams* ss = srk_side_streams();
   StageTimer tm(st);
   // h1..h3: high-priority chains beside the critical path; s2 / s3: weight gradients; s4: catalog-wide bulk passes
   cudaStream_t h1 = ss ? ss->s[1] : st, h2 = ss ? ss->s[2] : st, h3 = ss ? ss->s[3] : st;
@@ -483,13 +364,7 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   // ---- forward / backward boundary: every side stream has been joined into `st` -------------------------------------
   // The forward half is always launched kernel by kernel (the GPU starts working while the host is still enqueueing);
   // the backward half is what gets captured into / replayed from a CUDA graph (see srk_msgifsr_train_step).
-  if (SrkLaunchCtx* lc = srk_get_launch_ctx()) {
-    if (lc->mode_after_boundary == SRK_LAUNCH_CAPTURE) {
-      SRK_CUDA(cudaStreamBeginCapture(lc->capture_stream, cudaStreamCaptureModeThreadLocal));
-      lc->capturing = true;
-    }
-    lc->mode = lc->mode_after_boundary;
-  }
+  SRK_TRY(srk_step_boundary());
   // the backward needs the row log-sum-exps, not their mean: the loss reduction runs beside the head's backward (s2 is
   // joined before the optimizer step)
   SRK_TRY(order(st, s2));
@@ -705,64 +580,40 @@ struct GraphEntry {
 
 }  // namespace
 
-// phase: 0 = everything; 1 = zero_grad + forward + backward only (no Adam): lets the caller all-reduce the gradients;
-// 2 = Adam only.
-//
-// Host cost: the step is ~60 kernels on 7 streams.  Launched one by one that is ~0.36 ms of CPU per step (2.7 us per
-// launch + ~60 event record / wait calls + memsets), more than the GPU needs once several ranks share the host.  After two
-// warm-up steps the sequence is therefore captured ONCE into a CUDA graph (per model configuration); every later step
-// only rewrites the kernel-node parameters (shapes and pointers change with the batch, the sequence does not) and issues
-// one cudaGraphLaunch.  SESSREC_GRAPH=0 disables it; any mismatch falls back to plain launches for that step.
-extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
-                                      const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed,
-                                      int use_umma, void* workspace, long long workspace_bytes, const float* one_dev,
-                                      float* loss_out, int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat,
-                                      const long long* seg_off_dev, const float* seg_decay_dev, int n_seg, float lr,
-                                      float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase,
-                                      int head_chunks, void* stream) {
-  cudaStream_t caller = (cudaStream_t)stream;
-  if (phase == 2) {
-    return srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2,
-                         eps, adam_step, grad_scale, caller);
+int srk_step_boundary() {
+  if (SrkLaunchCtx* lc = srk_get_launch_ctx()) {
+    if (lc->mode_after_boundary == SRK_LAUNCH_CAPTURE) {
+      SRK_CUDA(cudaStreamBeginCapture(lc->capture_stream, cudaStreamCaptureModeThreadLocal));
+      lc->capturing = true;
+    }
+    lc->mode = lc->mode_after_boundary;
   }
+  return SRK_OK;
+}
+
+// Host cost: a step is ~60 kernels on 7 streams.  Launched one by one that is ~0.36 ms of CPU per step (2.7 us per
+// launch + ~60 event record / wait calls + memsets), more than the GPU needs once several ranks share the host.  After two
+// warm-up steps the sequence is therefore captured ONCE into a CUDA graph (per model configuration `key`); every later
+// step only rewrites the kernel-node parameters (shapes and pointers change with the batch, the sequence does not) and
+// issues one cudaGraphLaunch.  SESSREC_GRAPH=0 disables it; any mismatch falls back to plain launches for that step.
+int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body_on) {
   // The step runs on our own high-priority stream s[0] (the user's stream may be the legacy default stream, which can
   // neither be prioritised nor captured); it is ordered after / before the user's stream with events.
-  SideStreams* ss0 = side_streams();
+  SideStreams* ss0 = srk_side_streams();
   cudaStream_t run = ss0 ? ss0->s[0] : caller;
-  auto body_on_run = [&]() {
-    return step_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, dropout_p, seed, use_umma, workspace,
-                     workspace_bytes, one_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg,
-                     lr, beta1, beta2, eps, adam_step, grad_scale, phase, head_chunks, (void*)run);
-  };
+  auto body_on_run = [&]() { return body_on((void*)run); };
   auto body = [&]() {                     // plain launches
     if (ss0) SRK_TRY(ss0->order_always(caller, run));
     SRK_TRY(body_on_run());
     if (ss0) SRK_TRY(ss0->order_always(run, caller));
     return (int)SRK_OK;
   };
-  if (g_graphs_on < 0) {
-    const char* e = getenv("SESSREC_GRAPH");
-    g_graphs_on = !e ? 2 : (e[0] == '0' ? 0 : 1);
-  }
-  // auto: replay pays off when the host is the bottleneck, i.e. when several ranks share the CPU (measured on 8 x B200:
-  // 0.83 -> 0.32 ms of enqueue per step, 4.8 M -> 6.8 M sessions/s); a single rank is GPU-bound either way and keeps the
-  // plain launches, whose first kernels start while the rest is still being enqueued
-  const bool want_graph = g_graphs_on == 1 || (g_graphs_on == 2 && phase == 1);
   const char* timing = getenv("SESSREC_STEP_TIMING");
-  if (!want_graph || side_streams() == nullptr || (timing && timing[0] != '0')) return body();
+  if (!want_graph || ss0 == nullptr || (timing && timing[0] != '0')) return body();
 
   static std::mutex mu;
   static std::map<unsigned long long, GraphEntry> cache;
   std::lock_guard<std::mutex> lock(mu);
-  int dev = 0;
-  SRK_CUDA(cudaGetDevice(&dev));
-  const int has_edges = batch_hdr_host[REL_TAB + 2] > 0;
-  const unsigned long long key = ((unsigned long long)(batch_hdr_host[1] & 0xFFFFF) << 44) | ((unsigned long long)(d & 0x3FF) << 34) |
-                                 ((unsigned long long)(V & 0x3FFFF) << 16) | ((unsigned long long)(dev & 15) << 12) |
-                                 ((unsigned long long)(L & 15) << 8) | ((unsigned long long)(use_umma & 7) << 5) |
-                                 ((unsigned long long)(dropout_p > 0.f) << 4) | ((unsigned long long)(phase & 1) << 3) |
-                                 ((unsigned long long)(do_adam != 0) << 2) | ((unsigned long long)has_edges << 1) |
-                                 (unsigned long long)(head_chunks > 1);
   GraphEntry& e = cache[key];
   ++e.seen;
   if (e.bad || e.seen <= 2) return body();          // warm-up steps also run every one-time cudaFuncSetAttribute
@@ -826,6 +677,48 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   }
   SRK_TRY(ss0->order_always(run, caller));
   return SRK_OK;
+}
+
+// 0 never, 1 always, 2 auto (data-parallel steps: phase 1)
+bool srk_step_want_graph(int phase) {
+  if (g_graphs_on < 0) {
+    const char* e = getenv("SESSREC_GRAPH");
+    g_graphs_on = !e ? 2 : (e[0] == '0' ? 0 : 1);
+  }
+  // auto: replay pays off when the host is the bottleneck, i.e. when several ranks share the CPU (measured on 8 x B200:
+  // 0.83 -> 0.32 ms of enqueue per step, 4.8 M -> 6.8 M sessions/s); a single rank is GPU-bound either way and keeps the
+  // plain launches, whose first kernels start while the rest is still being enqueued
+  return g_graphs_on == 1 || (g_graphs_on == 2 && phase == 1);
+}
+
+// phase: 0 = everything; 1 = zero_grad + forward + backward only (no Adam): lets the caller all-reduce the gradients;
+// 2 = Adam only.
+extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
+                                      const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed,
+                                      int use_umma, void* workspace, long long workspace_bytes, const float* one_dev,
+                                      float* loss_out, int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat,
+                                      const long long* seg_off_dev, const float* seg_decay_dev, int n_seg, float lr,
+                                      float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase,
+                                      int head_chunks, void* stream) {
+  cudaStream_t caller = (cudaStream_t)stream;
+  if (phase == 2) {
+    return srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2,
+                         eps, adam_step, grad_scale, caller);
+  }
+  int dev = 0;
+  SRK_CUDA(cudaGetDevice(&dev));
+  const int has_edges = batch_hdr_host[REL_TAB + 2] > 0;
+  const unsigned long long key = ((unsigned long long)(batch_hdr_host[1] & 0xFFFFF) << 44) | ((unsigned long long)(d & 0x3FF) << 34) |
+                                 ((unsigned long long)(V & 0x3FFFF) << 16) | ((unsigned long long)(dev & 15) << 12) |
+                                 ((unsigned long long)(L & 15) << 8) | ((unsigned long long)(use_umma & 7) << 5) |
+                                 ((unsigned long long)(dropout_p > 0.f) << 4) | ((unsigned long long)(phase & 1) << 3) |
+                                 ((unsigned long long)(do_adam != 0) << 2) | ((unsigned long long)has_edges << 1) |
+                                 (unsigned long long)(head_chunks > 1);
+  return srk_step_driver(caller, key, srk_step_want_graph(phase), [&](void* run) {
+    return step_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, dropout_p, seed, use_umma, workspace,
+                     workspace_bytes, one_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg,
+                     lr, beta1, beta2, eps, adam_step, grad_scale, phase, head_chunks, run);
+  });
 }
 
 extern "C" int srk_set_graph_mode(int on) {

@@ -76,6 +76,7 @@ struct UmmaParams {
   long long ldc;
   float alpha;
   int atomic;             // 1: atomicAdd epilogue (split-K / accumulate), 0: plain store
+  const float* bias;      // optional [N]: added once (by the first split-K slice)
   uint32_t idesc;
   uint32_t tmem_cols;
 };
@@ -191,6 +192,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
+          if (p.bias != nullptr && blockIdx.z == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] += p.bias[n0 + c0 + j];
+          }
           store_chunk(stile, v, p.C + n0 + c0, p.ldc, m0 + q * 32, p.M, nvalid, lane, p.atomic != 0);
         }
       }
@@ -409,12 +415,111 @@ __global__ void split_tf32_kernel(const float* __restrict__ X, long long ldx, in
   }
 }
 
+// TF32 hi / lo split of TWO pitched fp32 matrices into dense copies in ONE launch (the operand pair of srk_tc_gemm)
+struct Split2 {
+  const float* X[2];
+  float *hi[2], *lo[2];
+  long long ldx[2], ldo[2];
+  int rows[2], cols[2];
+  long long n4[2];        // float4 groups per matrix (cols rounded up to 4; ldo is a multiple of 4)
+};
+
+__global__ void __launch_bounds__(256) split2_tf32_kernel(const Split2 sp) {
+  const long long total = sp.n4[0] + sp.n4[1];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int w = t >= sp.n4[0];
+    const long long q = w ? t - sp.n4[0] : t;
+    const int c4 = (sp.cols[w] + 3) >> 2;
+    const long long r = q / c4;
+    const int c = (int)(q - r * c4) * 4;
+    const float* src = sp.X[w] + r * sp.ldx[w] + c;
+    float x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (c + j < sp.cols[w]) ? src[j] : 0.f;
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
+      l[j] = x[j] - h[j];
+    }
+    *reinterpret_cast<float4*>(sp.hi[w] + r * sp.ldo[w] + c) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(sp.lo[w] + r * sp.ldo[w] + c) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+int umma_gemm_impl(int form, int M, int N, int K, const float* Ahi, const float* Alo, long long lda, const float* Bhi,
+                   const float* Blo, long long ldb, float* C, long long ldc, const float* bias, float alpha, int accumulate,
+                   int split_k, void* stream);
+
 }  // namespace
 
 // form: 0 = NT (A[M,K], B[N,K]), 1 = NN (A[M,K], B[K,N]), 2 = TN (A[K,M], B[K,N]).  All row-major with pitches lda / ldb.
 extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, const float* Alo, long long lda,
                              const float* Bhi, const float* Blo, long long ldb, float* C, long long ldc, float alpha,
                              int accumulate, int split_k, void* stream) {
+  return umma_gemm_impl(form, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, nullptr, alpha, accumulate, split_k, stream);
+}
+
+static inline long long r4(long long x) { return (x + 3) / 4 * 4; }
+
+// floats of scratch srk_tc_gemm needs: dense hi / lo copies of both operands
+extern "C" long long srk_tc_gemm_scratch_floats(int form, int M, int N, int K) {
+  const long long a = form == 2 ? (long long)K * r4(M) : (long long)M * r4(K);
+  const long long b = form == 0 ? (long long)N * r4(K) : (long long)K * r4(N);
+  return 2 * (a + b) + 64;
+}
+
+// C (+)= alpha * op(A) op(B) (+ bias) from PLAIN fp32 operands on the tcgen05 tensor cores: one launch splits both operands
+// into TF32 hi / lo pairs (scratch), then the 3xTF32 kernel runs.  Same forms as srk_umma_gemm; any N (forms 1 and 2 are
+// tiled over 256 output columns).  split_k <= 0 picks a split that fills the SMs (needs accumulate).
+extern "C" int srk_tc_gemm(int form, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+                           float* C, long long ldc, const float* bias, float alpha, int accumulate, int split_k,
+                           float* scratch, void* stream) {
+  SRK_REQUIRE(form >= 0 && form <= 2, "tc_gemm: bad form %d", form);
+  if (M <= 0 || N <= 0) return SRK_OK;
+  SRK_REQUIRE(K > 0 && scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0, "tc_gemm: bad arguments");
+  Split2 sp;
+  sp.X[0] = A; sp.ldx[0] = lda;
+  sp.X[1] = B; sp.ldx[1] = ldb;
+  sp.rows[0] = form == 2 ? K : M; sp.cols[0] = form == 2 ? M : K;
+  sp.rows[1] = form == 0 ? N : K; sp.cols[1] = form == 0 ? K : N;
+  float* w = scratch;
+  for (int i = 0; i < 2; ++i) {
+    sp.ldo[i] = r4(sp.cols[i]);
+    sp.n4[i] = (long long)sp.rows[i] * (sp.ldo[i] / 4);
+    sp.hi[i] = w; w += (long long)sp.rows[i] * sp.ldo[i];
+    sp.lo[i] = w; w += (long long)sp.rows[i] * sp.ldo[i];
+  }
+  long long g = (sp.n4[0] + sp.n4[1] + 255) / 256;
+  if (g > 148LL * 8) g = 148LL * 8;
+  srk_launch(split2_tf32_kernel, (int)g, 256, 0, (cudaStream_t)stream, sp);
+  SRK_LAUNCH_CHECK();
+  const int nstep = form == 0 ? N : 256;
+  for (int n0 = 0; n0 < N; n0 += nstep) {
+    const int nc = N - n0 < nstep ? N - n0 : nstep;
+    int S = split_k;
+    if (S <= 0) {
+      if (!accumulate) S = 1;
+      else {
+        const int bn = form == 0 ? 128 : nc;
+        const long long tiles = (long long)((M + 127) / 128) * ((nc + bn - 1) / bn);
+        S = (int)(148 / (tiles < 1 ? 1 : tiles));
+        if (S < 1) S = 1;
+      }
+    }
+    const float* bh = form == 0 ? sp.hi[1] : sp.hi[1] + n0;
+    const float* bl = form == 0 ? sp.lo[1] : sp.lo[1] + n0;
+    SRK_TRY(umma_gemm_impl(form, M, nc, K, sp.hi[0], sp.lo[0], sp.ldo[0], bh, bl, sp.ldo[1], C + n0, ldc,
+                           bias ? bias + n0 : nullptr, alpha, accumulate, S, stream));
+  }
+  return SRK_OK;
+}
+
+namespace {
+int umma_gemm_impl(int form, int M, int N, int K, const float* Ahi, const float* Alo, long long lda, const float* Bhi,
+                   const float* Blo, long long ldb, float* C, long long ldc, const float* bias, float alpha, int accumulate,
+                   int split_k, void* stream) {
   SRK_REQUIRE(form >= 0 && form <= 2, "umma_gemm: bad form %d", form);
   if (M <= 0 || N <= 0) return SRK_OK;
   SRK_REQUIRE(K > 0, "umma_gemm: K must be positive");
@@ -442,6 +547,7 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
   S = (nkb + p.kb_per_split - 1) / p.kb_per_split;
   p.C = C; p.ldc = ldc; p.alpha = alpha;
   p.atomic = accumulate ? 1 : 0;
+  p.bias = bias;
   p.tmem_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
@@ -480,6 +586,7 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }
+}  // namespace
 
 extern "C" int srk_split_tf32(const float* X, long long ldx, int rows, int cols, float* hi, float* lo, long long ldo,
                               void* stream) {

@@ -246,9 +246,9 @@ class MSGIFSR(SessRecModule):
         rel_edges = None
         if batch is not None:
             rel_edges = {}
-            for r in batch.rels:
-                et = 'inter' if r['name'].startswith('inter') else r['name']
-                rel_edges[et] = rel_edges.get(et, 0) + int(r['M'])
+            for name, m in batch.rel_edge_counts().items():
+                et = 'inter' if name.startswith('inter') else name
+                rel_edges[et] = rel_edges.get(et, 0) + m
         out = []
         for n, _ in self.named_parameters():
             dead = False

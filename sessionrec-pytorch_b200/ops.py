@@ -46,12 +46,43 @@ def gemm(M, N, K, A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, a_idx=None, b_idx=None, 
           ptr(bias), float(alpha), int(bool(accumulate)), int(split_k if accumulate else 1))
 
 
+# Encoder GEMMs go to the tcgen05 tensor cores (srk_tc_gemm: 3xTF32, fp32-faithful) once they are big enough to pay for
+# the operand-split launch; below that the fp32 CUDA-core kernel wins on latency.  SESSREC_TC_GEMM=0 disables the routing.
+import os as _os
+
+TC_GEMM = _os.environ.get('SESSREC_TC_GEMM', '1') != '0' and _os.environ.get('SESSREC_NO_UMMA', '0') != '1'
+TC_MIN_MACS = int(_os.environ.get('SESSREC_TC_MIN_MACS', str(1 << 24)))
+
+
+def _tc_ok(M, N, K, *mats):
+    if not TC_GEMM or M * N * K < TC_MIN_MACS or K < 32 or N < 16:
+        return False
+    for t, ld in mats:
+        if t.data_ptr() % 16 or ld % 4:
+            return False
+    return True
+
+
+def tc_gemm(form, M, N, K, A, lda, Bm, ldb, C, ldc, bias=None, alpha=1.0, accumulate=False, split_k=0):
+    """C (+)= alpha * op(A) op(B) (+ bias) on the tensor cores from plain fp32 operands (form 0: A[M,K] B[N,K]; 1: A[M,K] B[K,N];
+    2: A[K,M] B[K,N])."""
+    _need_cuda(A, Bm, C)
+    n = int(_lib.lib().functions['srk_tc_gemm_scratch_floats'](form, M, N, K))
+    scratch = torch.empty(n, dtype=torch.float32, device=C.device)
+    _call('srk_tc_gemm', form, M, N, K, ptr(A), lda, ptr(Bm), ldb, ptr(C), ldc, ptr(bias), float(alpha),
+          int(bool(accumulate)), int(split_k), ptr(scratch))
+
+
 def linear_nt(X, W, C, M=None, K=None, lda=None, ldc=None, a_idx=None, c_idx=None, bias=None, alpha=1.0,
               accumulate=False):
     """C[M, N] (+)= alpha * X[M, K] @ W[N, K]^T (+ bias)."""
     N, Kw = W.shape
     K = Kw if K is None else K
     M = X.shape[0] if M is None else M
+    lda_ = X.stride(0) if lda is None else lda
+    if a_idx is None and c_idx is None and _tc_ok(M, N, K, (X, lda_), (W, W.stride(0))):
+        return tc_gemm(0, M, N, K, X, lda_, W, W.stride(0), C, C.stride(0) if ldc is None else ldc, bias=bias, alpha=alpha,
+                       accumulate=accumulate, split_k=1)
     gemm(M, N, K, X, X.stride(0) if lda is None else lda, 1, W, 1, W.stride(0), C, C.stride(0) if ldc is None else ldc,
          a_idx=a_idx, c_idx=c_idx, bias=bias, alpha=alpha, accumulate=accumulate)
 
@@ -60,7 +91,11 @@ def mm_nn(A, Bm, C, M=None, lda=None, ldc=None, c_idx=None, alpha=1.0, accumulat
     """C[M, N] (+)= alpha * A[M, K] @ Bm[K, N]."""
     K, N = Bm.shape
     M = A.shape[0] if M is None else M
-    gemm(M, N, K, A, A.stride(0) if lda is None else lda, 1, Bm, Bm.stride(0), 1, C, C.stride(0) if ldc is None else ldc,
+    lda_ = A.stride(0) if lda is None else lda
+    if c_idx is None and _tc_ok(M, N, K, (A, lda_), (Bm, Bm.stride(0))):
+        return tc_gemm(1, M, N, K, A, lda_, Bm, Bm.stride(0), C, C.stride(0) if ldc is None else ldc, alpha=alpha,
+                       accumulate=accumulate, split_k=1)
+    gemm(M, N, K, A, lda_, 1, Bm, Bm.stride(0), 1, C, C.stride(0) if ldc is None else ldc,
          c_idx=c_idx, alpha=alpha, accumulate=accumulate)
 
 
@@ -69,7 +104,11 @@ def mm_tn(A, Bm, C, K=None, lda=None, ldb=None, ldc=None, b_idx=None, alpha=1.0,
     K = A.shape[0] if K is None else K
     M = A.shape[1] if M is None else M
     N = Bm.shape[1] if N is None else N
-    gemm(M, N, K, A, 1, A.stride(0) if lda is None else lda, Bm, Bm.stride(0) if ldb is None else ldb, 1, C,
+    lda_, ldb_ = A.stride(0) if lda is None else lda, Bm.stride(0) if ldb is None else ldb
+    if b_idx is None and accumulate and _tc_ok(M, N, K, (A, lda_), (Bm, ldb_)):
+        return tc_gemm(2, M, N, K, A, lda_, Bm, ldb_, C, C.stride(0) if ldc is None else ldc, alpha=alpha, accumulate=True,
+                       split_k=0)
+    gemm(M, N, K, A, 1, lda_, Bm, ldb_, 1, C,
          C.stride(0) if ldc is None else ldc, b_idx=b_idx, alpha=alpha, accumulate=accumulate, split_k=0)
 
 
@@ -91,7 +130,7 @@ def split_tf32(X, ldx, rows, cols, hi, lo, ldo):
 # ---- fused scoring + cross-entropy head (csrc/flash_ce.cu) ---------------------------------------------------
 
 def flash_ce_supported(d):
-    return 16 <= d <= 128 and d % 16 == 0
+    return bool(_lib.lib().functions['srk_flash_ce_supported'](int(d)))
 
 
 def split_bf16(X, ldx, rows, cols, hi, lo, ldo):

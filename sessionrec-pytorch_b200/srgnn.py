@@ -104,6 +104,7 @@ class SRGNN(SessRecModule):
         self.dropout_p = float(feat_drop)
         # The reference runs the GGNN layers and drops their result; keep the same amount of device work by default.
         self.compute_dead_layers = True
+        self.native_step = True
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.embedding_dim)
@@ -113,6 +114,62 @@ class SRGNN(SessRecModule):
     def _inactive_params(self, batch=None):
         # the GGNN layers are evaluated and discarded (srgnn.py:135-142): their parameters never get a gradient
         return frozenset(n for n, _ in self.named_parameters() if n.startswith('layers.'))
+
+    # ---- native fused step (csrc/step_srgnn.cu) ------------------------------------------------------------------
+    def _slot_offsets(self):
+        import numpy as np
+        fp = self._flat
+        names = ['embedding.weight']
+        for l in range(self.num_layers):
+            names += [f'layers.{l}.{n}' for n in ('gru.weight_ih', 'gru.weight_hh', 'gru.bias_ih', 'gru.bias_hh', 'W1.weight',
+                                                  'W2.weight')]
+        names += ['readout.fc_u.weight', 'readout.fc_v.weight', 'readout.fc_v.bias', 'readout.fc_e.weight', 'fc_sr.weight']
+        return np.ascontiguousarray([fp.offsets[fp.index[n]] for n in names], dtype=np.int64)
+
+    def train_step(self, batch, group=None, global_batch=None):
+        """One TrainRunner iteration (`utils/train.py:95-101`) in ONE C call (srk_srgnn_train_step): zero_grad, forward,
+        nll_loss, backward, Adam.  The catalog-sharded head is composed from the staged kernels instead."""
+        fp = self._ensure_flat()
+        if batch is None or batch.B == 0 or not self.native_step or self._shard is not None or batch.kind != 'session':
+            return super().train_step(batch, group, global_batch)
+        import ctypes
+        from ._lib import lib, ptr
+        if self._opt is None:
+            self.configure_optimizer()
+        o = self._opt
+        st = getattr(self, '_native', None)
+        if st is None or st['flat'] is not fp:
+            st = self._native = dict(flat=fp, slots=self._slot_offsets(), ws=None, ws_bytes=0)
+        L = lib()
+        V, d = self.num_items, self.embedding_dim
+        need = L.call('srk_srgnn_workspace_bytes', batch.B, batch.N1, batch.M1, V, d, self.num_layers)
+        if need > st['ws_bytes']:
+            st['ws_bytes'] = int(need * 1.2)
+            st['ws'] = torch.empty(st['ws_bytes'], dtype=torch.uint8, device=fp.data.device)
+        p, seed = self._p(), self._next_seed()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        gseed = self._dp_weight(batch, group, global_batch)
+        seg_decay = self._seg_decay(batch)
+        o['step'] += 1
+        loss = torch.empty((), dtype=torch.float32, device=fp.data.device)
+        flags = int(self.use_tensor_cores) | (2 if self.fused_lse else 0) | (4 if self.flash_ce else 0)
+
+        def call(phase):
+            ops._count[0] += 1
+            L.call('srk_srgnn_train_step', ptr(batch.buf), ctypes.c_void_p(batch.hdr.ctypes.data), ptr(fp.data), ptr(fp.grad),
+                   ctypes.c_void_p(st['slots'].ctypes.data), V, d, self.num_layers, int(self.niser),
+                   float(self.scale) if self.scale else 1.0, int(self.compute_dead_layers), float(p), ctypes.c_uint64(seed),
+                   flags, ptr(st['ws']), st['ws_bytes'], ptr(gseed), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
+                   ptr(o['seg_off']), ptr(seg_decay), o['n_seg'], float(o['lr']), float(o['betas'][0]), float(o['betas'][1]),
+                   float(o['eps']), int(o['step']), 1.0, phase, stream)
+        if group is None:
+            call(0)
+        else:
+            import torch.distributed as dist
+            call(1)
+            dist.all_reduce(fp.grad, group=group)
+            call(2)
+        return loss
 
     # ---- forward / backward over the kernels -----------------------------------------------------------------
     def _fwd(self, batch, mode, need_grad=True):

@@ -164,6 +164,19 @@ def test_fused_train_step_trajectory_vs_reference(pkg, name, head):
         assert_close(f'{name}.final_embedding', m.state_dict()[emb], c['final_embedding'], rtol=RTOL, floor=0.1)   # Adam steps are lr-sized: 1e-5 abs
     else:
         assert_close_after_adam(f'{name}.final_embedding', m.state_dict()[emb], c['final_embedding'], 1e-3, c['steps'])
+    # every other tensor of the reference's state_dict after the same steps: parameters its forward never reaches keep their
+    # initial values bit for bit (torch.optim.Adam skips a parameter whose grad is None; so does the fused step)
+    sd = m.state_dict()
+    untouched = 0
+    for n_, ref_t in c['final_state'].items():
+        if torch.equal(ref_t, c['params'][n_]):
+            untouched += 1
+            assert torch.equal(sd[n_].cpu(), ref_t), f'{name}: {n_} must stay at its initial value'
+        elif head == 'tf32':
+            assert_close(f'{name}.final[{n_}]', sd[n_], ref_t, rtol=RTOL, floor=0.1)
+        else:
+            assert_close_after_adam(f'{name}.final[{n_}]', sd[n_], ref_t, 1e-3, c['steps'])
+    assert untouched >= 5, 'the goldens hold parameters the reference never updates (dead GGNN layers, lint / linq / link ...)'
     m.eval()
     mrr = hit = n = 0
     with torch.no_grad():
@@ -263,6 +276,60 @@ def test_native_step_matches_staged_composition(pkg, p):
         assert abs(a - b_) <= 2e-6 * abs(b_), (l1, l2)
     for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
         assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)   # Adam turns 1e-9 gradient noise (atomics) into lr-sized steps
+
+
+@pytest.mark.parametrize('name', ['srgnn', 'niser'])
+@pytest.mark.parametrize('p', [0.0, 0.3])
+@pytest.mark.parametrize('head', ['flash', 'tf32'])
+def test_native_srgnn_step_matches_staged_composition(pkg, name, p, head):
+    """csrc/step_srgnn.cu (one C call per SRGNN / NISER training step, dead GGNN layers on a side stream) against the
+    stage-by-stage Python composition of the same kernels: same losses, same parameters after a few Adam steps."""
+    c = TRAINS[name]
+    models = []
+    for native in (True, False):
+        m = make_model(pkg, c, dropout=p)
+        m.train()
+        m.native_step, m.flash_ce = native, head == 'flash'
+        m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+        losses = []
+        for it in range(4):
+            m.set_dropout_seed(999 + it)
+            b, _ = make_batch(pkg, c, c['samples'][it * c['bs']:(it + 1) * c['bs']])
+            losses.append(float(m.train_step(b)))
+        models.append((m, losses))
+    (m1, l1), (m2, l2) = models
+    for a, b_ in zip(l1, l2):
+        assert abs(a - b_) <= 2e-6 * abs(b_), (l1, l2)
+    for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)
+
+
+@pytest.mark.parametrize('model,d,L', [('SRGNN', 256, 1), ('NISER', 64, 2), ('SRGNN', 96, 2)])
+def test_native_srgnn_step_with_tensor_core_projections(pkg, model, d, L):
+    """Shapes where the read-out / GGNN projections of the native step go to the tcgen05 GEMM (srk_tc_gemm) and, for d = 256,
+    the head runs on the materialised 3xTF32 scores: native step == staged composition, dropout masks included."""
+    from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
+    from sessionrec_pytorch_b200.synthetic import SessionSampler
+    V, B = 3000, 640
+    smp = SessionSampler(V, seed=11)
+    res = []
+    for native in (True, False):
+        torch.manual_seed(3)
+        m = {'SRGNN': SRGNN, 'NISER': NISER}[model](V, d, L, 0.2).to(DEV).train()
+        m.native_step = native
+        m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+        smp2 = SessionSampler(V, seed=11)
+        losses = []
+        for it in range(3):
+            seqs, labels = smp2.sessions(B)
+            m.set_dropout_seed(31 + it)
+            losses.append(float(m.train_step(pkg.SessionBatch.build(seqs, labels, 'session', 1).to(DEV))))
+        res.append((m, losses))
+    (m1, l1), (m2, l2) = res
+    for a, b_ in zip(l1, l2):
+        assert abs(a - b_) <= 5e-6 * abs(b_), (l1, l2)
+    for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)
 
 
 @pytest.mark.parametrize('p,inject', [(0.0, 0), (0.2, 0), (0.2, 3)])

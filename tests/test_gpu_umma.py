@@ -98,3 +98,37 @@ def test_umma_score_fwd_fused_lse(ops, M, N, K):
     rn = rl - ref.gather(1, labels.unsqueeze(1)).squeeze(1)
     assert float((nll.cpu().double() - rn).abs().max()) < 3e-5
     assert bool((Z[:, N:] == 7.0).all())
+
+
+@pytest.mark.parametrize('form,M,N,K,bias,acc', [
+    (0, 9000, 768, 512, True, False),      # GGNN gate projection at the cfg2 shape: gi = hn W_ih^T + b_ih
+    (0, 333, 100, 72, True, False),        # ragged everything
+    (0, 2048, 256, 512, False, True),      # accumulate into an existing C
+    (1, 9000, 256, 256, False, True),      # dF += du W_u
+    (1, 2048, 512, 256, False, False),     # d sr_in = ds W_sr: 512 output columns = two N tiles
+    (1, 500, 40, 300, False, False),
+    (2, 256, 256, 9000, False, True),      # dW_u += du^T F, split-K picked by the library
+    (2, 256, 512, 2048, False, True),      # dW_sr += ds^T sr_in: two N tiles
+    (2, 100, 36, 777, False, True),
+])
+def test_tc_gemm_plain_fp32_operands(ops, form, M, N, K, bias, acc):
+    """srk_tc_gemm: operand split + 3xTF32 tensor-core GEMM from plain (pitched) fp32 operands, optional bias, any N."""
+    g = torch.Generator().manual_seed(form * 7 + M + N + K)
+    sa = (K, M) if form == 2 else (M, K)
+    sb = (N, K) if form == 0 else (K, N)
+    pa, pb = (sa[1] + 3) // 4 * 4 + 4, (sb[1] + 3) // 4 * 4 + 8          # pitched: views into wider buffers
+    Af, Bf = torch.randn(sa[0], pa, generator=g), torch.randn(sb[0], pb, generator=g)
+    A, Bm = Af[:, :sa[1]], Bf[:, :sb[1]]
+    bv = torch.randn(N, generator=g) if bias else None
+    C0 = torch.randn(M, N, generator=g)
+    Cd = C0.to(DEV).contiguous()
+    Ad, Bd = Af.to(DEV), Bf.to(DEV)
+    ops.tc_gemm(form, M, N, K, Ad, pa, Bd, pb, Cd, N, bias=None if bv is None else bv.to(DEV), alpha=0.75, accumulate=acc, split_k=0)
+    torch.cuda.synchronize()
+    a, b = A.double(), Bm.double()
+    ref = 0.75 * ((a.t() if form == 2 else a) @ (b.t() if form == 0 else b))
+    if bv is not None:
+        ref = ref + bv.double()
+    if acc:
+        ref = ref + C0.double()
+    _check(f'tc_gemm form {form} {M}x{N}x{K}', Cd, ref)
