@@ -445,9 +445,15 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
     shard = args.parallelism == 'shard' and world > 1
     model = build_model(cfg, device)
     model.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+    native_comm = False
+    if world > 1 and os.environ.get('SESSREC_NATIVE_COMM', '1') != '0':
+        from sessionrec_pytorch_b200 import parallel
+        parallel.init_comm(group)          # the library's own NCCL communicator: collectives enqueued inside the native step
+        native_comm = True
     if shard:
         model.shard_catalog(group)
     step_group = None if shard else group
+    gb = None if (shard or world == 1) else world * cfg['B']      # equal shards: B_global is known on the host
     # data parallel: every rank draws its own sessions (weak scaling); catalog sharding: every rank sees the SAME global
     # batch and scores its slice of the catalog (strong scaling)
     smp = SessionSampler(cfg['V'], seed=123 + (0 if shard else rank))
@@ -461,7 +467,7 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
 
     # ---- device-timed region: K steps, inputs resident in HBM -------------------------------------------------
     for i in range(args.warmup):
-        model.train_step(resident[i % n_batches], step_group)
+        model.train_step(resident[i % n_batches], step_group, gb)
     barrier()
     clocks = ClockSampler(device.index)
     clocks.start()
@@ -475,7 +481,7 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
         kk = ops.kernel_launches()
         a.record()
         tq = time.perf_counter()
-        model.train_step(resident[(args.warmup + i) % n_batches], step_group)
+        model.train_step(resident[(args.warmup + i) % n_batches], step_group, gb)
         enqueue_s += time.perf_counter() - tq
         b.record()
         launches += ops.kernel_launches() - kk
@@ -517,7 +523,7 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
     for i in range(args.steps):
         hb = host[i % n_batches]
         db = hb.to(device, non_blocking=True)           # H2D of the whole batch (one pinned buffer)
-        loss = model.train_step(db, step_group)
+        loss = model.train_step(db, step_group, gb)
         loss.item()                                     # D2H read of the step's loss (what TrainRunner does, train.py:103)
         h2d += hb.nbytes
     barrier()
@@ -570,8 +576,18 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
             'wall_s_timed_region': round(t_wall, 4), 'host_enqueue_ms_per_step': round(1e3 * enqueue_s / args.steps, 4),
             'roofline': roofline_probe(cfg, device, pk),
         }
-        if shard or world > 1:
-            out['collectives'] = getattr(model, 'collectives_per_step', lambda: None)()
+        if world > 1:
+            nflat = int(model._flat.data.numel())
+            where = ('enqueued by the native step itself on the library\'s own NCCL communicator (csrc/comm.cu), inside its CUDA-graph replay'
+                     if native_comm else 'torch.distributed (NCCL) between the two halves of the native step')
+            if shard:
+                out['collectives'] = dict(per_step=[f'ncclAllReduce(sum) [2, B={cfg["B"]}] fp32: per-session sum exp(logit - 12) + label logit',
+                                                    f'ncclAllReduce(sum) dS [B={cfg["B"]}, d={cfg["d"]}] fp32',
+                                                    f'2 x ncclAllReduce(avg) of the replicated (non-table) gradients, {nflat - cfg["V"] * cfg["d"]} floats',
+                                                    f'grouped ncclBroadcast of the owners\' updated table rows, V*d = {cfg["V"] * cfg["d"]} floats'],
+                                          where=where, table_gradient_allreduce=False)
+            else:
+                out['collectives'] = dict(per_step=[f'ncclAllReduce(sum) of the flat fp32 gradient buffer, {nflat} floats'], where=where)
         if primary:
             out['roofline_gather_scatter'] = gather_scatter_probe(device, pk) if not args.no_gather_probe else None
             out['batch_builder'] = builder_probe(pkg, cfg) if world == 1 else None

@@ -358,7 +358,39 @@ int srk_adam_step_split(float* param, const float* grad, float* exp_avg, float* 
 /* ---- native training step (MSGIFSR order 1, extra=False): utils/train.py:95-101 around msgifsr.py:241-323 ----
  * zero_grad + forward + nll_loss + backward (+ Adam) enqueued by ONE host call from a caller-provided device
  * workspace (srk_msgifsr_workspace_bytes).  slot_off_host: float offsets of the parameters inside the flat buffers,
- * order documented in csrc/step.cu.  phase 0 = all, 1 = up to the gradients (data parallel: all-reduce, then) 2 = Adam. */
+ * order documented in csrc/step.cu.  phase 0 = all, 1 = up to the gradients (data parallel: all-reduce, then) 2 = Adam;
+ * phase 3 = all, with the data-parallel gradient all-reduce (srk_comm_allreduce over the flat gradient buffer) enqueued by
+ * the step itself between the backward pass and Adam (needs srk_comm_init). */
+/* ---- collectives of the multi-GPU path (csrc/comm.cu; the reference is single-device) ----
+ * One process per GPU; a process-wide NCCL communicator owned by this library (libnccl.so.2 is resolved with dlopen at run
+ * time, nccl_path may be NULL) so that a training step's exchanges are enqueued from inside the native step, between its
+ * kernels and inside its CUDA-graph replay.  Bootstrap: rank 0 calls srk_comm_unique_id, the caller hands the 128 bytes to
+ * every rank (parallel.init_comm broadcasts them over torch.distributed), every rank calls srk_comm_init with its CUDA device
+ * current.  All buffers are fp32 device buffers; calls only enqueue on `stream`. */
+int srk_comm_unique_id(char* id128_host, const char* nccl_path);
+int srk_comm_init(const char* id128_host, int rank, int world, const char* nccl_path);
+int srk_comm_destroy(void);
+int srk_comm_world(void);
+int srk_comm_rank(void);
+int srk_comm_nccl_version(void);
+/* in-place all-reduce of buf[n]: op 0 = sum, 1 = max, 2 = average */
+int srk_comm_allreduce(float* buf, long long n, int op, void* stream);
+/* recv[world * n] <- every rank's send[n], in rank order */
+int srk_comm_allgather(const float* send, float* recv, long long n, void* stream);
+/* [rows, d] table whose rows are sharded over the ranks (balanced contiguous split, first rows % world ranks hold one more):
+ * every owner broadcasts its rows in place - one grouped NCCL call - so that all replicas hold all updated rows again */
+int srk_comm_share_rows(float* table, int rows, int d, void* stream);
+/* Catalog-sharded scoring head (BASELINE config 5): rank r scores catalog rows [lo, hi) only.  srk_shard_labels:
+ * labels_local[b] = labels[b] - lo where owned, else -1 (srk_flash_ce_fwd / srk_umma_score_fwd then return the LOCAL
+ * log-sum-exp and, where owned, the NLL).  srk_shard_lse_pack builds the payload of the ONE sum all-reduce - pack[0:B] =
+ * exp(lse_local - shift), pack[B:2B] = label logit where owned else 0 - and srk_shard_lse_unpack turns the reduced payload
+ * into the global log-sum-exp and NLL.  shift = NULL: the constant `bound` (cosine heads, |logit| <= scale); else the
+ * per-session max of lse_local over the ranks (one extra max all-reduce: SRGNN's unbounded logits). */
+int srk_shard_labels(const int* labels, int B, int lo, int hi, int* labels_local, void* stream);
+int srk_shard_lse_pack(const float* lse_local, const float* nll_local, const int* labels_local, const float* shift,
+                       float bound, int B, float* pack, void* stream);
+int srk_shard_lse_unpack(const float* pack, const float* shift, float bound, int B, float* lse, float* nll, void* stream);
+
 /* CUDA-graph replay of the native step's backward half: after two warm-up steps per model configuration its ~40
  * launches (7 streams) are captured once; later steps only rewrite the kernel-node parameters and issue one
  * cudaGraphLaunch.  Default: on for data-parallel steps (phase 1), where the ranks share the host CPU; SESSREC_GRAPH=1

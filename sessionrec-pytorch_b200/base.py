@@ -363,14 +363,17 @@ class SessRecModule(nn.Module):
             self.configure_optimizer(lr=lr)
         self._opt['lr'] = float(lr)
 
-    def _seg_decay(self, batch=None):
-        """Per-segment decay (negative = inactive) for this batch's set of unreached parameters; cached on the device by
-        the batch's set of edge-less relations (the only data-dependent input), so a step pays one dict lookup."""
+    def _segments(self, batch=None, owned_rows=None):
+        """(seg_off, seg_decay, n_seg) of the Adam kernels for this batch: per-parameter weight decay, negative = inactive
+        (parameters the reference's forward does not reach for this batch; under catalog sharding the table rows of the
+        other owners).  Cached on the device by the batch's set of edge-less relations - the only data-dependent input -
+        so a step pays one dict lookup."""
         o = self._opt
-        key = batch.empty_relations() if batch is not None else None
+        key = (batch.empty_relations() if batch is not None else None, owned_rows)
         t = o['seg_decay'].get(key)
         if t is None:
-            t = o['seg_decay'][key] = self._flat.decay_segments(o['weight_decay'], self._inactive_params(batch))[1]
+            off, dec = self._flat.decay_segments(o['weight_decay'], self._inactive_params(batch), owned_rows)
+            t = o['seg_decay'][key] = (off, dec, int(dec.numel()))
         return t
 
     def optimizer_state_dict(self):
@@ -417,10 +420,15 @@ class SessRecModule(nn.Module):
                 ops.fill(fp.grad, 0.0)
                 self._bwd(tape, seed, fp.grad)
             if group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(fp.grad, group=group)
+                from . import parallel
+                if parallel.comm_ready() and getattr(self, 'dp_allreduce_inside', True):
+                    ops.comm_allreduce(fp.grad)            # same communicator as the native steps of the other ranks
+                else:
+                    import torch.distributed as dist
+                    dist.all_reduce(fp.grad, group=group)
             o['step'] += 1
-            ops.adam_step(fp.data, fp.grad, o['m'], o['v'], o['seg_off'], self._seg_decay(batch), o['n_seg'], o['lr'],
+            seg_off, seg_decay, n_seg = self._segments(batch)
+            ops.adam_step(fp.data, fp.grad, o['m'], o['v'], seg_off, seg_decay, n_seg, o['lr'],
                           o['betas'][0], o['betas'][1], o['eps'], o['step'], 1.0)
         return loss
 

@@ -18,7 +18,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclFloat32 = 7 };
-enum { ncclSum = 0, ncclMax = 2 };
+enum { ncclSum = 0, ncclMax = 2, ncclAvg = 4 };
 
 struct Nccl {
   void* h = nullptr;
@@ -117,11 +117,14 @@ extern "C" int srk_comm_nccl_version(void) {
   return v;
 }
 
-/* In-place fp32 all-reduce (op 0 = sum, 1 = max) of buf[n] on `stream`. */
+/* In-place fp32 all-reduce (op 0 = sum, 1 = max, 2 = average) of buf[n] on `stream`. */
 extern "C" int srk_comm_allreduce(float* buf, long long n, int op, void* stream) {
   if (n <= 0) return SRK_OK;
+  // inside a native step whose backward half is being replayed from a CUDA graph the collective is a node of that graph
+  // (captured once, same buffer every step): the update / skip passes of the launch layer must not enqueue it again
+  if (srk_launch_mode() == SRK_LAUNCH_UPDATE || srk_launch_mode() == SRK_LAUNCH_SKIP) return SRK_OK;
   SRK_REQUIRE(g_comm != nullptr, "comm: no communicator (call srk_comm_init on every rank first)");
-  SRK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, op == 1 ? ncclMax : ncclSum, g_comm, (cudaStream_t)stream));
+  SRK_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, op == 1 ? ncclMax : (op == 2 ? ncclAvg : ncclSum), g_comm, (cudaStream_t)stream));
   ++g_srk_launches;
   return SRK_OK;
 }
@@ -129,6 +132,7 @@ extern "C" int srk_comm_allreduce(float* buf, long long n, int op, void* stream)
 /* recv[world * n] <- every rank's send[n] (rank order). */
 extern "C" int srk_comm_allgather(const float* send, float* recv, long long n, void* stream) {
   if (n <= 0) return SRK_OK;
+  if (srk_launch_mode() == SRK_LAUNCH_UPDATE || srk_launch_mode() == SRK_LAUNCH_SKIP) return SRK_OK;
   SRK_REQUIRE(g_comm != nullptr, "comm: no communicator (call srk_comm_init on every rank first)");
   SRK_NCCL(g_nccl.AllGather(send, recv, (size_t)n, ncclFloat32, g_comm, (cudaStream_t)stream));
   ++g_srk_launches;
@@ -140,6 +144,7 @@ extern "C" int srk_comm_allgather(const float* send, float* recv, long long n, v
  * NCCL call (uneven shards allowed).  After it every replica holds every owner's rows. */
 extern "C" int srk_comm_share_rows(float* table, int rows, int d, void* stream) {
   if (rows <= 0 || g_world == 1) return SRK_OK;
+  if (srk_launch_mode() == SRK_LAUNCH_UPDATE || srk_launch_mode() == SRK_LAUNCH_SKIP) return SRK_OK;
   SRK_REQUIRE(g_comm != nullptr, "comm: no communicator (call srk_comm_init on every rank first)");
   const int base = rows / g_world, rem = rows % g_world;
   SRK_NCCL(g_nccl.GroupStart());
@@ -157,5 +162,66 @@ extern "C" int srk_comm_share_rows(float* table, int rows, int d, void* stream) 
   }
   SRK_NCCL(g_nccl.GroupEnd());
   ++g_srk_launches;
+  return SRK_OK;
+}
+
+// ---- catalog-sharded head: glue around the ONE exchange of per-session soft-max statistics ---------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) shard_labels_kernel(const int* __restrict__ labels, int B, int lo, int hi, int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const int l = labels[b];
+    out[b] = (l >= lo && l < hi) ? l - lo : -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) shard_pack_kernel(const float* __restrict__ lse_local, const float* __restrict__ nll_local,
+                                                         const int* __restrict__ labels_local, const float* __restrict__ shift,
+                                                         float bound, int B, float* __restrict__ pack) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const float l = lse_local[b];
+    pack[b] = expf(l - (shift ? shift[b] : bound));
+    pack[B + b] = labels_local[b] >= 0 ? l - nll_local[b] : 0.f;      // the label logit lives on exactly one rank
+  }
+}
+
+__global__ void __launch_bounds__(256) shard_unpack_kernel(const float* __restrict__ pack, const float* __restrict__ shift, float bound,
+                                                           int B, float* __restrict__ lse, float* __restrict__ nll) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const float l = (shift ? shift[b] : bound) + logf(pack[b]);
+    lse[b] = l;
+    nll[b] = l - pack[B + b];
+  }
+}
+
+}  // namespace
+
+/* labels_local[b] = labels[b] - lo when this rank's catalog rows [lo, hi) hold the label, else -1 */
+extern "C" int srk_shard_labels(const int* labels, int B, int lo, int hi, int* labels_local, void* stream) {
+  if (B <= 0) return SRK_OK;
+  srk_launch(shard_labels_kernel, srk_cdiv(B, 256), 256, 0, (cudaStream_t)stream, labels, B, lo, hi, labels_local);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+/* pack[0:B] = exp(lse_local - shift), pack[B:2B] = label logit where owned else 0: the payload of the ONE sum all-reduce of
+ * the sharded head.  shift: per-session (the all-reduced max of lse_local, unbounded logits) or NULL = the constant `bound`
+ * (cosine heads: |logit| <= scale, so lse_local - scale is safe to exponentiate on every rank). */
+extern "C" int srk_shard_lse_pack(const float* lse_local, const float* nll_local, const int* labels_local, const float* shift,
+                                  float bound, int B, float* pack, void* stream) {
+  if (B <= 0) return SRK_OK;
+  srk_launch(shard_pack_kernel, srk_cdiv(B, 256), 256, 0, (cudaStream_t)stream, lse_local, nll_local, labels_local, shift, bound, B, pack);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+/* after the all-reduce: lse[b] = shift + log(pack[b]) (log-sum-exp over the whole catalog), nll[b] = lse[b] - pack[B + b] */
+extern "C" int srk_shard_lse_unpack(const float* pack, const float* shift, float bound, int B, float* lse, float* nll, void* stream) {
+  if (B <= 0) return SRK_OK;
+  srk_launch(shard_unpack_kernel, srk_cdiv(B, 256), 256, 0, (cudaStream_t)stream, pack, shift, bound, B, lse, nll);
+  SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

@@ -678,6 +678,464 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
   }
 }
 
+// =========================================================================================================================
+// Wide embeddings (d = 256: BASELINE configs[2] SRGNN / Yoochoose1/64 and configs[4] MSGIFSR / Yoochoose1/4).
+//
+// At d = 256 one 128-row operand tile is 128 KB as a bf16 hi / lo pair, so the layout of the kernels above (session tile + catalog
+// tile + dZ tile resident in shared memory) does not fit.  What changes:
+//   forward   the catalog tile streams through shared memory in 64-column K chunks (one pipeline stage = hi + lo chunk, 32 KB,
+//             6-7 stages) and the logit tile accumulates over the chunks; the session operand lives in TMEM (256 columns) as before.
+//   backward  the session tile stays resident (128 KB: K-major A of the logits, MN-major A of dE^T); the catalog tile shrinks to
+//             64 rows and streams in 64-column chunks of 16 KB TWICE per tile - once as the K-major B of the logit product, once
+//             as the MN-major B of dS (an extra L2 -> SM pass of 64 KB per tile against 4608 cycles of tensor work: 28 B/clk);
+//             dE is produced transposed, dE^T[d, 64 v] = S^T dZ in two M = 128 halves, so that every product keeps M = 128 and
+//             the accumulator lanes are embedding columns - a warp then stores 32 consecutive floats of one catalog row, a
+//             coalesced 128-byte store, and the dE partial needs no staging buffer.
+// TMEM (512 columns): logit tile 2 x 64 | dS 256 | dE^T 2 x 64.
+constexpr int WTV = 64;                          // catalog rows per backward tile
+constexpr uint32_t WECHUNK = 64 * 128;           // bytes of one 64-row x 128-byte catalog chunk (backward)
+constexpr int W_MAX_STAGES = 8;
+constexpr uint32_t TMW_Z = 0, TMW_DS = 128, TMW_DE = 384;
+
+struct FceWide {
+  int B, V, d, nch;        // nch = d / 64 chunks of 64 columns
+  int ntm, nvr, nvt;       // session tiles, catalog ranges, catalog tiles (128 rows forward, 64 rows backward)
+  int tv;                  // catalog rows per tile
+  int estages;
+  float scale;
+  const int* labels;
+  float* part;             // fwd
+  float* zlab;             // fwd
+  const float* lse;        // bwd
+  const float* gout;       // bwd
+  float* dEpart;           // bwd: [ntm][V][d]
+  const uint16_t *Shi, *Slo;   // fwd: bf16 hi / lo of shat in global memory, row pitch lds (staged into TMEM)
+  long long lds;
+  uint32_t idesc_z, idesc_ds, idesc_de;
+};
+
+struct WideSched {
+  int tb, t0, t1;
+  __device__ WideSched(const FceWide& p) {
+    tb = blockIdx.x % p.ntm;
+    const int vr = blockIdx.x / p.ntm;
+    t0 = (int)((long long)vr * p.nvt / p.nvr);
+    t1 = (int)((long long)(vr + 1) * p.nvt / p.nvr);
+  }
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl, const FceWide p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full, e_full[W_MAX_STAGES], e_empty[W_MAX_STAGES], z_full[2], z_empty[2];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lo_off = (uint32_t)p.d >> 1;          // TMEM columns between shat hi and shat lo (packed bf16 pairs)
+  const WideSched ts(p);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_full, EPI_WARPS);
+    for (int s = 0; s < W_MAX_STAGES; ++s) {
+      mbar_init(&e_full[s], 1);
+      mbar_init(&e_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_tc_before();
+  __syncthreads();
+  fence_tc_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int u = 0;                                       // pipeline-stage uses so far
+      for (int t = ts.t0; t < ts.t1; ++t)
+        for (int c = 0; c < p.nch; ++c, ++u) {
+          const int s = u % p.estages;
+          mbar_wait(&e_empty[s], ((uint32_t)(u / p.estages) & 1u) ^ 1u);
+          uint8_t* st = smem + (size_t)s * 2 * CHUNK;
+          mbar_expect_tx(&e_full[s], 2 * CHUNK);
+          tma_load_2d(st, &mEh, &e_full[s], c * 64, t * TV);
+          tma_load_2d(st + CHUNK, &mEl, &e_full[s], c * 64, t * TV);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(&s_full, 0);
+      fence_tc_after();
+      int u = 0, it = 0;
+      for (int t = ts.t0; t < ts.t1; ++t, ++it) {
+        const int zb = it & 1;
+        mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        fence_tc_after();
+        const uint32_t tz = tmem_base + TM_Z + (uint32_t)zb * TV;
+        for (int c = 0; c < p.nch; ++c, ++u) {
+          const int s = u % p.estages;
+          mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
+          fence_tc_after();
+          const uint32_t Ea = smem_u32(smem + (size_t)s * 2 * CHUNK);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t kk = (uint32_t)(c * 4 + ks);
+            const uint32_t ah = tmem_base + TM_SA + kk * 8, al = ah + lo_off;
+            const uint64_t eh = kdesc(Ea + ks * 32), el = kdesc(Ea + CHUNK + ks * 32);
+            umma_bf16_ts(tz, ah, eh, p.idesc_z, kk ? 1u : 0u);
+            umma_bf16_ts(tz, ah, el, p.idesc_z, 1u);
+            umma_bf16_ts(tz, al, eh, p.idesc_z, 1u);
+          }
+          umma_commit(&e_empty[s]);
+        }
+        umma_commit(&z_full[zb]);
+      }
+    }
+  } else {
+    // soft-max math: identical to fce_fwd_kernel (per-row online max / sum exp in base 2, label logit)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int b = ts.tb * TB + q * 32 + lane;
+    const int lab = b < p.B ? p.labels[b] : -1;
+    const float c2 = p.scale * LOG2E;
+    const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+    {
+      const uint16_t* src = (half == 0 ? p.Shi : p.Slo) + (long long)b * p.lds;
+      const uint32_t dst = tmem_base + lanebits + TM_SA + (uint32_t)half * lo_off;
+      for (int w = 0; w < (p.d >> 1); w += 8) {
+        uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
+        if (b < p.B) {
+          x0 = *reinterpret_cast<const uint4*>(src + 2 * w);
+          x1 = *reinterpret_cast<const uint4*>(src + 2 * w + 8);
+        }
+        const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        tmem_st8(dst + (uint32_t)w, v);
+      }
+      tmem_wait_st();
+      fence_tc_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full);
+    }
+    float m2 = -3.0e38f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, zl = 0.f;
+    bool has = false;
+    int it = 0;
+    for (int t = ts.t0; t < ts.t1; ++t, ++it) {
+      const int zb = it & 1;
+      mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
+      fence_tc_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        const uint32_t taddr = tmem_base + lanebits + TM_Z + (uint32_t)(zb * TV + c0);
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
+        const int v0 = t * TV + c0;
+        const int nvalid = min(32, p.V - v0);
+        if (nvalid == 32) {
+          float a0 = __uint_as_float(r[0]), a1 = __uint_as_float(r[1]), a2 = __uint_as_float(r[2]), a3 = __uint_as_float(r[3]);
+#pragma unroll
+          for (int j = 4; j < 32; j += 4) {
+            a0 = fmaxf(a0, __uint_as_float(r[j]));
+            a1 = fmaxf(a1, __uint_as_float(r[j + 1]));
+            a2 = fmaxf(a2, __uint_as_float(r[j + 2]));
+            a3 = fmaxf(a3, __uint_as_float(r[j + 3]));
+          }
+          const float cm2 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)) * c2;
+          if (cm2 > m2) {
+            const float f = ex2f(m2 - cm2);
+            s0 *= f; s1 *= f; s2 *= f; s3 *= f;
+            m2 = cm2;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            s0 += ex2f(fmaf(__uint_as_float(r[j]), c2, -m2));
+            s1 += ex2f(fmaf(__uint_as_float(r[j + 1]), c2, -m2));
+            s2 += ex2f(fmaf(__uint_as_float(r[j + 2]), c2, -m2));
+            s3 += ex2f(fmaf(__uint_as_float(r[j + 3]), c2, -m2));
+          }
+        } else if (nvalid > 0) {
+          float cm = -3.0e38f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) cm = fmaxf(cm, __uint_as_float(r[j]));
+          const float cm2 = cm * c2;
+          if (cm2 > m2) {
+            const float f = ex2f(m2 - cm2);
+            s0 *= f; s1 *= f; s2 *= f; s3 *= f;
+            m2 = cm2;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) s0 += ex2f(fmaf(__uint_as_float(r[j]), c2, -m2));
+        }
+        const bool mine = lab >= v0 && lab < v0 + nvalid;
+        if (__any_sync(SRK_FULL, mine)) {
+          const float x = p.scale * pick_column(taddr, lab - v0);
+          if (mine) {
+            zl = x;
+            has = true;
+          }
+        }
+      }
+      fence_tc_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&z_empty[zb]);
+    }
+    if (b < p.B) {
+      const int vr = blockIdx.x / p.ntm;
+      float* pp = p.part + ((long long)(vr * 2 + half) * p.B + b) * 2;
+      pp[0] = m2 * LN2;
+      pp[1] = (s0 + s1) + (s2 + s3);
+      if (has) p.zlab[b] = zl;
+    }
+  }
+  fence_tc_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(THREADS_BWD, 1)
+fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
+                    const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl,
+                    const __grid_constant__ CUtensorMap mdS, const FceWide p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full, e_full[W_MAX_STAGES], e_empty[W_MAX_STAGES], z_full[2], z_empty[2], d_full, d_empty, de_free;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t op_bytes = (uint32_t)p.nch * CHUNK;          // one of shat hi / lo: nch chunks of 128 rows x 128 bytes
+  uint8_t* S = smem;                                          // hi chunks | lo chunks
+  uint8_t* Dt = smem + 2 * op_bytes;                          // dZ hi (one chunk) | dZ lo; fp32 staging of the final dS drain
+  uint8_t* E0 = Dt + 2 * CHUNK;                               // estages x (hi chunk | lo chunk) of 64 rows
+  const WideSched ts(p);
+  const int ntiles = ts.t1 - ts.t0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_full, 1);
+    for (int s = 0; s < W_MAX_STAGES; ++s) {
+      mbar_init(&e_full[s], 1);
+      mbar_init(&e_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], EPI_WARPS);
+    }
+    mbar_init(&d_full, EPI_WARPS);
+    mbar_init(&d_empty, 1);
+    mbar_init(&de_free, DRAIN_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_tc_before();
+  __syncthreads();
+  fence_tc_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer.  Stage order = the order the MMA warp consumes: L(0); then per tile L(it + 1), dS(it). =====
+      mbar_expect_tx(&s_full, 2 * op_bytes);
+      for (int c = 0; c < p.nch; ++c) {
+        tma_load_2d(S + c * CHUNK, &mSh, &s_full, c * 64, ts.tb * TB);
+        tma_load_2d(S + op_bytes + c * CHUNK, &mSl, &s_full, c * 64, ts.tb * TB);
+      }
+      int u = 0;
+      auto tile_chunks = [&](int x) {
+        for (int c = 0; c < p.nch; ++c, ++u) {
+          const int s = u % p.estages;
+          mbar_wait(&e_empty[s], ((uint32_t)(u / p.estages) & 1u) ^ 1u);
+          uint8_t* st = E0 + (size_t)s * 2 * WECHUNK;
+          mbar_expect_tx(&e_full[s], 2 * WECHUNK);
+          tma_load_2d(st, &mEh, &e_full[s], c * 64, (ts.t0 + x) * WTV);
+          tma_load_2d(st + WECHUNK, &mEl, &e_full[s], c * 64, (ts.t0 + x) * WTV);
+        }
+      };
+      if (ntiles > 0) tile_chunks(0);
+      for (int it = 0; it < ntiles; ++it) {
+        if (it + 1 < ntiles) tile_chunks(it + 1);
+        tile_chunks(it);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t Sa = smem_u32(S), Da = smem_u32(Dt);
+      const uint32_t tds = tmem_base + TMW_DS, tde = tmem_base + TMW_DE;
+      int u = 0;
+      auto logits = [&](int x) {
+        const int zb = x & 1;
+        mbar_wait(&z_empty[zb], ((uint32_t)(x >> 1) & 1u) ^ 1u);
+        fence_tc_after();
+        const uint32_t tz = tmem_base + TMW_Z + (uint32_t)zb * WTV;
+        for (int c = 0; c < p.nch; ++c, ++u) {
+          const int s = u % p.estages;
+          mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
+          fence_tc_after();
+          const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * WECHUNK);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t so = (uint32_t)c * CHUNK + (uint32_t)ks * 32;
+            mma3(tz, kdesc(Sa + so), kdesc(Sa + op_bytes + so), kdesc(Ea + ks * 32), kdesc(Ea + WECHUNK + ks * 32), p.idesc_z,
+                 (c | ks) ? 1u : 0u);
+          }
+          umma_commit(&e_empty[s]);
+        }
+        umma_commit(&z_full[zb]);
+      };
+      mbar_wait(&s_full, 0);
+      if (ntiles > 0) logits(0);
+      for (int it = 0; it < ntiles; ++it) {
+        if (it + 1 < ntiles) logits(it + 1);
+        mbar_wait(&d_full, (uint32_t)it & 1u);
+        fence_tc_after();
+        // dS[128 b, 64 columns of chunk c] += dZ[128 b x 64 v] E_c[64 v x 64]: A = D K-major, B = catalog chunk MN-major
+        for (int c = 0; c < p.nch; ++c, ++u) {
+          const int s = u % p.estages;
+          mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
+          fence_tc_after();
+          const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * WECHUNK);
+#pragma unroll
+          for (int ks = 0; ks < WTV / 16; ++ks)
+            mma3(tds + (uint32_t)c * 64, kdesc(Da + ks * 32), kdesc(Da + CHUNK + ks * 32), mdesc(Ea + ks * 2048),
+                 mdesc(Ea + WECHUNK + ks * 2048), p.idesc_ds, (it | ks) ? 1u : 0u);
+          umma_commit(&e_empty[s]);
+        }
+        if (it > 0) {                             // the drain warps have read the previous tile's dE^T accumulators
+          mbar_wait(&de_free, (uint32_t)(it - 1) & 1u);
+          fence_tc_after();
+        }
+        // dE^T[128 embedding columns of half h, 64 v] = S_h^T[128 x 128 b] dZ[128 b x 64 v]: A = S MN-major (two chunks,
+        // LBO = CHUNK), B = D MN-major, K = sessions in steps of 16 rows
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t sa = Sa + (uint32_t)(2 * h) * CHUNK;
+#pragma unroll
+          for (int ks = 0; ks < TB / 16; ++ks)
+            mma3(tde + (uint32_t)h * WTV, mdesc(sa + ks * 2048), mdesc(sa + op_bytes + ks * 2048), mdesc(Da + ks * 2048),
+                 mdesc(Da + CHUNK + ks * 2048), p.idesc_de, ks ? 1u : 0u);
+        }
+        umma_commit(&d_empty);
+      }
+    }
+  } else if (warp < 2 + EPI_WARPS) {
+    // ===== math warps: 64-column logit tile -> dZ = coef (softmax - onehot) -> bf16 hi / lo -> D tile (one 64-column chunk) =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int b = ts.tb * TB + r;
+    const bool bvalid = b < p.B;
+    const int lab = bvalid ? p.labels[b] : -1;
+    const float c2 = p.scale * LOG2E;
+    const float lse_b = bvalid ? p.lse[b] : 0.f;
+    const float lse2 = lse_b * LOG2E;
+    const float coef = bvalid ? p.scale * (p.gout ? p.gout[0] : 1.f) / (float)p.B : 0.f;
+    const float coef_p = coef * ex2f(-fmaf(lse_b, LOG2E, -lse2));
+    const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+    uint8_t* Dhi = Dt;
+    uint8_t* Dlo = Dt + CHUNK;
+    const int c0 = half * 32;
+    for (int it = 0; it < ntiles; ++it) {
+      const int t = ts.t0 + it, zb = it & 1;
+      mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
+      fence_tc_after();
+      uint32_t hw[16], lw[16];
+      {
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + lanebits + TMW_Z + (uint32_t)(zb * WTV + c0), acc);
+        const int v0 = t * WTV + c0;
+        float dz[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz[j] = coef_p * ex2f(fmaf(__uint_as_float(acc[j]), c2, -lse2));
+        if (v0 + 32 > p.V) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (v0 + j >= p.V) dz[j] = 0.f;
+        }
+        pack_dz(dz, hw, lw);
+      }
+      fence_tc_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&z_empty[zb]);
+      if (it > 0) mbar_wait(&d_empty, (uint32_t)(it - 1) & 1u);       // previous tile's gradient products have read D
+      store_dz(Dhi, Dlo, r, c0, hw, lw);
+      const int v0 = t * WTV + c0;
+      if (lab >= v0 && lab < v0 + 32) fix_dz(Dhi, Dlo, r, lab - t * WTV, coef);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_full);
+    }
+  } else {
+    // ===== drain warps (TMEM lane quadrant = warp % 4).  dE^T: lane = embedding column, register j = catalog row, so one
+    // store instruction of a warp writes 32 consecutive floats of ONE catalog row (128 bytes, coalesced). =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lanebits = (uint32_t)(q * 32) << 16;
+    const bool elected = (warp == 2 + EPI_WARPS && lane == 0);
+    float* outp = p.dEpart + (long long)ts.tb * p.V * p.d;
+    for (int it = 0; it < ntiles; ++it) {
+      mbar_wait(&d_empty, (uint32_t)it & 1u);
+      fence_tc_after();
+      const int v0 = (ts.t0 + it) * WTV;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t a0[32], a1[32];
+        tmem_ld32(tmem_base + lanebits + TMW_DE + (uint32_t)(h * WTV), a0);
+        tmem_ld32(tmem_base + lanebits + TMW_DE + (uint32_t)(h * WTV + 32), a1);
+        if (h == 1) {                             // both halves are in registers: the next tile may overwrite the accumulators
+          fence_tc_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&de_free);
+        }
+        float* col = outp + h * 128 + r;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (v0 + j < p.V) col[(long long)(v0 + j) * p.d] = __uint_as_float(a0[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (v0 + 32 + j < p.V) col[(long long)(v0 + 32 + j) * p.d] = __uint_as_float(a1[j]);
+        }
+      }
+    }
+    // dS accumulator of this CTA's whole catalog range -> TMA reduce-add into dS[B, d], 32 columns at a time through a 16 KB
+    // staging buffer in the (now idle) D tile
+    if (ntiles > 0) {
+      for (int cc = 0; cc < (p.d >> 5); ++cc) {
+        uint32_t a[32];
+        tmem_ld32(tmem_base + lanebits + TMW_DS + (uint32_t)(cc * 32), a);
+        if (elected) tma_wait_group_read0();
+        named_bar_sync(2, DRAIN_THREADS);
+        stage_row(Dt, r, a);
+        fence_async_smem();
+        named_bar_sync(2, DRAIN_THREADS);
+        if (elected) {
+          tma_reduce_add_2d(&mdS, Dt, cc * 32, ts.tb * TB);
+          tma_commit_group();
+        }
+      }
+      if (elected) tma_wait_group0();
+    }
+  }
+  fence_tc_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 __global__ void split_bf16_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long ldo) {
   const long long total = (long long)rows * cols;
@@ -694,11 +1152,11 @@ __global__ void split_bf16_kernel(const float* __restrict__ X, long long ldx, in
 
 long long* g_trace = nullptr;
 
-int bf16_map(CUtensorMap* m, const uint16_t* base, int d, int rows, long long ld, int cw) {
+int bf16_map(CUtensorMap* m, const uint16_t* base, int d, int rows, long long ld, int cw, int box_rows = 128) {
   SRK_REQUIRE(ld % 8 == 0, "flash_ce: bf16 operand pitch must be a multiple of 8 elements");
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)cw, 128};
+  cuuint32_t box[2] = {(cuuint32_t)cw, (cuuint32_t)box_rows};
   // operand rows are 2 * d bytes apart and every 128-byte box row is consumed whole: L2 promotion beyond the box row only
   // multiplies the L2 -> SM sector traffic (measured: 3x with L2_256B at d = 96).  SESSREC_FCE_L2PROMO = 0..3 overrides.
   static int promo = -1;
@@ -790,7 +1248,111 @@ extern "C" int srk_split_bf16(const float* X, long long ldx, int rows, int cols,
   return SRK_OK;
 }
 
-extern "C" int srk_flash_ce_supported(int d) { return d >= 16 && d <= 128 && d % 16 == 0; }
+extern "C" int srk_flash_ce_supported(int d) {
+  static int wide = -1;                   // SESSREC_FCE_WIDE=0 keeps d = 256 on the materialised 3xTF32 head
+  if (wide < 0) {
+    const char* e = getenv("SESSREC_FCE_WIDE");
+    wide = !(e && e[0] == '0');
+  }
+  return (d >= 16 && d <= 128 && d % 16 == 0) || (d == 256 && wide);
+}
+
+namespace {
+
+int fill_wide(FceWide& p, int B, int V, int d, float scale, const int* labels, bool bwd) {
+  SRK_REQUIRE(d == 256, "flash_ce (wide): d = %d unsupported", d);
+  SRK_REQUIRE(scale > 0.f, "flash_ce: scale must be positive");
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.V = V; p.d = d;
+  p.nch = d / 64;
+  p.tv = bwd ? WTV : TV;
+  p.ntm = srk_cdiv(B, TB);
+  p.nvt = srk_cdiv(V, p.tv);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    SRK_CUDA(cudaGetDevice(&dev));
+    SRK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int nvr = sms / p.ntm;
+  if (nvr < 1) nvr = 1;
+  if (nvr > p.nvt) nvr = p.nvt;
+  p.nvr = nvr;
+  const size_t fixed = bwd ? (size_t)2 * p.nch * CHUNK + 2 * CHUNK : 0;
+  const size_t stage = bwd ? 2 * (size_t)WECHUNK : 2 * (size_t)CHUNK;
+  int st = (int)((FCE_MAX_SMEM - 1024 - fixed) / stage);
+  if (st > W_MAX_STAGES) st = W_MAX_STAGES;
+  SRK_REQUIRE(st >= 2, "flash_ce (wide): shared-memory budget exceeded");
+  p.estages = st;
+  p.scale = scale;
+  p.labels = labels;
+  // instruction descriptors: D = F32, A = B = BF16, majors (bit 15 / 16: 1 = MN-major), N >> 3, M >> 4
+  const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 4) << 24);
+  p.idesc_z = base | ((uint32_t)(p.tv >> 3) << 17);
+  p.idesc_ds = base | (1u << 16) | ((uint32_t)(64 >> 3) << 17);
+  p.idesc_de = base | (1u << 15) | (1u << 16) | ((uint32_t)(WTV >> 3) << 17);
+  return SRK_OK;
+}
+
+size_t wide_smem(const FceWide& p, bool bwd) {
+  return (bwd ? (size_t)2 * p.nch * CHUNK + 2 * CHUNK + (size_t)p.estages * 2 * WECHUNK : (size_t)p.estages * 2 * CHUNK) + 1024;
+}
+
+int wide_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi, const uint16_t* Elo,
+             long long lde, float scale, const int* labels, float* lse, float* nll, float* part, cudaStream_t st) {
+  FceWide p;
+  SRK_TRY(fill_wide(p, B, V, d, scale, labels, false));
+  p.part = part;
+  p.zlab = part + 4LL * p.nvr * B;
+  p.Shi = Shi; p.Slo = Slo; p.lds = lds;
+  SRK_REQUIRE(((reinterpret_cast<uintptr_t>(Shi) | reinterpret_cast<uintptr_t>(Slo)) & 15u) == 0 && lds % 8 == 0,
+              "flash_ce_fwd: shat operands must be 16-byte aligned");
+  CUtensorMap mEh, mEl;
+  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde, 64));
+  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde, 64));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    attr_set = true;
+  }
+  srk_launch(fce_fwd_wide_kernel, p.ntm * p.nvr, THREADS, wide_smem(p, false), st, mEh, mEl, p);
+  SRK_LAUNCH_CHECK();
+  srk_launch(fce_finalize_kernel, srk_cdiv((long long)B * 32, 256), 256, 0, st, p.part, p.zlab, labels, B, V, 2 * p.nvr, lse, nll);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+int wide_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi, const uint16_t* Elo,
+             long long lde, float scale, const int* labels, const float* lse, const float* gout, float* dS, float* dEpart,
+             cudaStream_t st) {
+  FceWide p;
+  SRK_TRY(fill_wide(p, B, V, d, scale, labels, true));
+  p.lse = lse;
+  p.gout = gout;
+  p.dEpart = dEpart;
+  CUtensorMap mSh, mSl, mEh, mEl, mdS;
+  SRK_TRY(bf16_map(&mSh, Shi, d, B, lds, 64));
+  SRK_TRY(bf16_map(&mSl, Slo, d, B, lds, 64));
+  SRK_TRY(bf16_map(&mEh, Ehi, d, V, lde, 64, WTV));
+  SRK_TRY(bf16_map(&mEl, Elo, d, V, lde, 64, WTV));
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)B};
+    cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+    cuuint32_t box[2] = {32, 128};
+    SRK_TRY(make_map_nd(&mdS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dS, dims, strides, box));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CUDA(cudaFuncSetAttribute(fce_bwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    attr_set = true;
+  }
+  SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
+  srk_launch(fce_bwd_wide_kernel, p.ntm * p.nvr, THREADS_BWD, wide_smem(p, true), st, mSh, mSl, mEh, mEl, mdS, p);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+}  // namespace
 
 extern "C" long long srk_flash_ce_part_floats(int B, int V) {
   // upper bound that does not depend on the SM count: 2 partial pairs per (catalog tile, row) + label logits
@@ -803,6 +1365,7 @@ extern "C" int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const 
   if (B <= 0) return SRK_OK;
   SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && part != nullptr, "flash_ce_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (d > 128) return wide_fwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, nll, part, st);
   FceParams p;
   SRK_TRY(fill_params(p, B, V, d, scale, labels, false));
   p.part = part;
@@ -835,6 +1398,7 @@ extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const 
   if (B <= 0) return SRK_OK;
   SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && dS != nullptr && dEpart != nullptr, "flash_ce_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (d > 128) return wide_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, st);
   FceParams p;
   SRK_TRY(fill_params(p, B, V, d, scale, labels, true));
   p.lse = lse;

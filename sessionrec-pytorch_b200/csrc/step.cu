@@ -131,16 +131,40 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   SRK_TRY(parse_batch(batch_dev, batch_hdr_host, b));
   SRK_REQUIRE(L >= 1 && L <= 8, "step: 1..8 layers");
   const int B = b.B, N = b.N, M = b.M;
-  const long long ldz = (V + 3) / 4 * 4;
   const int ldzel = H * d + H;
   const bool umma = (use_umma & 1) && d <= 256;
   const bool fused_lse = (use_umma & 2) != 0;      // bit 1: persistent forward kernel with the fused LSE epilogue
   // bit 2: fused scoring + CE head (csrc/flash_ce.cu): no (B, V) logits in memory, bf16 x 3 tensor-core products
   const bool flash = umma && (use_umma & 4) != 0 && srk_flash_ce_supported(d);
   const bool drop = dropout_p > 0.f;
+  // bit 3: catalog-sharded head (BASELINE config 5): this rank scores rows [lo, hi) of the table only; the session encoder
+  // is replicated on the whole batch.  Exchanges, all enqueued here through csrc/comm.cu: ONE sum all-reduce of [2, B]
+  // soft-max statistics (|logit| <= 12: constant shift), one of dS [B, d], and at the end of the step every owner
+  // broadcasts its updated rows (the table gradient is never all-reduced: rank-local Adam on the owned rows).
+  const int world = srk_comm_world(), rank = srk_comm_rank();
+  const bool shard = (use_umma & 8) != 0 && world > 1;
+  int lo = 0, hi = V;
+  if (shard) {
+    const int base = V / world, rem = V % world;
+    lo = rank * base + (rank < rem ? rank : rem);
+    hi = lo + base + (rank < rem ? 1 : 0);
+  }
+  const int Vl = hi - lo;              // catalog rows this rank scores
+  const long long ldz = (Vl + 3) / 4 * 4;
+  const bool dp_inside = phase == 3;   // data parallel: the gradient all-reduce is enqueued by this step
+  SRK_REQUIRE(!dp_inside || world > 1, "step: phase 3 needs a communicator (srk_comm_init)");
   Arena ar{reinterpret_cast<uint8_t*>(workspace), (size_t)workspace_bytes, 0, true};
   auto P = [&](int slot) { return params + slot_off_host[slot]; };
   auto G = [&](int slot) { return grads + slot_off_host[slot]; };
+  // buffers that cross the links sit at fixed workspace offsets (they depend on B and d only): the captured NCCL nodes
+  // of a replayed step keep their pointers
+  float *xpack = nullptr, *dshat_x = nullptr;
+  int* labels_l = nullptr;
+  if (shard) {
+    xpack = ar.f(2 * (size_t)b.B);
+    dshat_x = ar.f((size_t)b.B * d);
+    labels_l = reinterpret_cast<int*>(ar.raw(sizeof(int) * (size_t)b.B));
+  }
   const int s_ro = 1 + 8 * L;        // readout.fc_u.0.weight, .bias, fc_v, fc_e, fc_sr
   float* E = P(0);
   auto dcfg = [&](uint32_t site) { srk_dropout c; c.p = dropout_p; c.site = site; c.seed = seed; return c; };
@@ -159,30 +183,33 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   tm.mark("zero_grad");
 
   // ---- forward -------------------------------------------------------------------------------------------
-  float *Ehat = ar.f((size_t)V * d), *enorm = ar.f(V);
+  float *Ehat = ar.f((size_t)Vl * d), *enorm = ar.f(Vl);
   float *Ehi = nullptr, *Elo = nullptr;
   uint16_t *Ebh = nullptr, *Ebl = nullptr;
   if (flash) {
-    Ebh = reinterpret_cast<uint16_t*>(ar.raw((size_t)V * d * 2));
-    Ebl = reinterpret_cast<uint16_t*>(ar.raw((size_t)V * d * 2));
+    Ebh = reinterpret_cast<uint16_t*>(ar.raw((size_t)Vl * d * 2));
+    Ebl = reinterpret_cast<uint16_t*>(ar.raw((size_t)Vl * d * 2));
   } else if (umma) {
-    Ehi = ar.f((size_t)V * d);
-    Elo = ar.f((size_t)V * d);
+    Ehi = ar.f((size_t)Vl * d);
+    Elo = ar.f((size_t)Vl * d);
   }
+  float* El = E + (size_t)lo * d;      // the rows this rank scores (all of them without sharding)
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   // nn.Embedding(max_norm=1) renorms the rows a lookup touches (msgifsr.py:247) and, at the scoring head, every row
   // (msgifsr.py:276).  The gather only needs the touched rows: they are renormed first on the critical path; the
   // catalog-wide pass (renorm of the remaining rows + normalisation + bf16 split) starts once the gather has read the
   // table and runs beside the encoder.
-  if (ss) SRK_TRY(srk_renorm_rows(E, b.uid, b.U, d, 1.0f, st));
+  // Sharded: the rows of other owners are renormed by their owners and come back with the end-of-step broadcast; the rows
+  // the gather touches are renormed by every replica (same arithmetic on the same values).
+  if (ss || shard) SRK_TRY(srk_renorm_rows(E, b.uid, b.U, d, 1.0f, st));
   else SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, Ebh, Ebl, st));
   tm.mark("catalog_prep");
   float *X = ar.f((size_t)N * d), *rnX = ar.f(N);
   srk_dropout dc_e = dcfg(SRK_SITE_EMBED + 1);
   SRK_TRY(srk_embed_gather_fwd(E, b.iid, N, d, SRK_NORM_L2, drop ? &dc_e : nullptr, X, rnX, nullptr, st));
-  if (ss) {
+  if (ss || shard) {
     SRK_TRY(order(st, s4));
-    SRK_TRY(srk_catalog_prep_fwd(E, V, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, Ebh, Ebl, s4));
+    SRK_TRY(srk_catalog_prep_fwd(El, Vl, d, SRK_NORM_L2, 1.0f, Ehat, enorm, Ehi, Elo, Ebh, Ebl, s4));
   }
   srk_dropout dc_attn = dcfg(SRK_SITE_GAT_ATTN);
 
@@ -192,7 +219,7 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   // dZel^T x_s) run on the tcgen05 3xTF32 GEMM instead of the fp32 CUDA-core kernel (measured 0.441 -> 0.419 ms/step at
   // cfg1 for the two on the critical path); SESSREC_TC_ENCODER=0 switches back.
   const char* tce = getenv("SESSREC_TC_ENCODER");
-  const bool tc_enc = umma && d <= 128 && d % 32 == 0 && !(tce && tce[0] == '0');
+  const bool tc_enc = umma && d <= 256 && d % 32 == 0 && !(tce && tce[0] == '0');
   // W_aug = [W ; a_l-contracted rows] and w_r depend on the parameters only: built beside the gather (s2)
   SRK_TRY(order(st, s2));                        // after the previous step's optimizer update
   for (int l = 0; l < L; ++l) {
@@ -340,24 +367,37 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   float *Z = flash ? nullptr : ar.f((size_t)B * ldz), *lse = ar.f(B), *nll = ar.f(B);
   float *sh = nullptr, *sl = nullptr;
   SRK_REQUIRE(ar.ok, "step: workspace too small");
+  // sharded: the head sees the label only where this rank owns its row; lse / nll are then LOCAL until the exchange below
+  const int* hlabels = b.labels;
+  if (shard) {
+    SRK_TRY(srk_shard_labels(b.labels, B, lo, hi, labels_l, st));
+    hlabels = labels_l;
+  }
   if (flash) {
-    float* part = ar.f((size_t)srk_flash_ce_part_floats(B, V));
+    float* part = ar.f((size_t)srk_flash_ce_part_floats(B, Vl));
     SRK_REQUIRE(ar.ok, "step: workspace too small");
-    SRK_TRY(srk_flash_ce_fwd(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, b.labels, lse, nll, part, st));
+    SRK_TRY(srk_flash_ce_fwd(B, Vl, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, hlabels, lse, nll, part, st));
   } else if (umma) {
     sh = ar.f((size_t)B * d); sl = ar.f((size_t)B * d);
     SRK_TRY(srk_split_tf32(shat, d, B, d, sh, sl, d, st));
     if (fused_lse) {
-      float* part = ar.f(4 * (size_t)((V + 255) / 256) * B + B);
+      float* part = ar.f(4 * (size_t)((Vl + 255) / 256) * B + B);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_TRY(srk_umma_score_fwd(B, V, d, sh, sl, d, Ehi, Elo, d, Z, ldz, 12.0f, b.labels, lse, nll, part, st));
+      SRK_TRY(srk_umma_score_fwd(B, Vl, d, sh, sl, d, Ehi, Elo, d, Z, ldz, 12.0f, hlabels, lse, nll, part, st));
     } else {
-      SRK_TRY(srk_umma_gemm(0, B, V, d, sh, sl, d, Ehi, Elo, d, Z, ldz, 12.0f, 0, 1, st));
-      SRK_TRY(srk_ce_rows_fwd(Z, ldz, b.labels, B, V, 0, lse, nll, st));
+      SRK_TRY(srk_umma_gemm(0, B, Vl, d, sh, sl, d, Ehi, Elo, d, Z, ldz, 12.0f, 0, 1, st));
+      SRK_TRY(srk_ce_rows_fwd(Z, ldz, hlabels, B, Vl, 0, lse, nll, st));
     }
   } else {
-    SRK_TRY(gemm(st, B, V, d, shat, d, 1, Ehat, 1, d, Z, ldz, nullptr, nullptr, nullptr, nullptr, 12.0f));
-    SRK_TRY(srk_ce_rows_fwd(Z, ldz, b.labels, B, V, 0, lse, nll, st));
+    SRK_TRY(gemm(st, B, Vl, d, shat, d, 1, Ehat, 1, d, Z, ldz, nullptr, nullptr, nullptr, nullptr, 12.0f));
+    SRK_TRY(srk_ce_rows_fwd(Z, ldz, hlabels, B, Vl, 0, lse, nll, st));
+  }
+  if (shard) {
+    // THE exchange of the sharded head: per session sum_v exp(logit - 12) over this rank's rows and the label logit where
+    // owned - one [2, B] sum all-reduce over NVLink - then the global log-sum-exp / NLL (cosine logits: |logit| <= 12)
+    SRK_TRY(srk_shard_lse_pack(lse, nll, labels_l, nullptr, 12.0f, B, xpack, st));
+    SRK_TRY(srk_comm_allreduce(xpack, 2LL * B, 0, st));
+    SRK_TRY(srk_shard_lse_unpack(xpack, nullptr, 12.0f, B, lse, nll, st));
   }
 
   tm.mark("score_fwd+lse");
@@ -372,19 +412,19 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   // ---- backward ------------------------------------------------------------------------------------------
   const int de_parts = flash ? srk_flash_ce_bwd_parts(B) : 1;
   float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;
-  float *dshat = ar.f((size_t)B * d), *dEhat = ar.f((size_t)de_parts * V * d);
+  float *dshat = shard ? dshat_x : ar.f((size_t)B * d), *dEhat = ar.f((size_t)de_parts * Vl * d);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   if (flash) {
-    SRK_TRY(srk_flash_ce_bwd(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, b.labels, lse, one_dev, dshat, dEhat, st));
+    SRK_TRY(srk_flash_ce_bwd(B, Vl, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, hlabels, lse, one_dev, dshat, dEhat, st));
   } else if (umma) {
     SRK_TRY(srk_zero_async(dshat, sizeof(float) * (size_t)B * d, st));
     // Backward of the head, chunked over catalog columns so that each chunk's dZ hi/lo pair (2 x B x Vc x 4 bytes) is
     // still L2-resident when the two tensor-core GEMMs read it (the whole pair, 2 x 88 MB at cfg1, is not).
     int chunks = head_chunks < 1 ? 1 : head_chunks;
-    int Vc = ((V + chunks - 1) / chunks + 255) / 256 * 256;
-    for (int c0 = 0; c0 < V; c0 += Vc) {
-      const int nc = V - c0 < Vc ? V - c0 : Vc;
-      SRK_TRY(srk_ce_rows_bwd_cols(Z, ldz, b.labels, lse, one_dev, 12.0f, B, c0, nc, Zlo, st));
+    int Vc = ((Vl + chunks - 1) / chunks + 255) / 256 * 256;
+    for (int c0 = 0; c0 < Vl; c0 += Vc) {
+      const int nc = Vl - c0 < Vc ? Vl - c0 : Vc;
+      SRK_TRY(srk_ce_rows_bwd_cols(Z, ldz, hlabels, lse, one_dev, 12.0f, B, c0, nc, Zlo, st));
       const int nkb = (nc + 31) / 32;
       int split = 148 / ((B + 127) / 128);      // one wave of CTAs
       if (split < 1) split = 1;
@@ -395,23 +435,27 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
     }
   } else {
     SRK_TRY(srk_zero_async(dshat, sizeof(float) * (size_t)B * d, st));
-    SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, one_dev, 12.0f, B, V, 0, Zlo, st));
-    SRK_TRY(srk_zero_async(dEhat, sizeof(float) * (size_t)V * d, st));
-    SRK_TRY(gemm(st, B, d, V, Z, ldz, 1, Ehat, d, 1, dshat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
-    SRK_TRY(gemm(st, V, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
+    SRK_TRY(srk_ce_rows_bwd(Z, ldz, hlabels, lse, one_dev, 12.0f, B, Vl, 0, Zlo, st));
+    SRK_TRY(srk_zero_async(dEhat, sizeof(float) * (size_t)Vl * d, st));
+    SRK_TRY(gemm(st, B, d, Vl, Z, ldz, 1, Ehat, d, 1, dshat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
+    SRK_TRY(gemm(st, Vl, d, B, Z, 1, ldz, shat, d, 1, dEhat, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
   }
   tm.mark("ce_bwd+dS+dE");
   // gradients start here: zero_grad (s4) must be complete; the catalog backward (a [V, d] pass) stays on s4 and runs
   // beside the whole encoder backward, it only has to finish before the scatter-add touches the same rows
   // (zero_grad and the catalog pass on s4 were joined before the head's forward)
   SRK_TRY(order(st, s4));
-  SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, de_parts, V, d, SRK_NORM_L2, G(0), s4));
+  SRK_TRY(srk_catalog_prep_bwd(El, Ehat, enorm, dEhat, de_parts, Vl, d, SRK_NORM_L2, G(0) + (size_t)lo * d, s4));
+  // sharded: every rank holds dS of its own catalog rows only - the second (and last) exchange of the head, while the
+  // catalog backward above runs on s4
+  if (shard) SRK_TRY(srk_comm_allreduce(dshat, (long long)B * d, 0, st));
   const bool live = srk_launch_mode() == SRK_LAUNCH_DIRECT || srk_launch_mode() == SRK_LAUNCH_CAPTURE;
   if (ss && live) SRK_CUDA(cudaEventRecord(ss->ev_cat, s4));
   // Adam in two parts: the table rows this batch did not gather have their final gradient now (the scatter-add only
   // touches gathered rows, and only those rows of E are read again by the backward), so their update - 95 % of the
   // optimizer's bytes - runs on s4 beside the encoder backward; the gathered rows and all other parameters follow at the end
-  const bool split_adam = ss != nullptr && phase == 0 && do_adam;
+  // (single device only: under data parallelism a row is final after the all-reduce, under sharding the owner updates it)
+  const bool split_adam = ss != nullptr && phase == 0 && do_adam && !shard;
   const long long tab = slot_off_host[0];
   const long long tab_span = ((long long)V * d + 63) / 64 * 64;
   if (split_adam)
@@ -552,12 +596,29 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   SRK_TRY(order(s2, st));
   SRK_TRY(order(s3, st));
   tm.mark("scatter");
+  if (dp_inside) {
+    // data parallel: the flat gradient buffer (every rank seeded its backward with B_local / B_global) is summed over the
+    // ranks right here, behind the last gradient kernel and inside the same graph replay - no return to Python
+    SRK_TRY(order(s4, st));
+    SRK_TRY(srk_comm_allreduce(grads, n_flat, 0, st));
+  }
   if (split_adam) {
     SRK_TRY(srk_adam_step_split(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, tab, V, d,
                                 tab_span, b.uid, b.U, 1, lr, beta1, beta2, eps, adam_step, grad_scale, st));
-  } else if (phase == 0 && do_adam) {
+  } else if ((phase == 0 || phase == 3) && do_adam) {
+    if (shard) {
+      SRK_TRY(order(s4, st));                    // the owned rows' head gradient (catalog backward on s4)
+      // The encoder is replicated: every rank computed the gradients of the non-table parameters from the same inputs, up
+      // to the summation order of atomics.  Averaging them (two small all-reduces around the table, ~MBs) makes the
+      // replicas' updates bit-identical, so they cannot drift apart over a long run.
+      SRK_TRY(srk_comm_allreduce(grads, tab, 2, st));
+      SRK_TRY(srk_comm_allreduce(grads + tab + tab_span, n_flat - tab - tab_span, 2, st));
+    }
     SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
                           adam_step, grad_scale, st));
+    // sharded: seg_decay marks the table rows of the other owners inactive (rank-local Adam); every owner now hands its
+    // updated rows to the other replicas - one grouped broadcast instead of an all-reduce of the [V, d] table gradient
+    if (shard) SRK_TRY(srk_comm_share_rows(E, V, d, st));
   }
   tm.mark("adam");
   SRK_TRY(order(s4, st));
@@ -688,7 +749,7 @@ bool srk_step_want_graph(int phase) {
   // auto: replay pays off when the host is the bottleneck, i.e. when several ranks share the CPU (measured on 8 x B200:
   // 0.83 -> 0.32 ms of enqueue per step, 4.8 M -> 6.8 M sessions/s); a single rank is GPU-bound either way and keeps the
   // plain launches, whose first kernels start while the rest is still being enqueued
-  return g_graphs_on == 1 || (g_graphs_on == 2 && phase == 1);
+  return g_graphs_on == 1 || (g_graphs_on == 2 && (phase == 1 || phase == 3));
 }
 
 // phase: 0 = everything; 1 = zero_grad + forward + backward only (no Adam): lets the caller all-reduce the gradients;
@@ -710,8 +771,8 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
   const int has_edges = batch_hdr_host[REL_TAB + 2] > 0;
   const unsigned long long key = ((unsigned long long)(batch_hdr_host[1] & 0xFFFFF) << 44) | ((unsigned long long)(d & 0x3FF) << 34) |
                                  ((unsigned long long)(V & 0x3FFFF) << 16) | ((unsigned long long)(dev & 15) << 12) |
-                                 ((unsigned long long)(L & 15) << 8) | ((unsigned long long)(use_umma & 7) << 5) |
-                                 ((unsigned long long)(dropout_p > 0.f) << 4) | ((unsigned long long)(phase & 1) << 3) |
+                                 ((unsigned long long)(L & 15) << 8) | ((unsigned long long)(use_umma & 7) << 5) | ((unsigned long long)(phase == 3) << 62) |
+                                 ((unsigned long long)(dropout_p > 0.f) << 4) | ((unsigned long long)(phase & 1) << 3) | ((unsigned long long)(use_umma & 8) << 60) |
                                  ((unsigned long long)(do_adam != 0) << 2) | ((unsigned long long)has_edges << 1) |
                                  (unsigned long long)(head_chunks > 1);
   return srk_step_driver(caller, key, srk_step_want_graph(phase), [&](void* run) {

@@ -335,10 +335,17 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   SRK_TRY(srk_embed_scatter_bwd(E, b.iid, b.perm, b.uoff, b.uid, b.U, N, d, emb_mode, drop ? &dc_e : nullptr, rn, dX, nullptr, G(0), st));
   SRK_TRY(order(s2, st));
   tm.mark("scatter");
+  if (phase == 3) {
+    // data parallel: the flat gradient buffer (every rank seeded its backward with B_local / B_global) is summed over the
+    // ranks right here, behind the last gradient kernel and inside the same graph replay (csrc/comm.cu)
+    SRK_REQUIRE(srk_comm_world() > 1, "srgnn step: phase 3 needs a communicator (srk_comm_init)");
+    SRK_TRY(order(s4, st));
+    SRK_TRY(srk_comm_allreduce(grads, n_flat, 0, st));
+  }
   if (split_adam) {
     SRK_TRY(srk_adam_step_split(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, tab, V, d,
                                 tab_span, b.uid, b.U, 1, lr, beta1, beta2, eps, adam_step, grad_scale, st));
-  } else if (phase == 0 && do_adam) {
+  } else if ((phase == 0 || phase == 3) && do_adam) {
     SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
                           adam_step, grad_scale, st));
   }
@@ -349,7 +356,8 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   return SRK_OK;
 }
 
-// phase: 0 = everything; 1 = zero_grad + forward + backward only (the caller all-reduces the gradients); 2 = Adam only.
+// phase: 0 = everything; 1 = zero_grad + forward + backward only (the caller all-reduces the gradients); 2 = Adam only;
+// 3 = everything with the data-parallel gradient all-reduce enqueued by the step itself (srk_comm_allreduce).
 // flags: bit 0 tensor cores, bit 1 fused-LSE forward scoring kernel, bit 2 fused scoring + CE head (flash CE).
 extern "C" int srk_srgnn_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
                                     const long long* slot_off_host, int V, int d, int L, int niser, float scale,
@@ -370,7 +378,7 @@ extern "C" int srk_srgnn_train_step(const int* batch_dev, const int* batch_hdr_h
                                  ((unsigned long long)(dev & 15) << 11) | ((unsigned long long)(L & 15) << 7) |
                                  ((unsigned long long)(flags & 7) << 4) | ((unsigned long long)(dropout_p > 0.f) << 3) |
                                  ((unsigned long long)(niser != 0) << 2) | ((unsigned long long)(dead_layers != 0) << 1) |
-                                 (unsigned long long)(do_adam != 0 && phase == 0);
+                                 (unsigned long long)(do_adam != 0 && phase == 0) | ((unsigned long long)(phase == 3) << 62);
   return srk_step_driver(caller, key, srk_step_want_graph(phase), [&](void* run) {
     return srgnn_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, niser, scale, dead_layers, dropout_p, seed,
                       flags, workspace, workspace_bytes, gseed_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev,

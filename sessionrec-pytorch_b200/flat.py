@@ -40,13 +40,22 @@ class FlatParams:
         p, o = self.params[i], self.offsets[i]
         return flat[o:o + p.numel()].view(p.shape)
 
-    def decay_segments(self, weight_decay, inactive=()):
+    def decay_segments(self, weight_decay, inactive=(), owned_rows=None):
         """(seg_off int64[S+1], seg_decay fp32[S]) on the device: `fix_weight_decay` semantics of the reference
         (`src/utils/train.py:12-23`): names containing bias / batch_norm / activation get no L2 term.  Names in `inactive`
-        get -1: the Adam kernels leave such a segment untouched, like torch.optim.Adam skips a parameter whose grad is None."""
-        offs = list(self.offsets) + [self.total]
-        dec = [-1.0 if n in inactive else
-               (0.0 if any(t in n for t in ('bias', 'batch_norm', 'activation')) else float(weight_decay))
-               for n in self.names]
+        get -1: the Adam kernels leave such a segment untouched, like torch.optim.Adam skips a parameter whose grad is None.
+        owned_rows = (name, lo, hi): catalog sharding - of that [V, d] table only rows [lo, hi) are this rank's to update;
+        the table becomes three segments with the outer two inactive (their owners broadcast the updated rows)."""
+        offs, dec = [], []
+        for n, p, o in zip(self.names, self.params, self.offsets):
+            dcy = -1.0 if n in inactive else (0.0 if any(t in n for t in ('bias', 'batch_norm', 'activation')) else float(weight_decay))
+            if owned_rows is not None and n == owned_rows[0]:
+                lo, hi, d = owned_rows[1], owned_rows[2], p.shape[1]
+                offs += [o, o + lo * d, o + hi * d]
+                dec += [-1.0, dcy, -1.0]
+            else:
+                offs.append(o)
+                dec.append(dcy)
+        offs.append(self.total)
         dev = self.data.device
         return (torch.tensor(offs, dtype=torch.int64, device=dev), torch.tensor(dec, dtype=torch.float32, device=dev))

@@ -103,6 +103,7 @@ class MSGIFSR(SessRecModule):
         self.beta.data = torch.tensor(1.0)
         self.fusion, self.extra = fusion, extra
         self.native_step = True
+        self.dp_allreduce_inside = True      # data parallel: all-reduce from inside the native step once parallel.init_comm ran
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.embedding_dim)
@@ -269,8 +270,11 @@ class MSGIFSR(SessRecModule):
 
     # ---- native fused step (csrc/step.cu) ------------------------------------------------------------------------
     def _native_ok(self, batch):
+        from . import parallel
+        # catalog sharding inside the native step needs this library's own communicator (parallel.init_comm); without it the
+        # sharded head is composed from the staged kernels with torch.distributed collectives
         return (self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
-                and self._shard is None)          # the catalog-sharded head is composed from the staged kernels
+                and (self._shard is None or parallel.comm_ready()))
 
     def _slot_offsets(self):
         import numpy as np
@@ -310,8 +314,16 @@ class MSGIFSR(SessRecModule):
         if group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(group)
+        from . import parallel
         gseed = self._dp_weight(batch, group, global_batch)       # B_local / B_global: the all-reduced sum is the global mean
-        seg_decay = self._seg_decay(batch)
+        shard = self._shard is not None
+        owned = None
+        if shard:
+            if group is not None:
+                raise SessRecError('catalog sharding and data parallelism are separate modes: pass group=None')
+            lo, hi = self._rows(self.num_items)
+            owned = ('embeddings.weight', lo, hi)
+        seg_off, seg_decay, n_seg = self._segments(batch, owned)
         o['step'] += 1
         loss = torch.empty((), dtype=torch.float32, device=fp.data.device)
 
@@ -320,12 +332,14 @@ class MSGIFSR(SessRecModule):
             L.call('srk_msgifsr_train_step', ptr(batch.buf), ctypes.c_void_p(batch.hdr.ctypes.data), ptr(fp.data),
                    ptr(fp.grad), ctypes.c_void_p(st['slots'].ctypes.data), self.num_items, self.embedding_dim,
                    self.num_layers, float(p), ctypes.c_uint64(seed),
-                   int(self.use_tensor_cores) | (2 if self.fused_lse else 0) | (4 if self.flash_ce else 0), ptr(st['ws']),
-                   st['ws_bytes'], ptr(gseed), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
-                   ptr(o['seg_off']), ptr(seg_decay), o['n_seg'], float(o['lr']), float(o['betas'][0]),
+                   int(self.use_tensor_cores) | (2 if self.fused_lse else 0) | (4 if self.flash_ce else 0) | (8 if shard else 0),
+                   ptr(st['ws']), st['ws_bytes'], ptr(gseed), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
+                   ptr(seg_off), ptr(seg_decay), n_seg, float(o['lr']), float(o['betas'][0]),
                    float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0, phase, int(self.head_chunks), stream)
         if world == 1:
             call(0)
+        elif parallel.comm_ready() and self.dp_allreduce_inside:
+            call(3)             # the gradient all-reduce is enqueued by the step itself (csrc/comm.cu), no return to Python
         else:
             call(1)
             dist.all_reduce(fp.grad, group=group)

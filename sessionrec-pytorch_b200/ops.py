@@ -118,6 +118,12 @@ def umma_gemm(form, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, alpha=1.0, ac
           int(bool(accumulate)), int(split_k))
 
 
+def comm_allreduce(buf, op=0):
+    """In-place all-reduce on this library's own NCCL communicator (parallel.init_comm): op 0 sum, 1 max, 2 average."""
+    _need_cuda(buf)
+    _call('srk_comm_allreduce', ptr(buf), buf.numel(), int(op))
+
+
 def umma_score_fwd(M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, Z, ldz, alpha, labels, lse, nll, part):
     _call('srk_umma_score_fwd', M, N, K, ptr(Ahi), ptr(Alo), lda, ptr(Bhi), ptr(Blo), ldb, ptr(Z), ldz, float(alpha),
           ptr(labels), ptr(lse), ptr(nll), ptr(part))

@@ -7,8 +7,46 @@ The reference is single-device; the path shards two ways
     soft-max statistics (and the label logit) cross the links: ONE all-reduce of a [B, 2] tensor when the logits are
     bounded (NISER / MSGIFSR: |z| <= scale), a max + sum pair otherwise; backward needs one all-reduce of dS [B, d].
 Everything here is device-agnostic tensor plumbing so that it can be exercised on CPU with gloo."""
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+_COMM = dict(ready=False, rank=0, world=1)
+
+
+def init_comm(group=None, nccl_path=None):
+    """Creates this process's own NCCL communicator inside libsessrec_b200.so (csrc/comm.cu) so that the collectives of a
+    training step are enqueued by the native step itself, between its kernels.  Collective over `group` (default: WORLD):
+    rank 0 draws the NCCL unique id, torch.distributed only carries those 128 bytes (bootstrap).  The CUDA device of this
+    process must be current.  Idempotent; returns (rank, world)."""
+    if _COMM['ready']:
+        return _COMM['rank'], _COMM['world']
+    from ._lib import lib
+    L = lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    path = None if nccl_path is None else str(nccl_path).encode()
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        L.call('srk_comm_unique_id', buf, path)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().tolist())
+    L.call('srk_comm_init', ctypes.create_string_buffer(raw, 128), rank, world, path)
+    _COMM.update(ready=True, rank=rank, world=world)
+    return rank, world
+
+
+def comm_ready():
+    return _COMM['ready']
+
+
+def destroy_comm():
+    if _COMM['ready']:
+        from ._lib import lib
+        lib().call('srk_comm_destroy')
+        _COMM.update(ready=False, rank=0, world=1)
 
 
 def shard_slice(n, rank, world):

@@ -105,6 +105,7 @@ class SRGNN(SessRecModule):
         # The reference runs the GGNN layers and drops their result; keep the same amount of device work by default.
         self.compute_dead_layers = True
         self.native_step = True
+        self.dp_allreduce_inside = True      # data parallel: all-reduce from inside the native step once parallel.init_comm ran
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.embedding_dim)
@@ -133,6 +134,7 @@ class SRGNN(SessRecModule):
         if batch is None or batch.B == 0 or not self.native_step or self._shard is not None or batch.kind != 'session':
             return super().train_step(batch, group, global_batch)
         import ctypes
+        from . import parallel
         from ._lib import lib, ptr
         if self._opt is None:
             self.configure_optimizer()
@@ -149,7 +151,7 @@ class SRGNN(SessRecModule):
         p, seed = self._p(), self._next_seed()
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         gseed = self._dp_weight(batch, group, global_batch)
-        seg_decay = self._seg_decay(batch)
+        seg_off, seg_decay, n_seg = self._segments(batch)
         o['step'] += 1
         loss = torch.empty((), dtype=torch.float32, device=fp.data.device)
         flags = int(self.use_tensor_cores) | (2 if self.fused_lse else 0) | (4 if self.flash_ce else 0)
@@ -160,10 +162,12 @@ class SRGNN(SessRecModule):
                    ctypes.c_void_p(st['slots'].ctypes.data), V, d, self.num_layers, int(self.niser),
                    float(self.scale) if self.scale else 1.0, int(self.compute_dead_layers), float(p), ctypes.c_uint64(seed),
                    flags, ptr(st['ws']), st['ws_bytes'], ptr(gseed), ptr(loss), 1, ptr(o['m']), ptr(o['v']), fp.data.numel(),
-                   ptr(o['seg_off']), ptr(seg_decay), o['n_seg'], float(o['lr']), float(o['betas'][0]), float(o['betas'][1]),
+                   ptr(seg_off), ptr(seg_decay), n_seg, float(o['lr']), float(o['betas'][0]), float(o['betas'][1]),
                    float(o['eps']), int(o['step']), 1.0, phase, stream)
         if group is None:
             call(0)
+        elif parallel.comm_ready() and self.dp_allreduce_inside:
+            call(3)             # the gradient all-reduce is enqueued by the step itself (csrc/comm.cu)
         else:
             import torch.distributed as dist
             call(1)

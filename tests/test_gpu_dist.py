@@ -37,12 +37,30 @@ def _worker(rank, world, port, mode, ret):
         seqs = [s for s, _ in c['samples']]
         labels = [l for _, l in c['samples']]
         kind = 'session' if c['model'] in ('SRGNN', 'NISER') else 'ccs'
-        if mode == 'dp':
-            s_r, l_r = parallel.shard_batch(seqs, labels, rank, world)
-            b = pkg.SessionBatch.build(s_r, l_r, kind, c['K']).to(dev)
+        if mode.startswith('dp'):
+            # dp: even halves, gradient all-reduce through torch.distributed between two C calls; dp_native: the step enqueues
+            # the all-reduce itself on this library's own NCCL communicator; dp_uneven: rank 0 holds two thirds of the batch,
+            # B_global is all-reduced; dp_empty: rank 1's shard is empty and it still joins the collectives
+            if mode in ('dp_native', 'dp_uneven_native'):
+                parallel.init_comm(dist.group.WORLD)
+            else:
+                m.dp_allreduce_inside = False
+            n = len(seqs)
+            cut = {'dp': n // 2, 'dp_native': n // 2, 'dp_uneven': 2 * n // 3, 'dp_uneven_native': 2 * n // 3, 'dp_empty': n}[mode]
+            s_r, l_r = (seqs[:cut], labels[:cut]) if rank == 0 else (seqs[cut:], labels[cut:])
+            b = pkg.SessionBatch.build(s_r, l_r, kind, c['K']).to(dev) if len(s_r) else None
             m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
-            m.train_step(b, dist.group.WORLD)
-            ret[rank] = {n: p.detach().cpu() for n, p in m.named_parameters()}
+            for _ in range(4 if 'native' in mode else 1):       # > 2 steps: the third captures the graph, the fourth replays it
+                m.train_step(b, dist.group.WORLD, global_batch=n if mode in ('dp', 'dp_native') else None)
+            ret[rank] = {n_: p.detach().cpu() for n_, p in m.named_parameters()}
+        elif mode == 'shard_step':
+            # catalog-sharded training step, all exchanges enqueued by the native step (csrc/comm.cu)
+            parallel.init_comm(dist.group.WORLD)
+            b = pkg.SessionBatch.build(seqs, labels, kind, c['K']).to(dev)
+            m.shard_catalog(dist.group.WORLD)
+            m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+            losses = [float(m.train_step(b)) for _ in range(4)]
+            ret[rank] = dict(losses=losses, params={n_: p.detach().cpu() for n_, p in m.named_parameters()})
         else:
             b = pkg.SessionBatch.build(seqs, labels, kind, c['K']).to(dev)
             m.shard_catalog(dist.group.WORLD)
@@ -63,7 +81,12 @@ def _run(mode, world=2):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(300)
+        p.join(180)
+    hung = [p for p in procs if p.is_alive()]
+    for p in hung:                       # a rank stuck in a collective must not outlive the test
+        p.kill()
+    assert not hung, f'{len(hung)} rank(s) still running after 180 s (killed)'
+    for p in procs:
         assert p.exitcode == 0
     return dict(ret)
 
@@ -84,17 +107,43 @@ def test_catalog_sharded_head_matches_single_gpu(pkg, mode):
 
 
 @needs2
-def test_data_parallel_step_matches_full_batch_step(pkg):
-    """Two ranks with half the batch each + one all-reduce == one rank with the full batch (batch halves are equal)."""
+@pytest.mark.parametrize('mode', ['dp', 'dp_native', 'dp_uneven', 'dp_uneven_native', 'dp_empty'])
+def test_data_parallel_step_matches_full_batch_step(pkg, mode):
+    """Two ranks with a shard of the batch each + one all-reduce == one rank with the full batch: equal halves, uneven
+    shards (the gradients are weighted by B_local / B_global), an empty shard; through torch.distributed between two C calls
+    and (native) with the all-reduce enqueued by the step itself, graph replay included."""
     from tests.test_gpu_models import make_batch, make_model
     from tests.util import assert_close, golden
-    out = _run('dp')
+    out = _run(mode)
     c = golden('models_golden.pt')['msgifsr_k1']
     m = make_model(pkg, c)
     m.train()
     m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
     b, _ = make_batch(pkg, c)
-    m.train_step(b)
+    for _ in range(4 if 'native' in mode else 1):
+        m.train_step(b)
     for n, p in m.named_parameters():
-        assert_close(f'dp.{n}', out[0][n], p, rtol=1e-4, floor=0.5)
+        assert_close(f'{mode}.{n}', out[0][n], p, rtol=1e-4, floor=0.5)
         assert torch.equal(out[0][n], out[1][n]), f'replicas diverged on {n}'
+
+
+@needs2
+def test_catalog_sharded_native_step_matches_single_gpu(pkg):
+    """MSGIFSR training steps with the catalog rows sharded over two ranks - [2, B] soft-max statistics and dS all-reduced,
+    rank-local Adam on the owned rows, owners broadcast their updated rows - against the same steps on one GPU."""
+    from tests.test_gpu_models import make_batch, make_model
+    from tests.util import assert_close, golden
+    out = _run('shard_step')
+    c = golden('models_golden.pt')['msgifsr_k1']
+    m = make_model(pkg, c)
+    m.train()
+    m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+    b, _ = make_batch(pkg, c)
+    losses = [float(m.train_step(b)) for _ in range(4)]
+    for r in (0, 1):
+        for a, b_ in zip(out[r]['losses'], losses):
+            assert abs(a - b_) <= 1e-5 * abs(b_), (r, out[r]['losses'], losses)
+        for n, p in m.named_parameters():
+            assert_close(f'shard_step.rank{r}.{n}', out[r]['params'][n], p, rtol=1e-4, floor=0.5)
+    for n in out[0]['params']:
+        assert torch.equal(out[0]['params'][n], out[1]['params'][n]), f'replicas diverged on {n}'

@@ -54,7 +54,10 @@ def _errmap(name, got, ref, row_blk, col_blk=32):
 
 
 CASES = [(128, 128, 64, 12.0, True), (16, 200, 32, 12.0, True), (100, 1000, 64, 12.0, True), (300, 5000, 128, 12.0, True),
-         (512, 43097, 96, 12.0, True), (2048, 3000, 16, 1.0, False), (130, 129, 112, 1.0, False), (640, 17000, 128, 12.0, True)]
+         (512, 43097, 96, 12.0, True), (2048, 3000, 16, 1.0, False), (130, 129, 112, 1.0, False), (640, 17000, 128, 12.0, True),
+         # d = 256: the wide kernels (catalog tile streamed in K chunks, 64-row backward tiles, dE produced transposed)
+         (128, 128, 256, 12.0, True), (100, 1000, 256, 12.0, True), (130, 129, 256, 1.0, False), (300, 5000, 256, 12.0, True),
+         (512, 3703, 256, 12.0, True), (2048, 17000, 256, 1.0, False)]
 
 
 @pytest.mark.parametrize('B,V,d,scale,normed', CASES)

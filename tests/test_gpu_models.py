@@ -304,6 +304,33 @@ def test_native_srgnn_step_matches_staged_composition(pkg, name, p, head):
         assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)
 
 
+@pytest.mark.parametrize('d', [256, 128])
+def test_native_msgifsr_step_wide_embedding(pkg, d):
+    """BASELINE configs[4] embedding width (d = 256: scores materialised on the 3xTF32 GEMM, GAT projections on the
+    CUDA-core kernel) and d = 128 (largest width of the fused head): native step == staged composition, dropout included."""
+    from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+    from sessionrec_pytorch_b200.synthetic import SessionSampler
+    V, B = 2500, 384
+    res = []
+    for native in (True, False):
+        torch.manual_seed(4)
+        m = MSGIFSR(V, 'x', d, 1, dropout=0.2, order=1, extra=False, fusion=False).to(DEV).train()
+        m.native_step = native
+        m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+        smp = SessionSampler(V, seed=12)
+        losses = []
+        for it in range(3):
+            seqs, labels = smp.sessions(B)
+            m.set_dropout_seed(41 + it)
+            losses.append(float(m.train_step(pkg.SessionBatch.build(seqs, labels, 'ccs', 1).to(DEV))))
+        res.append((m, losses))
+    (m1, l1), (m2, l2) = res
+    for a, b_ in zip(l1, l2):
+        assert abs(a - b_) <= 5e-6 * abs(b_), (l1, l2)
+    for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)
+
+
 @pytest.mark.parametrize('model,d,L', [('SRGNN', 256, 1), ('NISER', 64, 2), ('SRGNN', 96, 2)])
 def test_native_srgnn_step_with_tensor_core_projections(pkg, model, d, L):
     """Shapes where the read-out / GGNN projections of the native step go to the tcgen05 GEMM (srk_tc_gemm) and, for d = 256,
