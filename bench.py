@@ -408,8 +408,8 @@ def reference_arm(args, cfg, rank, guard):
 
 
 def workload_name(key, cfg):
-    idx = int(key[3:])
-    return (f"BASELINE.json configs[{idx}]: {cfg['model']} order {cfg['order']}, {cfg['layers']} layer(s), {cfg['note']} "
+    head = f"BASELINE.json configs[{int(key[3:])}]" if key[3:].isdigit() else f"{key} (not a BASELINE config)"
+    return (f"{head}: {cfg['model']} order {cfg['order']}, {cfg['layers']} layer(s), {cfg['note']} "
             f"V={cfg['V']} d={cfg['d']} B={cfg['B']}")
 
 
@@ -597,7 +597,9 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
     if world > 1:
         dist.barrier()
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        nst = max(3, min(120, int(12.0 * 5000 / cfg['B'])))          # ~10-20 s of CPU work at ~5 k sessions/s
+        # bounded sample: ~10 s of CPU work, sized from the reference's indicative step times
+        guess_s = {'cfg1': 0.16, 'cfg2': 0.13, 'cfg3': 0.03, 'cfg4': 0.35, 'cfg1k3': 0.8}.get(key, 0.2)
+        nst = max(3, min(120, int(10.0 / guess_s)))
         out['cpu_baseline'] = cpu_arm(cfg, key, nst, 1)
     return out
 
@@ -615,6 +617,7 @@ def main():
                     help='N > 1: dp = data parallel, weak scaling (default); shard = item-catalog rows sharded across the ranks, '
                          'strong scaling on BASELINE configs[4]')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--secondary', action='store_true', help='internal: this process measures one workload of the `workloads` block')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gather-probe', action='store_true')
     args = ap.parse_args()
@@ -647,17 +650,23 @@ def main():
     pk = peaks()
     also = args.also
     if also is None:
-        also = 'cfg2' if (world == 1 and args.workload == 'cfg1') else ''
-    out = measure(args.workload, cfg, args, pkg, device, group, world, rank, pk, True)
+        also = 'cfg2,cfg4,cfg1k3' if (world == 1 and args.workload == 'cfg1') else ''
+    out = measure(args.workload, cfg, args, pkg, device, group, world, rank, pk, not args.secondary)
     extra = {}
     for key in [k for k in also.split(',') if k and k != args.workload]:
-        try:
+        if world > 1:
             extra[key] = measure(key, dict(CONFIGS[key]), args, pkg, device, group, world, rank, pk, False)
-        except Exception as e:                                  # noqa: BLE001 - a secondary workload never costs the headline
-            if world > 1:
-                raise                                             # a rank that stops would leave the others in a collective
+            continue
+        # single GPU: every further workload runs in its own process (a fresh allocator, no host threads left over from the
+        # CPU arm of the previous workload, and a failure there never costs the headline line)
+        cmd = [sys.executable, str(ROOT / 'bench.py'), '--workload', key, '--also', '', '--secondary', '--steps', str(args.steps),
+               '--warmup', str(args.warmup), '--no-gather-probe'] + (['--no-cpu-baseline'] if args.no_cpu_baseline else [])
+        try:
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+            lines = [ln for ln in p.stdout.splitlines() if ln.strip().startswith('{')]
+            extra[key] = json.loads(lines[-1]) if (p.returncode == 0 and lines) else dict(error=f'exit {p.returncode}: {p.stderr[-300:]}')
+        except Exception as e:                                  # noqa: BLE001
             extra[key] = dict(error=f'{type(e).__name__}: {e}')
-            torch.cuda.synchronize()
     if rank == 0:
         if extra:
             out['headline_workload'] = args.workload

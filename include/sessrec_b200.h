@@ -131,6 +131,14 @@ int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const
                           int P, int d, int norm_mode, const srk_dropout* drop, const float* rnorm, const float* dX,
                           const float* dX_first, float* dE, void* stream);
 
+/* The same with a workspace of srk_embed_scatter_ws_floats(P, d) floats: runs of one item that a chunk boundary cuts are
+ * written as partial sums and added up in chunk order by a second small launch - no atomics, bit-reproducible from run to
+ * run (ws == NULL: atomicAdd for the cut runs, as srk_embed_scatter_bwd). */
+long long srk_embed_scatter_ws_floats(int P, int d);
+int srk_embed_scatter_bwd_ws(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid, int U, int P,
+                             int d, int norm_mode, const srk_dropout* drop, const float* rnorm, const float* dX,
+                             const float* dX_first, float* dE, float* ws, void* stream);
+
 /* ---- catalog pre-pass (K6a) -------------------------------------------------------------------------
  * mode SRK_NORM_L2 (MSGIFSR): renormalise IN PLACE every row of E whose norm exceeds max_norm (> 0) by
  * max_norm / (norm + 1e-7) (`nn.Embedding(max_norm=1)`, msgifsr.py:162,276), then Ehat = F.normalize(E)

@@ -1,6 +1,8 @@
 // K1 / K8 / K6a: item-embedding gather (+dropout +row normalisation), deterministic scatter-add of the
 // embedding gradient, catalog pre-pass (max_norm renorm + row normalisation) and generic row normalisation.
 // All kernels are warp-per-row with 128-bit coalesced accesses (rowops.cuh); HBM/L2-bandwidth bound.
+#include <stdlib.h>
+
 #include "rowops.cuh"
 
 namespace {
@@ -37,6 +39,99 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_fwd_kernel(const float* __
   }
 }
 
+// The same gather with the table rows STAGED THROUGH SHARED MEMORY BY THE BULK-COPY ENGINE (TMA, `cp.async.bulk`): every warp
+// owns a two-deep ring of row groups; its lane 0 issues one bulk copy per row (d * 4 bytes, 16-byte aligned) of the NEXT
+// group while the warp normalises the current one out of shared memory.  The copies complete on an mbarrier
+// (expect_tx / complete_tx), so a warp keeps 2 x G rows in flight without holding a single register for them - what a
+// latency-bound gather of a few thousand L2-resident rows wants - and the normalised rows leave with coalesced 128-bit
+// stores.  G is sized on the host so that the CTA's rings fit GATHER_TMA_SMEM bytes.
+constexpr int GATHER_TMA_SMEM = 96 * 1024;
+
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "GWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra GDONE;\n\t"
+      "bra GWAIT_LOOP;\n\t"
+      "GDONE:\n\t"
+      "}" ::"r"(g_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void g_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(g_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(g_smem_u32(bar))
+               : "memory");
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) gather_tma_kernel(const float* __restrict__ E, const int* __restrict__ iid, int P,
+                                                                 int d, int mode, DropCfg dc, int G, float* __restrict__ X,
+                                                                 float* __restrict__ rnorm, float* __restrict__ x_first) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  __shared__ __align__(8) uint64_t bars[ROW_THREADS / 32][2];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)d * 4;
+  float* ring = reinterpret_cast<float*>(gsm) + (size_t)wib * 2 * G * d;        // this warp's two row groups
+  if (lane == 0) {
+    g_mbar_init(&bars[wib][0], 1);
+    g_mbar_init(&bars[wib][1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int ngroups = (P + G - 1) / G;
+  // issue the bulk copies of group g (rows g * G ...) into ring slot `slot`
+  auto issue = [&](int g, int slot) {             // called by the whole warp: lane k issues the copy of the group's k-th row
+    const int r0 = g * G, n = min(G, P - r0);
+    if (lane == 0) g_mbar_expect_tx(&bars[wib][slot], (uint32_t)n * row_bytes);
+    __syncwarp();
+    if (lane < n)
+      g_bulk_load(ring + ((size_t)slot * G + lane) * d, E + (long long)iid[r0 + lane] * d, row_bytes, &bars[wib][slot]);
+  };
+  int it = 0;
+  if (w0 < ngroups) issue(w0, 0);
+  for (int g = w0; g < ngroups; g += warps, ++it) {
+    const int slot = it & 1;
+    if (g + warps < ngroups) issue(g + warps, slot ^ 1);         // next group in flight while this one is processed
+    g_mbar_wait(&bars[wib][slot], (uint32_t)(it >> 1) & 1u);
+    const int r0 = g * G, n = min(G, P - r0);
+    for (int k = 0; k < n; ++k) {
+      const int i = r0 + k;
+      RowVec<NC> x, y;
+      row_load(x, ring + ((size_t)slot * G + k) * d, d, lane);
+      row_dropout(x, dc, i, d, lane);
+      float nn;
+      if (mode == SRK_NORM_NISER && x_first) {
+        nn = sqrtf(row_dot(x, x));
+        y = x;
+        row_scale(y, 1.f / (nn + 1e-12f));
+        row_store(y, x_first + (long long)i * d, d, lane);
+        float n1 = sqrtf(row_dot(y, y));
+        row_scale(y, 1.f / n1);
+      } else if (mode == SRK_NORM_NONE) {
+        nn = 0.f;
+        y = x;
+      } else {
+        nn = row_normalize(x, y, mode);
+      }
+      row_store(y, X + (long long)i * d, d, lane);
+      if (rnorm && lane == 0) rnorm[i] = nn;
+    }
+    __syncwarp();                                                 // every lane has read the slot before it is refilled
+  }
+}
+
 // Embedding-gradient scatter-add, load-balanced: the occurrence list is sorted by item id (perm / uoff / uid from the
 // batch builder); every warp takes SCATTER_CHUNK consecutive occurrences, so a hot item (Zipf head, ~10% of a batch)
 // is spread over many warps instead of serialising one.  Runs of one item that lie entirely inside a warp's chunk are
@@ -45,10 +140,17 @@ constexpr int SCATTER_CHUNK = 8;            // large tables / batches: long regi
 constexpr int SCATTER_CHUNK_SMALL = 2;      // a training batch (P ~ 2 k): the kernel is a latency chain, not a bandwidth
                                             // problem - 4x more warps with 4x shorter per-warp loops
 
+// where a finished run of one item goes: a run that lies entirely inside the warp's chunk is added to dE with a plain
+// read-modify-write (nobody else touches that row in this launch); a run cut by a chunk boundary is written as a PARTIAL
+// sum into the workspace (slot 0: the run began in an earlier chunk, slot 1: it began here and continues) and added up in
+// chunk order by scatter_fixup_kernel - deterministic, no atomics.  Without a workspace cut runs fall back to atomicAdd.
 template <int NC>
-__device__ __forceinline__ void scatter_flush(const RowVec<NC>& acc, float* __restrict__ row, int d, int lane, bool whole) {
+__device__ __forceinline__ void scatter_flush(const RowVec<NC>& acc, float* __restrict__ row, int d, int lane, bool whole,
+                                              float* __restrict__ ws_slot) {
   if (whole) {
     row_add_store(acc, row, d, lane);
+  } else if (ws_slot != nullptr) {
+    row_store(acc, ws_slot, d, lane);
   } else {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -68,10 +170,13 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
                                                                   const float* __restrict__ rnorm,
                                                                   const float* __restrict__ dX,
                                                                   const float* __restrict__ dX_first,
-                                                                  float* __restrict__ dE) {
+                                                                  float* __restrict__ dE, float* __restrict__ ws) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int nchunks = (P + chunk - 1) / chunk;
+  // the table row is only needed to rebuild the normalised output for the normalise-backward: a plain embedding (SRGNN)
+  // never reads E here, so the kernel moves exactly N (4 + 4d) + 2 U 4d bytes
+  const bool need_x = mode != SRK_NORM_NONE;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nchunks; w += warps) {
     const int j0 = w * chunk, j1 = min(P, j0 + chunk);
     int lo = 0, hi = U - 1;                    // distinct item u with uoff[u] <= j0 < uoff[u + 1]
@@ -80,23 +185,32 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
       if (uoff[mid] <= j0) lo = mid; else hi = mid - 1;
     }
     int u = lo;
-    RowVec<NC> erow, acc;
-    row_load(erow, E + (long long)uid[u] * d, d, lane);
+    float* wsw = ws ? ws + (long long)w * 2 * d : nullptr;
+    RowVec<NC> erow, acc, dy;
+    int i = perm[j0];
+    row_load(dy, dX + (long long)i * d, d, lane);               // software pipeline: the gradient row of occurrence j + 1 is
+    if (need_x) row_load(erow, E + (long long)uid[u] * d, d, lane);   // in flight while occurrence j is being processed
     row_zero(acc);
     for (int j = j0; j < j1; ++j) {
       while (j >= uoff[u + 1]) {
-        scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, uoff[u] >= j0);
+        const bool whole = uoff[u] >= j0;
+        scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, whole, wsw);       // a run that ends here can only be cut at its head
         ++u;
-        row_load(erow, E + (long long)uid[u] * d, d, lane);
+        if (need_x) row_load(erow, E + (long long)uid[u] * d, d, lane);
         row_zero(acc);
       }
-      const int i = perm[j];
-      RowVec<NC> x = erow, y, dy, dx;
-      row_dropout(x, dc, i, d, lane);
-      row_load(dy, dX + (long long)i * d, d, lane);
-      if (mode == SRK_NORM_NONE) {
+      RowVec<NC> dy_next;
+      int i_next = i;
+      if (j + 1 < j1) {
+        i_next = perm[j + 1];
+        row_load(dy_next, dX + (long long)i_next * d, d, lane);
+      }
+      RowVec<NC> dx;
+      if (!need_x) {
         dx = dy;
       } else {
+        RowVec<NC> x = erow, y;
+        row_dropout(x, dc, i, d, lane);
         const float n = rnorm[i];
         y = x;
         if (mode == SRK_NORM_L2) row_scale(y, 1.f / fmaxf(n, 1e-12f));
@@ -112,8 +226,41 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
       }
       row_dropout(dx, dc, i, d, lane);
       row_axpy(acc, 1.f, dx);
+      if (j + 1 < j1) dy = dy_next;
+      i = i_next;
     }
-    scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, uoff[u] >= j0 && uoff[u + 1] <= j1);
+    const bool head_cut = uoff[u] < j0, tail_cut = uoff[u + 1] > j1;
+    scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, !head_cut && !tail_cut, wsw ? wsw + (head_cut ? 0 : d) : nullptr);
+  }
+}
+
+// second pass of the deterministic scatter-add: the chunk in which a cut run BEGINS owns it and adds up the partial sums of
+// every chunk the run crosses, in chunk order, then adds the total to the item's gradient row
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS) scatter_fixup_kernel(const int* __restrict__ uoff, const int* __restrict__ uid, int U,
+                                                                    int P, int d, int chunk, const float* __restrict__ ws,
+                                                                    float* __restrict__ dE) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int nchunks = (P + chunk - 1) / chunk;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nchunks; w += warps) {
+    const int j0 = w * chunk, j1 = min(P, j0 + chunk);
+    if (j1 >= P) continue;                     // the last chunk cannot be cut at its tail
+    int lo = 0, hi = U - 1;                    // item of the chunk's last occurrence
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (uoff[mid] <= j1 - 1) lo = mid; else hi = mid - 1;
+    }
+    const int u = lo;
+    if (uoff[u] < j0 || uoff[u + 1] <= j1) continue;          // not cut at the tail, or owned by an earlier chunk
+    RowVec<NC> acc, t;
+    row_load(acc, ws + ((long long)w * 2 + 1) * d, d, lane);
+    const int end = uoff[u + 1];
+    for (int w2 = w + 1; w2 < nchunks && (long long)w2 * chunk < end; ++w2) {
+      row_load(t, ws + (long long)w2 * 2 * d, d, lane);
+      row_axpy(acc, 1.f, t);
+    }
+    row_add_store(acc, dE + (long long)uid[u] * d, d, lane);
   }
 }
 
@@ -276,22 +423,63 @@ extern "C" int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d
   if (P <= 0) return SRK_OK;
   SRK_REQUIRE(norm_mode == SRK_NORM_NONE || rnorm, "embed_gather_fwd: rnorm is required when normalising");
   DropCfg dc = make_drop(drop);
+  static int use_tma = -1;              // SESSREC_GATHER_TMA=0: plain warp-per-row loads
+  if (use_tma < 0) {
+    const char* e = getenv("SESSREC_GATHER_TMA");
+    use_tma = !(e && e[0] == '0');
+  }
+  if (use_tma && (reinterpret_cast<uintptr_t>(E) & 15u) == 0) {
+    // rows per group: the 8 warps' two-deep rings share GATHER_TMA_SMEM bytes (d = 96: 16 rows, d = 256: 6, d = 1024: 1)
+    int G = GATHER_TMA_SMEM / (8 * 2 * d * 4);
+    if (G > 16) G = 16;
+    if (G >= 1) {
+      const size_t smem = (size_t)8 * 2 * G * d * 4;
+      const int groups = (P + G - 1) / G;
+      int grid = (groups + 7) / 8;
+      if (grid > 148 * 2) grid = 148 * 2;
+      cudaError_t ae = cudaSuccess;       // > 48 KB of dynamic shared memory is an opt-in per kernel instantiation
+      SRK_DISPATCH_NC(d, (ae = cudaFuncSetAttribute(gather_tma_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_TMA_SMEM)));
+      SRK_CUDA(ae);
+      SRK_DISPATCH_NC(d, (srk_launch(gather_tma_kernel<NC>, grid, ROW_THREADS, smem, (cudaStream_t)stream, E, iid, P, d, norm_mode, dc, G, X, rnorm, x_first)));
+      SRK_LAUNCH_CHECK();
+      return SRK_OK;
+    }
+  }
   SRK_DISPATCH_NC(d, (srk_launch(gather_fwd_kernel<NC>, row_grid(P), ROW_THREADS, 0, (cudaStream_t)stream, E, iid, P, d, norm_mode, dc, X, rnorm, x_first)));
   SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+static inline int scatter_chunk(int P) { return P >= 65536 ? SCATTER_CHUNK : SCATTER_CHUNK_SMALL; }
+
+extern "C" long long srk_embed_scatter_ws_floats(int P, int d) {
+  if (P <= 0) return 0;
+  const int chunk = scatter_chunk(P);
+  return (long long)((P + chunk - 1) / chunk) * 2 * d;
+}
+
+extern "C" int srk_embed_scatter_bwd_ws(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid,
+                                        int U, int P, int d, int norm_mode, const srk_dropout* drop, const float* rnorm,
+                                        const float* dX, const float* dX_first, float* dE, float* ws, void* stream) {
+  (void)iid;
+  SRK_TRY(srk_check_dim(d));
+  if (U <= 0 || P <= 0) return SRK_OK;
+  DropCfg dc = make_drop(drop);
+  const int chunk = scatter_chunk(P);
+  const int nchunks = (P + chunk - 1) / chunk;
+  SRK_DISPATCH_NC(d, (srk_launch(scatter_bwd_kernel<NC>, row_grid(nchunks), ROW_THREADS, 0, (cudaStream_t)stream, E, perm, uoff, uid, U, P, d, norm_mode, chunk, dc, rnorm, dX, dX_first, dE, ws)));
+  SRK_LAUNCH_CHECK();
+  if (ws != nullptr && nchunks > 1) {
+    SRK_DISPATCH_NC(d, (srk_launch(scatter_fixup_kernel<NC>, row_grid(nchunks), ROW_THREADS, 0, (cudaStream_t)stream, uoff, uid, U, P, d, chunk, ws, dE)));
+    SRK_LAUNCH_CHECK();
+  }
   return SRK_OK;
 }
 
 extern "C" int srk_embed_scatter_bwd(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid,
                                      int U, int P, int d, int norm_mode, const srk_dropout* drop, const float* rnorm,
                                      const float* dX, const float* dX_first, float* dE, void* stream) {
-  (void)iid;
-  SRK_TRY(srk_check_dim(d));
-  if (U <= 0 || P <= 0) return SRK_OK;
-  DropCfg dc = make_drop(drop);
-  const int chunk = P >= 65536 ? SCATTER_CHUNK : SCATTER_CHUNK_SMALL;
-  SRK_DISPATCH_NC(d, (srk_launch(scatter_bwd_kernel<NC>, row_grid((P + chunk - 1) / chunk), ROW_THREADS, 0, (cudaStream_t)stream, E, perm, uoff, uid, U, P, d, norm_mode, chunk, dc, rnorm, dX, dX_first, dE)));
-  SRK_LAUNCH_CHECK();
-  return SRK_OK;
+  return srk_embed_scatter_bwd_ws(E, iid, perm, uoff, uid, U, P, d, norm_mode, drop, rnorm, dX, dX_first, dE, nullptr, stream);
 }
 
 extern "C" int srk_renorm_rows(float* E, const int* uid, int U, int d, float max_norm, void* stream) {

@@ -107,13 +107,23 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float* __restric
     }
     row_store(dv, v + (long long)b * d, d, lane);
   }
+  // d w_e: one set of atomics per CTA, not per warp.  With a warp per session B = 2048 warps would each fire d atomicAdds at
+  // the same d addresses (measured: 98 us of serialised L2 atomics at cfg2); the 8 warps of a CTA are summed in shared memory
+  // first and the grid is capped, so an address sees at most a few hundred adds.
+  __shared__ float red[8][NC * 128];
+  const int wib = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    int col = (c * 32 + lane) * 4;
-    if (col < d) {
-      atomicAdd(dwe + col, dwe_acc.v[c].x); atomicAdd(dwe + col + 1, dwe_acc.v[c].y);
-      atomicAdd(dwe + col + 2, dwe_acc.v[c].z); atomicAdd(dwe + col + 3, dwe_acc.v[c].w);
-    }
+    const int col = (c * 32 + lane) * 4;
+    red[wib][col] = dwe_acc.v[c].x; red[wib][col + 1] = dwe_acc.v[c].y;
+    red[wib][col + 2] = dwe_acc.v[c].z; red[wib][col + 3] = dwe_acc.v[c].w;
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < d; col += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][col];
+    atomicAdd(dwe + col, t);
   }
 }
 
@@ -453,7 +463,9 @@ extern "C" int srk_readout_bwd(const float* F, float* u, float* v, const float* 
                                int with_last, float* dF, float* dwe, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (B <= 0) return SRK_OK;
-  SRK_DISPATCH_NC(d, (srk_launch(readout_bwd_kernel<NC>, row_grid(B), 256, 0, (cudaStream_t)stream, F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe)));
+  int grid = row_grid(B);
+  if (grid > 2 * 148) grid = 2 * 148;          // sessions beyond that are taken by the grid-stride loop (fewer atomics on d w_e)
+  SRK_DISPATCH_NC(d, (srk_launch(readout_bwd_kernel<NC>, grid, 256, 0, (cudaStream_t)stream, F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

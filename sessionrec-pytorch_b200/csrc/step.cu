@@ -105,7 +105,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   fl += (long long)L * (2 * ((ldzel + H) * d + 2LL * N * d + N * ldzel + N * H + (long long)(M + 1) * H) + B * d + N * d + N + N * d / 4 + 64);
   fl += 2LL * N * d + 3LL * B * d + N + 2LL * B + 4LL * B * d + B;    // u, v, e, ms, sr_in, s, shat, rn_s
   fl += 2LL * B * ldz + 4LL * B * d + 2LL * B + 64 + 4LL * ((V + 255) / 256) * B + B;        // Z, Zlo, sh, sl, dshat, ds, lse, nll
-  fl += 2LL * B * d + (long long)N * d + 2LL * d * d;      // dsr_in, dF, W_sr^T
+  fl += 2LL * B * d + (long long)N * d + 2LL * d * d + (long long)(N + 4) * d;      // dsr_in, dF, W_sr^T, scatter partials
   // flash CE head: bf16 hi/lo of Ehat and shat, soft-max partials, one [V, d] dE partial per 128-session tile
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
@@ -591,8 +591,10 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   tm.mark("gat_bwd");
   // catalog backward done (not the early Adam part queued behind it): the scatter-add updates the same table rows
   if (ss && live) SRK_CUDA(cudaStreamWaitEvent(st, ss->ev_cat, 0));
-  SRK_TRY(srk_embed_scatter_bwd(E, b.iid, b.perm, b.uoff, b.uid, b.U, b.P, d, SRK_NORM_L2, drop ? &dc_e : nullptr, rnX, dH,
-                                nullptr, G(0), st));
+  float* sws = ar.f((size_t)srk_embed_scatter_ws_floats(b.P, d));    // cut runs are combined in chunk order: no atomics
+  SRK_REQUIRE(ar.ok, "step: workspace too small");
+  SRK_TRY(srk_embed_scatter_bwd_ws(E, b.iid, b.perm, b.uoff, b.uid, b.U, b.P, d, SRK_NORM_L2, drop ? &dc_e : nullptr, rnX, dH,
+                                   nullptr, G(0), sws, st));
   SRK_TRY(order(s2, st));
   SRK_TRY(order(s3, st));
   tm.mark("scatter");

@@ -90,7 +90,7 @@ extern "C" long long srk_srgnn_workspace_bytes(int B, int N, int M, int V, int d
   fl += 2LL * N * d + 6LL * B * d + N + 4LL * B;             // u, e, v, ms, sr_in, s, shat, rn_s
   fl += 2LL * B * ldz + 4LL * B * d + 2LL * B + 4LL * ((V + 255) / 256) * B + B + 64;      // Z, Zlo, sh, sl, lse, nll, partials
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;   // flash head
-  fl += 4LL * B * d + 3LL * N * d;                           // dshat, ds, dsr_in, dF, dX
+  fl += 4LL * B * d + 3LL * N * d + (long long)(N + 4) * d;  // dshat, ds, dsr_in, dF, dX, scatter partials
   fl += 3 * scratch_floats(B, N, d);                         // tensor-core operand splits: one region per stream
   return fl * 4 + fl + (1 << 20);                            // floats -> bytes with 25% head-room + alignment slack
 }
@@ -332,7 +332,10 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   }
   tm.mark("readout_bwd");
   if (ss && live) SRK_CUDA(cudaStreamWaitEvent(st, ss->ev_cat, 0));
-  SRK_TRY(srk_embed_scatter_bwd(E, b.iid, b.perm, b.uoff, b.uid, b.U, N, d, emb_mode, drop ? &dc_e : nullptr, rn, dX, nullptr, G(0), st));
+  float* sws = ar.f((size_t)srk_embed_scatter_ws_floats(N, d));      // cut runs are combined in chunk order: no atomics
+  SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
+  SRK_TRY(srk_embed_scatter_bwd_ws(E, b.iid, b.perm, b.uoff, b.uid, b.U, N, d, emb_mode, drop ? &dc_e : nullptr, rn, dX, nullptr, G(0),
+                                   sws, st));
   SRK_TRY(order(s2, st));
   tm.mark("scatter");
   if (phase == 3) {

@@ -31,8 +31,11 @@ using namespace umma;
 // Epilogue store of one 32 x 32 accumulator chunk (lane = row) with coalesced global accesses: the chunk is transposed
 // through a padded per-warp shared-memory tile so that every store instruction covers 4 rows x 128 contiguous bytes
 // (the naive lane-per-row store touches 32 different cache lines with 16 bytes each and is LSU-bound).
+// mode: 0 = store, 1 = atomicAdd (split-K: several CTAs add into one tile), 2 = C += tile with plain loads / stores (the CTA is
+// the only writer of its tile: accumulate without split-K)
 __device__ __forceinline__ void store_chunk(float* __restrict__ stile, const float* v, float* __restrict__ C, long long ldc,
-                                            int m_base, int M, int nvalid, int lane, bool atomic) {
+                                            int m_base, int M, int nvalid, int lane, int mode) {
+  const bool atomic = mode == 1;
 #pragma unroll
   for (int j = 0; j < 32; ++j) stile[lane * 33 + j] = v[j];
   __syncwarp();
@@ -50,7 +53,17 @@ __device__ __forceinline__ void store_chunk(float* __restrict__ stile, const flo
         if (c + 2 < nvalid) atomicAdd(dst + 2, x2);
         if (c + 3 < nvalid) atomicAdd(dst + 3, x3);
       } else if (c + 3 < nvalid && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-        *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+        float4 o = make_float4(x0, x1, x2, x3);
+        if (mode == 2) {
+          const float4 p = *reinterpret_cast<const float4*>(dst);
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *reinterpret_cast<float4*>(dst) = o;
+      } else if (mode == 2) {
+        dst[0] += x0;
+        if (c + 1 < nvalid) dst[1] += x1;
+        if (c + 2 < nvalid) dst[2] += x2;
+        if (c + 3 < nvalid) dst[3] += x3;
       } else {
         dst[0] = x0;
         if (c + 1 < nvalid) dst[1] = x1;
@@ -75,7 +88,7 @@ struct UmmaParams {
   float* C;
   long long ldc;
   float alpha;
-  int atomic;             // 1: atomicAdd epilogue (split-K / accumulate), 0: plain store
+  int atomic;             // epilogue: 0 plain store, 1 atomicAdd (split-K), 2 C += (accumulate, one CTA per tile)
   const float* bias;      // optional [N]: added once (by the first split-K slice)
   uint32_t idesc;
   uint32_t tmem_cols;
@@ -197,7 +210,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
             for (int j = 0; j < 32; ++j)
               if (j < nvalid) v[j] += p.bias[n0 + c0 + j];
           }
-          store_chunk(stile, v, p.C + n0 + c0, p.ldc, m0 + q * 32, p.M, nvalid, lane, p.atomic != 0);
+          store_chunk(stile, v, p.C + n0 + c0, p.ldc, m0 + q * 32, p.M, nvalid, lane, p.atomic);
         }
       }
     }
@@ -351,7 +364,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
           float v2[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v2[j] = p.alpha * __uint_as_float(r[j]);
-          store_chunk(stile, v2, p.Z + n0 + c0, p.ldz, mt * BM + q * 32, p.M, nvalid, lane, false);
+          store_chunk(stile, v2, p.Z + n0 + c0, p.ldz, mt * BM + q * 32, p.M, nvalid, lane, 0);
         }
       }
       // accumulator fully read: hand the TMEM buffer back to the MMA warp
@@ -546,7 +559,7 @@ int umma_gemm_impl(int form, int M, int N, int K, const float* Ahi, const float*
   p.kb_per_split = (nkb + S - 1) / S;
   S = (nkb + p.kb_per_split - 1) / p.kb_per_split;
   p.C = C; p.ldc = ldc; p.alpha = alpha;
-  p.atomic = accumulate ? 1 : 0;
+  p.atomic = accumulate ? (S > 1 ? 1 : 2) : 0;
   p.bias = bias;
   p.tmem_cols = p.BN <= 32 ? 32 : (p.BN <= 64 ? 64 : (p.BN <= 128 ? 128 : 256));
   // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4

@@ -174,9 +174,15 @@ def embed_gather_fwd(E, iid, P, d, mode, dc, X, rnorm, x_first=None):
     _call('srk_embed_gather_fwd', ptr(E), ptr(iid), P, d, mode, _dref(dc), ptr(X), ptr(rnorm), ptr(x_first))
 
 
-def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE):
-    _call('srk_embed_scatter_bwd', ptr(E), ptr(t['iid']), ptr(t['perm']), ptr(t['uoff']), ptr(t['uid']), t['U'], t['P'], d, mode,
-          _dref(dc), ptr(rnorm), ptr(dX), ptr(dX_first), ptr(dE))
+def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE, deterministic=True):
+    """dE[item] += gradient of every occurrence of the item.  deterministic: runs cut by a chunk boundary are combined in a
+    fixed order through a small workspace (no atomics); False keeps the one-launch variant with atomicAdd on those rows."""
+    ws = None
+    if deterministic:
+        n = int(_lib.lib().functions['srk_embed_scatter_ws_floats'](t['P'], d))
+        ws = torch.empty(max(n, 1), dtype=torch.float32, device=dE.device)
+    _call('srk_embed_scatter_bwd_ws', ptr(E), ptr(t['iid']), ptr(t['perm']), ptr(t['uoff']), ptr(t['uid']), t['U'], t['P'], d, mode,
+          _dref(dc), ptr(rnorm), ptr(dX), ptr(dX_first), ptr(dE), ptr(ws))
 
 
 def catalog_prep_fwd(E, mode, max_norm, Ehat, enorm, Ehi=None, Elo=None, Bhi=None, Blo=None):
