@@ -354,17 +354,22 @@ def gather_scatter_probe(device, pk, shapes=None):
                 ts.append(a.elapsed_time(b))
             return float(np.median(ts))
         ms_g = timeit(lambda: ops.embed_gather_fwd(E, t['iid'], N, d, 2, None, X, rn))
-        ms_s = timeit(lambda: ops.embed_scatter_bwd(E, t, d, 2, None, rn, X, None, dE))
+        ws = torch.empty(max(1, ops.embed_scatter_ws_floats(N, d)), device=device)
+        ms_s = timeit(lambda: ops.embed_scatter_bwd(E, t, d, 2, None, rn, X, None, dE, ws=ws))
+        ms_p = timeit(lambda: ops.embed_scatter_bwd(E, t, d, 0, None, None, X, None, dE, ws=ws))
         bg = N * (4 + 2 * 4 * d)
-        bs = N * (4 + 4 * d) + 2 * t['U'] * 4 * d
+        bp = N * (4 + 4 * d) + 2 * t['U'] * 4 * d           # plain scatter-add (SRGNN): BASELINE.md section 4
+        bs = bp + t['U'] * 4 * d                             # + one table row per distinct item for the normalise-backward
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
         # stress shape (profiles/*_ncu_full_gather_scatter.json); the L2-resident shape has no capture
         caps = sorted((ROOT / 'profiles').glob('*_ncu_full_gather_scatter.json'))
         cap = json.loads(caps[-1].read_text()) if caps and name.startswith('stress') else []
-        for kname, ms, by in (('gather_fwd_kernel (K1: gather + L2 normalise)', ms_g, bg),
-                              ('scatter_bwd_kernel (K8: normalise-backward + scatter-add)', ms_s, bs)):
+        for kname, ms, by in (('gather_tma_kernel (K1: TMA bulk-staged gather + L2 normalise)', ms_g, bg),
+                              ('scatter_bwd_kernel (K8: normalise-backward + deterministic scatter-add; reads one table row per distinct item)', ms_s, bs),
+                              ('scatter_bwd_kernel (K8 plain: deterministic scatter-add, SRGNN)', ms_p, bp)):
             ach = by / (ms * 1e-3) / 1e9
-            tr = [round(r['dram_bytes_read'] + r['dram_bytes_write']) for r in cap if kname.split(' ')[0][:-7] in r['kernel']]
+            tr = [round(r['dram_bytes_read'] + r['dram_bytes_write']) for r in cap
+                  if kname.split(' ')[0][:-7] in r['kernel'] and 'plain' not in kname]
             out.append(dict(bound='hbm', kernel=kname, shape=name, achieved=round(ach, 1), peak=pk['hbm'], unit='GB/s',
                             frac=round(ach / pk['hbm'], 4), ms=round(ms, 4), algorithmic_bytes=by,
                             traffic=tr[0] if tr else None, traffic_source=f'profiles/{caps[-1].name}' if tr else None))
@@ -517,6 +522,8 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
             clk['continuation_error'] = f'{type(e).__name__}: {e}'
 
     # ---- end-to-end through the public API with host buffers -----------------------------------------------------
+    for i in range(min(3, args.warmup)):                 # untimed warm-up of THIS path: first pinned H2D, first D2H read of the loss
+        model.train_step(host[i % n_batches].to(device, non_blocking=True), step_group, gb).item()
     barrier()
     t0 = time.perf_counter()
     h2d = 0

@@ -103,6 +103,14 @@ long long srk_flash_ce_part_floats(int B, int V);
 int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
                      const uint16_t* Elo, long long lde, float scale, const int* labels, float* lse, float* nll, float* part,
                      void* stream);
+/* Fused evaluation head (evaluate(), utils/train.py:36-55): ids (best first; ties: smaller id first) and optionally values of
+ * the K <= 32 largest logits of every row, kept by the soft-max threads of the scoring kernel while the tiles go by and merged
+ * per row by a second small launch - `logits.topk(k=cutoff)` (train.py:49) without the (B, V) matrix.  scratch:
+ * srk_flash_ce_topk_scratch_floats floats. */
+long long srk_flash_ce_topk_scratch_floats(int B, int V, int K);
+int srk_flash_ce_topk(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                      const uint16_t* Elo, long long lde, float scale, int K, int* out_idx, float* out_val, float* scratch,
+                      void* stream);
 /* number of [V, d] partial buffers srk_flash_ce_bwd writes (= ceil(B / 128)) */
 int srk_flash_ce_bwd_parts(int B);
 /* Backward of the mean loss: recomputes every 128 x 128 logit tile, dZ = gout[0] * scale * (softmax - onehot) / B

@@ -93,6 +93,11 @@ class SessRecModule(nn.Module):
         """Ids [B, k] (int64, best first) of the k highest-scoring items per session: the `logits.topk(k)[1]` of the
         reference's evaluate() (`utils/train.py:49`) without materialising (B, V) log-probabilities."""
         self._ensure_flat()
+        if k <= 32 and self._shard is None and self._use_flash(self.embedding_dim, 'topk'):
+            # fused: the scoring kernel's soft-max threads keep the k best logits of their rows while the tiles go by
+            self._topk_k = int(k)
+            idx, _ = self._fwd(mg, 'topk', need_grad=False)
+            return idx.long()
         Zv, _ = self._fwd(mg, 'logits', need_grad=False)
         B, V = Zv.shape
         idx = torch.empty(B, k, dtype=torch.int32, device=Zv.device)
@@ -118,7 +123,7 @@ class SessRecModule(nn.Module):
         return True
 
     def _use_flash(self, d, mode):
-        return (self.use_tensor_cores and self.flash_ce and mode == 'loss' and self._single_head()
+        return (self.use_tensor_cores and self.flash_ce and mode in ('loss', 'topk') and self._single_head()
                 and ops.flash_ce_supported(d))
 
     def _catalog_fwd(self, E, norm_mode, max_norm, tape):
@@ -165,6 +170,10 @@ class SessRecModule(nn.Module):
             Shi = torch.empty(B, d, dtype=torch.int16, device=dev)
             Slo = torch.empty(B, d, dtype=torch.int16, device=dev)
             ops.split_bf16(shat, ld_s, B, d, Shi, Slo, d)
+            if mode == 'topk':
+                idx = torch.empty(B, self._topk_k, dtype=torch.int32, device=dev)
+                ops.flash_ce_topk(B, V, d, Shi, Slo, d, cat['Bhi'], cat['Blo'], d, scale, self._topk_k, idx)
+                return idx
             lse = torch.empty(B, dtype=torch.float32, device=dev)
             nll = torch.empty(B, dtype=torch.float32, device=dev)
             part = torch.empty(ops.flash_ce_part_floats(B, V), dtype=torch.float32, device=dev)

@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
                                                                   const float* __restrict__ rnorm,
                                                                   const float* __restrict__ dX,
                                                                   const float* __restrict__ dX_first,
-                                                                  float* __restrict__ dE, float* __restrict__ ws) {
+                                                                  float* __restrict__ dE, float* __restrict__ ws,
+                                                                  int* __restrict__ owner) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int nchunks = (P + chunk - 1) / chunk;
@@ -190,14 +191,18 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
     int i = perm[j0];
     row_load(dy, dX + (long long)i * d, d, lane);               // software pipeline: the gradient row of occurrence j + 1 is
     if (need_x) row_load(erow, E + (long long)uid[u] * d, d, lane);   // in flight while occurrence j is being processed
-    row_zero(acc);
+    // A run that lies entirely inside this chunk starts from the CURRENT gradient row (loaded here, beside the other loads)
+    // and ends with a plain store: no dependent read-modify-write at the end of the run.  Cut runs start from zero.
+    bool whole = uoff[u] >= j0 && uoff[u + 1] <= j1;
+    if (whole) row_load(acc, dE + (long long)uid[u] * d, d, lane); else row_zero(acc);
     for (int j = j0; j < j1; ++j) {
       while (j >= uoff[u + 1]) {
-        const bool whole = uoff[u] >= j0;
-        scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, whole, wsw);       // a run that ends here can only be cut at its head
+        if (whole) row_store(acc, dE + (long long)uid[u] * d, d, lane);
+        else scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, false, wsw);     // a run that ends here was cut at its head
         ++u;
         if (need_x) row_load(erow, E + (long long)uid[u] * d, d, lane);
-        row_zero(acc);
+        whole = uoff[u + 1] <= j1;                                // it begins inside the chunk
+        if (whole) row_load(acc, dE + (long long)uid[u] * d, d, lane); else row_zero(acc);
       }
       RowVec<NC> dy_next;
       int i_next = i;
@@ -230,7 +235,10 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
       i = i_next;
     }
     const bool head_cut = uoff[u] < j0, tail_cut = uoff[u + 1] > j1;
-    scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, !head_cut && !tail_cut, wsw ? wsw + (head_cut ? 0 : d) : nullptr);
+    if (whole) row_store(acc, dE + (long long)uid[u] * d, d, lane);
+    else scatter_flush(acc, dE + (long long)uid[u] * d, d, lane, false, wsw ? wsw + (head_cut ? 0 : d) : nullptr);
+    // the chunk in which a cut run BEGINS owns it: the second pass starts from this record instead of searching
+    if (owner && lane == 0) owner[w] = (!head_cut && tail_cut) ? u : -1;
   }
 }
 
@@ -239,20 +247,13 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
 template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) scatter_fixup_kernel(const int* __restrict__ uoff, const int* __restrict__ uid, int U,
                                                                     int P, int d, int chunk, const float* __restrict__ ws,
-                                                                    float* __restrict__ dE) {
+                                                                    const int* __restrict__ owner, float* __restrict__ dE) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int nchunks = (P + chunk - 1) / chunk;
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nchunks; w += warps) {
-    const int j0 = w * chunk, j1 = min(P, j0 + chunk);
-    if (j1 >= P) continue;                     // the last chunk cannot be cut at its tail
-    int lo = 0, hi = U - 1;                    // item of the chunk's last occurrence
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (uoff[mid] <= j1 - 1) lo = mid; else hi = mid - 1;
-    }
-    const int u = lo;
-    if (uoff[u] < j0 || uoff[u + 1] <= j1) continue;          // not cut at the tail, or owned by an earlier chunk
+    const int u = owner[w];                    // item whose run begins in chunk w and continues beyond it, or -1
+    if (u < 0) continue;
     RowVec<NC> acc, t;
     row_load(acc, ws + ((long long)w * 2 + 1) * d, d, lane);
     const int end = uoff[u + 1];
@@ -428,18 +429,29 @@ extern "C" int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d
     const char* e = getenv("SESSREC_GATHER_TMA");
     use_tma = !(e && e[0] == '0');
   }
-  if (use_tma && (reinterpret_cast<uintptr_t>(E) & 15u) == 0) {
-    // rows per group: the 8 warps' two-deep rings share GATHER_TMA_SMEM bytes (d = 96: 16 rows, d = 256: 6, d = 1024: 1)
+  // Staging pays where the gather is a latency problem (a training batch: a few thousand L2-resident rows; measured 24.6 ->
+  // 10.2 us at the cfg2 shape); a gather that streams a table far larger than L2 is already at 98.6 % of the copy peak with
+  // plain 128-bit loads and loses ~12 % to the shared-memory round trip, so it keeps the plain kernel.
+  if (use_tma && P < (1 << 18) && (reinterpret_cast<uintptr_t>(E) & 15u) == 0) {
+    // rows per group: the 8 warps' two-deep rings share GATHER_TMA_SMEM bytes (d = 96: 16 rows, d = 256: 6, d = 1024: 1),
+    // but never so many that fewer than ~2 warps per SM scheduler are left with work
     int G = GATHER_TMA_SMEM / (8 * 2 * d * 4);
     if (G > 16) G = 16;
+    const int gpar = P / (148 * 8 * 2);
+    if (G > gpar) G = gpar < 1 ? 1 : gpar;
     if (G >= 1) {
       const size_t smem = (size_t)8 * 2 * G * d * 4;
       const int groups = (P + G - 1) / G;
       int grid = (groups + 7) / 8;
       if (grid > 148 * 2) grid = 148 * 2;
-      cudaError_t ae = cudaSuccess;       // > 48 KB of dynamic shared memory is an opt-in per kernel instantiation
-      SRK_DISPATCH_NC(d, (ae = cudaFuncSetAttribute(gather_tma_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_TMA_SMEM)));
-      SRK_CUDA(ae);
+      static bool attr_set[9] = {false};  // > 48 KB of dynamic shared memory is an opt-in per kernel instantiation
+      const int nci = (d + 127) / 128;
+      if (!attr_set[nci]) {
+        cudaError_t ae = cudaSuccess;
+        SRK_DISPATCH_NC(d, (ae = cudaFuncSetAttribute(gather_tma_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GATHER_TMA_SMEM)));
+        SRK_CUDA(ae);
+        attr_set[nci] = true;
+      }
       SRK_DISPATCH_NC(d, (srk_launch(gather_tma_kernel<NC>, grid, ROW_THREADS, smem, (cudaStream_t)stream, E, iid, P, d, norm_mode, dc, G, X, rnorm, x_first)));
       SRK_LAUNCH_CHECK();
       return SRK_OK;
@@ -455,7 +467,8 @@ static inline int scatter_chunk(int P) { return P >= 65536 ? SCATTER_CHUNK : SCA
 extern "C" long long srk_embed_scatter_ws_floats(int P, int d) {
   if (P <= 0) return 0;
   const int chunk = scatter_chunk(P);
-  return (long long)((P + chunk - 1) / chunk) * 2 * d;
+  const long long nchunks = (P + chunk - 1) / chunk;
+  return nchunks * 2 * d + (nchunks + 3) / 4 * 4;          // two partial rows per chunk + one owner record per chunk
 }
 
 extern "C" int srk_embed_scatter_bwd_ws(const float* E, const int* iid, const int* perm, const int* uoff, const int* uid,
@@ -467,10 +480,11 @@ extern "C" int srk_embed_scatter_bwd_ws(const float* E, const int* iid, const in
   DropCfg dc = make_drop(drop);
   const int chunk = scatter_chunk(P);
   const int nchunks = (P + chunk - 1) / chunk;
-  SRK_DISPATCH_NC(d, (srk_launch(scatter_bwd_kernel<NC>, row_grid(nchunks), ROW_THREADS, 0, (cudaStream_t)stream, E, perm, uoff, uid, U, P, d, norm_mode, chunk, dc, rnorm, dX, dX_first, dE, ws)));
+  int* owner = ws ? reinterpret_cast<int*>(ws + (long long)nchunks * 2 * d) : nullptr;
+  SRK_DISPATCH_NC(d, (srk_launch(scatter_bwd_kernel<NC>, row_grid(nchunks), ROW_THREADS, 0, (cudaStream_t)stream, E, perm, uoff, uid, U, P, d, norm_mode, chunk, dc, rnorm, dX, dX_first, dE, ws, owner)));
   SRK_LAUNCH_CHECK();
   if (ws != nullptr && nchunks > 1) {
-    SRK_DISPATCH_NC(d, (srk_launch(scatter_fixup_kernel<NC>, row_grid(nchunks), ROW_THREADS, 0, (cudaStream_t)stream, uoff, uid, U, P, d, chunk, ws, dE)));
+    SRK_DISPATCH_NC(d, (srk_launch(scatter_fixup_kernel<NC>, row_grid(nchunks), ROW_THREADS, 0, (cudaStream_t)stream, uoff, uid, U, P, d, chunk, ws, owner, dE)));
     SRK_LAUNCH_CHECK();
   }
   return SRK_OK;

@@ -78,6 +78,9 @@ struct FceParams {
   const uint16_t *Shi, *Slo;   // fwd, a_tmem: bf16 hi / lo of shat in global memory, row pitch lds
   long long lds;
   long long* trace;        // debug: clock64 stamps of CTA 0, [role 0..10][tile < 64][8] (srk_flash_ce_set_trace), else null
+  int topk;                // fwd: 0, or K <= TOPK_MAX: write the K largest logits of every (range, half, row) to cand_*
+  float* cand_val;         // [2 * nvr][B][K]
+  int* cand_idx;
 };
 
 // role: 0 = TMA producer, 1 = MMA issuer, 2 + w = epilogue warp w (lane 0)
@@ -150,6 +153,39 @@ __device__ __noinline__ float pick_column(uint32_t taddr, int j) {
   return x;
 }
 
+// Fused evaluation head (evaluate(), utils/train.py:36-55: `logits.topk(k=20)`): every soft-max thread keeps the K largest
+// logits of its (row, column half) over the CTA's catalog range in a small sorted list - one compare per logit against the
+// current K-th value, an insertion is rare once the list has warmed up - and writes the list out; fce_topk_merge_kernel
+// merges the 2 * nvr lists of a row.  The (B, V) score matrix never exists, in HBM or anywhere else.
+constexpr int TOPK_MAX = 32;
+struct TopK {
+  float v[TOPK_MAX];
+  int i[TOPK_MAX];
+  float vmin;
+  int n;
+  __device__ __forceinline__ void init() { n = 0; vmin = -3.0e38f; }
+  __device__ __noinline__ void insert(float a, int col, int K) {
+    int p = n < K ? n : K - 1;
+    while (p > 0 && v[p - 1] < a) {            // strict: among equal values the smaller column (seen first) stays ahead
+      v[p] = v[p - 1];
+      i[p] = i[p - 1];
+      --p;
+    }
+    v[p] = a;
+    i[p] = col;
+    if (n < K) ++n;
+    vmin = n == K ? v[K - 1] : -3.0e38f;
+  }
+  // 32 accumulator columns starting at catalog column col0, the first nvalid of them inside the catalog
+  __device__ __forceinline__ void scan(const uint32_t* r, int nvalid, int col0, int K) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = __uint_as_float(r[j]);
+      if (j < nvalid && a > vmin) insert(a, col0 + j, K);
+    }
+  }
+};
+
 struct TileSched {
   int tb, t0, t1;
   __device__ TileSched(const FceParams& p) {
@@ -169,6 +205,7 @@ __device__ __forceinline__ void load_operand(uint8_t* dst, const CUtensorMap* hi
 }
 
 // ---- forward: per-row (max, sum exp) partials + label logit, nothing else leaves the SM ---------------------------------
+template <bool TOPK>
 __global__ void __launch_bounds__(THREADS, 1)
 fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
                const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl, const FceParams p) {
@@ -246,7 +283,7 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
     // Per element: FMNMX, FFMA, MUFU.EX2, FADD.
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int b = ts.tb * TB + q * 32 + lane;
-    const int lab = b < p.B ? p.labels[b] : -1;
+    const int lab = (b < p.B && p.labels != nullptr) ? p.labels[b] : -1;
     const float c2 = p.scale * LOG2E;
     const uint32_t lanebits = (uint32_t)(q * 32) << 16;
     if (ats) {
@@ -269,6 +306,8 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
     }
     float m2 = -3.0e38f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, zl = 0.f;
     bool has = false;
+    TopK tk;
+    if (TOPK) tk.init();
     int it = 0;
     for (int t = ts.t0; t < ts.t1; ++t, ++it) {
       const int zb = it & 1;
@@ -320,6 +359,7 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
           for (int j = 0; j < 32; ++j)
             if (j < nvalid) s0 += ex2f(fmaf(__uint_as_float(r[j]), c2, -m2));
         }
+        if (TOPK && nvalid > 0) tk.scan(r, nvalid, v0, p.topk);
         const bool mine = lab >= v0 && lab < v0 + nvalid;
         if (__any_sync(SRK_FULL, mine)) {          // tcgen05.ld is warp-collective: every lane re-reads, owners keep
           const float x = p.scale * pick_column(taddr, lab - v0);
@@ -340,6 +380,14 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       pp[0] = m2 * LN2;                          // natural-log units: max logit, sum exp(logit - max)
       pp[1] = (s0 + s1) + (s2 + s3);
       if (has) p.zlab[b] = zl;
+      if (TOPK) {
+        float* cv = p.cand_val + ((long long)(vr * 2 + half) * p.B + b) * p.topk;
+        int* ci = p.cand_idx + ((long long)(vr * 2 + half) * p.B + b) * p.topk;
+        for (int k = 0; k < p.topk; ++k) {
+          cv[k] = k < tk.n ? tk.v[k] : -3.0e38f;
+          ci[k] = k < tk.n ? tk.i[k] : 0x7fffffff;
+        }
+      }
     }
   }
   fence_tc_before();
@@ -712,6 +760,9 @@ struct FceWide {
   const uint16_t *Shi, *Slo;   // fwd: bf16 hi / lo of shat in global memory, row pitch lds (staged into TMEM)
   long long lds;
   uint32_t idesc_z, idesc_ds, idesc_de;
+  int topk;                // fwd: see FceParams
+  float* cand_val;
+  int* cand_idx;
 };
 
 struct WideSched {
@@ -724,6 +775,7 @@ struct WideSched {
   }
 };
 
+template <bool TOPK>
 __global__ void __launch_bounds__(THREADS, 1)
 fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl, const FceWide p) {
   extern __shared__ uint8_t smem_raw[];
@@ -802,7 +854,7 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
     // soft-max math: identical to fce_fwd_kernel (per-row online max / sum exp in base 2, label logit)
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int b = ts.tb * TB + q * 32 + lane;
-    const int lab = b < p.B ? p.labels[b] : -1;
+    const int lab = (b < p.B && p.labels != nullptr) ? p.labels[b] : -1;
     const float c2 = p.scale * LOG2E;
     const uint32_t lanebits = (uint32_t)(q * 32) << 16;
     {
@@ -824,6 +876,8 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
     }
     float m2 = -3.0e38f, s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, zl = 0.f;
     bool has = false;
+    TopK tk;
+    if (TOPK) tk.init();
     int it = 0;
     for (int t = ts.t0; t < ts.t1; ++t, ++it) {
       const int zb = it & 1;
@@ -874,6 +928,7 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
           for (int j = 0; j < 32; ++j)
             if (j < nvalid) s0 += ex2f(fmaf(__uint_as_float(r[j]), c2, -m2));
         }
+        if (TOPK && nvalid > 0) tk.scan(r, nvalid, v0, p.topk);
         const bool mine = lab >= v0 && lab < v0 + nvalid;
         if (__any_sync(SRK_FULL, mine)) {
           const float x = p.scale * pick_column(taddr, lab - v0);
@@ -893,6 +948,14 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
       pp[0] = m2 * LN2;
       pp[1] = (s0 + s1) + (s2 + s3);
       if (has) p.zlab[b] = zl;
+      if (TOPK) {
+        float* cv = p.cand_val + ((long long)(vr * 2 + half) * p.B + b) * p.topk;
+        int* ci = p.cand_idx + ((long long)(vr * 2 + half) * p.B + b) * p.topk;
+        for (int k = 0; k < p.topk; ++k) {
+          cv[k] = k < tk.n ? tk.v[k] : -3.0e38f;
+          ci[k] = k < tk.n ? tk.i[k] : 0x7fffffff;
+        }
+      }
     }
   }
   fence_tc_before();
@@ -1257,6 +1320,8 @@ extern "C" int srk_flash_ce_supported(int d) {
   return (d >= 16 && d <= 128 && d % 16 == 0) || (d == 256 && wide);
 }
 
+extern "C" long long srk_flash_ce_part_floats(int B, int V);
+
 namespace {
 
 int fill_wide(FceWide& p, int B, int V, int d, float scale, const int* labels, bool bwd) {
@@ -1299,11 +1364,18 @@ size_t wide_smem(const FceWide& p, bool bwd) {
 }
 
 int wide_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi, const uint16_t* Elo,
-             long long lde, float scale, const int* labels, float* lse, float* nll, float* part, cudaStream_t st) {
+             long long lde, float scale, const int* labels, float* lse, float* nll, float* part, cudaStream_t st, int topk = 0,
+             int* nvr_out = nullptr) {
   FceWide p;
   SRK_TRY(fill_wide(p, B, V, d, scale, labels, false));
   p.part = part;
   p.zlab = part + 4LL * p.nvr * B;
+  if (topk > 0) {
+    p.topk = topk;
+    p.cand_val = part + srk_flash_ce_part_floats(B, V);
+    p.cand_idx = reinterpret_cast<int*>(p.cand_val + 2LL * p.nvr * B * topk);
+    *nvr_out = p.nvr;
+  }
   p.Shi = Shi; p.Slo = Slo; p.lds = lds;
   SRK_REQUIRE(((reinterpret_cast<uintptr_t>(Shi) | reinterpret_cast<uintptr_t>(Slo)) & 15u) == 0 && lds % 8 == 0,
               "flash_ce_fwd: shat operands must be 16-byte aligned");
@@ -1312,10 +1384,16 @@ int wide_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long
   SRK_TRY(bf16_map(&mEl, Elo, d, V, lde, 64));
   static bool attr_set = false;
   if (!attr_set) {
-    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
     attr_set = true;
   }
-  srk_launch(fce_fwd_wide_kernel, p.ntm * p.nvr, THREADS, wide_smem(p, false), st, mEh, mEl, p);
+  if (topk > 0) {
+    srk_launch(fce_fwd_wide_kernel<true>, p.ntm * p.nvr, THREADS, wide_smem(p, false), st, mEh, mEl, p);
+    SRK_LAUNCH_CHECK();
+    return SRK_OK;
+  }
+  srk_launch(fce_fwd_wide_kernel<false>, p.ntm * p.nvr, THREADS, wide_smem(p, false), st, mEh, mEl, p);
   SRK_LAUNCH_CHECK();
   srk_launch(fce_finalize_kernel, srk_cdiv((long long)B * 32, 256), 256, 0, st, p.part, p.zlab, labels, B, V, 2 * p.nvr, lse, nll);
   SRK_LAUNCH_CHECK();
@@ -1359,18 +1437,20 @@ extern "C" long long srk_flash_ce_part_floats(int B, int V) {
   return 4LL * srk_cdiv(V, TV) * B + B;
 }
 
-extern "C" int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds,
-                                const uint16_t* Ehi, const uint16_t* Elo, long long lde, float scale, const int* labels,
-                                float* lse, float* nll, float* part, void* stream) {
-  if (B <= 0) return SRK_OK;
-  SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && part != nullptr, "flash_ce_fwd: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (d > 128) return wide_fwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, nll, part, st);
+static int narrow_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                      const uint16_t* Elo, long long lde, float scale, const int* labels, float* lse, float* nll, float* part,
+                      cudaStream_t st, int topk, int* nvr_out) {
   FceParams p;
   SRK_TRY(fill_params(p, B, V, d, scale, labels, false));
   p.part = part;
   p.zlab = part + 4LL * p.nvr * B;
   p.Shi = Shi; p.Slo = Slo; p.lds = lds;
+  if (topk > 0) {
+    p.topk = topk;
+    p.cand_val = part + srk_flash_ce_part_floats(B, V);
+    p.cand_idx = reinterpret_cast<int*>(p.cand_val + 2LL * p.nvr * B * topk);
+    *nvr_out = p.nvr;
+  }
   SRK_REQUIRE(!p.a_tmem || ((reinterpret_cast<uintptr_t>(Shi) | reinterpret_cast<uintptr_t>(Slo)) & 15u) == 0,
               "flash_ce_fwd: shat operands must be 16-byte aligned");
   CUtensorMap mSh, mSl, mEh, mEl;
@@ -1380,12 +1460,105 @@ extern "C" int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const 
   SRK_TRY(bf16_map(&mEl, Elo, d, V, lde, p.cw));
   static bool attr_set = false;
   if (!attr_set) {
-    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
+    SRK_CUDA(cudaFuncSetAttribute(fce_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
     attr_set = true;
   }
-  srk_launch(fce_fwd_kernel, p.ntm * p.nvr, THREADS, smem_bytes(p, false), st, mSh, mSl, mEh, mEl, p);
+  if (topk > 0) {
+    srk_launch(fce_fwd_kernel<true>, p.ntm * p.nvr, THREADS, smem_bytes(p, false), st, mSh, mSl, mEh, mEl, p);
+    SRK_LAUNCH_CHECK();
+    return SRK_OK;
+  }
+  srk_launch(fce_fwd_kernel<false>, p.ntm * p.nvr, THREADS, smem_bytes(p, false), st, mSh, mSl, mEh, mEl, p);
   SRK_LAUNCH_CHECK();
   srk_launch(fce_finalize_kernel, srk_cdiv((long long)B * 32, 256), 256, 0, st, p.part, p.zlab, labels, B, V, 2 * p.nvr, lse, nll);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_flash_ce_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds,
+                                const uint16_t* Ehi, const uint16_t* Elo, long long lde, float scale, const int* labels,
+                                float* lse, float* nll, float* part, void* stream) {
+  if (B <= 0) return SRK_OK;
+  SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && part != nullptr, "flash_ce_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d > 128) return wide_fwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, nll, part, st);
+  return narrow_fwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, nll, part, st, 0, nullptr);
+}
+
+namespace {
+// one CTA per row: the K best of the row's 2 * nvr candidate lists, best first (ties: smaller item id first)
+__global__ void __launch_bounds__(128) fce_topk_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int B,
+                                                             int nlists, int K, int* __restrict__ out_idx, float* __restrict__ out_val,
+                                                             float scale) {
+  extern __shared__ float msm[];
+  float* v = msm;
+  int* ix = reinterpret_cast<int*>(msm + (size_t)nlists * K);
+  __shared__ float rv[4];
+  __shared__ int ri[4], rp[4];
+  const int b = blockIdx.x, C = nlists * K;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int l = c / K, k = c - l * K;
+    v[c] = cand_val[((long long)l * B + b) * K + k];
+    ix[c] = cand_idx[((long long)l * B + b) * K + k];
+  }
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    float bv = -3.0e38f;
+    int bi = 0x7fffffff, bp = -1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float x = v[c];
+      const int id = ix[c];
+      if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; bp = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(SRK_FULL, bv, o);
+      const int oi = __shfl_xor_sync(SRK_FULL, bi, o), op = __shfl_xor_sync(SRK_FULL, bp, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bp = op; }
+    }
+    if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = bv; ri[threadIdx.x >> 5] = bi; rp[threadIdx.x >> 5] = bp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 4; ++w)
+        if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; bp = rp[w]; }
+      out_idx[(long long)b * K + k] = bi;
+      if (out_val) out_val[(long long)b * K + k] = scale * bv;
+      if (bp >= 0) { v[bp] = -3.0e38f; ix[bp] = 0x7fffffff; }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+
+/* floats of scratch srk_flash_ce_topk needs (soft-max partials + the candidate lists; SM-count independent bound) */
+extern "C" long long srk_flash_ce_topk_scratch_floats(int B, int V, int K) {
+  return srk_flash_ce_part_floats(B, V) + 2LL * 2 * 148 * B * K + 64;
+}
+
+/* Fused evaluation head: ids (best first) and optionally values of the K <= 32 largest logits scale * shat Ehat^T of every
+ * row, straight from the tensor-core tiles of the fused scoring kernel - the (B, V) matrix is never written.  Replaces
+ * `logits.topk(k=cutoff)` of evaluate() (utils/train.py:49; soft-max is monotone, so the ids are the same). */
+extern "C" int srk_flash_ce_topk(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                                 const uint16_t* Elo, long long lde, float scale, int K, int* out_idx, float* out_val, float* scratch,
+                                 void* stream) {
+  if (B <= 0) return SRK_OK;
+  SRK_REQUIRE(V > 0 && K >= 1 && K <= TOPK_MAX && K <= V && out_idx != nullptr && scratch != nullptr, "flash_ce_topk: bad arguments (K <= %d)", TOPK_MAX);
+  SRK_REQUIRE(srk_flash_ce_supported(d), "flash_ce_topk: d = %d unsupported", d);
+  cudaStream_t st = (cudaStream_t)stream;
+  int nvr = 0;
+  if (d > 128) SRK_TRY(wide_fwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, nullptr, nullptr, nullptr, scratch, st, K, &nvr));
+  else SRK_TRY(narrow_fwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, nullptr, nullptr, nullptr, scratch, st, K, &nvr));
+  SRK_REQUIRE(nvr >= 1 && nvr <= 148 * 2, "flash_ce_topk: unexpected range count %d", nvr);
+  const float* cv = scratch + srk_flash_ce_part_floats(B, V);
+  const int* ci = reinterpret_cast<const int*>(cv + 2LL * nvr * B * K);
+  const size_t smem = (size_t)2 * nvr * K * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SRK_CUDA(cudaFuncSetAttribute(fce_topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 148 * TOPK_MAX * 8 * 2));
+    attr_set = true;
+  }
+  srk_launch(fce_topk_merge_kernel, B, 128, smem, st, cv, ci, B, 2 * nvr, K, out_idx, out_val, scale);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

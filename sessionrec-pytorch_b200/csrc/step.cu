@@ -591,7 +591,11 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   tm.mark("gat_bwd");
   // catalog backward done (not the early Adam part queued behind it): the scatter-add updates the same table rows
   if (ss && live) SRK_CUDA(cudaStreamWaitEvent(st, ss->ev_cat, 0));
-  float* sws = ar.f((size_t)srk_embed_scatter_ws_floats(b.P, d));    // cut runs are combined in chunk order: no atomics
+  // The step is not bit-reproducible from run to run as a whole (split-K weight-gradient GEMMs, the d w_e reduction), so it
+  // takes the one-launch scatter-add by default (atomicAdd on runs cut by a chunk boundary; measured 0.402 vs 0.418 ms per
+  // step at cfg1); SESSREC_DETERMINISTIC_SCATTER=1 selects the two-pass variant without atomics.
+  static const bool scatter_det = getenv("SESSREC_DETERMINISTIC_SCATTER") != nullptr;
+  float* sws = !scatter_det ? nullptr : ar.f((size_t)srk_embed_scatter_ws_floats(b.P, d));
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   SRK_TRY(srk_embed_scatter_bwd_ws(E, b.iid, b.perm, b.uoff, b.uid, b.U, b.P, d, SRK_NORM_L2, drop ? &dc_e : nullptr, rnX, dH,
                                    nullptr, G(0), sws, st));

@@ -332,7 +332,11 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   }
   tm.mark("readout_bwd");
   if (ss && live) SRK_CUDA(cudaStreamWaitEvent(st, ss->ev_cat, 0));
-  float* sws = ar.f((size_t)srk_embed_scatter_ws_floats(N, d));      // cut runs are combined in chunk order: no atomics
+  // The step is not bit-reproducible from run to run as a whole (split-K weight-gradient GEMMs, the d w_e reduction), so it
+  // takes the one-launch scatter-add by default (atomicAdd on runs cut by a chunk boundary; measured 0.402 vs 0.418 ms per
+  // step at cfg1); SESSREC_DETERMINISTIC_SCATTER=1 selects the two-pass variant without atomics.
+  static const bool scatter_det = getenv("SESSREC_DETERMINISTIC_SCATTER") != nullptr;
+  float* sws = !scatter_det ? nullptr : ar.f((size_t)srk_embed_scatter_ws_floats(N, d));  
   SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   SRK_TRY(srk_embed_scatter_bwd_ws(E, b.iid, b.perm, b.uoff, b.uid, b.U, N, d, emb_mode, drop ? &dc_e : nullptr, rn, dX, nullptr, G(0),
                                    sws, st));

@@ -163,6 +163,15 @@ def flash_ce_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout
           ptr(gout), ptr(dS), ptr(dEpart))
 
 
+def flash_ce_topk(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, k, out_idx, out_val=None):
+    """ids [B, k] int32 (best first) of the k largest logits per row, fused into the scoring kernel (no (B, V) matrix)."""
+    _need_cuda(Shi, Slo, Ehi, Elo, out_idx)
+    n = int(_lib.lib().functions['srk_flash_ce_topk_scratch_floats'](B, V, k))
+    scratch = torch.empty(n, dtype=torch.float32, device=out_idx.device)
+    _call('srk_flash_ce_topk', B, V, d, ptr(Shi), ptr(Slo), lds, ptr(Ehi), ptr(Elo), lde, float(scale), int(k), ptr(out_idx),
+          ptr(out_val), ptr(scratch))
+
+
 def sum_parts(parts, stride, nparts, n, out, accumulate=False):
     _call('srk_sum_parts', ptr(parts), stride, nparts, n, ptr(out), int(bool(accumulate)))
 
@@ -174,13 +183,17 @@ def embed_gather_fwd(E, iid, P, d, mode, dc, X, rnorm, x_first=None):
     _call('srk_embed_gather_fwd', ptr(E), ptr(iid), P, d, mode, _dref(dc), ptr(X), ptr(rnorm), ptr(x_first))
 
 
-def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE, deterministic=True):
+def embed_scatter_ws_floats(P, d):
+    return int(_lib.lib().functions['srk_embed_scatter_ws_floats'](int(P), int(d)))
+
+
+def embed_scatter_bwd(E, t, d, mode, dc, rnorm, dX, dX_first, dE, deterministic=True, ws=None):
     """dE[item] += gradient of every occurrence of the item.  deterministic: runs cut by a chunk boundary are combined in a
     fixed order through a small workspace (no atomics); False keeps the one-launch variant with atomicAdd on those rows."""
-    ws = None
-    if deterministic:
-        n = int(_lib.lib().functions['srk_embed_scatter_ws_floats'](t['P'], d))
-        ws = torch.empty(max(n, 1), dtype=torch.float32, device=dE.device)
+    if deterministic and ws is None:
+        ws = torch.empty(max(embed_scatter_ws_floats(t['P'], d), 1), dtype=torch.float32, device=dE.device)
+    if not deterministic:
+        ws = None
     _call('srk_embed_scatter_bwd_ws', ptr(E), ptr(t['iid']), ptr(t['perm']), ptr(t['uoff']), ptr(t['uid']), t['U'], t['P'], d, mode,
           _dref(dc), ptr(rnorm), ptr(dX), ptr(dX_first), ptr(dE), ptr(ws))
 

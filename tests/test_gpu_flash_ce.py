@@ -130,3 +130,34 @@ def test_flash_ce_rejects_unsupported_dim(ops, pkg):
     with pytest.raises(pkg._lib.SessRecError):
         ops.flash_ce_fwd(B, V, d, z, z, d, e, e, d, 1.0, torch.zeros(B, dtype=torch.int32, device=DEV),
                          torch.empty(B, device=DEV), None, torch.empty(ops.flash_ce_part_floats(B, V), device=DEV))
+
+
+@pytest.mark.parametrize('B,V,d,K', [(512, 43097, 96, 20), (300, 5000, 256, 20), (100, 1000, 64, 32), (16, 40, 32, 20), (130, 129, 128, 1)])
+def test_flash_ce_topk_matches_fp64_ranking(ops, B, V, d, K):
+    """Fused evaluation head: the K best items per row straight from the scoring kernel (no (B, V) matrix) against an fp64
+    ranking of the same logits; positions where two consecutive reference scores are closer than the path's tolerance may swap."""
+    S = torch.nn.functional.normalize(_r(B, d), dim=-1)
+    E = torch.nn.functional.normalize(_r(V, d, seed=1), dim=-1)
+    E[5] = E[3]                                             # an exact tie: the smaller id must come first
+    Sh, Sl = _split(ops, S)
+    Eh, El = _split(ops, E)
+    idx = torch.full((B, K), -7, dtype=torch.int32, device=DEV)
+    val = torch.empty(B, K, device=DEV)
+    ops.flash_ce_topk(B, V, d, Sh, Sl, d, Eh, El, d, 12.0, K, idx, val)
+    torch.cuda.synchronize()
+    Z = 12.0 * (S.double() @ E.double().t())
+    rv, ri = Z.topk(min(K + 1, V))
+    got = idx.cpu().long()
+    assert int(got.min()) >= 0 and int(got.max()) < V
+    gv = Z.gather(1, got)                                   # reference scores of the returned ids
+    assert float((val.cpu().double() - gv).abs().max()) <= 1e-4 * 12.0, 'returned values are not the logits of the returned ids'
+    assert float((gv - rv[:, :K]).abs().max()) <= 2e-4 * 12.0, 'a returned item is not among the K best within tolerance'
+    gaps = (rv[:, :-1] - rv[:, 1:]).min(-1)[0] if rv.shape[1] > 1 else torch.ones(B, dtype=torch.float64)
+    safe = gaps > 1e-3
+    assert int(safe.sum()) >= B // 4
+    assert torch.equal(got[safe], ri[safe][:, :K]), 'ids differ on rows without near-ties'
+    for b in range(B):
+        assert len(set(got[b].tolist())) == K, 'duplicate ids in a row'
+        row = got[b].tolist()
+        if 3 in row and 5 in row:
+            assert row.index(3) < row.index(5), 'exact tie: the smaller id comes first'
