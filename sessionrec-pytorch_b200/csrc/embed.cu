@@ -462,7 +462,15 @@ extern "C" int srk_embed_gather_fwd(const float* E, const int* iid, int P, int d
   return SRK_OK;
 }
 
-static inline int scatter_chunk(int P) { return P >= 65536 ? SCATTER_CHUNK : SCATTER_CHUNK_SMALL; }
+static inline int scatter_chunk(int P) {
+  static int forced = -1;                 // SESSREC_SCATTER_CHUNK=n: experiment switch
+  if (forced < 0) {
+    const char* e = getenv("SESSREC_SCATTER_CHUNK");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+  return P >= 65536 ? SCATTER_CHUNK : SCATTER_CHUNK_SMALL;
+}
 
 extern "C" long long srk_embed_scatter_ws_floats(int P, int d) {
   if (P <= 0) return 0;

@@ -1,5 +1,6 @@
 // Graph context of the launch layer (common.cuh): used by csrc/step.cu only.
 #pragma once
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -36,6 +37,10 @@ struct SrkLaunchCtx {
   // refused (fail_cuda = the CUDA error), 5 launch outside the capture
   int fail_reason = 0;
   int fail_cuda = 0;
+  // Work the step wants enqueued with plain calls AFTER its captured / replayed part (on the same stream): the data-parallel
+  // all-reduce and the optimizer behind it.  NCCL collectives inside a replayed graph were measured pathological at 8 ranks
+  // (1.9 ms per step against 0.65 ms with the collective outside), so the graph ends before them.
+  std::function<int()> tail;
 };
 SrkLaunchCtx* srk_get_launch_ctx();
 

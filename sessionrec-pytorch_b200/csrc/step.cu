@@ -604,14 +604,22 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   tm.mark("scatter");
   if (dp_inside) {
     // data parallel: the flat gradient buffer (every rank seeded its backward with B_local / B_global) is summed over the
-    // ranks right here, behind the last gradient kernel and inside the same graph replay - no return to Python
+    // ranks right here, behind the last gradient kernel, by this library's own communicator - no return to Python - and Adam
+    // follows.  When the backward half is replayed from a CUDA graph the two are enqueued with plain calls behind the graph.
     SRK_TRY(order(s4, st));
-    SRK_TRY(srk_comm_allreduce(grads, n_flat, 0, st));
-  }
-  if (split_adam) {
+    auto tail = [=]() -> int {
+      SRK_TRY(srk_comm_allreduce(grads, n_flat, 0, st));
+      if (do_adam)
+        SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
+                              adam_step, grad_scale, st));
+      return SRK_OK;
+    };
+    if (SrkLaunchCtx* lc = srk_get_launch_ctx()) lc->tail = tail;
+    else SRK_TRY(tail());
+  } else if (split_adam) {
     SRK_TRY(srk_adam_step_split(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, tab, V, d,
                                 tab_span, b.uid, b.U, 1, lr, beta1, beta2, eps, adam_step, grad_scale, st));
-  } else if ((phase == 0 || phase == 3) && do_adam) {
+  } else if (phase == 0 && do_adam) {
     if (shard) {
       SRK_TRY(order(s4, st));                    // the owned rows' head gradient (catalog backward on s4)
       // The encoder is replicated: every rank computed the gradients of the non-table parameters from the same inputs, up
@@ -728,6 +736,7 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
       }
     }
   }
+  std::function<int()> tail = ctx.tail;
   if (ok) {
     SRK_CUDA(cudaGraphLaunch(e.g.exec, run));
     ++g_graph_launches;
@@ -741,7 +750,9 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
     rc = body_on_run();
     srk_set_launch_ctx(nullptr);
     if (rc != SRK_OK) return rc;
+    tail = redo.tail;
   }
+  if (tail) SRK_TRY(tail());                 // plain calls behind the graph: collective + optimizer of a data-parallel step
   SRK_TRY(ss0->order_always(run, caller));
   return SRK_OK;
 }

@@ -344,15 +344,22 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   tm.mark("scatter");
   if (phase == 3) {
     // data parallel: the flat gradient buffer (every rank seeded its backward with B_local / B_global) is summed over the
-    // ranks right here, behind the last gradient kernel and inside the same graph replay (csrc/comm.cu)
+    // ranks right here, behind the last gradient kernel (csrc/comm.cu), then Adam; behind the graph when one is replayed
     SRK_REQUIRE(srk_comm_world() > 1, "srgnn step: phase 3 needs a communicator (srk_comm_init)");
     SRK_TRY(order(s4, st));
-    SRK_TRY(srk_comm_allreduce(grads, n_flat, 0, st));
-  }
-  if (split_adam) {
+    auto tail = [=]() -> int {
+      SRK_TRY(srk_comm_allreduce(grads, n_flat, 0, st));
+      if (do_adam)
+        SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
+                              adam_step, grad_scale, st));
+      return SRK_OK;
+    };
+    if (SrkLaunchCtx* lc = srk_get_launch_ctx()) lc->tail = tail;
+    else SRK_TRY(tail());
+  } else if (split_adam) {
     SRK_TRY(srk_adam_step_split(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, tab, V, d,
                                 tab_span, b.uid, b.U, 1, lr, beta1, beta2, eps, adam_step, grad_scale, st));
-  } else if ((phase == 0 || phase == 3) && do_adam) {
+  } else if (phase == 0 && do_adam) {
     SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
                           adam_step, grad_scale, st));
   }
