@@ -450,11 +450,15 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
     shard = args.parallelism == 'shard' and world > 1
     model = build_model(cfg, device)
     model.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+    # The library's own NCCL communicator (collectives enqueued inside the native step): always for the catalog-sharded
+    # step; for data parallelism only with SESSREC_NATIVE_COMM=1 - measured equal to the torch.distributed all-reduce at 2
+    # GPUs, but back-to-back steps stall on it at 8 GPUs (profiles/r2o_*_8gpu.json), so torch.distributed stays the default
     native_comm = False
-    if world > 1 and os.environ.get('SESSREC_NATIVE_COMM', '1') != '0':
+    if world > 1 and (shard or os.environ.get('SESSREC_NATIVE_COMM', '0') == '1'):
         from sessionrec_pytorch_b200 import parallel
-        parallel.init_comm(group)          # the library's own NCCL communicator: collectives enqueued inside the native step
+        parallel.init_comm(group)
         native_comm = True
+        model.dp_allreduce_inside = True
     if shard:
         model.shard_catalog(group)
     step_group = None if shard else group

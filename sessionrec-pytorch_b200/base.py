@@ -430,7 +430,7 @@ class SessRecModule(nn.Module):
                 self._bwd(tape, seed, fp.grad)
             if group is not None:
                 from . import parallel
-                if parallel.comm_ready() and getattr(self, 'dp_allreduce_inside', True):
+                if parallel.comm_ready() and getattr(self, 'dp_allreduce_inside', False):
                     ops.comm_allreduce(fp.grad)            # same communicator as the native steps of the other ranks
                 else:
                     import torch.distributed as dist

@@ -103,7 +103,10 @@ class MSGIFSR(SessRecModule):
         self.beta.data = torch.tensor(1.0)
         self.fusion, self.extra = fusion, extra
         self.native_step = True
-        self.dp_allreduce_inside = True      # data parallel: all-reduce from inside the native step once parallel.init_comm ran
+        # data parallel: True = the gradient all-reduce is enqueued by the native step itself on the library's own communicator
+        # (needs parallel.init_comm).  Off by default: equal to the torch.distributed path at 2 GPUs (0.465 vs 0.469 ms/step), but
+        # at 8 GPUs back-to-back steps stall on it (1.6 vs 0.54 ms/step, profiles/r2o_*_8gpu.json) - not understood yet
+        self.dp_allreduce_inside = False
 
     def reset_parameters(self):
         stdv = 1.0 / math.sqrt(self.embedding_dim)

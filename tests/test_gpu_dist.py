@@ -43,6 +43,7 @@ def _worker(rank, world, port, mode, ret):
             # B_global is all-reduced; dp_empty: rank 1's shard is empty and it still joins the collectives
             if mode in ('dp_native', 'dp_uneven_native'):
                 parallel.init_comm(dist.group.WORLD)
+                m.dp_allreduce_inside = True
             else:
                 m.dp_allreduce_inside = False
             n = len(seqs)

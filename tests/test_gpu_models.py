@@ -304,6 +304,46 @@ def test_native_srgnn_step_matches_staged_composition(pkg, name, p, head):
         assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)
 
 
+@pytest.mark.parametrize('name', ['srgnn', 'msgifsr_k1'])
+def test_optimizer_state_survives_reflattening_and_checkpointing(pkg, name):
+    """`load_state_dict(assign=True)` (or model.to / p.data = ...) invalidates the flat parameter views; the next
+    train_step must carry lr / weight decay / step count / both Adam moments over instead of silently starting a default
+    optimizer, and optimizer_state_dict() / load_optimizer_state_dict() must resume a run bit for bit."""
+    c = TRAINS[name]
+    batches = [make_batch(pkg, c, c['samples'][it * c['bs']:(it + 1) * c['bs']])[0] for it in range(4)]
+
+    def fresh():
+        m = make_model(pkg, c)
+        m.train()
+        m.configure_optimizer(lr=3e-3, weight_decay=2e-4)
+        return m
+    ref = fresh()
+    for b in batches:
+        ref.train_step(b)
+    # (1) re-flatten in the middle of the run
+    m1 = fresh()
+    m1.train_step(batches[0])
+    m1.train_step(batches[1])
+    m1.load_state_dict({k: v.clone() for k, v in m1.state_dict().items()}, assign=True)      # parameters are new tensors now
+    m1.train_step(batches[2])
+    m1.train_step(batches[3])
+    assert m1._opt['lr'] == 3e-3 and m1._opt['weight_decay'] == 2e-4 and m1._opt['step'] == 4
+    # (2) checkpoint after two steps, resume in a new module
+    m2 = fresh()
+    m2.train_step(batches[0])
+    m2.train_step(batches[1])
+    osd, msd = m2.optimizer_state_dict(), {k: v.clone() for k, v in m2.state_dict().items()}
+    m3 = make_model(pkg, c)
+    m3.train()
+    m3.load_state_dict(msd)
+    m3.load_optimizer_state_dict(osd)
+    m3.train_step(batches[2])
+    m3.train_step(batches[3])
+    for (n, p), (_, q1), (_, q3) in zip(ref.named_parameters(), m1.named_parameters(), m3.named_parameters()):
+        assert_close(f'reflatten {n}', q1, p, rtol=1e-4, floor=0.5)
+        assert_close(f'resume {n}', q3, p, rtol=1e-4, floor=0.5)
+
+
 @pytest.mark.parametrize('d', [256, 128])
 def test_native_msgifsr_step_wide_embedding(pkg, d):
     """BASELINE configs[4] embedding width (d = 256: scores materialised on the 3xTF32 GEMM, GAT projections on the

@@ -143,3 +143,41 @@ def test_train_runner_accepts_bare_batches(pkg):
     r = TrainRunner('x', m, [_FakeBatch(lab)] * 4, [([_FakeBatch(lab)], lab)], 'cpu', lr=1e-3, weight_decay=0, patience=2)
     r.train(1, log=lambda s: None)
     assert len(m.lrs) == 4 and m._opt['weight_decay'] == 0 and abs(m._opt['lr'] - 1e-3) < 1e-15
+
+
+def test_inactive_parameters_match_the_reference_goldens(pkg):
+    """Parameters the reference's forward never reaches keep grad None, so torch.optim.Adam never touches them: the static
+    rule of the drop-ins (`_inactive_params`) names exactly the parameters whose value did not change over the reference's own
+    training steps in the trajectory goldens (plus biases whose gradient is exactly zero: no decay, no update either way)."""
+    import torch
+    from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+    from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
+    from tests.util import golden
+    seen = 0
+    for f in ('train_golden.pt', 'train_extra_golden.pt'):
+        for name, c in golden(f).items():
+            untouched = {n for n, v in c['final_state'].items() if torch.equal(v, c['params'][n])}
+            if c['model'] == 'MSGIFSR':
+                m = MSGIFSR(c['V'], 'g', c['d'], 1, dropout=0.0, order=c['K'], extra=c.get('extra', False), fusion=False)
+            else:
+                m = {'SRGNN': SRGNN, 'NISER': NISER}[c['model']](c['V'], c['d'], 1, 0.0)
+            mine = set(m._inactive_params(None))
+            assert mine <= untouched, (name, sorted(mine - untouched))
+            assert all('bias' in n for n in untouched - mine), (name, sorted(untouched - mine))
+            seen += 1
+    assert seen >= 5
+
+
+def test_adam_segments_for_inactive_parameters_and_owned_rows(pkg):
+    import torch
+    from sessionrec_pytorch_b200.flat import FlatParams
+    m = torch.nn.Module()
+    m.emb = torch.nn.Embedding(10, 8)
+    m.lin = torch.nn.Linear(8, 4)
+    fp = FlatParams(m)
+    off, dec = fp.decay_segments(1e-4, inactive={'lin.weight'}, owned_rows=('emb.weight', 3, 7))
+    names = dict(zip(fp.names, fp.offsets))
+    e0 = names['emb.weight']
+    assert off.tolist() == [e0, e0 + 3 * 8, e0 + 7 * 8, names['lin.weight'], names['lin.bias'], fp.total]
+    assert dec.tolist()[0] == -1.0 and abs(dec.tolist()[1] - 1e-4) < 1e-9 and dec.tolist()[2] == -1.0      # only rows [3, 7) are ours
+    assert dec.tolist()[3] == -1.0 and dec.tolist()[4] == 0.0                                                # inactive weight, bias without decay
