@@ -53,7 +53,7 @@ class SessRecModule(nn.Module):
         if not p0.is_cuda:
             raise _lib.SessRecError(f'{type(self).__name__}: parameters live on {p0.device}; this path only runs on '
                                     'CUDA (sm_100a) and has no CPU fallback - call model.to("cuda") first')
-        if self._flat is None or not self._flat.valid():
+        if self._flat is None or not self._flat.valid(self):
             # the parameters were moved / re-assigned (model.to(), load_state_dict(assign=True), p.data = ...): re-flatten and
             # carry the optimizer over by parameter name - hyper-parameters, step count and both moments survive
             old = self.optimizer_state_dict() if self._opt is not None else None

@@ -763,6 +763,7 @@ struct FceWide {
   int topk;                // fwd: see FceParams
   float* cand_val;
   int* cand_idx;
+  int dz_tmem;             // bwd: dZ also lives in TMEM (A operand of the dS product); the logit tile is then single-buffered
 };
 
 struct WideSched {
@@ -1038,9 +1039,13 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
       const uint32_t Sa = smem_u32(S), Da = smem_u32(Dt);
       const uint32_t tds = tmem_base + TMW_DS, tde = tmem_base + TMW_DE;
       int u = 0;
+      // dz_tmem: ONE logit buffer (columns 0..63) and dZ as packed bf16 pairs at columns 64..127 (hi 32 | lo 32): the dS product
+      // takes its A operand from TMEM and no longer re-reads the 128-row D tile from shared memory for every 64-column slice
+      const bool dzt = p.dz_tmem != 0;
+      const uint32_t tdz = tmem_base + TMW_Z + WTV;
       auto logits = [&](int x) {
-        const int zb = x & 1;
-        mbar_wait(&z_empty[zb], ((uint32_t)(x >> 1) & 1u) ^ 1u);
+        const int zb = dzt ? 0 : (x & 1);
+        mbar_wait(&z_empty[zb], (dzt ? ((uint32_t)x & 1u) : ((uint32_t)(x >> 1) & 1u)) ^ 1u);
         fence_tc_after();
         const uint32_t tz = tmem_base + TMW_Z + (uint32_t)zb * WTV;
         for (int c = 0; c < p.nch; ++c, ++u) {
@@ -1070,10 +1075,21 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
           mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
           fence_tc_after();
           const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * WECHUNK);
+          if (dzt) {
 #pragma unroll
-          for (int ks = 0; ks < WTV / 16; ++ks)
-            mma3(tds + (uint32_t)c * 64, kdesc(Da + ks * 32), kdesc(Da + CHUNK + ks * 32), mdesc(Ea + ks * 2048),
-                 mdesc(Ea + WECHUNK + ks * 2048), p.idesc_ds, (it | ks) ? 1u : 0u);
+            for (int ks = 0; ks < WTV / 16; ++ks) {
+              const uint32_t ah = tdz + (uint32_t)ks * 8, al = ah + 32;
+              const uint64_t bh = mdesc(Ea + ks * 2048), bl = mdesc(Ea + WECHUNK + ks * 2048);
+              umma_bf16_ts(tds + (uint32_t)c * 64, ah, bh, p.idesc_ds, (it | ks) ? 1u : 0u);
+              umma_bf16_ts(tds + (uint32_t)c * 64, ah, bl, p.idesc_ds, 1u);
+              umma_bf16_ts(tds + (uint32_t)c * 64, al, bh, p.idesc_ds, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < WTV / 16; ++ks)
+              mma3(tds + (uint32_t)c * 64, kdesc(Da + ks * 32), kdesc(Da + CHUNK + ks * 32), mdesc(Ea + ks * 2048),
+                   mdesc(Ea + WECHUNK + ks * 2048), p.idesc_ds, (it | ks) ? 1u : 0u);
+          }
           umma_commit(&e_empty[s]);
         }
         if (it > 0) {                             // the drain warps have read the previous tile's dE^T accumulators
@@ -1109,15 +1125,17 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
     uint8_t* Dhi = Dt;
     uint8_t* Dlo = Dt + CHUNK;
     const int c0 = half * 32;
+    const bool dzt = p.dz_tmem != 0;
+    const uint32_t tdz = tmem_base + lanebits + TMW_Z + WTV + (uint32_t)(c0 >> 1);       // this thread's 16 packed columns (hi; lo at +32)
     for (int it = 0; it < ntiles; ++it) {
-      const int t = ts.t0 + it, zb = it & 1;
-      mbar_wait(&z_full[zb], (uint32_t)(it >> 1) & 1u);
+      const int t = ts.t0 + it, zb = dzt ? 0 : (it & 1);
+      mbar_wait(&z_full[zb], dzt ? ((uint32_t)it & 1u) : ((uint32_t)(it >> 1) & 1u));
       fence_tc_after();
       uint32_t hw[16], lw[16];
+      const int v0 = t * WTV + c0;
       {
         uint32_t acc[32];
         tmem_ld32(tmem_base + lanebits + TMW_Z + (uint32_t)(zb * WTV + c0), acc);
-        const int v0 = t * WTV + c0;
         float dz[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) dz[j] = coef_p * ex2f(fmaf(__uint_as_float(acc[j]), c2, -lse2));
@@ -1126,15 +1144,29 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
           for (int j = 0; j < 32; ++j)
             if (v0 + j >= p.V) dz[j] = 0.f;
         }
+        if (dzt && lab >= v0 && lab < v0 + 32) {        // the onehot term goes into the registers: both copies of dZ get it
+          const int lj = lab - v0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] -= (j == lj) ? coef : 0.f;
+        }
         pack_dz(dz, hw, lw);
       }
       fence_tc_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&z_empty[zb]);
-      if (it > 0) mbar_wait(&d_empty, (uint32_t)(it - 1) & 1u);       // previous tile's gradient products have read D
+      if (it > 0) mbar_wait(&d_empty, (uint32_t)(it - 1) & 1u);       // previous tile's gradient products have read D (and dZ in TMEM)
       store_dz(Dhi, Dlo, r, c0, hw, lw);
-      const int v0 = t * WTV + c0;
-      if (lab >= v0 && lab < v0 + 32) fix_dz(Dhi, Dlo, r, lab - t * WTV, coef);
+      if (dzt) {
+        fence_tc_after();
+        tmem_st8(tdz, hw);
+        tmem_st8(tdz + 8, hw + 8);
+        tmem_st8(tdz + 32, lw);
+        tmem_st8(tdz + 40, lw + 8);
+        tmem_wait_st();
+        fence_tc_before();
+      } else if (lab >= v0 && lab < v0 + 32) {
+        fix_dz(Dhi, Dlo, r, lab - t * WTV, coef);
+      }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&d_full);
@@ -1408,6 +1440,12 @@ int wide_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long
   p.lse = lse;
   p.gout = gout;
   p.dEpart = dEpart;
+  static int dzt = -1;                    // SESSREC_FCE_WIDE_DZT=0: dZ only in shared memory, double-buffered logit tile
+  if (dzt < 0) {
+    const char* e = getenv("SESSREC_FCE_WIDE_DZT");
+    dzt = !(e && e[0] == '0');
+  }
+  p.dz_tmem = dzt;
   CUtensorMap mSh, mSl, mEh, mEl, mdS;
   SRK_TRY(bf16_map(&mSh, Shi, d, B, lds, 64));
   SRK_TRY(bf16_map(&mSl, Slo, d, B, lds, 64));

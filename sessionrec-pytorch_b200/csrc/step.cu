@@ -220,8 +220,10 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   // cfg1 for the two on the critical path); SESSREC_TC_ENCODER=0 switches back.
   const char* tce = getenv("SESSREC_TC_ENCODER");
   const bool tc_enc = umma && d <= 256 && d % 32 == 0 && !(tce && tce[0] == '0');
-  // W_aug = [W ; a_l-contracted rows] and w_r depend on the parameters only: built beside the gather (s2)
+  // W_aug = [W ; a_l-contracted rows] and w_r depend on the parameters only: built beside the gather, the two convolutions
+  // of a layer on two streams (the first projection of the step waits for this chain: gat_prep -> split, ~10 us per conv)
   SRK_TRY(order(st, s2));                        // after the previous step's optimizer update
+  SRK_TRY(order(st, s3));
   for (int l = 0; l < L; ++l) {
     LayerRec& R = layers[l];
     R.n_inst = M > 0 ? 2 : 0;
@@ -233,13 +235,14 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       I.Waug = ar.f((size_t)ldzel * d);
       I.wr = ar.f((size_t)H * d);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, s2));
+      cudaStream_t ps = c == 0 ? s2 : s3;
+      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, ps));
       I.Wh = I.Wl = nullptr;
       if (tc_enc) {
         I.Wh = ar.f((size_t)ldzel * d);
         I.Wl = ar.f((size_t)ldzel * d);
         SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(srk_split_tf32(I.Waug, d, ldzel, d, I.Wh, I.Wl, d, s2));
+        SRK_TRY(srk_split_tf32(I.Waug, d, ldzel, d, I.Wh, I.Wl, d, ps));
       }
     }
   }
@@ -255,6 +258,7 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
     SRK_TRY(srk_transpose(P(s_ro + 4), d, 2 * d, WsrT, s2));
   }
   SRK_TRY(order(s2, st));
+  SRK_TRY(order(s3, st));
   const float* h = X;
   for (int l = 0; l < L; ++l) {
     LayerRec& R = layers[l];

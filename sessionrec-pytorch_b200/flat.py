@@ -25,11 +25,28 @@ class FlatParams:
             p.data = self.data[o:o + p.numel()].view(p.shape)
         self.grad = torch.zeros_like(self.data)
         self.index = {n: i for i, n in enumerate(self.names)}
+        # where every parameter hangs in the module tree: lets valid() notice swapped Parameter objects in O(1)
+        owner = {}
+        for sub in module.modules():
+            for key, p in sub._parameters.items():
+                if p is not None:
+                    owner.setdefault(id(p), (sub, key))
+        self._owner = [owner[id(p)] for p in self.params]
 
-    def valid(self):
-        p0, pl = self.params[0], self.params[-1]
-        return (p0.data_ptr() == self.data.data_ptr() + 4 * self.offsets[0]
-                and pl.data_ptr() == self.data.data_ptr() + 4 * self.offsets[-1])
+    def valid(self, module=None):
+        """The parameters still ARE the views into the flat buffer: same Parameter objects (load_state_dict(assign=True)
+        swaps them), same storage (model.to() / p.data = ... re-point them).  Checked on the first, middle and last parameter."""
+        base = self.data.data_ptr()
+        n = len(self.params)
+        probe = sorted({0, n // 2, n - 1})
+        for i in probe:
+            if self.params[i].data_ptr() != base + 4 * self.offsets[i]:
+                return False
+        for i in probe:
+            sub, key = self._owner[i]
+            if sub._parameters.get(key) is not self.params[i]:
+                return False
+        return True
 
     def views(self, flat):
         """Per-parameter views (same order as `params`) into another flat buffer of the same layout."""
