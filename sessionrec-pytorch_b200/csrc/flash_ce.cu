@@ -760,6 +760,7 @@ struct FceWide {
   const uint16_t *Shi, *Slo;   // fwd: bf16 hi / lo of shat in global memory, row pitch lds (staged into TMEM)
   long long lds;
   uint32_t idesc_z, idesc_ds, idesc_de;
+  uint32_t idesc_de2;      // bwd: the dS product with N = d (whole catalog tile resident in the stage ring)
   int topk;                // fwd: see FceParams
   float* cand_val;
   int* cand_idx;
@@ -837,14 +838,14 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
           mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
           fence_tc_after();
           const uint32_t Ea = smem_u32(smem + (size_t)s * 2 * CHUNK);
+          const uint64_t eh0 = kdesc(Ea), el0 = kdesc(Ea + CHUNK);      // + 2 per UMMA K step (32 bytes inside the 128-byte row)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t kk = (uint32_t)(c * 4 + ks);
             const uint32_t ah = tmem_base + TM_SA + kk * 8, al = ah + lo_off;
-            const uint64_t eh = kdesc(Ea + ks * 32), el = kdesc(Ea + CHUNK + ks * 32);
-            umma_bf16_ts(tz, ah, eh, p.idesc_z, kk ? 1u : 0u);
-            umma_bf16_ts(tz, ah, el, p.idesc_z, 1u);
-            umma_bf16_ts(tz, al, eh, p.idesc_z, 1u);
+            umma_bf16_ts(tz, ah, eh0 + 2 * ks, p.idesc_z, kk ? 1u : 0u);
+            umma_bf16_ts(tz, ah, el0 + 2 * ks, p.idesc_z, 1u);
+            umma_bf16_ts(tz, al, eh0 + 2 * ks, p.idesc_z, 1u);
           }
           umma_commit(&e_empty[s]);
         }
@@ -1036,8 +1037,17 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
+      // The issuing thread is a single lane and the N = 64 MMAs of this kernel take only 32 cycles each: every instruction
+      // between two tcgen05.mma is tensor-pipe idle time (the first version rebuilt four 64-bit descriptors per product
+      // triple and was issue-bound at ~100 cycles per MMA).  All descriptors are therefore loop-invariant 64-bit bases built
+      // once, plus small immediate offsets: the address field counts 16-byte units, +2 = 32 bytes (one UMMA K inside a
+      // K-major 128-byte row), +128 = 2048 bytes (16 rows of an MN-major operand), +1024 = one 16 KB chunk.
       const uint32_t Sa = smem_u32(S), Da = smem_u32(Dt);
       const uint32_t tds = tmem_base + TMW_DS, tde = tmem_base + TMW_DE;
+      const uint64_t sKh = kdesc(Sa), sKl = kdesc(Sa + op_bytes);              // shat, K-major (logits A)
+      const uint64_t sMh = mdesc(Sa), sMl = mdesc(Sa + op_bytes);              // shat, MN-major (dE^T A)
+      const uint64_t dKh = kdesc(Da), dKl = kdesc(Da + CHUNK);                 // dZ, K-major (dS A, shared-memory variant)
+      const uint64_t dMh = mdesc(Da), dMl = mdesc(Da + CHUNK);                 // dZ, MN-major (dE^T B)
       int u = 0;
       // dz_tmem: ONE logit buffer (columns 0..63) and dZ as packed bf16 pairs at columns 64..127 (hi 32 | lo 32): the dS product
       // takes its A operand from TMEM and no longer re-reads the 128-row D tile from shared memory for every 64-column slice
@@ -1053,12 +1063,11 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
           mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
           fence_tc_after();
           const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * WECHUNK);
+          const uint64_t eh = kdesc(Ea), el = kdesc(Ea + WECHUNK);
+          const uint64_t so = (uint64_t)((uint32_t)c * (CHUNK >> 4));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t so = (uint32_t)c * CHUNK + (uint32_t)ks * 32;
-            mma3(tz, kdesc(Sa + so), kdesc(Sa + op_bytes + so), kdesc(Ea + ks * 32), kdesc(Ea + WECHUNK + ks * 32), p.idesc_z,
-                 (c | ks) ? 1u : 0u);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            mma3(tz, sKh + so + 2 * ks, sKl + so + 2 * ks, eh + 2 * ks, el + 2 * ks, p.idesc_z, (c | ks) ? 1u : 0u);
           umma_commit(&e_empty[s]);
         }
         umma_commit(&z_full[zb]);
@@ -1069,28 +1078,55 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
         if (it + 1 < ntiles) logits(it + 1);
         mbar_wait(&d_full, (uint32_t)it & 1u);
         fence_tc_after();
-        // dS[128 b, 64 columns of chunk c] += dZ[128 b x 64 v] E_c[64 v x 64]: A = D K-major, B = catalog chunk MN-major
-        for (int c = 0; c < p.nch; ++c, ++u) {
-          const int s = u % p.estages;
-          mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
+        // dS[128 b, d] += dZ[128 b x 64 v] E[64 v x d]: A = D K-major (or TMEM), B = the catalog tile MN-major.  Every pass over a
+        // tile takes nch stages, so with a ring of exactly nch stages the chunks of this pass sit in slots 0 .. nch - 1, one
+        // stage stride (= CHUNK bytes, the LBO of mdesc) apart: ONE N = d MMA per K step instead of nch N = 64 ones (the
+        // issuing thread needs ~50-100 cycles per tcgen05.mma, a 32-cycle N = 64 MMA cannot hide that, a 128-cycle one can).
+        if (p.estages == p.nch && u % p.nch == 0 && 2 * WECHUNK == CHUNK) {
+          for (int c = 0; c < p.nch; ++c) {
+            mbar_wait(&e_full[c], (uint32_t)((u + c) / p.estages) & 1u);
+          }
           fence_tc_after();
-          const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * WECHUNK);
+          const uint32_t Ea = smem_u32(E0);
+          const uint64_t bh = mdesc(Ea), bl = mdesc(Ea + WECHUNK);
           if (dzt) {
 #pragma unroll
             for (int ks = 0; ks < WTV / 16; ++ks) {
               const uint32_t ah = tdz + (uint32_t)ks * 8, al = ah + 32;
-              const uint64_t bh = mdesc(Ea + ks * 2048), bl = mdesc(Ea + WECHUNK + ks * 2048);
-              umma_bf16_ts(tds + (uint32_t)c * 64, ah, bh, p.idesc_ds, (it | ks) ? 1u : 0u);
-              umma_bf16_ts(tds + (uint32_t)c * 64, ah, bl, p.idesc_ds, 1u);
-              umma_bf16_ts(tds + (uint32_t)c * 64, al, bh, p.idesc_ds, 1u);
+              umma_bf16_ts(tds, ah, bh + 128 * ks, p.idesc_de2, (it | ks) ? 1u : 0u);
+              umma_bf16_ts(tds, ah, bl + 128 * ks, p.idesc_de2, 1u);
+              umma_bf16_ts(tds, al, bh + 128 * ks, p.idesc_de2, 1u);
             }
           } else {
 #pragma unroll
             for (int ks = 0; ks < WTV / 16; ++ks)
-              mma3(tds + (uint32_t)c * 64, kdesc(Da + ks * 32), kdesc(Da + CHUNK + ks * 32), mdesc(Ea + ks * 2048),
-                   mdesc(Ea + WECHUNK + ks * 2048), p.idesc_ds, (it | ks) ? 1u : 0u);
+              mma3(tds, dKh + 2 * ks, dKl + 2 * ks, bh + 128 * ks, bl + 128 * ks, p.idesc_de2, (it | ks) ? 1u : 0u);
           }
-          umma_commit(&e_empty[s]);
+          for (int c = 0; c < p.nch; ++c) umma_commit(&e_empty[c]);
+          u += p.nch;
+        } else {
+          for (int c = 0; c < p.nch; ++c, ++u) {
+            const int s = u % p.estages;
+            mbar_wait(&e_full[s], (uint32_t)(u / p.estages) & 1u);
+            fence_tc_after();
+            const uint32_t Ea = smem_u32(E0 + (size_t)s * 2 * WECHUNK);
+            const uint64_t bh = mdesc(Ea), bl = mdesc(Ea + WECHUNK);
+            const uint32_t tacc = tds + (uint32_t)c * 64;
+            if (dzt) {
+#pragma unroll
+              for (int ks = 0; ks < WTV / 16; ++ks) {
+                const uint32_t ah = tdz + (uint32_t)ks * 8, al = ah + 32;
+                umma_bf16_ts(tacc, ah, bh + 128 * ks, p.idesc_ds, (it | ks) ? 1u : 0u);
+                umma_bf16_ts(tacc, ah, bl + 128 * ks, p.idesc_ds, 1u);
+                umma_bf16_ts(tacc, al, bh + 128 * ks, p.idesc_ds, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < WTV / 16; ++ks)
+                mma3(tacc, dKh + 2 * ks, dKl + 2 * ks, bh + 128 * ks, bl + 128 * ks, p.idesc_ds, (it | ks) ? 1u : 0u);
+            }
+            umma_commit(&e_empty[s]);
+          }
         }
         if (it > 0) {                             // the drain warps have read the previous tile's dE^T accumulators
           mbar_wait(&de_free, (uint32_t)(it - 1) & 1u);
@@ -1100,11 +1136,10 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
         // LBO = CHUNK), B = D MN-major, K = sessions in steps of 16 rows
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint32_t sa = Sa + (uint32_t)(2 * h) * CHUNK;
 #pragma unroll
           for (int ks = 0; ks < TB / 16; ++ks)
-            mma3(tde + (uint32_t)h * WTV, mdesc(sa + ks * 2048), mdesc(sa + op_bytes + ks * 2048), mdesc(Da + ks * 2048),
-                 mdesc(Da + CHUNK + ks * 2048), p.idesc_de, ks ? 1u : 0u);
+            mma3(tde + (uint32_t)h * WTV, sMh + 2048 * h + 128 * ks, sMl + 2048 * h + 128 * ks, dMh + 128 * ks, dMl + 128 * ks,
+                 p.idesc_de, ks ? 1u : 0u);
         }
         umma_commit(&d_empty);
       }
@@ -1184,23 +1219,23 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
       fence_tc_after();
       const int v0 = (ts.t0 + it) * WTV;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t a0[32], a1[32];
-        tmem_ld32(tmem_base + lanebits + TMW_DE + (uint32_t)(h * WTV), a0);
-        tmem_ld32(tmem_base + lanebits + TMW_DE + (uint32_t)(h * WTV + 32), a1);
-        if (h == 1) {                             // both halves are in registers: the next tile may overwrite the accumulators
+      for (int q4 = 0; q4 < 4; ++q4) {             // (embedding half h, 32 catalog rows): 32 accumulator columns at a time
+        const int h = q4 >> 1, vo = (q4 & 1) * 32;
+        uint32_t a[32];
+        tmem_ld32(tmem_base + lanebits + TMW_DE + (uint32_t)(h * WTV + vo), a);
+        if (q4 == 3) {                            // everything is in registers: the next tile may overwrite the accumulators
           fence_tc_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&de_free);
         }
-        float* col = outp + h * 128 + r;
+        float* col = outp + (long long)(v0 + vo) * p.d + h * 128 + r;
+        if (v0 + vo + 32 <= p.V) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (v0 + j < p.V) col[(long long)(v0 + j) * p.d] = __uint_as_float(a0[j]);
-        }
+          for (int j = 0; j < 32; ++j) col[(long long)j * p.d] = __uint_as_float(a[j]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (v0 + 32 + j < p.V) col[(long long)(v0 + 32 + j) * p.d] = __uint_as_float(a1[j]);
+          for (int j = 0; j < 32; ++j)
+            if (v0 + vo + j < p.V) col[(long long)j * p.d] = __uint_as_float(a[j]);
         }
       }
     }
@@ -1380,6 +1415,7 @@ int fill_wide(FceWide& p, int B, int V, int d, float scale, const int* labels, b
   int st = (int)((FCE_MAX_SMEM - 1024 - fixed) / stage);
   if (st > W_MAX_STAGES) st = W_MAX_STAGES;
   SRK_REQUIRE(st >= 2, "flash_ce (wide): shared-memory budget exceeded");
+  if (bwd && st >= p.nch) st = p.nch;        // ring = one catalog tile: the dS pass finds its chunks in slots 0 .. nch - 1
   p.estages = st;
   p.scale = scale;
   p.labels = labels;
@@ -1387,6 +1423,7 @@ int fill_wide(FceWide& p, int B, int V, int d, float scale, const int* labels, b
   const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TB >> 4) << 24);
   p.idesc_z = base | ((uint32_t)(p.tv >> 3) << 17);
   p.idesc_ds = base | (1u << 16) | ((uint32_t)(64 >> 3) << 17);
+  p.idesc_de2 = base | (1u << 16) | ((uint32_t)(d >> 3) << 17);
   p.idesc_de = base | (1u << 15) | (1u << 16) | ((uint32_t)(WTV >> 3) << 17);
   return SRK_OK;
 }
