@@ -14,7 +14,7 @@ OBJ = PKG / 'build'
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default', '--expt-relaxed-constexpr',
-              '-I', str(INCLUDE)]
+              '-I', str(INCLUDE)] + os.environ.get('SESSREC_NVCC_EXTRA', '').split()
 
 
 def _nvcc():

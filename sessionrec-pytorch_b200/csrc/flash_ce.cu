@@ -85,7 +85,7 @@ struct FceParams {
 
 // role: 0 = TMA producer, 1 = MMA issuer, 2 + w = epilogue warp w (lane 0)
 __device__ __forceinline__ void tr(const FceParams& p, int role, int it, int k) {
-  if (p.trace != nullptr && blockIdx.x == 0 && it < 64) p.trace[(role * 64 + it) * 8 + k] = clock64();
+  if (p.trace != nullptr && blockIdx.x == 0 && it < 64 && (SRK_ISSUE_MODE == 2 || (threadIdx.x & 31) == 0)) p.trace[(role * 64 + it) * 8 + k] = clock64();
 }
 
 // UMMA shared-memory descriptors (SWIZZLE_128B, version 1): constant high part | (address >> 4).  K-major operands step
@@ -99,12 +99,34 @@ __device__ __forceinline__ uint64_t mdesc(uint32_t addr) { return MDESC_HI | (ui
 
 __device__ __forceinline__ uint64_t odesc(uint64_t hi, uint32_t addr) { return hi | (uint64_t)((addr >> 4) & 0x3FFFu); }
 
+// MMA issue: see SRK_ISSUE_MODE in umma.cuh.  In the default mode the wrappers below are plain calls inside an
+// `if (elect_one())` block; modes 0 / 1 run the issue loops with all 32 lanes and predicate the instructions.
+#if SRK_ISSUE_MODE == 2
+#define SRK_ISSUER_BLOCK if (elect_one())
+__device__ __forceinline__ bool lane0() { return true; }
+#elif SRK_ISSUE_MODE == 1
+#define SRK_ISSUER_BLOCK
+__device__ __forceinline__ bool lane0() { return elect_one(); }
+#else
+#define SRK_ISSUER_BLOCK
+__device__ __forceinline__ bool lane0() { return (threadIdx.x & 31) == 0; }
+#endif
+__device__ __forceinline__ void e_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (lane0()) umma::umma_bf16(tmem_d, adesc, bdesc, idesc, accum);
+}
+__device__ __forceinline__ void e_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (lane0()) umma::umma_bf16_ts(tmem_d, tmem_a, bdesc, idesc, accum);
+}
+__device__ __forceinline__ void e_commit(uint64_t* bar) {
+  if (lane0()) umma::umma_commit(bar);
+}
+
 // acc (+)= A B with both operands split hi/lo: hi*hi + hi*lo + lo*hi
 __device__ __forceinline__ void mma3(uint32_t tacc, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc,
                                      uint32_t accum) {
-  umma_bf16(tacc, ah, bh, idesc, accum);
-  umma_bf16(tacc, ah, bl, idesc, 1u);
-  umma_bf16(tacc, al, bh, idesc, 1u);
+  e_umma(tacc, ah, bh, idesc, accum);
+  e_umma(tacc, ah, bl, idesc, 1u);
+  e_umma(tacc, al, bh, idesc, 1u);
 }
 
 // logit tile: Z[128 b x 128 v] = S E^T, K = d in steps of 16 (32 bytes inside the swizzled chunk row)
@@ -130,9 +152,9 @@ __device__ __forceinline__ void issue_logits_ts(uint32_t tz, uint32_t ta, uint32
   for (int ks = 0; ks < nks; ++ks) {
     const uint64_t off = (uint64_t)(((uint32_t)(ks >> p.kpc_log2) * p.chunk_bytes + (uint32_t)(ks & kmask) * 32) >> 4);
     const uint32_t ah = ta + (uint32_t)ks * 8, al = ah + 64;
-    umma_bf16_ts(tz, ah, eh + off, p.idesc_z, ks ? 1u : 0u);
-    umma_bf16_ts(tz, ah, el + off, p.idesc_z, 1u);
-    umma_bf16_ts(tz, al, eh + off, p.idesc_z, 1u);
+    e_umma_ts(tz, ah, eh + off, p.idesc_z, ks ? 1u : 0u);
+    e_umma_ts(tz, ah, el + off, p.idesc_z, 1u);
+    e_umma_ts(tz, al, eh + off, p.idesc_z, 1u);
   }
 }
 
@@ -243,7 +265,7 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (issue_lane()) {
       if (!ats) {
         mbar_expect_tx(&s_full, 2 * op_bytes);
         load_operand(S, &mSh, &mSl, &s_full, p.nch, p.chunk_bytes, p.cw, op_bytes, ts.tb * TB);
@@ -259,7 +281,7 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    SRK_ISSUER_BLOCK {
       mbar_wait(&s_full, 0);
       fence_tc_after();
       int it = 0;
@@ -272,8 +294,8 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         fence_tc_after();
         if (ats) issue_logits_ts(tmem_base + TM_Z + (uint32_t)zb * TV, tmem_base + TM_SA, smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p);
         else issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, smem_u32(S), smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p);
-        umma_commit(&e_empty[s]);
-        umma_commit(&z_full[zb]);
+        e_commit(&e_empty[s]);
+        e_commit(&z_full[zb]);
         tr(p, 1, it, 2);
       }
     }
@@ -533,7 +555,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (issue_lane()) {
       mbar_expect_tx(&s_full, 2 * op_bytes);
       load_operand(S, &mSh, &mSl, &s_full, p.nch, p.chunk_bytes, p.cw, op_bytes, ts.tb * TB);
       for (int it = 0; it < ntiles; ++it) {
@@ -546,7 +568,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    SRK_ISSUER_BLOCK {
       const uint32_t Sa = smem_u32(S), Da = smem_u32(Dt);
       const uint32_t tds = tmem_base + TM_DS, tde = tmem_base + TM_DE;
       auto logits = [&](int it) {
@@ -556,7 +578,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
         mbar_wait(&z_empty[zb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         fence_tc_after();
         issue_logits(tmem_base + TM_Z + (uint32_t)zb * TV, Sa, smem_u32(E0 + (size_t)s * 2 * op_bytes), op_bytes, p);
-        umma_commit(&z_full[zb]);
+        e_commit(&z_full[zb]);
         tr(p, 1, it, 1);
       };
       mbar_wait(&s_full, 0);
@@ -580,7 +602,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
             mma3(tds, ah + aoff, al + aoff, bh + boff, bl + boff, p.idesc_ds, (it | ks) ? 1u : 0u);
           }
         }
-        umma_commit(&e_empty[s]);
+        e_commit(&e_empty[s]);
         // the drain warps have read the previous tile's dE accumulator out of TMEM
         if (it > 0) {
           mbar_wait(&de_free, (uint32_t)(it - 1) & 1u);
@@ -596,7 +618,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
             mma3(tde, ah + aoff, al + aoff, bh + boff, bl + boff, p.idesc_de, ks ? 1u : 0u);
           }
         }
-        umma_commit(&d_empty);
+        e_commit(&d_empty);
         tr(p, 1, it, 3);
         if (p.estages == 1 && it + 1 < ntiles) logits(it + 1);
       }
@@ -811,7 +833,7 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (issue_lane()) {
       int u = 0;                                       // pipeline-stage uses so far
       for (int t = ts.t0; t < ts.t1; ++t)
         for (int c = 0; c < p.nch; ++c, ++u) {
@@ -824,7 +846,7 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    SRK_ISSUER_BLOCK {
       mbar_wait(&s_full, 0);
       fence_tc_after();
       int u = 0, it = 0;
@@ -843,13 +865,13 @@ fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_consta
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t kk = (uint32_t)(c * 4 + ks);
             const uint32_t ah = tmem_base + TM_SA + kk * 8, al = ah + lo_off;
-            umma_bf16_ts(tz, ah, eh0 + 2 * ks, p.idesc_z, kk ? 1u : 0u);
-            umma_bf16_ts(tz, ah, el0 + 2 * ks, p.idesc_z, 1u);
-            umma_bf16_ts(tz, al, eh0 + 2 * ks, p.idesc_z, 1u);
+            e_umma_ts(tz, ah, eh0 + 2 * ks, p.idesc_z, kk ? 1u : 0u);
+            e_umma_ts(tz, ah, el0 + 2 * ks, p.idesc_z, 1u);
+            e_umma_ts(tz, al, eh0 + 2 * ks, p.idesc_z, 1u);
           }
-          umma_commit(&e_empty[s]);
+          e_commit(&e_empty[s]);
         }
-        umma_commit(&z_full[zb]);
+        e_commit(&z_full[zb]);
       }
     }
   } else {
@@ -1010,7 +1032,7 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (issue_lane()) {
       // ===== TMA producer.  Stage order = the order the MMA warp consumes: L(0); then per tile L(it + 1), dS(it). =====
       mbar_expect_tx(&s_full, 2 * op_bytes);
       for (int c = 0; c < p.nch; ++c) {
@@ -1035,7 +1057,7 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    SRK_ISSUER_BLOCK {
       // ===== MMA issuer =====
       // The issuing thread is a single lane and the N = 64 MMAs of this kernel take only 32 cycles each: every instruction
       // between two tcgen05.mma is tensor-pipe idle time (the first version rebuilt four 64-bit descriptors per product
@@ -1068,9 +1090,9 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             mma3(tz, sKh + so + 2 * ks, sKl + so + 2 * ks, eh + 2 * ks, el + 2 * ks, p.idesc_z, (c | ks) ? 1u : 0u);
-          umma_commit(&e_empty[s]);
+          e_commit(&e_empty[s]);
         }
-        umma_commit(&z_full[zb]);
+        e_commit(&z_full[zb]);
       };
       mbar_wait(&s_full, 0);
       if (ntiles > 0) logits(0);
@@ -1093,16 +1115,16 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
 #pragma unroll
             for (int ks = 0; ks < WTV / 16; ++ks) {
               const uint32_t ah = tdz + (uint32_t)ks * 8, al = ah + 32;
-              umma_bf16_ts(tds, ah, bh + 128 * ks, p.idesc_de2, (it | ks) ? 1u : 0u);
-              umma_bf16_ts(tds, ah, bl + 128 * ks, p.idesc_de2, 1u);
-              umma_bf16_ts(tds, al, bh + 128 * ks, p.idesc_de2, 1u);
+              e_umma_ts(tds, ah, bh + 128 * ks, p.idesc_de2, (it | ks) ? 1u : 0u);
+              e_umma_ts(tds, ah, bl + 128 * ks, p.idesc_de2, 1u);
+              e_umma_ts(tds, al, bh + 128 * ks, p.idesc_de2, 1u);
             }
           } else {
 #pragma unroll
             for (int ks = 0; ks < WTV / 16; ++ks)
               mma3(tds, dKh + 2 * ks, dKl + 2 * ks, bh + 128 * ks, bl + 128 * ks, p.idesc_de2, (it | ks) ? 1u : 0u);
           }
-          for (int c = 0; c < p.nch; ++c) umma_commit(&e_empty[c]);
+          for (int c = 0; c < p.nch; ++c) e_commit(&e_empty[c]);
           u += p.nch;
         } else {
           for (int c = 0; c < p.nch; ++c, ++u) {
@@ -1116,16 +1138,16 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
 #pragma unroll
               for (int ks = 0; ks < WTV / 16; ++ks) {
                 const uint32_t ah = tdz + (uint32_t)ks * 8, al = ah + 32;
-                umma_bf16_ts(tacc, ah, bh + 128 * ks, p.idesc_ds, (it | ks) ? 1u : 0u);
-                umma_bf16_ts(tacc, ah, bl + 128 * ks, p.idesc_ds, 1u);
-                umma_bf16_ts(tacc, al, bh + 128 * ks, p.idesc_ds, 1u);
+                e_umma_ts(tacc, ah, bh + 128 * ks, p.idesc_ds, (it | ks) ? 1u : 0u);
+                e_umma_ts(tacc, ah, bl + 128 * ks, p.idesc_ds, 1u);
+                e_umma_ts(tacc, al, bh + 128 * ks, p.idesc_ds, 1u);
               }
             } else {
 #pragma unroll
               for (int ks = 0; ks < WTV / 16; ++ks)
                 mma3(tacc, dKh + 2 * ks, dKl + 2 * ks, bh + 128 * ks, bl + 128 * ks, p.idesc_ds, (it | ks) ? 1u : 0u);
             }
-            umma_commit(&e_empty[s]);
+            e_commit(&e_empty[s]);
           }
         }
         if (it > 0) {                             // the drain warps have read the previous tile's dE^T accumulators
@@ -1141,7 +1163,7 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
             mma3(tde + (uint32_t)h * WTV, sMh + 2048 * h + 128 * ks, sMl + 2048 * h + 128 * ks, dMh + 128 * ks, dMl + 128 * ks,
                  p.idesc_de, ks ? 1u : 0u);
         }
-        umma_commit(&d_empty);
+        e_commit(&d_empty);
       }
     }
   } else if (warp < 2 + EPI_WARPS) {

@@ -81,6 +81,31 @@ static __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Single-thread issue.  SRK_ISSUE_MODE (compile time, kept for A/B on the hardware):
+//   2 (default)  the issuing / producing warp enters its loop through `if (elect_one())`: ptxas then KNOWS that exactly one thread
+//                runs the block, keeps the descriptor arithmetic in uniform registers and emits the tcgen05.mma / TMA
+//                instructions back to back;
+//   0            `if (lane == 0)`: same single thread, but ptxas cannot prove it: every UTCHMMA / UTMALDG is wrapped in a
+//                vote + elect "waterfall" loop with R2UR moves (8-13 instructions and 50-100 cycles per MMA - the flash kernels were
+//                MMA-issue bound because of this);
+//   1            all 32 lanes run the loops, elect.sync around every tcgen05 instruction (flash_ce.cu only).
+#ifndef SRK_ISSUE_MODE
+#define SRK_ISSUE_MODE 2
+#endif
+static __device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// the guard of a single-thread producer / issuer loop; the warp must be converged here
+static __device__ __forceinline__ bool issue_lane() {
+#if SRK_ISSUE_MODE == 2
+  return elect_one();
+#else
+  return (threadIdx.x & 31) == 0;
+#endif
+}
+
 static __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -134,7 +134,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (issue_lane()) {
         // ===== TMA producer =====
         for (int i = 0; i < nkb; ++i) {
           const int s = i % p.stages;
@@ -165,7 +165,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant_
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (issue_lane()) {
         // ===== MMA issuer =====
         for (int i = 0; i < nkb; ++i) {
           const int s = i % p.stages;
@@ -277,7 +277,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (issue_lane()) {
       int it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int m0 = (t % p.ntm) * BM, n0 = (t / p.ntm) * FBN;
@@ -294,7 +294,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (issue_lane()) {
       int it = 0, tc = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tc) {
         const int buf = tc & 1;
