@@ -466,7 +466,7 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
     # data parallel: every rank draws its own sessions (weak scaling); catalog sharding: every rank sees the SAME global
     # batch and scores its slice of the catalog (strong scaling)
     smp = SessionSampler(cfg['V'], seed=123 + (0 if shard else rank))
-    n_batches = 8
+    n_batches = int(os.environ.get('SESSREC_BENCH_BATCHES', '8'))      # experiment knob: 1 = the same batch every step
     host = []
     for _ in range(n_batches):
         items, offs, labels = smp.batch(cfg['B'])
@@ -484,6 +484,7 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
     launches = 0
     enqueue_s = 0.0
     t_wall0 = time.perf_counter()
+    nat0 = list(ops.native_call_s)
     for i in range(args.steps):
         flush.fill_(0)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -497,6 +498,9 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
         evs.append((a, b))
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    if ops.HOST_PROFILE and rank == 0:
+        print(f'[host profile] train_step {1e3 * enqueue_s / args.steps:.4f} ms/step, of which inside the native C call '
+              f'{1e3 * (ops.native_call_s[0] - nat0[0]) / max(1, ops.native_call_s[1] - nat0[1]):.4f} ms', file=sys.stderr)
     clk = clocks.stop()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)

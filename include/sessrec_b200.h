@@ -183,6 +183,8 @@ int srk_expander_combine_bwd(const float* out, const float* rnorm, const float* 
 /* ---- elementwise helpers -------------------------------------------------------------------------------
  * Y = dropout(X) over n elements (flat index = element index); accumulate: Y += dropout_mask * X. */
 int srk_dropout_apply(const float* X, float* Y, long long n, const srk_dropout* drop, int accumulate, void* stream);
+/* Y = dropout(X + A) (Y may alias X or A). */
+int srk_dropout_apply_add(const float* X, const float* A, float* Y, long long n, const srk_dropout* drop, void* stream);
 /* Y = dropout(X) plus its TF32 hi / lo split (Yhi + Ylo == Y exactly; operands of srk_umma_gemm) in one launch. */
 int srk_dropout_apply_split(const float* X, float* Y, float* Yhi, float* Ylo, long long n, const srk_dropout* drop,
                             void* stream);
@@ -326,6 +328,9 @@ typedef struct srk_gat_inst {
 /* wl[h, :] = sum_j attn_l[h, j] W[h*d + j, :], wr likewise: Waug[8d+8, d] = [W ; wl], wr[8, d]. (gatconv.py:285-286
  * reassociated so that el/er come out of the same GEMM as the projection.) */
 int srk_gat_prep(const float* W, const float* attn_l, const float* attn_r, int d, float* Waug, float* wr, void* stream);
+/* the same in one launch together with the TF32 hi / lo split of W_aug (dense [8d + 8, d] each) that srk_umma_gemm reads */
+int srk_gat_prep_split(const float* W, const float* attn_l, const float* attn_r, int d, float* Waug, float* wr, float* Whi,
+                       float* Wlo, void* stream);
 /* dW += dWaug[:8d] + attn_l (x) dwl + attn_r (x) dwr ; dattn_l[h, j] += <W[h*d+j], dwl[h]> ; same for r. */
 int srk_gat_prep_bwd(const float* W, const float* attn_l, const float* attn_r, const float* dWaug, const float* dwr,
                      int d, float* dW, float* dattn_l, float* dattn_r, void* stream);
@@ -413,11 +418,18 @@ int srk_shard_lse_unpack(const float* pack, const float* shift, float bound, int
  * forces it for every step, SESSREC_GRAPH=0 turns it off.  srk_set_graph_mode(0 never / 1 always / 2 auto) overrides the environment; the counters tell how many steps were
  * replayed and how many update passes had to fall back to plain launches. */
 int srk_set_graph_mode(int on);
+/* Whole-step graph: forward, backward and optimizer of a single-rank step (phase 0) as ONE graph.  An update pass leaves a
+ * kernel node alone when its launch configuration and arguments are byte-identical to what the node holds, so with batches
+ * padded to a fixed shape at a fixed address (srk_batch_build_padded) only the nodes that carry the dropout seed / the Adam
+ * step count are rewritten and the host cost of a step is the body's bookkeeping + one cudaGraphLaunch.  mode: 0 never,
+ * 1 always, 2 auto = when the batch header says it is padded (default; SESSREC_GRAPH_WHOLE=0/1 overrides). */
+int srk_set_graph_whole(int mode);
 /* Test hook: the nth_update-th next replay finds a "different kernel sequence" half-way through its update pass and must
  * fall back to plain launches for the backward half (0 = off). */
 int srk_graph_inject_mismatch(int nth_update);
 long long srk_graph_launches(void);
 long long srk_graph_fallbacks(void);
+long long srk_graph_node_updates(void); /* kernel nodes re-parameterised by update passes (unchanged nodes are skipped) */
 long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int d, int L);
 int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
                            const long long* slot_off_host, int V, int d, int L, float dropout_p, uint64_t seed,

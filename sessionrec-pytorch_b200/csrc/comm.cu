@@ -169,6 +169,7 @@ extern "C" int srk_comm_share_rows(float* table, int rows, int d, void* stream) 
 namespace {
 
 __global__ void __launch_bounds__(256) shard_labels_kernel(const int* __restrict__ labels, int B, int lo, int hi, int* __restrict__ out) {
+  SRK_PDL();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     const int l = labels[b];
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(256) shard_labels_kernel(const int* __restrict
 __global__ void __launch_bounds__(256) shard_pack_kernel(const float* __restrict__ lse_local, const float* __restrict__ nll_local,
                                                          const int* __restrict__ labels_local, const float* __restrict__ shift,
                                                          float bound, int B, float* __restrict__ pack) {
+  SRK_PDL();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     const float l = lse_local[b];
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256) shard_pack_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) shard_unpack_kernel(const float* __restrict__ pack, const float* __restrict__ shift, float bound,
                                                            int B, float* __restrict__ lse, float* __restrict__ nll) {
+  SRK_PDL();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     const float l = (shift ? shift[b] : bound) + logf(pack[b]);

@@ -48,16 +48,37 @@ extern long long g_srk_launches;   // kernels launched by this library (bench.py
 // (used to replay only the host-side bookkeeping of a part of the step that has already been enqueued).
 enum { SRK_LAUNCH_DIRECT = 0, SRK_LAUNCH_CAPTURE = 1, SRK_LAUNCH_UPDATE = 2, SRK_LAUNCH_SKIP = 3 };
 int srk_launch_mode();             // of the calling thread
-int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args);
+// blob / blob_bytes: the launch configuration and every argument, byte for byte (only built in capture / update mode): an
+// update pass leaves a kernel node alone when its blob equals the one the node was last given
+int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args,
+                   const unsigned char* blob = nullptr, size_t blob_bytes = 0);
 extern thread_local int g_srk_launch_rc;      // result of the last srk_launch on this thread
 
 #ifdef __CUDACC__
+#include <cstring>
 #include <tuple>
 #include <utility>
+constexpr size_t SRK_BLOB_MAX = 2048;
+template <typename T>
+inline void srk_blob_put(unsigned char* blob, size_t& n, const T& v) {
+  if (n + sizeof(T) <= SRK_BLOB_MAX) memcpy(blob + n, &v, sizeof(T));
+  n += sizeof(T);
+}
 template <typename Tuple, size_t... I>
 inline int srk_launch_packed(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Tuple& pack,
                              std::index_sequence<I...>) {
   void* ptrs[] = {static_cast<void*>(&std::get<I>(pack))...};
+  const int mode = srk_launch_mode();
+  if (mode == SRK_LAUNCH_CAPTURE || mode == SRK_LAUNCH_UPDATE) {
+    unsigned char blob[SRK_BLOB_MAX];
+    size_t n = 0;
+    srk_blob_put(blob, n, grid);
+    srk_blob_put(blob, n, block);
+    srk_blob_put(blob, n, smem);
+    (void)std::initializer_list<int>{(srk_blob_put(blob, n, std::get<I>(pack)), 0)...};
+    // an argument list that does not fit is never treated as unchanged
+    return srk_launch_raw(func, grid, block, smem, st, ptrs, n <= SRK_BLOB_MAX ? blob : nullptr, n <= SRK_BLOB_MAX ? n : 0);
+  }
   return srk_launch_raw(func, grid, block, smem, st, ptrs);
 }
 template <typename... KArgs, typename... Args>
@@ -76,6 +97,7 @@ inline void srk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 
 // stream-ordered zero fill / device copy as kernels (graph-capturable as plain kernel nodes; short-lived CTAs)
 int srk_zero_async(void* p, size_t bytes, cudaStream_t st);
+int srk_zero2_async(void* p0, size_t bytes0, void* p1, size_t bytes1, cudaStream_t st);      // two regions, one launch
 int srk_copy_async(void* dst, const void* src, size_t bytes, cudaStream_t st);
 int srk_zero2d_async(float* C, long long ldc, int rows, int cols, cudaStream_t st);
 
@@ -84,6 +106,21 @@ int srk_zero2d_async(float* C, long long ldc, int rows, int cols, cudaStream_t s
     int r__ = (expr);               \
     if (r__ != SRK_OK) return r__;  \
   } while (0)
+
+// Programmatic dependent launch.  Every kernel of this library starts with SRK_PDL(): griddepcontrol.wait blocks until the
+// kernels this launch depends on have completed and flushed their writes (a no-op for a launch without the attribute);
+// griddepcontrol.launch_dependents then lets the NEXT kernel of the stream be scheduled while this one runs, so that its
+// launch latency and prologue overlap this kernel instead of following it - the training steps are chains of 40-70 dependent
+// kernels of a few microseconds each.  The wait comes first and is executed by every thread before anything else, so a
+// kernel never touches memory before its producers are done, and "kernel N + 1 complete" still implies "kernel N complete".
+// srk_launch() sets cudaLaunchAttributeProgrammaticStreamSerialization (SESSREC_PDL=0 turns it off).
+#ifdef __CUDACC__
+#define SRK_PDL()                                             \
+  do {                                                        \
+    asm volatile("griddepcontrol.wait;" ::: "memory");        \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+#endif
 
 static inline int srk_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_fwd_kernel(const float* __
                                                                  int P, int d, int mode, DropCfg dc,
                                                                  float* __restrict__ X, float* __restrict__ rnorm,
                                                                  float* __restrict__ x_first) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < P; i += warps) {
@@ -77,6 +78,7 @@ template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) gather_tma_kernel(const float* __restrict__ E, const int* __restrict__ iid, int P,
                                                                  int d, int mode, DropCfg dc, int G, float* __restrict__ X,
                                                                  float* __restrict__ rnorm, float* __restrict__ x_first) {
+  SRK_PDL();
   extern __shared__ __align__(128) uint8_t gsm[];
   __shared__ __align__(8) uint64_t bars[ROW_THREADS / 32][2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_bwd_kernel(const float* _
                                                                   const float* __restrict__ dX_first,
                                                                   float* __restrict__ dE, float* __restrict__ ws,
                                                                   int* __restrict__ owner) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int nchunks = (P + chunk - 1) / chunk;
@@ -249,6 +252,7 @@ template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) scatter_fixup_kernel(const int* __restrict__ uoff, const int* __restrict__ uid, int U,
                                                                     int P, int d, int chunk, const float* __restrict__ ws,
                                                                     const int* __restrict__ owner, float* __restrict__ dE) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int nchunks = (P + chunk - 1) / chunk;
@@ -269,6 +273,7 @@ __global__ void __launch_bounds__(ROW_THREADS) scatter_fixup_kernel(const int* _
 template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) renorm_rows_kernel(float* __restrict__ E, const int* __restrict__ uid, int U,
                                                                   int d, float max_norm) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < U; u += warps) {
@@ -289,6 +294,7 @@ __global__ void __launch_bounds__(ROW_THREADS) catalog_prep_fwd_kernel(float* __
                                                                        float* __restrict__ enorm, float* __restrict__ Ehi,
                                                                        float* __restrict__ Elo, uint16_t* __restrict__ Bhi,
                                                                        uint16_t* __restrict__ Blo) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < V; v += warps) {
@@ -320,6 +326,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rownorm_fwd_kernel(const float* _
                                                                   int mode, float* __restrict__ Y, long long ldy,
                                                                   float* __restrict__ rnorm, uint16_t* __restrict__ Bhi,
                                                                   uint16_t* __restrict__ Blo) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -340,6 +347,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rownorm_bwd_kernel(const float* _
                                                                   int d, int mode, float* __restrict__ dX,
                                                                   long long lddx, int accumulate, int nparts,
                                                                   long long part_stride) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -364,6 +372,7 @@ template <int NC>
 __global__ void __launch_bounds__(ROW_THREADS) expander_combine_fwd_kernel(const float* __restrict__ X, const float* __restrict__ h,
                                                                            int N, int k, int d, float* __restrict__ out,
                                                                            float* __restrict__ rnorm) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {
@@ -393,6 +402,7 @@ __global__ void __launch_bounds__(ROW_THREADS) expander_combine_bwd_kernel(const
                                                                            const float* __restrict__ rnorm,
                                                                            const float* __restrict__ dout, int N, int k, int d,
                                                                            float* __restrict__ dh, float* __restrict__ dX) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += warps) {

@@ -231,6 +231,7 @@ template <bool TOPK>
 __global__ void __launch_bounds__(THREADS, 1)
 fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
                const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl, const FceParams p) {
+  SRK_PDL();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full, e_full[MAX_STAGES], e_empty[MAX_STAGES], z_full[2], z_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -424,6 +425,7 @@ fce_fwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
 __global__ void __launch_bounds__(256) fce_finalize_kernel(const float* __restrict__ part, const float* __restrict__ zlab,
                                                            const int* __restrict__ labels, int B, int V, int nparts,
                                                            float* __restrict__ lse, float* __restrict__ nll) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(256) fce_finalize_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) sum_parts_kernel(const float4* __restrict__ parts, long long stride4, int nparts, long long n4,
                                                         float4* __restrict__ out, int accumulate) {
+  SRK_PDL();
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
     float4 a = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -516,6 +519,7 @@ __global__ void __launch_bounds__(THREADS_BWD, 1)
 fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
                const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl,
                const __grid_constant__ CUtensorMap mdE, const __grid_constant__ CUtensorMap mdS, const FceParams p) {
+  SRK_PDL();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full, e_full[MAX_STAGES], e_empty[MAX_STAGES], z_full[2], z_empty[2], d_full, d_empty, de_free;
   __shared__ uint32_t tmem_slot;
@@ -802,6 +806,7 @@ struct WideSched {
 template <bool TOPK>
 __global__ void __launch_bounds__(THREADS, 1)
 fce_fwd_wide_kernel(const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl, const FceWide p) {
+  SRK_PDL();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full, e_full[W_MAX_STAGES], e_empty[W_MAX_STAGES], z_full[2], z_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -994,6 +999,7 @@ __global__ void __launch_bounds__(THREADS_BWD, 1)
 fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ CUtensorMap mSl,
                     const __grid_constant__ CUtensorMap mEh, const __grid_constant__ CUtensorMap mEl,
                     const __grid_constant__ CUtensorMap mdS, const FceWide p) {
+  SRK_PDL();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full, e_full[W_MAX_STAGES], e_empty[W_MAX_STAGES], z_full[2], z_empty[2], d_full, d_empty, de_free;
   __shared__ uint32_t tmem_slot;
@@ -1290,6 +1296,7 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
 
 __global__ void split_bf16_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long ldo) {
+  SRK_PDL();
   const long long total = (long long)rows * cols;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -1493,7 +1500,7 @@ int wide_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long
 
 int wide_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi, const uint16_t* Elo,
              long long lde, float scale, const int* labels, const float* lse, const float* gout, float* dS, float* dEpart,
-             cudaStream_t st) {
+             bool ds_zeroed, cudaStream_t st) {
   FceWide p;
   SRK_TRY(fill_wide(p, B, V, d, scale, labels, true));
   p.lse = lse;
@@ -1521,7 +1528,7 @@ int wide_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long
     SRK_CUDA(cudaFuncSetAttribute(fce_bwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
     attr_set = true;
   }
-  SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
+  if (!ds_zeroed) SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
   srk_launch(fce_bwd_wide_kernel, p.ntm * p.nvr, THREADS_BWD, wide_smem(p, true), st, mSh, mSl, mEh, mEl, mdS, p);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
@@ -1588,6 +1595,7 @@ namespace {
 __global__ void __launch_bounds__(128) fce_topk_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int B,
                                                              int nlists, int K, int* __restrict__ out_idx, float* __restrict__ out_val,
                                                              float scale) {
+  SRK_PDL();
   extern __shared__ float msm[];
   float* v = msm;
   int* ix = reinterpret_cast<int*>(msm + (size_t)nlists * K);
@@ -1662,13 +1670,24 @@ extern "C" int srk_flash_ce_topk(int B, int V, int d, const uint16_t* Shi, const
 
 extern "C" int srk_flash_ce_bwd_parts(int B) { return srk_cdiv(B, TB); }
 
+int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                        const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,
+                        float* dS, float* dEpart, int ds_zeroed, void* stream);
+
 extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds,
                                 const uint16_t* Ehi, const uint16_t* Elo, long long lde, float scale, const int* labels,
                                 const float* lse, const float* gout, float* dS, float* dEpart, void* stream) {
+  return srk_flash_ce_bwd_ex(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, 0, stream);
+}
+
+// ds_zeroed: the caller has zeroed dS already (the native steps zero it with their scratch pool): no memset launch here
+int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                        const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,
+                        float* dS, float* dEpart, int ds_zeroed, void* stream) {
   if (B <= 0) return SRK_OK;
   SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && dS != nullptr && dEpart != nullptr, "flash_ce_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d > 128) return wide_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, st);
+  if (d > 128) return wide_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, ds_zeroed != 0, st);
   FceParams p;
   SRK_TRY(fill_params(p, B, V, d, scale, labels, true));
   p.lse = lse;
@@ -1696,7 +1715,7 @@ extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const 
     SRK_CUDA(cudaFuncSetAttribute(fce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
     attr_set = true;
   }
-  SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
+  if (!ds_zeroed) SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
   srk_launch(fce_bwd_kernel, p.ntm * p.nvr, THREADS_BWD, smem_bytes(p, true), st, mSh, mSl, mEh, mEl, mdE, mdS, p);
   SRK_LAUNCH_CHECK();
   return SRK_OK;

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) gat_agg_fwd_kernel(const GatParams P, int
                                                           const int* __restrict__ node2seg, DropCfg adrop, int normalize,
                                                           float* __restrict__ Hout, float* __restrict__ rnorm,
                                                           uint8_t* __restrict__ amax) {
+  SRK_PDL();
   extern __shared__ float smem[];           // O[H][d]
   __shared__ float red[8];
   const int v = blockIdx.x;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) gat_bwd_dst_kernel(const GatParams P, int
                                                           const float* __restrict__ Hn, const float* __restrict__ rnorm,
                                                           const uint8_t* __restrict__ amax, const float* __restrict__ dH,
                                                           float* __restrict__ dHpre) {
+  SRK_PDL();
   const int v = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ldz = H * d + H;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(256) gat_bwd_src_kernel(const srk_gat_inst I, 
                                                           const float* __restrict__ dHpre,
                                                           const uint8_t* __restrict__ amax, float* __restrict__ Zhi,
                                                           float* __restrict__ Zlo) {
+  SRK_PDL();
   const int u = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ldz = H * d + H;
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(256) gat_bwd_src_kernel(const srk_gat_inst I, 
 
 __global__ void __launch_bounds__(256) gat_bias_bwd_kernel(const float* __restrict__ dHpre, const uint8_t* __restrict__ amax,
                                                            int N, int d, int rows_per_block, float* __restrict__ dbias) {
+  SRK_PDL();
   __shared__ float red[8][H][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(256) gat_bias_bwd_kernel(const float* __restri
 template <int NC>
 __global__ void __launch_bounds__(256) segmean_fwd_kernel(const float* __restrict__ X, const int* __restrict__ seg, int B,
                                                           int d, float* __restrict__ mean) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
@@ -267,6 +272,7 @@ __global__ void __launch_bounds__(256) segmean_fwd_kernel(const float* __restric
 template <int NC>
 __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restrict__ dHpre, const int* __restrict__ seg,
                                                           int B, int d, float* __restrict__ dX, int accumulate) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
@@ -289,10 +295,19 @@ __global__ void __launch_bounds__(256) segmean_bwd_kernel(const float* __restric
   }
 }
 
-// Waug rows 8d..8d+7 (wl) and wr[8, d]: CTA per (head, 32-column tile); 8 row groups x 32 columns, smem reduce.
+// W_aug = [W ; wl] (rows 8d..8d+7 = a_l contracted with W) and wr[8, d], optionally together with the TF32 hi / lo split of
+// W_aug the tensor-core projection reads: CTA per (head, 32-column tile); 8 row groups x 32 columns, smem reduce.  One launch
+// instead of copy + contraction + split.
+__device__ __forceinline__ void tf32_split_store(float x, float* hi, float* lo, long long at) {
+  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  hi[at] = h;
+  lo[at] = x - h;
+}
 __global__ void __launch_bounds__(256) gat_prep_kernel(const float* __restrict__ W, const float* __restrict__ al,
                                                        const float* __restrict__ ar, int d, float* __restrict__ Waug,
-                                                       float* __restrict__ wr) {
+                                                       float* __restrict__ wr, float* __restrict__ Whi,
+                                                       float* __restrict__ Wlo) {
+  SRK_PDL();
   __shared__ float red[2][8][33];
   const int h = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -300,7 +315,10 @@ __global__ void __launch_bounds__(256) gat_prep_kernel(const float* __restrict__
   float sl = 0.f, sr = 0.f;
   if (i < d)
     for (int j = ty; j < d; j += 8) {
-      const float w = W[(long long)(h * d + j) * d + i];
+      const long long at = (long long)(h * d + j) * d + i;
+      const float w = W[at];
+      Waug[at] = w;
+      if (Whi) tf32_split_store(w, Whi, Wlo, at);
       sl = fmaf(al[h * d + j], w, sl);
       sr = fmaf(ar[h * d + j], w, sr);
     }
@@ -313,7 +331,9 @@ __global__ void __launch_bounds__(256) gat_prep_kernel(const float* __restrict__
       sl += red[0][k][tx];
       sr += red[1][k][tx];
     }
-    Waug[(long long)(H * d + h) * d + i] = sl;
+    const long long at = (long long)(H * d + h) * d + i;
+    Waug[at] = sl;
+    if (Whi) tf32_split_store(sl, Whi, Wlo, at);
     wr[h * d + i] = sr;
   }
 }
@@ -323,6 +343,7 @@ __global__ void __launch_bounds__(256) gat_prep_bwd_kernel(const float* __restri
                                                            const float* __restrict__ ar, const float* __restrict__ dWaug,
                                                            const float* __restrict__ dwr, int d, float* __restrict__ dW,
                                                            float* __restrict__ dal, float* __restrict__ dar) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < H * d; r += warps) {
@@ -360,14 +381,18 @@ int fill_params(GatParams& P, const srk_gat_inst* inst_host, int n_inst) {
 
 }  // namespace
 
-extern "C" int srk_gat_prep(const float* W, const float* attn_l, const float* attn_r, int d, float* Waug, float* wr,
-                            void* stream) {
+extern "C" int srk_gat_prep_split(const float* W, const float* attn_l, const float* attn_r, int d, float* Waug, float* wr,
+                                  float* Whi, float* Wlo, void* stream) {
   SRK_TRY(srk_check_dim(d));
-  cudaStream_t st = (cudaStream_t)stream;
-  SRK_TRY(srk_copy_async(Waug, W, sizeof(float) * (size_t)H * d * d, st));
-  srk_launch(gat_prep_kernel, dim3(srk_cdiv(d, 32), H), 256, 0, st, W, attn_l, attn_r, d, Waug, wr);
+  SRK_REQUIRE((Whi == nullptr) == (Wlo == nullptr), "gat_prep: pass both halves of the TF32 split or neither");
+  srk_launch(gat_prep_kernel, dim3(srk_cdiv(d, 32), H), 256, 0, (cudaStream_t)stream, W, attn_l, attn_r, d, Waug, wr, Whi, Wlo);
   SRK_LAUNCH_CHECK();
   return SRK_OK;
+}
+
+extern "C" int srk_gat_prep(const float* W, const float* attn_l, const float* attn_r, int d, float* Waug, float* wr,
+                            void* stream) {
+  return srk_gat_prep_split(W, attn_l, attn_r, d, Waug, wr, nullptr, nullptr, stream);
 }
 
 extern "C" int srk_gat_prep_bwd(const float* W, const float* attn_l, const float* attn_r, const float* dWaug,

@@ -105,6 +105,7 @@ struct GemmParams {
 };
 
 __global__ void __launch_bounds__(NT) sgemm_kernel(const GemmParams p) {
+  SRK_PDL();
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const GemmArgs& g = p.g;
@@ -177,6 +178,7 @@ constexpr int SS_MAXK = 256;
 constexpr int SS_BATCH = 8;          // k-tiles (of 16) loaded per register batch
 
 __global__ void __launch_bounds__(NT) sgemm_singleshot_kernel(const GemmParams p) {
+  SRK_PDL();
   extern __shared__ __align__(16) float ss_smem[];
   const GemmArgs& g = p.g;
   const int tid = threadIdx.x;
@@ -335,6 +337,7 @@ __device__ __forceinline__ void small_load(float (*S)[SB + SPAD], const float* _
 }
 
 __global__ void __launch_bounds__(NT) sgemm_small_kernel(const GemmParams p) {
+  SRK_PDL();
   __shared__ __align__(16) float As[SKMAX + 4][SB + SPAD];
   __shared__ __align__(16) float Bs[SKMAX + 4][SB + SPAD];
   const GemmArgs& g = p.g;

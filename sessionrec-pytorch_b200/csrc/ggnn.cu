@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) ggnn_agg_fwd_kernel(const float* __restri
                                                            const int* __restrict__ out_dst, const int* __restrict__ out_eid,
                                                            const float* __restrict__ w, float* __restrict__ NN,
                                                            float* __restrict__ wsum) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < N; v += warps) {
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) ggnn_agg_bwd_kernel(const float* __restri
                                                            const int* __restrict__ out_dst, const int* __restrict__ out_eid,
                                                            const float* __restrict__ w, const float* __restrict__ wsum,
                                                            float* __restrict__ dX, int accumulate) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < N; u += warps) {
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256) ggnn_agg_bwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) gru_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
                                                       const float* __restrict__ h, long long total, int d,
                                                       float* __restrict__ hnew) {
+  SRK_PDL();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     long long i = t / d;
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(256) gru_fwd_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) gru_bwd_kernel(float* __restrict__ gi, float* __restrict__ gh,
                                                       const float* __restrict__ h, const float* __restrict__ dhnew,
                                                       long long total, int d, float* __restrict__ dh, int accumulate) {
+  SRK_PDL();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     long long i = t / d;

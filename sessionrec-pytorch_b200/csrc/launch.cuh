@@ -8,6 +8,7 @@
 struct SrkGraphNode {
   cudaGraphNode_t node;
   const void* func;
+  std::vector<unsigned char> blob;      // launch configuration + arguments the node holds now (empty: unknown)
 };
 
 struct SrkStepGraph {
@@ -32,6 +33,10 @@ struct SrkLaunchCtx {
   int mode_after_boundary = SRK_LAUNCH_DIRECT;
   cudaStream_t capture_stream = nullptr;
   bool capturing = false;
+  // whole-step graph: the capture / update mode starts at srk_step_begin() (first launch of the step) instead of at the
+  // forward / backward boundary
+  bool whole = false;
+  size_t updated = 0;                   // update pass: nodes whose parameters had to be rewritten
   size_t fail_at = (size_t)-1;          // test hook: pretend the kernel sequence differs at this node
   // why the pass failed (SESSREC_GRAPH_DEBUG): 1 more launches than nodes, 2 other kernel, 3 test hook, 4 node update
   // refused (fail_cuda = the CUDA error), 5 launch outside the capture

@@ -21,6 +21,7 @@ namespace {
 
 __global__ void dropout_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, long long n, DropCfg dc,
                                      int accumulate) {
+  SRK_PDL();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float v = X[i] * drop_mul(dc, (uint64_t)i);
@@ -28,9 +29,19 @@ __global__ void dropout_apply_kernel(const float* __restrict__ X, float* __restr
   }
 }
 
+// Y = dropout(X + A): the residual add of the GAT destination-copy gradient folded into the mask pass
+__global__ void dropout_add_kernel(const float* __restrict__ X, const float* __restrict__ A, float* __restrict__ Y, long long n,
+                                   DropCfg dc) {
+  SRK_PDL();
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    Y[i] = (X[i] + A[i]) * drop_mul(dc, (uint64_t)i);
+}
+
 // Y = dropout(X) together with its TF32 hi / lo split (operands of the tensor-core projection that consumes Y)
 __global__ void dropout_split_kernel(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ Yhi,
                                      float* __restrict__ Ylo, long long n, DropCfg dc) {
+  SRK_PDL();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = X[i] * drop_mul(dc, (uint64_t)i);
@@ -42,6 +53,7 @@ __global__ void dropout_split_kernel(const float* __restrict__ X, float* __restr
 }
 
 __global__ void fill_kernel(float* __restrict__ X, long long n, float value) {
+  SRK_PDL();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) X[i] = value;
 }
@@ -49,6 +61,7 @@ __global__ void fill_kernel(float* __restrict__ X, long long n, float value) {
 template <int NC>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ X, const int* __restrict__ idx, int R,
                                                           int d, float* __restrict__ Y, long long ldy) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -63,6 +76,7 @@ template <int NC>
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ X, long long ldx,
                                                                const int* __restrict__ idx, int R, int d,
                                                                float* __restrict__ Y) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -74,6 +88,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, long long ldx, int R, int d,
                                                      int rows_per_block, float* __restrict__ out) {
+  SRK_PDL();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -92,6 +107,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 }
 
 __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  SRK_PDL();
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
@@ -124,6 +140,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    const long long* __restrict__ seg_off, const float* __restrict__ seg_decay,
                                                    int n_seg, float lr, float b1, float b2, float eps, float bc1,
                                                    float bc2_sqrt, float grad_scale) {
+  SRK_PDL();
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int lo = 0, hi = n_seg - 1;           // segment of element i (seg_off ascending, seg_off[n_seg] == n)
@@ -161,6 +178,7 @@ __global__ void __launch_bounds__(256) adam_split_kernel(float* __restrict__ p, 
                                                          const int* __restrict__ rows_sorted, int n_rows, int part, float lr,
                                                          float b1, float b2, float eps, float bc1, float bc2_sqrt,
                                                          float grad_scale) {
+  SRK_PDL();
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (part == 0) {
     // one float4 per thread and NO grid-stride loop: this launch runs beside latency-critical kernels on higher-priority
@@ -233,6 +251,13 @@ extern "C" int srk_dropout_apply(const float* X, float* Y, long long n, const sr
                                  void* stream) {
   if (n <= 0) return SRK_OK;
   srk_launch(dropout_apply_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, X, Y, n, make_drop(drop), accumulate);
+  SRK_LAUNCH_CHECK();
+  return SRK_OK;
+}
+
+extern "C" int srk_dropout_apply_add(const float* X, const float* A, float* Y, long long n, const srk_dropout* drop, void* stream) {
+  if (n <= 0) return SRK_OK;
+  srk_launch(dropout_add_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, X, A, Y, n, make_drop(drop));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

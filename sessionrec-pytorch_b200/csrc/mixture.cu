@@ -35,6 +35,7 @@ __device__ __forceinline__ void mix_weights(const MixArgs& m, float* a, float* l
 }
 
 __global__ void __launch_bounds__(512) mix_logp_kernel(MixArgs m, float* __restrict__ out, long long ldo) {
+  SRK_PDL();
   const int b = blockIdx.x;
   float wa[MAXK], wl[MAXK];
   mix_weights(m, wa, wl);
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(512) mix_logp_kernel(MixArgs m, float* __restr
 
 // loss[b] = -log sum_k a_k exp(-nll_k[b]); mean over b.  Single CTA.
 __global__ void __launch_bounds__(1024) mix_loss_kernel(const float* __restrict__ nll, MixArgs m, float* __restrict__ out) {
+  SRK_PDL();
   __shared__ float red[32];
   float wa[MAXK], wl[MAXK];
   mix_weights(m, wa, wl);
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(1024) mix_loss_kernel(const float* __restrict_
 __global__ void __launch_bounds__(512) mix_bwd_kernel(MixArgs m, const float* __restrict__ G, long long ldg,
                                                       const int* __restrict__ labels, const float* __restrict__ gscale,
                                                       float scale, float* __restrict__ rsum) {
+  SRK_PDL();
   __shared__ float red[MAXK][16];
   __shared__ float rk[MAXK];
   const int b = blockIdx.x;
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(512) mix_bwd_kernel(MixArgs m, const float* __
 // d alpha_j += a_j (da_j - sum_k a_k da_k),  da_k = (sum_b rsum[k][b]) / a_k.  Single CTA.
 __global__ void __launch_bounds__(256) mix_alpha_bwd_kernel(const float* __restrict__ rsum, MixArgs m,
                                                             float* __restrict__ dalpha) {
+  SRK_PDL();
   __shared__ float tot[MAXK];
   __shared__ float red[MAXK][8];
   float wa[MAXK], wl[MAXK];

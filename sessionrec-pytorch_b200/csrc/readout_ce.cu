@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) readout_fwd_kernel(const float* __restric
                                                           const int* __restrict__ seg, const int* __restrict__ last, int B,
                                                           int d, int with_last, float* __restrict__ e,
                                                           float* __restrict__ ms, float* __restrict__ sr_in) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   RowVec<NC> wev;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float* __restric
                                                           const float* __restrict__ dsr_in, int B, int d,
                                                           int with_last, float* __restrict__ dF,
                                                           float* __restrict__ dwe) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   RowVec<NC> wev, dwe_acc;
@@ -186,6 +188,7 @@ __device__ __forceinline__ MS block_lse(const float* z, int V, MS* red) {
 __global__ void __launch_bounds__(512) ce_rows_fwd_kernel(float* __restrict__ Z, long long ldz, const int* __restrict__ labels,
                                                           int V, int write_logp, float* __restrict__ lse,
                                                           float* __restrict__ nll) {
+  SRK_PDL();
   __shared__ MS red[16];
   float* z = Z + (long long)blockIdx.x * ldz;
   MS r = block_lse(z, V, red);
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(512) ce_rows_bwd_kernel(float* __restrict__ Z,
                                                           const float* __restrict__ lse, const float* __restrict__ gscale,
                                                           float scale, int B, int V, int z_is_logp,
                                                           float* __restrict__ Zlo, int col0) {
+  SRK_PDL();
   // columns [col0, col0 + V) of every row (col0 = 0, V = catalog size for the whole matrix)
   float* z = Z + (long long)blockIdx.x * ldz + col0;
   float* zl = Zlo ? Zlo + (long long)blockIdx.x * ldz + col0 : nullptr;
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(512) ce_rows_bwd_kernel(float* __restrict__ Z,
 __global__ void __launch_bounds__(512) logp_bwd_kernel(const float* __restrict__ LP, long long ldlp,
                                                        const float* __restrict__ G, long long ldg, float scale, int V,
                                                        float* __restrict__ DZ, long long lddz, float* __restrict__ DZlo) {
+  SRK_PDL();
   __shared__ float red[16];
   __shared__ float total;
   const float* lp = LP + (long long)blockIdx.x * ldlp;
@@ -301,6 +306,7 @@ __device__ __forceinline__ void store_split(float* dz, float* dzl, long long j, 
 __global__ void __launch_bounds__(512) renorm_head_fwd_kernel(float* Z, long long ldz, int V, const int* __restrict__ iid,
                                                               const int* __restrict__ seg, const float* __restrict__ lphi,
                                                               float* __restrict__ zin) {
+  SRK_PDL();
   __shared__ MS red_in[16];
   __shared__ MS red_ex[16];
   float* z = Z + (long long)blockIdx.x * ldz;
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(512) renorm_head_bwd_kernel(const float* LP, l
                                                               const int* __restrict__ seg, const float* __restrict__ lphi,
                                                               float* __restrict__ tmp, float* DZ, long long lddz, float* DZlo,
                                                               float* __restrict__ dlphi) {
+  SRK_PDL();
   __shared__ float red[2][16];
   __shared__ float tot[2];
   const float* lp = LP + (long long)blockIdx.x * ldlp;
@@ -400,6 +407,7 @@ __global__ void __launch_bounds__(512) renorm_head_bwd_kernel(const float* LP, l
 // Warp per session; H is rewritten with relu(h), lphi[b, :] = log phi.
 __global__ void __launch_bounds__(256) gate_fwd_kernel(float* __restrict__ H, const float* __restrict__ W2, int B, int d,
                                                        float* __restrict__ lphi) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.x * (blockDim.x >> 5)) {
     float* h = H + (long long)b * d;
@@ -425,6 +433,7 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(float* __restrict__ H, co
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ Hr, const float* __restrict__ W2,
                                                        const float* __restrict__ lphi, const float* __restrict__ dlphi, int B,
                                                        int d, float* __restrict__ da, float* __restrict__ dH) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   for (int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += gridDim.x * (blockDim.x >> 5)) {
     const float g0 = dlphi[2 * b], g1 = dlphi[2 * b + 1];

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(RT_THREADS) readout_tail_fwd_kernel(
     const float* __restrict__ WsrT, const int* __restrict__ seg, const int* __restrict__ last, int B, int d, int norm_mode,
     float* __restrict__ e, float* __restrict__ ms, float* __restrict__ sr_in, float* __restrict__ s, float* __restrict__ shat,
     float* __restrict__ rn_s, uint16_t* __restrict__ sbh, uint16_t* __restrict__ sbl) {
+  SRK_PDL();
   extern __shared__ float xsm[];                    // [warps][2 d]
   const int lane = threadIdx.x & 31;
   float* xs = xsm + (threadIdx.x >> 5) * 2 * d;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(RT_THREADS) readout_head_bwd_kernel(
     const float* __restrict__ rn_s, const float* __restrict__ sr_in, const float* __restrict__ e, const float* __restrict__ ms,
     const float* __restrict__ dshat, float* __restrict__ u, float* __restrict__ v, float* __restrict__ ds, float* __restrict__ dF,
     float* __restrict__ dwe) {
+  SRK_PDL();
   extern __shared__ float xsm[];                    // [warps][d]
   const int lane = threadIdx.x & 31;
   float* xs = xsm + (threadIdx.x >> 5) * d;
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(RT_THREADS) readout_head_bwd_kernel(
 }
 
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ X, int rows, int cols, float* __restrict__ Y) {
+  SRK_PDL();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {

@@ -111,6 +111,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
   fl += 8LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
   fl += (long long)L * 2 * (2 * ldzel * d + 2LL * N * d) + 2 * (2LL * N * ldzel);     // opt-in tensor-core projections: hi / lo copies
+  fl += (long long)L * 2 * (ldzel * d + (long long)H * d + (long long)N * d + 192) + 2LL * B * d + 192;      // zeroed pool
   return fl * 5 + (1 << 20);                               // floats -> bytes with 25% head-room + alignment slack
 }
 
@@ -177,9 +178,16 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   cudaStream_t s2 = ss ? ss->s[4] : st, s3 = ss ? ss->s[5] : st, s4 = ss ? ss->s[6] : st;
   cudaStream_t s1 = h1;
   auto order = [&](cudaStream_t from, cudaStream_t to) { return ss ? ss->order(from, to) : (int)SRK_OK; };
-  // zero_grad runs beside the forward pass; the first gradient is written after the head's backward
+  SRK_TRY(srk_step_begin());
+  // zero_grad runs beside the forward pass; the first gradient is written after the head's backward.  Every scratch buffer of
+  // the step that is accumulated into (split-K GEMM outputs, staged weight gradients, dS of the fused head) comes from ONE
+  // pool that the same launch zeroes: 8 zero-fill launches less per step, three of them on the critical path.
+  const size_t zp_bytes = sizeof(float) * ((size_t)L * 2 * ((size_t)ldzel * d + (size_t)H * d + (size_t)N * d + 192) +
+                                            2 * (size_t)b.B * d + 192);
+  Arena zp{ar.raw(zp_bytes), zp_bytes, 0, true};
+  SRK_REQUIRE(ar.ok, "step: workspace too small");
   SRK_TRY(order(st, s4));
-  SRK_TRY(srk_zero_async(grads, sizeof(float) * (size_t)n_flat, s4));
+  SRK_TRY(srk_zero2_async(grads, sizeof(float) * (size_t)n_flat, zp.base, zp_bytes, s4));
   tm.mark("zero_grad");
 
   // ---- forward -------------------------------------------------------------------------------------------
@@ -236,14 +244,13 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       I.wr = ar.f((size_t)H * d);
       SRK_REQUIRE(ar.ok, "step: workspace too small");
       cudaStream_t ps = c == 0 ? s2 : s3;
-      SRK_TRY(srk_gat_prep(I.W, I.al, I.ar, d, I.Waug, I.wr, ps));
       I.Wh = I.Wl = nullptr;
       if (tc_enc) {
         I.Wh = ar.f((size_t)ldzel * d);
         I.Wl = ar.f((size_t)ldzel * d);
         SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(srk_split_tf32(I.Waug, d, ldzel, d, I.Wh, I.Wl, d, ps));
       }
+      SRK_TRY(srk_gat_prep_split(I.W, I.al, I.ar, d, I.Waug, I.wr, I.Wh, I.Wl, ps));      // one launch incl. the TF32 split
     }
   }
   // W_sr^T for the fused read-out tail (the lanes read consecutive output columns)
@@ -343,7 +350,7 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   tm.mark("gat_fwd");
   const float* F = h;
   float *u = ar.f((size_t)N * d), *v = ar.f((size_t)B * d), *e = ar.f(N), *ms = ar.f(2 * (size_t)B);
-  float *sr_in = ar.f(2 * (size_t)B * d), *s = ar.f((size_t)B * d), *shat = ar.f((size_t)B * d), *rn_s = ar.f(B);
+  float *sr_in = ar.f(2 * (size_t)B * d), *s = fused_ro ? ar.f((size_t)B * d) : zp.f((size_t)B * d), *shat = ar.f((size_t)B * d), *rn_s = ar.f(B);
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   uint16_t *Sbh = nullptr, *Sbl = nullptr;
   if (flash) {
@@ -361,7 +368,8 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
                                  Sbl, st));
   } else {
     SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, 1, e, ms, sr_in, st));
-    SRK_TRY(linear_nt(st, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), s, d));
+    // s comes zeroed from the pool: the split-K accumulate path without the zero launch srk_gemm would put in front
+    SRK_TRY(gemm(st, B, d, 2 * d, sr_in, 2 * d, 1, P(s_ro + 4), 1, 2 * d, s, d, nullptr, nullptr, nullptr, nullptr, 1.f, 1));
     if (flash) SRK_TRY(srk_rownorm_split_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, Sbh, Sbl, st));
     else SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_L2, shat, d, rn_s, st));
   }
@@ -416,10 +424,11 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   // ---- backward ------------------------------------------------------------------------------------------
   const int de_parts = flash ? srk_flash_ce_bwd_parts(B) : 1;
   float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;
-  float *dshat = shard ? dshat_x : ar.f((size_t)B * d), *dEhat = ar.f((size_t)de_parts * Vl * d);
-  SRK_REQUIRE(ar.ok, "step: workspace too small");
+  const bool ds_pooled = flash && !shard;       // dS accumulates (TMA reduce-add): zeroed with the pool
+  float *dshat = shard ? dshat_x : (ds_pooled ? zp.f((size_t)B * d) : ar.f((size_t)B * d)), *dEhat = ar.f((size_t)de_parts * Vl * d);
+  SRK_REQUIRE(ar.ok && zp.ok, "step: workspace too small");
   if (flash) {
-    SRK_TRY(srk_flash_ce_bwd(B, Vl, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, hlabels, lse, one_dev, dshat, dEhat, st));
+    SRK_TRY(srk_flash_ce_bwd_ex(B, Vl, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, hlabels, lse, one_dev, dshat, dEhat, ds_pooled, st));
   } else if (umma) {
     SRK_TRY(srk_zero_async(dshat, sizeof(float) * (size_t)B * d, st));
     // Backward of the head, chunked over catalog columns so that each chunk's dZ hi/lo pair (2 x B x Vc x 4 bytes) is
@@ -546,11 +555,9 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       SRK_TRY(order(zs, wsc));
       // weight gradients
       SRK_TRY(srk_gat_bias_bwd(dHpre, R.amax, N, d, I.gbias, wsc));
-      float* dWaug = ar.f((size_t)ldzel * d);
-      float* dwr = ar.f((size_t)H * d);
-      SRK_REQUIRE(ar.ok, "step: workspace too small");
-      SRK_TRY(srk_zero_async(dWaug, sizeof(float) * (size_t)ldzel * d, wsc));
-      SRK_TRY(srk_zero_async(dwr, sizeof(float) * (size_t)H * d, wsc));
+      float* dWaug = zp.f((size_t)ldzel * d);      // zeroed with the pool
+      float* dwr = zp.f((size_t)H * d);
+      SRK_REQUIRE(zp.ok, "step: zero pool too small");
       if (tc_enc) {                               // dW_aug[8d + 8, d] = dZel^T x_s, split over the N rows
         int split = 148 / ((ldzel + 127) / 128);
         SRK_TRY(srk_umma_gemm(2, ldzel, d, N, zh, zl, ldzel, I.xh, I.xl, d, dWaug, d, 1.0f, 1, split < 1 ? 1 : split, wsc));
@@ -560,26 +567,25 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
       SRK_TRY(mm_tn(wsc, H, d, N, der[c], H, I.xd, d, dwr, d));
       SRK_TRY(srk_gat_prep_bwd(I.W, I.al, I.ar, dWaug, dwr, d, I.gW, I.gal, I.gar, wsc));
       // data gradients
-      auto dz_times_waug = [&](float* out) -> int {          // out[N, d] = dZel[N, 8d + 8] W_aug[8d + 8, d]
+      auto dz_times_waug = [&](float* out, bool out_zeroed) -> int {          // out[N, d] = dZel[N, 8d + 8] W_aug[8d + 8, d]
         if (!tc_enc) return mm_nn(zs, N, d, ldzel, dZel[c], ldzel, I.Waug, d, out, d, 0);
-        SRK_TRY(srk_zero_async(out, sizeof(float) * (size_t)N * d, zs));
+        if (!out_zeroed) SRK_TRY(srk_zero_async(out, sizeof(float) * (size_t)N * d, zs));
         int split = 148 / ((N + 127) / 128);
         if (split < 1) split = 1;
         return srk_umma_gemm(1, N, d, ldzel, zh, zl, ldzel, I.Wh, I.Wl, d, out, d, 1.0f, 1, split, zs);
       };
       if (!I.drop) {
-        SRK_TRY(dz_times_waug(pz));
+        SRK_TRY(dz_times_waug(pz, false));
         SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, pe, d, 0));
         SRK_TRY(srk_dropout_apply(dHpre, pe, (long long)nd, nullptr, 1, es));            // residual
       } else {
-        float* tmp = ar.f(nd);
+        float* tmp = tc_enc ? zp.f(nd) : ar.f(nd);      // split-K accumulation target: zeroed with the pool
         float* tmp2 = ar.f(nd);
-        SRK_REQUIRE(ar.ok, "step: workspace too small");
-        SRK_TRY(dz_times_waug(tmp));
+        SRK_REQUIRE(ar.ok && zp.ok, "step: workspace too small");
+        SRK_TRY(dz_times_waug(tmp, tc_enc));
         SRK_TRY(srk_dropout_apply(tmp, pz, (long long)nd, &I.dcs, 0, zs));
-        SRK_TRY(srk_copy_async(tmp2, dHpre, sizeof(float) * nd, es));
-        SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, tmp2, d, 1));
-        SRK_TRY(srk_dropout_apply(tmp2, pe, (long long)nd, &I.dcd, 0, es));
+        SRK_TRY(mm_nn(es, N, d, H, der[c], H, I.wr, d, tmp2, d, 0));
+        SRK_TRY(srk_dropout_apply_add(dHpre, tmp2, pe, (long long)nd, &I.dcd, es));       // mask(residual + der w_r)
       }
     }
     SRK_TRY(order(h1, st));
@@ -648,6 +654,7 @@ namespace {
 
 int g_graphs_on = -1;                  // -1: read SESSREC_GRAPH on first use; 0 never, 1 always, 2 auto (data-parallel steps)
 long long g_graph_launches = 0;        // steps issued as one cudaGraphLaunch
+long long g_graph_node_updates = 0;
 long long g_graph_fallbacks = 0;       // update passes that found a different kernel sequence
 int g_inject_mismatch = 0;             // test hook: the n-th next update pass is made to fail half-way (0 = off)
 
@@ -659,14 +666,24 @@ struct GraphEntry {
 
 }  // namespace
 
-int srk_step_boundary() {
-  if (SrkLaunchCtx* lc = srk_get_launch_ctx()) {
-    if (lc->mode_after_boundary == SRK_LAUNCH_CAPTURE) {
-      SRK_CUDA(cudaStreamBeginCapture(lc->capture_stream, cudaStreamCaptureModeThreadLocal));
-      lc->capturing = true;
-    }
-    lc->mode = lc->mode_after_boundary;
+static int switch_launch_mode(SrkLaunchCtx* lc) {
+  if (lc->mode == lc->mode_after_boundary) return SRK_OK;
+  if (lc->mode_after_boundary == SRK_LAUNCH_CAPTURE) {
+    SRK_CUDA(cudaStreamBeginCapture(lc->capture_stream, cudaStreamCaptureModeThreadLocal));
+    lc->capturing = true;
   }
+  lc->mode = lc->mode_after_boundary;
+  return SRK_OK;
+}
+
+// first call of a step body: a whole-step graph starts here
+int srk_step_begin() {
+  SrkLaunchCtx* lc = srk_get_launch_ctx();
+  return lc && lc->whole ? switch_launch_mode(lc) : (int)SRK_OK;
+}
+
+int srk_step_boundary() {
+  if (SrkLaunchCtx* lc = srk_get_launch_ctx()) return switch_launch_mode(lc);
   return SRK_OK;
 }
 
@@ -675,7 +692,8 @@ int srk_step_boundary() {
 // warm-up steps the sequence is therefore captured ONCE into a CUDA graph (per model configuration `key`); every later
 // step only rewrites the kernel-node parameters (shapes and pointers change with the batch, the sequence does not) and
 // issues one cudaGraphLaunch.  SESSREC_GRAPH=0 disables it; any mismatch falls back to plain launches for that step.
-int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body_on) {
+int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body_on,
+                    bool whole) {
   // The step runs on our own high-priority stream s[0] (the user's stream may be the legacy default stream, which can
   // neither be prioritised nor captured); it is ordered after / before the user's stream with events.
   SideStreams* ss0 = srk_side_streams();
@@ -701,6 +719,7 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
   SrkLaunchCtx ctx;
   ctx.g = &e.g;
   ctx.capture_stream = run;
+  ctx.whole = whole;
   const bool capture = e.g.exec == nullptr;
   ctx.mode_after_boundary = capture ? SRK_LAUNCH_CAPTURE : SRK_LAUNCH_UPDATE;
   if (!capture && g_inject_mismatch > 0 && --g_inject_mismatch == 0) ctx.fail_at = e.g.nodes.size() / 2;
@@ -729,6 +748,8 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
     }
   } else {
     ok = ok && ctx.cursor == e.g.nodes.size();
+    g_graph_node_updates += (long long)ctx.updated;
+    if (debug && ok) fprintf(stderr, "[sessrec graph] replay: %zu of %zu nodes rewritten\n", ctx.updated, e.g.nodes.size());
     if (!ok) {
       ++g_graph_fallbacks;
       if (debug)
@@ -748,7 +769,7 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
     // The forward half is already enqueued.  Re-run the step's bookkeeping with the forward launches dropped and launch
     // the backward half kernel by kernel.
     SrkLaunchCtx redo;
-    redo.mode = SRK_LAUNCH_SKIP;
+    redo.mode = whole ? SRK_LAUNCH_DIRECT : SRK_LAUNCH_SKIP;     // whole-step graph: nothing has been enqueued yet
     redo.mode_after_boundary = SRK_LAUNCH_DIRECT;
     srk_set_launch_ctx(&redo);
     rc = body_on_run();
@@ -762,6 +783,21 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
 }
 
 // 0 never, 1 always, 2 auto (data-parallel steps: phase 1)
+// whole-step graph (forward + backward + optimizer as ONE graph): single-rank steps with the optimizer inside (phase 0).
+// SESSREC_GRAPH_WHOLE=1 always, =0 never; default: when the batch says it was padded to a fixed shape (header word 11).
+bool srk_step_want_graph(int phase);
+static int g_whole_mode = -1;
+bool srk_step_want_whole(int phase, int padded) {
+  int& mode = g_whole_mode;
+  if (mode < 0) {
+    const char* e = getenv("SESSREC_GRAPH_WHOLE");
+    mode = !e ? 2 : (e[0] == '0' ? 0 : 1);
+  }
+  (void)srk_step_want_graph(phase);      // reads SESSREC_GRAPH on first use
+  if (phase != 0 || g_graphs_on == 0) return false;
+  return mode == 1 || (mode == 2 && padded != 0);
+}
+
 bool srk_step_want_graph(int phase) {
   if (g_graphs_on < 0) {
     const char* e = getenv("SESSREC_GRAPH");
@@ -796,15 +832,21 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
                                  ((unsigned long long)(dropout_p > 0.f) << 4) | ((unsigned long long)(phase & 1) << 3) | ((unsigned long long)(use_umma & 8) << 60) |
                                  ((unsigned long long)(do_adam != 0) << 2) | ((unsigned long long)has_edges << 1) |
                                  (unsigned long long)(head_chunks > 1);
-  return srk_step_driver(caller, key, srk_step_want_graph(phase), [&](void* run) {
+  const bool whole = srk_step_want_whole(phase, batch_hdr_host[11]);
+  return srk_step_driver(caller, key ^ ((unsigned long long)whole << 63), srk_step_want_graph(phase) || whole, [&](void* run) {
     return step_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, dropout_p, seed, use_umma, workspace,
                      workspace_bytes, one_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg,
                      lr, beta1, beta2, eps, adam_step, grad_scale, phase, head_chunks, run);
-  });
+  }, whole);
 }
 
 extern "C" int srk_set_graph_mode(int on) {
   g_graphs_on = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 never, 1 always, 2 auto (data-parallel steps only)
+  return SRK_OK;
+}
+
+extern "C" int srk_set_graph_whole(int mode) {
+  g_whole_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);      // 0 never, 1 always, 2 auto (batches padded to a fixed shape)
   return SRK_OK;
 }
 
@@ -814,4 +856,5 @@ extern "C" int srk_graph_inject_mismatch(int nth_update) {
 }
 
 extern "C" long long srk_graph_launches(void) { return g_graph_launches; }
+extern "C" long long srk_graph_node_updates(void) { return g_graph_node_updates; }
 extern "C" long long srk_graph_fallbacks(void) { return g_graph_fallbacks; }

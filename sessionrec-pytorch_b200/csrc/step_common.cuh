@@ -132,7 +132,18 @@ SideStreams* srk_side_streams();
 // its forward / backward boundary (srk_step_boundary) - on the step's own high-priority stream, ordered after / before
 // `caller`.  want_graph: after two warm-up steps per `key` the backward half is captured ONCE into a CUDA graph; every
 // later step only rewrites the kernel-node parameters and issues one cudaGraphLaunch (any mismatch: plain launches).
-int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body);
+// whole: the graph starts at srk_step_begin() - the whole step is one graph - instead of at srk_step_boundary().  With inputs of
+// constant shape at constant addresses (padded batches, see batch_builder.cu) an update pass then finds nearly every node
+// unchanged (launch.cu compares the argument bytes) and the host cost of a step is the bookkeeping of its body plus one
+// cudaGraphLaunch.
+int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body,
+                    bool whole = false);
+int srk_step_begin();
+// srk_flash_ce_bwd without its dS memset launch when the caller zeroed dS itself (csrc/flash_ce.cu)
+int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
+                        const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,
+                        float* dS, float* dEpart, int ds_zeroed, void* stream);
+bool srk_step_want_whole(int phase, int padded);      // SESSREC_GRAPH_WHOLE policy
 // forward / backward boundary of a step body: starts the capture (or switches to node updates) when the driver asked for it
 int srk_step_boundary();
 bool srk_step_want_graph(int phase);      // SESSREC_GRAPH / srk_set_graph_mode policy

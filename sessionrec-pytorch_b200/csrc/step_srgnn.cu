@@ -130,8 +130,12 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   cudaStream_t s1 = ss ? ss->s[1] : st, s2 = ss ? ss->s[4] : st, sdead = ss ? ss->s[5] : st, s4 = ss ? ss->s[6] : st;
   auto order = [&](cudaStream_t from, cudaStream_t to) { return ss ? ss->order(from, to) : (int)SRK_OK; };
   const bool graph_planned = srk_get_launch_ctx() != nullptr;     // the backward half will be captured / replayed
+  SRK_TRY(srk_step_begin());
+  // dS of the head accumulates (TMA reduce-add / split-K): it is zeroed by the launch that zeroes the gradient buffer
+  float* dshat = ar.f((size_t)b.B * d);
+  SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   SRK_TRY(order(st, s4));
-  SRK_TRY(srk_zero_async(grads, sizeof(float) * (size_t)n_flat, s4));
+  SRK_TRY(srk_zero2_async(grads, sizeof(float) * (size_t)n_flat, dshat, sizeof(float) * (size_t)b.B * d, s4));
   tm.mark("zero_grad");
 
   const long long scf = scratch_floats(B, N, d);
@@ -264,15 +268,13 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   // ---- backward ------------------------------------------------------------------------------------------
   const int de_parts = flash ? srk_flash_ce_bwd_parts(B) : 1;
   float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;
-  float* dshat = ar.f((size_t)B * d);
   // SRGNN scores the table itself: without row normalisation the head's table gradient IS d E, accumulated straight
   // into the (zeroed) gradient buffer by the materialised paths; the fused head leaves per-tile partials to be summed
   float* dEhat = (niser || flash) ? ar.f((size_t)de_parts * V * d) : G(0);
   SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   if (flash) {
-    SRK_TRY(srk_flash_ce_bwd(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, scale, b.labels, lse, gseed_dev, dshat, dEhat, st));
+    SRK_TRY(srk_flash_ce_bwd_ex(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, scale, b.labels, lse, gseed_dev, dshat, dEhat, 1, st));
   } else {
-    SRK_TRY(srk_zero_async(dshat, sizeof(float) * (size_t)B * d, st));
     SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, gseed_dev, scale, B, V, 0, Zlo, st));
     if (umma) {
       int split = 148 / ((B + 127) / 128);
@@ -393,9 +395,10 @@ extern "C" int srk_srgnn_train_step(const int* batch_dev, const int* batch_hdr_h
                                  ((unsigned long long)(flags & 7) << 4) | ((unsigned long long)(dropout_p > 0.f) << 3) |
                                  ((unsigned long long)(niser != 0) << 2) | ((unsigned long long)(dead_layers != 0) << 1) |
                                  (unsigned long long)(do_adam != 0 && phase == 0) | ((unsigned long long)(phase == 3) << 62);
-  return srk_step_driver(caller, key, srk_step_want_graph(phase), [&](void* run) {
+  const bool whole = srk_step_want_whole(phase, batch_hdr_host[11]);
+  return srk_step_driver(caller, key ^ ((unsigned long long)whole << 61), srk_step_want_graph(phase) || whole, [&](void* run) {
     return srgnn_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, niser, scale, dead_layers, dropout_p, seed,
                       flags, workspace, workspace_bytes, gseed_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev,
                       seg_decay_dev, n_seg, lr, beta1, beta2, eps, adam_step, grad_scale, phase, run);
-  });
+  }, whole);
 }

@@ -17,6 +17,7 @@ __device__ __forceinline__ uint32_t f2key(float x) {
 
 __global__ void __launch_bounds__(TK_THREADS) topk_rows_kernel(const float* __restrict__ Z, long long ldz, int V, int k,
                                                                int* __restrict__ out_idx, float* __restrict__ out_val) {
+  SRK_PDL();
   __shared__ int hist[2048];
   __shared__ uint32_t cand_u[TK_CAP];
   __shared__ int cand_i[TK_CAP];

@@ -97,6 +97,7 @@ struct UmmaParams {
 __global__ void __launch_bounds__(THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                  const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const UmmaParams p) {
+  SRK_PDL();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], acc_bar;
   __shared__ uint32_t tmem_slot;
@@ -248,6 +249,7 @@ struct FwdParams {
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                       const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const FwdParams p) {
+  SRK_PDL();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
@@ -390,6 +392,7 @@ umma_score_fwd_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_cons
 // lse[m] = log sum over the ntn tile partials; nll[m] = lse[m] - zlab[m].  Warp per row.
 __global__ void __launch_bounds__(256) lse_finalize_kernel(const float* __restrict__ part, const float* __restrict__ zlab,
                                                            int M, int ntn, float* __restrict__ lse, float* __restrict__ nll) {
+  SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (m >= M) return;
@@ -416,6 +419,7 @@ __global__ void __launch_bounds__(256) lse_finalize_kernel(const float* __restri
 
 __global__ void split_tf32_kernel(const float* __restrict__ X, long long ldx, int rows, int cols, float* __restrict__ hi,
                                   float* __restrict__ lo, long long ldo) {
+  SRK_PDL();
   long long total = (long long)rows * cols;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -438,6 +442,7 @@ struct Split2 {
 };
 
 __global__ void __launch_bounds__(256) split2_tf32_kernel(const Split2 sp) {
+  SRK_PDL();
   const long long total = sp.n4[0] + sp.n4[1];
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {

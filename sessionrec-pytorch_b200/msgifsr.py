@@ -340,7 +340,7 @@ class MSGIFSR(SessRecModule):
                    ptr(seg_off), ptr(seg_decay), n_seg, float(o['lr']), float(o['betas'][0]),
                    float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0, phase, int(self.head_chunks), stream)
         if world == 1:
-            call(0)
+            ops.timed_native(lambda: call(0))
         elif parallel.comm_ready() and self.dp_allreduce_inside:
             call(3)             # the gradient all-reduce is enqueued by the step itself (csrc/comm.cu), no return to Python
         else:

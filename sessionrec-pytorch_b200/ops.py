@@ -8,6 +8,22 @@ from . import _lib
 from ._lib import Dropout, GatInst, ptr
 
 _count = [0]
+# SESSREC_HOST_PROFILE=1: seconds spent inside the native one-call training steps (the C call alone), next to
+# bench.py's host_enqueue_ms_per_step (the whole train_step call) - tells how much of the enqueue time is Python
+import os as _os
+import time as _time
+HOST_PROFILE = _os.environ.get('SESSREC_HOST_PROFILE', '0') == '1'
+native_call_s = [0.0, 0]
+
+
+def timed_native(fn):
+    if not HOST_PROFILE:
+        return fn()
+    t = _time.perf_counter()
+    r = fn()
+    native_call_s[0] += _time.perf_counter() - t
+    native_call_s[1] += 1
+    return r
 
 
 def launches():

@@ -399,12 +399,12 @@ def test_native_srgnn_step_with_tensor_core_projections(pkg, model, d, L):
         assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)
 
 
-@pytest.mark.parametrize('p,inject', [(0.0, 0), (0.2, 0), (0.2, 3)])
-def test_native_step_graph_replay_matches_plain_launches(pkg, p, inject):
+@pytest.mark.parametrize('p,inject,whole', [(0.0, 0, 0), (0.2, 0, 0), (0.2, 3, 0), (0.0, 0, 1), (0.2, 0, 1), (0.2, 3, 1)])
+def test_native_step_graph_replay_matches_plain_launches(pkg, p, inject, whole):
     """The native step with its backward half replayed as ONE CUDA graph (kernel-node parameters rewritten per batch:
     different batch shapes, pointers, dropout seeds) against the same steps issued as plain launches: same losses, same
     parameters.  inject > 0: one replay hits a (forced) kernel-sequence mismatch half-way and must finish the step with
-    plain launches."""
+    plain launches.  whole: forward + backward + optimizer as ONE graph (srk_set_graph_whole)."""
     from sessionrec_pytorch_b200._lib import lib
     L = lib().functions
     c = TRAINS['msgifsr_k1']
@@ -413,6 +413,7 @@ def test_native_step_graph_replay_matches_plain_launches(pkg, p, inject):
     try:
         for graphs in (1, 0):
             L['srk_set_graph_mode'](graphs)
+            L['srk_set_graph_whole'](1 if (graphs and whole) else 0)
             L['srk_graph_inject_mismatch'](inject if graphs else 0)      # one replay must fall back half-way
             g0, f0 = L['srk_graph_launches'](), L['srk_graph_fallbacks']()
             m = make_model(pkg, c, dropout=p)
@@ -428,6 +429,7 @@ def test_native_step_graph_replay_matches_plain_launches(pkg, p, inject):
             res.append((m, losses, L['srk_graph_launches']() - g0, L['srk_graph_fallbacks']() - f0))
     finally:
         L['srk_set_graph_mode'](2)                      # back to the default (replay for data-parallel steps only)
+        L['srk_set_graph_whole'](2)
         L['srk_graph_inject_mismatch'](0)
     (m1, l1, n1, fb1), (m2, l2, n2, _) = res
     # two batch sizes = two graphs; each takes two warm-up steps, then capture (+ launch) and replays
