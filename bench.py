@@ -95,6 +95,9 @@ def build_model(cfg, device):
                     extra=False, fusion=False)
     else:
         m = {'SRGNN': SRGNN, 'NISER': NISER}[cfg['model']](cfg['V'], cfg['d'], cfg['layers'], cfg['dropout'])
+        if os.environ.get('SESSREC_BENCH_NO_DEAD') == '1':      # diagnosis only (is the dead-layer stream the critical path?)
+            m.compute_dead_layers = False
+            print('[bench] DIAGNOSTIC RUN: dead GGNN layers skipped - not a valid bench line', file=sys.stderr)
     return m.to(device).train()
 
 

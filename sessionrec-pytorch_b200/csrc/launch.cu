@@ -52,8 +52,22 @@ int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
     const char* e = getenv("SESSREC_PDL");
     return e ? atoi(e) : 1;
   }();
+  // A kernel that is scheduled early holds its SM resources while it waits for its producers: only launches whose
+  // footprint is a fraction of the machine may, or they crowd out the side streams.  Measured (B200, r2x): no limit 0.350 /
+  // 0.735 ms per step at cfg1 / cfg2, <= 75 776 threads (a quarter of the resident threads) and <= 4 MB of shared memory
+  // 0.345 / 0.664, PDL off 0.360 / 0.690.
+  static const long long pdl_max_threads = [] {
+    const char* e = getenv("SESSREC_PDL_MAX_THREADS");
+    return e ? atoll(e) : 75776LL;
+  }();
+  static const long long pdl_max_smem = [] {
+    const char* e = getenv("SESSREC_PDL_MAX_SMEM_KB");
+    return (e ? atoll(e) : 4096LL) * 1024;
+  }();
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  const bool small = ctas * block.x * block.y * block.z <= pdl_max_threads && ctas * (long long)smem <= pdl_max_smem;
   const bool capturing = c && c->mode == SRK_LAUNCH_CAPTURE;
-  if (pdl >= (capturing ? 2 : 1)) {
+  if (pdl >= (capturing ? 2 : 1) && small) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;

@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float* __restric
                                                           const float* __restrict__ sr_in,
                                                           const float* __restrict__ dsr_in, int B, int d,
                                                           int with_last, float* __restrict__ dF,
-                                                          float* __restrict__ dwe) {
+                                                          float* __restrict__ dwe, float* __restrict__ duh,
+                                                          float* __restrict__ dul) {
   SRK_PDL();
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float* __restric
       }
       row_axpy(dv, 1.f, du);
       row_store(du, u + (long long)i * d, d, lane);
+      if (duh) row_store_tf32_split(du, duh + (long long)i * d, dul + (long long)i * d, d, lane);
       df = dg;
       row_scale(df, alpha);
       if (i == lb) row_axpy(df, 1.f, dl);
@@ -467,14 +469,25 @@ extern "C" int srk_readout_fwd(const float* F, const float* u, const float* v, c
   return SRK_OK;
 }
 
+int srk_readout_bwd_split(const float* F, float* u, float* v, const float* we, const int* seg, const int* last, const float* e,
+                          const float* ms, const float* sr_in, const float* dsr_in, int B, int d, int with_last, float* dF,
+                          float* dwe, float* duh, float* dul, void* stream);
+
 extern "C" int srk_readout_bwd(const float* F, float* u, float* v, const float* we, const int* seg, const int* last,
                                const float* e, const float* ms, const float* sr_in, const float* dsr_in, int B, int d,
                                int with_last, float* dF, float* dwe, void* stream) {
+  return srk_readout_bwd_split(F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe, nullptr, nullptr, stream);
+}
+
+// duh / dul: also write the TF32 hi / lo pair of du (dense [N, d]) for the tensor-core products that consume it
+int srk_readout_bwd_split(const float* F, float* u, float* v, const float* we, const int* seg, const int* last, const float* e,
+                          const float* ms, const float* sr_in, const float* dsr_in, int B, int d, int with_last, float* dF,
+                          float* dwe, float* duh, float* dul, void* stream) {
   SRK_TRY(srk_check_dim(d));
   if (B <= 0) return SRK_OK;
   int grid = row_grid(B);
   if (grid > 2 * 148) grid = 2 * 148;          // sessions beyond that are taken by the grid-stride loop (fewer atomics on d w_e)
-  SRK_DISPATCH_NC(d, (srk_launch(readout_bwd_kernel<NC>, grid, 256, 0, (cudaStream_t)stream, F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe)));
+  SRK_DISPATCH_NC(d, (srk_launch(readout_bwd_kernel<NC>, grid, 256, 0, (cudaStream_t)stream, F, u, v, we, seg, last, e, ms, sr_in, dsr_in, B, d, with_last, dF, dwe, duh, dul)));
   SRK_LAUNCH_CHECK();
   return SRK_OK;
 }

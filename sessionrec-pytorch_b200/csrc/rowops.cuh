@@ -35,6 +35,24 @@ __device__ __forceinline__ void row_store(const RowVec<NC>& r, float* __restrict
   }
 }
 
+// the row's TF32 hi / lo pair (hi = upper 19 bits, lo = x - hi exactly): the operand format of the 3xTF32 tensor-core GEMMs,
+// written by the producer so that no separate split pass is needed
+template <int NC>
+__device__ __forceinline__ void row_store_tf32_split(const RowVec<NC>& r, float* __restrict__ hi, float* __restrict__ lo, int d,
+                                                     int lane) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    int col = (c * 32 + lane) * 4;
+    if (col < d) {
+      float4 h;
+      h.x = __uint_as_float(__float_as_uint(r.v[c].x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(r.v[c].y) & 0xFFFFE000u);
+      h.z = __uint_as_float(__float_as_uint(r.v[c].z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(r.v[c].w) & 0xFFFFE000u);
+      *reinterpret_cast<float4*>(hi + col) = h;
+      *reinterpret_cast<float4*>(lo + col) = make_float4(r.v[c].x - h.x, r.v[c].y - h.y, r.v[c].z - h.z, r.v[c].w - h.w);
+    }
+  }
+}
+
 template <int NC>
 __device__ __forceinline__ void row_add_store(const RowVec<NC>& r, float* __restrict__ p, int d, int lane) {
 #pragma unroll

@@ -139,6 +139,14 @@ SideStreams* srk_side_streams();
 int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body,
                     bool whole = false);
 int srk_step_begin();
+// srk_readout_bwd that also writes the TF32 hi / lo pair of du (csrc/readout_ce.cu)
+int srk_readout_bwd_split(const float* F, float* u, float* v, const float* we, const int* seg, const int* last, const float* e,
+                          const float* ms, const float* sr_in, const float* dsr_in, int B, int d, int with_last, float* dF,
+                          float* dwe, float* duh, float* dul, void* stream);
+// srk_tc_gemm with operands whose TF32 hi / lo pair already exists (csrc/umma_gemm.cu)
+int srk_tc_gemm_pre(int form, int M, int N, int K, const float* A, long long lda, const float* Ahi, const float* Alo,
+                    long long ldah, const float* B, long long ldb, const float* Bhi, const float* Blo, long long ldbh, float* C,
+                    long long ldc, const float* bias, float alpha, int accumulate, int split_k, float* scratch, void* stream);
 // srk_flash_ce_bwd without its dS memset launch when the caller zeroed dS itself (csrc/flash_ce.cu)
 int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
                         const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,

@@ -57,17 +57,32 @@ long long tc_min_macs() {
   return v;
 }
 
-// C (op)= op(A) op(B) (+ bias): tensor cores when the product is big enough and nothing is row-indexed, else CUDA cores
-int mm(cudaStream_t st, const TcScratch& sc, bool tc, int form, int M, int N, int K, const float* A, long long lda, const float* Bm,
-       long long ldb, float* C, long long ldc, const float* bias, int accumulate) {
+// TF32 hi / lo pair of an operand that already exists (written by the operand's producer or by one split launch)
+struct Pre {
+  const float *hi = nullptr, *lo = nullptr;
+  long long ld = 0;
+};
+
+bool tc_shape_ok(int M, int N, int K) { return (long long)M * N * K >= tc_min_macs() && K >= 32 && N >= 16; }
+
+// C (op)= op(A) op(B) (+ bias): tensor cores when the product is big enough and nothing is row-indexed, else CUDA cores.
+// accumulate: the split-K that fills the SMs is picked (C must hold the addend, or zeros).
+int mmp(cudaStream_t st, const TcScratch& sc, bool tc, int form, int M, int N, int K, const float* A, long long lda, Pre pa,
+        const float* Bm, long long ldb, Pre pb, float* C, long long ldc, const float* bias, int accumulate) {
   if (M <= 0 || N <= 0) return SRK_OK;
-  const bool ok = tc && (long long)M * N * K >= tc_min_macs() && K >= 32 && N >= 16 && lda % 4 == 0 && ldb % 4 == 0 &&
+  const bool ok = tc && tc_shape_ok(M, N, K) && lda % 4 == 0 && ldb % 4 == 0 &&
                   ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bm)) & 15u) == 0 &&
-                  srk_tc_gemm_scratch_floats(form, M, N, K) <= sc.floats && (form != 2 || accumulate);
-  if (ok) return srk_tc_gemm(form, M, N, K, A, lda, Bm, ldb, C, ldc, bias, 1.0f, accumulate, form == 2 ? 0 : 1, sc.p, st);
+                  ((pa.hi && pb.hi) || srk_tc_gemm_scratch_floats(form, M, N, K) <= sc.floats) && (form != 2 || accumulate);
+  if (ok)
+    return srk_tc_gemm_pre(form, M, N, K, A, lda, pa.hi, pa.lo, pa.ld, Bm, ldb, pb.hi, pb.lo, pb.ld, C, ldc, bias, 1.0f, accumulate,
+                           accumulate ? 0 : 1, sc.p, st);
   if (form == 0) return srk_gemm(M, N, K, A, lda, 1, Bm, 1, ldb, C, ldc, nullptr, nullptr, nullptr, bias, 1.f, accumulate, 0, st);
   if (form == 1) return srk_gemm(M, N, K, A, lda, 1, Bm, ldb, 1, C, ldc, nullptr, nullptr, nullptr, bias, 1.f, accumulate, 0, st);
   return srk_gemm(M, N, K, A, 1, lda, Bm, ldb, 1, C, ldc, nullptr, nullptr, nullptr, bias, 1.f, accumulate, 0, st);
+}
+int mm(cudaStream_t st, const TcScratch& sc, bool tc, int form, int M, int N, int K, const float* A, long long lda, const float* Bm,
+       long long ldb, float* C, long long ldc, const float* bias, int accumulate) {
+  return mmp(st, sc, tc, form, M, N, K, A, lda, Pre{}, Bm, ldb, Pre{}, C, ldc, bias, accumulate);
 }
 
 long long scratch_floats(int B, int N, int d) {
@@ -92,6 +107,7 @@ extern "C" long long srk_srgnn_workspace_bytes(int B, int N, int M, int V, int d
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;   // flash head
   fl += 4LL * B * d + 3LL * N * d + (long long)(N + 4) * d;  // dshat, ds, dsr_in, dF, dX, scatter partials
   fl += 3 * scratch_floats(B, N, d);                         // tensor-core operand splits: one region per stream
+  fl += 4LL * N * d + 8LL * B * d + 14LL * d * d + 8192;     // TF32 pairs made once: F, du, sr_in, ds, read-out weights; zero pool
   return fl * 4 + fl + (1 << 20);                            // floats -> bytes with 25% head-room + alignment slack
 }
 
@@ -132,10 +148,37 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   const bool graph_planned = srk_get_launch_ctx() != nullptr;     // the backward half will be captured / replayed
   SRK_TRY(srk_step_begin());
   // dS of the head accumulates (TMA reduce-add / split-K): it is zeroed by the launch that zeroes the gradient buffer
-  float* dshat = ar.f((size_t)b.B * d);
+  // ... together with the two session-level products that run split-K (fc_sr and its data gradient: 16 row tiles only)
+  const size_t bd = (size_t)b.B * d;
+  float* zpool = ar.f(4 * bd);
+  float *dshat = zpool, *s = zpool + bd, *dsr_in = zpool + 2 * bd;
   SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   SRK_TRY(order(st, s4));
-  SRK_TRY(srk_zero2_async(grads, sizeof(float) * (size_t)n_flat, dshat, sizeof(float) * (size_t)b.B * d, s4));
+  SRK_TRY(srk_zero2_async(grads, sizeof(float) * (size_t)n_flat, zpool, sizeof(float) * 4 * bd, s4));
+  // Every tensor-core product of the live path reads operands whose TF32 hi / lo pair is made ONCE: by the operand's producer
+  // (dropout pass, read-out backward) or by one split launch per tensor - not once per product.  The read-out weights are
+  // split here, beside the gather.
+  const bool tc_ro = umma && d % 4 == 0 && tc_shape_ok(N, d, d);
+  Pre Wu, Wsr;
+  if (tc_ro) {
+    const long long o_u = slot_off_host[s_ro], o_s = slot_off_host[s_ro + 4];
+    const long long span = o_s + 2LL * d * d - o_u;
+    SRK_TRY(order(st, s1));
+    if (o_s > o_u && span % 4 == 0 && span <= 6LL * d * d + 4096) {          // fc_u .. fc_sr contiguous: one pass
+      float *wh = ar.f((size_t)span), *wl = ar.f((size_t)span);
+      SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
+      SRK_TRY(srk_split_tf32(params + o_u, span, 1, (int)span, wh, wl, span, s1));
+      Wu.hi = wh; Wu.lo = wl;
+      Wsr.hi = wh + (o_s - o_u); Wsr.lo = wl + (o_s - o_u);
+    } else {
+      float *uh = ar.f((size_t)d * d), *ul = ar.f((size_t)d * d), *sh_ = ar.f(2 * (size_t)d * d), *sl_ = ar.f(2 * (size_t)d * d);
+      SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
+      SRK_TRY(srk_split_tf32(P(s_ro), d, d, d, uh, ul, d, s1));
+      SRK_TRY(srk_split_tf32(P(s_ro + 4), 2 * d, d, 2 * d, sh_, sl_, 2 * d, s1));
+      Wu.hi = uh; Wu.lo = ul; Wsr.hi = sh_; Wsr.lo = sl_;
+    }
+    Wu.ld = d; Wsr.ld = 2 * d;
+  }
   tm.mark("zero_grad");
 
   const long long scf = scratch_floats(B, N, d);
@@ -202,14 +245,27 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   // read-out (with its own feat_drop on top of the embedding dropout, srgnn.py:79)
   const float* F = X;
   srk_dropout dc_r = dcfg(SRK_SITE_READOUT);
+  Pre Fp, SRp, DSp, DUp;
+  if (tc_ro) {
+    float *fh = ar.f((size_t)N * d), *fl = ar.f((size_t)N * d), *rh = ar.f(2 * bd), *rl = ar.f(2 * bd);
+    float *dh = ar.f(bd), *dl = ar.f(bd), *uh = ar.f((size_t)N * d), *ul = ar.f((size_t)N * d);
+    SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
+    Fp.hi = fh; Fp.lo = fl; Fp.ld = d;
+    SRp.hi = rh; SRp.lo = rl; SRp.ld = 2 * d;
+    DSp.hi = dh; DSp.lo = dl; DSp.ld = d;
+    DUp.hi = uh; DUp.lo = ul; DUp.ld = d;
+  }
   if (drop) {
     float* Fd = ar.f((size_t)N * d);
     SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
-    SRK_TRY(srk_dropout_apply(X, Fd, (long long)N * d, &dc_r, 0, st));
+    if (tc_ro) SRK_TRY(srk_dropout_apply_split(X, Fd, const_cast<float*>(Fp.hi), const_cast<float*>(Fp.lo), (long long)N * d, &dc_r, st));
+    else SRK_TRY(srk_dropout_apply(X, Fd, (long long)N * d, &dc_r, 0, st));
     F = Fd;
+  } else if (tc_ro) {
+    SRK_TRY(srk_split_tf32(X, d, N, d, const_cast<float*>(Fp.hi), const_cast<float*>(Fp.lo), d, st));
   }
   float *u = ar.f((size_t)N * d), *v = ar.f((size_t)B * d), *e = ar.f(N), *ms = ar.f(2 * (size_t)B);
-  float *sr_in = ar.f(2 * (size_t)B * d), *s = ar.f((size_t)B * d);
+  float* sr_in = ar.f(2 * (size_t)B * d);
   float *shat = niser ? ar.f((size_t)B * d) : s, *rn_s = niser ? ar.f(B) : nullptr;
   SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   uint16_t *Sbh = nullptr, *Sbl = nullptr;
@@ -218,13 +274,16 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
     Sbl = reinterpret_cast<uint16_t*>(ar.raw((size_t)B * d * 2));
     SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   }
+  if (tc_ro) SRK_TRY(order(s1, st));            // the weight pairs
   SRK_TRY(order(st, s1));
-  SRK_TRY(mm(st, sc_main, umma, 0, N, d, d, F, d, P(s_ro), d, u, d, nullptr, 0));
+  SRK_TRY(mmp(st, sc_main, umma, 0, N, d, d, F, d, Fp, P(s_ro), d, Wu, u, d, nullptr, 0));
   SRK_TRY(srk_gemm(B, d, d, F, d, 1, P(s_ro + 1), 1, d, v, d, b.last, nullptr, nullptr, P(s_ro + 2), 1.f, 0, 0, s1));
   SRK_TRY(order(s1, st));
   SRK_TRY(srk_readout_fwd(F, u, v, P(s_ro + 3), b.seg, b.last, B, d, drop ? 0 : 1, e, ms, sr_in, st));
   if (drop) SRK_TRY(srk_gather_rows(X, b.last, B, d, sr_in, 2 * d, st));      // sr_l uses the once-dropped rows
-  SRK_TRY(mm(st, sc_main, umma, 0, B, d, 2 * d, sr_in, 2 * d, P(s_ro + 4), 2 * d, s, d, nullptr, 0));
+  if (tc_ro) SRK_TRY(srk_split_tf32(sr_in, 2 * d, B, 2 * d, const_cast<float*>(SRp.hi), const_cast<float*>(SRp.lo), 2 * d, st));
+  // s comes zeroed from the pool: split-K over the 2d inputs (M = B gives 16 row tiles only)
+  SRK_TRY(mmp(st, sc_main, umma, 0, B, d, 2 * d, sr_in, 2 * d, SRp, P(s_ro + 4), 2 * d, Wsr, s, d, nullptr, 1));
   if (niser) {
     if (flash) SRK_TRY(srk_rownorm_split_fwd(s, d, B, d, SRK_NORM_EPS, shat, d, rn_s, Sbh, Sbl, st));
     else SRK_TRY(srk_rownorm_fwd(s, d, B, d, SRK_NORM_EPS, shat, d, rn_s, st));
@@ -311,16 +370,18 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
     SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
     SRK_TRY(srk_rownorm_bwd(s, d, shat, d, rn_s, dshat, d, B, d, SRK_NORM_EPS, ds, d, 0, st));
   }
-  float *dsr_in = ar.f(2 * (size_t)B * d), *dF = ar.f((size_t)N * d);
+  float* dF = ar.f((size_t)N * d);
   SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
+  if (tc_ro) SRK_TRY(srk_split_tf32(ds, d, B, d, const_cast<float*>(DSp.hi), const_cast<float*>(DSp.lo), d, st));
   // data gradients on the main stream, weight gradients (into the flat gradient buffer) on s2
   SRK_TRY(order(st, s2));
-  SRK_TRY(mm(st, sc_main, umma, 1, B, 2 * d, d, ds, d, P(s_ro + 4), 2 * d, dsr_in, 2 * d, nullptr, 0));
-  SRK_TRY(mm(s2, sc_w, umma, 2, d, 2 * d, B, ds, d, sr_in, 2 * d, G(s_ro + 4), 2 * d, nullptr, 1));
-  SRK_TRY(srk_readout_bwd(F, u, v, P(s_ro + 3), b.seg, b.last, e, ms, sr_in, dsr_in, B, d, drop ? 0 : 1, dF, G(s_ro + 3), st));
+  SRK_TRY(mmp(st, sc_main, umma, 1, B, 2 * d, d, ds, d, DSp, P(s_ro + 4), 2 * d, Wsr, dsr_in, 2 * d, nullptr, 1));     // zeroed: split-K
+  SRK_TRY(mmp(s2, sc_w, umma, 2, d, 2 * d, B, ds, d, DSp, sr_in, 2 * d, SRp, G(s_ro + 4), 2 * d, nullptr, 1));
+  SRK_TRY(srk_readout_bwd_split(F, u, v, P(s_ro + 3), b.seg, b.last, e, ms, sr_in, dsr_in, B, d, drop ? 0 : 1, dF, G(s_ro + 3),
+                                const_cast<float*>(DUp.hi), const_cast<float*>(DUp.lo), st));
   SRK_TRY(order(st, s2));
-  SRK_TRY(mm(st, sc_main, umma, 1, N, d, d, u, d, P(s_ro), d, dF, d, nullptr, 1));                               // u holds du
-  SRK_TRY(mm(s2, sc_w, umma, 2, d, d, N, u, d, F, d, G(s_ro), d, nullptr, 1));
+  SRK_TRY(mmp(st, sc_main, umma, 1, N, d, d, u, d, DUp, P(s_ro), d, Wu, dF, d, nullptr, 1));                     // u holds du
+  SRK_TRY(mmp(s2, sc_w, umma, 2, d, d, N, u, d, DUp, F, d, Fp, G(s_ro), d, nullptr, 1));
   SRK_TRY(srk_gemm(B, d, d, v, d, 1, P(s_ro + 1), d, 1, dF, d, nullptr, nullptr, b.last, nullptr, 1.f, 1, 0, st));    // v holds dv
   SRK_TRY(srk_gemm(d, d, B, v, 1, d, F, d, 1, G(s_ro + 1), d, nullptr, b.last, nullptr, nullptr, 1.f, 1, 0, s2));
   SRK_TRY(srk_colsum(v, d, B, d, G(s_ro + 2), 1, s2));

@@ -481,6 +481,10 @@ extern "C" int srk_umma_gemm(int form, int M, int N, int K, const float* Ahi, co
 
 static inline long long r4(long long x) { return (x + 3) / 4 * 4; }
 
+int srk_tc_gemm_pre(int form, int M, int N, int K, const float* A, long long lda, const float* Ahi, const float* Alo,
+                    long long ldah, const float* B, long long ldb, const float* Bhi, const float* Blo, long long ldbh, float* C,
+                    long long ldc, const float* bias, float alpha, int accumulate, int split_k, float* scratch, void* stream);
+
 // floats of scratch srk_tc_gemm needs: dense hi / lo copies of both operands
 extern "C" long long srk_tc_gemm_scratch_floats(int form, int M, int N, int K) {
   const long long a = form == 2 ? (long long)K * r4(M) : (long long)M * r4(K);
@@ -494,25 +498,50 @@ extern "C" long long srk_tc_gemm_scratch_floats(int form, int M, int N, int K) {
 extern "C" int srk_tc_gemm(int form, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
                            float* C, long long ldc, const float* bias, float alpha, int accumulate, int split_k,
                            float* scratch, void* stream) {
+  return srk_tc_gemm_pre(form, M, N, K, A, lda, nullptr, nullptr, 0, B, ldb, nullptr, nullptr, 0, C, ldc, bias, alpha, accumulate,
+                         split_k, scratch, stream);
+}
+
+// The same with operands that may already be split: Ahi / Alo (pitch ldah) and / or Bhi / Blo (pitch ldbh) non-null = that
+// operand's TF32 pair exists (its producer wrote it, or an earlier product of the step split it) and only the other one is
+// split here; both given = no split launch at all.  The native steps split every activation and weight once.
+int srk_tc_gemm_pre(int form, int M, int N, int K, const float* A, long long lda, const float* Ahi, const float* Alo,
+                    long long ldah, const float* B, long long ldb, const float* Bhi, const float* Blo, long long ldbh, float* C,
+                    long long ldc, const float* bias, float alpha, int accumulate, int split_k, float* scratch, void* stream) {
   SRK_REQUIRE(form >= 0 && form <= 2, "tc_gemm: bad form %d", form);
   if (M <= 0 || N <= 0) return SRK_OK;
-  SRK_REQUIRE(K > 0 && scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0, "tc_gemm: bad arguments");
+  const bool need_a = Ahi == nullptr, need_b = Bhi == nullptr;
+  SRK_REQUIRE(K > 0 && (!(need_a || need_b) || (scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0)),
+              "tc_gemm: bad arguments");
+  SRK_REQUIRE((need_a || Alo != nullptr) && (need_b || Blo != nullptr), "tc_gemm: a pre-split operand needs both halves");
   Split2 sp;
+  memset(&sp, 0, sizeof(sp));
   sp.X[0] = A; sp.ldx[0] = lda;
   sp.X[1] = B; sp.ldx[1] = ldb;
   sp.rows[0] = form == 2 ? K : M; sp.cols[0] = form == 2 ? M : K;
   sp.rows[1] = form == 0 ? N : K; sp.cols[1] = form == 0 ? K : N;
+  const float *hi[2] = {Ahi, Bhi}, *lo[2] = {Alo, Blo};
+  long long ldo[2] = {ldah, ldbh};
   float* w = scratch;
   for (int i = 0; i < 2; ++i) {
+    if (i == 0 ? !need_a : !need_b) {
+      sp.rows[i] = 0;                          // nothing to split
+      sp.n4[i] = 0;
+      sp.cols[i] = 4;
+      continue;
+    }
     sp.ldo[i] = r4(sp.cols[i]);
     sp.n4[i] = (long long)sp.rows[i] * (sp.ldo[i] / 4);
     sp.hi[i] = w; w += (long long)sp.rows[i] * sp.ldo[i];
     sp.lo[i] = w; w += (long long)sp.rows[i] * sp.ldo[i];
+    hi[i] = sp.hi[i]; lo[i] = sp.lo[i]; ldo[i] = sp.ldo[i];
   }
-  long long g = (sp.n4[0] + sp.n4[1] + 255) / 256;
-  if (g > 148LL * 8) g = 148LL * 8;
-  srk_launch(split2_tf32_kernel, (int)g, 256, 0, (cudaStream_t)stream, sp);
-  SRK_LAUNCH_CHECK();
+  if (need_a || need_b) {
+    long long g = (sp.n4[0] + sp.n4[1] + 255) / 256;
+    if (g > 148LL * 8) g = 148LL * 8;
+    srk_launch(split2_tf32_kernel, (int)g, 256, 0, (cudaStream_t)stream, sp);
+    SRK_LAUNCH_CHECK();
+  }
   const int nstep = form == 0 ? N : 256;
   for (int n0 = 0; n0 < N; n0 += nstep) {
     const int nc = N - n0 < nstep ? N - n0 : nstep;
@@ -526,10 +555,10 @@ extern "C" int srk_tc_gemm(int form, int M, int N, int K, const float* A, long l
         if (S < 1) S = 1;
       }
     }
-    const float* bh = form == 0 ? sp.hi[1] : sp.hi[1] + n0;
-    const float* bl = form == 0 ? sp.lo[1] : sp.lo[1] + n0;
-    SRK_TRY(umma_gemm_impl(form, M, nc, K, sp.hi[0], sp.lo[0], sp.ldo[0], bh, bl, sp.ldo[1], C + n0, ldc,
-                           bias ? bias + n0 : nullptr, alpha, accumulate, S, stream));
+    const float* bh = form == 0 ? hi[1] : hi[1] + n0;
+    const float* bl = form == 0 ? lo[1] : lo[1] + n0;
+    SRK_TRY(umma_gemm_impl(form, M, nc, K, hi[0], lo[0], ldo[0], bh, bl, ldo[1], C + n0, ldc, bias ? bias + n0 : nullptr, alpha,
+                           accumulate, S, stream));
   }
   return SRK_OK;
 }
