@@ -298,11 +298,16 @@ def roofline_probe(cfg, device, pk):
     ach = flops / (ms * 1e-3) / 1e12
     traffic, traffic_src = None, None
     if flash:
+        # dram__bytes_read.sum + dram__bytes_write.sum of the forward + backward launch from the committed `ncu --set full`
+        # capture; only valid for the shape a capture was taken on (narrow kernels: cfg1 shape, wide kernels: cfg2 shape)
         caps = sorted((ROOT / 'profiles').glob('*_ncu_full_flash_ce.json'))
-        if caps and (B, V, d) == (512, 43097, 96):
-            rows = json.loads(caps[-1].read_text())
-            traffic = round(sum(float(r['dram_bytes_read']) + float(r['dram_bytes_write']) for r in rows))
-            traffic_src = f'profiles/{caps[-1].name} (bytes of the forward + backward launches)'
+        wide = {(512, 43097, 96): False, (2048, 17000, 256): True}.get((B, V, d))
+        if caps and wide is not None:
+            rows = [r for r in json.loads(caps[-1].read_text()) if ('wide' in r['kernel']) == wide]
+            if len(rows) == 2:
+                traffic = round(sum(float(r['dram_bytes_read']) + float(r['dram_bytes_write']) for r in rows))
+                traffic_src = (f'profiles/{caps[-1].name} (bytes of the forward + backward launch; tensor pipe active '
+                               + ' / '.join(f"{r['tensor_pipe_pct_active']:.1f} %" for r in rows) + ')')
     elif umma and (B, V, d) == (512, 43097, 96):
         # dram__bytes_read.sum + dram__bytes_write.sum of the same three launches from the committed `ncu --set full`
         # capture (profiles/); only valid for the shape it was captured on
@@ -413,6 +418,14 @@ def reference_arm(args, cfg, rank, guard):
         'cpu_baseline': cb,
         'e2e': dict(value=round(v, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         'note': cb['what']})
+
+
+def graph_counters():
+    """CUDA-graph replay statistics of the native steps in this process (whole run, not only the timed region)."""
+    from sessionrec_pytorch_b200._lib import lib
+    f = lib().functions
+    return dict(steps_replayed=int(f['srk_graph_launches']()), fallbacks=int(f['srk_graph_fallbacks']()),
+                nodes_rewritten=int(f['srk_graph_node_updates']()))
 
 
 def workload_name(key, cfg):
@@ -592,6 +605,7 @@ def measure(key, cfg, args, pkg, device, group, world, rank, pk, primary):
             'e2e': dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=int(h2d / args.steps), d2h_bytes_per_step=4,
                         timing='wall clock over K steps incl. H2D batch copy + loss.item() per step'),
             'wall_s_timed_region': round(t_wall, 4), 'host_enqueue_ms_per_step': round(1e3 * enqueue_s / args.steps, 4),
+            'graph': graph_counters(),
             'roofline': roofline_probe(cfg, device, pk),
         }
         if world > 1:
