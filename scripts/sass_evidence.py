@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / 'sessionrec-pytorch_b200' / 'libsessrec_b200.so'
 PAT = {'UTC*MMA (tcgen05.mma)': r'\bUTC\w*MMA\b', 'LDTM (tcgen05.ld)': r'\bLDTM\b', 'STTM (tcgen05.st)': r'\bSTTM\b',
        'UTMALDG (TMA load)': r'\bUTMALDG\b', 'UTMASTG (TMA store)': r'\bUTMASTG\b', 'UTMAREDG (TMA reduce-add)': r'\bUTMAREDG\b',
-       'UBLKCP (bulk copy)': r'\bUBLKCP\b', 'HMMA (legacy mma.sync)': r'\bHMMA\b', 'SYNCS (mbarrier)': r'\bSYNCS\b'}
+       'UBLKCP (bulk copy)': r'\bUBLKCP\b', 'ACQBULK (griddepcontrol.wait)': r'\bACQBULK\b', 'PREEXIT (launch_dependents)': r'\bPREEXIT\b', 'ELECT': r'\bELECT\b', 'BRA.U.ANY (vote loop)': r'BRA\.U\.ANY', 'HMMA (legacy mma.sync)': r'\bHMMA\b', 'SYNCS (mbarrier)': r'\bSYNCS\b'}
 
 
 def demangle(names):
