@@ -455,6 +455,20 @@ int srk_srgnn_train_step(const int* batch_dev, const int* batch_hdr_host, float*
                          float beta1, float beta2, float eps, int adam_step, float grad_scale, int phase, void* stream);
 
 
+/* ---- native training step, MSGIFSR of any order K (k-gram node types): SemanticExpander (msgifsr.py:32-45), L heterogeneous
+ * MSHGNN layers over intra_k / inter relations (msgifsr.py:47-91), multi-order read-out (msgifsr.py:124-155), fused head,
+ * backward, Adam; without --extra / --fusion.  Same contract as srk_msgifsr_train_step.  slot_off_host (n_slots entries):
+ * [0] embeddings.weight; 1 + ((l*2 + conv)*(K+1) + e)*4 + {0: attn_l, 1: attn_r, 2: bias, 3: fc.weight} of layers.l.conv{conv+1}
+ * .mods.{intra1..intraK (e = k-1), inter (e = K)}; then per k = 2..K expander.GRUs.{k-2}.{weight_ih_l0, weight_hh_l0, bias_ih_l0,
+ * bias_hh_l0}; then readout.fc_u.0.weight, readout.fc_u.0.bias, readout.fc_v.0.weight, readout.fc_e.0.weight, fc_sr.0.weight. */
+long long srk_msgifsr_k_workspace_bytes(const int* batch_hdr_host, int V, int d, int L);
+int srk_msgifsr_k_train_step(const int* batch_dev, const int* batch_hdr_host, float* params, float* grads,
+                             const long long* slot_off_host, int n_slots, int V, int d, int L, float dropout_p, uint64_t seed,
+                             int flags, void* workspace, long long workspace_bytes, const float* gseed_dev, float* loss_out,
+                             int do_adam, float* exp_avg, float* exp_avg_sq, long long n_flat, const long long* seg_off_dev,
+                             const float* seg_decay_dev, int n_seg, float lr, float beta1, float beta2, float eps, int adam_step,
+                             float grad_scale, int phase, void* stream);
+
 /* ---- native batch builder (host; next-row: utils/data/collate.py:61-85,87-217,219-256) ---------------------------
  * Sessions are given as a flat item array + offsets. kind 0 = session graph (weights, self-loop rule), kind 1 =
  * ccs heterograph of the given order. Two calls: srk_batch_size() returns the number of int32 words needed,

@@ -279,6 +279,69 @@ class MSGIFSR(SessRecModule):
         return (self.order == 1 and batch.K == 1 and not self.extra and self.norm and self.num_layers >= 1
                 and (self._shard is None or parallel.comm_ready()))
 
+    def _native_k_ok(self, batch):
+        """The general native step (csrc/step_k.cu): any order, k-gram node types, without --extra / --fusion heads."""
+        return (self.order > 1 and batch.K == self.order and not self.extra and not self.fusion and self.norm
+                and self.num_layers >= 1 and self._shard is None and self.use_tensor_cores and self.flash_ce
+                and ops.flash_ce_supported(self.embedding_dim))
+
+    def _slot_offsets_k(self):
+        import numpy as np
+        fp, K = self._flat, self.order
+        names = ['embeddings.weight']
+        for l in range(self.num_layers):
+            for c in (1, 2):
+                for et in [f'intra{k}' for k in range(1, K + 1)] + ['inter']:
+                    names += [f'layers.{l}.conv{c}.mods.{et}.{n}' for n in ('attn_l', 'attn_r', 'bias', 'fc.weight')]
+        for k in range(2, K + 1):
+            names += [f'expander.GRUs.{k - 2}.{n}' for n in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')]
+        names += ['readout.fc_u.0.weight', 'readout.fc_u.0.bias', 'readout.fc_v.0.weight', 'readout.fc_e.0.weight',
+                  'fc_sr.0.weight']
+        return np.ascontiguousarray([fp.offsets[fp.index[n]] for n in names], dtype=np.int64)
+
+    def _train_step_k(self, batch, group, global_batch):
+        """One TrainRunner iteration of an order-K model in ONE C call (srk_msgifsr_k_train_step)."""
+        import ctypes
+        from ._lib import lib, ptr
+        fp = self._flat
+        if self._opt is None:
+            self.configure_optimizer()
+        o = self._opt
+        st = getattr(self, '_native_k', None)
+        if st is None or st['flat'] is not fp:
+            st = self._native_k = dict(flat=fp, slots=self._slot_offsets_k(), ws=None, ws_bytes=0)
+        L = lib()
+        hdr = ctypes.c_void_p(batch.hdr.ctypes.data)
+        need = L.call('srk_msgifsr_k_workspace_bytes', hdr, self.num_items, self.embedding_dim, self.num_layers)
+        if need > st['ws_bytes']:
+            st['ws_bytes'] = int(need * 1.2)
+            st['ws'] = torch.empty(st['ws_bytes'], dtype=torch.uint8, device=fp.data.device)
+        p, seed = self._p(), self._next_seed()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        world = 1
+        if group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+        gseed = self._dp_weight(batch, group, global_batch)
+        seg_off, seg_decay, n_seg = self._segments(batch, None)
+        o['step'] += 1
+        loss = torch.empty((), dtype=torch.float32, device=fp.data.device)
+
+        def call(phase):
+            ops._count[0] += 1
+            L.call('srk_msgifsr_k_train_step', ptr(batch.buf), hdr, ptr(fp.data), ptr(fp.grad),
+                   ctypes.c_void_p(st['slots'].ctypes.data), int(st['slots'].size), self.num_items, self.embedding_dim,
+                   self.num_layers, float(p), ctypes.c_uint64(seed), 5, ptr(st['ws']), st['ws_bytes'], ptr(gseed), ptr(loss), 1,
+                   ptr(o['m']), ptr(o['v']), fp.data.numel(), ptr(seg_off), ptr(seg_decay), n_seg, float(o['lr']),
+                   float(o['betas'][0]), float(o['betas'][1]), float(o['eps']), int(o['step']), 1.0, phase, stream)
+        if world == 1:
+            call(0)
+        else:
+            call(1)
+            dist.all_reduce(fp.grad, group=group)
+            call(2)
+        return loss
+
     def _slot_offsets(self):
         import numpy as np
         fp = self._flat
@@ -294,6 +357,8 @@ class MSGIFSR(SessRecModule):
         """One TrainRunner iteration in ONE C call (srk_msgifsr_train_step): zero_grad, forward, nll_loss, backward,
         Adam.  Falls back to the staged Python composition for configurations the native step does not cover."""
         fp = self._ensure_flat()
+        if batch is not None and batch.B > 0 and self.native_step and self._native_k_ok(batch):
+            return self._train_step_k(batch, group, global_batch)
         if batch is None or batch.B == 0 or not self._native_ok(batch) or not self.native_step:
             return super().train_step(batch, group, global_batch)
         import ctypes

@@ -371,6 +371,41 @@ def test_native_msgifsr_step_wide_embedding(pkg, d):
         assert_close(f'native vs staged {n}', q1, q2, rtol=1e-4, floor=0.5)
 
 
+@pytest.mark.parametrize('K,d,L,p', [(2, 32, 1, 0.0), (3, 96, 1, 0.2), (3, 32, 2, 0.2), (4, 64, 1, 0.2), (2, 256, 1, 0.2)])
+def test_native_order_k_step_matches_staged_composition(pkg, K, d, L, p):
+    """MSGIFSR of order K > 1 (k-gram node types, SemanticExpander, intra / inter relations, multi-order read-out): the general
+    native step (csrc/step_k.cu, ONE C call) == the staged composition of the same kernels, dropout masks included; the staged
+    composition itself is pinned by the reference's goldens (msgifsr_k2 / msgifsr_k3 trajectories)."""
+    from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+    from sessionrec_pytorch_b200.synthetic import SessionSampler
+    V, B = 2500, 300
+    res = []
+    for native in (True, False):
+        torch.manual_seed(5)
+        m = MSGIFSR(V, 'x', d, L, dropout=p, order=K, extra=False, fusion=False).to(DEV).train()
+        m.native_step = native
+        m.configure_optimizer(lr=1e-3, weight_decay=1e-4)
+        smp = SessionSampler(V, seed=13)
+        losses = []
+        for it in range(3):
+            seqs, labels = smp.sessions(B)
+            if it == 2:
+                seqs = [q[:1] for q in seqs[:B // 2]] + seqs[B // 2:]       # many single-click sessions: dummy k-gram nodes
+            m.set_dropout_seed(51 + it)
+            b = pkg.SessionBatch.build(seqs, labels, 'ccs', K).to(DEV)
+            assert m._native_k_ok(b) or not native
+            losses.append(float(m.train_step(b)))
+        res.append((m, losses))
+    (m1, l1), (m2, l2) = res
+    for a, b_ in zip(l1, l2):
+        assert abs(a - b_) <= 5e-6 * abs(b_), (l1, l2)
+    # d = 256: the staged composition sends its big products to the 3xTF32 tensor-core GEMM, the native step keeps them in fp32;
+    # Adam turns a 1e-6 difference of a near-zero gradient into a visible step for a handful of the 640 000 table entries
+    rtol = 1e-3 if d >= 256 else 1e-4
+    for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert_close(f'native vs staged {n}', q1, q2, rtol=rtol, floor=0.5)
+
+
 @pytest.mark.parametrize('model,d,L', [('SRGNN', 256, 1), ('NISER', 64, 2), ('SRGNN', 96, 2)])
 def test_native_srgnn_step_with_tensor_core_projections(pkg, model, d, L):
     """Shapes where the read-out / GGNN projections of the native step go to the tcgen05 GEMM (srk_tc_gemm) and, for d = 256,
