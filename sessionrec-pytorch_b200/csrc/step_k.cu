@@ -3,10 +3,12 @@
 // inter relations (msgifsr.py:47-91, gatconv.py:254-319), the multi-order attention read-out (msgifsr.py:124-155), the fused
 // scoring + cross-entropy head, the whole backward and Adam - ONE host call that enqueues ~350 kernels at order 3.
 //
-// csrc/step.cu is the tuned order-1 path (7 streams, graph replay).  This file is the general one: the same kernels in the order
-// of the staged Python composition (msgifsr.py of this package), on one stream plus the catalog stream, because at order 3 the
-// step is bound by the ~350 launches themselves: the point of the port is 4 us of host time per launch instead of the 16 us a
-// Python + ctypes launch costs.
+// csrc/step.cu is the tuned order-1 path (graph replay, tensor-core projections).  This file is the general one: the same kernels
+// as the staged Python composition (msgifsr.py of this package), enqueued from C++ (4 us of host time per launch instead of the
+// 16 us of a Python + ctypes launch) and forked over the step's streams: at order 3 a layer has 14 independent convolutions
+// (7 relations, each on the graph and on the reversed graph).  Convolutions that share a parameter module (`inter`) stay on one
+// stream because their weight gradients accumulate into the same rows; every data-gradient term of a node type is written to its
+// own slice and one pass per type adds them up, so no two streams ever accumulate into the same buffer.
 #include <vector>
 
 #include "launch.cuh"
@@ -83,6 +85,9 @@ struct Inst {
   int st, dt, M, pslot;                  // pslot: first of the module's 4 parameter slots (attn_l, attn_r, bias, fc.weight)
   float *Waug, *wr, *xs, *xd;
   srk_dropout dcs, dcd;
+  cudaStream_t sq, sp;                   // sq: the stream of this convolution's parameter module; sp: its own (round robin)
+  float *src_term, *dst_term;            // slices of the per-type gradient-term buffers (backward)
+  float *dWaug, *dwr;
 };
 struct TypeRec {
   std::vector<Inst> inst;
@@ -113,7 +118,7 @@ long long ws_floats(const int* hdr, int V, int d, int L) {
     const long long M = hdr[REL_TAB + TAB_W * r + 2];
     Mmax = M > Mmax ? M : Mmax;
   }
-  const long long per_inst = 2 * (ldzel + H) * d + 7 * Nmax * d + 2 * Nmax * ldzel + 2 * Nmax * H + 2 * (Mmax + 1) * H + 2048;
+  const long long per_inst = 2 * (ldzel + H) * d + 8 * Nmax * d + 2 * Nmax * ldzel + 2 * Nmax * H + 2 * (Mmax + 1) * H + 2048;
   const long long per_type = (long long)B * d + 5 * Nmax * d + 2 * Nmax + 1024;
   fl += (long long)L * (2LL * nrel * per_inst + K * per_type);
   fl += 4LL * V * d + V + (long long)V * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 1024;
@@ -149,7 +154,13 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
 
   SideStreams* ss = srk_side_streams();
   cudaStream_t s4 = ss ? ss->s[6] : st;
+  constexpr int NP = 6;
+  cudaStream_t pool[NP];                    // [0] = the step's main stream
+  for (int i = 0; i < NP; ++i) pool[i] = ss ? ss->s[i] : st;
   auto order = [&](cudaStream_t from, cudaStream_t to) { return ss ? ss->order(from, to) : (int)SRK_OK; };
+  auto fork_all = [&]() -> int { for (int i = 1; i < NP; ++i) SRK_TRY(order(st, pool[i])); return SRK_OK; };
+  auto join_all = [&]() -> int { for (int i = 1; i < NP; ++i) SRK_TRY(order(pool[i], st)); return SRK_OK; };
+  auto type_stream = [&](int k) { return pool[(k - 1) % NP]; };
   SRK_TRY(srk_step_begin());
   SRK_TRY(order(st, s4));
   SRK_TRY(srk_zero_async(grads, sizeof(float) * (size_t)n_flat, s4));
@@ -177,6 +188,8 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
     const TypeView& t = b.t[k];
     ExpRec& e = ex[k];
     const int N = t.N, g0 = s_gru + (k - 2) * 4;
+    cudaStream_t st = type_stream(k);                 // shadows the main stream inside this loop body
+    SRK_TRY(order(pool[0], st));                      // the catalog pass has renormed the table
     e.dc = dcfg(SRK_SITE_EMBED + k);
     e.Xk = ar.f((size_t)N * k * d);
     e.hs[0] = ar.f((size_t)N * d);
@@ -198,6 +211,7 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
     SRK_TRY(srk_expander_combine_fwd(e.Xk, e.hs[k], N, k, d, e.out, e.rn, st));
     feat[k] = e.out;
   }
+  for (int k = 2; k <= K; ++k) SRK_TRY(order(type_stream(k), st));
 
   // MSHGNN layers: conv1 over every relation, conv2 over every reversed relation (msgifsr.py:70-91); a relation without edges
   // is skipped like HeteroGraphConv skips it
@@ -207,6 +221,8 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
     LayerRec& R = layers[l];
     R.normalize = (l == L - 1);
     for (int k = 1; k <= K; ++k) R.in[k] = feat[k];
+    SRK_TRY(fork_all());                           // the layer input is complete on the main stream
+    int rr = 0;
     for (int conv = 0; conv < 2; ++conv)
       for (int r = 0; r < b.nrel; ++r) {
         const RelView& rv = b.rel[r];
@@ -219,6 +235,11 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
         I.M = rv.M;
         const int e = inter ? K : rv.code - 1;
         I.pslot = 1 + ((l * 2 + conv) * (K + 1) + e) * 4;
+        // sq: one stream per parameter module - convolutions that share a module (`inter`: 2 (K - 1) of them) accumulate their
+        // weight gradients into the same rows, those kernels are serialised there; everything else of a convolution runs on sp
+        I.sq = pool[(inter ? 1 + conv : 3 + conv * K + e) % NP];
+        I.sp = pool[rr++ % NP];
+        cudaStream_t st = I.sp;                     // shadows the main stream for this convolution's chain
         const int gs = gat_slot(l, conv, inter, I.st, I.dt, K);
         const int Ns = b.t[I.st].N, Nd = b.t[I.dt].N;
         I.Waug = ar.f((size_t)ldzel * d);
@@ -253,9 +274,12 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
         g.attn_site = SRK_SITE_GAT_ATTN + 4 * gs;
         R.t[I.dt].inst.push_back(I);
       }
+    SRK_TRY(join_all());
+    SRK_TRY(fork_all());
     for (int k = 1; k <= K; ++k) {
       TypeRec& T = R.t[k];
       const int N = b.t[k].N;
+      cudaStream_t st = type_stream(k);            // the K aggregations run side by side
       SRK_REQUIRE((int)T.inst.size() <= SRK_MAX_GAT_INST, "msgifsr step: %d convolutions into one node type", (int)T.inst.size());
       float* segmean = ar.f((size_t)B * d);
       T.Hout = ar.f((size_t)N * d);
@@ -268,6 +292,7 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
       SRK_TRY(srk_gat_aggregate_fwd(arr.data(), (int)arr.size(), N, d, segmean, b.t[k].node2seg, drop ? &dc_attn : nullptr, R.normalize,
                                     T.Hout, T.rn, T.amax, st));
     }
+    SRK_TRY(join_all());
     for (int k = 1; k <= K; ++k) feat[k] = R.t[k].Hout;
   }
 
@@ -335,11 +360,33 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
 
   for (int l = L - 1; l >= 0; --l) {
     LayerRec& R = layers[l];
-    float* dfeat[MAXK + 1] = {nullptr};
+    // d(layer input of type k) = segment-mean term + one term per convolution out of / into the type: every term gets its own
+    // [N_k, d] slice of parts[k] and one pass adds them up
+    float *dfeat[MAXK + 1] = {nullptr}, *parts[MAXK + 1] = {nullptr};
+    int nterm[MAXK + 1] = {0};
+    for (int k = 1; k <= K; ++k) nterm[k] = 1;
+    for (int k = 1; k <= K; ++k)
+      for (Inst& I : R.t[k].inst) {
+        ++nterm[I.st];
+        ++nterm[k];
+      }
+    for (int k = 1; k <= K; ++k) {
+      const size_t nd = (size_t)b.t[k].N * d;
+      dfeat[k] = ar.f(nd);
+      parts[k] = ar.f(nd * nterm[k]);
+      nterm[k] = 1;                                  // slice 0 = segment-mean term; re-counted while the slices are handed out
+    }
+    SRK_REQUIRE(ar.ok, "msgifsr step: workspace too small");
+    for (int k = 1; k <= K; ++k)
+      for (Inst& I : R.t[k].inst) {
+        I.src_term = parts[I.st] + (size_t)b.t[I.st].N * d * nterm[I.st]++;
+        I.dst_term = parts[k] + (size_t)b.t[k].N * d * nterm[k]++;
+      }
+    SRK_TRY(fork_all());
     for (int k = 1; k <= K; ++k) {
       TypeRec& T = R.t[k];
       const int N = b.t[k].N;
-      dfeat[k] = ar.f((size_t)N * d);
+      cudaStream_t st = type_stream(k);
       T.dHpre = ar.f((size_t)N * d);
       std::vector<srk_gat_inst> arr;
       for (Inst& I : T.inst) {
@@ -351,47 +398,64 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
       SRK_REQUIRE(ar.ok, "msgifsr step: workspace too small");
       SRK_TRY(srk_gat_aggregate_bwd_dst(arr.data(), (int)arr.size(), N, d, drop ? &dc_attn : nullptr, R.normalize, T.Hout, T.rn, T.amax,
                                         dH[k], T.dHpre, st));
-      SRK_TRY(srk_segmean_bwd(T.dHpre, b.t[k].seg, B, d, dfeat[k], 0, st));          // first writer of dfeat[k]
+      SRK_TRY(srk_segmean_bwd(T.dHpre, b.t[k].seg, B, d, parts[k], 0, st));
     }
+    SRK_TRY(join_all());
+    SRK_TRY(fork_all());
     for (int k = 1; k <= K; ++k) {
       TypeRec& T = R.t[k];
       const int N = b.t[k].N;
       for (Inst& I : T.inst) {
         const int Ns = I.gi.n_src;
-        SRK_TRY(srk_gat_bias_bwd(T.dHpre, T.amax, N, d, G(I.pslot + 2), st));
+        cudaStream_t st = I.sp;
         SRK_TRY(srk_gat_aggregate_bwd_src(&I.gi, d, drop ? &dc_attn : nullptr, T.dHpre, T.amax, st));
-        float *dWaug = ar.f((size_t)ldzel * d), *dwr = ar.f((size_t)H * d);
+        float *dWaug = I.dWaug = ar.f((size_t)ldzel * d), *dwr = I.dwr = ar.f((size_t)H * d);
         SRK_REQUIRE(ar.ok, "msgifsr step: workspace too small");
         SRK_TRY(srk_zero2_async(dWaug, sizeof(float) * (size_t)ldzel * d, dwr, sizeof(float) * (size_t)H * d, st));
         SRK_TRY(mm_tn(st, ldzel, d, Ns, I.gi.dZel, ldzel, I.xs, d, dWaug, d));
         SRK_TRY(mm_tn(st, H, d, N, I.gi.der, H, I.xd, d, dwr, d));
-        SRK_TRY(srk_gat_prep_bwd(P(I.pslot + 3), P(I.pslot), P(I.pslot + 1), dWaug, dwr, d, G(I.pslot + 3), G(I.pslot), G(I.pslot + 1), st));
+        // source-copy term: mask_s(dZel W_aug); destination-copy term: mask_d(residual + der w_r)
+        float* tmp2 = ar.f((size_t)N * d);
         if (!drop) {
-          SRK_TRY(mm_nn(st, Ns, d, ldzel, I.gi.dZel, ldzel, I.Waug, d, dfeat[I.st], d, 1));
-          SRK_TRY(mm_nn(st, N, d, H, I.gi.der, H, I.wr, d, dfeat[k], d, 1));
-          SRK_TRY(srk_dropout_apply(T.dHpre, dfeat[k], (long long)N * d, nullptr, 1, st));      // residual
+          SRK_REQUIRE(ar.ok, "msgifsr step: workspace too small");
+          SRK_TRY(mm_nn(st, Ns, d, ldzel, I.gi.dZel, ldzel, I.Waug, d, I.src_term, d, 0));
         } else {
-          float *tmp = ar.f((size_t)Ns * d), *tmp2 = ar.f((size_t)N * d), *tmp3 = ar.f((size_t)N * d);
+          float* tmp = ar.f((size_t)Ns * d);
           SRK_REQUIRE(ar.ok, "msgifsr step: workspace too small");
           SRK_TRY(mm_nn(st, Ns, d, ldzel, I.gi.dZel, ldzel, I.Waug, d, tmp, d, 0));
-          SRK_TRY(srk_dropout_apply(tmp, dfeat[I.st], (long long)Ns * d, &I.dcs, 1, st));
-          SRK_TRY(mm_nn(st, N, d, H, I.gi.der, H, I.wr, d, tmp2, d, 0));
-          SRK_TRY(srk_dropout_apply_add(T.dHpre, tmp2, tmp3, (long long)N * d, &I.dcd, st));    // mask(residual + der w_r)
-          SRK_TRY(srk_dropout_apply(tmp3, dfeat[k], (long long)N * d, nullptr, 1, st));
+          SRK_TRY(srk_dropout_apply(tmp, I.src_term, (long long)Ns * d, &I.dcs, 0, st));
         }
+        SRK_TRY(mm_nn(st, N, d, H, I.gi.der, H, I.wr, d, tmp2, d, 0));
+        SRK_TRY(srk_dropout_apply_add(T.dHpre, tmp2, I.dst_term, (long long)N * d, drop ? &I.dcd : nullptr, st));
       }
     }
+    SRK_TRY(join_all());
+    SRK_TRY(fork_all());
+    for (int k = 1; k <= K; ++k) {
+      const long long nd = (long long)b.t[k].N * d;
+      SRK_TRY(srk_sum_parts(parts[k], nd, nterm[k], nd, dfeat[k], 0, type_stream(k)));
+    }
+    // the kernels that accumulate into a module's gradient rows, one module per stream
+    for (int k = 1; k <= K; ++k)
+      for (Inst& I : R.t[k].inst) {
+        SRK_TRY(srk_gat_bias_bwd(R.t[k].dHpre, R.t[k].amax, b.t[k].N, d, G(I.pslot + 2), I.sq));
+        SRK_TRY(srk_gat_prep_bwd(P(I.pslot + 3), P(I.pslot), P(I.pslot + 1), I.dWaug, I.dwr, d, G(I.pslot + 3), G(I.pslot), G(I.pslot + 1),
+                                 I.sq));
+      }
+    SRK_TRY(join_all());
     for (int k = 1; k <= K; ++k) dH[k] = dfeat[k];
   }
 
-  // the scatter-adds touch the table rows the catalog backward writes
-  SRK_TRY(order(s4, st));
+  float* dXk_of[MAXK + 1] = {nullptr};
+  SRK_TRY(fork_all());
   for (int k = 2; k <= K; ++k) {
     const TypeView& t = b.t[k];
     ExpRec& x = ex[k];
     const int N = t.N, g0 = s_gru + (k - 2) * 4;
+    cudaStream_t st = type_stream(k);
     float *dXk = ar.f((size_t)N * k * d), *dh = ar.f((size_t)N * d), *dprev = ar.f((size_t)N * d);
     SRK_REQUIRE(ar.ok, "msgifsr step: workspace too small");
+    dXk_of[k] = dXk;
     SRK_TRY(srk_expander_combine_bwd(x.out, x.rn, dH[k], N, k, d, dh, dXk, st));
     for (int step = k - 1; step >= 0; --step) {
       float *gi = x.gi[step], *gh = x.gh[step];
@@ -404,11 +468,18 @@ int body(const int* batch_dev, const int* hdr, float* params, float* grads, cons
       SRK_TRY(mm_nn(st, N, d, 3 * d, gh, 3 * d, P(g0 + 1), d, dprev, d, 1));
       float* t2 = dh; dh = dprev; dprev = t2;
     }
-    SRK_TRY(srk_embed_scatter_bwd_ws(E, t.iid, t.perm, t.uoff, t.uid, t.U, t.P, d, SRK_NORM_NONE, drop ? &x.dc : nullptr, nullptr, dXk,
-                                     nullptr, G(0), nullptr, st));
   }
+  // the scatter-adds update table rows in place (and the catalog backward wrote the same rows): one after the other on the
+  // main stream
+  SRK_TRY(order(s4, st));
   SRK_TRY(srk_embed_scatter_bwd_ws(E, b.t[1].iid, b.t[1].perm, b.t[1].uoff, b.t[1].uid, b.t[1].U, b.t[1].P, d, SRK_NORM_L2,
                                    drop ? &dc_e : nullptr, rnX, dH[1], nullptr, G(0), nullptr, st));
+  SRK_TRY(join_all());
+  for (int k = 2; k <= K; ++k) {
+    const TypeView& t = b.t[k];
+    SRK_TRY(srk_embed_scatter_bwd_ws(E, t.iid, t.perm, t.uoff, t.uid, t.U, t.P, d, SRK_NORM_NONE, drop ? &ex[k].dc : nullptr, nullptr,
+                                     dXk_of[k], nullptr, G(0), nullptr, st));
+  }
   if (phase == 0 && do_adam)
     SRK_TRY(srk_adam_step(params, grads, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
                           adam_step, grad_scale, st));
