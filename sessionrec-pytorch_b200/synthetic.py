@@ -12,7 +12,7 @@ CONFIGS = {
     'cfg3': dict(model='NISER', V=29510, d=64, B=128, order=1, layers=2, dropout=0.5, note='Gowalla shape, per rank'),
     'cfg4': dict(model='MSGIFSR', V=29618, d=256, B=512, order=1, layers=1, dropout=0.1, note='Yoochoose1/4 shape'),
     # not a BASELINE config: the reference's argparse default order (main_msgifsr.py:84) at the cfg1 shape; K > 1 runs through
-    # the staged composition of the kernels (no one-call native step)
+    # the general native step (csrc/step_k.cu: k-gram node types, intra / inter relations, ~330 launches per step)
     'cfg1k3': dict(model='MSGIFSR', V=43097, d=96, B=512, order=3, layers=1, dropout=0.1, note='Diginetica shape, order 3'),
 }
 
