@@ -412,11 +412,13 @@ int srk_shard_lse_pack(const float* lse_local, const float* nll_local, const int
                        float bound, int B, float* pack, void* stream);
 int srk_shard_lse_unpack(const float* pack, const float* shift, float bound, int B, float* lse, float* nll, void* stream);
 
-/* CUDA-graph replay of the native step's backward half: after two warm-up steps per model configuration its ~40
- * launches (7 streams) are captured once; later steps only rewrite the kernel-node parameters and issue one
- * cudaGraphLaunch.  Default: on for data-parallel steps (phase 1), where the ranks share the host CPU; SESSREC_GRAPH=1
- * forces it for every step, SESSREC_GRAPH=0 turns it off.  srk_set_graph_mode(0 never / 1 always / 2 auto) overrides the environment; the counters tell how many steps were
- * replayed and how many update passes had to fall back to plain launches. */
+/* CUDA-graph replay of the native step's backward half: after two warm-up steps per model configuration its ~35
+ * launches (7 streams) are captured once (programmatic-dependent-launch edges included); later steps only rewrite the
+ * kernel-node parameters that changed and issue one cudaGraphLaunch.  srk_set_graph_mode: 0 never, 1 always, 2 auto (default;
+ * SESSREC_GRAPH=0/1 overrides): data-parallel steps always replay (the ranks share the host CPU); a single-rank step times
+ * steps 2..5 on the host and on the device and replays from step 6 on when the enqueue time is at least 0.85 of the device
+ * time, i.e. when the host is the bottleneck on this machine.  The counters tell how many steps were replayed, how many update passes had to
+ * fall back to plain launches and how many nodes were rewritten. */
 int srk_set_graph_mode(int on);
 /* Whole-step graph: forward, backward and optimizer of a single-rank step (phase 0) as ONE graph.  An update pass leaves a
  * kernel node alone when its launch configuration and arguments are byte-identical to what the node holds, so with batches

@@ -47,10 +47,11 @@ int srk_launch_raw(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
     ++c->cursor;
     return SRK_OK;
   }
-  // SESSREC_PDL: 0 off, 1 (default) programmatic dependent launch for plain launches, 2 also while capturing a graph
+  // SESSREC_PDL: 0 off, 1 programmatic dependent launch for plain launches only, 2 (default) also while capturing a graph
+  // (programmatic edges between the kernel nodes; cfg1 backward-half replay 0.3625 -> 0.3493 ms per step)
   static const int pdl = [] {
     const char* e = getenv("SESSREC_PDL");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 2;
   }();
   // A kernel that is scheduled early holds its SM resources while it waits for its producers: only launches whose
   // footprint is a fraction of the machine may, or they crowd out the side streams.  Measured (B200, r2x): no limit 0.350 /

@@ -5,6 +5,7 @@
 // drive stage by stage (msgifsr.py::MSGIFSR._fwd/_bwd is the readable twin and the parity reference of this file).
 // All temporaries come from a caller-provided device workspace through a bump allocator; nothing is allocated,
 // nothing synchronises; ~60 kernel launches are enqueued back to back on the given stream.
+#include <chrono>
 #include <map>
 #include <mutex>
 
@@ -662,6 +663,11 @@ struct GraphEntry {
   int seen = 0, fails = 0;
   bool bad = false;
   SrkStepGraph g;
+  // auto policy of single-rank steps: host and device time of steps 2..5 (warm, plain launches) decide once
+  static constexpr int NMEAS = 4;
+  int decided = -1;                     // -1 not yet, 0 plain launches, 1 graph replay
+  cudaEvent_t ev0[NMEAS] = {nullptr}, ev1[NMEAS] = {nullptr};
+  double host_ms = 0.0;
 };
 
 }  // namespace
@@ -692,7 +698,7 @@ int srk_step_boundary() {
 // warm-up steps the sequence is therefore captured ONCE into a CUDA graph (per model configuration `key`); every later
 // step only rewrites the kernel-node parameters (shapes and pointers change with the batch, the sequence does not) and
 // issues one cudaGraphLaunch.  SESSREC_GRAPH=0 disables it; any mismatch falls back to plain launches for that step.
-int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body_on,
+int srk_step_driver(cudaStream_t caller, unsigned long long key, int want_graph, const std::function<int(void*)>& body_on,
                     bool whole) {
   // The step runs on our own high-priority stream s[0] (the user's stream may be the legacy default stream, which can
   // neither be prioritised nor captured); it is ordered after / before the user's stream with events.
@@ -710,9 +716,50 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
 
   static std::mutex mu;
   static std::map<unsigned long long, GraphEntry> cache;
+  static const bool debug = getenv("SESSREC_GRAPH_DEBUG") != nullptr;
   std::lock_guard<std::mutex> lock(mu);
   GraphEntry& e = cache[key];
   ++e.seen;
+  if (want_graph == 2 && !e.bad && e.decided < 0) {
+    // Auto (single-rank steps): replay pays when the HOST is the bottleneck.  A cfg1 step needs ~0.29 ms of enqueue on a fast
+    // host against 0.34 ms on the GPU, but 0.45 ms on a slower one and 0.7-0.8 ms when the process shares its core (measured:
+    // replay then runs the step in 0.54 ms).  Steps 2..5 - warm, plain launches - are timed on both sides (wall clock inside
+    // the call, CUDA events around the step) and the sums decide once per configuration at step 6.
+    constexpr int NM = GraphEntry::NMEAS;
+    if (e.seen == 1) return body();
+    if (e.seen <= 1 + NM) {
+      const int i = e.seen - 2;
+      if (cudaEventCreate(&e.ev0[i]) != cudaSuccess || cudaEventCreate(&e.ev1[i]) != cudaSuccess) {
+        cudaGetLastError();
+        e.decided = 0;
+        return body();
+      }
+      SRK_TRY(ss0->order_always(caller, run));
+      SRK_CUDA(cudaEventRecord(e.ev0[i], run));
+      const auto t0 = std::chrono::steady_clock::now();
+      SRK_TRY(body_on_run());
+      e.host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      SRK_CUDA(cudaEventRecord(e.ev1[i], run));
+      SRK_TRY(ss0->order_always(run, caller));
+      return SRK_OK;
+    }
+    double dev_ms = 0.0;
+    bool timed = cudaEventSynchronize(e.ev1[NM - 1]) == cudaSuccess;
+    for (int i = 0; i < NM; ++i) {
+      float ms = 0.f;
+      timed = timed && cudaEventElapsedTime(&ms, e.ev0[i], e.ev1[i]) == cudaSuccess;
+      dev_ms += ms;
+      cudaEventDestroy(e.ev0[i]);
+      cudaEventDestroy(e.ev1[i]);
+      e.ev0[i] = e.ev1[i] = nullptr;
+    }
+    if (!timed) cudaGetLastError();
+    e.decided = timed && e.host_ms >= 0.85 * dev_ms ? 1 : 0;
+    if (debug)
+      fprintf(stderr, "[sessrec graph] auto: steps 2..%d took %.3f ms of host enqueue, %.3f ms on the device -> %s\n", 1 + NM,
+              e.host_ms, dev_ms, e.decided ? "graph replay of the backward half" : "plain launches");
+  }
+  if (want_graph == 2 && e.decided == 0) return body();
   if (e.bad || e.seen <= 2) return body();          // warm-up steps also run every one-time cudaFuncSetAttribute
 
   // forward: plain launches; backward: captured once, afterwards its kernel nodes are re-parameterised and replayed
@@ -728,7 +775,6 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
   int rc = body_on_run();
   srk_set_launch_ctx(nullptr);
   bool ok = rc == SRK_OK && !ctx.failed;
-  static const bool debug = getenv("SESSREC_GRAPH_DEBUG") != nullptr;
   if (capture) {
     if (ctx.capturing) {
       const cudaError_t ce = cudaStreamEndCapture(run, &e.g.graph);
@@ -785,7 +831,7 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph
 // 0 never, 1 always, 2 auto (data-parallel steps: phase 1)
 // whole-step graph (forward + backward + optimizer as ONE graph): single-rank steps with the optimizer inside (phase 0).
 // SESSREC_GRAPH_WHOLE=1 always, =0 never; default: when the batch says it was padded to a fixed shape (header word 11).
-bool srk_step_want_graph(int phase);
+int srk_step_want_graph(int phase);
 static int g_whole_mode = -1;
 bool srk_step_want_whole(int phase, int padded) {
   int& mode = g_whole_mode;
@@ -798,15 +844,17 @@ bool srk_step_want_whole(int phase, int padded) {
   return mode == 1 || (mode == 2 && padded != 0);
 }
 
-bool srk_step_want_graph(int phase) {
+// 0 = plain launches, 1 = replay the backward half as a graph, 2 = let the driver decide from the timing of the second step
+int srk_step_want_graph(int phase) {
   if (g_graphs_on < 0) {
     const char* e = getenv("SESSREC_GRAPH");
     g_graphs_on = !e ? 2 : (e[0] == '0' ? 0 : 1);
   }
-  // auto: replay pays off when the host is the bottleneck, i.e. when several ranks share the CPU (measured on 8 x B200:
-  // 0.83 -> 0.32 ms of enqueue per step, 4.8 M -> 6.8 M sessions/s); a single rank is GPU-bound either way and keeps the
-  // plain launches, whose first kernels start while the rest is still being enqueued
-  return g_graphs_on == 1 || (g_graphs_on == 2 && (phase == 1 || phase == 3));
+  if (g_graphs_on != 2) return g_graphs_on;
+  // auto: replay pays off when the host is the bottleneck.  Data-parallel steps: several ranks share the CPU (measured on
+  // 8 x B200: 0.83 -> 0.32 ms of enqueue per step, 5.7 M -> 8.3 M sessions/s) - always.  A single rank: depends on the host
+  // (see srk_step_driver) - measured.
+  return (phase == 1 || phase == 3) ? 1 : 2;
 }
 
 // phase: 0 = everything; 1 = zero_grad + forward + backward only (no Adam): lets the caller all-reduce the gradients;
@@ -833,7 +881,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
                                  ((unsigned long long)(do_adam != 0) << 2) | ((unsigned long long)has_edges << 1) |
                                  (unsigned long long)(head_chunks > 1);
   const bool whole = srk_step_want_whole(phase, batch_hdr_host[11]);
-  return srk_step_driver(caller, key ^ ((unsigned long long)whole << 63), srk_step_want_graph(phase) || whole, [&](void* run) {
+  return srk_step_driver(caller, key ^ ((unsigned long long)whole << 63), whole ? 1 : srk_step_want_graph(phase), [&](void* run) {
     return step_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, dropout_p, seed, use_umma, workspace,
                      workspace_bytes, one_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg,
                      lr, beta1, beta2, eps, adam_step, grad_scale, phase, head_chunks, run);
@@ -841,7 +889,7 @@ extern "C" int srk_msgifsr_train_step(const int* batch_dev, const int* batch_hdr
 }
 
 extern "C" int srk_set_graph_mode(int on) {
-  g_graphs_on = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 never, 1 always, 2 auto (data-parallel steps only)
+  g_graphs_on = on < 0 ? 0 : (on > 2 ? 2 : on);      // 0 never, 1 always, 2 auto (srk_step_want_graph)
   return SRK_OK;
 }
 

@@ -136,7 +136,7 @@ SideStreams* srk_side_streams();
 // constant shape at constant addresses (padded batches, see batch_builder.cu) an update pass then finds nearly every node
 // unchanged (launch.cu compares the argument bytes) and the host cost of a step is the bookkeeping of its body plus one
 // cudaGraphLaunch.
-int srk_step_driver(cudaStream_t caller, unsigned long long key, bool want_graph, const std::function<int(void*)>& body,
+int srk_step_driver(cudaStream_t caller, unsigned long long key, int want_graph, const std::function<int(void*)>& body,
                     bool whole = false);
 int srk_step_begin();
 // srk_readout_bwd that also writes the TF32 hi / lo pair of du (csrc/readout_ce.cu)
@@ -154,4 +154,4 @@ int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t
 bool srk_step_want_whole(int phase, int padded);      // SESSREC_GRAPH_WHOLE policy
 // forward / backward boundary of a step body: starts the capture (or switches to node updates) when the driver asked for it
 int srk_step_boundary();
-bool srk_step_want_graph(int phase);      // SESSREC_GRAPH / srk_set_graph_mode policy
+int srk_step_want_graph(int phase);       // SESSREC_GRAPH / srk_set_graph_mode policy: 0 plain, 1 replay, 2 measure and decide

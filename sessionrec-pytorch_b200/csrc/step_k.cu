@@ -509,7 +509,7 @@ extern "C" int srk_msgifsr_k_train_step(const int* batch_dev, const int* batch_h
   SRK_REQUIRE(K >= 1 && K <= MAXK, "msgifsr step: order %d unsupported", K);
   SRK_REQUIRE(n_slots == 1 + L * 2 * (K + 1) * 4 + (K - 1) * 4 + 5, "msgifsr step: slot table of %d entries does not fit order %d, %d layers",
               n_slots, K, L);
-  return srk_step_driver(caller, 0, false, [&](void* run) {
+  return srk_step_driver(caller, 0, 0, [&](void* run) {
     return body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, dropout_p, seed, flags, workspace, workspace_bytes,
                 gseed_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev, seg_decay_dev, n_seg, lr, beta1, beta2, eps,
                 adam_step, grad_scale, phase, run);

@@ -457,7 +457,7 @@ extern "C" int srk_srgnn_train_step(const int* batch_dev, const int* batch_hdr_h
                                  ((unsigned long long)(niser != 0) << 2) | ((unsigned long long)(dead_layers != 0) << 1) |
                                  (unsigned long long)(do_adam != 0 && phase == 0) | ((unsigned long long)(phase == 3) << 62);
   const bool whole = srk_step_want_whole(phase, batch_hdr_host[11]);
-  return srk_step_driver(caller, key ^ ((unsigned long long)whole << 61), srk_step_want_graph(phase) || whole, [&](void* run) {
+  return srk_step_driver(caller, key ^ ((unsigned long long)whole << 61), whole ? 1 : srk_step_want_graph(phase), [&](void* run) {
     return srgnn_body(batch_dev, batch_hdr_host, params, grads, slot_off_host, V, d, L, niser, scale, dead_layers, dropout_p, seed,
                       flags, workspace, workspace_bytes, gseed_dev, loss_out, do_adam, exp_avg, exp_avg_sq, n_flat, seg_off_dev,
                       seg_decay_dev, n_seg, lr, beta1, beta2, eps, adam_step, grad_scale, phase, run);

@@ -399,11 +399,11 @@ def test_native_order_k_step_matches_staged_composition(pkg, K, d, L, p):
     (m1, l1), (m2, l2) = res
     for a, b_ in zip(l1, l2):
         assert abs(a - b_) <= 5e-6 * abs(b_), (l1, l2)
-    # d = 256: the staged composition sends its big products to the 3xTF32 tensor-core GEMM, the native step keeps them in fp32;
-    # Adam turns a 1e-6 difference of a near-zero gradient into a visible step for a handful of the 640 000 table entries
-    rtol = 1e-3 if d >= 256 else 1e-4
+    # The two paths are not bitwise identical (atomics in the one-launch scatter-add and the split-K products; at d = 256 the
+    # staged composition sends its big products to the 3xTF32 tensor-core GEMM, the native step keeps them in fp32) and Adam
+    # turns a 1e-9 difference of a near-zero gradient into a visible step: see assert_close_after_adam
     for (n, q1), (_, q2) in zip(m1.named_parameters(), m2.named_parameters()):
-        assert_close(f'native vs staged {n}', q1, q2, rtol=rtol, floor=0.5)
+        assert_close_after_adam(f'native vs staged {n}', q1, q2, 1e-3, 3, rtol=1e-4, floor=0.5, max_frac=1e-4)
 
 
 @pytest.mark.parametrize('model,d,L', [('SRGNN', 256, 1), ('NISER', 64, 2), ('SRGNN', 96, 2)])
