@@ -416,7 +416,7 @@ int srk_shard_lse_unpack(const float* pack, const float* shift, float bound, int
  * launches (7 streams) are captured once (programmatic-dependent-launch edges included); later steps only rewrite the
  * kernel-node parameters that changed and issue one cudaGraphLaunch.  srk_set_graph_mode: 0 never, 1 always, 2 auto (default;
  * SESSREC_GRAPH=0/1 overrides): data-parallel steps always replay (the ranks share the host CPU); a single-rank step times
- * steps 2..5 on the host and on the device and replays from step 6 on when the enqueue time is at least 0.85 of the device
+ * steps 2 and 3 on the host and on the device and replays from step 4 on when the enqueue time is at least 0.85 of the device
  * time, i.e. when the host is the bottleneck on this machine.  The counters tell how many steps were replayed, how many update passes had to
  * fall back to plain launches and how many nodes were rewritten. */
 int srk_set_graph_mode(int on);

@@ -663,8 +663,9 @@ struct GraphEntry {
   int seen = 0, fails = 0;
   bool bad = false;
   SrkStepGraph g;
-  // auto policy of single-rank steps: host and device time of steps 2..5 (warm, plain launches) decide once
-  static constexpr int NMEAS = 4;
+  // auto policy of single-rank steps: host and device time of steps 2 and 3 (warm, plain launches) decide once, so that a
+  // capture happens at step 4 - inside the warm-up of any training loop or benchmark
+  static constexpr int NMEAS = 2;
   int decided = -1;                     // -1 not yet, 0 plain launches, 1 graph replay
   cudaEvent_t ev0[NMEAS] = {nullptr}, ev1[NMEAS] = {nullptr};
   double host_ms = 0.0;
@@ -723,8 +724,8 @@ int srk_step_driver(cudaStream_t caller, unsigned long long key, int want_graph,
   if (want_graph == 2 && !e.bad && e.decided < 0) {
     // Auto (single-rank steps): replay pays when the HOST is the bottleneck.  A cfg1 step needs ~0.29 ms of enqueue on a fast
     // host against 0.34 ms on the GPU, but 0.45 ms on a slower one and 0.7-0.8 ms when the process shares its core (measured:
-    // replay then runs the step in 0.54 ms).  Steps 2..5 - warm, plain launches - are timed on both sides (wall clock inside
-    // the call, CUDA events around the step) and the sums decide once per configuration at step 6.
+    // replay then runs the step in 0.54 ms).  Steps 2 and 3 - warm, plain launches - are timed on both sides (wall clock inside
+    // the call, CUDA events around the step) and the sums decide once per configuration at step 4.
     constexpr int NM = GraphEntry::NMEAS;
     if (e.seen == 1) return body();
     if (e.seen <= 1 + NM) {
