@@ -791,6 +791,7 @@ struct FceWide {
   float* cand_val;
   int* cand_idx;
   int dz_tmem;             // bwd: dZ also lives in TMEM (A operand of the dS product); the logit tile is then single-buffered
+  int de_atomic;           // bwd: dEpart is ONE zero-initialised [V][d] buffer that every session tile adds into (red.global.add)
 };
 
 struct WideSched {
@@ -1241,7 +1242,9 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
     const int r = q * 32 + lane;
     const uint32_t lanebits = (uint32_t)(q * 32) << 16;
     const bool elected = (warp == 2 + EPI_WARPS && lane == 0);
-    float* outp = p.dEpart + (long long)ts.tb * p.V * p.d;
+    // de_atomic: all session tiles add into one [V, d] buffer with coalesced 128-byte reductions in L2 (where a 17 MB buffer
+    // stays resident) instead of writing one partial table per session tile to HBM for a later pass to add up
+    float* outp = p.de_atomic ? p.dEpart : p.dEpart + (long long)ts.tb * p.V * p.d;
     for (int it = 0; it < ntiles; ++it) {
       mbar_wait(&d_empty, (uint32_t)it & 1u);
       fence_tc_after();
@@ -1257,7 +1260,11 @@ fce_bwd_wide_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_consta
           if (lane == 0) mbar_arrive(&de_free);
         }
         float* col = outp + (long long)(v0 + vo) * p.d + h * 128 + r;
-        if (v0 + vo + 32 <= p.V) {
+        if (p.de_atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (v0 + vo + j < p.V) atomicAdd(col + (long long)j * p.d, __uint_as_float(a[j]));
+        } else if (v0 + vo + 32 <= p.V) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) col[(long long)j * p.d] = __uint_as_float(a[j]);
         } else {
@@ -1500,9 +1507,10 @@ int wide_fwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long
 
 int wide_bwd(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi, const uint16_t* Elo,
              long long lde, float scale, const int* labels, const float* lse, const float* gout, float* dS, float* dEpart,
-             bool ds_zeroed, cudaStream_t st) {
+             bool ds_zeroed, bool de_atomic, cudaStream_t st) {
   FceWide p;
   SRK_TRY(fill_wide(p, B, V, d, scale, labels, true));
+  p.de_atomic = de_atomic;
   p.lse = lse;
   p.gout = gout;
   p.dEpart = dEpart;
@@ -1680,14 +1688,17 @@ extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const 
   return srk_flash_ce_bwd_ex(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, 0, stream);
 }
 
-// ds_zeroed: the caller has zeroed dS already (the native steps zero it with their scratch pool): no memset launch here
+// ds_zeroed bit 0: the caller has zeroed dS already (the native steps zero it with their scratch pool): no memset launch here.
+// bit 1 (d > 128 only): dEpart is ONE zero-initialised [V, d] buffer - e.g. the table's gradient rows themselves - that the
+// kernel adds into, instead of srk_flash_ce_bwd_parts(B) partial tables
 int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
                         const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,
                         float* dS, float* dEpart, int ds_zeroed, void* stream) {
   if (B <= 0) return SRK_OK;
   SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && dS != nullptr && dEpart != nullptr, "flash_ce_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d > 128) return wide_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, ds_zeroed != 0, st);
+  SRK_REQUIRE(!(ds_zeroed & 2) || d > 128, "flash_ce_bwd: the accumulating dE form exists for the wide kernels (d > 128) only");
+  if (d > 128) return wide_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, (ds_zeroed & 1) != 0, (ds_zeroed & 2) != 0, st);
   FceParams p;
   SRK_TRY(fill_params(p, B, V, d, scale, labels, true));
   p.lse = lse;
@@ -1715,7 +1726,7 @@ int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t
     SRK_CUDA(cudaFuncSetAttribute(fce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCE_MAX_SMEM));
     attr_set = true;
   }
-  if (!ds_zeroed) SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
+  if (!(ds_zeroed & 1)) SRK_TRY(srk_zero_async(dS, sizeof(float) * (size_t)B * d, st));
   srk_launch(fce_bwd_kernel, p.ntm * p.nvr, THREADS_BWD, smem_bytes(p, true), st, mSh, mSl, mEh, mEl, mdE, mdS, p);
   SRK_LAUNCH_CHECK();
   return SRK_OK;

@@ -112,7 +112,7 @@ extern "C" long long srk_msgifsr_workspace_bytes(int B, int N, int M, int V, int
   // backward per layer (reused across layers): dHpre, dfeat, per inst dedge, der, dZel, dWaug, dwr, tmp, tmp2
   fl += 8LL * N * d + 2 * ((long long)(M + 1) * H + N * H + N * ldzel + (ldzel + H) * d + 2LL * N * d);
   fl += (long long)L * 2 * (2 * ldzel * d + 2LL * N * d) + 2 * (2LL * N * ldzel);     // opt-in tensor-core projections: hi / lo copies
-  fl += (long long)L * 2 * (ldzel * d + (long long)H * d + (long long)N * d + 192) + 2LL * B * d + 192;      // zeroed pool
+  fl += (long long)L * 2 * (ldzel * d + (long long)H * d + (long long)N * d + 192) + 2LL * B * d + 256 + (long long)V * d;      // zeroed pool
   return fl * 5 + (1 << 20);                               // floats -> bytes with 25% head-room + alignment slack
 }
 
@@ -183,8 +183,11 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   // zero_grad runs beside the forward pass; the first gradient is written after the head's backward.  Every scratch buffer of
   // the step that is accumulated into (split-K GEMM outputs, staged weight gradients, dS of the fused head) comes from ONE
   // pool that the same launch zeroes: 8 zero-fill launches less per step, three of them on the critical path.
+  // wide fused head (d > 128): the session tiles add their table gradient into ONE zeroed [Vl, d] buffer (see step_srgnn.cu)
+  static const bool de_atomic_on = [] { const char* e = getenv("SESSREC_FCE_DE_ATOMIC"); return !(e && e[0] == '0'); }();
+  const bool de_atomic = flash && d > 128 && de_atomic_on;
   const size_t zp_bytes = sizeof(float) * ((size_t)L * 2 * ((size_t)ldzel * d + (size_t)H * d + (size_t)N * d + 192) +
-                                            2 * (size_t)b.B * d + 192);
+                                            2 * (size_t)b.B * d + 256 + (de_atomic ? (size_t)Vl * d : 0));
   Arena zp{ar.raw(zp_bytes), zp_bytes, 0, true};
   SRK_REQUIRE(ar.ok, "step: workspace too small");
   SRK_TRY(order(st, s4));
@@ -423,13 +426,15 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   SRK_TRY(order(st, s2));
   SRK_TRY(srk_mean(nll, B, loss_out, s2));
   // ---- backward ------------------------------------------------------------------------------------------
-  const int de_parts = flash ? srk_flash_ce_bwd_parts(B) : 1;
+  const int de_parts = (flash && !de_atomic) ? srk_flash_ce_bwd_parts(B) : 1;
   float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;
   const bool ds_pooled = flash && !shard;       // dS accumulates (TMA reduce-add): zeroed with the pool
-  float *dshat = shard ? dshat_x : (ds_pooled ? zp.f((size_t)B * d) : ar.f((size_t)B * d)), *dEhat = ar.f((size_t)de_parts * Vl * d);
+  float *dshat = shard ? dshat_x : (ds_pooled ? zp.f((size_t)B * d) : ar.f((size_t)B * d));
+  float* dEhat = de_atomic ? zp.f((size_t)Vl * d) : ar.f((size_t)de_parts * Vl * d);
   SRK_REQUIRE(ar.ok && zp.ok, "step: workspace too small");
   if (flash) {
-    SRK_TRY(srk_flash_ce_bwd_ex(B, Vl, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, hlabels, lse, one_dev, dshat, dEhat, ds_pooled, st));
+    SRK_TRY(srk_flash_ce_bwd_ex(B, Vl, d, Sbh, Sbl, d, Ebh, Ebl, d, 12.0f, hlabels, lse, one_dev, dshat, dEhat,
+                                (ds_pooled ? 1 : 0) | (de_atomic ? 2 : 0), st));
   } else if (umma) {
     SRK_TRY(srk_zero_async(dshat, sizeof(float) * (size_t)B * d, st));
     // Backward of the head, chunked over catalog columns so that each chunk's dZ hi/lo pair (2 x B x Vc x 4 bytes) is

@@ -107,7 +107,7 @@ extern "C" long long srk_srgnn_workspace_bytes(int B, int N, int M, int V, int d
   fl += (long long)V * d + B * d + srk_flash_ce_part_floats(B, V) + (long long)srk_flash_ce_bwd_parts(B) * V * d + 256;   // flash head
   fl += 4LL * B * d + 3LL * N * d + (long long)(N + 4) * d;  // dshat, ds, dsr_in, dF, dX, scatter partials
   fl += 3 * scratch_floats(B, N, d);                         // tensor-core operand splits: one region per stream
-  fl += 4LL * N * d + 8LL * B * d + 14LL * d * d + 8192;     // TF32 pairs made once: F, du, sr_in, ds, read-out weights; zero pool
+  fl += 4LL * N * d + 8LL * B * d + 14LL * d * d + 8192 + (long long)V * d;     // TF32 pairs made once: F, du, sr_in, ds, read-out weights; zero pool
   return fl * 4 + fl + (1 << 20);                            // floats -> bytes with 25% head-room + alignment slack
 }
 
@@ -150,11 +150,18 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   // dS of the head accumulates (TMA reduce-add / split-K): it is zeroed by the launch that zeroes the gradient buffer
   // ... together with the two session-level products that run split-K (fc_sr and its data gradient: 16 row tiles only)
   const size_t bd = (size_t)b.B * d;
-  float* zpool = ar.f(4 * bd);
+  // Wide fused head (d > 128): every session tile ADDS its table gradient into one [V, d] buffer (coalesced reductions in L2)
+  // instead of writing B / 128 partial tables that a later pass sums (278 MB written + read at cfg2).  SRGNN scores the table
+  // itself, so the buffer is the table's gradient rows (zeroed by zero_grad); NISER needs dEhat apart for the row-normalisation
+  // backward: a zeroed buffer from the pool.  SESSREC_FCE_DE_ATOMIC=0 keeps the partial tables.
+  static const bool de_atomic_on = [] { const char* e = getenv("SESSREC_FCE_DE_ATOMIC"); return !(e && e[0] == '0'); }();
+  const bool de_atomic = flash && d > 128 && de_atomic_on;
+  const size_t zextra = (de_atomic && niser) ? (size_t)V * d : 0;
+  float* zpool = ar.f(4 * bd + zextra);
   float *dshat = zpool, *s = zpool + bd, *dsr_in = zpool + 2 * bd;
   SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   SRK_TRY(order(st, s4));
-  SRK_TRY(srk_zero2_async(grads, sizeof(float) * (size_t)n_flat, zpool, sizeof(float) * 4 * bd, s4));
+  SRK_TRY(srk_zero2_async(grads, sizeof(float) * (size_t)n_flat, zpool, sizeof(float) * (4 * bd + zextra), s4));
   // Every tensor-core product of the live path reads operands whose TF32 hi / lo pair is made ONCE: by the operand's producer
   // (dropout pass, read-out backward) or by one split launch per tensor - not once per product.  The read-out weights are
   // split here, beside the gather.
@@ -329,10 +336,10 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   float* Zlo = (umma && !flash) ? ar.f((size_t)B * ldz) : nullptr;
   // SRGNN scores the table itself: without row normalisation the head's table gradient IS d E, accumulated straight
   // into the (zeroed) gradient buffer by the materialised paths; the fused head leaves per-tile partials to be summed
-  float* dEhat = (niser || flash) ? ar.f((size_t)de_parts * V * d) : G(0);
+  float* dEhat = de_atomic ? (niser ? zpool + 4 * bd : G(0)) : ((niser || flash) ? ar.f((size_t)de_parts * V * d) : G(0));
   SRK_REQUIRE(ar.ok, "srgnn step: workspace too small");
   if (flash) {
-    SRK_TRY(srk_flash_ce_bwd_ex(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, scale, b.labels, lse, gseed_dev, dshat, dEhat, 1, st));
+    SRK_TRY(srk_flash_ce_bwd_ex(B, V, d, Sbh, Sbl, d, Ebh, Ebl, d, scale, b.labels, lse, gseed_dev, dshat, dEhat, de_atomic ? 3 : 1, st));
   } else {
     SRK_TRY(srk_ce_rows_bwd(Z, ldz, b.labels, lse, gseed_dev, scale, B, V, 0, Zlo, st));
     if (umma) {
@@ -352,8 +359,8 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   // the catalog-wide part of the table gradient stays on s4 beside the encoder backward; it only has to finish before
   // the scatter-add touches the same rows
   SRK_TRY(order(st, s4));
-  if (niser) SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, de_parts, V, d, SRK_NORM_EPS, G(0), s4));
-  else if (flash) SRK_TRY(srk_sum_parts(dEhat, (long long)V * d, de_parts, (long long)V * d, G(0), 1, s4));
+  if (niser) SRK_TRY(srk_catalog_prep_bwd(E, Ehat, enorm, dEhat, de_atomic ? 1 : de_parts, V, d, SRK_NORM_EPS, G(0), s4));
+  else if (flash && !de_atomic) SRK_TRY(srk_sum_parts(dEhat, (long long)V * d, de_parts, (long long)V * d, G(0), 1, s4));
   const bool live = srk_launch_mode() == SRK_LAUNCH_DIRECT || srk_launch_mode() == SRK_LAUNCH_CAPTURE;
   if (ss && live) SRK_CUDA(cudaEventRecord(ss->ev_cat, s4));
   // Adam in two parts (see csrc/step.cu): the table rows this batch did not gather are final now
