@@ -73,6 +73,7 @@ struct FceParams {
   const float* lse;        // bwd: [B]
   const float* gout;       // bwd: upstream gradient of the mean loss (device scalar) or null
   float* dEpart;           // bwd: [ntm][V][d] partial table gradients, one per session tile
+  int de_atomic;           // bwd: dEpart is ONE zero-initialised [V][d] buffer, every session tile adds into it (TMA reduce-add)
   uint32_t idesc_z, idesc_ds, idesc_de;
   int a_tmem;              // fwd: the session operand (A of the logit product) lives in TMEM instead of shared memory
   const uint16_t *Shi, *Slo;   // fwd, a_tmem: bf16 hi / lo of shat in global memory, row pitch lds
@@ -707,6 +708,7 @@ fce_bwd_kernel(const __grid_constant__ CUtensorMap mSh, const __grid_constant__ 
       named_bar_sync(2, DRAIN_THREADS);
       if (elected) {
         if (reduce) tma_reduce_add_2d(&mdS, Stg, cc * 32, row0);
+        else if (p.de_atomic) tma_reduce_add_3d(&mdE, Stg, cc * 32, row0, 0);
         else tma_store_3d(&mdE, Stg, cc * 32, row0, ts.tb);
         tma_commit_group();
       }
@@ -1689,7 +1691,7 @@ extern "C" int srk_flash_ce_bwd(int B, int V, int d, const uint16_t* Shi, const 
 }
 
 // ds_zeroed bit 0: the caller has zeroed dS already (the native steps zero it with their scratch pool): no memset launch here.
-// bit 1 (d > 128 only): dEpart is ONE zero-initialised [V, d] buffer - e.g. the table's gradient rows themselves - that the
+// bit 1: dEpart is ONE zero-initialised [V, d] buffer - e.g. the table's gradient rows themselves - that the
 // kernel adds into, instead of srk_flash_ce_bwd_parts(B) partial tables
 int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t* Slo, long long lds, const uint16_t* Ehi,
                         const uint16_t* Elo, long long lde, float scale, const int* labels, const float* lse, const float* gout,
@@ -1697,16 +1699,16 @@ int srk_flash_ce_bwd_ex(int B, int V, int d, const uint16_t* Shi, const uint16_t
   if (B <= 0) return SRK_OK;
   SRK_REQUIRE(V > 0 && labels != nullptr && lse != nullptr && dS != nullptr && dEpart != nullptr, "flash_ce_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  SRK_REQUIRE(!(ds_zeroed & 2) || d > 128, "flash_ce_bwd: the accumulating dE form exists for the wide kernels (d > 128) only");
   if (d > 128) return wide_bwd(B, V, d, Shi, Slo, lds, Ehi, Elo, lde, scale, labels, lse, gout, dS, dEpart, (ds_zeroed & 1) != 0, (ds_zeroed & 2) != 0, st);
   FceParams p;
   SRK_TRY(fill_params(p, B, V, d, scale, labels, true));
   p.lse = lse;
   p.gout = gout;
   p.dEpart = dEpart;
+  p.de_atomic = (ds_zeroed & 2) != 0;
   CUtensorMap mSh, mSl, mEh, mEl, mdE, mdS;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)V, (cuuint64_t)p.ntm};
+    cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)V, (cuuint64_t)(p.de_atomic ? 1 : p.ntm)};
     cuuint64_t strides[2] = {(cuuint64_t)d * 4, (cuuint64_t)V * d * 4};
     cuuint32_t box[3] = {32, 128, 1};
     SRK_TRY(make_map_nd(&mdE, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dEpart, dims, strides, box));

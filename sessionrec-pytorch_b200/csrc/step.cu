@@ -185,7 +185,7 @@ static int step_body(const int* batch_dev, const int* batch_hdr_host, float* par
   // pool that the same launch zeroes: 8 zero-fill launches less per step, three of them on the critical path.
   // wide fused head (d > 128): the session tiles add their table gradient into ONE zeroed [Vl, d] buffer (see step_srgnn.cu)
   static const bool de_atomic_on = [] { const char* e = getenv("SESSREC_FCE_DE_ATOMIC"); return !(e && e[0] == '0'); }();
-  const bool de_atomic = flash && d > 128 && de_atomic_on;
+  const bool de_atomic = flash && de_atomic_on && srk_flash_ce_bwd_parts(b.B) > 1;      // one session tile: nothing to add up
   const size_t zp_bytes = sizeof(float) * ((size_t)L * 2 * ((size_t)ldzel * d + (size_t)H * d + (size_t)N * d + 192) +
                                             2 * (size_t)b.B * d + 256 + (de_atomic ? (size_t)Vl * d : 0));
   Arena zp{ar.raw(zp_bytes), zp_bytes, 0, true};

@@ -155,7 +155,7 @@ static int srgnn_body(const int* batch_dev, const int* batch_hdr_host, float* pa
   // itself, so the buffer is the table's gradient rows (zeroed by zero_grad); NISER needs dEhat apart for the row-normalisation
   // backward: a zeroed buffer from the pool.  SESSREC_FCE_DE_ATOMIC=0 keeps the partial tables.
   static const bool de_atomic_on = [] { const char* e = getenv("SESSREC_FCE_DE_ATOMIC"); return !(e && e[0] == '0'); }();
-  const bool de_atomic = flash && d > 128 && de_atomic_on;
+  const bool de_atomic = flash && de_atomic_on && srk_flash_ce_bwd_parts(b.B) > 1;      // one session tile: nothing to add up
   const size_t zextra = (de_atomic && niser) ? (size_t)V * d : 0;
   float* zpool = ar.f(4 * bd + zextra);
   float *dshat = zpool, *s = zpool + bd, *dsr_in = zpool + 2 * bd;
