@@ -285,9 +285,9 @@ class MSGIFSR(SessRecModule):
                 and self.num_layers >= 1 and self._shard is None and self.use_tensor_cores and self.flash_ce
                 and ops.flash_ce_supported(self.embedding_dim))
 
-    def _slot_offsets_k(self):
-        import numpy as np
-        fp, K = self._flat, self.order
+    def _slot_names_k(self):
+        """Parameter names in the slot order srk_msgifsr_k_train_step expects (include/sessrec_b200.h)."""
+        K = self.order
         names = ['embeddings.weight']
         for l in range(self.num_layers):
             for c in (1, 2):
@@ -297,7 +297,12 @@ class MSGIFSR(SessRecModule):
             names += [f'expander.GRUs.{k - 2}.{n}' for n in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')]
         names += ['readout.fc_u.0.weight', 'readout.fc_u.0.bias', 'readout.fc_v.0.weight', 'readout.fc_e.0.weight',
                   'fc_sr.0.weight']
-        return np.ascontiguousarray([fp.offsets[fp.index[n]] for n in names], dtype=np.int64)
+        return names
+
+    def _slot_offsets_k(self):
+        import numpy as np
+        fp = self._flat
+        return np.ascontiguousarray([fp.offsets[fp.index[n]] for n in self._slot_names_k()], dtype=np.int64)
 
     def _train_step_k(self, batch, group, global_batch):
         """One TrainRunner iteration of an order-K model in ONE C call (srk_msgifsr_k_train_step)."""

@@ -181,3 +181,22 @@ def test_adam_segments_for_inactive_parameters_and_owned_rows(pkg):
     assert off.tolist() == [e0, e0 + 3 * 8, e0 + 7 * 8, names['lin.weight'], names['lin.bias'], fp.total]
     assert dec.tolist()[0] == -1.0 and abs(dec.tolist()[1] - 1e-4) < 1e-9 and dec.tolist()[2] == -1.0      # only rows [3, 7) are ours
     assert dec.tolist()[3] == -1.0 and dec.tolist()[4] == 0.0                                                # inactive weight, bias without decay
+
+
+@pytest.mark.parametrize('K,L', [(2, 1), (3, 2), (4, 1)])
+def test_order_k_native_step_slot_table(K, L):
+    """The slot table handed to srk_msgifsr_k_train_step (csrc/step_k.cu): every name is a parameter of the module, no name
+    twice, and the count is the one the C side checks (1 + L*2*(K+1)*4 + (K-1)*4 + 5)."""
+    from __graft_entry__ import load_package
+    load_package()
+    from sessionrec_pytorch_b200.msgifsr import MSGIFSR
+    m = MSGIFSR(300, 'x', 16, L, dropout=0.1, order=K, extra=False, fusion=False)
+    names = m._slot_names_k()
+    params = dict(m.named_parameters())
+    assert all(n in params for n in names), [n for n in names if n not in params]
+    assert len(set(names)) == len(names) == 1 + L * 2 * (K + 1) * 4 + (K - 1) * 4 + 5
+    # shapes the step relies on
+    d = 16
+    assert tuple(params[f'expander.GRUs.{K - 2}.weight_ih_l0'].shape) == (3 * d, d)
+    assert tuple(params['layers.0.conv1.mods.inter.fc.weight'].shape) == (8 * d, d)
+    assert tuple(params['fc_sr.0.weight'].shape) == (d, 2 * d)
