@@ -12,6 +12,8 @@ all-reduce per step (weak scaling).  Prints ONE JSON line on rank 0.
 `value`     device-timed (CUDA events per step, L2 flushed between steps), batches already resident in HBM.
 `e2e`       the same metric through the public API with HOST (pinned) batch buffers: H2D copy of the batch and a
             D2H read of the loss inside every timed step.
+            `e2e_loss_read_one_step_late` (N = 1): the same loop with every step's loss copied D2H asynchronously and read one
+            step later - shows how much of the value / e2e gap is the per-step synchronisation; never replaces `e2e`.
 `roofline`  the dominant kernel family (catalog scoring GEMMs), timed live in isolation with CUDA events.
 `cpu_baseline` the reference's own CPU implementation of the path timed on this box's host cores on a bounded sample
             of the same workload: the UNMODIFIED reference sources (oracle/_ref, a byte-identical copy of
