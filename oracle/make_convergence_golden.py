@@ -37,12 +37,13 @@ RUNS = {
     'srgnn_cfg0': ('SRGNN', 256, 1, 32, 0.1, 3, 8),            # BASELINE.json configs[0]
     'niser': ('NISER', 64, 2, 128, 0.5, 2, 12),                # main_niser.py defaults
     'msgifsr_k1': ('MSGIFSR', 96, 1, 512, 0.1, 3, 12),         # start.sh: --order 1 --num-layers 1, cfg1's d
+    'msgifsr_k3': ('MSGIFSR', 96, 1, 512, 0.1, 3, 12, 3),      # the argparse default order (main_msgifsr.py:84), no --extra / --fusion
 }
 
 
-def loaders(R, name, bs, train_sessions, test_sessions):
+def loaders(R, name, bs, train_sessions, test_sessions, order=1):
     if name == 'MSGIFSR':
-        fn = R.collate.collate_fn_factory_ccs((R.collate.seq_to_ccs_graph,), order=1)
+        fn = R.collate.collate_fn_factory_ccs((R.collate.seq_to_ccs_graph,), order=order)
     else:
         fn = R.collate.collate_fn_factory(R.collate.seq_to_session_graph)
     out = []
@@ -66,10 +67,10 @@ def reseed_init(m, seed):
         m.beta.data = th.tensor(1.0)
 
 
-def one_run(R, name, d, L, bs, p, patience, epochs, seed, threads, train_l, test_l, V):
+def one_run(R, name, d, L, bs, p, patience, epochs, seed, threads, train_l, test_l, V, order=1):
     th.set_num_threads(threads)
     if name == 'MSGIFSR':
-        m = R.MSGIFSR(V, 'sample', d, L, dropout=p, order=1, extra=False, fusion=False)
+        m = R.MSGIFSR(V, 'sample', d, L, dropout=p, order=order, extra=False, fusion=False)
     else:
         m = getattr(R, name)(V, d, L, p)
     reseed_init(m, 123)                 # every run starts from the same weights
@@ -105,18 +106,19 @@ def main():
     path = GOLD / 'convergence_golden.json'
     out = json.loads(path.read_text()) if path.exists() else {}
     for key in names:
-        name, d, L, bs, p, patience, epochs = RUNS[key]
-        train_l, test_l = loaders(R, name, bs, train_s, test_s)
+        name, d, L, bs, p, patience, epochs = RUNS[key][:7]
+        order = RUNS[key][7] if len(RUNS[key]) > 7 else 1
+        train_l, test_l = loaders(R, name, bs, train_s, test_s, order)
         init = None
         runs = {}
         for tag, pp, seed, thr in (('p0', 0.0, 123, 4), ('p0_t1', 0.0, 123, 1), ('stock_s123', p, 123, 4),
                                    ('stock_s124', p, 124, 4), ('stock_s125', p, 125, 4)):
-            runs[tag] = one_run(R, name, d, L, bs, pp, patience, epochs, seed, thr, train_l, test_l, V)
+            runs[tag] = one_run(R, name, d, L, bs, pp, patience, epochs, seed, thr, train_l, test_l, V, order)
             e = runs[tag]['evals']
             print(f'{key:12s} {tag:11s} epochs {len(e) - 1:2d}  best MRR {runs[tag]["best_mrr"]:.5f} HR {runs[tag]["best_hit"]:.5f}  '
                   f'({runs[tag]["seconds"]} s)', flush=True)
-            out[key] = dict(model=name, V=V, d=d, layers=L, batch_size=bs, stock_dropout=p, patience=patience, max_epochs=epochs,
-                            lr=1e-3, weight_decay=1e-4, init_seed=123, runs=runs,
+            out[key] = dict(model=name, V=V, d=d, layers=L, order=order, batch_size=bs, stock_dropout=p, patience=patience,
+                            max_epochs=epochs, lr=1e-3, weight_decay=1e-4, init_seed=123, runs=runs,
                             note='evals[0] is the evaluation before epoch 0; evals[i] after epoch i-1: [MRR@20, HR@20]')
             path.write_text(json.dumps(out, indent=1))
     print('done ->', path)

@@ -27,7 +27,7 @@ def _model(pkg, c, p):
     from sessionrec_pytorch_b200.msgifsr import MSGIFSR
     from sessionrec_pytorch_b200.srgnn import NISER, SRGNN
     if c['model'] == 'MSGIFSR':
-        m = MSGIFSR(c['V'], 'sample', c['d'], c['layers'], dropout=p, order=1, extra=False, fusion=False)
+        m = MSGIFSR(c['V'], 'sample', c['d'], c['layers'], dropout=p, order=c.get('order', 1), extra=False, fusion=False)
     else:
         m = {'SRGNN': SRGNN, 'NISER': NISER}[c['model']](c['V'], c['d'], c['layers'], p)
     # oracle/make_convergence_golden.py::reseed_init: weights as a function of the seed alone
@@ -49,7 +49,7 @@ def _loaders(pkg, c):
     out = []
     for sess in (train_s, test_s):
         items, offs, labels = AugmentedDataset(sess).flat()            # SequentialSampler order (`main_msgifsr.py:156`)
-        out.append(EpochBatches(items, offs, labels, c['batch_size'], kind, 1).to(DEV))
+        out.append(EpochBatches(items, offs, labels, c['batch_size'], kind, c.get('order', 1)).to(DEV))
     train, test = out
     return train, [([b], b.labels.long()) for b in test]
 
@@ -91,7 +91,8 @@ def test_converged_metrics_match_the_reference_run_without_dropout(pkg, name):
         assert abs(rec[i][1] - ref['evals'][i][1]) <= 3e-3 and abs(rec[i][0] - ref['evals'][i][0]) <= 3e-3, (i, rec[i], ref['evals'][i])
 
 
-@pytest.mark.parametrize('name', sorted(CONV))
+# msgifsr_k3 has two stock-dropout seeds recorded (8-16 minutes of reference CPU time per run): too few for a range
+@pytest.mark.parametrize('name', sorted(k for k, c in CONV.items() if sum(t.startswith('stock_') for t in c['runs']) >= 3))
 def test_converged_hr_with_stock_dropout_inside_reference_seed_spread(pkg, name):
     c = CONV[name]
     hits = [r['best_hit'] for t, r in c['runs'].items() if t.startswith('stock_')]
