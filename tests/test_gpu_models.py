@@ -463,7 +463,7 @@ def test_native_step_graph_replay_matches_plain_launches(pkg, p, inject, whole):
                 losses.append(float(m.train_step(b)))
             res.append((m, losses, L['srk_graph_launches']() - g0, L['srk_graph_fallbacks']() - f0))
     finally:
-        L['srk_set_graph_mode'](2)                      # back to the default (replay for data-parallel steps only)
+        L['srk_set_graph_mode'](2)                      # back to the default (auto: always for data-parallel steps, measured for a single rank)
         L['srk_set_graph_whole'](2)
         L['srk_graph_inject_mismatch'](0)
     (m1, l1, n1, fb1), (m2, l2, n2, _) = res
