@@ -85,8 +85,11 @@ def test_converged_metrics_match_the_reference_run_without_dropout(pkg, name):
                       for i in range(n))
     print(f'{name}: best MRR@20 {mrr:.5f} (ref {ref["best_mrr"]:.5f}), best HR@20 {hit:.5f} (ref {ref["best_hit"]:.5f})\n{table}')
     assert len(rec) == len(ref['evals']), f'early stopping differs: {len(rec) - 1} epochs here, {len(ref["evals"]) - 1} in the reference'
-    assert abs(hit - ref['best_hit']) <= 1e-3, (hit, ref['best_hit'])
-    assert abs(mrr - ref['best_mrr']) <= 1e-3, (mrr, ref['best_mrr'])
+    # the bar (+-0.001) plus the reference's OWN floating-point spread between 1 and 4 host threads (< 1e-4 for SRGNN / NISER /
+    # MSGIFSR order 1; 2.7e-4 = one test sample at order 3)
+    t1 = c['runs'].get('p0_t1', ref)
+    assert abs(hit - ref['best_hit']) <= 1e-3 + abs(ref['best_hit'] - t1['best_hit']), (hit, ref['best_hit'], t1['best_hit'])
+    assert abs(mrr - ref['best_mrr']) <= 1e-3 + abs(ref['best_mrr'] - t1['best_mrr']), (mrr, ref['best_mrr'], t1['best_mrr'])
     for i in range(n):
         assert abs(rec[i][1] - ref['evals'][i][1]) <= 3e-3 and abs(rec[i][0] - ref['evals'][i][0]) <= 3e-3, (i, rec[i], ref['evals'][i])
 
