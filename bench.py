@@ -323,7 +323,9 @@ def roofline_probe(cfg, device, pk):
                 traffic=traffic, traffic_source=traffic_src, ms_for_the_head=round(ms, 4), ms_per_kernel=per_kernel,
                 algorithmic_flops=flops,
                 note='algorithmic FLOPs 6*B*V*d (Z = s E^T, dS = dZ E, dE = dZ^T s) counted once; the 3 passes of the hi/lo '
-                     'split and the logit recomputation in the backward are the kernels\' own cost',
+                     'split and the logit recomputation in the backward are the kernels\' own cost.  Timed here (and captured by '
+                     'ncu) is the public srk_flash_ce_bwd, which writes one partial table gradient per 128-session tile; the '
+                     'native steps run the same kernel in its accumulating form (one L2-resident [V, d] buffer, no partial tables)',
                 peak_source=f"{pk['src']} bf16 burst (kernel timed alone)")
 
 
